@@ -1,0 +1,49 @@
+"""Shared helpers for the tests (golden loading, oracle construction)."""
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from cgr_mpnn_3d_b200.data import Batch, make_batch
+from oracle.gnn_oracle import OracleGNN
+
+ACTS = {"relu": F.relu, "silu": F.silu, "gelu": F.gelu}
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SMALL_CASES = ["small_relu", "small_skip", "small_silu", "small_gelu", "single_nobatch"]
+BIG_CASES = ["cfg1_d3_h300", "cfg2_d4_h400"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fa, fb, depth, hid, skip, nb, dseed, wseed, nobatch = (int(v) for v in z["meta"])
+    meta = dict(fa=fa, fb=fb, depth=depth, hidden=hid, skip=bool(skip), nb=nb, dseed=dseed,
+                wseed=wseed, nobatch=bool(nobatch), act=str(z["act"]))
+    return z, meta
+
+
+def case_batch(z, meta):
+    if "x" in z.files:
+        t = lambda k: torch.from_numpy(z[k])
+        batch = None if meta["nobatch"] else t("batch")
+        ptr = None if meta["nobatch"] else t("ptr")
+        return Batch(t("x"), t("edge_index"), t("edge_attr"), batch, ptr, t("y"))
+    return make_batch(meta["nb"], seed=meta["dseed"], kind="t1x", fa=meta["fa"])
+
+
+def case_state_dict(z):
+    return {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+
+
+def build_oracle(meta, state=None, dtype=torch.float32):
+    torch.manual_seed(meta["wseed"])
+    m = OracleGNN(meta["fa"], meta["fb"], depth=meta["depth"], hidden_sizes=[meta["hidden"]] * meta["depth"],
+                  dropout_ps=[0.0] * meta["depth"], activation_fn=ACTS[meta["act"]],
+                  use_learnable_skip=meta["skip"])
+    if state is not None:
+        m.load_state_dict(state)
+    elif meta["skip"]:
+        with torch.no_grad():
+            for l, p in enumerate(m.skip_weights):
+                p.fill_(1.0 - 0.15 * l + 0.05 * (l % 2))
+    return m.to(dtype)
