@@ -1,0 +1,131 @@
+"""ctypes binding of ``libcgr_b200.so`` (the C ABI declared in ``include/cgr_b200.h``).
+
+The library is loaded lazily at module scope so that ``torch.save(model)`` never has to pickle a
+handle (reference ``cgr_mpnn_3D/training/trainer.py:208`` pickles the whole module).  There is no
+fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcgr_b200.so")
+
+ENGINE_SIMT = 0
+ENGINE_TC = 1
+ACT_IDS = {"relu": 0, "silu": 1, "gelu": 2}
+
+c_float_p = C.POINTER(C.c_float)
+c_void_pp = C.POINTER(C.c_void_p)
+
+
+class CgrParams(C.Structure):
+    _fields_ = [
+        ("fa", C.c_int32), ("fb", C.c_int32), ("hidden", C.c_int32), ("depth", C.c_int32),
+        ("act", C.c_int32), ("use_skip", C.c_int32),
+        ("w_init", C.c_void_p), ("b_init", C.c_void_p),
+        ("w_conv", c_void_pp), ("b_conv", c_void_pp), ("skip", c_void_pp),
+        ("w_e2n", C.c_void_p), ("b_e2n", C.c_void_p), ("w_ffn", C.c_void_p), ("b_ffn", C.c_void_p),
+        ("host_dropout_p", c_float_p),
+    ]
+
+
+class CgrGrads(C.Structure):
+    _fields_ = [
+        ("w_init", C.c_void_p), ("b_init", C.c_void_p),
+        ("w_conv", c_void_pp), ("b_conv", c_void_pp), ("skip", c_void_pp),
+        ("w_e2n", C.c_void_p), ("b_e2n", C.c_void_p), ("w_ffn", C.c_void_p), ("b_ffn", C.c_void_p),
+    ]
+
+
+class CgrGraph(C.Structure):
+    _fields_ = [
+        ("n_atoms", C.c_int64), ("n_bonds", C.c_int64), ("n_rxn", C.c_int64),
+        ("x", C.c_void_p), ("edge_attr", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p),
+        ("in_ptr", C.c_void_p), ("in_idx", C.c_void_p), ("atom_ptr", C.c_void_p),
+    ]
+
+
+class CgrSaved(C.Structure):
+    _fields_ = [
+        ("h_all", C.c_void_p), ("m_all", C.c_void_p), ("z_all", C.c_void_p), ("s", C.c_void_p),
+        ("hv", C.c_void_p), ("zv", C.c_void_p), ("pooled", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/cgr_b200.h declares
+_V = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_SZ = C.c_size_t
+PROTOTYPES = {
+    "cgr_version": (C.c_int, []),
+    "cgr_last_error_string": (C.c_char_p, []),
+    "cgr_collate_workspace": (_SZ, [_I64]),
+    "cgr_collate_indices": (C.c_int, [_V, _V, _V, _I64, _I64, _I64, _V, _V, _V, _V, _V, _SZ, _V]),
+    "cgr_csr_workspace": (_SZ, [_I64, _I64]),
+    "cgr_csr_build": (C.c_int, [_V, _I64, _I64, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "cgr_atom_ptr_from_batch": (C.c_int, [_V, _I64, _I64, _V, _V]),
+    "cgr_edge_init_fwd": (C.c_int, [_V, _V, _V, _V, _V, _I64, _I64, _I32, _I32, _I32, _I32, _V, _V, _V, _SZ, _V]),
+    "cgr_bond_update_fwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _I32, C.c_float, C.c_uint64, C.c_uint32,
+                                      _I32, _V, _V, _V, _I64, _I64, _I32, _V]),
+    "cgr_conv_fwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I64, _I64, _I32, _V]),
+    "cgr_readout_fwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I32, _V, _V, _V, _V, _V, _I64, _I64, _I64,
+                                  _I32, _I32, _V]),
+    "cgr_forward_workspace": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph), _I32, _I32]),
+    "cgr_gnn_forward": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrGraph), _V, C.POINTER(CgrSaved), _I32,
+                                  C.c_uint64, _I32, _V, _SZ, _V]),
+    "cgr_backward_workspace": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph), _I32]),
+    "cgr_gnn_backward": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrGraph), C.POINTER(CgrSaved), _V,
+                                   C.POINTER(CgrGrads), C.c_uint64, _I32, _V, _SZ, _V]),
+    "cgr_mse_sum_fwd_bwd": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
+    "cgr_launch_count": (C.c_longlong, []),
+    "cgr_profile_enable": (C.c_int, [C.c_int]),
+    "cgr_profile_count": (C.c_int, []),
+    "cgr_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, c_float_p]),
+    "cgr_dropout_mask": (C.c_int, [C.c_uint64, C.c_uint32, C.c_float, _I64, _I32, _V, _V]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and attach prototypes.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m cgr_mpnn_3d_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for the CGR hot path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)      # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cgr_last_error_string()
+        raise RuntimeError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int:
+    """Device (or host) address of a torch tensor, or 0 for None."""
+    return 0 if t is None else t.data_ptr()
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * max(1, len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr

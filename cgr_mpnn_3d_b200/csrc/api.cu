@@ -1,0 +1,408 @@
+// C ABI of libcgr_b200: stage-level entry points and whole-network forward / backward
+// (reference cgr_mpnn_3D/models/GNN.py:76-145; backward = explicit mirror of autograd).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/cgr_b200.h"
+#include "common.cuh"
+#include "simt.cuh"
+#include "tc.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cgr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- launch counter and event-based per-stage timing -------------------------------------------
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <string>
+namespace {
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_profile{0};
+std::mutex g_prof_mu;
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+void cgr_note_launch(const char*, cudaStream_t, int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+CgrRange::CgrRange(const char* name_, cudaStream_t st_) : name(name_), st(st_), active(g_profile.load() != 0) {
+  if (!active) return;
+  ProfRec r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { active = false; return; }
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+CgrRange::~CgrRange() {
+  if (!active) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (size_t i = g_prof.size(); i-- > 0;)
+    if (g_prof[i].name == name) { cudaEventRecord(g_prof[i].b, st); break; }
+}
+
+extern "C" long long cgr_launch_count(void) { return g_launches.load(); }
+extern "C" int cgr_profile_enable(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_profile.store(enable ? 1 : 0);
+  return CGR_OK;
+}
+extern "C" int cgr_profile_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return (int)g_prof.size();
+}
+extern "C" int cgr_profile_get(int i, char* name_out, int name_cap, float* ms_out) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  CGR_CHECK_ARG(i >= 0 && i < (int)g_prof.size() && name_out && name_cap > 0 && ms_out, "cgr_profile_get: bad index");
+  CGR_CUDA(cudaEventSynchronize(g_prof[i].b));
+  CGR_CUDA(cudaEventElapsedTime(ms_out, g_prof[i].a, g_prof[i].b));
+  snprintf(name_out, name_cap, "%s", g_prof[i].name.c_str());
+  return CGR_OK;
+}
+
+extern "C" int cgr_version(void) { return CGR_B200_VERSION; }
+extern "C" const char* cgr_last_error_string(void) { return g_err; }
+
+namespace {
+
+struct Carver {   // bump allocator over a caller-provided workspace, 256-byte aligned pieces
+  char* base;
+  size_t cap, off = 0;
+  bool ok = true;
+  Carver(void* p, size_t n) : base((char*)p), cap(n) {}
+  float* floats(size_t n) {
+    size_t bytes = cgr_align_up(n * sizeof(float), 256);
+    if (off + bytes > cap) { ok = false; return nullptr; }
+    float* r = (float*)(base + off);
+    off += bytes;
+    return r;
+  }
+};
+size_t fbytes(size_t n) { return cgr_align_up(n * sizeof(float), 256); }
+
+int check_params(const cgr_params_t* p) {
+  CGR_CHECK_ARG(p, "null params");
+  CGR_CHECK_ARG(p->hidden > 0 && p->depth > 0 && p->fa > 0 && p->fb >= 0, "bad architecture sizes");
+  CGR_CHECK_ARG(p->act >= 0 && p->act <= 2, "unknown activation id %d", p->act);
+  CGR_CHECK_ARG(p->w_init && p->b_init && p->w_conv && p->b_conv && p->w_e2n && p->b_e2n && p->w_ffn && p->b_ffn,
+                "null parameter pointer");
+  CGR_CHECK_ARG(!p->use_skip || p->skip, "use_skip set but skip pointers missing");
+  return CGR_OK;
+}
+
+int check_graph(const cgr_graph_t* g) {
+  CGR_CHECK_ARG(g, "null graph");
+  CGR_CHECK_ARG(g->n_atoms > 0 && g->n_bonds > 0 && g->n_rxn > 0, "empty batch");
+  CGR_CHECK_ARG((g->n_bonds & 1) == 0, "odd number of directed bonds (reference GNN.py:136-138 needs pairs)");
+  CGR_CHECK_ARG(g->x && g->edge_attr && g->src && g->dst && g->in_ptr && g->in_idx && g->atom_ptr,
+                "null graph pointer");
+  return CGR_OK;
+}
+
+size_t max_splitk_floats(const cgr_params_t* p, const cgr_graph_t* g) {
+  const int64_t H = p->hidden, E = g->n_bonds, N = g->n_atoms;
+  size_t m = 0;
+  auto upd = [&](int64_t M_, int64_t N_, int64_t K_) {
+    int s = simt_splitk_choose(M_, N_, K_);
+    if (s > 1) { size_t f = (size_t)s * M_ * N_; if (f > m) m = f; }
+  };
+  upd(H, H, E);
+  upd(H, p->fa, N);
+  upd(H, H, N);
+  upd(H, p->fb > 0 ? p->fb : 1, E);
+  return m;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points
+// ------------------------------------------------------------------------------------------------
+
+extern "C" int cgr_edge_init_fwd(const float* x, const float* edge_attr, const int32_t* src, const float* w_init,
+                                 const float* b_init, int64_t n_atoms, int64_t n_bonds, int32_t fa, int32_t fb,
+                                 int32_t hidden, int32_t act, float* h0, float* z0, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  CGR_CHECK_ARG(x && src && w_init && b_init && h0, "cgr_edge_init_fwd: null pointer");
+  CGR_CHECK_ARG(fb == 0 || edge_attr, "cgr_edge_init_fwd: edge_attr is null but fb > 0");
+  CGR_CHECK_ARG(workspace_bytes >= fbytes((size_t)n_atoms * hidden), "cgr_edge_init_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* P = (float*)workspace;
+  // P = x . W_x^T with W_x = w_init[:, :fa]; per-atom projection, algebraically equal to the
+  // reference's [x[src] || ea] GEMM (GNN.py:86) without materialising the [E, Fa+Fb] concat.
+  GemmEpilogue none;
+  none.tag = "gemm_atom_proj";
+  int rc = simt_gemm(x, fa, true, w_init, fa + fb, true, P, hidden, n_atoms, hidden, fa, none, 1, nullptr, st);
+  if (rc) return rc;
+  return simt_edge_init(P, edge_attr, src, w_init, b_init, n_bonds, fa, fb, hidden, act, h0, z0, st);
+}
+
+extern "C" int cgr_bond_update_fwd(const float* h_in, const float* h0, const int32_t* in_ptr,
+                                   const int32_t* in_idx, const int32_t* src, const float* w, const float* b,
+                                   const float* skip, int32_t act, float dropout_p, uint64_t seed, uint32_t layer,
+                                   int32_t training, float* h_out, float* m_out, float* z_out, int64_t n_bonds,
+                                   int64_t n_atoms, int32_t hidden, void* stream) {
+  (void)n_atoms;
+  CGR_CHECK_ARG(h_in && h0 && in_ptr && in_idx && src && w && b && h_out && m_out, "cgr_bond_update_fwd: null pointer");
+  CGR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "cgr_bond_update_fwd: dropout_p out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  GatherPost np;
+  int rc = simt_gather_bonds(h_in, src, in_ptr, in_idx, 0, m_out, n_bonds, hidden, np, st);   // GNN.py:134-141
+  if (rc) return rc;
+  GemmEpilogue e;
+  e.bias = b;
+  e.res = h0; e.ldr = hidden; e.res_scale = skip;          // GNN.py:94-97
+  e.preact = z_out;
+  e.act = act;                                             // GNN.py:100-102
+  e.dropout_p = (training && dropout_p > 0.f) ? dropout_p : 0.f;
+  e.seed = seed; e.layer = layer;
+  e.tag = "gemm_bond_update";
+  return simt_gemm(m_out, hidden, true, w, hidden, true, h_out, hidden, n_bonds, hidden, hidden, e, 1, nullptr, st);
+}
+
+extern "C" int cgr_conv_fwd(const float* h, const int32_t* in_ptr, const int32_t* in_idx, const int32_t* src,
+                            const float* w, const float* b, float* a_out, float* y_out, float* m_ws,
+                            int64_t n_bonds, int64_t n_atoms, int32_t hidden, void* stream) {
+  CGR_CHECK_ARG(h && in_ptr && in_idx && src && w && b && a_out && y_out && m_ws, "cgr_conv_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = simt_atom_sum(h, in_ptr, in_idx, 0, a_out, n_atoms, hidden, st);        // GNN.py:134
+  if (rc) return rc;
+  GatherPost np;
+  rc = simt_gather_bonds(h, src, in_ptr, in_idx, 0, m_ws, n_bonds, hidden, np, st); // GNN.py:136-141
+  if (rc) return rc;
+  GemmEpilogue e;
+  e.bias = b;
+  return simt_gemm(m_ws, hidden, true, w, hidden, true, y_out, hidden, n_bonds, hidden, hidden, e, 1, nullptr, st);
+}
+
+extern "C" int cgr_readout_fwd(const float* h, const float* x, const int32_t* in_ptr, const int32_t* in_idx,
+                               const int32_t* atom_ptr, const float* w_e2n, const float* b_e2n, const float* w_ffn,
+                               const float* b_ffn, int32_t act, float* out, float* s_out, float* hv_out,
+                               float* zv_out, float* pooled_out, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                               int32_t fa, int32_t hidden, void* stream) {
+  (void)n_bonds;
+  CGR_CHECK_ARG(h && x && in_ptr && in_idx && atom_ptr && w_e2n && b_e2n && w_ffn && b_ffn && out && s_out &&
+                    hv_out && pooled_out, "cgr_readout_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = simt_atom_sum(h, in_ptr, in_idx, 0, s_out, n_atoms, hidden, st);                  // GNN.py:105
+  if (rc) return rc;
+  // W_o [x || s] = x W_ox^T + s W_os^T  (GNN.py:106-107 without the concat)
+  GemmEpilogue e1;
+  e1.tag = "gemm_readout_x";
+  e1.bias = b_e2n;
+  rc = simt_gemm(x, fa, true, w_e2n, fa + hidden, true, hv_out, hidden, n_atoms, hidden, fa, e1, 1, nullptr, st);
+  if (rc) return rc;
+  GemmEpilogue e2;
+  e2.res = hv_out; e2.ldr = hidden;
+  e2.preact = zv_out;
+  e2.act = act;
+  e2.tag = "gemm_readout_s";
+  rc = simt_gemm(s_out, hidden, true, w_e2n + fa, fa + hidden, true, hv_out, hidden, n_atoms, hidden, hidden, e2, 1,
+                 nullptr, st);
+  if (rc) return rc;
+  return simt_pool_ffn(hv_out, atom_ptr, w_ffn, b_ffn, pooled_out, out, n_rxn, hidden, st);  // GNN.py:110
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole network
+// ------------------------------------------------------------------------------------------------
+
+extern "C" size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t training,
+                                        int32_t engine) {
+  if (!p || !g) return 0;
+  if (engine == CGR_ENGINE_TC) return tc_forward_workspace(p, g, training);
+  const size_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
+  size_t b = fbytes(N * H);
+  if (!training) b += 4 * fbytes(E * H) + 2 * fbytes(N * H) + fbytes(B * H);
+  return b + 256;
+}
+
+extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved,
+                               int32_t training, uint64_t seed, int32_t engine, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_graph(g);
+  if (rc) return rc;
+  CGR_CHECK_ARG(out, "cgr_gnn_forward: null output");
+  CGR_CHECK_ARG(!training || saved, "cgr_gnn_forward: training forward needs a cgr_saved_t");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_forward_workspace(p, g, training, engine),
+                "cgr_gnn_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                cgr_forward_workspace(p, g, training, engine));
+  if (engine == CGR_ENGINE_TC)
+    return tc_gnn_forward(p, g, out, saved, training, seed, workspace, workspace_bytes, (cudaStream_t)stream);
+  CGR_CHECK_ARG(engine == CGR_ENGINE_SIMT, "unknown engine %d", engine);
+
+  const int64_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
+  const int d = p->depth;
+  const size_t EH = (size_t)E * H;
+  Carver ws(workspace, workspace_bytes);
+  float* P = ws.floats(N * H);
+  float *h0, *hbuf[2] = {nullptr, nullptr}, *mbuf = nullptr, *s, *hv, *pooled;
+  if (saved) {
+    CGR_CHECK_ARG(saved->h_all && saved->m_all && saved->s && saved->hv && saved->pooled,
+                  "cgr_gnn_forward: saved buffers missing");
+    CGR_CHECK_ARG(p->act == CGR_ACT_RELU || (saved->z_all && saved->zv),
+                  "cgr_gnn_forward: z_all/zv required for silu/gelu");
+    h0 = saved->h_all; s = saved->s; hv = saved->hv; pooled = saved->pooled;
+  } else {
+    h0 = ws.floats(EH); hbuf[0] = ws.floats(EH); hbuf[1] = ws.floats(EH); mbuf = ws.floats(EH);
+    s = ws.floats(N * H); hv = ws.floats(N * H); pooled = ws.floats(B * H);
+  }
+  if (!ws.ok) { cgr_set_error("cgr_gnn_forward: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  float* z_all = saved ? saved->z_all : nullptr;
+
+  rc = cgr_edge_init_fwd(g->x, g->edge_attr, g->src, p->w_init, p->b_init, N, E, p->fa, p->fb, p->hidden, p->act,
+                         h0, z_all, P, fbytes(N * H), stream);
+  if (rc) return rc;
+  const float* h = h0;
+  for (int l = 0; l < d; ++l) {
+    float* h_out = saved ? saved->h_all + (size_t)(l + 1) * EH : hbuf[l & 1];
+    float* m_out = saved ? saved->m_all + (size_t)l * EH : mbuf;
+    float* z_out = z_all ? z_all + (size_t)(l + 1) * EH : nullptr;
+    const float pdrop = p->host_dropout_p ? p->host_dropout_p[l] : 0.f;
+    rc = cgr_bond_update_fwd(h, h0, g->in_ptr, g->in_idx, g->src, p->w_conv[l], p->b_conv[l],
+                             p->use_skip ? p->skip[l] : nullptr, p->act, pdrop, seed, (uint32_t)l, training, h_out,
+                             m_out, z_out, E, N, p->hidden, stream);
+    if (rc) return rc;
+    h = h_out;
+  }
+  return cgr_readout_fwd(h, g->x, g->in_ptr, g->in_idx, g->atom_ptr, p->w_e2n, p->b_e2n, p->w_ffn, p->b_ffn, p->act,
+                         out, s, hv, saved ? saved->zv : nullptr, pooled, N, E, B, p->fa, p->hidden, stream);
+}
+
+extern "C" size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t engine) {
+  if (!p || !g) return 0;
+  (void)engine;
+  const size_t H = p->hidden, E = g->n_bonds, N = g->n_atoms;
+  return 2 * fbytes(N * H) + 3 * fbytes(E * H) + fbytes(max_splitk_floats(p, g)) +
+         fbytes(simt_colsum_workspace(E > N ? E : N, (int)H)) + 256;
+}
+
+extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved,
+                                const float* grad_out, cgr_grads_t* grads, uint64_t seed, int32_t engine,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_graph(g);
+  if (rc) return rc;
+  (void)engine;   // the backward currently always runs on the SIMT fp32 engine
+  CGR_CHECK_ARG(saved && grad_out && grads, "cgr_gnn_backward: null pointer");
+  CGR_CHECK_ARG(saved->h_all && saved->m_all && saved->s && saved->hv && saved->pooled,
+                "cgr_gnn_backward: saved buffers missing");
+  CGR_CHECK_ARG(p->act == CGR_ACT_RELU || (saved->z_all && saved->zv), "cgr_gnn_backward: z_all/zv required");
+  CGR_CHECK_ARG(grads->w_init && grads->b_init && grads->w_conv && grads->b_conv && grads->w_e2n && grads->b_e2n &&
+                    grads->w_ffn && grads->b_ffn && (!p->use_skip || grads->skip), "cgr_gnn_backward: null grad");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_backward_workspace(p, g, engine), "cgr_gnn_backward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
+  const int d = p->depth, fa = p->fa, fb = p->fb;
+  const size_t EH = (size_t)E * H;
+  Carver ws(workspace, workspace_bytes);
+  float* dzv = ws.floats(N * H);
+  float* ds = ws.floats(N * H);
+  float* dz = ws.floats(EH);
+  float* dm = ws.floats(EH);
+  float* dh0 = ws.floats(EH);
+  float* partial = ws.floats(max_splitk_floats(p, g));
+  float* csws = ws.floats(simt_colsum_workspace(E > N ? E : N, (int)H));
+  if (!ws.ok) { cgr_set_error("cgr_gnn_backward: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  GemmEpilogue none;
+  const float* h0 = saved->h_all;
+
+  // ---- readout (GNN.py:105-110) ----
+  rc = simt_ffn_grads(grad_out, saved->pooled, grads->w_ffn, grads->b_ffn, B, (int)H, st);
+  if (rc) return rc;
+  rc = simt_readout_dz(grad_out, g->atom_ptr, p->w_ffn, saved->hv, saved->zv, p->act, dzv, B, (int)H, st);
+  if (rc) return rc;
+  rc = simt_colsum(dzv, N, (int)H, grads->b_e2n, nullptr, nullptr, nullptr, nullptr, true, csws, st);
+  if (rc) return rc;
+  // dW_o[:, :fa] = dzv^T x ; dW_o[:, fa:] = dzv^T s
+  rc = simt_gemm(dzv, H, false, g->x, fa, false, grads->w_e2n, fa + H, H, fa, N, none,
+                 simt_splitk_choose(H, fa, N), partial, st);
+  if (rc) return rc;
+  rc = simt_gemm(dzv, H, false, saved->s, H, false, grads->w_e2n + fa, fa + H, H, H, N, none,
+                 simt_splitk_choose(H, H, N), partial, st);
+  if (rc) return rc;
+  // ds = dzv . W_os
+  rc = simt_gemm(dzv, H, true, p->w_e2n + fa, fa + H, false, ds, H, N, H, H, none, 1, nullptr, st);
+  if (rc) return rc;
+
+  // ---- message passing layers, last to first ----
+  auto post_for_layer = [&](int l) {   // derivative of layer l's activation / dropout
+    GatherPost gp;
+    gp.mode = 1;
+    gp.act = p->act;
+    gp.h_next = saved->h_all + (size_t)(l + 1) * EH;
+    gp.z = saved->z_all ? saved->z_all + (size_t)(l + 1) * EH : nullptr;
+    gp.dropout_p = p->host_dropout_p ? p->host_dropout_p[l] : 0.f;
+    gp.seed = seed;
+    gp.layer = (uint32_t)l;
+    return gp;
+  };
+  rc = simt_expand_dst(ds, g->dst, dz, E, (int)H, post_for_layer(d - 1), st);   // dh_d[e] = ds[dst e]
+  if (rc) return rc;
+  for (int l = d - 1; l >= 0; --l) {
+    const float* skip = p->use_skip ? p->skip[l] : nullptr;
+    // db_l, dskip_l, dh0 += skip_l * dz_l
+    rc = simt_colsum(dz, E, (int)H, grads->b_conv[l], p->use_skip ? h0 : nullptr,
+                     p->use_skip ? grads->skip[l] : nullptr, dh0, skip, l == d - 1, csws, st);
+    if (rc) return rc;
+    // dW_l = dz^T m_l
+    rc = simt_gemm(dz, H, false, saved->m_all + (size_t)l * EH, H, false, grads->w_conv[l], H, H, H, E, none,
+                   simt_splitk_choose(H, H, E), partial, st);
+    if (rc) return rc;
+    // dm = dz . W_l
+    rc = simt_gemm(dz, H, true, p->w_conv[l], H, false, dm, H, E, H, H, none, 1, nullptr, st);
+    if (rc) return rc;
+    // dh_l[k] = sum_{j in in(dst k)} dm[j^1] - dm[k^1]
+    GatherPost gp;
+    if (l > 0) {
+      gp = post_for_layer(l - 1);
+    } else {                      // h_0 feeds layer 0 and every skip: dz0 = (dh_0 + dh0) * act'(z_init)
+      gp.mode = 2;
+      gp.add = dh0;
+      gp.act = p->act;
+      gp.h_next = h0;
+      gp.z = saved->z_all;
+      gp.dropout_p = 0.f;
+    }
+    rc = simt_gather_bonds(dm, g->dst, g->in_ptr, g->in_idx, 1, dz, E, (int)H, gp, st);
+    if (rc) return rc;
+  }
+
+  // ---- edge initialisation (GNN.py:85-86) ----
+  rc = simt_colsum(dz, E, (int)H, grads->b_init, nullptr, nullptr, nullptr, nullptr, true, csws, st);
+  if (rc) return rc;
+  if (fb > 0) {
+    rc = simt_gemm(dz, H, false, g->edge_attr, fb, false, grads->w_init + fa, fa + fb, H, fb, E, none,
+                   simt_splitk_choose(H, fb, E), partial, st);
+    if (rc) return rc;
+  }
+  float* dP = ds;   // dP[v] = sum_{e: src e = v} dz0[e] = sum_{j in in(v)} dz0[j^1]
+  rc = simt_atom_sum(dz, g->in_ptr, g->in_idx, 1, dP, N, (int)H, st);
+  if (rc) return rc;
+  return simt_gemm(dP, H, false, g->x, fa, false, grads->w_init, fa + fb, H, fa, N, none,
+                   simt_splitk_choose(H, fa, N), partial, st);
+}
+
+extern "C" int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss, float* grad_pred,
+                                   void* stream) {
+  CGR_CHECK_ARG(pred && y && n_rxn >= 0, "cgr_mse_sum_fwd_bwd: bad argument");
+  return simt_mse_sum(pred, y, n_rxn, loss, grad_pred, (cudaStream_t)stream);
+}
+
+extern "C" int cgr_dropout_mask(uint64_t seed, uint32_t layer, float dropout_p, int64_t n_bonds, int32_t hidden,
+                                uint8_t* mask, void* stream) {
+  CGR_CHECK_ARG(mask && n_bonds >= 0 && hidden > 0, "cgr_dropout_mask: bad argument");
+  return simt_dropout_mask(seed, layer, dropout_p, n_bonds * hidden, mask, (cudaStream_t)stream);
+}

@@ -1,0 +1,267 @@
+// Batch collation and CSR (a2b / b2a / b2revb) construction — integer work, bit-exact.
+//
+// Replaces the host-side PyG collate the reference loaders run
+// (cgr_mpnn_3D/training/trainer.py:105-118, test.py:85-90) and derives the index arrays the
+// message passing needs from the batched edge_index (cgr_mpnn_3D/models/GNN.py:85,132-138).
+#include "common.cuh"
+#include "../../include/cgr_b200.h"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// exclusive scan of one value per thread across a 256-thread block; returns block total via *total
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total) {
+  __shared__ T warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : T(0);
+    T wi = w;
+#pragma unroll
+    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+      T t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = wi - w;  // exclusive warp offsets
+    if (lane == SCAN_THREADS / 32 - 1) *total = wi;
+  }
+  __syncthreads();
+  T res = warp_sums[warp] + incl - v;
+  __syncthreads();
+  return res;
+}
+
+// phase A: per-tile totals
+template <typename TIn, typename TOut>
+__global__ void scan_tile_sums(const TIn* __restrict__ in, int64_t n, TOut* __restrict__ tile_sums) {
+  __shared__ TOut total;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  TOut s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < n) s += (TOut)in[base + i];
+  block_exclusive_scan<TOut>(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// phase B: one block turns tile totals into exclusive tile offsets (any count, carried chunks)
+template <typename TOut>
+__global__ void scan_tile_offsets(TOut* __restrict__ tile_sums, int64_t n_tiles) {
+  __shared__ TOut total;
+  __shared__ TOut carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+    const int64_t i = base + threadIdx.x;
+    TOut v = i < n_tiles ? tile_sums[i] : TOut(0);
+    TOut ex = block_exclusive_scan<TOut>(v, &total);
+    TOut carry = carry_s;
+    if (i < n_tiles) tile_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+}
+
+// phase C: exclusive scan written to out[0..n], out[n] = grand total
+template <typename TIn, typename TOut>
+__global__ void scan_write(const TIn* __restrict__ in, int64_t n, const TOut* __restrict__ tile_offsets,
+                           TOut* __restrict__ out) {
+  __shared__ TOut total;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  TOut v[SCAN_ITEMS];
+  TOut s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = base + i < n ? (TOut)in[base + i] : TOut(0);
+    s += v[i];
+  }
+  TOut ex = block_exclusive_scan<TOut>(s, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = ex;
+    ex += v[i];
+    if (base + i == n - 1) out[n] = ex;
+  }
+  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+template <typename TIn, typename TOut>
+int exclusive_scan(const TIn* in, int64_t n, TOut* out, TOut* tile_ws, cudaStream_t st) {
+  const int64_t n_tiles = n > 0 ? cgr_ceil_div(n, SCAN_TILE) : 1;
+  scan_tile_sums<TIn, TOut><<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(in, n, tile_ws);
+  scan_tile_offsets<TOut><<<1, SCAN_THREADS, 0, st>>>(tile_ws, n_tiles);
+  scan_write<TIn, TOut><<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(in, n, tile_ws, out);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+// largest g with ptr[g] <= i  (ptr non-decreasing, ptr[0] == 0, ptr[nb] == total > i)
+__device__ __forceinline__ int64_t segment_of(const int64_t* __restrict__ ptr, int64_t nb, int64_t i) {
+  int64_t lo = 0, hi = nb;  // invariant: ptr[lo] <= i < ptr[hi]
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void collate_edges_kernel(const int64_t* __restrict__ local_ei, const int64_t* __restrict__ ptr,
+                                     const int64_t* __restrict__ edge_ptr, int64_t nb, int64_t ne,
+                                     int64_t* __restrict__ edge_index) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int64_t off = ptr[segment_of(edge_ptr, nb, e)];
+  edge_index[e] = local_ei[e] + off;
+  edge_index[ne + e] = local_ei[ne + e] + off;
+}
+
+__global__ void collate_batch_kernel(const int64_t* __restrict__ ptr, int64_t nb, int64_t na,
+                                     int64_t* __restrict__ batch) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= na) return;
+  batch[v] = segment_of(ptr, nb, v);
+}
+
+// ---- CSR -------------------------------------------------------------------------------------
+
+__global__ void csr_count_kernel(const int64_t* __restrict__ ei, int64_t ne, int64_t na,
+                                 int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                 int32_t* __restrict__ deg, int32_t* __restrict__ status) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int64_t s = ei[e], d = ei[ne + e];
+  int flag = 0;
+  if (s < 0 || s >= na || d < 0 || d >= na) flag |= 2;
+  const int64_t r = e ^ 1;                       // b2revb: reference GNN.py:136-138
+  if (r >= ne || ei[r] != d || ei[ne + r] != s) flag |= 1;
+  src[e] = (int32_t)s;
+  dst[e] = (int32_t)d;
+  if (!(flag & 2)) atomicAdd(&deg[d], 1);
+  if (flag) atomicOr(status, flag);
+}
+
+__global__ void csr_fill_kernel(const int32_t* __restrict__ dst, int64_t ne, int64_t na,
+                                const int32_t* __restrict__ in_ptr, int32_t* __restrict__ cursor,
+                                int32_t* __restrict__ in_idx) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int32_t d = dst[e];
+  if (d < 0 || d >= na) return;
+  const int32_t pos = in_ptr[d] + atomicAdd(&cursor[d], 1);
+  in_idx[pos] = (int32_t)e;
+}
+
+// ascending bond id inside each atom's group == the order CPU scatter_add_ accumulates in
+__global__ void csr_sort_kernel(const int32_t* __restrict__ in_ptr, int64_t na, int32_t* __restrict__ in_idx,
+                                int32_t* __restrict__ status) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= na) return;
+  const int32_t b = in_ptr[v], e = in_ptr[v + 1];
+  if (e == b) atomicOr(status, 4);
+  for (int32_t i = b + 1; i < e; ++i) {
+    const int32_t key = in_idx[i];
+    int32_t j = i - 1;
+    while (j >= b && in_idx[j] > key) {
+      in_idx[j + 1] = in_idx[j];
+      --j;
+    }
+    in_idx[j + 1] = key;
+  }
+}
+
+__global__ void atom_ptr_kernel(const int64_t* __restrict__ batch, int64_t na, int64_t nb,
+                                int32_t* __restrict__ atom_ptr) {
+  // atom_ptr[g] = first v with batch[v] >= g; batch sorted ascending (PyG collate)
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > na) return;
+  const int64_t cur = v < na ? batch[v] : nb;
+  const int64_t prev = v > 0 ? batch[v - 1] : -1;
+  for (int64_t g = prev + 1; g <= cur && g <= nb; ++g) atom_ptr[g] = (int32_t)v;
+}
+
+}  // namespace
+
+extern "C" size_t cgr_collate_workspace(int64_t n_rxn) {
+  return (size_t)(cgr_ceil_div(n_rxn > 0 ? n_rxn : 1, SCAN_TILE) + 1) * sizeof(int64_t);
+}
+
+extern "C" int cgr_collate_indices(const int64_t* n_nodes, const int64_t* n_edges,
+                                   const int64_t* local_edge_index, int64_t n_rxn, int64_t n_bonds,
+                                   int64_t n_atoms, int64_t* edge_index, int64_t* batch, int64_t* ptr,
+                                   int64_t* edge_ptr, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  CGR_CHECK_ARG(n_rxn >= 0 && n_bonds >= 0 && n_atoms >= 0, "cgr_collate_indices: negative size");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_collate_workspace(n_rxn), "cgr_collate_indices: workspace too small");
+  CGR_CHECK_ARG(ptr && edge_ptr && workspace, "cgr_collate_indices: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* tile_ws = (int64_t*)workspace;
+  int rc = exclusive_scan<int64_t, int64_t>(n_nodes, n_rxn, ptr, tile_ws, st);
+  if (rc) return rc;
+  rc = exclusive_scan<int64_t, int64_t>(n_edges, n_rxn, edge_ptr, tile_ws, st);
+  if (rc) return rc;
+  if (n_bonds > 0) {
+    collate_edges_kernel<<<(unsigned)cgr_ceil_div(n_bonds, 256), 256, 0, st>>>(
+        local_edge_index, ptr, edge_ptr, n_rxn, n_bonds, edge_index);
+  }
+  if (n_atoms > 0) {
+    collate_batch_kernel<<<(unsigned)cgr_ceil_div(n_atoms, 256), 256, 0, st>>>(ptr, n_rxn, n_atoms, batch);
+  }
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+extern "C" size_t cgr_csr_workspace(int64_t n_atoms, int64_t n_bonds) {
+  (void)n_bonds;
+  const size_t na = (size_t)(n_atoms > 0 ? n_atoms : 1);
+  return cgr_align_up(2 * na * sizeof(int32_t), 256) +
+         (size_t)(cgr_ceil_div((int64_t)na, SCAN_TILE) + 1) * sizeof(int32_t);
+}
+
+extern "C" int cgr_csr_build(const int64_t* edge_index, int64_t n_bonds, int64_t n_atoms, int32_t* src,
+                             int32_t* dst, int32_t* in_ptr, int32_t* in_idx, int32_t* status,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  CGR_CHECK_ARG(n_bonds >= 0 && n_atoms >= 0, "cgr_csr_build: negative size");
+  CGR_CHECK_ARG(n_bonds < (1ll << 31) && n_atoms < (1ll << 31), "cgr_csr_build: sizes exceed int32 index range");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_csr_workspace(n_atoms, n_bonds), "cgr_csr_build: workspace too small");
+  CGR_CHECK_ARG(src && dst && in_ptr && in_idx && status && workspace, "cgr_csr_build: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t na = (size_t)(n_atoms > 0 ? n_atoms : 1);
+  int32_t* deg = (int32_t*)workspace;
+  int32_t* cursor = deg + na;
+  int32_t* tile_ws = (int32_t*)((char*)workspace + cgr_align_up(2 * na * sizeof(int32_t), 256));
+  CGR_CUDA(cudaMemsetAsync(deg, 0, 2 * na * sizeof(int32_t), st));
+  CGR_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  if (n_bonds > 0)
+    csr_count_kernel<<<(unsigned)cgr_ceil_div(n_bonds, 256), 256, 0, st>>>(edge_index, n_bonds, n_atoms, src,
+                                                                           dst, deg, status);
+  int rc = exclusive_scan<int32_t, int32_t>(deg, n_atoms, in_ptr, tile_ws, st);
+  if (rc) return rc;
+  if (n_bonds > 0)
+    csr_fill_kernel<<<(unsigned)cgr_ceil_div(n_bonds, 256), 256, 0, st>>>(dst, n_bonds, n_atoms, in_ptr,
+                                                                          cursor, in_idx);
+  if (n_atoms > 0)
+    csr_sort_kernel<<<(unsigned)cgr_ceil_div(n_atoms, 128), 128, 0, st>>>(in_ptr, n_atoms, in_idx, status);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+extern "C" int cgr_atom_ptr_from_batch(const int64_t* batch, int64_t n_atoms, int64_t n_rxn,
+                                       int32_t* atom_ptr, void* stream) {
+  CGR_CHECK_ARG(n_atoms >= 0 && n_rxn >= 0 && atom_ptr, "cgr_atom_ptr_from_batch: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  atom_ptr_kernel<<<(unsigned)cgr_ceil_div(n_atoms + 1, 256), 256, 0, st>>>(batch, n_atoms, n_rxn, atom_ptr);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}

@@ -1,0 +1,200 @@
+"""torch custom ops ``cgr_b200::gnn_forward`` / ``cgr_b200::gnn_backward`` over the C ABI.
+
+The ops take the reference model's parameter tensors in state_dict order
+(``cgr_mpnn_3D/models/GNN.py:53-74``) and run the whole forward
+(``GNN.forward``, ``GNN.py:76-110``) or its explicit backward in ``libcgr_b200.so``.
+Autograd is registered explicitly (``register_autograd``); there is no composite fallback and no
+CPU kernel: calling them with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+# order of the flat parameter list passed to the ops
+#   [edge_init.weight, edge_init.bias, convs.0.lin.weight, convs.0.lin.bias, ..., edge_to_node.weight,
+#    edge_to_node.bias, ffn.weight, ffn.bias, (skip_weights.0, ...)]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _unpack(params: Sequence[Tensor], depth: int, use_skip: bool):
+    w_init, b_init = params[0], params[1]
+    w_conv = [params[2 + 2 * l] for l in range(depth)]
+    b_conv = [params[3 + 2 * l] for l in range(depth)]
+    o = 2 + 2 * depth
+    w_e2n, b_e2n, w_ffn, b_ffn = params[o], params[o + 1], params[o + 2], params[o + 3]
+    skip = [params[o + 4 + l] for l in range(depth)] if use_skip else []
+    return w_init, b_init, w_conv, b_conv, w_e2n, b_e2n, w_ffn, b_ffn, skip
+
+
+class _Ctx:
+    """Keeps ctypes arrays alive for the duration of one C call."""
+
+    def __init__(self, params: Sequence[Tensor], depth: int, act: int, use_skip: bool, fa: int, fb: int,
+                 dropout_ps: Sequence[float]):
+        w_init, b_init, w_conv, b_conv, w_e2n, b_e2n, w_ffn, b_ffn, skip = _unpack(params, depth, use_skip)
+        hidden = int(w_init.shape[0])
+        self.hidden = hidden
+        self._wc = _lib.ptr_array(w_conv)
+        self._bc = _lib.ptr_array(b_conv)
+        self._sk = _lib.ptr_array(skip) if use_skip else None
+        self._dp = (C.c_float * depth)(*[float(p) for p in dropout_ps[:depth]])
+        self.params = _lib.CgrParams(
+            fa=fa, fb=fb, hidden=hidden, depth=depth, act=act, use_skip=int(use_skip),
+            w_init=w_init.data_ptr(), b_init=b_init.data_ptr(),
+            w_conv=C.cast(self._wc, _lib.c_void_pp), b_conv=C.cast(self._bc, _lib.c_void_pp),
+            skip=C.cast(self._sk, _lib.c_void_pp) if use_skip else None,
+            w_e2n=w_e2n.data_ptr(), b_e2n=b_e2n.data_ptr(), w_ffn=w_ffn.data_ptr(), b_ffn=b_ffn.data_ptr(),
+            host_dropout_p=C.cast(self._dp, _lib.c_float_p),
+        )
+
+
+def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr) -> _lib.CgrGraph:
+    return _lib.CgrGraph(
+        n_atoms=int(x.shape[0]), n_bonds=int(src.shape[0]), n_rxn=int(atom_ptr.shape[0]) - 1,
+        x=x.data_ptr(), edge_attr=edge_attr.data_ptr(), src=src.data_ptr(), dst=dst.data_ptr(),
+        in_ptr=in_ptr.data_ptr(), in_idx=in_idx.data_ptr(), atom_ptr=atom_ptr.data_ptr(),
+    )
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("cgr_b200 ops need CUDA tensors: the CGR hot path has no CPU implementation")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+@torch.library.custom_op("cgr_b200::gnn_forward", mutates_args=())
+def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor, in_idx: Tensor,
+                atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
+                dropout_ps: Sequence[float], training: bool, seed: int, engine: int) -> List[Tensor]:
+    """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled]`` (saved tensors are empty in eval)."""
+    _require_cuda(x, edge_attr, src, *params)
+    lib = _lib.load()
+    x, edge_attr = _f32c(x), _f32c(edge_attr)
+    params = [_f32c(p) for p in params]
+    fa, fb = int(x.shape[1]), int(edge_attr.shape[1])
+    ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
+    H = ctx.hidden
+    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr)
+    n, e, b = g.n_atoms, g.n_bonds, g.n_rxn
+    f32 = dict(dtype=torch.float32, device=x.device)
+    out = torch.empty(b, **f32)
+    if training:
+        h_all = torch.empty((depth + 1, e, H), **f32)
+        m_all = torch.empty((depth, e, H), **f32)
+        need_z = act != 0
+        z_all = torch.empty((depth + 1, e, H), **f32) if need_z else torch.empty(0, **f32)
+        s = torch.empty((n, H), **f32)
+        hv = torch.empty((n, H), **f32)
+        zv = torch.empty((n, H), **f32) if need_z else torch.empty(0, **f32)
+        pooled = torch.empty((b, H), **f32)
+        saved = _lib.CgrSaved(h_all=h_all.data_ptr(), m_all=m_all.data_ptr(),
+                              z_all=z_all.data_ptr() if need_z else None, s=s.data_ptr(), hv=hv.data_ptr(),
+                              zv=zv.data_ptr() if need_z else None, pooled=pooled.data_ptr())
+        saved_p = C.byref(saved)
+    else:
+        h_all, m_all, z_all, s, hv, zv, pooled = (torch.empty(0, **f32) for _ in range(7))
+        saved_p = None
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.cgr_forward_workspace(C.byref(ctx.params), C.byref(g), int(training), engine)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.cgr_gnn_forward(C.byref(ctx.params), C.byref(g), out.data_ptr(), saved_p, int(training),
+                                       seed & 0xFFFFFFFFFFFFFFFF, engine, ws.data_ptr(), ws_bytes, _stream()),
+                   "cgr_gnn_forward")
+    return [out, h_all, m_all, z_all, s, hv, zv, pooled]
+
+
+@gnn_forward.register_fake
+def _(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
+      engine):
+    H = params[0].shape[0]
+    n, e, b = x.shape[0], src.shape[0], atom_ptr.shape[0] - 1
+    mk = lambda *s: x.new_empty(s, dtype=torch.float32)
+    if not training:
+        return [mk(b)] + [mk(0) for _ in range(7)]
+    need_z = act != 0
+    return [mk(b), mk(depth + 1, e, H), mk(depth, e, H), mk(depth + 1, e, H) if need_z else mk(0), mk(n, H),
+            mk(n, H), mk(n, H) if need_z else mk(0), mk(b, H)]
+
+
+@torch.library.custom_op("cgr_b200::gnn_backward", mutates_args=())
+def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor,
+                 in_idx: Tensor, atom_ptr: Tensor, params: Sequence[Tensor], saved: Sequence[Tensor], depth: int,
+                 act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int) -> List[Tensor]:
+    """Explicit backward: gradients of every parameter, in parameter-list order."""
+    _require_cuda(grad_out, x, *params)
+    lib = _lib.load()
+    x, edge_attr = _f32c(x), _f32c(edge_attr)
+    params = [_f32c(p) for p in params]
+    grad_out = _f32c(grad_out)
+    fa, fb = int(x.shape[1]), int(edge_attr.shape[1])
+    ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
+    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr)
+    h_all, m_all, z_all, s, hv, zv, pooled = saved
+    need_z = act != 0
+    sv = _lib.CgrSaved(h_all=h_all.data_ptr(), m_all=m_all.data_ptr(), z_all=z_all.data_ptr() if need_z else None,
+                       s=s.data_ptr(), hv=hv.data_ptr(), zv=zv.data_ptr() if need_z else None,
+                       pooled=pooled.data_ptr())
+    grads = [torch.empty_like(p) for p in params]
+    gw_init, gb_init, gw_conv, gb_conv, gw_e2n, gb_e2n, gw_ffn, gb_ffn, gskip = _unpack(grads, depth, use_skip)
+    wc, bc = _lib.ptr_array(gw_conv), _lib.ptr_array(gb_conv)
+    sk = _lib.ptr_array(gskip) if use_skip else None
+    gs = _lib.CgrGrads(w_init=gw_init.data_ptr(), b_init=gb_init.data_ptr(), w_conv=C.cast(wc, _lib.c_void_pp),
+                       b_conv=C.cast(bc, _lib.c_void_pp), skip=C.cast(sk, _lib.c_void_pp) if use_skip else None,
+                       w_e2n=gw_e2n.data_ptr(), b_e2n=gb_e2n.data_ptr(), w_ffn=gw_ffn.data_ptr(),
+                       b_ffn=gb_ffn.data_ptr())
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.cgr_backward_workspace(C.byref(ctx.params), C.byref(g), engine)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.cgr_gnn_backward(C.byref(ctx.params), C.byref(g), C.byref(sv), grad_out.data_ptr(),
+                                        C.byref(gs), seed & 0xFFFFFFFFFFFFFFFF, engine, ws.data_ptr(), ws_bytes,
+                                        _stream()), "cgr_gnn_backward")
+    return grads
+
+
+@gnn_backward.register_fake
+def _(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip, dropout_ps,
+      seed, engine):
+    return [torch.empty_like(p) for p in params]
+
+
+def _setup_context(ctx, inputs, output):
+    (x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
+     engine) = inputs
+    ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine)
+    ctx.n_params = len(params)
+    ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:])
+
+
+def _backward(ctx, grads):
+    depth, act, use_skip, dropout_ps, training, seed, engine = ctx.cfg
+    if not training:
+        raise RuntimeError("cgr_b200::gnn_forward was run with training=False; no activations were saved "
+                           "(call model.train() before a forward that needs gradients)")
+    t = ctx.saved_tensors
+    x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr = t[:7]
+    params = list(t[7:7 + ctx.n_params])
+    saved = list(t[7 + ctx.n_params:])
+    g_out = grads[0]
+    if g_out is None:
+        g_out = torch.zeros(atom_ptr.shape[0] - 1, dtype=torch.float32, device=x.device)
+    pg = gnn_backward(g_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip,
+                      dropout_ps, seed, engine)
+    return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None)
+
+
+gnn_forward.register_autograd(_backward, setup_context=_setup_context)

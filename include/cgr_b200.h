@@ -1,0 +1,197 @@
+/*
+ * libcgr_b200 — C ABI of the B200-native CGR-MPNN-3D hot path.
+ *
+ * Drop-in boundary for the reference model `cgr_mpnn_3D/models/GNN.py` (GNN.forward :76-110,
+ * DMPNNConv.forward :131-145) and for the batch collation its loaders perform
+ * (`cgr_mpnn_3D/training/trainer.py:105-118`, `test.py:85-90`).  The reference has no FFI of
+ * its own (it is pure Python on ATen + torch_geometric); these entry points are what a ctypes
+ * binding on the reference side calls instead of those Python lines.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the calling thread's current device unless the
+ *     parameter name starts with `host_`;
+ *   - nothing is allocated or retained: the caller owns outputs and workspaces;
+ *   - `stream` is a `cudaStream_t` passed as `void*`;
+ *   - return 0 on success, a positive `cudaError_t` value, or a negative CGR_ERR_* code;
+ *     `cgr_last_error_string()` describes the last failure on the calling thread;
+ *   - functions are re-entrant (autograd runs backward on a different thread).
+ *   - all floating tensors are fp32 row-major, index tensors are int32 unless stated.
+ */
+#ifndef CGR_B200_H_
+#define CGR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGR_B200_VERSION 100
+
+/* activation ids: reference train.py:284-292 maps ReLU/SiLU/GELU to F.relu/F.silu/F.gelu */
+#define CGR_ACT_RELU_ID 0
+#define CGR_ACT_SILU_ID 1
+#define CGR_ACT_GELU_ID 2
+
+/* engines: 0 = SIMT fp32 (exact fp32 FMA, layer-wise), 1 = tcgen05 FP16x3 split (tensor cores) */
+#define CGR_ENGINE_SIMT 0
+#define CGR_ENGINE_TC 1
+
+int cgr_version(void);
+const char* cgr_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Parameter tree of the reference model (GNN.py:53-74), same tensors as its state_dict:
+ *   edge_init.{weight [H,Fa+Fb], bias [H]}, convs.{l}.lin.{weight [H,H], bias [H]},
+ *   edge_to_node.{weight [H,Fa+H], bias [H]}, ffn.{weight [1,H], bias [1]}, skip_weights.{l} [].
+ * `host_dropout_p`, `w_conv`, `b_conv`, `skip` are HOST arrays of `depth` entries
+ * (device pointers inside).  `skip == NULL` <=> use_learnable_skip=False (weight 1).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cgr_params {
+  int32_t fa, fb, hidden, depth, act, use_skip;
+  const float* w_init;
+  const float* b_init;
+  const float* const* w_conv;
+  const float* const* b_conv;
+  const float* const* skip;
+  const float* w_e2n;
+  const float* b_e2n;
+  const float* w_ffn;
+  const float* b_ffn;
+  const float* host_dropout_p;
+} cgr_params_t;
+
+/* gradient buffers, same shapes as cgr_params (written, not accumulated) */
+typedef struct cgr_grads {
+  float* w_init;
+  float* b_init;
+  float* const* w_conv;
+  float* const* b_conv;
+  float* const* skip;
+  float* w_e2n;
+  float* b_e2n;
+  float* w_ffn;
+  float* b_ffn;
+} cgr_grads_t;
+
+/* A collated batch of CGR graphs plus the derived index arrays (cgr_csr_build). */
+typedef struct cgr_graph {
+  int64_t n_atoms, n_bonds, n_rxn;
+  const float* x;            /* [N, Fa]  data.x (atom features, MACE block included) */
+  const float* edge_attr;    /* [E, Fb]  data.edge_attr */
+  const int32_t* src;        /* [E]   b2a   = edge_index[0]           (GNN.py:85)  */
+  const int32_t* dst;        /* [E]         = edge_index[1]                         */
+  const int32_t* in_ptr;     /* [N+1] a2b CSR offsets of bonds grouped by dst (GNN.py:134) */
+  const int32_t* in_idx;     /* [E]   a2b CSR bond ids, ascending inside a group    */
+  const int32_t* atom_ptr;   /* [B+1] first atom of each reaction (Batch.ptr)       */
+} cgr_graph_t;
+
+/* activations kept for the backward pass (caller-allocated; NULL members are not written) */
+typedef struct cgr_saved {
+  float* h_all;     /* [(depth+1), E, H]  h_0 .. h_depth (post activation / dropout)      */
+  float* m_all;     /* [depth, E, H]      gathered messages m_l = a[src] - h[rev]          */
+  float* z_all;     /* [(depth+1), E, H]  pre-activations, only for act != relu, else NULL */
+  float* s;         /* [N, H]  bond->atom sums of h_depth (GNN.py:105)                     */
+  float* hv;        /* [N, H]  atom hidden states (GNN.py:107)                             */
+  float* zv;        /* [N, H]  their pre-activations, only for act != relu, else NULL      */
+  float* pooled;    /* [B, H]  per-reaction sums (GNN.py:110)                              */
+} cgr_saved_t;
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Collation — replaces PyG Batch.from_data_list at trainer.py:105-118 / test.py:85-90.
+ * `local_edge_index` is the concatenation over graphs of the per-graph [2,e_g] int64 arrays
+ * (row 0 = all sources, row 1 = all targets, each of total length E).  Outputs, all int64 like
+ * the reference: edge_index [2,E] with cumulative node offsets, batch [N], ptr [B+1],
+ * edge_ptr [B+1].  workspace >= cgr_collate_workspace(B).
+ * ---------------------------------------------------------------------------------------- */
+size_t cgr_collate_workspace(int64_t n_rxn);
+int cgr_collate_indices(const int64_t* n_nodes, const int64_t* n_edges,
+                        const int64_t* local_edge_index, int64_t n_rxn, int64_t n_bonds,
+                        int64_t n_atoms, int64_t* edge_index, int64_t* batch, int64_t* ptr,
+                        int64_t* edge_ptr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* CSR a2b / b2a / b2revb from a batched edge_index [2,E] int64 (GNN.py:85,132-138).
+ * status[0] bit0: E odd or some bond e^1 is not the reverse of e; bit1: an index is out of
+ * range; bit2: an atom without incoming bond (reference raises at GNN.py:106).
+ * workspace >= cgr_csr_workspace(N, E). */
+size_t cgr_csr_workspace(int64_t n_atoms, int64_t n_bonds);
+int cgr_csr_build(const int64_t* edge_index, int64_t n_bonds, int64_t n_atoms, int32_t* src,
+                  int32_t* dst, int32_t* in_ptr, int32_t* in_idx, int32_t* status,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* atom_ptr [B+1] (int32) from a sorted `batch` vector [N] int64 (Batch.batch). */
+int cgr_atom_ptr_from_batch(const int64_t* batch, int64_t n_atoms, int64_t n_rxn,
+                            int32_t* atom_ptr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2)-(4) Stage-level forward entry points (one per north-star subsystem).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Edge initialisation, GNN.py:85-86: h0[e] = act(W_i [x[src e] || ea[e]] + b_i).
+ * z0 (pre-activation) may be NULL.  workspace >= N*H floats. */
+int cgr_edge_init_fwd(const float* x, const float* edge_attr, const int32_t* src,
+                      const float* w_init, const float* b_init, int64_t n_atoms, int64_t n_bonds,
+                      int32_t fa, int32_t fb, int32_t hidden, int32_t act, float* h0, float* z0,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* One directed-bond update, GNN.py:91-102 + DMPNNConv.forward :131-141:
+ *   m[e] = sum_{k in in(src e)} h[k] - h[e^1];  z = W m + b + skip*h0;  h' = dropout(act(z)).
+ * m_out [E,H] is required (it doubles as the saved message for backward); z_out may be NULL.
+ * skip == NULL means weight 1.  Dropout is applied iff training && dropout_p > 0. */
+int cgr_bond_update_fwd(const float* h_in, const float* h0, const int32_t* in_ptr,
+                        const int32_t* in_idx, const int32_t* src, const float* w, const float* b,
+                        const float* skip, int32_t act, float dropout_p, uint64_t seed,
+                        uint32_t layer, int32_t training, float* h_out, float* m_out, float* z_out,
+                        int64_t n_bonds, int64_t n_atoms, int32_t hidden, void* stream);
+
+/* Stand-alone DMPNNConv.forward, GNN.py:131-141: a_out[v] = sum_{e in in(v)} h[e] (a_message) and
+ * y_out[e] = W (a[src e] - h[e^1]) + b.  m_ws is [E,H] scratch. */
+int cgr_conv_fwd(const float* h, const int32_t* in_ptr, const int32_t* in_idx, const int32_t* src,
+                 const float* w, const float* b, float* a_out, float* y_out, float* m_ws, int64_t n_bonds,
+                 int64_t n_atoms, int32_t hidden, void* stream);
+
+/* Readout, GNN.py:105-110: s[v] = sum_{e in in(v)} h[e]; hv = act(W_o [x || s] + b_o);
+ * out[b] = w_f . sum_{v in b} hv[v] + b_f.  s_out, hv_out, pooled_out are required scratch /
+ * saved tensors; zv_out may be NULL. */
+int cgr_readout_fwd(const float* h, const float* x, const int32_t* in_ptr, const int32_t* in_idx,
+                    const int32_t* atom_ptr, const float* w_e2n, const float* b_e2n,
+                    const float* w_ffn, const float* b_ffn, int32_t act, float* out, float* s_out,
+                    float* hv_out, float* zv_out, float* pooled_out, int64_t n_atoms,
+                    int64_t n_bonds, int64_t n_rxn, int32_t fa, int32_t hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-network entry points (what the torch custom ops call).
+ * ---------------------------------------------------------------------------------------- */
+size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t training,
+                             int32_t engine);
+/* out [B].  `saved` must be non-NULL when training != 0 (activations for backward). */
+int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved,
+                    int32_t training, uint64_t seed, int32_t engine, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t engine);
+/* (5) explicit backward of (2)-(4): grad_out [B] -> every parameter gradient. */
+int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved,
+                     const float* grad_out, cgr_grads_t* grads, uint64_t seed, int32_t engine,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
+int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,
+                        float* grad_pred, void* stream);
+
+/* Measurement hooks used by bench.py: number of kernels this library has launched so far, and
+ * optional CUDA-event timing of each named stage (events are recorded on the launching stream). */
+long long cgr_launch_count(void);
+int cgr_profile_enable(int enable);            /* also clears previously recorded ranges */
+int cgr_profile_count(void);
+int cgr_profile_get(int i, char* name_out, int name_cap, float* ms_out);
+
+/* Debug / test helper: the dropout keep-mask (uint8 [E,H]) the kernels use for `layer`. */
+int cgr_dropout_mask(uint64_t seed, uint32_t layer, float dropout_p, int64_t n_bonds,
+                     int32_t hidden, uint8_t* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGR_B200_H_ */

@@ -1,0 +1,88 @@
+"""CPU: the C-ABI library loads, exports every symbol the header declares, and the host-side
+module mirrors the reference's constructor / error behaviour.  No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cgr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cgr_mpnn_3d_b200 import _lib
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/cgr_b200.h but not exported"
+        assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype"
+    assert lib.cgr_version() == 100
+    assert lib.cgr_csr_workspace(1000, 2000) > 0 and lib.cgr_collate_workspace(64) > 0
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from cgr_mpnn_3d_b200 import _lib
+    lib = _lib.load()
+    rc = lib.cgr_csr_build(None, -1, 5, None, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"negative" in lib.cgr_last_error_string()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "cgr_csr_build")
+
+
+def test_constructor_matches_reference_signature():
+    from cgr_mpnn_3D.models.GNN import GNN, DMPNNConv
+    # reference tests/test_trainer.py:37-38 : positional, num_edge_features = 0
+    m = GNN(5, 0)
+    assert isinstance(m, torch.nn.Module) and m.depth == 3
+    assert m.hidden_sizes == [300] * 3 and m.dropout_ps == [0.02] * 3
+    assert m.edge_init.weight.shape == (300, 5)
+    m = GNN(num_node_features=846, num_edge_features=14, depth=4, hidden_sizes=[400] * 4, dropout_ps=[0.1] * 4,
+            activation_fn=F.relu, use_learnable_skip=True)
+    keys = list(m.state_dict().keys())
+    assert keys[:2] == ["edge_init.weight", "edge_init.bias"]
+    assert keys[2:10] == [f"convs.{l}.lin.{k}" for l in range(4) for k in ("weight", "bias")]
+    assert keys[10:14] == ["edge_to_node.weight", "edge_to_node.bias", "ffn.weight", "ffn.bias"]
+    assert keys[14:] == [f"skip_weights.{l}" for l in range(4)]
+    assert sum(p.numel() for p in m.parameters()) == 1485205
+    assert isinstance(m.convs[0], DMPNNConv) and m.convs[0].lin.weight.shape == (400, 400)
+    # README config (depth 4, three hidden sizes) raises IndexError exactly like GNN.py:59-60
+    with pytest.raises(IndexError):
+        GNN(846, 14, depth=4, hidden_sizes=[400, 400, 400])
+
+
+def test_state_dict_roundtrip_with_oracle_layout():
+    from cgr_mpnn_3D.models.GNN import GNN
+    from oracle.gnn_oracle import OracleGNN
+    o = OracleGNN(78, 14, depth=3, hidden_sizes=[64] * 3, use_learnable_skip=True)
+    m = GNN(78, 14, depth=3, hidden_sizes=[64] * 3, use_learnable_skip=True)
+    m.load_state_dict(o.state_dict())          # strict: identical keys and shapes
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), o.state_dict().values()))
+
+
+def test_whole_module_pickle(tmp_path):
+    """reference trainer.py:208 pickles the module; test.py:93 / CLI :62 unpickle it."""
+    from cgr_mpnn_3D.models.GNN import GNN
+    m = GNN(78, 14, depth=2, hidden_sizes=[32] * 2, use_learnable_skip=True)
+    path = tmp_path / "model.pth"
+    torch.save(m, path)
+    m2 = torch.load(path, map_location="cpu", weights_only=False)
+    assert type(m2).__module__ == "cgr_mpnn_3D.models.GNN"
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_no_cpu_fallback():
+    from cgr_mpnn_3D.models.GNN import GNN
+    from cgr_mpnn_3d_b200.data import make_batch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    m = GNN(78, 14, depth=2, hidden_sizes=[32] * 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        m(make_batch(2, seed=0, fa=78))

@@ -1,0 +1,274 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): integer index arrays bit-exact; per-reaction Ea within 1e-4
+scale-normalised error (``|d| / max(|ref_b|, mean|ref|)``) in the fp32 modes;
+gradients within 1e-4 of each tensor's max-abs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cgr_mpnn_3d_b200.data import Batch, make_batch, make_reactions
+from oracle import collate_oracle
+from oracle.gnn_oracle import mse_sum_loss, scale_normalised_error, tensor_error
+from tests.util import (ACTS, BIG_CASES, SMALL_CASES, build_model, build_oracle, case_batch, case_state_dict,
+                        load_case)
+
+pytestmark = pytest.mark.gpu
+
+EA_TOL = 1e-4      # north_star: per-reaction Ea within 1e-4 relative (fp32 / split-precision mode)
+GRAD_TOL = 1e-4
+
+ENGINES = ["simt"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from cgr_mpnn_3d_b200 import _lib
+    _lib.load()    # fails loudly if the extension is missing
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) collation + CSR: bit-exact integers
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nb,kind,seed", [(1, "t1x", 0), (7, "t1x", 1), (64, "t1x", 2), (1500, "t1x", 3),
+                                          (33, "drug", 4)])
+def test_collate_and_csr_bit_exact(nb, kind, seed):
+    from cgr_mpnn_3d_b200.collate import build_plan, collate
+    graphs = make_reactions(nb, seed=seed, kind=kind, fa=20)
+    dev = collate(graphs)
+    ref = collate_oracle.collate_indices([g.num_nodes for g in graphs], [g.edge_index for g in graphs])
+    assert dev.edge_index.dtype == torch.int64 and dev.batch.dtype == torch.int64
+    assert np.array_equal(dev.edge_index.cpu().numpy(), ref["edge_index"])
+    assert np.array_equal(dev.batch.cpu().numpy(), ref["batch"])
+    assert np.array_equal(dev.ptr.cpu().numpy(), ref["ptr"])
+    assert np.array_equal(dev.edge_ptr.cpu().numpy(), ref["edge_ptr"])
+    x_ref = np.concatenate([g.x for g in graphs])
+    assert np.array_equal(dev.x.cpu().numpy(), x_ref)
+    n = x_ref.shape[0]
+    plan = build_plan(dev.edge_index, n, dev.batch, dev.ptr)
+    plan.check()
+    csr = collate_oracle.csr_arrays(ref["edge_index"], n)
+    for k in ("src", "dst", "in_ptr", "in_idx"):
+        got = getattr(plan, k).cpu().numpy()
+        assert got.dtype == np.int32 and np.array_equal(got, csr[k]), k
+    assert np.array_equal(plan.atom_ptr.cpu().numpy(), ref["ptr"].astype(np.int32))
+    # atom_ptr derived from the batch vector alone (no ptr attribute, reference global_add_pool sizing)
+    plan2 = build_plan(dev.edge_index, n, dev.batch, None)
+    assert plan2.n_rxn == nb and np.array_equal(plan2.atom_ptr.cpu().numpy(), ref["ptr"].astype(np.int32))
+
+
+def test_csr_flags_bad_inputs():
+    from cgr_mpnn_3d_b200.collate import build_plan
+    b = make_batch(3, seed=5, fa=8)
+    ei = b.edge_index.clone()
+    ei[:, [2, 4]] = ei[:, [4, 2]]                     # break the (e, e^1) pairing
+    with pytest.raises(RuntimeError, match="reverse pairs"):
+        build_plan(ei.cuda(), b.num_nodes, None).check()
+    with pytest.raises(RuntimeError, match="no incoming bond"):
+        build_plan(b.edge_index.cuda(), b.num_nodes + 1, None).check()   # isolated last atom, GNN.py:106
+    ei = b.edge_index.clone()
+    ei[0, 0] = b.num_nodes + 7
+    with pytest.raises(RuntimeError, match="outside"):
+        build_plan(ei.cuda(), b.num_nodes, None).check()
+
+
+def test_collate_large_property():
+    """Full-size (B=8192) collate: checksum-of-checksums + sortedness instead of a CPU restatement pass."""
+    from cgr_mpnn_3d_b200.collate import build_plan, collate
+    graphs = make_reactions(8192, seed=0, kind="t1x", fa=4)
+    dev = collate(graphs)
+    n = dev.num_nodes
+    plan = build_plan(dev.edge_index, n, dev.batch, dev.ptr)
+    plan.check()
+    in_ptr, in_idx, dst = plan.in_ptr.cpu().numpy(), plan.in_idx.cpu().numpy(), plan.dst.cpu().numpy()
+    assert in_ptr[0] == 0 and in_ptr[-1] == dev.num_edges and np.all(np.diff(in_ptr) > 0)
+    assert np.array_equal(np.sort(in_idx), np.arange(dev.num_edges))          # a permutation
+    assert np.array_equal(dst[in_idx], np.repeat(np.arange(n), np.diff(in_ptr)))  # grouped by target atom
+    seg_start = np.zeros(dev.num_edges, bool)
+    seg_start[in_ptr[:-1]] = True
+    assert np.all((np.diff(in_idx) > 0) | seg_start[1:])                      # ascending inside a group
+    assert np.all(np.diff(dev.batch.cpu().numpy()) >= 0)
+    ptr = dev.ptr.cpu().numpy()
+    expect = sum(int(g.edge_index.sum()) + 2 * g.num_edges * int(ptr[i]) for i, g in enumerate(graphs))
+    assert int(dev.edge_index.sum()) == expect                                # checksum of the offset arithmetic
+
+
+# ---------------------------------------------------------------------------------------------
+# (2)-(4) stage-level parity
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small_skip", "small_gelu"])
+def test_stage_level_parity(name):
+    from cgr_mpnn_3d_b200 import stage_ops
+    from cgr_mpnn_3d_b200.collate import build_plan
+    from oracle.gnn_oracle import propagate_add
+    z, meta = load_case(name)
+    data = case_batch(z, meta)
+    oracle = build_oracle(meta, case_state_dict(z)).eval()
+    act = ACTS[meta["act"]]
+    act_id = {"relu": 0, "silu": 1, "gelu": 2}[meta["act"]]
+    d = data.to("cuda")
+    plan = build_plan(d.edge_index, d.num_nodes, d.batch, d.ptr)
+    with torch.no_grad():
+        row = data.edge_index[0]
+        h0_ref = act(oracle.edge_init(torch.cat([data.x[row], data.edge_attr], 1)))
+        h0 = stage_ops.edge_init_fwd(d.x, d.edge_attr, plan, oracle.edge_init.weight.cuda(),
+                                     oracle.edge_init.bias.cuda(), act_id)
+        assert tensor_error(h0, h0_ref) < 1e-5
+        a_ref, y_ref = oracle.convs[0](data.edge_index, h0_ref)
+        skip = oracle.skip_weights[0] if meta["skip"] else None
+        h1_ref = act(y_ref + (skip * h0_ref if skip is not None else h0_ref))
+        h1, m, zz = stage_ops.bond_update_fwd(h0_ref.cuda(), h0_ref.cuda(), plan, oracle.convs[0].lin.weight.cuda(),
+                                              oracle.convs[0].lin.bias.cuda(),
+                                              None if skip is None else skip.detach().cuda(), act_id)
+        # the gather is a pure sum in the reference's order: bit-exact against CPU scatter_add_
+        rev = torch.flip(h0_ref.view(-1, 2, h0_ref.shape[1]), dims=[1]).view_as(h0_ref)
+        assert torch.equal(m.cpu(), a_ref[row] - rev)
+        assert tensor_error(h1, h1_ref) < 1e-5
+        # stand-alone DMPNNConv.forward
+        from cgr_mpnn_3D.models.GNN import DMPNNConv
+        conv = DMPNNConv(meta["hidden"]).cuda()
+        conv.load_state_dict(oracle.convs[0].state_dict())
+        a, y = conv(d.edge_index, h0_ref.cuda())
+        assert torch.equal(a.cpu(), a_ref) and tensor_error(y, y_ref) < 1e-5
+        # readout
+        s_ref = propagate_add(data.edge_index, h1_ref)
+        hv_ref = act(oracle.edge_to_node(torch.cat([data.x, s_ref], 1)))
+        from oracle.gnn_oracle import global_add_pool
+        out_ref = oracle.ffn(global_add_pool(hv_ref, data.batch)).squeeze(-1)
+        out, s, hv, pooled = stage_ops.readout_fwd(h1_ref.cuda(), d.x, plan, oracle.edge_to_node.weight.cuda(),
+                                                   oracle.edge_to_node.bias.cuda(), oracle.ffn.weight.cuda(),
+                                                   oracle.ffn.bias.cuda(), act_id)
+        assert torch.equal(s.cpu(), s_ref)
+        assert tensor_error(hv, hv_ref) < 1e-5
+        assert scale_normalised_error(out, out_ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# whole model: forward + backward against the golden vectors of the unmodified reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_golden_forward_backward(name, engine):
+    z, meta = load_case(name)
+    data = case_batch(z, meta).to("cuda")
+    model = build_model(meta, case_state_dict(z), engine=engine).train()
+    model.validate_inputs = True
+    out = model(data)
+    assert out.shape == tuple(z["out"].shape) and out.dtype == torch.float32 and out.is_cuda
+    ref = torch.from_numpy(z["out"])
+    assert scale_normalised_error(out, ref) < EA_TOL
+    loss = mse_sum_loss(out, data.y)
+    loss.backward()
+    assert abs(float(loss) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert tensor_error(p.grad, torch.from_numpy(z["g/" + k])) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", BIG_CASES)
+def test_baseline_configs_forward_backward(name, engine):
+    """cfg-1 (d3 h300 B32) and cfg-2 (d4 h400 skip B64, Fa=846) at full size."""
+    z, meta = load_case(name)
+    data_cpu = case_batch(z, meta)
+    model = build_model(meta, engine=engine).train()
+    out = model(data_cpu.to("cuda"))
+    assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL
+    mse_sum_loss(out, data_cpu.y.cuda()).backward()
+    oracle = build_oracle(meta).train()
+    mse_sum_loss(oracle(data_cpu), data_cpu.y).backward()
+    og = dict(oracle.named_parameters())
+    for k, p in model.named_parameters():
+        assert tensor_error(p.grad, og[k].grad) < GRAD_TOL, k
+        g = p.grad.double()
+        got = np.array([float(g.sum()), float(g.abs().sum()), float(g.abs().max())])
+        np.testing.assert_allclose(got[1:], z["gsum/" + k][1:], rtol=2e-4, err_msg=k)
+    # eval / no_grad path gives the same energies and is run-to-run bit-stable (no float atomics)
+    model.eval()
+    with torch.no_grad():
+        o1 = model(data_cpu.to("cuda"))
+        o2 = model(data_cpu.to("cuda"))
+    assert torch.equal(o1, o2)
+    assert scale_normalised_error(o1, torch.from_numpy(z["out"])) < EA_TOL
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_fp64_accuracy_yardstick(engine):
+    """Error vs an fp64 evaluation of the same graph must stay at fp32 level (2.4e-6)."""
+    z, meta = load_case("cfg2_d4_h400")
+    data = case_batch(z, meta)
+    o64 = build_oracle(meta, dtype=torch.float64).eval()
+    d64 = Batch(data.x.double(), data.edge_index, data.edge_attr.double(), data.batch, data.ptr, data.y)
+    with torch.no_grad():
+        ref = o64(d64)
+        out = build_model(meta, engine=engine).eval()(data.to("cuda"))
+    assert scale_normalised_error(out, ref) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# behaviours of the drop-in boundary
+# ---------------------------------------------------------------------------------------------
+def test_host_inputs_are_staged():
+    """CPU tensors in -> result on CPU (reference CLI feeds un-batched CPU Data, CLI :71-76)."""
+    z, meta = load_case("single_nobatch")
+    data = case_batch(z, meta)
+    assert data.batch is None
+    model = build_model(meta, case_state_dict(z)).eval()
+    with torch.no_grad():
+        out = model(data)
+    assert out.device.type == "cpu" and out.shape == (1,)
+    assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL
+    cpu_model = build_model(meta, case_state_dict(z), device="cpu").eval()   # CPU-resident module (CLI :62)
+    with torch.no_grad():
+        out2 = cpu_model(data)
+    assert torch.equal(out, out2)
+
+
+def test_dropout_replay_against_oracle():
+    """Train-mode dropout: the kernel's Philox keep-mask is exported and replayed in the oracle."""
+    from cgr_mpnn_3d_b200 import ops, stage_ops
+    from cgr_mpnn_3d_b200.collate import plan_for
+    z, meta = load_case("small_skip")
+    data = case_batch(z, meta)
+    p = 0.25
+    model = build_model(meta, case_state_dict(z), dropout_ps=[p] * meta["depth"]).train()
+    d = data.to("cuda")
+    plan = plan_for(d)
+    seed = 1234567
+    res = ops.gnn_forward(d.x, d.edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr,
+                          model._param_list(), meta["depth"], 0, True, [p] * meta["depth"], True, seed, 0)
+    out = res[0]
+    masks = [stage_ops.dropout_mask(seed, l, p, d.num_edges, meta["hidden"], "cuda").cpu()
+             for l in range(meta["depth"])]
+    keep = float(torch.stack(masks).float().mean())
+    assert abs(keep - (1 - p)) < 0.01
+    oracle = build_oracle(meta, case_state_dict(z)).train()
+    oracle.dropout_ps = [p] * meta["depth"]
+    ref = oracle(data, dropout_masks=masks)
+    assert scale_normalised_error(out, ref) < EA_TOL
+    mse_sum_loss(out, d.y).backward()
+    mse_sum_loss(ref, data.y).backward()
+    og = dict(oracle.named_parameters())
+    for k, q in model.named_parameters():
+        assert tensor_error(q.grad, og[k].grad) < GRAD_TOL, k
+
+
+def test_training_step_matches_reference_optimizer():
+    """Three Adam(amsgrad) steps with MSE(sum) (reference train.py:117-121, trainer.py:138-147)."""
+    z, meta = load_case("small_skip")
+    data = case_batch(z, meta)
+    model = build_model(meta, case_state_dict(z)).train()
+    oracle = build_oracle(meta, case_state_dict(z)).train()
+    om = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True)
+    oo = torch.optim.Adam(oracle.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True)
+    d = data.to("cuda")
+    for _ in range(3):
+        om.zero_grad(); oo.zero_grad()
+        lm = mse_sum_loss(model(d), d.y); lm.backward(); om.step()
+        lo = mse_sum_loss(oracle(data), data.y); lo.backward(); oo.step()
+        assert abs(float(lm) - float(lo)) <= 2e-4 * abs(float(lo))
+    for (k, p), q in zip(model.named_parameters(), oracle.parameters()):
+        assert tensor_error(p, q) < 1e-4, k

@@ -47,3 +47,20 @@ def build_oracle(meta, state=None, dtype=torch.float32):
             for l, p in enumerate(m.skip_weights):
                 p.fill_(1.0 - 0.15 * l + 0.05 * (l % 2))
     return m.to(dtype)
+
+
+def build_model(meta, state=None, device="cuda", engine="simt", dropout_ps=None):
+    """The product model (drop-in module path) with the same weights as ``build_oracle``."""
+    from cgr_mpnn_3D.models.GNN import GNN
+    torch.manual_seed(meta["wseed"])
+    m = GNN(meta["fa"], meta["fb"], depth=meta["depth"], hidden_sizes=[meta["hidden"]] * meta["depth"],
+            dropout_ps=dropout_ps or [0.0] * meta["depth"], activation_fn=ACTS[meta["act"]],
+            use_learnable_skip=meta["skip"])
+    if state is not None:
+        m.load_state_dict(state)
+    elif meta["skip"]:
+        with torch.no_grad():
+            for l, p in enumerate(m.skip_weights):
+                p.fill_(1.0 - 0.15 * l + 0.05 * (l % 2))
+    m.engine = engine
+    return m.to(device)
