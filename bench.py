@@ -215,8 +215,9 @@ def main():
     # ---- leg 1: device-resident throughput (CUDA-graph replay of the forward, one graph per batch) ----
     outs = [None] * n_pool
     with torch.no_grad():
-        for i in range(min(3, n_pool)):           # eager warm-up (allocator, module load)
+        for i in range(n_pool):                   # eager pass: builds every plan (tile packing syncs once per batch)
             outs[i] = model(pool[i])
+        model.check_numerics()
         torch.cuda.synchronize()
         launches_per_step = 0
         graphs = None

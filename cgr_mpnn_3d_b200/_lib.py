@@ -29,6 +29,7 @@ class CgrParams(C.Structure):
         ("w_conv", c_void_pp), ("b_conv", c_void_pp), ("skip", c_void_pp),
         ("w_e2n", C.c_void_p), ("b_e2n", C.c_void_p), ("w_ffn", C.c_void_p), ("b_ffn", C.c_void_p),
         ("host_dropout_p", c_float_p),
+        ("tc_weights", C.c_void_p),
     ]
 
 
@@ -45,6 +46,7 @@ class CgrGraph(C.Structure):
         ("n_atoms", C.c_int64), ("n_bonds", C.c_int64), ("n_rxn", C.c_int64),
         ("x", C.c_void_p), ("edge_attr", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p),
         ("in_ptr", C.c_void_p), ("in_idx", C.c_void_p), ("atom_ptr", C.c_void_p),
+        ("tile_info", C.c_void_p), ("n_tiles", C.c_int64), ("tc_status", C.c_void_p),
     ]
 
 
@@ -80,6 +82,12 @@ PROTOTYPES = {
     "cgr_backward_workspace": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph), _I32]),
     "cgr_gnn_backward": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrGraph), C.POINTER(CgrSaved), _V,
                                    C.POINTER(CgrGrads), C.c_uint64, _I32, _V, _SZ, _V]),
+    "cgr_tc_plan_build": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
+    "cgr_tc_plan_check": (C.c_int, [_V, _I64, _V, _V, _V, _V]),
+    "cgr_tc_weights_bytes": (_SZ, [C.POINTER(CgrParams)]),
+    "cgr_tc_prepare_weights": (C.c_int, [C.POINTER(CgrParams), _V, _SZ, _V]),
+    "cgr_tc_linear_workspace": (_SZ, [_I64, _I64, _I64]),
+    "cgr_tc_linear": (C.c_int, [_V, _I64, _I64, _V, _I64, _V, _V, _V, _SZ, _V]),
     "cgr_mse_sum_fwd_bwd": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
     "cgr_launch_count": (C.c_longlong, []),
     "cgr_profile_enable": (C.c_int, [C.c_int]),

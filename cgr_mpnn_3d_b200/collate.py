@@ -28,10 +28,33 @@ def _stream() -> int:
 class GraphPlan:
     """Index arrays the kernels consume, built once per batch and cached on the batch object."""
 
-    __slots__ = ("n_atoms", "n_bonds", "n_rxn", "src", "dst", "in_ptr", "in_idx", "atom_ptr", "status", "tc")
+    __slots__ = ("n_atoms", "n_bonds", "n_rxn", "src", "dst", "in_ptr", "in_idx", "atom_ptr", "status",
+                 "tile_info", "n_tiles", "tc_ok", "tc_status")
 
     def __init__(self):
-        self.tc = None   # lazily built tile plan of the tcgen05 engine
+        self.tile_info = None    # tile plan of the tcgen05 engine (built lazily by ensure_tiles)
+        self.n_tiles = 0
+        self.tc_ok = None
+        self.tc_status = None
+
+    def ensure_tiles(self) -> bool:
+        """Pack whole reactions into 128-bond row tiles (tcgen05 engine).  One host sync, cached."""
+        if self.tc_ok is not None:
+            return self.tc_ok
+        lib = _lib.load()
+        dev = self.src.device
+        self.tile_info = torch.zeros((max(1, self.n_rxn), 8), dtype=torch.int32, device=dev)
+        st = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.tc_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.cgr_tc_plan_build(self.in_ptr.data_ptr(), self.atom_ptr.data_ptr(), self.n_rxn,
+                                             self.tile_info.data_ptr(), st.data_ptr(), _stream()), "cgr_tc_plan_build")
+            _lib.check(lib.cgr_tc_plan_check(self.tile_info.data_ptr(), self.n_rxn, self.src.data_ptr(),
+                                             self.dst.data_ptr(), st.data_ptr(), _stream()), "cgr_tc_plan_check")
+        n_tiles, ok = (int(v) for v in st.tolist())
+        self.n_tiles = n_tiles
+        self.tc_ok = bool(ok) and n_tiles > 0
+        return self.tc_ok
 
     def check(self) -> None:
         """Synchronising validity check of the reference's silent preconditions (GNN.py:106,136-138)."""

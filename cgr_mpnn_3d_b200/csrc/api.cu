@@ -395,6 +395,27 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
                    simt_splitk_choose(H, fa, N), partial, st);
 }
 
+extern "C" int cgr_tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, int64_t n_rxn, int32_t* tile_info,
+                                 int32_t* status, void* stream) {
+  return tc_plan_build(in_ptr, atom_ptr, nullptr, nullptr, n_rxn, tile_info, status, (cudaStream_t)stream);
+}
+extern "C" int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst,
+                                 int32_t* status, void* stream) {
+  CGR_CHECK_ARG(tile_info && src && dst && status, "cgr_tc_plan_check: null pointer");
+  return tc_plan_check(tile_info, n_tiles, src, dst, status, (cudaStream_t)stream);
+}
+extern "C" size_t cgr_tc_weights_bytes(const cgr_params_t* p) { return p ? tc_weights_bytes(p) : 0; }
+extern "C" int cgr_tc_prepare_weights(const cgr_params_t* p, void* buffer, size_t buffer_bytes, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  return tc_prepare_weights(p, buffer, buffer_bytes, (cudaStream_t)stream);
+}
+extern "C" size_t cgr_tc_linear_workspace(int64_t m, int64_t n, int64_t k) { return tc_linear_workspace(m, n, k); }
+extern "C" int cgr_tc_linear(const float* x, int64_t m, int64_t k, const float* w, int64_t n, const float* bias,
+                             float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return tc_linear(x, m, k, k, w, n, k, bias, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss, float* grad_pred,
                                    void* stream) {
   CGR_CHECK_ARG(pred && y && n_rxn >= 0, "cgr_mse_sum_fwd_bwd: bad argument");

@@ -7,3 +7,13 @@
 size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int training);
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+size_t tc_weights_bytes(const cgr_params_t* p);
+int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cudaStream_t st);
+int tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, const int32_t* src, const int32_t* dst,
+                  int64_t n_rxn, int32_t* tile_info, int32_t* status, cudaStream_t st);
+int tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst, int32_t* status,
+                  cudaStream_t st);
+size_t tc_linear_workspace(int64_t M, int64_t N, int64_t K);
+int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wgt, int64_t N, int64_t ldw,
+              const float* bias, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);

@@ -116,13 +116,31 @@ class GNN(nn.Module):
             ps += list(self.skip_weights)
         return ps
 
-    def _engine_id(self) -> int:
+    def _engine_id(self, plan, needs_saved: bool) -> int:
+        """simt = exact-fp32 layer-wise kernels; tc = tcgen05 FP16x3 fused kernels (inference forward).
+        auto picks tc whenever it applies: no activations to save, even hidden size, every reaction
+        fits a 128-bond tile."""
         e = getattr(self, "engine", "auto")
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
+        can_tc = (not needs_saved) and self.hidden_sizes[0] % 2 == 0 and self.depth <= 13 and plan.ensure_tiles()
         if e in ("tc", 1):
+            if not can_tc:
+                raise RuntimeError("engine='tc' needs an inference forward (no grad, no dropout), an even hidden "
+                                   "size and reactions of at most 128 directed bonds")
             return _lib.ENGINE_TC
-        return _lib.ENGINE_SIMT
+        return _lib.ENGINE_TC if can_tc else _lib.ENGINE_SIMT
+
+    def _tc_weights(self, params, fa: int, fb: int) -> torch.Tensor:
+        from . import ops
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        cache = self.__dict__.get("_tc_cache")
+        if cache is None or cache[0] != key:
+            buf = ops.prepare_tc_weights(params, self.depth, _act_id(self.activation_fn),
+                                         bool(self.use_learnable_skip), fa, fb)
+            cache = (key, buf)
+            self.__dict__["_tc_cache"] = cache
+        return cache[1]
 
     def _check_arch(self) -> None:
         hs = list(self.hidden_sizes[: self.depth])
@@ -158,9 +176,18 @@ class GNN(nn.Module):
         # dropout only in train mode (GNN.py:100-102); activations are saved whenever a backward may follow
         dps = [float(p) if self.training else 0.0 for p in self.dropout_ps[: self.depth]]
         train_flag = needs_grad or any(p > 0 for p in dps)
+        engine = self._engine_id(plan, train_flag)
+        empty_i = torch.empty(0, dtype=torch.int32, device=dev)
+        if engine == _lib.ENGINE_TC:
+            tile_info, n_tiles, tc_status = plan.tile_info, plan.n_tiles, plan.tc_status
+            tc_w = self._tc_weights(params, int(x.shape[1]), int(edge_attr.shape[1]))
+        else:
+            tile_info, n_tiles, tc_status = empty_i, 0, empty_i
+            tc_w = torch.empty(0, dtype=torch.uint8, device=dev)
         res = ops.gnn_forward(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr, params,
                               self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
-                              train_flag, seed, self._engine_id())
+                              train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w)
+        self.__dict__["_last_plan"] = plan if engine == _lib.ENGINE_TC else None
         out = res[0]
         if caller_device != dev:
             out = out.to(caller_device)
@@ -176,9 +203,19 @@ class GNN(nn.Module):
             self.__dict__["_mirror_cache"] = cache
         return cache[1]
 
+    def check_numerics(self) -> None:
+        """Synchronising check of the last tcgen05 forward: raises if an activation left the fp16 range
+        of the FP16x3 split (then use ``engine='simt'``)."""
+        plan = self.__dict__.get("_last_plan")
+        if plan is not None and plan.tc_status is not None and int(plan.tc_status.item()) != 0:
+            raise RuntimeError("tcgen05 engine: an activation exceeded the fp16 range of the FP16x3 split; "
+                               "set model.engine = 'simt'")
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_mirror_cache", None)     # torch.save(model) must not pickle device mirrors
+        state.pop("_tc_cache", None)
+        state.pop("_last_plan", None)
         return state
 
 

@@ -57,11 +57,15 @@ class _Ctx:
         )
 
 
-def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr) -> _lib.CgrGraph:
+def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info=None, n_tiles=0,
+                  tc_status=None) -> _lib.CgrGraph:
+    has_tiles = tile_info is not None and tile_info.numel() > 0 and n_tiles > 0
     return _lib.CgrGraph(
         n_atoms=int(x.shape[0]), n_bonds=int(src.shape[0]), n_rxn=int(atom_ptr.shape[0]) - 1,
         x=x.data_ptr(), edge_attr=edge_attr.data_ptr(), src=src.data_ptr(), dst=dst.data_ptr(),
         in_ptr=in_ptr.data_ptr(), in_idx=in_idx.data_ptr(), atom_ptr=atom_ptr.data_ptr(),
+        tile_info=tile_info.data_ptr() if has_tiles else None, n_tiles=int(n_tiles) if has_tiles else 0,
+        tc_status=tc_status.data_ptr() if (has_tiles and tc_status is not None and tc_status.numel() > 0) else None,
     )
 
 
@@ -80,16 +84,22 @@ def _f32c(t: Tensor) -> Tensor:
 @torch.library.custom_op("cgr_b200::gnn_forward", mutates_args=())
 def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor, in_idx: Tensor,
                 atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
-                dropout_ps: Sequence[float], training: bool, seed: int, engine: int) -> List[Tensor]:
-    """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled]`` (saved tensors are empty in eval)."""
+                dropout_ps: Sequence[float], training: bool, seed: int, engine: int, tile_info: Tensor,
+                n_tiles: int, tc_status: Tensor, tc_weights: Tensor) -> List[Tensor]:
+    """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled]`` (saved tensors are empty in eval).
+
+    ``tile_info`` / ``n_tiles`` / ``tc_status`` / ``tc_weights`` feed the tcgen05 engine (empty tensors
+    when unused)."""
     _require_cuda(x, edge_attr, src, *params)
     lib = _lib.load()
     x, edge_attr = _f32c(x), _f32c(edge_attr)
     params = [_f32c(p) for p in params]
     fa, fb = int(x.shape[1]), int(edge_attr.shape[1])
     ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
+    if tc_weights.numel() > 0:
+        ctx.params.tc_weights = tc_weights.data_ptr()
     H = ctx.hidden
-    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr)
+    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info, n_tiles, tc_status)
     n, e, b = g.n_atoms, g.n_bonds, g.n_rxn
     f32 = dict(dtype=torch.float32, device=x.device)
     out = torch.empty(b, **f32)
@@ -120,7 +130,7 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
 
 @gnn_forward.register_fake
 def _(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-      engine):
+      engine, tile_info, n_tiles, tc_status, tc_weights):
     H = params[0].shape[0]
     n, e, b = x.shape[0], src.shape[0], atom_ptr.shape[0] - 1
     mk = lambda *s: x.new_empty(s, dtype=torch.float32)
@@ -174,7 +184,7 @@ def _(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved,
 
 def _setup_context(ctx, inputs, output):
     (x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-     engine) = inputs
+     engine, _tile_info, _n_tiles, _tc_status, _tc_weights) = inputs
     ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine)
     ctx.n_params = len(params)
     ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:])
@@ -193,8 +203,41 @@ def _backward(ctx, grads):
     if g_out is None:
         g_out = torch.zeros(atom_ptr.shape[0] - 1, dtype=torch.float32, device=x.device)
     pg = gnn_backward(g_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip,
-                      dropout_ps, seed, engine)
-    return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None)
+                      dropout_ps, seed, 0)
+    return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None, None, None,
+            None, None)
 
 
 gnn_forward.register_autograd(_backward, setup_context=_setup_context)
+
+
+def prepare_tc_weights(params: Sequence[Tensor], depth: int, act: int, use_skip: bool, fa: int, fb: int) -> Tensor:
+    """FP16 (hi, lo) operand form of the parameter tree for the tcgen05 engine (``cgr_tc_prepare_weights``)."""
+    _require_cuda(*params)
+    lib = _lib.load()
+    params = [_f32c(p.detach()) for p in params]
+    ctx = _Ctx(params, depth, act, use_skip, fa, fb, [0.0] * depth)
+    dev = params[0].device
+    with torch.cuda.device(dev):
+        nbytes = lib.cgr_tc_weights_bytes(C.byref(ctx.params))
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.cgr_tc_prepare_weights(C.byref(ctx.params), buf.data_ptr(), nbytes, _stream()),
+                   "cgr_tc_prepare_weights")
+    return buf
+
+
+def tc_linear(x: Tensor, w: Tensor, bias=None) -> Tensor:
+    """Test entry: ``x @ w.T + bias`` on the TMA + tcgen05 FP16x3 pipeline (``cgr_tc_linear``)."""
+    _require_cuda(x, w)
+    lib = _lib.load()
+    x, w = _f32c(x), _f32c(w)
+    m, k = x.shape
+    n = w.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        nbytes = lib.cgr_tc_linear_workspace(m, n, k)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        b = None if bias is None else _f32c(bias)
+        _lib.check(lib.cgr_tc_linear(x.data_ptr(), m, k, w.data_ptr(), n, _lib.ptr(b), out.data_ptr(), ws.data_ptr(),
+                                     nbytes, _stream()), "cgr_tc_linear")
+    return out

@@ -60,6 +60,7 @@ typedef struct cgr_params {
   const float* w_ffn;
   const float* b_ffn;
   const float* host_dropout_p;
+  const void* tc_weights;    /* optional: buffer filled by cgr_tc_prepare_weights (NULL: prepared per call) */
 } cgr_params_t;
 
 /* gradient buffers, same shapes as cgr_params (written, not accumulated) */
@@ -85,6 +86,9 @@ typedef struct cgr_graph {
   const int32_t* in_ptr;     /* [N+1] a2b CSR offsets of bonds grouped by dst (GNN.py:134) */
   const int32_t* in_idx;     /* [E]   a2b CSR bond ids, ascending inside a group    */
   const int32_t* atom_ptr;   /* [B+1] first atom of each reaction (Batch.ptr)       */
+  const int32_t* tile_info;  /* [n_tiles, 8] tile plan of the tcgen05 engine (cgr_tc_plan_build) or NULL */
+  int64_t n_tiles;
+  int32_t* tc_status;        /* optional [1]: receives the fp16-range overflow flag of a tcgen05 forward */
 } cgr_graph_t;
 
 /* activations kept for the backward pass (caller-allocated; NULL members are not written) */
@@ -175,6 +179,26 @@ size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32
 int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved,
                      const float* grad_out, cgr_grads_t* grads, uint64_t seed, int32_t engine,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 engine helpers.
+ * cgr_tc_plan_build packs consecutive whole reactions into 128-bond row tiles: tile_info[t] =
+ * {first bond, #bonds, first atom, #atoms, first reaction, #reactions, 0, 0}; status[0] = number of
+ * tiles, status[1] = 1 iff every reaction fits a tile (<= 128 bonds).  tile_info needs room for
+ * n_rxn tiles.  cgr_tc_plan_check (after reading status[0]) clears status[1] if a bond leaves its tile.
+ * cgr_tc_prepare_weights converts the parameter tree into the FP16 (hi, lo) operand layout once;
+ * pass the buffer as cgr_params_t.tc_weights to skip the per-call conversion.
+ * ---------------------------------------------------------------------------------------- */
+int cgr_tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, int64_t n_rxn, int32_t* tile_info,
+                      int32_t* status, void* stream);
+int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst,
+                      int32_t* status, void* stream);
+size_t cgr_tc_weights_bytes(const cgr_params_t* p);
+int cgr_tc_prepare_weights(const cgr_params_t* p, void* buffer, size_t buffer_bytes, void* stream);
+/* Test entry: out[M,N] = x[M,K] w[N,K]^T + bias (bias may be NULL) on the TMA + tcgen05 FP16x3 pipeline. */
+size_t cgr_tc_linear_workspace(int64_t m, int64_t n, int64_t k);
+int cgr_tc_linear(const float* x, int64_t m, int64_t k, const float* w, int64_t n, const float* bias,
+                  float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,
