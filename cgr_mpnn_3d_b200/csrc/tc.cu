@@ -17,274 +17,12 @@
 #include <math.h>
 #include <string.h>
 
+#include "tc_gemm.cuh"
 #include "umma.cuh"
 
 namespace {
 
-constexpr int TM = 128;                 // rows of a tile (UMMA M)
-constexpr int BK = 64;                  // fp16 elements per k-chunk = one 128-byte swizzle row
-constexpr int BN = 80;                  // output columns per CTA (UMMA N), multiple of 16
-constexpr int BNP = BN + 4;             // padded row of the fp32 staging tiles (conflict-free float4 rows)
-constexpr int STAGES = 4;
-constexpr int A_BYTES = TM * BK * 2;    // 16 KB
-constexpr int B_BYTES = BN * BK * 2;    // 10 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-constexpr int TMEM_COLS = 128;          // power of two >= BN
-constexpr int THREADS = 256;
-constexpr int AUX_BYTES = 2048;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
-static_assert(2 * TM * BNP * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
-
-enum { EPI_PLAIN = 0, EPI_BOND = 1, EPI_READOUT = 2 };
-
-struct TcGemmParams {
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  int num_k;                    // k-chunks of BK
-  int n_total;                  // real output columns
-  int m_rows;                   // real rows (EPI_PLAIN)
-  const float* unscale;         // device scalar 1 / (scale_A * scale_W)
-  const float* bias;            // [n_total] or null
-  // EPI_PLAIN
-  float* out_f32;
-  int64_t ldc;
-  // tile-local epilogues
-  const int32_t* tile_info;     // [T][8]: ebase, ecount, abase, acount, rx0, rxcount, 0, 0
-  const int32_t* in_ptr;
-  const int32_t* in_idx;
-  const int32_t* src;
-  const int32_t* atom_ptr;
-  const float* skip;            // device scalar or null (=1)
-  const float* h0;              // [T*128, H] fp32 (tile-packed rows)
-  int act;
-  float dropout_p;
-  uint64_t seed;
-  uint32_t layer;
-  __half* o_hi;                 // next operand, [T*128, ldo]
-  __half* o_lo;
-  int64_t ldo;
-  const float* Q;               // readout: x W_ox^T + b_o, [N, ldq]
-  int64_t ldq;
-  const float* w_ffn;
-  float* partial_out;           // [n_slices, B]
-  int64_t n_rxn;
-  int* overflow;                // sticky flag: an activation left the fp16 range
-};
-
-struct Aux {                    // small per-CTA shared state, lives after the pipeline buffers
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
-  uint64_t tmem_full;
-  uint32_t tmem_base;
-  int32_t info[8];
-  uint16_t ptr_l[TM + 2];       // local CSR offsets of the tile's atoms
-  uint8_t src_l[TM];            // local source atom of each bond row
-  uint8_t idx_l[TM];            // local bond ids grouped by target atom
-  float tat[TM];                // readout: per-atom dot with w_ffn
-};
-static_assert(sizeof(Aux) <= AUX_BYTES, "Aux too large");
-
-__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
-}
-
-template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = umma::smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = smem_raw + (base - raw);
-  Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, slice = blockIdx.y;
-  const int n0 = slice * BN;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      umma::mbar_init(umma::smem_u32(&aux->full[s]), 1);
-      umma::mbar_init(umma::smem_u32(&aux->empty[s]), 1);
-    }
-    umma::mbar_init(umma::smem_u32(&aux->tmem_full), 1);
-    umma::mbar_fence_init();
-    umma::tma_prefetch_desc(&p.tmA_hi);
-    umma::tma_prefetch_desc(&p.tmA_lo);
-    umma::tma_prefetch_desc(&p.tmB_hi);
-    umma::tma_prefetch_desc(&p.tmB_lo);
-  }
-  if (warp == 1) {
-    umma::tmem_alloc(umma::smem_u32(&aux->tmem_base), TMEM_COLS);
-    umma::tmem_relinquish();
-  }
-  if (EPI != EPI_PLAIN && threadIdx.x < 8) aux->info[threadIdx.x] = __ldg(p.tile_info + (int64_t)tile * 8 + threadIdx.x);
-  umma::tc_fence_before_sync();
-  __syncthreads();
-  umma::tc_fence_after_sync();
-  const uint32_t tmem = aux->tmem_base;
-
-  // ------------------------------------------------------------------ main loop (warp-specialised)
-  if (warp == 0) {
-    // TMA producer: one elected lane streams A (hi, lo) and B (hi, lo) k-chunks through the ring
-    for (int kc = 0; kc < p.num_k; ++kc) {
-      const int s = kc % STAGES;
-      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-      if (lane == 0) {
-        umma::mbar_wait(umma::smem_u32(&aux->empty[s]), ph ^ 1u);
-        const uint32_t full = umma::smem_u32(&aux->full[s]);
-        const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
-        umma::mbar_arrive_expect_tx(full, STAGE_BYTES);
-        umma::tma_load_2d(&p.tmA_hi, full, st, kc * BK, tile * TM);
-        umma::tma_load_2d(&p.tmA_lo, full, st + A_BYTES, kc * BK, tile * TM);
-        umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
-        umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // MMA issuer: one lane issues 3 tcgen05.mma per 16-wide k-step (hi.hi + lo.hi + hi.lo)
-    constexpr uint32_t idesc = umma::idesc_f16_f32(TM, BN);
-    for (int kc = 0; kc < p.num_k; ++kc) {
-      const int s = kc % STAGES;
-      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-      if (lane == 0) {
-        umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
-        umma::tc_fence_after_sync();
-        const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
-        const uint64_t da_hi = umma::smem_desc_k_sw128(st);
-        const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
-        const uint64_t db_hi = umma::smem_desc_k_sw128(st + 2 * A_BYTES);
-        const uint64_t db_lo = umma::smem_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 32 >> 4);          // 16 fp16 = 32 bytes along K inside the swizzle row
-          umma::mma_f16_ss(tmem, da_lo + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
-          umma::mma_f16_ss(tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-          umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc, 1u);
-        }
-        umma::mma_commit(umma::smem_u32(&aux->empty[s]));         // frees the stage when these MMAs retire
-        if (kc == p.num_k - 1) umma::mma_commit(umma::smem_u32(&aux->tmem_full));
-      }
-      __syncwarp();
-    }
-  } else if (EPI != EPI_PLAIN) {
-    // the other warps stage the tile's index rows into shared memory while the GEMM runs
-    const int ebase = aux->info[0], ecount = aux->info[1], abase = aux->info[2], acount = aux->info[3];
-    for (int j = threadIdx.x - 64; j < ecount; j += THREADS - 64) {
-      aux->src_l[j] = (uint8_t)(__ldg(p.src + ebase + j) - abase);
-      aux->idx_l[j] = (uint8_t)(__ldg(p.in_idx + ebase + j) - ebase);
-    }
-    for (int v = threadIdx.x - 64; v <= acount; v += THREADS - 64)
-      aux->ptr_l[v] = (uint16_t)(__ldg(p.in_ptr + abase + v) - ebase);
-  }
-
-  // ------------------------------------------------------------------ epilogue (all 8 warps)
-  umma::mbar_wait(umma::smem_u32(&aux->tmem_full), 0);
-  umma::tc_fence_after_sync();
-  float* y_s = reinterpret_cast<float*>(smem);                   // [TM][BNP], aliases the drained pipeline
-  float* a_s = y_s + TM * BNP;                                   // [TM][BNP]
-  {
-    const float us = __ldg(p.unscale);
-    const int q = warp & 3, half = warp >> 2;                    // TMEM lane quarter / column half
-    const int row = q * 32 + lane;
-    constexpr int COLS_PER_WARP = BN / 2;                        // 40
-#pragma unroll
-    for (int cc = 0; cc < COLS_PER_WARP; cc += 8) {
-      const int c = half * COLS_PER_WARP + cc;
-      float v[8];
-      umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      umma::tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(y_s + row * BNP + c);
-      dst[0] = make_float4(v[0] * us, v[1] * us, v[2] * us, v[3] * us);
-      dst[1] = make_float4(v[4] * us, v[5] * us, v[6] * us, v[7] * us);
-    }
-  }
-  umma::tc_fence_before_sync();
-  __syncthreads();
-
-  if (EPI == EPI_PLAIN) {
-    // rows are dense (atoms): out = y + bias, written as coalesced rows
-    for (int r = warp; r < TM; r += THREADS / 32) {
-      const int64_t row = (int64_t)tile * TM + r;
-      if (row >= p.m_rows) break;
-      for (int c = lane; c < BN; c += 32) {
-        const int n = n0 + c;
-        if (n < p.n_total) p.out_f32[row * p.ldc + n] = y_s[r * BNP + c] + (p.bias ? __ldg(p.bias + n) : 0.f);
-      }
-    }
-  } else if (EPI == EPI_BOND) {
-    const int ebase = aux->info[0], ecount = aux->info[1], acount = aux->info[3];
-    // a[v] = sum_{k in in(v)} y[k]   (ascending bond id, the reference's accumulation order)
-    for (int v = warp; v < acount; v += THREADS / 32) {
-      const int pb = aux->ptr_l[v], pe = aux->ptr_l[v + 1];
-      for (int c = lane; c < BN; c += 32) {
-        float a = 0.f;
-        for (int q = pb; q < pe; ++q) a += y_s[(int)aux->idx_l[q] * BNP + c];
-        a_s[v * BNP + c] = a;
-      }
-    }
-    __syncthreads();
-    const float skip = p.skip ? __ldg(p.skip) : 1.f;
-    const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-    const int H = p.n_total;
-    bool ovf = false;
-    // z[e] = a[src e] - y[e^1] + b + skip*h0[e];  h' = dropout(act(z));  written as the FP16 (hi, lo) operand
-    for (int j = warp; j < ecount; j += THREADS / 32) {
-      const int64_t r = (int64_t)tile * TM + j;
-      const float* arow = a_s + (int)aux->src_l[j] * BNP;
-      const float* yrev = y_s + (j ^ 1) * BNP;
-      for (int c2 = lane; c2 < BN / 2; c2 += 32) {
-        const int c = 2 * c2, n = n0 + c;
-        if (n >= H) continue;
-        const float2 h0v = *reinterpret_cast<const float2*>(p.h0 + r * H + n);
-        float z0 = arow[c] - yrev[c] + __ldg(p.bias + n) + skip * h0v.x;
-        float z1 = arow[c + 1] - yrev[c + 1] + __ldg(p.bias + n + 1) + skip * h0v.y;
-        z0 = cgr_act(z0, p.act);
-        z1 = cgr_act(z1, p.act);
-        if (p.dropout_p > 0.f) {
-          const uint64_t idx = (uint64_t)(ebase + j) * (uint64_t)H + (uint64_t)n;
-          z0 = cgr_dropout_keep(p.seed, p.layer, idx, p.dropout_p) ? z0 * keep_scale : 0.f;
-          z1 = cgr_dropout_keep(p.seed, p.layer, idx + 1, p.dropout_p) ? z1 * keep_scale : 0.f;
-        }
-        ovf |= (fabsf(z0) > 60000.f) | (fabsf(z1) > 60000.f);
-        __half h0h, h0l, h1h, h1l;
-        split_f16(z0, h0h, h0l);
-        split_f16(z1, h1h, h1l);
-        *reinterpret_cast<__half2*>(p.o_hi + r * p.ldo + n) = __halves2half2(h0h, h1h);
-        *reinterpret_cast<__half2*>(p.o_lo + r * p.ldo + n) = __halves2half2(h0l, h1l);
-      }
-    }
-    if (ovf) atomicOr(p.overflow, 1);
-  } else {
-    // readout: hv[v] = act(Q[v] + sum_{k in in(v)} y[k]);  t[v] = hv[v] . w_f (this CTA's columns)
-    const int abase = aux->info[2], acount = aux->info[3], rx0 = aux->info[4], rxcount = aux->info[5];
-    const int H = p.n_total;
-    for (int v = warp; v < acount; v += THREADS / 32) {
-      const int pb = aux->ptr_l[v], pe = aux->ptr_l[v + 1];
-      float t = 0.f;
-      for (int c = lane; c < BN; c += 32) {
-        const int n = n0 + c;
-        if (n >= H) continue;
-        float a = 0.f;
-        for (int q = pb; q < pe; ++q) a += y_s[(int)aux->idx_l[q] * BNP + c];
-        const float zv = __ldg(p.Q + (int64_t)(abase + v) * p.ldq + n) + a;
-        t = fmaf(cgr_act(zv, p.act), __ldg(p.w_ffn + n), t);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) aux->tat[v] = t;
-    }
-    __syncthreads();
-    for (int rx = threadIdx.x; rx < rxcount; rx += THREADS) {
-      const int b = rx0 + rx;
-      const int v0 = __ldg(p.atom_ptr + b) - abase, v1 = __ldg(p.atom_ptr + b + 1) - abase;
-      float s = 0.f;
-      for (int v = v0; v < v1; ++v) s += aux->tat[v];            // ascending atom id
-      p.partial_out[(int64_t)slice * p.n_rxn + b] = s;
-    }
-  }
-
-  __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, TMEM_COLS);
-}
+using namespace tcg;
 
 // ------------------------------------------------------------------------------------------------
 // small SIMT kernels around the GEMMs
@@ -510,6 +248,22 @@ int make_map(CUtensorMap* tm, const __half* basep, int64_t rows, int64_t cols, i
   return CGR_OK;
 }
 
+// fp32 matrix [rows, cols], row stride `ld` elements, dense (unswizzled) box [box_rows, box_cols]
+int make_map_f32(CUtensorMap* tm, const float* basep, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                 int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)basep, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cgr_set_error("cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r); return CGR_ERR_ARG; }
+  return CGR_OK;
+}
+
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 struct WLayout {                 // prepared-weight buffer: [amax | unscale | bias_cat | matrices (hi, lo)...]
@@ -651,7 +405,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CGR_CHECK_ARG(!saved, "tcgen05 engine: the training (activation-saving) forward is not available yet; use engine simt");
   CGR_CHECK_ARG(g->tile_info && g->n_tiles > 0, "tcgen05 engine needs a tile plan (reactions of <= 128 bonds)");
-  CGR_CHECK_ARG(p->hidden % 2 == 0, "tcgen05 engine needs an even hidden size");
+  CGR_CHECK_ARG(p->hidden % 4 == 0, "tcgen05 engine needs a hidden size that is a multiple of 4");
   CGR_CHECK_ARG(p->depth + 3 <= MAX_SEG, "tcgen05 engine supports depth <= %d", MAX_SEG - 3);
   const bool need_w = p->tc_weights == nullptr;
   const TcWs w = tc_ws(p, g, need_w);
@@ -733,7 +487,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.tile_info = g->tile_info;
     prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
     prm.skip = p->use_skip ? p->skip[l] : nullptr;
-    prm.h0 = h0;
+    if ((rc = make_map_f32(&prm.tmR, h0, w.rows_pad, H, H, BN, TM))) return rc;
+    prm.r_col0 = 0;
     prm.act = p->act;
     prm.dropout_p = (training && p->host_dropout_p) ? p->host_dropout_p[l] : 0.f;
     prm.seed = seed; prm.layer = (uint32_t)l;
@@ -757,7 +512,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.tile_info = g->tile_info;
     prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
     prm.act = p->act;
-    prm.Q = PQ + H; prm.ldq = 2 * H;
+    if ((rc = make_map_f32(&prm.tmR, PQ, N, 2 * H, 2 * H, BN, TM))) return rc;
+    prm.r_col0 = H;
     prm.w_ffn = p->w_ffn;
     prm.partial_out = partial;
     prm.n_rxn = B;

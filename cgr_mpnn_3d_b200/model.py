@@ -123,11 +123,11 @@ class GNN(nn.Module):
         e = getattr(self, "engine", "auto")
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
-        can_tc = (not needs_saved) and self.hidden_sizes[0] % 2 == 0 and self.depth <= 13 and plan.ensure_tiles()
+        can_tc = (not needs_saved) and self.hidden_sizes[0] % 4 == 0 and self.depth <= 13 and plan.ensure_tiles()
         if e in ("tc", 1):
             if not can_tc:
-                raise RuntimeError("engine='tc' needs an inference forward (no grad, no dropout), an even hidden "
-                                   "size and reactions of at most 128 directed bonds")
+                raise RuntimeError("engine='tc' needs an inference forward (no grad, no dropout), a hidden "
+                                   "size divisible by 4 and reactions of at most 128 directed bonds")
             return _lib.ENGINE_TC
         return _lib.ENGINE_TC if can_tc else _lib.ENGINE_SIMT
 
