@@ -84,6 +84,7 @@ PROTOTYPES = {
                                    C.POINTER(CgrGrads), C.c_uint64, _I32, _V, _SZ, _V]),
     "cgr_tc_plan_build": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
     "cgr_tc_plan_check": (C.c_int, [_V, _I64, _V, _V, _V, _V]),
+    "cgr_tc_debug_buffer": (C.c_int, [_V]),
     "cgr_tc_weights_bytes": (_SZ, [C.POINTER(CgrParams)]),
     "cgr_tc_prepare_weights": (C.c_int, [C.POINTER(CgrParams), _V, _SZ, _V]),
     "cgr_tc_linear_workspace": (_SZ, [_I64, _I64, _I64]),

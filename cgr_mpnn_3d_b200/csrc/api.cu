@@ -404,6 +404,7 @@ extern "C" int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, cons
   CGR_CHECK_ARG(tile_info && src && dst && status, "cgr_tc_plan_check: null pointer");
   return tc_plan_check(tile_info, n_tiles, src, dst, status, (cudaStream_t)stream);
 }
+extern "C" int cgr_tc_debug_buffer(void* p) { tc_set_debug_buffer((long long*)p); return CGR_OK; }
 extern "C" size_t cgr_tc_weights_bytes(const cgr_params_t* p) { return p ? tc_weights_bytes(p) : 0; }
 extern "C" int cgr_tc_prepare_weights(const cgr_params_t* p, void* buffer, size_t buffer_bytes, void* stream) {
   int rc = check_params(p);

@@ -294,23 +294,48 @@ WLayout wlayout(const cgr_params_t* p) {
   return w;
 }
 
-template <int EPI>
-int launch_gemm(const TcGemmParams& prm, int m_tiles, int n_slices, const char* name, cudaStream_t st) {
+template <int BN, int EPI, bool RELU>
+int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char* name, cudaStream_t st) {
+  using C = Cfg<BN, EPI>;
   static bool attr_done = false;      // benign race: the attribute is idempotent
   if (!attr_done) {
-    CGR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CGR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
     attr_done = true;
   }
   CgrRange prof(name, st);
   cgr_note_launch(name, st, 1);
-  tc_gemm_kernel<EPI><<<dim3((unsigned)m_tiles, (unsigned)n_slices), THREADS, SMEM_BYTES, st>>>(prm);
+  tc_gemm_kernel<BN, EPI, RELU><<<dim3((unsigned)n_slices, (unsigned)m_tiles), THREADS, C::SMEM_BYTES, st>>>(prm);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
+}
+
+constexpr int BN_SMALL = 80, BN_LARGE = 208;
+
+// Slice width: wide slices (208) amortise the A-operand fetch of the SS-mode MMA and halve the A re-reads;
+// narrow slices (80) give small batches enough CTAs to occupy the 148 SMs.
+int choose_bn(int64_t m_tiles, int64_t n_total) {
+  return m_tiles * cgr_ceil_div(n_total, BN_LARGE) >= 148 ? BN_LARGE : BN_SMALL;
+}
+int chunk_cols(int bn) { return bn > 128 ? bn / 2 : bn; }
+
+template <int EPI>
+int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const char* name, cudaStream_t st) {
+  const int n_slices = (int)cgr_ceil_div(prm.n_total, bn);
+  if (bn == BN_LARGE) {
+    return relu ? launch_gemm_t<BN_LARGE, EPI, true>(prm, m_tiles, n_slices, name, st)
+                : launch_gemm_t<BN_LARGE, EPI, false>(prm, m_tiles, n_slices, name, st);
+  }
+  return relu ? launch_gemm_t<BN_SMALL, EPI, true>(prm, m_tiles, n_slices, name, st)
+              : launch_gemm_t<BN_SMALL, EPI, false>(prm, m_tiles, n_slices, name, st);
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+
+static long long* g_tc_dbg = nullptr;   // debug: phase time stamps of the bond-layer kernel
+void tc_set_debug_buffer(long long* p) { g_tc_dbg = p; }
 
 size_t tc_weights_bytes(const cgr_params_t* p) { return wlayout(p).total; }
 
@@ -376,7 +401,7 @@ TcWs tc_ws(const cgr_params_t* p, const cgr_graph_t* g, bool need_w) {
   w.kp_x = round_up(p->fa, BK);
   w.kp_h = round_up(H, BK);
   w.rows_pad = T * TM;
-  w.n_slices = (int)cgr_ceil_div(H, BN);
+  w.n_slices = (int)cgr_ceil_div(H, BN_SMALL);   // upper bound over both slice widths
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += cgr_align_up(bytes, 1024); return o; };
   w.off_w = take(need_w ? tc_weights_bytes(p) : 0);
@@ -449,8 +474,9 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     memset(&prm, 0, sizeof(prm));
     if ((rc = make_map(&prm.tmA_hi, x_hi, N, fa, w.kp_x, TM))) return rc;
     if ((rc = make_map(&prm.tmA_lo, x_lo, N, fa, w.kp_x, TM))) return rc;
-    if ((rc = make_map(&prm.tmB_hi, w_hi(0), 2 * H, fa, wl.ld[0], BN))) return rc;
-    if ((rc = make_map(&prm.tmB_lo, w_lo(0), 2 * H, fa, wl.ld[0], BN))) return rc;
+    const int bn = choose_bn(cgr_ceil_div(N, TM), 2 * H);
+    if ((rc = make_map(&prm.tmB_hi, w_hi(0), 2 * H, fa, wl.ld[0], bn))) return rc;
+    if ((rc = make_map(&prm.tmB_lo, w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     prm.num_k = (int)cgr_ceil_div(fa, BK);
     prm.n_total = 2 * H;
     prm.m_rows = (int)N;
@@ -458,7 +484,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.bias = bias_cat;
     prm.out_f32 = PQ;
     prm.ldc = 2 * H;
-    rc = launch_gemm<EPI_PLAIN>(prm, (int)cgr_ceil_div(N, TM), (int)cgr_ceil_div(2 * H, BN), "tc_atom_proj", st);
+    rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", st);
     if (rc) return rc;
   }
   // 3. edge initialisation on tile-packed rows
@@ -472,14 +498,16 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     CGR_LAUNCH_CHECK();
   }
   // 4. message passing layers: one fused kernel each
+  const int bn_h = choose_bn(T, H);
+  const bool relu = p->act == CGR_ACT_RELU;
   for (int l = 0; l < d; ++l) {
     TcGemmParams prm;
     memset(&prm, 0, sizeof(prm));
     const int in = l & 1, ob = in ^ 1;
     if ((rc = make_map(&prm.tmA_hi, h_hi[in], w.rows_pad, H, w.kp_h, TM))) return rc;
     if ((rc = make_map(&prm.tmA_lo, h_lo[in], w.rows_pad, H, w.kp_h, TM))) return rc;
-    if ((rc = make_map(&prm.tmB_hi, w_hi(1 + l), H, H, wl.ld[1 + l], BN))) return rc;
-    if ((rc = make_map(&prm.tmB_lo, w_lo(1 + l), H, H, wl.ld[1 + l], BN))) return rc;
+    if ((rc = make_map(&prm.tmB_hi, w_hi(1 + l), H, H, wl.ld[1 + l], bn_h))) return rc;
+    if ((rc = make_map(&prm.tmB_lo, w_lo(1 + l), H, H, wl.ld[1 + l], bn_h))) return rc;
     prm.num_k = (int)cgr_ceil_div(H, BK);
     prm.n_total = H;
     prm.unscale = unscale + 1 + l;
@@ -487,14 +515,15 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.tile_info = g->tile_info;
     prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
     prm.skip = p->use_skip ? p->skip[l] : nullptr;
-    if ((rc = make_map_f32(&prm.tmR, h0, w.rows_pad, H, H, BN, TM))) return rc;
+    if ((rc = make_map_f32(&prm.tmR, h0, w.rows_pad, H, H, chunk_cols(bn_h), TM))) return rc;
     prm.r_col0 = 0;
     prm.act = p->act;
     prm.dropout_p = (training && p->host_dropout_p) ? p->host_dropout_p[l] : 0.f;
     prm.seed = seed; prm.layer = (uint32_t)l;
     prm.o_hi = h_hi[ob]; prm.o_lo = h_lo[ob]; prm.ldo = w.kp_h;
     prm.overflow = flag;
-    rc = launch_gemm<EPI_BOND>(prm, (int)T, w.n_slices, "bond_layer", st);
+    prm.dbg = g_tc_dbg;
+    rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", st);
     if (rc) return rc;
   }
   // 5. readout + pooling + FFN
@@ -504,27 +533,28 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     const int in = d & 1;
     if ((rc = make_map(&prm.tmA_hi, h_hi[in], w.rows_pad, H, w.kp_h, TM))) return rc;
     if ((rc = make_map(&prm.tmA_lo, h_lo[in], w.rows_pad, H, w.kp_h, TM))) return rc;
-    if ((rc = make_map(&prm.tmB_hi, w_hi(d + 1), H, H, wl.ld[d + 1], BN))) return rc;
-    if ((rc = make_map(&prm.tmB_lo, w_lo(d + 1), H, H, wl.ld[d + 1], BN))) return rc;
+    if ((rc = make_map(&prm.tmB_hi, w_hi(d + 1), H, H, wl.ld[d + 1], bn_h))) return rc;
+    if ((rc = make_map(&prm.tmB_lo, w_lo(d + 1), H, H, wl.ld[d + 1], bn_h))) return rc;
     prm.num_k = (int)cgr_ceil_div(H, BK);
     prm.n_total = H;
     prm.unscale = unscale + d + 1;
     prm.tile_info = g->tile_info;
     prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
     prm.act = p->act;
-    if ((rc = make_map_f32(&prm.tmR, PQ, N, 2 * H, 2 * H, BN, TM))) return rc;
+    if ((rc = make_map_f32(&prm.tmR, PQ, N, 2 * H, 2 * H, chunk_cols(bn_h), TM))) return rc;
     prm.r_col0 = H;
     prm.w_ffn = p->w_ffn;
     prm.partial_out = partial;
     prm.n_rxn = B;
     prm.overflow = flag;
-    rc = launch_gemm<EPI_READOUT>(prm, (int)T, w.n_slices, "tc_readout", st);
+    rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", st);
     if (rc) return rc;
   }
   {
     CgrRange prof("tc_finalize", st);
     cgr_note_launch("tc_finalize", st, 1);
-    tc_finalize_kernel<<<(unsigned)cgr_ceil_div(B, 256), 256, 0, st>>>(partial, w.n_slices, B, p->b_ffn, out);
+    tc_finalize_kernel<<<(unsigned)cgr_ceil_div(B, 256), 256, 0, st>>>(partial, (int)cgr_ceil_div(H, bn_h), B,
+                                                                         p->b_ffn, out);
     CGR_LAUNCH_CHECK();
   }
   if (g->tc_status) {      // sticky overflow report for the caller (checked lazily on the host)
@@ -567,8 +597,9 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   int rc;
   if ((rc = make_map(&prm.tmA_hi, a_hi, M, K, kp, TM))) return rc;
   if ((rc = make_map(&prm.tmA_lo, a_lo, M, K, kp, TM))) return rc;
-  if ((rc = make_map(&prm.tmB_hi, b_hi, N, K, kp, BN))) return rc;
-  if ((rc = make_map(&prm.tmB_lo, b_lo, N, K, kp, BN))) return rc;
+  const int bn = choose_bn(cgr_ceil_div(M, TM), N);
+  if ((rc = make_map(&prm.tmB_hi, b_hi, N, K, kp, bn))) return rc;
+  if ((rc = make_map(&prm.tmB_lo, b_lo, N, K, kp, bn))) return rc;
   prm.num_k = (int)cgr_ceil_div(K, BK);
   prm.n_total = (int)N;
   prm.m_rows = (int)M;
@@ -576,5 +607,5 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   prm.bias = bias;
   prm.out_f32 = out;
   prm.ldc = N;
-  return launch_gemm<EPI_PLAIN>(prm, (int)cgr_ceil_div(M, TM), (int)cgr_ceil_div(N, BN), "tc_linear", st);
+  return launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(M, TM), true, "tc_linear", st);
 }

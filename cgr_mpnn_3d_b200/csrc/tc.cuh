@@ -17,3 +17,4 @@ int tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src,
 size_t tc_linear_workspace(int64_t M, int64_t N, int64_t K);
 int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wgt, int64_t N, int64_t ldw,
               const float* bias, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+void tc_set_debug_buffer(long long* p);

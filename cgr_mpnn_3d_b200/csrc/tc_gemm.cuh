@@ -1,5 +1,10 @@
 // The fused tcgen05 kernel of the tensor-core engine: TMA-fed FP16x3 GEMM of one 128-row tile with the
 // accumulator in TMEM, followed by a shared-memory epilogue (plain / directed-bond gather / readout).
+//
+// Measured on B200 (tools/tc_phase_timing.py): an SS-mode tcgen05.mma with M=128, N=80 costs ~97 cycles
+// (operand fetch from shared memory, not the 40-cycle math), so wide slices amortise the A-operand fetch:
+// the kernel is templated on the slice width BN (80 for small batches that need many CTAs, 208 for large
+// batches) and the epilogue walks the slice in column chunks of <= 128.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -8,27 +13,39 @@ namespace tcg {
 
 constexpr int TM = 128;                 // rows of a tile (UMMA M)
 constexpr int BK = 64;                  // fp16 elements per k-chunk = one 128-byte swizzle row
-constexpr int BN = 80;                  // output columns per CTA (UMMA N), multiple of 16
-constexpr int BNP = BN + 4;             // padded row of the fp32 staging tiles (conflict-free float4 rows)
-constexpr int STAGES = 3;
 constexpr int A_BYTES = TM * BK * 2;    // 16 KB
-constexpr int B_BYTES = BN * BK * 2;    // 10 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-constexpr int R_BYTES = TM * BN * 4;    // prefetched fp32 operand of the epilogue (h0 slice / Q slice), dense rows
-constexpr int TMEM_COLS = 128;          // power of two >= BN
 constexpr int THREADS = 256;
 constexpr int NWARPS = THREADS / 32;
 constexpr int AUX_BYTES = 2048;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + R_BYTES + AUX_BYTES + 1024;   // + alignment slack
-constexpr int VL = BN / 4;              // lanes that own a float4 column group in the epilogue (20)
-static_assert(2 * TM * BNP * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
-static_assert(BN % 16 == 0 && VL <= 32, "BN must be a multiple of 16 and at most 128");
+constexpr int SMEM_LIMIT = 232448;      // 227 KB opt-in maximum per CTA
+constexpr int RU = 4;                   // rows processed together by a warp in the epilogue (ILP)
 
 enum { EPI_PLAIN = 0, EPI_BOND = 1, EPI_READOUT = 2 };
 
+template <int BN_, int EPI>
+struct Cfg {
+  static constexpr int BN = BN_;                          // output columns per CTA (UMMA N), multiple of 16
+  static constexpr int NCH = BN > 128 ? 2 : 1;            // epilogue column chunks
+  static constexpr int CH = BN / NCH;                     // columns per chunk (80 / 104 / 128)
+  static constexpr int CHP = CH + 4;                      // padded fp32 staging row (conflict-free float4 rows)
+  static constexpr int VL = CH / 4;                       // lanes owning a float4 column group
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int R_BYTES = EPI == EPI_PLAIN ? 0 : TM * CH * 4;   // TMA-prefetched fp32 epilogue operand
+  static constexpr int Y_BYTES = ((TM * CHP * 4 + 127) / 128) * 128;
+  static constexpr int FIT = (SMEM_LIMIT - R_BYTES - AUX_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 4 ? 4 : FIT;
+  static constexpr int TMEM_COLS = BN <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + R_BYTES + AUX_BYTES + 1024;
+  static_assert(BN % 16 == 0 && BN <= 256 && CH % 4 == 0 && VL <= 32, "bad slice width");
+  static_assert(STAGES >= 2, "pipeline needs two stages");
+  static_assert(Y_BYTES + (NCH > 1 ? R_BYTES : 0) <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
+};
+
 struct TcGemmParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  CUtensorMap tmR;              // fp32 [rows, cols] operand prefetched for the epilogue (BOND: h0, READOUT: Q)
+  CUtensorMap tmR;              // fp32 [rows, cols] operand of the epilogue (BOND: h0, READOUT: Q), box = [128, CH]
   int num_k;                    // k-chunks of BK
   int n_total;                  // real output columns
   int m_rows;                   // real rows (EPI_PLAIN)
@@ -56,13 +73,14 @@ struct TcGemmParams {
   float* partial_out;           // [n_slices, B]
   int64_t n_rxn;
   int* overflow;                // sticky flag: an activation left the fp16 range
+  long long* dbg;               // optional [n_cta][8] clock64 stamps of the kernel phases (debug)
 };
 
 struct Aux {                    // small per-CTA shared state, lives after the pipeline buffers
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[4];
+  uint64_t empty[4];
   uint64_t tmem_full;
-  uint64_t r_full;
+  uint64_t r_full[2];
   uint32_t tmem_base;
   int32_t info[8];
   uint16_t ptr_l[TM + 2];       // local CSR offsets of the tile's atoms
@@ -76,20 +94,34 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
 }
-
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+template <bool RELU>
+__device__ __forceinline__ float act_t(float z, int act) { return RELU ? fmaxf(z, 0.f) : cgr_act(z, act); }
 
-template <int EPI>
+// RELU: compile-time fast path for the reference's default activation (branch-free epilogue)
+template <int BN_, int EPI, bool RELU>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+  using C = Cfg<BN_, EPI>;
+  constexpr int BN = C::BN, CH = C::CH, CHP = C::CHP, VL = C::VL, NCH = C::NCH, STAGES = C::STAGES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = umma::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  float* r_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [TM][BN] dense
-  Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES + R_BYTES);
+  float* r0_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);         // [TM][CH] dense, chunk 0
+  Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES + C::R_BYTES);
+  float* y_s = reinterpret_cast<float*>(smem);                                  // [TM][CHP], aliases the drained pipeline
+  float* r1_s = reinterpret_cast<float*>(smem + C::Y_BYTES);                    // [TM][CH], chunk 1 (alias)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, slice = blockIdx.y;
+  const int slice = blockIdx.x, tile = blockIdx.y;               // slices of one tile are neighbours: they share A in L2
   const int n0 = slice * BN;
+  // columns this slice really owns, rounded up to the MMA granularity (runtime N of the instruction)
+  int n_eff = p.n_total - n0;
+  n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
+  long long* dbg = p.dbg ? p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+#define TC_STAMP(k) do { if (dbg && threadIdx.x == 64) dbg[k] = clock64(); } while (0)
+  TC_STAMP(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -97,7 +129,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       umma::mbar_init(umma::smem_u32(&aux->empty[s]), 1);
     }
     umma::mbar_init(umma::smem_u32(&aux->tmem_full), 1);
-    umma::mbar_init(umma::smem_u32(&aux->r_full), 1);
+    umma::mbar_init(umma::smem_u32(&aux->r_full[0]), 1);
+    umma::mbar_init(umma::smem_u32(&aux->r_full[1]), 1);
     umma::mbar_fence_init();
     umma::tma_prefetch_desc(&p.tmA_hi);
     umma::tma_prefetch_desc(&p.tmA_lo);
@@ -106,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (EPI != EPI_PLAIN) umma::tma_prefetch_desc(&p.tmR);
   }
   if (warp == 1) {
-    umma::tmem_alloc(umma::smem_u32(&aux->tmem_base), TMEM_COLS);
+    umma::tmem_alloc(umma::smem_u32(&aux->tmem_base), C::TMEM_COLS);
     umma::tmem_relinquish();
   }
   if (EPI != EPI_PLAIN && threadIdx.x >= 64 && threadIdx.x < 72)
@@ -115,16 +148,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem = aux->tmem_base;
+  const int r_row0 = EPI == EPI_BOND ? tile * TM : (EPI == EPI_READOUT ? aux->info[2] : 0);
+  TC_STAMP(1);
 
   // ------------------------------------------------------------------ main loop (warp-specialised)
   if (warp == 0) {
     // TMA producer: one elected lane streams A (hi, lo) and B (hi, lo) k-chunks through the ring and
-    // prefetches the epilogue's fp32 operand tile
+    // prefetches the first column chunk of the epilogue's fp32 operand
     if (lane == 0 && EPI != EPI_PLAIN) {
-      const uint32_t rb = umma::smem_u32(&aux->r_full);
-      umma::mbar_arrive_expect_tx(rb, R_BYTES);
-      const int row0 = EPI == EPI_BOND ? tile * TM : aux->info[2];
-      umma::tma_load_2d(&p.tmR, rb, umma::smem_u32(r_s), p.r_col0 + n0, row0);
+      const uint32_t rb = umma::smem_u32(&aux->r_full[0]);
+      umma::mbar_arrive_expect_tx(rb, C::R_BYTES);
+      umma::tma_load_2d(&p.tmR, rb, umma::smem_u32(r0_s), p.r_col0 + n0, r_row0);
     }
     for (int kc = 0; kc < p.num_k; ++kc) {
       const int s = kc % STAGES;
@@ -143,13 +177,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // MMA issuer: one lane issues 3 tcgen05.mma per 16-wide k-step (lo.hi + hi.lo + hi.hi)
-    constexpr uint32_t idesc = umma::idesc_f16_f32(TM, BN);
+    const uint32_t idesc = umma::idesc_f16_f32(TM, n_eff);
     for (int kc = 0; kc < p.num_k; ++kc) {
       const int s = kc % STAGES;
       const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
       if (lane == 0) {
         umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
         umma::tc_fence_after_sync();
+        if (dbg && kc == 0) dbg[6] = clock64();
+        if (dbg && kc == p.num_k - 1) dbg[7] = clock64();
         const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
         const uint64_t da_hi = umma::smem_desc_k_sw128(st);
         const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
@@ -178,146 +214,188 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       aux->ptr_l[v] = (uint16_t)(__ldg(p.in_ptr + abase + v) - ebase);
   }
 
-  // per-lane column group of the epilogue: 4 consecutive columns, constant across rows
-  const int c = 4 * lane;
-  const bool lane_on = lane < VL && (n0 + c) < p.n_total;          // n_total is even; tails handled per element
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), wf4 = bias4;
-  if (lane < VL) {
-    const int n = n0 + c;
-    if (p.bias) {
-      bias4.x = n + 0 < p.n_total ? __ldg(p.bias + n + 0) : 0.f;
-      bias4.y = n + 1 < p.n_total ? __ldg(p.bias + n + 1) : 0.f;
-      bias4.z = n + 2 < p.n_total ? __ldg(p.bias + n + 2) : 0.f;
-      bias4.w = n + 3 < p.n_total ? __ldg(p.bias + n + 3) : 0.f;
-    }
-    if (EPI == EPI_READOUT) {
-      wf4.x = n + 0 < p.n_total ? __ldg(p.w_ffn + n + 0) : 0.f;
-      wf4.y = n + 1 < p.n_total ? __ldg(p.w_ffn + n + 1) : 0.f;
-      wf4.z = n + 2 < p.n_total ? __ldg(p.w_ffn + n + 2) : 0.f;
-      wf4.w = n + 3 < p.n_total ? __ldg(p.w_ffn + n + 3) : 0.f;
-    }
-  }
   const float us = __ldg(p.unscale);
   const float skip = (EPI == EPI_BOND && p.skip) ? __ldg(p.skip) : 1.f;
+  const int c = 4 * lane;                                         // this lane's float4 column group inside a chunk
 
   // ------------------------------------------------------------------ epilogue (all 8 warps)
   umma::mbar_wait(umma::smem_u32(&aux->tmem_full), 0);
   umma::tc_fence_after_sync();
-  float* y_s = reinterpret_cast<float*>(smem);                   // [TM][BNP], aliases the drained pipeline
-  float* a_s = y_s + TM * BNP;                                   // [TM][BNP]
-  {
-    const int q = warp & 3, half = warp >> 2;                    // TMEM lane quarter / column half
-    const int row = q * 32 + lane;
-    constexpr int COLS_PER_WARP = BN / 2;                        // 40
-    float v[COLS_PER_WARP];
+  TC_STAMP(2);
+  if (NCH > 1 && EPI != EPI_PLAIN && threadIdx.x == 0) {
+    // second column chunk of the fp32 operand goes into the drained pipeline buffers
+    const uint32_t rb = umma::smem_u32(&aux->r_full[1]);
+    umma::mbar_arrive_expect_tx(rb, C::R_BYTES);
+    umma::tma_load_2d(&p.tmR, rb, umma::smem_u32(r1_s), p.r_col0 + n0 + CH, r_row0);
+  }
+  if (EPI == EPI_READOUT) {
+    for (int v = threadIdx.x; v < TM; v += THREADS) aux->tat[v] = 0.f;
+  }
+  bool ovf = false;
+
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch > 0) __syncthreads();                                  // every reader of the previous y_s chunk is done
+    // TMEM -> registers -> y_s (fp32, unscaled); warp w owns lane quarter w%4 and every other 8-column group
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane;
 #pragma unroll
-    for (int cc = 0; cc < COLS_PER_WARP; cc += 8)
-      umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + cc), v + cc);
-    umma::tmem_ld_wait();
+      for (int cc = half * 8; cc < CH; cc += 16) {
+        float v[8];
+        umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CH + cc), v);
+        umma::tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
+        dst[0] = make_float4(v[0] * us, v[1] * us, v[2] * us, v[3] * us);
+        dst[1] = make_float4(v[4] * us, v[5] * us, v[6] * us, v[7] * us);
+      }
+    }
+    umma::tc_fence_before_sync();
+    if (EPI != EPI_PLAIN) umma::mbar_wait(umma::smem_u32(&aux->r_full[ch]), 0);   // fp32 operand chunk has landed
+    __syncthreads();
+    if (ch == 0) TC_STAMP(3);
+
+    const int n = n0 + ch * CH + c;                               // first global column of this lane's group
+    const bool lane_on = lane < VL && n < p.n_total;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), wf4 = bias4;
+    if (lane_on) {
+      if (p.bias) {
+        bias4.x = __ldg(p.bias + n);
+        bias4.y = n + 1 < p.n_total ? __ldg(p.bias + n + 1) : 0.f;
+        bias4.z = n + 2 < p.n_total ? __ldg(p.bias + n + 2) : 0.f;
+        bias4.w = n + 3 < p.n_total ? __ldg(p.bias + n + 3) : 0.f;
+      }
+      if (EPI == EPI_READOUT) {
+        wf4.x = __ldg(p.w_ffn + n);
+        wf4.y = n + 1 < p.n_total ? __ldg(p.w_ffn + n + 1) : 0.f;
+        wf4.z = n + 2 < p.n_total ? __ldg(p.w_ffn + n + 2) : 0.f;
+        wf4.w = n + 3 < p.n_total ? __ldg(p.w_ffn + n + 3) : 0.f;
+      }
+    }
+    const float* r_s = ch == 0 ? r0_s : r1_s;
+
+    if (EPI == EPI_PLAIN) {
+      // rows are dense (atoms): out = y + bias, written as coalesced rows
+      if (lane_on) {
+        for (int r = warp; r < TM; r += NWARPS) {
+          const int64_t row = (int64_t)tile * TM + r;
+          if (row >= p.m_rows) break;
+          const float4 y = ld4(y_s + r * CHP + c);
+          float* o = p.out_f32 + row * p.ldc + n;
+          if (n + 3 < p.n_total && (p.ldc & 3) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(y.x + bias4.x, y.y + bias4.y, y.z + bias4.z, y.w + bias4.w);
+          } else {
+            o[0] = y.x + bias4.x;
+            if (n + 1 < p.n_total) o[1] = y.y + bias4.y;
+            if (n + 2 < p.n_total) o[2] = y.z + bias4.z;
+            if (n + 3 < p.n_total) o[3] = y.w + bias4.w;
+          }
+        }
+      }
+    } else if (EPI == EPI_BOND) {
+      // z[e] = sum_{k in in(src e)} y[k] - y[e^1] + b + skip*h0[e];  h' = dropout(act(z)); RU rows per warp step
+      const int ebase = aux->info[0], ecount = aux->info[1];
+      const int H = p.n_total;
+      const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+      for (int j0 = warp * RU; j0 < ecount; j0 += NWARPS * RU) {
+        int pb[RU], deg[RU], maxdeg = 0;
 #pragma unroll
-    for (int cc = 0; cc < COLS_PER_WARP; cc += 4) {
-      float4* dst = reinterpret_cast<float4*>(y_s + row * BNP + half * COLS_PER_WARP + cc);
-      *dst = make_float4(v[cc] * us, v[cc + 1] * us, v[cc + 2] * us, v[cc + 3] * us);
+        for (int u = 0; u < RU; ++u) {
+          const int j = j0 + u;
+          const int s = j < ecount ? (int)aux->src_l[j] : 0;
+          pb[u] = aux->ptr_l[s];
+          deg[u] = j < ecount ? (int)aux->ptr_l[s + 1] - pb[u] : 0;
+          maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
+        }
+        if (lane_on) {
+          float4 acc[RU];
+#pragma unroll
+          for (int u = 0; u < RU; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t = 0; t < maxdeg; ++t) {                      // ascending bond id: the reference's order
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+              if (t < deg[u]) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb[u] + t] * CHP + c));
+          }
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            const int j = j0 + u;
+            if (j >= ecount) break;
+            const int64_t r = (int64_t)tile * TM + j;
+            const float4 yr = ld4(y_s + (j ^ 1) * CHP + c);
+            const float4 h0v = ld4(r_s + j * CH + c);
+            float z[4] = {acc[u].x - yr.x + bias4.x + skip * h0v.x, acc[u].y - yr.y + bias4.y + skip * h0v.y,
+                          acc[u].z - yr.z + bias4.z + skip * h0v.z, acc[u].w - yr.w + bias4.w + skip * h0v.w};
+            __half hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float v = act_t<RELU>(z[i], p.act);
+              if (p.dropout_p > 0.f)
+                v = cgr_dropout_keep(p.seed, p.layer, (uint64_t)(ebase + j) * (uint64_t)H + (uint64_t)(n + i),
+                                     p.dropout_p) ? v * keep_scale : 0.f;
+              if (n + i >= H) v = 0.f;                            // K padding of the next operand
+              ovf |= fabsf(v) > 60000.f;
+              split_f16(v, hi[i], lo[i]);
+            }
+            uint2 ph, pl;
+            ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+            ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+            pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+            pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+            *reinterpret_cast<uint2*>(p.o_hi + r * p.ldo + n) = ph;
+            *reinterpret_cast<uint2*>(p.o_lo + r * p.ldo + n) = pl;
+          }
+        }
+      }
+    } else {
+      // readout: hv[v] = act(Q[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
+      const int acount = aux->info[3];
+      for (int v0 = warp * RU; v0 < acount; v0 += NWARPS * RU) {
+        int pb[RU], deg[RU], maxdeg = 0;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          const int v = v0 + u;
+          pb[u] = aux->ptr_l[v < acount ? v : 0];
+          deg[u] = v < acount ? (int)aux->ptr_l[v + 1] - pb[u] : 0;
+          maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
+        }
+        float t[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) t[u] = 0.f;
+        if (lane_on) {
+          float4 acc[RU];
+#pragma unroll
+          for (int u = 0; u < RU; ++u) acc[u] = v0 + u < acount ? ld4(r_s + (v0 + u) * CH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < maxdeg; ++k) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+              if (k < deg[u]) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb[u] + k] * CHP + c));
+          }
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            t[u] = act_t<RELU>(acc[u].x, p.act) * wf4.x;
+            t[u] = fmaf(act_t<RELU>(acc[u].y, p.act), wf4.y, t[u]);
+            t[u] = fmaf(act_t<RELU>(acc[u].z, p.act), wf4.z, t[u]);
+            t[u] = fmaf(act_t<RELU>(acc[u].w, p.act), wf4.w, t[u]);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < RU; ++u) t[u] += __shfl_xor_sync(0xffffffffu, t[u], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < RU; ++u)
+            if (v0 + u < acount) aux->tat[v0 + u] += t[u];       // the same warp owns atom v in every chunk
+        }
+      }
     }
   }
-  umma::tc_fence_before_sync();
-  __syncthreads();
 
-  if (EPI == EPI_PLAIN) {
-    // rows are dense (atoms): out = y + bias, written as coalesced rows
-    if (lane < VL) {
-      const int n = n0 + c;
-      for (int r = warp; r < TM; r += NWARPS) {
-        const int64_t row = (int64_t)tile * TM + r;
-        if (row >= p.m_rows) break;
-        const float4 y = ld4(y_s + r * BNP + c);
-        float* o = p.out_f32 + row * p.ldc + n;
-        if (n + 3 < p.n_total && (p.ldc & 3) == 0) {
-          *reinterpret_cast<float4*>(o) = make_float4(y.x + bias4.x, y.y + bias4.y, y.z + bias4.z, y.w + bias4.w);
-        } else {
-          if (n + 0 < p.n_total) o[0] = y.x + bias4.x;
-          if (n + 1 < p.n_total) o[1] = y.y + bias4.y;
-          if (n + 2 < p.n_total) o[2] = y.z + bias4.z;
-          if (n + 3 < p.n_total) o[3] = y.w + bias4.w;
-        }
-      }
-    }
-  } else if (EPI == EPI_BOND) {
-    const int ebase = aux->info[0], ecount = aux->info[1], acount = aux->info[3];
-    // a[v] = sum_{k in in(v)} y[k]   (ascending bond id, the reference's accumulation order)
-    if (lane < VL) {
-      for (int v = warp; v < acount; v += NWARPS) {
-        const int pb = aux->ptr_l[v], pe = aux->ptr_l[v + 1];
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = pb; q < pe; ++q) {
-          const float4 t = ld4(y_s + (int)aux->idx_l[q] * BNP + c);
-          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-        }
-        *reinterpret_cast<float4*>(a_s + v * BNP + c) = a;
-      }
-    }
-    umma::mbar_wait(umma::smem_u32(&aux->r_full), 0);              // h0 slice has landed (TMA)
+  if (EPI == EPI_BOND && ovf) atomicOr(p.overflow, 1);
+  if (EPI == EPI_READOUT) {
     __syncthreads();
-    const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-    const int H = p.n_total;
-    bool ovf = false;
-    // z[e] = a[src e] - y[e^1] + b + skip*h0[e];  h' = dropout(act(z));  written as the FP16 (hi, lo) operand
-    if (lane_on) {
-      const int n = n0 + c;
-#pragma unroll 2
-      for (int j = warp; j < ecount; j += NWARPS) {
-        const int64_t r = (int64_t)tile * TM + j;
-        const float4 av = ld4(a_s + (int)aux->src_l[j] * BNP + c);
-        const float4 yr = ld4(y_s + (j ^ 1) * BNP + c);
-        const float4 h0v = ld4(r_s + j * BN + c);
-        float z[4] = {av.x - yr.x + bias4.x + skip * h0v.x, av.y - yr.y + bias4.y + skip * h0v.y,
-                      av.z - yr.z + bias4.z + skip * h0v.z, av.w - yr.w + bias4.w + skip * h0v.w};
-        __half hi[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v = cgr_act(z[i], p.act);
-          if (p.dropout_p > 0.f)
-            v = cgr_dropout_keep(p.seed, p.layer, (uint64_t)(ebase + j) * (uint64_t)H + (uint64_t)(n + i), p.dropout_p)
-                    ? v * keep_scale : 0.f;
-          if (n + i >= H) v = 0.f;
-          ovf |= fabsf(v) > 60000.f;
-          split_f16(v, hi[i], lo[i]);
-        }
-        // columns beyond H inside the last 4-group fall in the operand's K padding (never read back: the
-        // tensor map's extent is H) -- ldo >= round_up(H, 64)
-        uint2 ph, pl;
-        ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
-        ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
-        pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
-        pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
-        *reinterpret_cast<uint2*>(p.o_hi + r * p.ldo + n) = ph;
-        *reinterpret_cast<uint2*>(p.o_lo + r * p.ldo + n) = pl;
-      }
-    }
-    if (ovf) atomicOr(p.overflow, 1);
-  } else {
-    // readout: hv[v] = act(Q[v] + sum_{k in in(v)} y[k]);  t[v] = hv[v] . w_f (this CTA's columns)
-    const int abase = aux->info[2], acount = aux->info[3], rx0 = aux->info[4], rxcount = aux->info[5];
-    umma::mbar_wait(umma::smem_u32(&aux->r_full), 0);              // Q slice has landed (TMA)
-    for (int v = warp; v < acount; v += NWARPS) {
-      float t = 0.f;
-      if (lane_on) {
-        const int pb = aux->ptr_l[v], pe = aux->ptr_l[v + 1];
-        float4 a = ld4(r_s + v * BN + c);
-        for (int q = pb; q < pe; ++q) {
-          const float4 y = ld4(y_s + (int)aux->idx_l[q] * BNP + c);
-          a.x += y.x; a.y += y.y; a.z += y.z; a.w += y.w;
-        }
-        t = cgr_act(a.x, p.act) * wf4.x;
-        t = fmaf(cgr_act(a.y, p.act), wf4.y, t);
-        t = fmaf(cgr_act(a.z, p.act), wf4.z, t);
-        t = fmaf(cgr_act(a.w, p.act), wf4.w, t);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) aux->tat[v] = t;
-    }
-    __syncthreads();
+    const int abase = aux->info[2], rx0 = aux->info[4], rxcount = aux->info[5];
     for (int rx = threadIdx.x; rx < rxcount; rx += THREADS) {
       const int b = rx0 + rx;
       const int v0 = __ldg(p.atom_ptr + b) - abase, v1 = __ldg(p.atom_ptr + b + 1) - abase;
@@ -328,7 +406,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   }
 
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, TMEM_COLS);
+  TC_STAMP(5);
+  if (warp == 1) umma::tmem_dealloc(tmem, C::TMEM_COLS);
+#undef TC_STAMP
 }
 
 }  // namespace tcg

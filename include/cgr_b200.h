@@ -193,6 +193,8 @@ int cgr_tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, int64_t n_
                       int32_t* status, void* stream);
 int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst,
                       int32_t* status, void* stream);
+/* Debug: device buffer [n_cta][8] of int64 receiving clock64 stamps of the bond-layer kernel phases (NULL = off). */
+int cgr_tc_debug_buffer(void* device_buffer);
 size_t cgr_tc_weights_bytes(const cgr_params_t* p);
 int cgr_tc_prepare_weights(const cgr_params_t* p, void* buffer, size_t buffer_bytes, void* stream);
 /* Test entry: out[M,N] = x[M,K] w[N,K]^T + bias (bias may be NULL) on the TMA + tcgen05 FP16x3 pipeline. */
