@@ -14,11 +14,12 @@ namespace tcg {
 constexpr int TM = 128;                 // rows of a tile (UMMA M)
 constexpr int BK = 64;                  // fp16 elements per k-chunk = one 128-byte swizzle row
 constexpr int A_BYTES = TM * BK * 2;    // 16 KB
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;           // 16 warps: 1 TMA, 1 MMA, 14 staging; all 16 run the epilogue
 constexpr int NWARPS = THREADS / 32;
-constexpr int AUX_BYTES = 2048;
+constexpr int AUX_BYTES = 4096;
 constexpr int SMEM_LIMIT = 232448;      // 227 KB opt-in maximum per CTA
 constexpr int RU = 4;                   // rows processed together by a warp in the epilogue (ILP)
+constexpr int NBR = 8;                  // neighbour slots per row kept in the packed descriptor
 
 enum { EPI_PLAIN = 0, EPI_BOND = 1, EPI_READOUT = 2 };
 
@@ -87,6 +88,10 @@ struct Aux {                    // small per-CTA shared state, lives after the p
   uint8_t src_l[TM];            // local source atom of each bond row
   uint8_t idx_l[TM];            // local bond ids grouped by target atom
   float tat[TM];                // readout: per-atom dot with w_ffn
+  // per epilogue row (BOND: bond j -> in-bonds of src(j); READOUT: atom v -> in-bonds of v):
+  uint2 nbr[TM];                // first NBR neighbour rows, one byte each
+  uint16_t nbr_pb[TM];          // CSR offset of the row's neighbour list (for degrees > NBR)
+  uint8_t nbr_deg[TM];          // its length
 };
 static_assert(sizeof(Aux) <= AUX_BYTES, "Aux too large");
 
@@ -212,6 +217,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     }
     for (int v = threadIdx.x - 64; v <= acount; v += THREADS - 64)
       aux->ptr_l[v] = (uint16_t)(__ldg(p.in_ptr + abase + v) - ebase);
+    // packed neighbour descriptor of every epilogue row, read straight from the CSR (L2 hits, hidden
+    // behind the GEMM): one 8-byte word + degree instead of a chain of dependent shared-memory loads
+    const int nrows = EPI == EPI_BOND ? ecount : acount;
+    for (int r = threadIdx.x - 64; r < nrows; r += THREADS - 64) {
+      const int a = EPI == EPI_BOND ? __ldg(p.src + ebase + r) : abase + r;
+      const int pb = __ldg(p.in_ptr + a), pe = __ldg(p.in_ptr + a + 1);
+      uint32_t w[2] = {0u, 0u};
+      for (int t = 0; t < NBR && pb + t < pe; ++t)
+        w[t >> 2] |= (uint32_t)((__ldg(p.in_idx + pb + t) - ebase) & 0xff) << (8 * (t & 3));
+      aux->nbr[r] = make_uint2(w[0], w[1]);
+      aux->nbr_pb[r] = (uint16_t)(pb - ebase);
+      aux->nbr_deg[r] = (uint8_t)(pe - pb > 255 ? 255 : pe - pb);
+    }
   }
 
   const float us = __ldg(p.unscale);
@@ -238,10 +256,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (ch > 0) __syncthreads();                                  // every reader of the previous y_s chunk is done
     // TMEM -> registers -> y_s (fp32, unscaled); warp w owns lane quarter w%4 and every other 8-column group
     {
-      const int q = warp & 3, half = warp >> 2;
+      const int q = warp & 3, grp = warp >> 2;
       const int row = q * 32 + lane;
 #pragma unroll
-      for (int cc = half * 8; cc < CH; cc += 16) {
+      for (int cc = grp * 8; cc < CH; cc += 8 * (NWARPS / 4)) {
         float v[8];
         umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CH + cc), v);
         umma::tmem_ld_wait();
@@ -298,23 +316,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       const int H = p.n_total;
       const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
       for (int j0 = warp * RU; j0 < ecount; j0 += NWARPS * RU) {
-        int pb[RU], deg[RU], maxdeg = 0;
+        uint2 nb[RU];
+        int deg[RU], maxdeg = 0;
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-          const int j = j0 + u;
-          const int s = j < ecount ? (int)aux->src_l[j] : 0;
-          pb[u] = aux->ptr_l[s];
-          deg[u] = j < ecount ? (int)aux->ptr_l[s + 1] - pb[u] : 0;
+          const int j = j0 + u < ecount ? j0 + u : j0;
+          nb[u] = aux->nbr[j];
+          deg[u] = j0 + u < ecount ? (int)aux->nbr_deg[j] : 0;
           maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
         }
         if (lane_on) {
           float4 acc[RU];
 #pragma unroll
           for (int u = 0; u < RU; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int t = 0; t < maxdeg; ++t) {                      // ascending bond id: the reference's order
+          const int fast = maxdeg < NBR ? maxdeg : NBR;
+          for (int t = 0; t < fast; ++t) {                        // ascending bond id: the reference's order
 #pragma unroll
-            for (int u = 0; u < RU; ++u)
-              if (t < deg[u]) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb[u] + t] * CHP + c));
+            for (int u = 0; u < RU; ++u) {
+              const uint32_t w = t < 4 ? nb[u].x : nb[u].y;
+              const int k = (int)((w >> (8 * (t & 3))) & 0xffu);
+              if (t < deg[u]) add4(acc[u], ld4(y_s + k * CHP + c));
+            }
+          }
+          if (maxdeg > NBR) {                                     // rare: atoms with more than NBR bonds
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+              if (j0 + u >= ecount) break;
+              const int pb = aux->nbr_pb[j0 + u];
+              for (int t = NBR; t < deg[u]; ++t) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb + t] * CHP + c));
+            }
           }
 #pragma unroll
           for (int u = 0; u < RU; ++u) {
@@ -325,7 +355,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const float4 h0v = ld4(r_s + j * CH + c);
             float z[4] = {acc[u].x - yr.x + bias4.x + skip * h0v.x, acc[u].y - yr.y + bias4.y + skip * h0v.y,
                           acc[u].z - yr.z + bias4.z + skip * h0v.z, acc[u].w - yr.w + bias4.w + skip * h0v.w};
-            __half hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float v = act_t<RELU>(z[i], p.act);
@@ -333,14 +362,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 v = cgr_dropout_keep(p.seed, p.layer, (uint64_t)(ebase + j) * (uint64_t)H + (uint64_t)(n + i),
                                      p.dropout_p) ? v * keep_scale : 0.f;
               if (n + i >= H) v = 0.f;                            // K padding of the next operand
-              ovf |= fabsf(v) > 60000.f;
-              split_f16(v, hi[i], lo[i]);
+              z[i] = v;
             }
+            ovf |= fmaxf(fmaxf(fabsf(z[0]), fabsf(z[1])), fmaxf(fabsf(z[2]), fabsf(z[3]))) > 60000.f;
+            // FP16 (hi, lo) split with packed conversions: hi = rn(v), lo = rn(v - hi)
+            const __half2 hi01 = __floats2half2_rn(z[0], z[1]), hi23 = __floats2half2_rn(z[2], z[3]);
+            const float2 f01 = __half22float2(hi01), f23 = __half22float2(hi23);
+            const __half2 lo01 = __floats2half2_rn(z[0] - f01.x, z[1] - f01.y);
+            const __half2 lo23 = __floats2half2_rn(z[2] - f23.x, z[3] - f23.y);
             uint2 ph, pl;
-            ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
-            ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
-            pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
-            pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+            ph.x = *reinterpret_cast<const uint32_t*>(&hi01);
+            ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
+            pl.x = *reinterpret_cast<const uint32_t*>(&lo01);
+            pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
             *reinterpret_cast<uint2*>(p.o_hi + r * p.ldo + n) = ph;
             *reinterpret_cast<uint2*>(p.o_lo + r * p.ldo + n) = pl;
           }
@@ -350,12 +384,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       // readout: hv[v] = act(Q[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
       const int acount = aux->info[3];
       for (int v0 = warp * RU; v0 < acount; v0 += NWARPS * RU) {
-        int pb[RU], deg[RU], maxdeg = 0;
+        uint2 nb[RU];
+        int deg[RU], maxdeg = 0;
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-          const int v = v0 + u;
-          pb[u] = aux->ptr_l[v < acount ? v : 0];
-          deg[u] = v < acount ? (int)aux->ptr_l[v + 1] - pb[u] : 0;
+          const int v = v0 + u < acount ? v0 + u : v0;
+          nb[u] = aux->nbr[v];
+          deg[u] = v0 + u < acount ? (int)aux->nbr_deg[v] : 0;
           maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
         }
         float t[RU];
@@ -365,10 +400,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           float4 acc[RU];
 #pragma unroll
           for (int u = 0; u < RU; ++u) acc[u] = v0 + u < acount ? ld4(r_s + (v0 + u) * CH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int k = 0; k < maxdeg; ++k) {
+          const int fast = maxdeg < NBR ? maxdeg : NBR;
+          for (int k = 0; k < fast; ++k) {
 #pragma unroll
-            for (int u = 0; u < RU; ++u)
-              if (k < deg[u]) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb[u] + k] * CHP + c));
+            for (int u = 0; u < RU; ++u) {
+              const uint32_t w = k < 4 ? nb[u].x : nb[u].y;
+              const int row = (int)((w >> (8 * (k & 3))) & 0xffu);
+              if (k < deg[u]) add4(acc[u], ld4(y_s + row * CHP + c));
+            }
+          }
+          if (maxdeg > NBR) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+              if (v0 + u >= acount) break;
+              const int pb = aux->nbr_pb[v0 + u];
+              for (int k = NBR; k < deg[u]; ++k) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb + k] * CHP + c));
+            }
           }
 #pragma unroll
           for (int u = 0; u < RU; ++u) {
