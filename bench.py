@@ -35,7 +35,7 @@ L2_BYTES = 126e6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default=os.environ.get("CGR_ENGINE", "auto"))
@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent steps are pipelined over")
     ap.add_argument("--train", action="store_true", help="also time the training step (fwd+loss+bwd[+allreduce])")
     return ap.parse_args()
 
@@ -70,7 +71,8 @@ def bond_update_bytes(n, e, h=HID, s=4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons streamed (-lms) while the GPU legs run (B200_PROFILING.md);
+    samples carry a host timestamp so the ones inside the timed region can be told apart."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -79,43 +81,69 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self.proc = None
         self._t = None
+        self.t_begin = self.t_end = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        try:
+            for line in self.proc.stdout:
+                cols = [c.strip() for c in line.strip().split(",")]
+                if len(cols) >= 7:
+                    self.rows.append((time.perf_counter(), cols))
+        except Exception:
+            pass
 
-    def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
         return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        if self._t is not None:
+            self._t.join(timeout=5)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0])); mx.append(float(r[1]))
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        timed = [x for x in self.rows if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30)]
+        window = "timed region"
+        if len(timed) < 3:      # timed region shorter than the sampler period: use every sample of the GPU-busy legs
+            timed, window = self.rows, "all GPU legs of this run (timed region shorter than the sampling period)"
+        sm, mx, reasons = parse(timed)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def build_model(engine: str, device):
@@ -236,23 +264,53 @@ def main():
             model(pool[0])
             launches_per_step = lib.cgr_launch_count() - c0
 
-        def step(i):
+        n_streams = max(1, args.streams) if graphs is not None else 1
+        while n_pool % n_streams:          # a graph must always replay on the same stream
+            n_streams -= 1
+        streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        main = torch.cuda.current_stream()
+
+        def run_steps(count):
+            """`count` independent forward passes; step i replays graph i % n_pool on stream i % n_streams."""
+            if graphs is None:
+                for i in range(count):
+                    outs[i % n_pool] = model(pool[i % n_pool])
+                return
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for st in streams:
+                st.wait_event(fork)
+            for i in range(count):
+                with torch.cuda.stream(streams[i % n_streams]):
+                    graphs[i % n_pool].replay()
+            for st in streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+
+        clocks = ClockSampler(local_rank).start()
+        run_steps(max(3, args.warmup))
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.mark_begin()
+        ev0.record(main)
+        run_steps(args.steps)
+        ev1.record(main)
+        barrier()
+        clocks.mark_end()
+        ms_total = ev0.elapsed_time(ev1)
+        # single-stream latency of one step (same graphs, back to back on one stream), for reference
+        lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_lat = min(args.steps, 200)
+        lat0.record(main)
+        for i in range(n_lat):
             if graphs is not None:
                 graphs[i % n_pool].replay()
             else:
                 outs[i % n_pool] = model(pool[i % n_pool])
-
-        for i in range(max(3, args.warmup)):
-            step(i)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
-            ev0.record()
-            for i in range(args.steps):
-                step(i)
-            ev1.record()
-            barrier()
-        ms_total = ev0.elapsed_time(ev1)
+        lat1.record(main)
+        torch.cuda.synchronize()
+        single_stream_ms = lat0.elapsed_time(lat1) / n_lat
 
     # ---- leg 2: per-stage CUDA-event timing of the same steps (eager, events on the launching stream) ----
     prof_steps = min(args.steps, 40)
@@ -318,6 +376,7 @@ def main():
         cpu = cpu_reference_leg(args.batch, 10 ** 9, 3, args.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    clocks.stop()
     if rank == 0:
         alg = algorithmic_bytes_fwd(n_atoms, n_bonds, args.batch)
         line = {
@@ -328,7 +387,9 @@ def main():
             "config": {"workload": f"cfg-2: CGR-MPNN-3D d{DEPTH} h{HID} learnable-skip forward (inference), batch "
                                    f"{args.batch}/GPU, Fa={FA} Fb={FB}, T1x-shaped synthetic reactions, random-init "
                                    f"weights in the reference .pth layout",
-                       "engine": engine, "cuda_graph": not args.no_graph, "parallelism": f"replicas x{world}, no collective",
+                       "engine": engine, "cuda_graph": not args.no_graph, "streams": n_streams,
+                       "single_stream_ms_per_step": single_stream_ms,
+                       "parallelism": f"replicas x{world}, no collective",
                        "l2": f"inputs rotate over {n_pool} distinct resident batches ({resident / 1e6:.0f} MB > "
                              f"{L2_BYTES / 1e6:.0f} MB L2); weights (5.9 MB) stay resident",
                        "atoms_per_batch": n_atoms, "bonds_per_batch": n_bonds},

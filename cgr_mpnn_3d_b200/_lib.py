@@ -47,6 +47,7 @@ class CgrGraph(C.Structure):
         ("x", C.c_void_p), ("edge_attr", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p),
         ("in_ptr", C.c_void_p), ("in_idx", C.c_void_p), ("atom_ptr", C.c_void_p),
         ("tile_info", C.c_void_p), ("n_tiles", C.c_int64), ("tc_status", C.c_void_p),
+        ("x_hi", C.c_void_p), ("x_lo", C.c_void_p),
     ]
 
 
@@ -84,6 +85,8 @@ PROTOTYPES = {
                                    C.POINTER(CgrGrads), C.c_uint64, _I32, _V, _SZ, _V]),
     "cgr_tc_plan_build": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
     "cgr_tc_plan_check": (C.c_int, [_V, _I64, _V, _V, _V, _V]),
+    "cgr_tc_features_ld": (_I64, [_I32]),
+    "cgr_tc_split_features": (C.c_int, [_V, _I64, _I32, _V, _V, _V, _V]),
     "cgr_tc_debug_buffer": (C.c_int, [_V]),
     "cgr_tc_weights_bytes": (_SZ, [C.POINTER(CgrParams)]),
     "cgr_tc_prepare_weights": (C.c_int, [C.POINTER(CgrParams), _V, _SZ, _V]),

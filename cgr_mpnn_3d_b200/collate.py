@@ -45,7 +45,6 @@ class GraphPlan:
         dev = self.src.device
         self.tile_info = torch.zeros((max(1, self.n_rxn), 8), dtype=torch.int32, device=dev)
         st = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.tc_status = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.cgr_tc_plan_build(self.in_ptr.data_ptr(), self.atom_ptr.data_ptr(), self.n_rxn,
                                              self.tile_info.data_ptr(), st.data_ptr(), _stream()), "cgr_tc_plan_build")
@@ -54,6 +53,8 @@ class GraphPlan:
         n_tiles, ok = (int(v) for v in st.tolist())
         self.n_tiles = n_tiles
         self.tc_ok = bool(ok) and n_tiles > 0
+        # [0] sticky fp16-range flag of the tcgen05 engine, [1..] self-resetting readout arrival counters
+        self.tc_status = torch.zeros(1 + max(1, n_tiles), dtype=torch.int32, device=dev)
         return self.tc_ok
 
     def check(self) -> None:
@@ -111,6 +112,30 @@ def build_plan(edge_index: torch.Tensor, num_nodes: int, batch: Optional[torch.T
             _lib.check(lib.cgr_atom_ptr_from_batch(b.data_ptr(), n, p.n_rxn, p.atom_ptr.data_ptr(), _stream()),
                        "cgr_atom_ptr_from_batch")
     return p
+
+
+def split_features_for(data, plan: GraphPlan):
+    """FP16 (hi, lo) form of ``data.x`` for the tcgen05 engine, cached on the batch object (batch
+    preparation, like the CSR arrays): ``cgr_tc_split_features``."""
+    x = data.x
+    key = (x.data_ptr(), x._version, tuple(x.shape))
+    cached = getattr(data, "_cgr_xsplit", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    lib = _lib.load()
+    xc = x.contiguous() if x.dtype == torch.float32 else x.float().contiguous()
+    n, fa = int(xc.shape[0]), int(xc.shape[1])
+    ld = int(lib.cgr_tc_features_ld(fa))
+    x_hi = torch.empty((n, ld), dtype=torch.float16, device=xc.device)
+    x_lo = torch.empty((n, ld), dtype=torch.float16, device=xc.device)
+    with torch.cuda.device(xc.device):
+        _lib.check(lib.cgr_tc_split_features(xc.data_ptr(), n, fa, x_hi.data_ptr(), x_lo.data_ptr(),
+                                             plan.tc_status.data_ptr(), _stream()), "cgr_tc_split_features")
+    try:
+        data._cgr_xsplit = (key, x_hi, x_lo)
+    except Exception:
+        pass
+    return x_hi, x_lo
 
 
 def plan_for(data) -> GraphPlan:

@@ -404,6 +404,11 @@ extern "C" int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, cons
   CGR_CHECK_ARG(tile_info && src && dst && status, "cgr_tc_plan_check: null pointer");
   return tc_plan_check(tile_info, n_tiles, src, dst, status, (cudaStream_t)stream);
 }
+extern "C" int64_t cgr_tc_features_ld(int32_t fa) { return ((int64_t)fa + 63) / 64 * 64; }
+extern "C" int cgr_tc_split_features(const float* x, int64_t n_atoms, int32_t fa, void* x_hi, void* x_lo,
+                                     int32_t* status, void* stream) {
+  return tc_split_features(x, n_atoms, fa, x_hi, x_lo, status, (cudaStream_t)stream);
+}
 extern "C" int cgr_tc_debug_buffer(void* p) { tc_set_debug_buffer((long long*)p); return CGR_OK; }
 extern "C" size_t cgr_tc_weights_bytes(const cgr_params_t* p) { return p ? tc_weights_bytes(p) : 0; }
 extern "C" int cgr_tc_prepare_weights(const cgr_params_t* p, void* buffer, size_t buffer_bytes, void* stream) {

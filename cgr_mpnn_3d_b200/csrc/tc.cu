@@ -46,58 +46,53 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   if (ovf) atomicOr(overflow, 1);
 }
 
-// h0 = act(P'[src e] + ea[e] . W_e^T) on tile-packed rows; writes the fp32 copy (skip input) and the split operand
-__global__ void __launch_bounds__(128) tc_edge_init_kernel(const float* __restrict__ PQ, int64_t ldpq,
+// h0 = act(P'[src e] + ea[e] . W_e^T) on tile-packed rows (P' already holds b_i); one warp per bond row,
+// lanes sweep float4 column groups; W_e^T [fb][H] is read coalesced.  Writes the fp32 copy (skip operand of
+// every layer) and the FP16 (hi, lo) operand of layer 0.
+__global__ void __launch_bounds__(256) tc_edge_init_kernel(const float* __restrict__ PQ, int64_t ldpq,
                                                            const float* __restrict__ ea, const int32_t* __restrict__ src,
-                                                           const float* __restrict__ w_init,
-                                                           const int32_t* __restrict__ tile_info, int fa, int fb, int H,
-                                                           int act, float* __restrict__ h0, __half* __restrict__ o_hi,
+                                                           const float* __restrict__ wet,
+                                                           const int32_t* __restrict__ tile_info, int fb, int H, int act,
+                                                           float* __restrict__ h0, __half* __restrict__ o_hi,
                                                            __half* __restrict__ o_lo, int64_t ldo,
                                                            int* __restrict__ overflow) {
-  extern __shared__ float ea_s[];                  // [4][fb]
   const int tile = blockIdx.y;
   const int ebase = __ldg(tile_info + tile * 8), ecount = __ldg(tile_info + tile * 8 + 1);
-  const int j0 = blockIdx.x * 4;
-  if (j0 >= ecount) return;
-  for (int i = threadIdx.x; i < 4 * fb; i += blockDim.x) {
-    const int j = j0 + i / fb;
-    ea_s[i] = j < ecount ? __ldg(ea + (int64_t)(ebase + j) * fb + (i % fb)) : 0.f;
-  }
-  __syncthreads();
-  const int ld = fa + fb;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= ecount) return;
+  const int64_t e = (int64_t)ebase + j, r = (int64_t)tile * TM + j;
+  const float* prow = PQ + (int64_t)__ldg(src + e) * ldpq;
+  const float ea_l = lane < fb ? __ldg(ea + e * fb + lane) : 0.f;      // fb <= 32 (checked by the caller)
   bool ovf = false;
-  for (int n = threadIdx.x; n < H; n += blockDim.x) {
-    const float* w = w_init + (int64_t)n * ld + fa;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = 4 * lane; n < H; n += 128) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(prow + n));
     for (int k = 0; k < fb; ++k) {
-      const float wk = __ldg(w + k);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(ea_s[i * fb + k], wk, acc[i]);
+      const float ek = __shfl_sync(0xffffffffu, ea_l, k);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wet + (int64_t)k * H + n));
+      a.x = fmaf(ek, w.x, a.x); a.y = fmaf(ek, w.y, a.y); a.z = fmaf(ek, w.z, a.z); a.w = fmaf(ek, w.w, a.w);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i;
-      if (j >= ecount) break;
-      const int64_t r = (int64_t)tile * TM + j;
-      const float v = cgr_act(__ldg(PQ + (int64_t)__ldg(src + ebase + j) * ldpq + n) + acc[i], act);
-      ovf |= fabsf(v) > 60000.f;
-      h0[r * H + n] = v;
-      __half h, l;
-      split_f16(v, h, l);
-      o_hi[r * ldo + n] = h;
-      o_lo[r * ldo + n] = l;
-    }
+    a.x = cgr_act(a.x, act); a.y = cgr_act(a.y, act); a.z = cgr_act(a.z, act); a.w = cgr_act(a.w, act);
+    ovf |= fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))) > 60000.f;
+    *reinterpret_cast<float4*>(h0 + r * H + n) = a;
+    const __half2 hi01 = __floats2half2_rn(a.x, a.y), hi23 = __floats2half2_rn(a.z, a.w);
+    const float2 f01 = __half22float2(hi01), f23 = __half22float2(hi23);
+    const __half2 lo01 = __floats2half2_rn(a.x - f01.x, a.y - f01.y), lo23 = __floats2half2_rn(a.z - f23.x, a.w - f23.y);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
+    pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
+    *reinterpret_cast<uint2*>(o_hi + r * ldo + n) = ph;
+    *reinterpret_cast<uint2*>(o_lo + r * ldo + n) = pl;
   }
   if (ovf) atomicOr(overflow, 1);
 }
 
-__global__ void tc_finalize_kernel(const float* __restrict__ partial, int n_slices, int64_t B,
-                                   const float* __restrict__ b_ffn, float* __restrict__ out) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float s = 0.f;
-  for (int i = 0; i < n_slices; ++i) s += partial[(int64_t)i * B + b];     // fixed order
-  out[b] = s + __ldg(b_ffn);
+// W_e^T [fb][H] from edge_init.weight[:, fa:]  (coalesced reads in the edge-init kernel)
+__global__ void transpose_we_kernel(const float* __restrict__ w_init, int fa, int fb, int H, float* __restrict__ wet) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < fb * H) {
+    const int k = i / H, n = i % H;
+    wet[i] = __ldg(w_init + (int64_t)n * (fa + fb) + fa + k);
+  }
 }
 
 // ---- weight preparation: per-matrix power-of-two scale, (hi, lo) split ----
@@ -269,7 +264,7 @@ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 struct WLayout {                 // prepared-weight buffer: [amax | unscale | bias_cat | matrices (hi, lo)...]
   int n_mat;
   int64_t kp_x, kp_h;
-  size_t off_amax, off_unscale, off_bias, off_hi[MAX_SEG], off_lo[MAX_SEG], total;
+  size_t off_amax, off_unscale, off_bias, off_wet, off_hi[MAX_SEG], off_lo[MAX_SEG], total;
   int64_t rows[MAX_SEG], ld[MAX_SEG];
 };
 
@@ -283,6 +278,7 @@ WLayout wlayout(const cgr_params_t* p) {
   w.off_amax = off; off += cgr_align_up(MAX_SEG * sizeof(unsigned int), 256);
   w.off_unscale = off; off += cgr_align_up(MAX_SEG * sizeof(float), 256);
   w.off_bias = off; off += cgr_align_up(2 * H * sizeof(float), 256);
+  w.off_wet = off; off += cgr_align_up((size_t)(p->fb > 0 ? p->fb : 1) * H * sizeof(float), 256);
   for (int m = 0; m < w.n_mat; ++m) {
     w.rows[m] = m == 0 ? 2 * H : H;
     w.ld[m] = m == 0 ? w.kp_x : w.kp_h;
@@ -334,6 +330,17 @@ int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const c
 
 // ------------------------------------------------------------------------------------------------
 
+int tc_split_features(const float* x, int64_t n, int fa, void* x_hi, void* x_lo, int* status, cudaStream_t st) {
+  CGR_CHECK_ARG(x && x_hi && x_lo && status && n >= 0 && fa > 0, "tc_split_features: bad argument");
+  if (n == 0) return CGR_OK;
+  CgrRange prof("tc_split_x", st);
+  cgr_note_launch("tc_split_x", st, 1);
+  split_rows_kernel<<<(unsigned)cgr_ceil_div(n, 8), 256, 0, st>>>(x, fa, n, fa, (__half*)x_hi, (__half*)x_lo,
+                                                                  round_up(fa, BK), status);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
 static long long* g_tc_dbg = nullptr;   // debug: phase time stamps of the bond-layer kernel
 void tc_set_debug_buffer(long long* p) { g_tc_dbg = p; }
 
@@ -366,6 +373,9 @@ int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cud
   prep_amax_kernel<<<dim3(64, (unsigned)ns), 256, 0, st>>>(a);
   prep_split_kernel<<<dim3(64, (unsigned)ns), 256, 0, st>>>(a);
   concat_bias_kernel<<<(unsigned)cgr_ceil_div(H, 256), 256, 0, st>>>(p->b_init, p->b_e2n, H, (float*)(b + w.off_bias));
+  if (fb > 0)
+    transpose_we_kernel<<<(unsigned)cgr_ceil_div((int64_t)fb * H, 256), 256, 0, st>>>(p->w_init, fa, fb, H,
+                                                                                       (float*)(b + w.off_wet));
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }
@@ -396,6 +406,7 @@ struct TcWs {
   int n_slices;
 };
 TcWs tc_ws(const cgr_params_t* p, const cgr_graph_t* g, bool need_w) {
+  const bool need_x = !(g->x_hi && g->x_lo);
   TcWs w;
   const int64_t H = p->hidden, N = g->n_atoms, T = g->n_tiles, B = g->n_rxn;
   w.kp_x = round_up(p->fa, BK);
@@ -405,8 +416,8 @@ TcWs tc_ws(const cgr_params_t* p, const cgr_graph_t* g, bool need_w) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += cgr_align_up(bytes, 1024); return o; };
   w.off_w = take(need_w ? tc_weights_bytes(p) : 0);
-  w.off_xhi = take((size_t)N * w.kp_x * sizeof(__half));
-  w.off_xlo = take((size_t)N * w.kp_x * sizeof(__half));
+  w.off_xhi = take(need_x ? (size_t)N * w.kp_x * sizeof(__half) : 0);
+  w.off_xlo = take(need_x ? (size_t)N * w.kp_x * sizeof(__half) : 0);
   w.off_pq = take((size_t)N * 2 * H * sizeof(float));
   w.off_h0 = take((size_t)w.rows_pad * H * sizeof(float));
   for (int i = 0; i < 2; ++i) {
@@ -432,6 +443,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   CGR_CHECK_ARG(g->tile_info && g->n_tiles > 0, "tcgen05 engine needs a tile plan (reactions of <= 128 bonds)");
   CGR_CHECK_ARG(p->hidden % 4 == 0, "tcgen05 engine needs a hidden size that is a multiple of 4");
   CGR_CHECK_ARG(p->depth + 3 <= MAX_SEG, "tcgen05 engine supports depth <= %d", MAX_SEG - 3);
+  CGR_CHECK_ARG(p->fb <= 32, "tcgen05 engine supports at most 32 bond features");
+  CGR_CHECK_ARG(g->tc_status, "tcgen05 engine needs cgr_graph_t.tc_status ([1 + n_tiles] zero-initialised ints)");
   const bool need_w = p->tc_weights == nullptr;
   const TcWs w = tc_ws(p, g, need_w);
   CGR_CHECK_ARG(workspace && workspace_bytes >= w.total, "tc_gnn_forward: workspace too small");
@@ -451,18 +464,19 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   auto w_hi = [&](int m) { return (const __half*)(wbuf + wl.off_hi[m]); };
   auto w_lo = [&](int m) { return (const __half*)(wbuf + wl.off_lo[m]); };
 
-  __half* x_hi = (__half*)(ws + w.off_xhi);
-  __half* x_lo = (__half*)(ws + w.off_xlo);
+  const bool need_x = !(g->x_hi && g->x_lo);
+  __half* x_hi = need_x ? (__half*)(ws + w.off_xhi) : (__half*)g->x_hi;
+  __half* x_lo = need_x ? (__half*)(ws + w.off_xlo) : (__half*)g->x_lo;
   float* PQ = (float*)(ws + w.off_pq);
   float* h0 = (float*)(ws + w.off_h0);
   __half* h_hi[2] = {(__half*)(ws + w.off_hhi[0]), (__half*)(ws + w.off_hhi[1])};
   __half* h_lo[2] = {(__half*)(ws + w.off_hlo[0]), (__half*)(ws + w.off_hlo[1])};
   float* partial = (float*)(ws + w.off_partial);
-  int* flag = (int*)(ws + w.off_flag);
-  CGR_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  int* flag = g->tc_status;              // [0] sticky fp16-range flag, [1..T] readout arrival counters
+  int* tile_counter = g->tc_status + 1;
 
-  // 1. x -> (hi, lo)
-  {
+  // 1. x -> (hi, lo), unless the caller prepared it with cgr_tc_split_features (batch preparation)
+  if (need_x) {
     CgrRange prof("tc_split_x", st);
     cgr_note_launch("tc_split_x", st, 1);
     split_rows_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(g->x, fa, N, fa, x_hi, x_lo, w.kp_x, flag);
@@ -491,10 +505,9 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   {
     CgrRange prof("tc_edge_init", st);
     cgr_note_launch("tc_edge_init", st, 1);
-    const size_t smem = (size_t)(4 * (fb > 0 ? fb : 1)) * sizeof(float);
-    tc_edge_init_kernel<<<dim3(TM / 4, (unsigned)T), 128, smem, st>>>(PQ, 2 * H, g->edge_attr, g->src, p->w_init,
-                                                                      g->tile_info, fa, fb, H, p->act, h0, h_hi[0],
-                                                                      h_lo[0], w.kp_h, flag);
+    tc_edge_init_kernel<<<dim3(TM / 8, (unsigned)T), 256, 0, st>>>(PQ, 2 * H, g->edge_attr, g->src,
+                                                                   (const float*)(wbuf + wl.off_wet), g->tile_info, fb,
+                                                                   H, p->act, h0, h_hi[0], h_lo[0], w.kp_h, flag);
     CGR_LAUNCH_CHECK();
   }
   // 4. message passing layers: one fused kernel each
@@ -544,21 +557,14 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     if ((rc = make_map_f32(&prm.tmR, PQ, N, 2 * H, 2 * H, chunk_cols(bn_h), TM))) return rc;
     prm.r_col0 = H;
     prm.w_ffn = p->w_ffn;
+    prm.b_ffn = p->b_ffn;
+    prm.out = out;
+    prm.tile_counter = tile_counter;
     prm.partial_out = partial;
     prm.n_rxn = B;
     prm.overflow = flag;
     rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", st);
     if (rc) return rc;
-  }
-  {
-    CgrRange prof("tc_finalize", st);
-    cgr_note_launch("tc_finalize", st, 1);
-    tc_finalize_kernel<<<(unsigned)cgr_ceil_div(B, 256), 256, 0, st>>>(partial, (int)cgr_ceil_div(H, bn_h), B,
-                                                                         p->b_ffn, out);
-    CGR_LAUNCH_CHECK();
-  }
-  if (g->tc_status) {      // sticky overflow report for the caller (checked lazily on the host)
-    CGR_CUDA(cudaMemcpyAsync(g->tc_status, flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
   }
   return CGR_OK;
 }

@@ -18,3 +18,4 @@ size_t tc_linear_workspace(int64_t M, int64_t N, int64_t K);
 int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wgt, int64_t N, int64_t ldw,
               const float* bias, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void tc_set_debug_buffer(long long* p);
+int tc_split_features(const float* x, int64_t n, int fa, void* x_hi, void* x_lo, int* status, cudaStream_t st);

@@ -36,7 +36,11 @@ struct Cfg {
   static constexpr int Y_BYTES = ((TM * CHP * 4 + 127) / 128) * 128;
   static constexpr int FIT = (SMEM_LIMIT - R_BYTES - AUX_BYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 4 ? 4 : FIT;
-  static constexpr int TMEM_COLS = BN <= 128 ? 128 : 256;
+  // [B_hi ; B_lo] are adjacent in a stage, so A_hi x [B_hi;B_lo] is ONE MMA of N = 2*BN when that fits the
+  // 256-column instruction limit: 2 MMAs per k-step instead of 3, and A_hi / B_hi are fetched once less
+  static constexpr bool CAT = 2 * BN <= 256;
+  static constexpr int ACC_COLS = CAT ? 2 * BN : BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + R_BYTES + AUX_BYTES + 1024;
   static_assert(BN % 16 == 0 && BN <= 256 && CH % 4 == 0 && VL <= 32, "bad slice width");
   static_assert(STAGES >= 2, "pipeline needs two stages");
@@ -71,7 +75,10 @@ struct TcGemmParams {
   __half* o_lo;
   int64_t ldo;
   const float* w_ffn;
+  const float* b_ffn;
   float* partial_out;           // [n_slices, B]
+  float* out;                   // [B] final energies, written by the last slice CTA of each tile
+  int* tile_counter;            // [T] arrival counters of the readout (self-resetting)
   int64_t n_rxn;
   int* overflow;                // sticky flag: an activation left the fp16 range
   long long* dbg;               // optional [n_cta][8] clock64 stamps of the kernel phases (debug)
@@ -183,6 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   } else if (warp == 1) {
     // MMA issuer: one lane issues 3 tcgen05.mma per 16-wide k-step (lo.hi + hi.lo + hi.hi)
     const uint32_t idesc = umma::idesc_f16_f32(TM, n_eff);
+    const uint32_t idesc_cat = umma::idesc_f16_f32(TM, 2 * BN);
     for (int kc = 0; kc < p.num_k; ++kc) {
       const int s = kc % STAGES;
       const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
@@ -199,9 +207,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 32 >> 4);          // 16 fp16 = 32 bytes along K inside the swizzle row
-          umma::mma_f16_ss(tmem, da_lo + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
-          umma::mma_f16_ss(tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-          umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          if (C::CAT) {
+            // cols [0,BN) += A_hi B_hi^T, cols [BN,2BN) += A_hi B_lo^T (one instruction), then cols [0,BN) += A_lo B_hi^T
+            umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc_cat, (kc | ks) ? 1u : 0u);
+            umma::mma_f16_ss(tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+          } else {
+            umma::mma_f16_ss(tmem, da_lo + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+            umma::mma_f16_ss(tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
         }
         umma::mma_commit(umma::smem_u32(&aux->empty[s]));         // frees the stage when these MMAs retire
         if (kc == p.num_k - 1) umma::mma_commit(umma::smem_u32(&aux->tmem_full));
@@ -235,6 +249,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   const float us = __ldg(p.unscale);
   const float skip = (EPI == EPI_BOND && p.skip) ? __ldg(p.skip) : 1.f;
   const int c = 4 * lane;                                         // this lane's float4 column group inside a chunk
+  // per-lane bias / readout weights of every column chunk, fetched while the GEMM is still running
+  float4 bias_r[NCH], wf_r[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    bias_r[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wf_r[ch] = bias_r[ch];
+    const int n = n0 + ch * CH + c;
+    if (lane < VL && n < p.n_total) {
+      if (p.bias) {
+        bias_r[ch].x = __ldg(p.bias + n);
+        bias_r[ch].y = n + 1 < p.n_total ? __ldg(p.bias + n + 1) : 0.f;
+        bias_r[ch].z = n + 2 < p.n_total ? __ldg(p.bias + n + 2) : 0.f;
+        bias_r[ch].w = n + 3 < p.n_total ? __ldg(p.bias + n + 3) : 0.f;
+      }
+      if (EPI == EPI_READOUT) {
+        wf_r[ch].x = __ldg(p.w_ffn + n);
+        wf_r[ch].y = n + 1 < p.n_total ? __ldg(p.w_ffn + n + 1) : 0.f;
+        wf_r[ch].z = n + 2 < p.n_total ? __ldg(p.w_ffn + n + 2) : 0.f;
+        wf_r[ch].w = n + 3 < p.n_total ? __ldg(p.w_ffn + n + 3) : 0.f;
+      }
+    }
+  }
 
   // ------------------------------------------------------------------ epilogue (all 8 warps)
   umma::mbar_wait(umma::smem_u32(&aux->tmem_full), 0);
@@ -251,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   }
   bool ovf = false;
 
-#pragma unroll 1
+#pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if (ch > 0) __syncthreads();                                  // every reader of the previous y_s chunk is done
     // TMEM -> registers -> y_s (fp32, unscaled); warp w owns lane quarter w%4 and every other 8-column group
@@ -262,7 +298,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       for (int cc = grp * 8; cc < CH; cc += 8 * (NWARPS / 4)) {
         float v[8];
         umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CH + cc), v);
-        umma::tmem_ld_wait();
+        if (C::CAT) {
+          float v2[8];
+          umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + ch * CH + cc), v2);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += v2[i];
+        } else {
+          umma::tmem_ld_wait();
+        }
         float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
         dst[0] = make_float4(v[0] * us, v[1] * us, v[2] * us, v[3] * us);
         dst[1] = make_float4(v[4] * us, v[5] * us, v[6] * us, v[7] * us);
@@ -275,21 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 
     const int n = n0 + ch * CH + c;                               // first global column of this lane's group
     const bool lane_on = lane < VL && n < p.n_total;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), wf4 = bias4;
-    if (lane_on) {
-      if (p.bias) {
-        bias4.x = __ldg(p.bias + n);
-        bias4.y = n + 1 < p.n_total ? __ldg(p.bias + n + 1) : 0.f;
-        bias4.z = n + 2 < p.n_total ? __ldg(p.bias + n + 2) : 0.f;
-        bias4.w = n + 3 < p.n_total ? __ldg(p.bias + n + 3) : 0.f;
-      }
-      if (EPI == EPI_READOUT) {
-        wf4.x = __ldg(p.w_ffn + n);
-        wf4.y = n + 1 < p.n_total ? __ldg(p.w_ffn + n + 1) : 0.f;
-        wf4.z = n + 2 < p.n_total ? __ldg(p.w_ffn + n + 2) : 0.f;
-        wf4.w = n + 3 < p.n_total ? __ldg(p.w_ffn + n + 3) : 0.f;
-      }
-    }
+    const float4 bias4 = bias_r[NCH > 1 ? ch : 0], wf4 = wf_r[NCH > 1 ? ch : 0];
     const float* r_s = ch == 0 ? r0_s : r1_s;
 
     if (EPI == EPI_PLAIN) {
@@ -449,6 +479,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       float s = 0.f;
       for (int v = v0; v < v1; ++v) s += aux->tat[v];            // ascending atom id
       p.partial_out[(int64_t)slice * p.n_rxn + b] = s;
+    }
+    // the last slice CTA of this tile to arrive adds the slices in a fixed order: deterministic, no extra kernel
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) aux->info[7] = atomicAdd(p.tile_counter + tile, 1);
+    __syncthreads();
+    if (aux->info[7] == (int)gridDim.x - 1) {
+      __threadfence();
+      const float bf = __ldg(p.b_ffn);
+      for (int rx = threadIdx.x; rx < rxcount; rx += THREADS) {
+        const int b = rx0 + rx;
+        float s = 0.f;
+        for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(p.partial_out + (int64_t)i * p.n_rxn + b);
+        p.out[b] = s + bf;
+      }
+      if (threadIdx.x == 0) p.tile_counter[tile] = 0;             // ready for the next forward
     }
   }
 

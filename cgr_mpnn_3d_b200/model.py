@@ -19,7 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .collate import plan_for
+from .collate import plan_for, split_features_for
 
 _ACT_BY_FN = {F.relu: 0, F.silu: 1, F.gelu: 2, torch.relu: 0}
 _ACT_BY_NAME = {"relu": 0, "silu": 1, "gelu": 2}
@@ -123,7 +123,8 @@ class GNN(nn.Module):
         e = getattr(self, "engine", "auto")
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
-        can_tc = (not needs_saved) and self.hidden_sizes[0] % 4 == 0 and self.depth <= 13 and plan.ensure_tiles()
+        can_tc = ((not needs_saved) and self.hidden_sizes[0] % 4 == 0 and self.depth <= 13
+                  and self.num_edge_features <= 32 and plan.ensure_tiles())
         if e in ("tc", 1):
             if not can_tc:
                 raise RuntimeError("engine='tc' needs an inference forward (no grad, no dropout), a hidden "
@@ -181,12 +182,14 @@ class GNN(nn.Module):
         if engine == _lib.ENGINE_TC:
             tile_info, n_tiles, tc_status = plan.tile_info, plan.n_tiles, plan.tc_status
             tc_w = self._tc_weights(params, int(x.shape[1]), int(edge_attr.shape[1]))
+            x_hi, x_lo = split_features_for(data, plan)
         else:
             tile_info, n_tiles, tc_status = empty_i, 0, empty_i
             tc_w = torch.empty(0, dtype=torch.uint8, device=dev)
+            x_hi = x_lo = torch.empty(0, dtype=torch.float16, device=dev)
         res = ops.gnn_forward(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr, params,
                               self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
-                              train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w)
+                              train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo)
         self.__dict__["_last_plan"] = plan if engine == _lib.ENGINE_TC else None
         out = res[0]
         if caller_device != dev:
@@ -207,7 +210,7 @@ class GNN(nn.Module):
         """Synchronising check of the last tcgen05 forward: raises if an activation left the fp16 range
         of the FP16x3 split (then use ``engine='simt'``)."""
         plan = self.__dict__.get("_last_plan")
-        if plan is not None and plan.tc_status is not None and int(plan.tc_status.item()) != 0:
+        if plan is not None and plan.tc_status is not None and int(plan.tc_status[0].item()) != 0:
             raise RuntimeError("tcgen05 engine: an activation exceeded the fp16 range of the FP16x3 split; "
                                "set model.engine = 'simt'")
 

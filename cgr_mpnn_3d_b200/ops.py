@@ -58,14 +58,16 @@ class _Ctx:
 
 
 def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info=None, n_tiles=0,
-                  tc_status=None) -> _lib.CgrGraph:
+                  tc_status=None, x_hi=None, x_lo=None) -> _lib.CgrGraph:
     has_tiles = tile_info is not None and tile_info.numel() > 0 and n_tiles > 0
+    has_split = has_tiles and x_hi is not None and x_lo is not None and x_hi.numel() > 0 and x_lo.numel() > 0
     return _lib.CgrGraph(
         n_atoms=int(x.shape[0]), n_bonds=int(src.shape[0]), n_rxn=int(atom_ptr.shape[0]) - 1,
         x=x.data_ptr(), edge_attr=edge_attr.data_ptr(), src=src.data_ptr(), dst=dst.data_ptr(),
         in_ptr=in_ptr.data_ptr(), in_idx=in_idx.data_ptr(), atom_ptr=atom_ptr.data_ptr(),
         tile_info=tile_info.data_ptr() if has_tiles else None, n_tiles=int(n_tiles) if has_tiles else 0,
         tc_status=tc_status.data_ptr() if (has_tiles and tc_status is not None and tc_status.numel() > 0) else None,
+        x_hi=x_hi.data_ptr() if has_split else None, x_lo=x_lo.data_ptr() if has_split else None,
     )
 
 
@@ -85,7 +87,7 @@ def _f32c(t: Tensor) -> Tensor:
 def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor, in_idx: Tensor,
                 atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
                 dropout_ps: Sequence[float], training: bool, seed: int, engine: int, tile_info: Tensor,
-                n_tiles: int, tc_status: Tensor, tc_weights: Tensor) -> List[Tensor]:
+                n_tiles: int, tc_status: Tensor, tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor) -> List[Tensor]:
     """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled]`` (saved tensors are empty in eval).
 
     ``tile_info`` / ``n_tiles`` / ``tc_status`` / ``tc_weights`` feed the tcgen05 engine (empty tensors
@@ -99,7 +101,7 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
     if tc_weights.numel() > 0:
         ctx.params.tc_weights = tc_weights.data_ptr()
     H = ctx.hidden
-    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info, n_tiles, tc_status)
+    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info, n_tiles, tc_status, x_hi, x_lo)
     n, e, b = g.n_atoms, g.n_bonds, g.n_rxn
     f32 = dict(dtype=torch.float32, device=x.device)
     out = torch.empty(b, **f32)
@@ -130,7 +132,7 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
 
 @gnn_forward.register_fake
 def _(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-      engine, tile_info, n_tiles, tc_status, tc_weights):
+      engine, tile_info, n_tiles, tc_status, tc_weights, x_hi, x_lo):
     H = params[0].shape[0]
     n, e, b = x.shape[0], src.shape[0], atom_ptr.shape[0] - 1
     mk = lambda *s: x.new_empty(s, dtype=torch.float32)
@@ -184,7 +186,7 @@ def _(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved,
 
 def _setup_context(ctx, inputs, output):
     (x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-     engine, _tile_info, _n_tiles, _tc_status, _tc_weights) = inputs
+     engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo) = inputs
     ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine)
     ctx.n_params = len(params)
     ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:])
@@ -205,7 +207,7 @@ def _backward(ctx, grads):
     pg = gnn_backward(g_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip,
                       dropout_ps, seed, 0)
     return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None, None, None,
-            None, None)
+            None, None, None, None)
 
 
 gnn_forward.register_autograd(_backward, setup_context=_setup_context)

@@ -88,7 +88,10 @@ typedef struct cgr_graph {
   const int32_t* atom_ptr;   /* [B+1] first atom of each reaction (Batch.ptr)       */
   const int32_t* tile_info;  /* [n_tiles, 8] tile plan of the tcgen05 engine (cgr_tc_plan_build) or NULL */
   int64_t n_tiles;
-  int32_t* tc_status;        /* optional [1]: receives the fp16-range overflow flag of a tcgen05 forward */
+  int32_t* tc_status;        /* tcgen05 engine: [1 + n_tiles] ints, zero-initialised once by the caller:
+                                [0] sticky fp16-range overflow flag, [1..] self-resetting readout counters */
+  const void* x_hi;          /* optional: data.x as FP16 (hi, lo) rows prepared by cgr_tc_split_features */
+  const void* x_lo;          /*           (row stride cgr_tc_features_ld(fa) halfs); NULL: converted per call */
 } cgr_graph_t;
 
 /* activations kept for the backward pass (caller-allocated; NULL members are not written) */
@@ -193,6 +196,11 @@ int cgr_tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, int64_t n_
                       int32_t* status, void* stream);
 int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst,
                       int32_t* status, void* stream);
+/* Batch preparation for the tcgen05 engine: data.x [N, fa] fp32 -> FP16 (hi, lo) rows of stride
+ * cgr_tc_features_ld(fa) halfs (part of collation, like the CSR arrays; status[0] gets the overflow flag). */
+int64_t cgr_tc_features_ld(int32_t fa);
+int cgr_tc_split_features(const float* x, int64_t n_atoms, int32_t fa, void* x_hi, void* x_lo,
+                          int32_t* status, void* stream);
 /* Debug: device buffer [n_cta][8] of int64 receiving clock64 stamps of the bond-layer kernel phases (NULL = off). */
 int cgr_tc_debug_buffer(void* device_buffer);
 size_t cgr_tc_weights_bytes(const cgr_params_t* p);

@@ -251,7 +251,9 @@ def test_dropout_replay_against_oracle():
                           model._param_list(), meta["depth"], 0, True, [p] * meta["depth"], True, seed, 0,
                           torch.empty(0, dtype=torch.int32, device="cuda"), 0,
                           torch.empty(0, dtype=torch.int32, device="cuda"),
-                          torch.empty(0, dtype=torch.uint8, device="cuda"))
+                          torch.empty(0, dtype=torch.uint8, device="cuda"),
+                          torch.empty(0, dtype=torch.float16, device="cuda"),
+                          torch.empty(0, dtype=torch.float16, device="cuda"))
     out = res[0]
     masks = [stage_ops.dropout_mask(seed, l, p, d.num_edges, meta["hidden"], "cuda").cpu()
              for l in range(meta["depth"])]
