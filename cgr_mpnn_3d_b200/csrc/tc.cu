@@ -64,13 +64,18 @@ __global__ void __launch_bounds__(256) tc_edge_init_kernel(const float* __restri
   const float* prow = PQ + (int64_t)__ldg(src + e) * ldpq;
   const float ea_l = lane < fb ? __ldg(ea + e * fb + lane) : 0.f;      // fb <= 32 (checked by the caller)
   bool ovf = false;
-  for (int n = 4 * lane; n < H; n += 128) {
-    float4 a = __ldg(reinterpret_cast<const float4*>(prow + n));
+  for (int nb = 0; nb < H; nb += 128) {            // warp-uniform trip count: every lane takes part in the shuffles
+    const int n = nb + 4 * lane;
+    const bool on = n < H;
+    float4 a = on ? __ldg(reinterpret_cast<const float4*>(prow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 0; k < fb; ++k) {
       const float ek = __shfl_sync(0xffffffffu, ea_l, k);
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wet + (int64_t)k * H + n));
-      a.x = fmaf(ek, w.x, a.x); a.y = fmaf(ek, w.y, a.y); a.z = fmaf(ek, w.z, a.z); a.w = fmaf(ek, w.w, a.w);
+      if (on) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wet + (int64_t)k * H + n));
+        a.x = fmaf(ek, w.x, a.x); a.y = fmaf(ek, w.y, a.y); a.z = fmaf(ek, w.z, a.z); a.w = fmaf(ek, w.w, a.w);
+      }
     }
+    if (!on) continue;
     a.x = cgr_act(a.x, act); a.y = cgr_act(a.y, act); a.z = cgr_act(a.z, act); a.w = cgr_act(a.w, act);
     ovf |= fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))) > 60000.f;
     *reinterpret_cast<float4*>(h0 + r * H + n) = a;
