@@ -341,8 +341,15 @@ def main():
             "atom_proj": 4 * (n_atoms * FA + 2 * n_atoms * HID + 2 * HID * FA),
         }.get(dominant, algorithmic_bytes_fwd(n_atoms, n_bonds, args.batch) / max(1, launches_per_step))
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+                traffic = json.load(fh).get(dominant, {}).get(f"batch_{args.batch}")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                    "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": per_launch,
+                    "peak_kind": peak_kind,
                     "avg_launch_us": avg_ms * 1e3, "launches_per_step": stage_cnt[dominant] / prof_steps,
                     "stage_share": {k: round(v / sum(stage_ms.values()), 4) for k, v in sorted(stage_ms.items())}}
 
@@ -363,11 +370,38 @@ def main():
             e2e_s = time.perf_counter() - t0
         e2e = {"seconds": e2e_s, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.numel() * 4)}
 
+    # ---- optional leg 4: training step (forward + MSE(sum) + explicit backward + gradient SUM all-reduce) ----
+    train = None
+    if args.train:
+        from cgr_mpnn_3d_b200.parallel import allreduce_gradients_
+        tm = build_model("auto", dev).train()
+        tb = [make_batch(args.batch, seed=5000 + 997 * rank + i, kind="t1x", fa=FA).to(dev) for i in range(8)]
+        n_t = min(args.steps, 100)
+
+        def train_step(i):
+            tm.zero_grad(set_to_none=True)
+            d = tb[i % len(tb)]
+            loss = ((tm(d) - d.y) ** 2).sum()
+            loss.backward()
+            allreduce_gradients_(tm.parameters())
+
+        for i in range(5):
+            train_step(i)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(n_t):
+            train_step(i)
+        t1e.record()
+        barrier()
+        train = {"ms_total": t0e.elapsed_time(t1e), "steps": n_t}
+
     # ---- reduce over ranks (max time), assemble the line ----
-    t = torch.tensor([ms_total, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e["seconds"] if e2e else 0.0, train["ms_total"] if train else 0.0],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s = float(t[0]), float(t[1])
+    ms_total, e2e_s, train_ms = float(t[0]), float(t[1]), float(t[2])
     total_rxn = args.batch * args.steps * world
     value = total_rxn / (ms_total * 1e-3)
 
@@ -399,6 +433,11 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "gpu_launches": int(launches_per_step) * args.steps,
         }
+        if train:
+            line["train_step"] = {"value": args.batch * train["steps"] * world / (train_ms * 1e-3), "unit": "reactions/s",
+                                  "ms_per_step": train_ms / train["steps"], "steps": train["steps"],
+                                  "what": "forward + MSE(sum) + explicit backward + flat gradient SUM all-reduce "
+                                          "(optimizer excluded), batch %d/GPU, eager custom ops" % args.batch}
         if e2e:
             line["e2e"] = {"value": total_rxn / e2e_s, "unit": "reactions/s",
                            "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],

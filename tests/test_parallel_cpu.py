@@ -1,0 +1,79 @@
+"""CPU, world_size 2 over gloo: sharding and the SUM gradient all-reduce of data-parallel training."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cgr_mpnn_3d_b200.parallel import shard_by_bonds, shard_range
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 64, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_by_bonds_balances():
+    nb = [10] * 50 + [200] * 5
+    spans = shard_by_bonds(nb, 4)
+    assert spans[0][0] == 0 and spans[-1][1] == len(nb)
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(3))
+    loads = [sum(nb[a:b]) for a, b in spans]
+    assert max(loads) <= 2 * (sum(nb) / 4) + 200
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn.functional as F
+    from cgr_mpnn_3d_b200.data import collate_host, make_reactions
+    from cgr_mpnn_3d_b200.parallel import allreduce_gradients_, broadcast_parameters_, shard_reactions
+    from oracle.gnn_oracle import OracleGNN, mse_sum_loss
+    torch.set_num_threads(1)
+    rx = make_reactions(12, seed=3, kind="t1x", fa=78)
+    torch.manual_seed(100 + rank)                      # deliberately different initial replicas
+    model = OracleGNN(78, 14, depth=2, hidden_sizes=[32] * 2, dropout_ps=[0.0] * 2, activation_fn=F.relu,
+                      use_learnable_skip=True)
+    broadcast_parameters_(model.parameters(), src=0)
+    mine = collate_host(shard_reactions(rx, rank, world))
+    mse_sum_loss(model(mine), mine.y).backward()
+    allreduce_gradients_(model.parameters())           # SUM, not mean: loss is MSE(reduction="sum")
+    if rank == 0:
+        ref = OracleGNN(78, 14, depth=2, hidden_sizes=[32] * 2, dropout_ps=[0.0] * 2, activation_fn=F.relu,
+                        use_learnable_skip=True)
+        ref.load_state_dict(model.state_dict())
+        full = collate_host(rx)
+        mse_sum_loss(ref(full), full.y).backward()
+        err = max(float((a.grad - b.grad).abs().max() / b.grad.abs().max().clamp_min(1e-30))
+                  for a, b in zip(model.parameters(), ref.parameters()))
+        q.put(err)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sum_allreduce_matches_single_process_on_concatenated_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-5
