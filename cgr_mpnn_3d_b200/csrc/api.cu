@@ -433,3 +433,165 @@ extern "C" int cgr_dropout_mask(uint64_t seed, uint32_t layer, float dropout_p, 
   CGR_CHECK_ARG(mask && n_bonds >= 0 && hidden > 0, "cgr_dropout_mask: bad argument");
   return simt_dropout_mask(seed, layer, dropout_p, n_bonds * hidden, mask, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// End-to-end inference on host buffers
+// ------------------------------------------------------------------------------------------------
+extern "C" int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
+                                         int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src, int32_t* dst,
+                                         int32_t* in_ptr, int32_t* in_idx, int32_t* status, void* stream);
+namespace {
+struct HostInferLayout {
+  int64_t t_max, kp_x;
+  size_t o_x, o_ea, o_ei, o_meta, o_src, o_dst, o_inidx, o_inptr, o_status, o_xhi, o_xlo, o_out, o_fwd, dev_total;
+  size_t meta_ints, fwd_bytes, host_total;
+};
+HostInferLayout host_infer_layout(const cgr_params_t* p, int64_t N, int64_t E, int64_t B) {
+  HostInferLayout L;
+  L.t_max = 2 * E / 128 + 1 < B ? 2 * E / 128 + 1 : B;       // greedy packing: two consecutive tiles hold > 128 bonds
+  if (L.t_max < 1) L.t_max = 1;
+  L.kp_x = ((int64_t)p->fa + 63) / 64 * 64;
+  L.meta_ints = (size_t)L.t_max * 8 + 2 * (size_t)(B + 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += cgr_align_up(bytes, 1024); return o; };
+  L.o_x = take((size_t)N * p->fa * 4);
+  L.o_ea = take((size_t)E * (p->fb > 0 ? p->fb : 1) * 4);
+  L.o_ei = take((size_t)2 * E * 8);
+  L.o_meta = take(L.meta_ints * 4);
+  L.o_src = take((size_t)E * 4);
+  L.o_dst = take((size_t)E * 4);
+  L.o_inidx = take((size_t)E * 4);
+  L.o_inptr = take((size_t)(N + 1) * 4);
+  L.o_status = take((size_t)(2 + L.t_max) * 4);
+  L.o_xhi = take((size_t)N * L.kp_x * 2);
+  L.o_xlo = take((size_t)N * L.kp_x * 2);
+  L.o_out = take((size_t)B * 4);
+  cgr_graph_t g;
+  memset(&g, 0, sizeof(g));
+  g.n_atoms = N; g.n_bonds = E; g.n_rxn = B; g.n_tiles = L.t_max;
+  g.tile_info = (const int32_t*)16; g.x_hi = (const void*)16; g.x_lo = (const void*)16;   // non-null markers for sizing
+  cgr_params_t pp = *p;
+  if (!pp.tc_weights) pp.tc_weights = (const void*)16;
+  L.fwd_bytes = tc_forward_workspace(&pp, &g, 0);
+  L.o_fwd = take(L.fwd_bytes);
+  L.dev_total = off + 1024;
+  L.host_total = cgr_align_up(L.meta_ints * 4, 256) + 256;
+  return L;
+}
+}  // namespace
+
+extern "C" int cgr_infer_host_workspace(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                                        size_t* dev_bytes, size_t* host_bytes) {
+  CGR_CHECK_ARG(p && dev_bytes && host_bytes && n_atoms > 0 && n_bonds > 0 && n_rxn > 0, "cgr_infer_host_workspace: bad argument");
+  const HostInferLayout L = host_infer_layout(p, n_atoms, n_bonds, n_rxn);
+  *dev_bytes = L.dev_total;
+  *host_bytes = L.host_total;
+  return CGR_OK;
+}
+
+extern "C" int cgr_gnn_infer_host(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
+                                  const int64_t* host_edge_index, const int64_t* host_ptr, const int64_t* host_batch,
+                                  int64_t n_atoms, int64_t n_bonds, int64_t n_rxn, float* host_out, void* dev_ws,
+                                  size_t dev_bytes, void* host_ws, size_t host_bytes, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  CGR_CHECK_ARG(host_x && host_edge_index && host_out && dev_ws && host_ws, "cgr_gnn_infer_host: null pointer");
+  CGR_CHECK_ARG(p->fb == 0 || host_edge_attr, "cgr_gnn_infer_host: edge_attr missing");
+  CGR_CHECK_ARG(p->tc_weights, "cgr_gnn_infer_host: prepare the weights first (cgr_tc_prepare_weights)");
+  CGR_CHECK_ARG(n_atoms > 0 && n_bonds > 0 && n_rxn > 0 && (n_bonds & 1) == 0, "cgr_gnn_infer_host: bad sizes");
+  const int64_t N = n_atoms, E = n_bonds, B = n_rxn;
+  const HostInferLayout L = host_infer_layout(p, N, E, B);
+  CGR_CHECK_ARG(dev_bytes >= L.dev_total && host_bytes >= L.host_total, "cgr_gnn_infer_host: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* dws = (char*)(((uintptr_t)dev_ws + 1023) & ~(uintptr_t)1023);
+  int32_t* h_meta = (int32_t*)host_ws;
+  int32_t* h_tiles = h_meta;
+  int32_t* h_aptr = h_meta + (size_t)L.t_max * 8;
+  int32_t* h_eptr = h_aptr + (B + 1);
+  int32_t* h_flags = (int32_t*)((char*)host_ws + cgr_align_up(L.meta_ints * 4, 256));
+
+  // ---- host side: per-reaction offsets and the greedy tile plan (same rule as cgr_tc_plan_build) ----
+  if (host_ptr) {
+    for (int64_t g = 0; g <= B; ++g) h_aptr[g] = (int32_t)host_ptr[g];
+  } else if (host_batch) {
+    int64_t v = 0;
+    for (int64_t g = 0; g < B; ++g) {
+      h_aptr[g] = (int32_t)v;
+      while (v < N && host_batch[v] <= g) ++v;
+    }
+    h_aptr[B] = (int32_t)N;
+  } else {
+    CGR_CHECK_ARG(B == 1, "cgr_gnn_infer_host: neither ptr nor batch given for a multi-graph batch");
+    h_aptr[0] = 0; h_aptr[1] = (int32_t)N;
+  }
+  {
+    int64_t e = 0;
+    h_eptr[0] = 0;
+    for (int64_t g = 0; g < B; ++g) {          // bonds of a collated batch are grouped by reaction
+      const int64_t a1 = h_aptr[g + 1];
+      while (e < E && host_edge_index[e] < a1) ++e;
+      h_eptr[g + 1] = (int32_t)e;
+    }
+    if (e != E) { cgr_set_error("edge_index is not grouped by reaction"); return CGR_ERR_ARG; }
+  }
+  int64_t T = -1;
+  {
+    int used_e = 129, used_a = 129;
+    for (int64_t g = 0; g < B; ++g) {
+      const int ne = h_eptr[g + 1] - h_eptr[g], na = h_aptr[g + 1] - h_aptr[g];
+      if (ne > 128 || na > 128 || ne <= 0 || na <= 0 || (ne & 1)) {
+        cgr_set_error("reaction %lld has %d bonds / %d atoms: not tileable for the tcgen05 engine", (long long)g, ne, na);
+        return CGR_ERR_UNSUPPORTED;
+      }
+      if (used_e + ne > 128 || used_a + na > 128) {
+        ++T;
+        if (T >= L.t_max) { cgr_set_error("tile bound exceeded"); return CGR_ERR_WORKSPACE; }
+        int32_t* ti = h_tiles + T * 8;
+        ti[0] = h_eptr[g]; ti[1] = 0; ti[2] = h_aptr[g]; ti[3] = 0; ti[4] = (int32_t)g; ti[5] = 0; ti[6] = 0; ti[7] = 0;
+        used_e = 0; used_a = 0;
+      }
+      used_e += ne; used_a += na;
+      int32_t* ti = h_tiles + T * 8;
+      ti[1] = used_e; ti[3] = used_a; ti[5] += 1;
+    }
+    ++T;
+  }
+
+  // ---- stage inputs, build index arrays, run the forward, fetch the energies ----
+  float* d_x = (float*)(dws + L.o_x);
+  float* d_ea = (float*)(dws + L.o_ea);
+  int64_t* d_ei = (int64_t*)(dws + L.o_ei);
+  int32_t* d_meta = (int32_t*)(dws + L.o_meta);
+  int32_t* d_status = (int32_t*)(dws + L.o_status);
+  float* d_out = (float*)(dws + L.o_out);
+  CGR_CUDA(cudaMemcpyAsync(d_meta, h_meta, L.meta_ints * 4, cudaMemcpyHostToDevice, st));
+  CGR_CUDA(cudaMemcpyAsync(d_ei, host_edge_index, (size_t)2 * E * 8, cudaMemcpyHostToDevice, st));
+  CGR_CUDA(cudaMemcpyAsync(d_x, host_x, (size_t)N * p->fa * 4, cudaMemcpyHostToDevice, st));
+  if (p->fb > 0) CGR_CUDA(cudaMemcpyAsync(d_ea, host_edge_attr, (size_t)E * p->fb * 4, cudaMemcpyHostToDevice, st));
+  CGR_CUDA(cudaMemsetAsync(d_status, 0, (size_t)(2 + L.t_max) * 4, st));
+  cgr_graph_t g;
+  memset(&g, 0, sizeof(g));
+  g.n_atoms = N; g.n_bonds = E; g.n_rxn = B;
+  g.x = d_x; g.edge_attr = d_ea;
+  g.src = (int32_t*)(dws + L.o_src); g.dst = (int32_t*)(dws + L.o_dst);
+  g.in_ptr = (int32_t*)(dws + L.o_inptr); g.in_idx = (int32_t*)(dws + L.o_inidx);
+  g.tile_info = d_meta; g.n_tiles = T;
+  g.atom_ptr = d_meta + (size_t)L.t_max * 8;
+  g.tc_status = d_status + 1;
+  g.x_hi = dws + L.o_xhi; g.x_lo = dws + L.o_xlo;
+  rc = cgr_csr_build_by_reaction(d_ei, g.atom_ptr + (B + 1), g.atom_ptr, B, E, N, (int32_t*)g.src, (int32_t*)g.dst,
+                                 (int32_t*)g.in_ptr, (int32_t*)g.in_idx, d_status, stream);
+  if (rc) return rc;
+  rc = tc_split_features(d_x, N, p->fa, (void*)g.x_hi, (void*)g.x_lo, g.tc_status, st);
+  if (rc) return rc;
+  rc = tc_gnn_forward(p, &g, d_out, nullptr, 0, 0, dws + L.o_fwd, L.fwd_bytes, st);
+  if (rc) return rc;
+  CGR_CUDA(cudaMemcpyAsync(host_out, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CGR_CUDA(cudaMemcpyAsync(h_flags, d_status, 2 * 4, cudaMemcpyDeviceToHost, st));
+  CGR_CUDA(cudaStreamSynchronize(st));
+  if (h_flags[0] & 1) { cgr_set_error("directed bonds are not adjacent (e, e^1) reverse pairs"); return CGR_ERR_ARG; }
+  if (h_flags[0] & 2) { cgr_set_error("a bond leaves its reaction's atom range"); return CGR_ERR_ARG; }
+  if (h_flags[0] & 4) { cgr_set_error("an atom has no incoming bond (reference GNN.py:106 raises on this input)"); return CGR_ERR_ARG; }
+  if (h_flags[1]) { cgr_set_error("an activation exceeded the fp16 range of the FP16x3 split"); return CGR_ERR_UNSUPPORTED; }
+  return CGR_OK;
+}

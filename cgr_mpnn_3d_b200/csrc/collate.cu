@@ -191,7 +191,76 @@ __global__ void atom_ptr_kernel(const int64_t* __restrict__ batch, int64_t na, i
   for (int64_t g = prev + 1; g <= cur && g <= nb; ++g) atom_ptr[g] = (int32_t)v;
 }
 
+// One block per reaction: the whole CSR of a collated batch in ONE launch when per-reaction offsets are known.
+// Same result as cgr_csr_build (bit-exact), used by the host-buffer inference entry.
+constexpr int RX_MAX = 256;     // atoms / bonds of one reaction handled in shared memory
+__global__ void __launch_bounds__(128) csr_by_reaction_kernel(const int64_t* __restrict__ ei, const int32_t* __restrict__ edge_ptr,
+                                                              const int32_t* __restrict__ atom_ptr, int64_t ne, int64_t na,
+                                                              int64_t nb, int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                                              int32_t* __restrict__ in_ptr, int32_t* __restrict__ in_idx,
+                                                              int32_t* __restrict__ status) {
+  __shared__ int deg[RX_MAX], off[RX_MAX + 1], cur[RX_MAX];
+  __shared__ int32_t loc[RX_MAX];
+  const int g = blockIdx.x;
+  const int e0 = edge_ptr[g], e1 = edge_ptr[g + 1], a0 = atom_ptr[g], a1 = atom_ptr[g + 1];
+  const int n_e = e1 - e0, n_a = a1 - a0;
+  if (n_e > RX_MAX || n_a > RX_MAX || n_e < 0 || n_a < 0) { if (threadIdx.x == 0) atomicOr(status, 8); return; }
+  for (int v = threadIdx.x; v < n_a; v += blockDim.x) { deg[v] = 0; cur[v] = 0; }
+  __syncthreads();
+  int flag = 0;
+  for (int j = threadIdx.x; j < n_e; j += blockDim.x) {
+    const int64_t e = e0 + j, s = ei[e], d = ei[ne + e];
+    if (s < a0 || s >= a1 || d < a0 || d >= a1) flag |= 2;
+    const int64_t r = e ^ 1;
+    if (r >= ne || ei[r] != d || ei[ne + r] != s) flag |= 1;
+    src[e] = (int32_t)s;
+    dst[e] = (int32_t)d;
+    if (!(flag & 2)) atomicAdd(&deg[d - a0], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int v = 0; v < n_a; ++v) { off[v] = acc; acc += deg[v]; }
+    off[n_a] = acc;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < n_a; v += blockDim.x) {
+    in_ptr[a0 + v] = e0 + off[v];
+    if (deg[v] == 0) flag |= 4;
+  }
+  if (g == nb - 1 && threadIdx.x == 0) in_ptr[na] = (int32_t)ne;
+  for (int j = threadIdx.x; j < n_e; j += blockDim.x) {
+    const int d = dst[e0 + j] - a0;
+    if (d >= 0 && d < n_a) loc[off[d] + atomicAdd(&cur[d], 1)] = e0 + j;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < n_a; v += blockDim.x) {          // ascending bond id inside each atom's group
+    const int b = off[v], e = off[v + 1];
+    for (int i = b + 1; i < e; ++i) {
+      const int32_t key = loc[i];
+      int k = i - 1;
+      while (k >= b && loc[k] > key) { loc[k + 1] = loc[k]; --k; }
+      loc[k + 1] = key;
+    }
+    for (int i = b; i < e; ++i) in_idx[e0 + i] = loc[i];
+  }
+  if (flag) atomicOr(status, flag);
+}
+
 }  // namespace
+
+extern "C" int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
+                                         int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src, int32_t* dst,
+                                         int32_t* in_ptr, int32_t* in_idx, int32_t* status, void* stream) {
+  CGR_CHECK_ARG(edge_index && edge_ptr && atom_ptr && src && dst && in_ptr && in_idx && status && n_rxn > 0,
+                "cgr_csr_build_by_reaction: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cgr_note_launch("csr_by_reaction", st, 1);
+  csr_by_reaction_kernel<<<(unsigned)n_rxn, 128, 0, st>>>(edge_index, edge_ptr, atom_ptr, n_bonds, n_atoms, n_rxn, src,
+                                                          dst, in_ptr, in_idx, status);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
 
 extern "C" size_t cgr_collate_workspace(int64_t n_rxn) {
   return (size_t)(cgr_ceil_div(n_rxn > 0 ? n_rxn : 1, SCAN_TILE) + 1) * sizeof(int64_t);

@@ -158,6 +158,12 @@ class GNN(nn.Module):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the CGR hot path only exists as sm_100a kernels (no CPU fallback)")
         caller_device = x.device
+        if caller_device.type == "cpu" and not (torch.is_grad_enabled() and any(
+                p.requires_grad for p in self.parameters())) and not (self.training and any(
+                    float(p) > 0 for p in self.dropout_ps[: self.depth])) and getattr(self, "engine", "auto") != "simt":
+            out = self._infer_host(data)            # one C call on the host buffers (end-to-end entry)
+            if out is not None:
+                return out
         params = self._param_list()
         pdev = params[0].device
         dev = pdev if pdev.type == "cuda" else (caller_device if caller_device.type == "cuda"
@@ -206,6 +212,60 @@ class GNN(nn.Module):
             self.__dict__["_mirror_cache"] = cache
         return cache[1]
 
+    def _infer_host(self, data):
+        """Inference on HOST tensors through ``cgr_gnn_infer_host``: H2D staging, index arrays, tcgen05
+        forward and D2H of the energies in one call.  Returns None when the batch is not tileable (the
+        generic path then handles it)."""
+        import ctypes as C
+        from . import ops
+        if self.hidden_sizes[0] % 4 or self.depth > 13 or self.num_edge_features > 32:
+            return None
+        x, ei, ea = data.x, data.edge_index, data.edge_attr
+        batch, ptr = getattr(data, "batch", None), getattr(data, "ptr", None)
+        if x.dtype != torch.float32 or ea.dtype != torch.float32 or ei.dtype != torch.int64:
+            return None
+        x, ei, ea = x.contiguous(), ei.contiguous(), ea.contiguous()
+        n, e = int(x.shape[0]), int(ei.shape[1])
+        if ptr is not None:
+            ptr = ptr.contiguous()
+            b = int(ptr.numel()) - 1
+        elif batch is not None:
+            batch = batch.contiguous()
+            b = int(batch[-1]) + 1          # sorted ascending (PyG collate)
+        else:
+            b = 1
+        lib = _lib.load()
+        params = self._param_list()
+        pdev = params[0].device
+        dev = pdev if pdev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        dparams = params if pdev == dev else self._device_mirror(dev)
+        dparams = [p.detach() for p in dparams]
+        fa, fb = int(x.shape[1]), int(ea.shape[1])
+        tc_w = self._tc_weights(dparams, fa, fb)
+        ctx = ops._Ctx([ops._f32c(p) for p in dparams], self.depth, _act_id(self.activation_fn),
+                       bool(self.use_learnable_skip), fa, fb, [0.0] * self.depth)
+        ctx.params.tc_weights = tc_w.data_ptr()
+        with torch.cuda.device(dev):
+            dev_b, host_b = C.c_size_t(), C.c_size_t()
+            _lib.check(lib.cgr_infer_host_workspace(C.byref(ctx.params), n, e, b, C.byref(dev_b), C.byref(host_b)),
+                       "cgr_infer_host_workspace")
+            cache = self.__dict__.get("_host_ws")
+            if cache is None or cache[0].numel() < dev_b.value or cache[1].numel() < host_b.value \
+                    or cache[2].numel() < b or cache[0].device != dev:
+                cache = (torch.empty(int(dev_b.value * 1.25) + 4096, dtype=torch.uint8, device=dev),
+                         torch.empty(int(host_b.value * 1.25) + 4096, dtype=torch.uint8).pin_memory(),
+                         torch.empty(max(b, 64) * 2, dtype=torch.float32).pin_memory())
+                self.__dict__["_host_ws"] = cache
+            dws, hws, hout = cache
+            rc = lib.cgr_gnn_infer_host(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
+                                        _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(), dws.data_ptr(),
+                                        dws.numel(), hws.data_ptr(), hws.numel(),
+                                        torch.cuda.current_stream().cuda_stream)
+        if rc == -3:            # not tileable / fp16 range: generic path (layer-wise kernels)
+            return None
+        _lib.check(rc, "cgr_gnn_infer_host")
+        return hout[:b].clone()
+
     def check_numerics(self) -> None:
         """Synchronising check of the last tcgen05 forward: raises if an activation left the fp16 range
         of the FP16x3 split (then use ``engine='simt'``)."""
@@ -218,6 +278,7 @@ class GNN(nn.Module):
         state = self.__dict__.copy()
         state.pop("_mirror_cache", None)     # torch.save(model) must not pickle device mirrors
         state.pop("_tc_cache", None)
+        state.pop("_host_ws", None)
         state.pop("_last_plan", None)
         return state
 

@@ -127,6 +127,13 @@ int cgr_csr_build(const int64_t* edge_index, int64_t n_bonds, int64_t n_atoms, i
                   int32_t* dst, int32_t* in_ptr, int32_t* in_idx, int32_t* status,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same arrays in ONE launch (one block per reaction) when the per-reaction offsets edge_ptr / atom_ptr
+ * (int32 [B+1]) are known and every reaction has <= 256 atoms and bonds; `status` must be zeroed by the
+ * caller (bit 3 = a reaction exceeds the in-kernel limit). */
+int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
+                              int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src, int32_t* dst,
+                              int32_t* in_ptr, int32_t* in_idx, int32_t* status, void* stream);
+
 /* atom_ptr [B+1] (int32) from a sorted `batch` vector [N] int64 (Batch.batch). */
 int cgr_atom_ptr_from_batch(const int64_t* batch, int64_t n_atoms, int64_t n_rxn,
                             int32_t* atom_ptr, void* stream);
@@ -209,6 +216,21 @@ int cgr_tc_prepare_weights(const cgr_params_t* p, void* buffer, size_t buffer_by
 size_t cgr_tc_linear_workspace(int64_t m, int64_t n, int64_t k);
 int cgr_tc_linear(const float* x, int64_t m, int64_t k, const float* w, int64_t n, const float* bias,
                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * End-to-end inference on HOST buffers (what test.py:111-113 / the CLI :71-76 do per batch):
+ * stages x / edge_attr / edge_index to the device, builds the index arrays and the tile plan, runs the
+ * tcgen05 forward and copies the energies back to `host_out` [B]; returns after the stream is idle.
+ * host_ptr [B+1] (Batch.ptr) may be NULL when host_batch [N] is given (or both NULL for one graph).
+ * `dev_ws` / `host_ws` (pinned) sizes from cgr_infer_host_workspace.  p->tc_weights must be prepared.
+ * Returns CGR_ERR_UNSUPPORTED (-3) when a reaction does not fit a 128-bond tile (use the generic path).
+ * ---------------------------------------------------------------------------------------- */
+int cgr_infer_host_workspace(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                             size_t* dev_bytes, size_t* host_bytes);
+int cgr_gnn_infer_host(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
+                       const int64_t* host_edge_index, const int64_t* host_ptr, const int64_t* host_batch,
+                       int64_t n_atoms, int64_t n_bonds, int64_t n_rxn, float* host_out, void* dev_ws,
+                       size_t dev_bytes, void* host_ws, size_t host_bytes, void* stream);
 
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,

@@ -373,3 +373,47 @@ def test_tc_engine_refuses_untileable_graphs():
     oracle = build_oracle(meta).eval()
     with torch.no_grad():
         assert scale_normalised_error(out, oracle(data.to("cpu"))) < EA_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# end-to-end host-buffer entry (cgr_gnn_infer_host) and the one-launch per-reaction CSR
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nb,kind", [(1, "t1x"), (64, "t1x"), (700, "t1x"), (9, "drug")])
+def test_csr_by_reaction_bit_exact(nb, kind):
+    from cgr_mpnn_3d_b200 import _lib
+    from cgr_mpnn_3d_b200.collate import collate
+    lib = _lib.load()
+    graphs = make_reactions(nb, seed=17, kind=kind, fa=4)
+    dev = collate(graphs)
+    n, e = dev.num_nodes, dev.num_edges
+    i32 = dict(dtype=torch.int32, device="cuda")
+    src, dst, in_idx, in_ptr = torch.empty(e, **i32), torch.empty(e, **i32), torch.empty(e, **i32), torch.empty(n + 1, **i32)
+    status = torch.zeros(1, **i32)
+    _lib.check(lib.cgr_csr_build_by_reaction(dev.edge_index.data_ptr(), dev.edge_ptr.int().data_ptr(),
+                                             dev.ptr.int().data_ptr(), nb, e, n, src.data_ptr(), dst.data_ptr(),
+                                             in_ptr.data_ptr(), in_idx.data_ptr(), status.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "cgr_csr_build_by_reaction")
+    assert int(status.item()) == 0
+    csr = collate_oracle.csr_arrays(dev.edge_index.cpu().numpy(), n)
+    for k, t in (("src", src), ("dst", dst), ("in_ptr", in_ptr), ("in_idx", in_idx)):
+        assert np.array_equal(t.cpu().numpy(), csr[k]), k
+
+
+@pytest.mark.parametrize("name", ["small_skip", "small_gelu", "cfg2_d4_h400"])
+def test_host_buffer_inference_entry(name):
+    """CPU batch in, CPU energies out through ONE C call; also with `ptr` removed (batch vector only)."""
+    z, meta = load_case(name)
+    state = case_state_dict(z) if "x" in z.files else None
+    data = case_batch(z, meta)
+    model = build_model(meta, state, engine="auto").eval()
+    with torch.no_grad():
+        out = model(data)
+        nb = Batch(data.x, data.edge_index, data.edge_attr, data.batch, None, None)
+        out_nb = model(nb)
+    assert out.device.type == "cpu" and "_host_ws" in model.__dict__        # took the host-buffer entry
+    assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL
+    assert torch.equal(out, out_nb)
+    bad = Batch(data.x, data.edge_index.clone(), data.edge_attr, data.batch, data.ptr, None)
+    bad.edge_index[:, [0, 2]] = bad.edge_index[:, [2, 0]]
+    with torch.no_grad(), pytest.raises(RuntimeError, match="reverse pairs|atom range|grouped"):
+        model(bad)
