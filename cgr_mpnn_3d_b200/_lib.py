@@ -73,6 +73,8 @@ PROTOTYPES = {
     "cgr_csr_build_by_reaction": (C.c_int, [_V, _V, _V, _I64, _I64, _I64, _V, _V, _V, _V, _V, _V]),
     "cgr_infer_host_workspace": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "cgr_gnn_infer_host": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
+    "cgr_gnn_infer_host_async": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
+    "cgr_infer_host_check": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, _V]),
     "cgr_atom_ptr_from_batch": (C.c_int, [_V, _I64, _I64, _V, _V]),
     "cgr_edge_init_fwd": (C.c_int, [_V, _V, _V, _V, _V, _I64, _I64, _I32, _I32, _I32, _I32, _V, _V, _V, _SZ, _V]),
     "cgr_bond_update_fwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _I32, C.c_float, C.c_uint64, C.c_uint32,

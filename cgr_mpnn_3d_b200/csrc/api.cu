@@ -489,10 +489,11 @@ extern "C" int cgr_infer_host_workspace(const cgr_params_t* p, int64_t n_atoms, 
   return CGR_OK;
 }
 
-extern "C" int cgr_gnn_infer_host(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
-                                  const int64_t* host_edge_index, const int64_t* host_ptr, const int64_t* host_batch,
-                                  int64_t n_atoms, int64_t n_bonds, int64_t n_rxn, float* host_out, void* dev_ws,
-                                  size_t dev_bytes, void* host_ws, size_t host_bytes, void* stream) {
+extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
+                                        const int64_t* host_edge_index, const int64_t* host_ptr,
+                                        const int64_t* host_batch, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                                        float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
+                                        size_t host_bytes, void* stream) {
   int rc = check_params(p);
   if (rc) return rc;
   CGR_CHECK_ARG(host_x && host_edge_index && host_out && dev_ws && host_ws, "cgr_gnn_infer_host: null pointer");
@@ -588,10 +589,28 @@ extern "C" int cgr_gnn_infer_host(const cgr_params_t* p, const float* host_x, co
   if (rc) return rc;
   CGR_CUDA(cudaMemcpyAsync(host_out, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   CGR_CUDA(cudaMemcpyAsync(h_flags, d_status, 2 * 4, cudaMemcpyDeviceToHost, st));
-  CGR_CUDA(cudaStreamSynchronize(st));
+  return CGR_OK;
+}
+
+extern "C" int cgr_infer_host_check(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                                    const void* host_ws) {
+  CGR_CHECK_ARG(p && host_ws, "cgr_infer_host_check: null pointer");
+  const HostInferLayout L = host_infer_layout(p, n_atoms, n_bonds, n_rxn);
+  const int32_t* h_flags = (const int32_t*)((const char*)host_ws + cgr_align_up(L.meta_ints * 4, 256));
   if (h_flags[0] & 1) { cgr_set_error("directed bonds are not adjacent (e, e^1) reverse pairs"); return CGR_ERR_ARG; }
   if (h_flags[0] & 2) { cgr_set_error("a bond leaves its reaction's atom range"); return CGR_ERR_ARG; }
   if (h_flags[0] & 4) { cgr_set_error("an atom has no incoming bond (reference GNN.py:106 raises on this input)"); return CGR_ERR_ARG; }
   if (h_flags[1]) { cgr_set_error("an activation exceeded the fp16 range of the FP16x3 split"); return CGR_ERR_UNSUPPORTED; }
   return CGR_OK;
+}
+
+extern "C" int cgr_gnn_infer_host(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
+                                  const int64_t* host_edge_index, const int64_t* host_ptr, const int64_t* host_batch,
+                                  int64_t n_atoms, int64_t n_bonds, int64_t n_rxn, float* host_out, void* dev_ws,
+                                  size_t dev_bytes, void* host_ws, size_t host_bytes, void* stream) {
+  int rc = cgr_gnn_infer_host_async(p, host_x, host_edge_attr, host_edge_index, host_ptr, host_batch, n_atoms, n_bonds,
+                                    n_rxn, host_out, dev_ws, dev_bytes, host_ws, host_bytes, stream);
+  if (rc) return rc;
+  CGR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return cgr_infer_host_check(p, n_atoms, n_bonds, n_rxn, host_ws);
 }

@@ -212,20 +212,51 @@ class GNN(nn.Module):
             self.__dict__["_mirror_cache"] = cache
         return cache[1]
 
-    def _infer_host(self, data):
-        """Inference on HOST tensors through ``cgr_gnn_infer_host``: H2D staging, index arrays, tcgen05
-        forward and D2H of the energies in one call.  Returns None when the batch is not tileable (the
-        generic path then handles it)."""
-        import ctypes as C
+    # ------------------------------------------------------------------ host-buffer inference ----
+    def _host_ctx(self, fa: int, fb: int):
+        """ctypes parameter block + prepared tcgen05 weights, cached per parameter version."""
         from . import ops
-        if self.hidden_sizes[0] % 4 or self.depth > 13 or self.num_edge_features > 32:
-            return None
+        params = self._param_list()
+        key = tuple((p.data_ptr(), p._version) for p in params) + (fa, fb)
+        cache = self.__dict__.get("_host_ctx_cache")
+        if cache is not None and cache[0] == key:
+            return cache[1], cache[2]
+        pdev = params[0].device
+        dev = pdev if pdev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        dparams = params if pdev == dev else self._device_mirror(dev)
+        dparams = [ops._f32c(p.detach()) for p in dparams]
+        tc_w = self._tc_weights(dparams, fa, fb)
+        ctx = ops._Ctx(dparams, self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), fa, fb,
+                       [0.0] * self.depth)
+        ctx.params.tc_weights = tc_w.data_ptr()
+        ctx._keep = (dparams, tc_w)
+        self.__dict__["_host_ctx_cache"] = (key, ctx, dev)
+        return ctx, dev
+
+    def _host_slot(self, slot: int, ctx, dev, n: int, e: int, b: int):
+        import ctypes as C
+        lib = _lib.load()
+        slots = self.__dict__.setdefault("_host_slots", {})
+        cur = slots.get(slot)
+        dev_b, host_b = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.cgr_infer_host_workspace(C.byref(ctx.params), n, e, b, C.byref(dev_b), C.byref(host_b)),
+                   "cgr_infer_host_workspace")
+        if cur is None or cur[0].numel() < dev_b.value or cur[1].numel() < host_b.value or cur[2].numel() < b \
+                or cur[0].device != dev:
+            cur = (torch.empty(int(dev_b.value * 1.25) + 4096, dtype=torch.uint8, device=dev),
+                   torch.empty(int(host_b.value * 1.25) + 4096, dtype=torch.uint8).pin_memory(),
+                   torch.empty(max(b, 64) * 2, dtype=torch.float32).pin_memory(),
+                   torch.cuda.Stream(device=dev))
+            slots[slot] = cur
+        return cur
+
+    @staticmethod
+    def _host_fields(data):
         x, ei, ea = data.x, data.edge_index, data.edge_attr
         batch, ptr = getattr(data, "batch", None), getattr(data, "ptr", None)
         if x.dtype != torch.float32 or ea.dtype != torch.float32 or ei.dtype != torch.int64:
             return None
         x, ei, ea = x.contiguous(), ei.contiguous(), ea.contiguous()
-        n, e = int(x.shape[0]), int(ei.shape[1])
         if ptr is not None:
             ptr = ptr.contiguous()
             b = int(ptr.numel()) - 1
@@ -234,29 +265,26 @@ class GNN(nn.Module):
             b = int(batch[-1]) + 1          # sorted ascending (PyG collate)
         else:
             b = 1
+        return x, ei, ea, batch, ptr, int(x.shape[0]), int(ei.shape[1]), b
+
+    def _host_supported(self) -> bool:
+        return not (self.hidden_sizes[0] % 4 or self.depth > 13 or self.num_edge_features > 32)
+
+    def _infer_host(self, data):
+        """Inference on HOST tensors through ``cgr_gnn_infer_host``: H2D staging, index arrays, tcgen05
+        forward and D2H of the energies in one call.  Returns None when the batch is not tileable (the
+        generic path then handles it)."""
+        import ctypes as C
+        if not self._host_supported():
+            return None
+        f = self._host_fields(data)
+        if f is None:
+            return None
+        x, ei, ea, batch, ptr, n, e, b = f
         lib = _lib.load()
-        params = self._param_list()
-        pdev = params[0].device
-        dev = pdev if pdev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
-        dparams = params if pdev == dev else self._device_mirror(dev)
-        dparams = [p.detach() for p in dparams]
-        fa, fb = int(x.shape[1]), int(ea.shape[1])
-        tc_w = self._tc_weights(dparams, fa, fb)
-        ctx = ops._Ctx([ops._f32c(p) for p in dparams], self.depth, _act_id(self.activation_fn),
-                       bool(self.use_learnable_skip), fa, fb, [0.0] * self.depth)
-        ctx.params.tc_weights = tc_w.data_ptr()
+        ctx, dev = self._host_ctx(int(x.shape[1]), int(ea.shape[1]))
         with torch.cuda.device(dev):
-            dev_b, host_b = C.c_size_t(), C.c_size_t()
-            _lib.check(lib.cgr_infer_host_workspace(C.byref(ctx.params), n, e, b, C.byref(dev_b), C.byref(host_b)),
-                       "cgr_infer_host_workspace")
-            cache = self.__dict__.get("_host_ws")
-            if cache is None or cache[0].numel() < dev_b.value or cache[1].numel() < host_b.value \
-                    or cache[2].numel() < b or cache[0].device != dev:
-                cache = (torch.empty(int(dev_b.value * 1.25) + 4096, dtype=torch.uint8, device=dev),
-                         torch.empty(int(host_b.value * 1.25) + 4096, dtype=torch.uint8).pin_memory(),
-                         torch.empty(max(b, 64) * 2, dtype=torch.float32).pin_memory())
-                self.__dict__["_host_ws"] = cache
-            dws, hws, hout = cache
+            dws, hws, hout, _ = self._host_slot(0, ctx, dev, n, e, b)
             rc = lib.cgr_gnn_infer_host(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
                                         _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(), dws.data_ptr(),
                                         dws.numel(), hws.data_ptr(), hws.numel(),
@@ -265,6 +293,54 @@ class GNN(nn.Module):
             return None
         _lib.check(rc, "cgr_gnn_infer_host")
         return hout[:b].clone()
+
+    def predict_stream(self, batches, depth: int = 3):
+        """Pipelined inference over an iterable of HOST batches (the screening workload): yields one CPU
+        tensor of energies per batch, in order.  Up to ``depth`` batches are in flight, each on its own
+        stream with its own staging buffers, so the H2D copy of batch i+1 overlaps the kernels of batch i
+        (``cgr_gnn_infer_host_async``).  Batches that cannot use the tcgen05 engine go through ``forward``."""
+        import ctypes as C
+        from collections import deque
+        lib = _lib.load()
+        pending = deque()
+
+        def finish():
+            slot, ctx, n, e, b, keep = pending.popleft()
+            dws, hws, hout, st = slot
+            st.synchronize()
+            _lib.check(lib.cgr_infer_host_check(C.byref(ctx.params), n, e, b, hws.data_ptr()), "cgr_infer_host_check")
+            return hout[:b].clone()
+
+        i = 0
+        with torch.no_grad():
+            for data in batches:
+                f = self._host_fields(data) if (self._host_supported() and data.x.device.type == "cpu") else None
+                if f is None:
+                    while pending:
+                        yield finish()
+                    yield self.forward(data)
+                    continue
+                x, ei, ea, batch, ptr, n, e, b = f
+                ctx, dev = self._host_ctx(int(x.shape[1]), int(ea.shape[1]))
+                if len(pending) >= depth:
+                    yield finish()
+                with torch.cuda.device(dev):
+                    slot = self._host_slot(1 + i % depth, ctx, dev, n, e, b)
+                    dws, hws, hout, st = slot
+                    rc = lib.cgr_gnn_infer_host_async(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
+                                                      _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(),
+                                                      dws.data_ptr(), dws.numel(), hws.data_ptr(), hws.numel(),
+                                                      st.cuda_stream)
+                if rc == -3:
+                    while pending:
+                        yield finish()
+                    yield self.forward(data)
+                    continue
+                _lib.check(rc, "cgr_gnn_infer_host_async")
+                pending.append((slot, ctx, n, e, b, (x, ei, ea, batch, ptr)))
+                i += 1
+            while pending:
+                yield finish()
 
     def check_numerics(self) -> None:
         """Synchronising check of the last tcgen05 forward: raises if an activation left the fp16 range
@@ -278,7 +354,8 @@ class GNN(nn.Module):
         state = self.__dict__.copy()
         state.pop("_mirror_cache", None)     # torch.save(model) must not pickle device mirrors
         state.pop("_tc_cache", None)
-        state.pop("_host_ws", None)
+        state.pop("_host_slots", None)
+        state.pop("_host_ctx_cache", None)
         state.pop("_last_plan", None)
         return state
 

@@ -232,6 +232,15 @@ int cgr_gnn_infer_host(const cgr_params_t* p, const float* host_x, const float* 
                        int64_t n_atoms, int64_t n_bonds, int64_t n_rxn, float* host_out, void* dev_ws,
                        size_t dev_bytes, void* host_ws, size_t host_bytes, void* stream);
 
+/* Asynchronous flavour for pipelining several batches over streams: enqueues everything on `stream` and
+ * returns; after the stream is synchronised, cgr_infer_host_check decodes the validity flags in host_ws. */
+int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
+                             const int64_t* host_edge_index, const int64_t* host_ptr, const int64_t* host_batch,
+                             int64_t n_atoms, int64_t n_bonds, int64_t n_rxn, float* host_out, void* dev_ws,
+                             size_t dev_bytes, void* host_ws, size_t host_bytes, void* stream);
+int cgr_infer_host_check(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                         const void* host_ws);
+
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,
                         float* grad_pred, void* stream);

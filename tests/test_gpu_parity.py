@@ -389,8 +389,9 @@ def test_csr_by_reaction_bit_exact(nb, kind):
     i32 = dict(dtype=torch.int32, device="cuda")
     src, dst, in_idx, in_ptr = torch.empty(e, **i32), torch.empty(e, **i32), torch.empty(e, **i32), torch.empty(n + 1, **i32)
     status = torch.zeros(1, **i32)
-    _lib.check(lib.cgr_csr_build_by_reaction(dev.edge_index.data_ptr(), dev.edge_ptr.int().data_ptr(),
-                                             dev.ptr.int().data_ptr(), nb, e, n, src.data_ptr(), dst.data_ptr(),
+    eptr32, aptr32 = dev.edge_ptr.int(), dev.ptr.int()
+    _lib.check(lib.cgr_csr_build_by_reaction(dev.edge_index.data_ptr(), eptr32.data_ptr(),
+                                             aptr32.data_ptr(), nb, e, n, src.data_ptr(), dst.data_ptr(),
                                              in_ptr.data_ptr(), in_idx.data_ptr(), status.data_ptr(),
                                              torch.cuda.current_stream().cuda_stream), "cgr_csr_build_by_reaction")
     assert int(status.item()) == 0
@@ -410,9 +411,13 @@ def test_host_buffer_inference_entry(name):
         out = model(data)
         nb = Batch(data.x, data.edge_index, data.edge_attr, data.batch, None, None)
         out_nb = model(nb)
-    assert out.device.type == "cpu" and "_host_ws" in model.__dict__        # took the host-buffer entry
+    assert out.device.type == "cpu" and "_host_slots" in model.__dict__     # took the host-buffer entry
     assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL
     assert torch.equal(out, out_nb)
+    # pipelined API over several host batches: same numbers, in order
+    many = [data, nb, data]
+    outs = list(model.predict_stream(many, depth=2))
+    assert len(outs) == 3 and all(torch.equal(o, out) for o in outs)
     bad = Batch(data.x, data.edge_index.clone(), data.edge_attr, data.batch, data.ptr, None)
     bad.edge_index[:, [0, 2]] = bad.edge_index[:, [2, 0]]
     with torch.no_grad(), pytest.raises(RuntimeError, match="reverse pairs|atom range|grouped"):
