@@ -15,6 +15,7 @@
 #include "tc.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_gemm.cuh"
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(256) tc_edge_init_kernel(const float* __restri
   const int tile = blockIdx.y;
   const int ebase = __ldg(tile_info + tile * 8), ecount = __ldg(tile_info + tile * 8 + 1);
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  umma::grid_dep_launch();
+  umma::grid_dep_wait();                          // PQ comes from the atom-projection kernel
   if (j >= ecount) return;
   const int64_t e = (int64_t)ebase + j, r = (int64_t)tile * TM + j;
   const float* prow = PQ + (int64_t)__ldg(src + e) * ldpq;
@@ -296,7 +299,7 @@ WLayout wlayout(const cgr_params_t* p) {
 }
 
 template <int BN, int EPI, bool RELU>
-int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char* name, cudaStream_t st) {
+int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char* name, bool pdl, cudaStream_t st) {
   using C = Cfg<BN, EPI>;
   static bool attr_done = false;      // benign race: the attribute is idempotent
   if (!attr_done) {
@@ -306,8 +309,18 @@ int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char
   }
   CgrRange prof(name, st);
   cgr_note_launch(name, st, 1);
-  tc_gemm_kernel<BN, EPI, RELU><<<dim3((unsigned)n_slices, (unsigned)m_tiles), THREADS, C::SMEM_BYTES, st>>>(prm);
-  CGR_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)n_slices, (unsigned)m_tiles);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;                    // pdl: this launch may overlap the tail of its predecessor
+  CGR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, EPI, RELU>, prm));
   return CGR_OK;
 }
 
@@ -321,14 +334,14 @@ int choose_bn(int64_t m_tiles, int64_t n_total) {
 int chunk_cols(int bn) { return bn > 128 ? bn / 2 : bn; }
 
 template <int EPI>
-int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const char* name, cudaStream_t st) {
+int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const char* name, bool pdl, cudaStream_t st) {
   const int n_slices = (int)cgr_ceil_div(prm.n_total, bn);
   if (bn == BN_LARGE) {
-    return relu ? launch_gemm_t<BN_LARGE, EPI, true>(prm, m_tiles, n_slices, name, st)
-                : launch_gemm_t<BN_LARGE, EPI, false>(prm, m_tiles, n_slices, name, st);
+    return relu ? launch_gemm_t<BN_LARGE, EPI, true>(prm, m_tiles, n_slices, name, pdl, st)
+                : launch_gemm_t<BN_LARGE, EPI, false>(prm, m_tiles, n_slices, name, pdl, st);
   }
-  return relu ? launch_gemm_t<BN_SMALL, EPI, true>(prm, m_tiles, n_slices, name, st)
-              : launch_gemm_t<BN_SMALL, EPI, false>(prm, m_tiles, n_slices, name, st);
+  return relu ? launch_gemm_t<BN_SMALL, EPI, true>(prm, m_tiles, n_slices, name, pdl, st)
+              : launch_gemm_t<BN_SMALL, EPI, false>(prm, m_tiles, n_slices, name, pdl, st);
 }
 
 }  // namespace
@@ -477,6 +490,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   __half* h_hi[2] = {(__half*)(ws + w.off_hhi[0]), (__half*)(ws + w.off_hhi[1])};
   __half* h_lo[2] = {(__half*)(ws + w.off_hlo[0]), (__half*)(ws + w.off_hlo[1])};
   float* partial = (float*)(ws + w.off_partial);
+  static const bool use_pdl = getenv("CGR_NO_PDL") == nullptr;   // programmatic dependent launch between the kernels
   int* flag = g->tc_status;              // [0] sticky fp16-range flag, [1..T] readout arrival counters
   int* tile_counter = g->tc_status + 1;
 
@@ -503,17 +517,26 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.bias = bias_cat;
     prm.out_f32 = PQ;
     prm.ldc = 2 * H;
-    rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", st);
+    rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false, st);
     if (rc) return rc;
   }
   // 3. edge initialisation on tile-packed rows
   {
     CgrRange prof("tc_edge_init", st);
     cgr_note_launch("tc_edge_init", st, 1);
-    tc_edge_init_kernel<<<dim3(TM / 8, (unsigned)T), 256, 0, st>>>(PQ, 2 * H, g->edge_attr, g->src,
-                                                                   (const float*)(wbuf + wl.off_wet), g->tile_info, fb,
-                                                                   H, p->act, h0, h_hi[0], h_lo[0], w.kp_h, flag);
-    CGR_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(TM / 8, (unsigned)T);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    CGR_CUDA(cudaLaunchKernelEx(&cfg, tc_edge_init_kernel, (const float*)PQ, (int64_t)(2 * H), g->edge_attr, g->src,
+                                (const float*)(wbuf + wl.off_wet), g->tile_info, fb, H, (int)p->act, h0, h_hi[0],
+                                h_lo[0], (int64_t)w.kp_h, flag));
   }
   // 4. message passing layers: one fused kernel each
   const int bn_h = choose_bn(T, H);
@@ -541,7 +564,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.o_hi = h_hi[ob]; prm.o_lo = h_lo[ob]; prm.ldo = w.kp_h;
     prm.overflow = flag;
     prm.dbg = g_tc_dbg;
-    rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", st);
+    rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", use_pdl, st);
     if (rc) return rc;
   }
   // 5. readout + pooling + FFN
@@ -568,7 +591,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.partial_out = partial;
     prm.n_rxn = B;
     prm.overflow = flag;
-    rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", st);
+    rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", use_pdl, st);
     if (rc) return rc;
   }
   return CGR_OK;
@@ -618,5 +641,5 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   prm.bias = bias;
   prm.out_f32 = out;
   prm.ldc = N;
-  return launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(M, TM), true, "tc_linear", st);
+  return launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(M, TM), true, "tc_linear", false, st);
 }

@@ -162,11 +162,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   const uint32_t tmem = aux->tmem_base;
   const int r_row0 = EPI == EPI_BOND ? tile * TM : (EPI == EPI_READOUT ? aux->info[2] : 0);
   TC_STAMP(1);
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, tile info) only touches
+  // data that no earlier kernel of the forward writes; let the next kernel start its own prologue now
+  if (threadIdx.x == 0) umma::grid_dep_launch();
 
   // ------------------------------------------------------------------ main loop (warp-specialised)
   if (warp == 0) {
     // TMA producer: one elected lane streams A (hi, lo) and B (hi, lo) k-chunks through the ring and
     // prefetches the first column chunk of the epilogue's fp32 operand
+    if (lane == 0) umma::grid_dep_wait();          // A / R operands are outputs of the previous kernel
     if (lane == 0 && EPI != EPI_PLAIN) {
       const uint32_t rb = umma::smem_u32(&aux->r_full[0]);
       umma::mbar_arrive_expect_tx(rb, C::R_BYTES);
