@@ -298,12 +298,13 @@ WLayout wlayout(const cgr_params_t* p) {
   return w;
 }
 
-template <int BN, int EPI, bool RELU>
+template <int BN, int EPI, bool RELU, int NT>
 int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char* name, bool pdl, cudaStream_t st) {
-  using C = Cfg<BN, EPI>;
+  using C = Cfg<BN, EPI, NT>;
+  constexpr int THREADS = NT;
   static bool attr_done = false;      // benign race: the attribute is idempotent
   if (!attr_done) {
-    CGR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CGR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, RELU, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
     attr_done = true;
   }
@@ -320,11 +321,12 @@ int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;                    // pdl: this launch may overlap the tail of its predecessor
-  CGR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, EPI, RELU>, prm));
+  CGR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, EPI, RELU, NT>, prm));
   return CGR_OK;
 }
 
 constexpr int BN_SMALL = 80, BN_LARGE = 208;
+constexpr int NT_SMALL = 256;     // narrow slices run two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
 
 // Slice width: wide slices (208) amortise the A-operand fetch of the SS-mode MMA and halve the A re-reads;
 // narrow slices (80) give small batches enough CTAs to occupy the 148 SMs.
@@ -337,11 +339,11 @@ template <int EPI>
 int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const char* name, bool pdl, cudaStream_t st) {
   const int n_slices = (int)cgr_ceil_div(prm.n_total, bn);
   if (bn == BN_LARGE) {
-    return relu ? launch_gemm_t<BN_LARGE, EPI, true>(prm, m_tiles, n_slices, name, pdl, st)
-                : launch_gemm_t<BN_LARGE, EPI, false>(prm, m_tiles, n_slices, name, pdl, st);
+    return relu ? launch_gemm_t<BN_LARGE, EPI, true, 512>(prm, m_tiles, n_slices, name, pdl, st)
+                : launch_gemm_t<BN_LARGE, EPI, false, 512>(prm, m_tiles, n_slices, name, pdl, st);
   }
-  return relu ? launch_gemm_t<BN_SMALL, EPI, true>(prm, m_tiles, n_slices, name, pdl, st)
-              : launch_gemm_t<BN_SMALL, EPI, false>(prm, m_tiles, n_slices, name, pdl, st);
+  return relu ? launch_gemm_t<BN_SMALL, EPI, true, NT_SMALL>(prm, m_tiles, n_slices, name, pdl, st)
+              : launch_gemm_t<BN_SMALL, EPI, false, NT_SMALL>(prm, m_tiles, n_slices, name, pdl, st);
 }
 
 }  // namespace

@@ -14,8 +14,6 @@ namespace tcg {
 constexpr int TM = 128;                 // rows of a tile (UMMA M)
 constexpr int BK = 64;                  // fp16 elements per k-chunk = one 128-byte swizzle row
 constexpr int A_BYTES = TM * BK * 2;    // 16 KB
-constexpr int THREADS = 512;           // 16 warps: 1 TMA, 1 MMA, 14 staging; all 16 run the epilogue
-constexpr int NWARPS = THREADS / 32;
 constexpr int AUX_BYTES = 4096;
 constexpr int SMEM_LIMIT = 232448;      // 227 KB opt-in maximum per CTA
 constexpr int RU = 4;                   // rows processed together by a warp in the epilogue (ILP)
@@ -23,8 +21,15 @@ constexpr int NBR = 8;                  // neighbour slots per row kept in the p
 
 enum { EPI_PLAIN = 0, EPI_BOND = 1, EPI_READOUT = 2 };
 
-template <int BN_, int EPI>
+// NT = threads per CTA.  NT=512: one CTA per SM, deep pipeline, dedicated buffer for the prefetched fp32 operand.
+// NT=256: two CTAs per SM (<= 113 KB each): 2-stage pipeline, the fp32 operand is loaded into the drained pipeline
+// after the GEMM -- its latency and the whole epilogue of one CTA hide behind the other CTA's MMA stream.
+template <int BN_, int EPI, int NT_>
 struct Cfg {
+  static constexpr int NT = NT_;
+  static constexpr int NWARPS = NT / 32;
+  static constexpr int CTAS_PER_SM = NT <= 256 ? 2 : 1;
+  static constexpr bool R_ALIAS = CTAS_PER_SM > 1;      // fp32 operand chunk 0 lives in the drained pipeline
   static constexpr int BN = BN_;                          // output columns per CTA (UMMA N), multiple of 16
   static constexpr int NCH = BN > 128 ? 2 : 1;            // epilogue column chunks
   static constexpr int CH = BN / NCH;                     // columns per chunk (80 / 104 / 128)
@@ -32,20 +37,24 @@ struct Cfg {
   static constexpr int VL = CH / 4;                       // lanes owning a float4 column group
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int R_BYTES = EPI == EPI_PLAIN ? 0 : TM * CH * 4;   // TMA-prefetched fp32 epilogue operand
+  static constexpr int R_BYTES = EPI == EPI_PLAIN ? 0 : TM * CH * 4;   // TMA-loaded fp32 epilogue operand (one chunk)
+  static constexpr int R_DEDICATED = R_ALIAS ? 0 : R_BYTES;
   static constexpr int Y_BYTES = ((TM * CHP * 4 + 127) / 128) * 128;
-  static constexpr int FIT = (SMEM_LIMIT - R_BYTES - AUX_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int BUDGET = SMEM_LIMIT / CTAS_PER_SM - (CTAS_PER_SM > 1 ? 1024 : 0);
+  static constexpr int FIT = (BUDGET - R_DEDICATED - AUX_BYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 4 ? 4 : FIT;
   // [B_hi ; B_lo] are adjacent in a stage, so A_hi x [B_hi;B_lo] is ONE MMA of N = 2*BN when that fits the
   // 256-column instruction limit: 2 MMAs per k-step instead of 3, and A_hi / B_hi are fetched once less
   static constexpr bool CAT = 2 * BN <= 256;
   static constexpr int ACC_COLS = CAT ? 2 * BN : BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + R_BYTES + AUX_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + R_DEDICATED + AUX_BYTES + 1024;
   static_assert(BN % 16 == 0 && BN <= 256 && CH % 4 == 0 && VL <= 32, "bad slice width");
   static_assert(STAGES >= 2, "pipeline needs two stages");
-  static_assert(Y_BYTES + (NCH > 1 ? R_BYTES : 0) <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
-  static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
+  static_assert(Y_BYTES + ((NCH > 1 || R_ALIAS) ? R_BYTES : 0) <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
+  static_assert(!(R_ALIAS && NCH > 1), "aliased fp32 operand supports a single column chunk");
+  static_assert(SMEM_BYTES <= BUDGET, "shared memory budget");
+  static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "TMEM budget");
 };
 
 struct TcGemmParams {
@@ -112,17 +121,19 @@ template <bool RELU>
 __device__ __forceinline__ float act_t(float z, int act) { return RELU ? fmaxf(z, 0.f) : cgr_act(z, act); }
 
 // RELU: compile-time fast path for the reference's default activation (branch-free epilogue)
-template <int BN_, int EPI, bool RELU>
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
-  using C = Cfg<BN_, EPI>;
+template <int BN_, int EPI, bool RELU, int NT_>
+__global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+  using C = Cfg<BN_, EPI, NT_>;
+  constexpr int THREADS = C::NT, NWARPS = C::NWARPS;
   constexpr int BN = C::BN, CH = C::CH, CHP = C::CHP, VL = C::VL, NCH = C::NCH, STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = umma::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  float* r0_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);         // [TM][CH] dense, chunk 0
-  Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES + C::R_BYTES);
+  // fp32 operand chunk 0: dedicated buffer (prefetched during the GEMM) or, with two CTAs per SM, the drained pipeline
+  float* r0_s = reinterpret_cast<float*>(C::R_ALIAS ? smem + C::Y_BYTES : smem + STAGES * STAGE_BYTES);
+  Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES + C::R_DEDICATED);
   float* y_s = reinterpret_cast<float*>(smem);                                  // [TM][CHP], aliases the drained pipeline
   float* r1_s = reinterpret_cast<float*>(smem + C::Y_BYTES);                    // [TM][CH], chunk 1 (alias)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     // TMA producer: one elected lane streams A (hi, lo) and B (hi, lo) k-chunks through the ring and
     // prefetches the first column chunk of the epilogue's fp32 operand
     if (lane == 0) umma::grid_dep_wait();          // A / R operands are outputs of the previous kernel
-    if (lane == 0 && EPI != EPI_PLAIN) {
+    if (lane == 0 && EPI != EPI_PLAIN && !C::R_ALIAS) {
       const uint32_t rb = umma::smem_u32(&aux->r_full[0]);
       umma::mbar_arrive_expect_tx(rb, C::R_BYTES);
       umma::tma_load_2d(&p.tmR, rb, umma::smem_u32(r0_s), p.r_col0 + n0, r_row0);
@@ -280,6 +291,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   umma::mbar_wait(umma::smem_u32(&aux->tmem_full), 0);
   umma::tc_fence_after_sync();
   TC_STAMP(2);
+  if (C::R_ALIAS && EPI != EPI_PLAIN && threadIdx.x == 0) {
+    // every MMA has retired and every pipeline load has landed: the stage buffers are free for the fp32 operand
+    const uint32_t rb = umma::smem_u32(&aux->r_full[0]);
+    umma::mbar_arrive_expect_tx(rb, C::R_BYTES);
+    umma::tma_load_2d(&p.tmR, rb, umma::smem_u32(r0_s), p.r_col0 + n0, r_row0);
+  }
   if (NCH > 1 && EPI != EPI_PLAIN && threadIdx.x == 0) {
     // second column chunk of the fp32 operand goes into the drained pipeline buffers
     const uint32_t rb = umma::smem_u32(&aux->r_full[1]);
