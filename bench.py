@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent steps are pipelined over")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over")
     ap.add_argument("--train", action="store_true", help="also time the training step (fwd+loss+bwd[+allreduce])")
     return ap.parse_args()
 
@@ -224,6 +224,8 @@ def main():
 
     engine = args.engine
     model = build_model(engine, dev).eval()
+    model.tile_policy = "throughput" if (args.streams > 1 and not args.no_graph) else "latency"
+    lat_model = build_model(engine, dev).eval()      # latency configuration for the single-stream figure
     n_pool = max(2, args.pool)
     host = [make_batch(args.batch, seed=1000 + 997 * rank + i, kind="t1x", fa=FA) for i in range(n_pool)]
     for hb in host:
@@ -301,15 +303,28 @@ def main():
         barrier()
         clocks.mark_end()
         ms_total = ev0.elapsed_time(ev1)
-        # single-stream latency of one step (same graphs, back to back on one stream), for reference
+        # single-stream latency of one step with the latency kernel configuration (one CTA per SM), for reference
+        n_lg = min(8, n_pool)
+        lat_graphs = []
+        for i in range(n_lg):
+            lat_model(pool[i])
+        if graphs is not None:
+            for i in range(n_lg):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    lat_model(pool[i])
+                lat_graphs.append(g)
         lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_lat = min(args.steps, 200)
+        n_lat = min(args.steps, 400)
+        for i in range(n_lg):
+            lat_graphs[i].replay() if lat_graphs else lat_model(pool[i])
+        torch.cuda.synchronize()
         lat0.record(main)
         for i in range(n_lat):
-            if graphs is not None:
-                graphs[i % n_pool].replay()
+            if lat_graphs:
+                lat_graphs[i % n_lg].replay()
             else:
-                outs[i % n_pool] = model(pool[i % n_pool])
+                lat_model(pool[i % n_lg])
         lat1.record(main)
         torch.cuda.synchronize()
         single_stream_ms = lat0.elapsed_time(lat1) / n_lat

@@ -30,6 +30,7 @@ class CgrParams(C.Structure):
         ("w_e2n", C.c_void_p), ("b_e2n", C.c_void_p), ("w_ffn", C.c_void_p), ("b_ffn", C.c_void_p),
         ("host_dropout_p", c_float_p),
         ("tc_weights", C.c_void_p),
+        ("tc_throughput", C.c_int32),
     ]
 
 

@@ -335,9 +335,15 @@ int choose_bn(int64_t m_tiles, int64_t n_total) {
 }
 int chunk_cols(int bn) { return bn > 128 ? bn / 2 : bn; }
 
+// two_per_sm: 256-thread CTAs, two per SM (throughput); otherwise 512-thread CTAs, one per SM (latency)
 template <int EPI>
-int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const char* name, bool pdl, cudaStream_t st) {
+int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const char* name, bool pdl, bool two_per_sm,
+                cudaStream_t st) {
   const int n_slices = (int)cgr_ceil_div(prm.n_total, bn);
+  if (bn == BN_SMALL && !two_per_sm) {
+    return relu ? launch_gemm_t<BN_SMALL, EPI, true, 512>(prm, m_tiles, n_slices, name, pdl, st)
+                : launch_gemm_t<BN_SMALL, EPI, false, 512>(prm, m_tiles, n_slices, name, pdl, st);
+  }
   if (bn == BN_LARGE) {
     return relu ? launch_gemm_t<BN_LARGE, EPI, true, 512>(prm, m_tiles, n_slices, name, pdl, st)
                 : launch_gemm_t<BN_LARGE, EPI, false, 512>(prm, m_tiles, n_slices, name, pdl, st);
@@ -493,6 +499,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   __half* h_lo[2] = {(__half*)(ws + w.off_hlo[0]), (__half*)(ws + w.off_hlo[1])};
   float* partial = (float*)(ws + w.off_partial);
   static const bool use_pdl = getenv("CGR_NO_PDL") == nullptr;   // programmatic dependent launch between the kernels
+  // grids larger than the machine, or forwards pipelined over streams by the caller, run two CTAs per SM
+  auto two_per_sm = [&](int64_t ctas) { return p->tc_throughput != 0 || ctas > 148; };
   int* flag = g->tc_status;              // [0] sticky fp16-range flag, [1..T] readout arrival counters
   int* tile_counter = g->tc_status + 1;
 
@@ -519,7 +527,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.bias = bias_cat;
     prm.out_f32 = PQ;
     prm.ldc = 2 * H;
-    rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false, st);
+    rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false,
+                                two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
     if (rc) return rc;
   }
   // 3. edge initialisation on tile-packed rows
@@ -566,7 +575,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.o_hi = h_hi[ob]; prm.o_lo = h_lo[ob]; prm.ldo = w.kp_h;
     prm.overflow = flag;
     prm.dbg = g_tc_dbg;
-    rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", use_pdl, st);
+    rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
   }
   // 5. readout + pooling + FFN
@@ -593,7 +602,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.partial_out = partial;
     prm.n_rxn = B;
     prm.overflow = flag;
-    rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", use_pdl, st);
+    rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
   }
   return CGR_OK;
@@ -643,5 +652,5 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   prm.bias = bias;
   prm.out_f32 = out;
   prm.ldc = N;
-  return launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(M, TM), true, "tc_linear", false, st);
+  return launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(M, TM), true, "tc_linear", false, false, st);
 }

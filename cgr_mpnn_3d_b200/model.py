@@ -93,6 +93,9 @@ class GNN(nn.Module):
         self.pooling_fn = pooling_fn
         self.use_learnable_skip = use_learnable_skip
         self.engine = "auto"
+        #: "latency": a lone forward gets the one-CTA-per-SM kernels; "throughput": the caller pipelines several
+        #: forwards over CUDA streams (bench, predict_stream) and wants the two-CTAs-per-SM configuration
+        self.tile_policy = "latency"
 
         self.edge_init = nn.Linear(num_node_features + num_edge_features, self.hidden_sizes[0])
         self.convs = nn.ModuleList()
@@ -195,7 +198,8 @@ class GNN(nn.Module):
             x_hi = x_lo = torch.empty(0, dtype=torch.float16, device=dev)
         res = ops.gnn_forward(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr, params,
                               self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
-                              train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo)
+                              train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo,
+                              getattr(self, "tile_policy", "latency") == "throughput")
         self.__dict__["_last_plan"] = plan if engine == _lib.ENGINE_TC else None
         out = res[0]
         if caller_device != dev:
@@ -230,6 +234,7 @@ class GNN(nn.Module):
                        [0.0] * self.depth)
         ctx.params.tc_weights = tc_w.data_ptr()
         ctx._keep = (dparams, tc_w)
+        ctx.params.tc_throughput = 0
         self.__dict__["_host_ctx_cache"] = (key, ctx, dev)
         return ctx, dev
 
@@ -285,6 +290,7 @@ class GNN(nn.Module):
         ctx, dev = self._host_ctx(int(x.shape[1]), int(ea.shape[1]))
         with torch.cuda.device(dev):
             dws, hws, hout, _ = self._host_slot(0, ctx, dev, n, e, b)
+            ctx.params.tc_throughput = 0
             rc = lib.cgr_gnn_infer_host(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
                                         _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(), dws.data_ptr(),
                                         dws.numel(), hws.data_ptr(), hws.numel(),
@@ -327,6 +333,7 @@ class GNN(nn.Module):
                 with torch.cuda.device(dev):
                     slot = self._host_slot(1 + i % depth, ctx, dev, n, e, b)
                     dws, hws, hout, st = slot
+                    ctx.params.tc_throughput = 1          # several batches in flight
                     rc = lib.cgr_gnn_infer_host_async(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
                                                       _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(),
                                                       dws.data_ptr(), dws.numel(), hws.data_ptr(), hws.numel(),

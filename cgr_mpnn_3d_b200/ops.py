@@ -87,7 +87,8 @@ def _f32c(t: Tensor) -> Tensor:
 def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor, in_idx: Tensor,
                 atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
                 dropout_ps: Sequence[float], training: bool, seed: int, engine: int, tile_info: Tensor,
-                n_tiles: int, tc_status: Tensor, tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor) -> List[Tensor]:
+                n_tiles: int, tc_status: Tensor, tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor,
+                tc_throughput: bool) -> List[Tensor]:
     """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled]`` (saved tensors are empty in eval).
 
     ``tile_info`` / ``n_tiles`` / ``tc_status`` / ``tc_weights`` feed the tcgen05 engine (empty tensors
@@ -100,6 +101,7 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
     ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
     if tc_weights.numel() > 0:
         ctx.params.tc_weights = tc_weights.data_ptr()
+    ctx.params.tc_throughput = int(tc_throughput)
     H = ctx.hidden
     g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info, n_tiles, tc_status, x_hi, x_lo)
     n, e, b = g.n_atoms, g.n_bonds, g.n_rxn
@@ -132,7 +134,7 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
 
 @gnn_forward.register_fake
 def _(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-      engine, tile_info, n_tiles, tc_status, tc_weights, x_hi, x_lo):
+      engine, tile_info, n_tiles, tc_status, tc_weights, x_hi, x_lo, tc_throughput):
     H = params[0].shape[0]
     n, e, b = x.shape[0], src.shape[0], atom_ptr.shape[0] - 1
     mk = lambda *s: x.new_empty(s, dtype=torch.float32)
@@ -186,7 +188,7 @@ def _(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved,
 
 def _setup_context(ctx, inputs, output):
     (x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-     engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo) = inputs
+     engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo, _tp) = inputs
     ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine)
     ctx.n_params = len(params)
     ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:])
@@ -207,7 +209,7 @@ def _backward(ctx, grads):
     pg = gnn_backward(g_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip,
                       dropout_ps, seed, 0)
     return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None, None, None,
-            None, None, None, None)
+            None, None, None, None, None)
 
 
 gnn_forward.register_autograd(_backward, setup_context=_setup_context)

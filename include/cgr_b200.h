@@ -61,6 +61,8 @@ typedef struct cgr_params {
   const float* b_ffn;
   const float* host_dropout_p;
   const void* tc_weights;    /* optional: buffer filled by cgr_tc_prepare_weights (NULL: prepared per call) */
+  int32_t tc_throughput;     /* tcgen05 engine: 1 = the caller pipelines several forwards over streams, prefer the
+                                two-CTAs-per-SM kernel configuration; 0 = optimise the latency of a lone forward */
 } cgr_params_t;
 
 /* gradient buffers, same shapes as cgr_params (written, not accumulated) */

@@ -253,7 +253,7 @@ def test_dropout_replay_against_oracle():
                           torch.empty(0, dtype=torch.int32, device="cuda"),
                           torch.empty(0, dtype=torch.uint8, device="cuda"),
                           torch.empty(0, dtype=torch.float16, device="cuda"),
-                          torch.empty(0, dtype=torch.float16, device="cuda"))
+                          torch.empty(0, dtype=torch.float16, device="cuda"), False)
     out = res[0]
     masks = [stage_ops.dropout_mask(seed, l, p, d.num_edges, meta["hidden"], "cuda").cpu()
              for l in range(meta["depth"])]
@@ -344,6 +344,8 @@ def test_tc_forward_golden(name):
     simt = build_model(meta, state, engine="simt").eval()
     with torch.no_grad():
         assert scale_normalised_error(out, simt(data)) < 2e-5
+        model.tile_policy = "throughput"               # two-CTAs-per-SM kernel configuration: same numbers
+        assert torch.equal(model(data), out)
 
 
 def test_tc_forward_large_batch_against_fp64():
