@@ -91,6 +91,8 @@ PROTOTYPES = {
                                    C.POINTER(CgrGrads), C.c_uint64, _I32, _V, _SZ, _V]),
     "cgr_tc_plan_build": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
     "cgr_tc_plan_check": (C.c_int, [_V, _I64, _V, _V, _V, _V]),
+    "cgr_tc_gemm_test_workspace": (_SZ, [_I64, _I64, _I64]),
+    "cgr_tc_gemm_test": (C.c_int, [_V, _V, _I64, _I64, _I64, _I32, _I32, _V, _V, _SZ, _V]),
     "cgr_tc_features_ld": (_I64, [_I32]),
     "cgr_tc_split_features": (C.c_int, [_V, _I64, _I32, _V, _V, _V, _V]),
     "cgr_tc_debug_buffer": (C.c_int, [_V]),

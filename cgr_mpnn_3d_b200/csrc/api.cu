@@ -404,6 +404,11 @@ extern "C" int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, cons
   CGR_CHECK_ARG(tile_info && src && dst && status, "cgr_tc_plan_check: null pointer");
   return tc_plan_check(tile_info, n_tiles, src, dst, status, (cudaStream_t)stream);
 }
+extern "C" size_t cgr_tc_gemm_test_workspace(int64_t m, int64_t n, int64_t k) { return tc_gemm2_test_workspace(m, n, k); }
+extern "C" int cgr_tc_gemm_test(const float* a, const float* b, int64_t m, int64_t n, int64_t k, int32_t a_mn, int32_t b_mn,
+                                float* c, void* workspace, size_t workspace_bytes, void* stream) {
+  return tc_gemm2_test(a, b, m, n, k, a_mn, b_mn, c, workspace, workspace_bytes, (cudaStream_t)stream);
+}
 extern "C" int64_t cgr_tc_features_ld(int32_t fa) { return ((int64_t)fa + 63) / 64 * 64; }
 extern "C" int cgr_tc_split_features(const float* x, int64_t n_atoms, int32_t fa, void* x_hi, void* x_lo,
                                      int32_t* status, void* stream) {

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 #include "umma.cuh"
 
 namespace {
@@ -653,4 +654,181 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   prm.out_f32 = out;
   prm.ldc = N;
   return launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(M, TM), true, "tc_linear", false, false, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Training path: every GEMM of the layer-wise forward / backward on tensor cores (tc_gemm2_kernel)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
+                                                   unsigned int* __restrict__ amax_bits) {
+  const int64_t total = rows * cols;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(in + (i / cols) * ld + (i % cols))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+// fp32 [rows, cols] -> FP16 (hi, lo) with the power-of-two scale that maps amax into (2^13, 2^14];
+// gradients are tiny, unscaled their lo halves would fall into the fp16 subnormal range
+__global__ void __launch_bounds__(256) split_scaled_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
+                                                           const unsigned int* __restrict__ amax_bits,
+                                                           float* __restrict__ unscale_out, __half* __restrict__ hi,
+                                                           __half* __restrict__ lo, int64_t ldo) {
+  const float amax = __uint_as_float(*amax_bits);
+  const float sc = (amax > 0.f && isfinite(amax)) ? exp2f(14.f - ceilf(log2f(amax))) : 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *unscale_out = 1.f / sc;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  for (int c = threadIdx.x & 31; c < cols; c += 32) {
+    __half h, l;
+    split_f16(__ldg(in + r * ld + c) * sc, h, l);
+    hi[r * ldo + c] = h;
+    lo[r * ldo + c] = l;
+  }
+}
+
+__global__ void splitk_reduce2_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N,
+                                      float* __restrict__ C, int64_t ldc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * M * N + i];   // fixed order
+  C[(i / N) * ldc + (i % N)] = s;
+}
+
+int make_operand_maps(CUtensorMap* hi_map, CUtensorMap* lo_map, const TcOperand& op, int64_t mn, int64_t K) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
+  // K-major: tensor [mn rows, K cols], box [128 rows, 64 cols];  MN-major: tensor [K rows, mn cols], box [64 rows, 64 cols]
+  cuuint64_t dims[2] = {(cuuint64_t)(op.mn_major ? mn : K), (cuuint64_t)(op.mn_major ? K : mn)};
+  cuuint64_t strides[1] = {(cuuint64_t)op.ld * sizeof(__half)};
+  cuuint32_t box[2] = {64u, op.mn_major ? 64u : 128u};
+  cuuint32_t estr[2] = {1, 1};
+  for (int h = 0; h < 2; ++h) {
+    CUresult r = fn(h ? lo_map : hi_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)(h ? op.lo : op.hi), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cgr_set_error("cuTensorMapEncodeTiled(gemm2) failed with CUresult %d", (int)r); return CGR_ERR_ARG; }
+  }
+  return CGR_OK;
+}
+
+}  // namespace
+
+int tc_split(const float* in, int64_t ld, int64_t rows, int cols, bool scaled, __half* hi, __half* lo, int64_t ldo,
+             unsigned int* amax_slot, float* unscale_slot, int* overflow, cudaStream_t st) {
+  if (rows <= 0) return CGR_OK;
+  CgrRange prof("tc_split", st);
+  if (scaled) {
+    cgr_note_launch("tc_split", st, 2);
+    CGR_CUDA(cudaMemsetAsync(amax_slot, 0, sizeof(unsigned int), st));
+    const int64_t total = rows * cols;
+    amax_kernel<<<(unsigned)(total > 65536 * 64 ? 256 : cgr_ceil_div(total, 16384) > 0 ? cgr_ceil_div(total, 16384) : 1), 256, 0,
+                  st>>>(in, ld, rows, cols, amax_slot);
+    split_scaled_kernel<<<(unsigned)cgr_ceil_div(rows, 8), 256, 0, st>>>(in, ld, rows, cols, amax_slot, unscale_slot, hi, lo,
+                                                                         ldo);
+  } else {
+    cgr_note_launch("tc_split", st, 1);
+    split_rows_kernel<<<(unsigned)cgr_ceil_div(rows, 8), 256, 0, st>>>(in, ld, rows, cols, hi, lo, ldo, overflow);
+  }
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+int tc_splitk_choose(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = cgr_ceil_div(M, tcg2::TM) * cgr_ceil_div(N, tcg2::TN);
+  const int64_t kc = cgr_ceil_div(K, tcg2::BK);
+  if (tiles >= 96 || kc < 8) return 1;
+  int64_t s = cgr_ceil_div(148, tiles);
+  if (s > kc / 4) s = kc / 4;
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : (int)s;
+}
+
+int tc_train_gemm(const TcOperand& A, const TcOperand& B, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
+                  const GemmEpilogue& epi, int split_k, float* partial, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return CGR_OK;
+  tcg2::Params prm;
+  memset(&prm, 0, sizeof(prm));
+  int rc;
+  if ((rc = make_operand_maps(&prm.tmA_hi, &prm.tmA_lo, A, M, K))) return rc;
+  if ((rc = make_operand_maps(&prm.tmB_hi, &prm.tmB_lo, B, N, K))) return rc;
+  const int64_t kc = cgr_ceil_div(K > 0 ? K : 1, tcg2::BK);
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && !partial) { cgr_set_error("tc_train_gemm: split-K without a partial buffer"); return CGR_ERR_ARG; }
+  const int64_t per = cgr_ceil_div(kc, split_k);
+  split_k = (int)cgr_ceil_div(kc, per);
+  prm.M = M; prm.N = N; prm.K = K;
+  prm.k_chunks_per_split = per;
+  prm.unscale_a = A.unscale; prm.unscale_b = B.unscale;
+  prm.split_k = split_k;
+  prm.C = split_k > 1 ? partial : C;
+  prm.ldc = ldc;
+  prm.bias = epi.bias; prm.res = epi.res; prm.ldr = epi.ldr; prm.res_scale = epi.res_scale; prm.preact = epi.preact;
+  prm.act = epi.act; prm.dropout_p = epi.dropout_p; prm.seed = epi.seed; prm.layer = epi.layer;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CGR_CUDA(cudaFuncSetAttribute(tcg2::tc_gemm2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg2::SMEM_BYTES));
+    CGR_CUDA(cudaFuncSetAttribute(tcg2::tc_gemm2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg2::SMEM_BYTES));
+    CGR_CUDA(cudaFuncSetAttribute(tcg2::tc_gemm2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg2::SMEM_BYTES));
+    CGR_CUDA(cudaFuncSetAttribute(tcg2::tc_gemm2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg2::SMEM_BYTES));
+    attr_done = true;
+  }
+  const char* name = epi.tag ? epi.tag : "tc_gemm2";
+  CgrRange prof(name, st);
+  cgr_note_launch(name, st, split_k > 1 ? 2 : 1);
+  dim3 grid((unsigned)cgr_ceil_div(N, tcg2::TN), (unsigned)cgr_ceil_div(M, tcg2::TM), (unsigned)split_k);
+  if (!A.mn_major && !B.mn_major) tcg2::tc_gemm2_kernel<false, false><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(prm);
+  else if (!A.mn_major && B.mn_major) tcg2::tc_gemm2_kernel<false, true><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(prm);
+  else if (A.mn_major && B.mn_major) tcg2::tc_gemm2_kernel<true, true><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(prm);
+  else tcg2::tc_gemm2_kernel<true, false><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(prm);
+  if (split_k > 1)
+    splitk_reduce2_kernel<<<(unsigned)cgr_ceil_div(M * N, 256), 256, 0, st>>>(partial, split_k, M, N, C, ldc);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+// prepared-weight accessor: matrix `mat` (0 = [W_x; W_ox], 1..depth = convs, depth+1 = W_os), rows from `row0`
+TcOperand tc_weight_operand(const cgr_params_t* p, const void* wbuf, int mat, int64_t row0, bool mn_major) {
+  const WLayout wl = wlayout(p);
+  const char* b = (const char*)wbuf;
+  TcOperand op;
+  op.hi = (const __half*)(b + wl.off_hi[mat]) + row0 * wl.ld[mat];
+  op.lo = (const __half*)(b + wl.off_lo[mat]) + row0 * wl.ld[mat];
+  op.ld = wl.ld[mat];
+  op.unscale = (const float*)(b + wl.off_unscale) + mat;
+  op.mn_major = mn_major;
+  return op;
+}
+
+// Test entry: C[M,N] = op(A) op(B)^T style contraction on fp32 inputs.  a_mn: A given as [K, M]; b_mn: B given as [K, N].
+size_t tc_gemm2_test_workspace(int64_t M, int64_t N, int64_t K) {
+  const int64_t a_el = (M > K ? M : K) * round_up(M > K ? M : K, 64), b_el = (N > K ? N : K) * round_up(N > K ? N : K, 64);
+  return (size_t)(a_el + b_el) * 2 * sizeof(__half) + (size_t)32 * M * N * sizeof(float) + 8192;
+}
+int tc_gemm2_test(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn, float* C,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  CGR_CHECK_ARG(A && B && C && workspace && workspace_bytes >= tc_gemm2_test_workspace(M, N, K), "tc_gemm2_test: bad argument");
+  char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  const int64_t a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
+  const int64_t a_ld = round_up(a_cols, 64), b_ld = round_up(b_cols, 64);
+  const int64_t a_el = (M > K ? M : K) * round_up(M > K ? M : K, 64), b_el = (N > K ? N : K) * round_up(N > K ? N : K, 64);
+  __half* a_hi = (__half*)ws;
+  __half* a_lo = a_hi + a_el;
+  __half* b_hi = a_lo + a_el;
+  __half* b_lo = b_hi + b_el;
+  float* partial = (float*)(b_lo + b_el);
+  unsigned int* slots = (unsigned int*)(partial + 32 * M * N);
+  float* us = (float*)(slots + 8);
+  int rc;
+  if ((rc = tc_split(A, a_cols, a_rows, (int)a_cols, true, a_hi, a_lo, a_ld, slots, us, nullptr, st))) return rc;
+  if ((rc = tc_split(B, b_cols, b_rows, (int)b_cols, true, b_hi, b_lo, b_ld, slots + 1, us + 1, nullptr, st))) return rc;
+  TcOperand oa{a_hi, a_lo, a_ld, us, a_mn != 0}, ob{b_hi, b_lo, b_ld, us + 1, b_mn != 0};
+  GemmEpilogue e;
+  return tc_train_gemm(oa, ob, M, N, K, C, N, e, tc_splitk_choose(M, N, K), partial, st);
 }

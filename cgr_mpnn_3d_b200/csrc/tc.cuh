@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/cgr_b200.h"
 #include "common.cuh"
+#include "simt.cuh"
 
 size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int training);
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
@@ -19,3 +20,21 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
               const float* bias, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void tc_set_debug_buffer(long long* p);
 int tc_split_features(const float* x, int64_t n, int fa, void* x_hi, void* x_lo, int* status, cudaStream_t st);
+
+// ---- training path: tensor-core GEMMs on FP16 (hi, lo) operands of either major ----
+struct TcOperand {
+  const __half* hi;
+  const __half* lo;
+  int64_t ld;              // row stride in halfs (multiple of 8)
+  const float* unscale;    // device scalar 1/scale or null
+  bool mn_major;           // false: [MN rows, K cols];  true: [K rows, MN cols]
+};
+int tc_split(const float* in, int64_t ld, int64_t rows, int cols, bool scaled, __half* hi, __half* lo, int64_t ldo,
+             unsigned int* amax_slot, float* unscale_slot, int* overflow, cudaStream_t st);
+int tc_splitk_choose(int64_t M, int64_t N, int64_t K);
+int tc_train_gemm(const TcOperand& A, const TcOperand& B, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
+                  const GemmEpilogue& epi, int split_k, float* partial, cudaStream_t st);
+TcOperand tc_weight_operand(const cgr_params_t* p, const void* wbuf, int mat, int64_t row0, bool mn_major);
+size_t tc_gemm2_test_workspace(int64_t M, int64_t N, int64_t K);
+int tc_gemm2_test(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn, float* C,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);

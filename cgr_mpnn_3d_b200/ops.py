@@ -245,3 +245,19 @@ def tc_linear(x: Tensor, w: Tensor, bias=None) -> Tensor:
         _lib.check(lib.cgr_tc_linear(x.data_ptr(), m, k, w.data_ptr(), n, _lib.ptr(b), out.data_ptr(), ws.data_ptr(),
                                      nbytes, _stream()), "cgr_tc_linear")
     return out
+
+
+def tc_gemm_test(a: Tensor, b: Tensor, a_mn: bool, b_mn: bool) -> Tensor:
+    """Test entry of the training GEMM: ``a`` is [m,k] (or [k,m] when ``a_mn``), ``b`` is [n,k] (or [k,n])."""
+    _require_cuda(a, b)
+    lib = _lib.load()
+    a, b = _f32c(a), _f32c(b)
+    k, m = (a.shape if a_mn else a.shape[::-1])
+    n = b.shape[1] if b_mn else b.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        nbytes = lib.cgr_tc_gemm_test_workspace(m, n, k)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        _lib.check(lib.cgr_tc_gemm_test(a.data_ptr(), b.data_ptr(), m, n, k, int(a_mn), int(b_mn), out.data_ptr(),
+                                        ws.data_ptr(), nbytes, _stream()), "cgr_tc_gemm_test")
+    return out

@@ -205,6 +205,12 @@ int cgr_tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, int64_t n_
                       int32_t* status, void* stream);
 int cgr_tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst,
                       int32_t* status, void* stream);
+/* Test entry of the training GEMM (tc_gemm2): c[m,n] = sum_k A(m,k) B(n,k) on fp32 inputs through the scaled FP16x3
+ * split; a_mn != 0: `a` is stored [k, m] (MN-major, as in weight gradients), else [m, k]; same for b. */
+size_t cgr_tc_gemm_test_workspace(int64_t m, int64_t n, int64_t k);
+int cgr_tc_gemm_test(const float* a, const float* b, int64_t m, int64_t n, int64_t k, int32_t a_mn, int32_t b_mn,
+                     float* c, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Batch preparation for the tcgen05 engine: data.x [N, fa] fp32 -> FP16 (hi, lo) rows of stride
  * cgr_tc_features_ld(fa) halfs (part of collation, like the CSR arrays; status[0] gets the overflow flag). */
 int64_t cgr_tc_features_ld(int32_t fa);

@@ -424,3 +424,22 @@ def test_host_buffer_inference_entry(name):
     bad.edge_index[:, [0, 2]] = bad.edge_index[:, [2, 0]]
     with torch.no_grad(), pytest.raises(RuntimeError, match="reverse pairs|atom range|grouped"):
         model(bad)
+
+
+# ---------------------------------------------------------------------------------------------
+# training GEMM (tc_gemm2): every operand-major combination, split-K, tiny-magnitude (gradient-like) inputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("m,n,k,scale", [(400, 400, 2192, 1e-4), (2192, 400, 400, 1.0), (130, 846, 1001, 1e-2),
+                                          (128, 128, 64, 1.0)])
+def test_tc_training_gemm(m, n, k, scale, a_mn, b_mn):
+    from cgr_mpnn_3d_b200 import ops
+    g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
+    A = torch.randn(m, k, generator=g) * scale
+    B = torch.randn(n, k, generator=g) * 0.05
+    a_in = A.t().contiguous() if a_mn else A
+    b_in = B.t().contiguous() if b_mn else B
+    out = ops.tc_gemm_test(a_in.cuda(), b_in.cuda(), a_mn, b_mn)
+    ref = A.double() @ B.double().t()
+    ref32 = A @ B.t()
+    assert tensor_error(out, ref) < max(2e-6, 4 * tensor_error(ref32, ref))
