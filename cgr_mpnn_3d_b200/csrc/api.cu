@@ -125,7 +125,186 @@ size_t max_splitk_floats(const cgr_params_t* p, const cgr_graph_t* g) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// stage-level entry points
+// The layer-wise path.  Its GEMMs run either on the SIMT fp32 kernel or -- training on the tcgen05 engine -- on
+// tensor cores through tc_train_gemm (operands split to FP16 (hi, lo) on the fly, weights prepared once per step);
+// gathers, element-wise kernels and reductions are shared.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Opnd {                    // one GEMM operand as stored: [rows, cols] fp32 with row stride ld
+  const float* f32 = nullptr;
+  int64_t ld = 0;
+  bool kmajor = true;            // true: rows = M (or N), cols = K;  false: rows = K, cols = M (or N)
+  int wmat = -1;                 // >= 0: matrix of the prepared-weight buffer (tcgen05 path), rows from wrow0
+  int64_t wrow0 = 0;
+  bool is_x = false;             // data.x (its split is cached per batch)
+  bool scaled = false;           // gradient-like operand: needs the amax-based power-of-two scale
+};
+
+struct GemmCtx {
+  bool tc = false;
+  const cgr_params_t* p = nullptr;
+  const void* wbuf = nullptr;
+  __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;     // split scratch slots
+  const __half *x_hi = nullptr, *x_lo = nullptr;
+  int64_t x_ld = 0;
+  unsigned int* amax = nullptr;  // [4]
+  float* unscale = nullptr;      // [4]
+  int* overflow = nullptr;
+  float* partial = nullptr;      // split-K partial sums
+  const float* last_a = nullptr; // fp32 tensor currently held by slot A (re-used by consecutive GEMMs)
+  bool last_a_scaled = false;
+};
+
+int64_t ru64(int64_t v) { return (v + 63) / 64 * 64; }
+
+int make_tc_operand(GemmCtx& c, const Opnd& o, int64_t mn, int64_t K, bool slot_b, TcOperand* out, cudaStream_t st) {
+  if (o.wmat >= 0) { *out = tc_weight_operand(c.p, c.wbuf, o.wmat, o.wrow0, !o.kmajor); return CGR_OK; }
+  if (o.is_x && c.x_hi) { *out = TcOperand{c.x_hi, c.x_lo, c.x_ld, nullptr, !o.kmajor}; return CGR_OK; }
+  const int64_t rows = o.kmajor ? mn : K, cols = o.kmajor ? K : mn;
+  __half* hi = slot_b ? c.b_hi : c.a_hi;
+  __half* lo = slot_b ? c.b_lo : c.a_lo;
+  const int slot = slot_b ? 1 : 0;
+  if (slot_b || c.last_a != o.f32 || c.last_a_scaled != o.scaled) {
+    int rc = tc_split(o.f32, o.ld, rows, (int)cols, o.scaled, hi, lo, ru64(cols), c.amax + slot, c.unscale + slot,
+                      c.overflow, st);
+    if (rc) return rc;
+    if (!slot_b) { c.last_a = o.f32; c.last_a_scaled = o.scaled; }
+  }
+  *out = TcOperand{hi, lo, ru64(cols), o.scaled ? c.unscale + slot : nullptr, !o.kmajor};
+  return CGR_OK;
+}
+
+// C[M,N] = sum_k A(m,k) B(n,k) with the fused epilogue; reduction GEMMs (K >> M,N) use deterministic split-K
+int gemm(GemmCtx& c, const Opnd& A, const Opnd& B, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+         const GemmEpilogue& epi, bool allow_splitk, cudaStream_t st) {
+  if (!c.tc)
+    return simt_gemm(A.f32, A.ld, A.kmajor, B.f32, B.ld, B.kmajor, C, ldc, M, N, K, epi,
+                     allow_splitk ? simt_splitk_choose(M, N, K) : 1, c.partial, st);
+  TcOperand oa, ob;
+  int rc = make_tc_operand(c, A, M, K, false, &oa, st);
+  if (rc) return rc;
+  rc = make_tc_operand(c, B, N, K, true, &ob, st);
+  if (rc) return rc;
+  return tc_train_gemm(oa, ob, M, N, K, C, ldc, epi, allow_splitk ? tc_splitk_choose(M, N, K) : 1, c.partial, st);
+}
+
+Opnd act_opnd(const float* p, int64_t ld, bool kmajor, bool scaled = false) {
+  Opnd o; o.f32 = p; o.ld = ld; o.kmajor = kmajor; o.scaled = scaled; return o;
+}
+Opnd x_opnd(const float* x, int64_t fa, bool kmajor) {
+  Opnd o; o.f32 = x; o.ld = fa; o.kmajor = kmajor; o.is_x = true; return o;
+}
+Opnd w_opnd(const float* w, int64_t ld, bool kmajor, int wmat, int64_t wrow0 = 0) {
+  Opnd o; o.f32 = w; o.ld = ld; o.kmajor = kmajor; o.wmat = wmat; o.wrow0 = wrow0; return o;
+}
+// without the tcgen05 path the prepared-weight ids are ignored (SIMT reads the fp32 parameter directly)
+
+int edge_init_impl(GemmCtx& c, const float* x, const float* edge_attr, const int32_t* src, const float* w_init,
+                   const float* b_init, int64_t N, int64_t E, int fa, int fb, int H, int act, float* h0, float* z0,
+                   float* P, cudaStream_t st) {
+  // P = x . W_x^T with W_x = w_init[:, :fa]; per-atom projection, algebraically equal to the reference's
+  // [x[src] || ea] GEMM (GNN.py:86) without materialising the [E, Fa+Fb] concat.
+  GemmEpilogue none;
+  none.tag = "gemm_atom_proj";
+  int rc = gemm(c, x_opnd(x, fa, true), w_opnd(w_init, fa + fb, true, 0, 0), P, H, N, H, fa, none, false, st);
+  if (rc) return rc;
+  return simt_edge_init(P, edge_attr, src, w_init, b_init, E, fa, fb, H, act, h0, z0, st);
+}
+
+int bond_update_impl(GemmCtx& c, const float* h_in, const float* h0, const int32_t* in_ptr, const int32_t* in_idx,
+                     const int32_t* src, const float* w, const float* b, const float* skip, int act, float dropout_p,
+                     uint64_t seed, uint32_t layer, int training, float* h_out, float* m_out, float* z_out, int64_t E,
+                     int H, int wmat, cudaStream_t st) {
+  GatherPost np;
+  int rc = simt_gather_bonds(h_in, src, in_ptr, in_idx, 0, m_out, E, H, np, st);   // GNN.py:134-141
+  if (rc) return rc;
+  GemmEpilogue e;
+  e.bias = b;
+  e.res = h0; e.ldr = H; e.res_scale = skip;               // GNN.py:94-97
+  e.preact = z_out;
+  e.act = act;                                             // GNN.py:100-102
+  e.dropout_p = (training && dropout_p > 0.f) ? dropout_p : 0.f;
+  e.seed = seed; e.layer = layer;
+  e.tag = "gemm_bond_update";
+  return gemm(c, act_opnd(m_out, H, true), w_opnd(w, H, true, wmat), h_out, H, E, H, H, e, false, st);
+}
+
+int readout_impl(GemmCtx& c, const float* h, const float* x, const int32_t* in_ptr, const int32_t* in_idx,
+                 const int32_t* atom_ptr, const float* w_e2n, const float* b_e2n, const float* w_ffn, const float* b_ffn,
+                 int act, float* out, float* s_out, float* hv_out, float* zv_out, float* pooled_out, int64_t N, int64_t B,
+                 int fa, int H, int depth, cudaStream_t st) {
+  int rc = simt_atom_sum(h, in_ptr, in_idx, 0, s_out, N, H, st);                  // GNN.py:105
+  if (rc) return rc;
+  // W_o [x || s] = x W_ox^T + s W_os^T  (GNN.py:106-107 without the concat)
+  GemmEpilogue e1;
+  e1.tag = "gemm_readout_x";
+  e1.bias = b_e2n;
+  rc = gemm(c, x_opnd(x, fa, true), w_opnd(w_e2n, fa + H, true, 0, H), hv_out, H, N, H, fa, e1, false, st);
+  if (rc) return rc;
+  GemmEpilogue e2;
+  e2.res = hv_out; e2.ldr = H;
+  e2.preact = zv_out;
+  e2.act = act;
+  e2.tag = "gemm_readout_s";
+  rc = gemm(c, act_opnd(s_out, H, true), w_opnd(w_e2n + fa, fa + H, true, depth + 1), hv_out, H, N, H, H, e2, false, st);
+  if (rc) return rc;
+  return simt_pool_ffn(hv_out, atom_ptr, w_ffn, b_ffn, pooled_out, out, B, H, st);  // GNN.py:110
+}
+
+// extra workspace of the tcgen05 training path: split slots, scale slots, weights / x split when not supplied
+struct TcTrainWs { size_t slot_bytes, w_bytes, x_bytes, total; };
+TcTrainWs tc_train_ws(const cgr_params_t* p, const cgr_graph_t* g) {
+  TcTrainWs w;
+  const int64_t rows = g->n_bonds > g->n_atoms ? g->n_bonds : g->n_atoms;
+  w.slot_bytes = cgr_align_up((size_t)rows * ru64(p->hidden) * sizeof(__half), 1024);
+  w.w_bytes = p->tc_weights ? 0 : cgr_align_up(tc_weights_bytes(p), 1024);
+  w.x_bytes = (g->x_hi && g->x_lo) ? 0 : cgr_align_up((size_t)g->n_atoms * ru64(p->fa) * sizeof(__half), 1024);
+  w.total = 4 * w.slot_bytes + w.w_bytes + 2 * w.x_bytes + 1024 + 2048;
+  return w;
+}
+
+int setup_tc_ctx(GemmCtx& c, const cgr_params_t* p, const cgr_graph_t* g, char* base, cudaStream_t st) {
+  const TcTrainWs w = tc_train_ws(p, g);
+  char* ptr = (char*)(((uintptr_t)base + 1023) & ~(uintptr_t)1023);
+  c.tc = true;
+  c.p = p;
+  c.a_hi = (__half*)ptr; ptr += w.slot_bytes;
+  c.a_lo = (__half*)ptr; ptr += w.slot_bytes;
+  c.b_hi = (__half*)ptr; ptr += w.slot_bytes;
+  c.b_lo = (__half*)ptr; ptr += w.slot_bytes;
+  c.amax = (unsigned int*)ptr;
+  c.unscale = (float*)(ptr + 64);
+  c.overflow = (int*)(ptr + 128);
+  ptr += 1024;
+  int rc;
+  if (p->tc_weights) {
+    c.wbuf = p->tc_weights;
+  } else {
+    rc = tc_prepare_weights(p, ptr, tc_weights_bytes(p), st);
+    if (rc) return rc;
+    c.wbuf = ptr;
+    ptr += w.w_bytes;
+  }
+  c.x_ld = ru64(p->fa);
+  if (g->x_hi && g->x_lo) {
+    c.x_hi = (const __half*)g->x_hi; c.x_lo = (const __half*)g->x_lo;
+  } else {
+    __half* xh = (__half*)ptr; ptr += w.x_bytes;
+    __half* xl = (__half*)ptr; ptr += w.x_bytes;
+    rc = tc_split_features(g->x, g->n_atoms, p->fa, xh, xl, c.overflow, st);
+    if (rc) return rc;
+    c.x_hi = xh; c.x_lo = xl;
+  }
+  return CGR_OK;
+}
+
+bool tc_training_ok(const cgr_params_t* p) { return p->depth + 3 <= 16; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points (SIMT fp32 engine)
 // ------------------------------------------------------------------------------------------------
 
 extern "C" int cgr_edge_init_fwd(const float* x, const float* edge_attr, const int32_t* src, const float* w_init,
@@ -135,15 +314,9 @@ extern "C" int cgr_edge_init_fwd(const float* x, const float* edge_attr, const i
   CGR_CHECK_ARG(x && src && w_init && b_init && h0, "cgr_edge_init_fwd: null pointer");
   CGR_CHECK_ARG(fb == 0 || edge_attr, "cgr_edge_init_fwd: edge_attr is null but fb > 0");
   CGR_CHECK_ARG(workspace_bytes >= fbytes((size_t)n_atoms * hidden), "cgr_edge_init_fwd: workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  float* P = (float*)workspace;
-  // P = x . W_x^T with W_x = w_init[:, :fa]; per-atom projection, algebraically equal to the
-  // reference's [x[src] || ea] GEMM (GNN.py:86) without materialising the [E, Fa+Fb] concat.
-  GemmEpilogue none;
-  none.tag = "gemm_atom_proj";
-  int rc = simt_gemm(x, fa, true, w_init, fa + fb, true, P, hidden, n_atoms, hidden, fa, none, 1, nullptr, st);
-  if (rc) return rc;
-  return simt_edge_init(P, edge_attr, src, w_init, b_init, n_bonds, fa, fb, hidden, act, h0, z0, st);
+  GemmCtx c;
+  return edge_init_impl(c, x, edge_attr, src, w_init, b_init, n_atoms, n_bonds, fa, fb, hidden, act, h0, z0,
+                        (float*)workspace, (cudaStream_t)stream);
 }
 
 extern "C" int cgr_bond_update_fwd(const float* h_in, const float* h0, const int32_t* in_ptr,
@@ -154,19 +327,9 @@ extern "C" int cgr_bond_update_fwd(const float* h_in, const float* h0, const int
   (void)n_atoms;
   CGR_CHECK_ARG(h_in && h0 && in_ptr && in_idx && src && w && b && h_out && m_out, "cgr_bond_update_fwd: null pointer");
   CGR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "cgr_bond_update_fwd: dropout_p out of range");
-  cudaStream_t st = (cudaStream_t)stream;
-  GatherPost np;
-  int rc = simt_gather_bonds(h_in, src, in_ptr, in_idx, 0, m_out, n_bonds, hidden, np, st);   // GNN.py:134-141
-  if (rc) return rc;
-  GemmEpilogue e;
-  e.bias = b;
-  e.res = h0; e.ldr = hidden; e.res_scale = skip;          // GNN.py:94-97
-  e.preact = z_out;
-  e.act = act;                                             // GNN.py:100-102
-  e.dropout_p = (training && dropout_p > 0.f) ? dropout_p : 0.f;
-  e.seed = seed; e.layer = layer;
-  e.tag = "gemm_bond_update";
-  return simt_gemm(m_out, hidden, true, w, hidden, true, h_out, hidden, n_bonds, hidden, hidden, e, 1, nullptr, st);
+  GemmCtx c;
+  return bond_update_impl(c, h_in, h0, in_ptr, in_idx, src, w, b, skip, act, dropout_p, seed, layer, training, h_out,
+                          m_out, z_out, n_bonds, hidden, -1, (cudaStream_t)stream);
 }
 
 extern "C" int cgr_conv_fwd(const float* h, const int32_t* in_ptr, const int32_t* in_idx, const int32_t* src,
@@ -192,24 +355,9 @@ extern "C" int cgr_readout_fwd(const float* h, const float* x, const int32_t* in
   (void)n_bonds;
   CGR_CHECK_ARG(h && x && in_ptr && in_idx && atom_ptr && w_e2n && b_e2n && w_ffn && b_ffn && out && s_out &&
                     hv_out && pooled_out, "cgr_readout_fwd: null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = simt_atom_sum(h, in_ptr, in_idx, 0, s_out, n_atoms, hidden, st);                  // GNN.py:105
-  if (rc) return rc;
-  // W_o [x || s] = x W_ox^T + s W_os^T  (GNN.py:106-107 without the concat)
-  GemmEpilogue e1;
-  e1.tag = "gemm_readout_x";
-  e1.bias = b_e2n;
-  rc = simt_gemm(x, fa, true, w_e2n, fa + hidden, true, hv_out, hidden, n_atoms, hidden, fa, e1, 1, nullptr, st);
-  if (rc) return rc;
-  GemmEpilogue e2;
-  e2.res = hv_out; e2.ldr = hidden;
-  e2.preact = zv_out;
-  e2.act = act;
-  e2.tag = "gemm_readout_s";
-  rc = simt_gemm(s_out, hidden, true, w_e2n + fa, fa + hidden, true, hv_out, hidden, n_atoms, hidden, hidden, e2, 1,
-                 nullptr, st);
-  if (rc) return rc;
-  return simt_pool_ffn(hv_out, atom_ptr, w_ffn, b_ffn, pooled_out, out, n_rxn, hidden, st);  // GNN.py:110
+  GemmCtx c;
+  return readout_impl(c, h, x, in_ptr, in_idx, atom_ptr, w_e2n, b_e2n, w_ffn, b_ffn, act, out, s_out, hv_out, zv_out,
+                      pooled_out, n_atoms, n_rxn, fa, hidden, 0, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -219,10 +367,11 @@ extern "C" int cgr_readout_fwd(const float* h, const float* x, const int32_t* in
 extern "C" size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t training,
                                         int32_t engine) {
   if (!p || !g) return 0;
-  if (engine == CGR_ENGINE_TC) return tc_forward_workspace(p, g, training);
+  if (engine == CGR_ENGINE_TC && !training) return tc_forward_workspace(p, g, training);
   const size_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
   size_t b = fbytes(N * H);
   if (!training) b += 4 * fbytes(E * H) + 2 * fbytes(N * H) + fbytes(B * H);
+  if (engine == CGR_ENGINE_TC) b += tc_train_ws(p, g).total;
   return b + 256;
 }
 
@@ -238,10 +387,11 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
   CGR_CHECK_ARG(workspace_bytes >= cgr_forward_workspace(p, g, training, engine),
                 "cgr_gnn_forward: workspace too small (%zu < %zu)", workspace_bytes,
                 cgr_forward_workspace(p, g, training, engine));
-  if (engine == CGR_ENGINE_TC)
+  CGR_CHECK_ARG(engine == CGR_ENGINE_SIMT || engine == CGR_ENGINE_TC, "unknown engine %d", engine);
+  // inference on the tcgen05 engine: fused tile kernels.  Training on it: layer-wise path with tensor-core GEMMs.
+  if (engine == CGR_ENGINE_TC && !saved)
     return tc_gnn_forward(p, g, out, saved, training, seed, workspace, workspace_bytes, (cudaStream_t)stream);
-  CGR_CHECK_ARG(engine == CGR_ENGINE_SIMT, "unknown engine %d", engine);
-
+  cudaStream_t st = (cudaStream_t)stream;
   const int64_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
   const int d = p->depth;
   const size_t EH = (size_t)E * H;
@@ -259,10 +409,16 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
     s = ws.floats(N * H); hv = ws.floats(N * H); pooled = ws.floats(B * H);
   }
   if (!ws.ok) { cgr_set_error("cgr_gnn_forward: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  GemmCtx c;
+  if (engine == CGR_ENGINE_TC) {
+    CGR_CHECK_ARG(tc_training_ok(p), "tcgen05 training path supports depth <= 13");
+    rc = setup_tc_ctx(c, p, g, ws.base + ws.off, st);
+    if (rc) return rc;
+  }
   float* z_all = saved ? saved->z_all : nullptr;
 
-  rc = cgr_edge_init_fwd(g->x, g->edge_attr, g->src, p->w_init, p->b_init, N, E, p->fa, p->fb, p->hidden, p->act,
-                         h0, z_all, P, fbytes(N * H), stream);
+  rc = edge_init_impl(c, g->x, g->edge_attr, g->src, p->w_init, p->b_init, N, E, p->fa, p->fb, p->hidden, p->act, h0,
+                      z_all, P, st);
   if (rc) return rc;
   const float* h = h0;
   for (int l = 0; l < d; ++l) {
@@ -270,22 +426,26 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
     float* m_out = saved ? saved->m_all + (size_t)l * EH : mbuf;
     float* z_out = z_all ? z_all + (size_t)(l + 1) * EH : nullptr;
     const float pdrop = p->host_dropout_p ? p->host_dropout_p[l] : 0.f;
-    rc = cgr_bond_update_fwd(h, h0, g->in_ptr, g->in_idx, g->src, p->w_conv[l], p->b_conv[l],
-                             p->use_skip ? p->skip[l] : nullptr, p->act, pdrop, seed, (uint32_t)l, training, h_out,
-                             m_out, z_out, E, N, p->hidden, stream);
+    rc = bond_update_impl(c, h, h0, g->in_ptr, g->in_idx, g->src, p->w_conv[l], p->b_conv[l],
+                          p->use_skip ? p->skip[l] : nullptr, p->act, pdrop, seed, (uint32_t)l, training, h_out, m_out,
+                          z_out, E, p->hidden, 1 + l, st);
     if (rc) return rc;
     h = h_out;
   }
-  return cgr_readout_fwd(h, g->x, g->in_ptr, g->in_idx, g->atom_ptr, p->w_e2n, p->b_e2n, p->w_ffn, p->b_ffn, p->act,
-                         out, s, hv, saved ? saved->zv : nullptr, pooled, N, E, B, p->fa, p->hidden, stream);
+  return readout_impl(c, h, g->x, g->in_ptr, g->in_idx, g->atom_ptr, p->w_e2n, p->b_e2n, p->w_ffn, p->b_ffn, p->act, out,
+                      s, hv, saved ? saved->zv : nullptr, pooled, N, B, p->fa, p->hidden, d, st);
 }
 
 extern "C" size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t engine) {
   if (!p || !g) return 0;
-  (void)engine;
   const size_t H = p->hidden, E = g->n_bonds, N = g->n_atoms;
-  return 2 * fbytes(N * H) + 3 * fbytes(E * H) + fbytes(max_splitk_floats(p, g)) +
-         fbytes(simt_colsum_workspace(E > N ? E : N, (int)H)) + 256;
+  size_t partial = max_splitk_floats(p, g);
+  const size_t tc_partial = (size_t)32 * H * (H > (size_t)p->fa ? H : (size_t)p->fa);
+  if (engine == CGR_ENGINE_TC && tc_partial > partial) partial = tc_partial;
+  size_t b = 2 * fbytes(N * H) + 3 * fbytes(E * H) + fbytes(partial) +
+             fbytes(simt_colsum_workspace(E > N ? E : N, (int)H)) + 256;
+  if (engine == CGR_ENGINE_TC) b += tc_train_ws(p, g).total;
+  return b;
 }
 
 extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved,
@@ -295,7 +455,6 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
   if (rc) return rc;
   rc = check_graph(g);
   if (rc) return rc;
-  (void)engine;   // the backward currently always runs on the SIMT fp32 engine
   CGR_CHECK_ARG(saved && grad_out && grads, "cgr_gnn_backward: null pointer");
   CGR_CHECK_ARG(saved->h_all && saved->m_all && saved->s && saved->hv && saved->pooled,
                 "cgr_gnn_backward: saved buffers missing");
@@ -313,9 +472,19 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
   float* dz = ws.floats(EH);
   float* dm = ws.floats(EH);
   float* dh0 = ws.floats(EH);
-  float* partial = ws.floats(max_splitk_floats(p, g));
+  size_t partial_floats = max_splitk_floats(p, g);
+  const size_t tc_partial = (size_t)32 * H * (H > fa ? H : fa);
+  if (engine == CGR_ENGINE_TC && tc_partial > partial_floats) partial_floats = tc_partial;
+  float* partial = ws.floats(partial_floats);
   float* csws = ws.floats(simt_colsum_workspace(E > N ? E : N, (int)H));
   if (!ws.ok) { cgr_set_error("cgr_gnn_backward: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  GemmCtx c;
+  if (engine == CGR_ENGINE_TC) {
+    CGR_CHECK_ARG(tc_training_ok(p), "tcgen05 training path supports depth <= 13");
+    rc = setup_tc_ctx(c, p, g, ws.base + ws.off, st);
+    if (rc) return rc;
+  }
+  c.partial = partial;
   GemmEpilogue none;
   const float* h0 = saved->h_all;
 
@@ -327,14 +496,16 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
   rc = simt_colsum(dzv, N, (int)H, grads->b_e2n, nullptr, nullptr, nullptr, nullptr, true, csws, st);
   if (rc) return rc;
   // dW_o[:, :fa] = dzv^T x ; dW_o[:, fa:] = dzv^T s
-  rc = simt_gemm(dzv, H, false, g->x, fa, false, grads->w_e2n, fa + H, H, fa, N, none,
-                 simt_splitk_choose(H, fa, N), partial, st);
+  none.tag = "wgrad_readout_x";
+  rc = gemm(c, act_opnd(dzv, H, false, true), x_opnd(g->x, fa, false), grads->w_e2n, fa + H, H, fa, N, none, true, st);
   if (rc) return rc;
-  rc = simt_gemm(dzv, H, false, saved->s, H, false, grads->w_e2n + fa, fa + H, H, H, N, none,
-                 simt_splitk_choose(H, H, N), partial, st);
+  none.tag = "wgrad_readout_s";
+  rc = gemm(c, act_opnd(dzv, H, false, true), act_opnd(saved->s, H, false), grads->w_e2n + fa, fa + H, H, H, N, none, true,
+            st);
   if (rc) return rc;
   // ds = dzv . W_os
-  rc = simt_gemm(dzv, H, true, p->w_e2n + fa, fa + H, false, ds, H, N, H, H, none, 1, nullptr, st);
+  none.tag = "dgrad_readout";
+  rc = gemm(c, act_opnd(dzv, H, true, true), w_opnd(p->w_e2n + fa, fa + H, false, d + 1), ds, H, N, H, H, none, false, st);
   if (rc) return rc;
 
   // ---- message passing layers, last to first ----
@@ -357,12 +528,15 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
     rc = simt_colsum(dz, E, (int)H, grads->b_conv[l], p->use_skip ? h0 : nullptr,
                      p->use_skip ? grads->skip[l] : nullptr, dh0, skip, l == d - 1, csws, st);
     if (rc) return rc;
+    c.last_a = nullptr;                 // dz was rewritten in place: its split is stale
     // dW_l = dz^T m_l
-    rc = simt_gemm(dz, H, false, saved->m_all + (size_t)l * EH, H, false, grads->w_conv[l], H, H, H, E, none,
-                   simt_splitk_choose(H, H, E), partial, st);
+    none.tag = "wgrad_bond";
+    rc = gemm(c, act_opnd(dz, H, false, true), act_opnd(saved->m_all + (size_t)l * EH, H, false), grads->w_conv[l], H, H, H,
+              E, none, true, st);
     if (rc) return rc;
     // dm = dz . W_l
-    rc = simt_gemm(dz, H, true, p->w_conv[l], H, false, dm, H, E, H, H, none, 1, nullptr, st);
+    none.tag = "dgrad_bond";
+    rc = gemm(c, act_opnd(dz, H, true, true), w_opnd(p->w_conv[l], H, false, 1 + l), dm, H, E, H, H, none, false, st);
     if (rc) return rc;
     // dh_l[k] = sum_{j in in(dst k)} dm[j^1] - dm[k^1]
     GatherPost gp;
@@ -379,20 +553,23 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
     rc = simt_gather_bonds(dm, g->dst, g->in_ptr, g->in_idx, 1, dz, E, (int)H, gp, st);
     if (rc) return rc;
   }
+  c.last_a = nullptr;
 
   // ---- edge initialisation (GNN.py:85-86) ----
   rc = simt_colsum(dz, E, (int)H, grads->b_init, nullptr, nullptr, nullptr, nullptr, true, csws, st);
   if (rc) return rc;
-  if (fb > 0) {
-    rc = simt_gemm(dz, H, false, g->edge_attr, fb, false, grads->w_init + fa, fa + fb, H, fb, E, none,
+  if (fb > 0) {       // [H x fb] with fb = 14: too narrow for a tensor-core tile, stays on the fp32 kernel
+    GemmEpilogue e;
+    e.tag = "wgrad_edge_attr";
+    rc = simt_gemm(dz, H, false, g->edge_attr, fb, false, grads->w_init + fa, fa + fb, H, fb, E, e,
                    simt_splitk_choose(H, fb, E), partial, st);
     if (rc) return rc;
   }
   float* dP = ds;   // dP[v] = sum_{e: src e = v} dz0[e] = sum_{j in in(v)} dz0[j^1]
   rc = simt_atom_sum(dz, g->in_ptr, g->in_idx, 1, dP, N, (int)H, st);
   if (rc) return rc;
-  return simt_gemm(dP, H, false, g->x, fa, false, grads->w_init, fa + fb, H, fa, N, none,
-                   simt_splitk_choose(H, fa, N), partial, st);
+  none.tag = "wgrad_init_x";
+  return gemm(c, act_opnd(dP, H, false, true), x_opnd(g->x, fa, false), grads->w_init, fa + fb, H, fa, N, none, true, st);
 }
 
 extern "C" int cgr_tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, int64_t n_rxn, int32_t* tile_info,

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) ffn_grads_kernel(const float* __restrict_
   }
 }
 
-constexpr int CS_ROWS = 256;   // rows per chunk in the column-sum pass
+constexpr int CS_ROWS = 32;    // rows per chunk in the column-sum pass (many small chunks: the pass is latency-bound)
 
 __global__ void __launch_bounds__(128) colsum_pass1_kernel(const float* __restrict__ A, int64_t M, int N,
                                                            const float* __restrict__ Bm, float* __restrict__ acc,

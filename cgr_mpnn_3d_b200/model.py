@@ -120,18 +120,22 @@ class GNN(nn.Module):
         return ps
 
     def _engine_id(self, plan, needs_saved: bool) -> int:
-        """simt = exact-fp32 layer-wise kernels; tc = tcgen05 FP16x3 fused kernels (inference forward).
-        auto picks tc whenever it applies: no activations to save, even hidden size, every reaction
-        fits a 128-bond tile."""
+        """simt = exact-fp32 layer-wise kernels.  tc = tcgen05 FP16x3 tensor-core kernels: fused tile kernels for
+        an inference forward (needs a hidden size divisible by 4 and reactions of at most 128 directed bonds),
+        layer-wise path with tensor-core GEMMs when activations must be saved for a backward.
+        auto picks tc whenever it applies."""
         e = getattr(self, "engine", "auto")
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
-        can_tc = ((not needs_saved) and self.hidden_sizes[0] % 4 == 0 and self.depth <= 13
-                  and self.num_edge_features <= 32 and plan.ensure_tiles())
+        if needs_saved:
+            can_tc = self.depth <= 13
+        else:
+            can_tc = (self.hidden_sizes[0] % 4 == 0 and self.depth <= 13 and self.num_edge_features <= 32
+                      and plan.ensure_tiles())
         if e in ("tc", 1):
             if not can_tc:
-                raise RuntimeError("engine='tc' needs an inference forward (no grad, no dropout), a hidden "
-                                   "size divisible by 4 and reactions of at most 128 directed bonds")
+                raise RuntimeError("engine='tc' inference needs a hidden size divisible by 4 and reactions of at most "
+                                   "128 directed bonds (depth <= 13)")
             return _lib.ENGINE_TC
         return _lib.ENGINE_TC if can_tc else _lib.ENGINE_SIMT
 
@@ -189,8 +193,14 @@ class GNN(nn.Module):
         engine = self._engine_id(plan, train_flag)
         empty_i = torch.empty(0, dtype=torch.int32, device=dev)
         if engine == _lib.ENGINE_TC:
-            tile_info, n_tiles, tc_status = plan.tile_info, plan.n_tiles, plan.tc_status
-            tc_w = self._tc_weights(params, int(x.shape[1]), int(edge_attr.shape[1]))
+            if train_flag:           # layer-wise path with tensor-core GEMMs: no tile plan needed
+                tile_info, n_tiles = empty_i, 0
+                if plan.tc_status is None:
+                    plan.tc_status = torch.zeros(2, dtype=torch.int32, device=dev)
+                tc_status = plan.tc_status
+            else:
+                tile_info, n_tiles, tc_status = plan.tile_info, plan.n_tiles, plan.tc_status
+            tc_w = self._tc_weights([p.detach() for p in params], int(x.shape[1]), int(edge_attr.shape[1]))
             x_hi, x_lo = split_features_for(data, plan)
         else:
             tile_info, n_tiles, tc_status = empty_i, 0, empty_i
@@ -200,7 +210,8 @@ class GNN(nn.Module):
                               self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
                               train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo,
                               getattr(self, "tile_policy", "latency") == "throughput")
-        self.__dict__["_last_plan"] = plan if engine == _lib.ENGINE_TC else None
+        self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and not train_flag) else None
+        self.__dict__["_last_engine"] = engine
         out = res[0]
         if caller_device != dev:
             out = out.to(caller_device)

@@ -60,7 +60,7 @@ class _Ctx:
 def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info=None, n_tiles=0,
                   tc_status=None, x_hi=None, x_lo=None) -> _lib.CgrGraph:
     has_tiles = tile_info is not None and tile_info.numel() > 0 and n_tiles > 0
-    has_split = has_tiles and x_hi is not None and x_lo is not None and x_hi.numel() > 0 and x_lo.numel() > 0
+    has_split = x_hi is not None and x_lo is not None and x_hi.numel() > 0 and x_lo.numel() > 0
     return _lib.CgrGraph(
         n_atoms=int(x.shape[0]), n_bonds=int(src.shape[0]), n_rxn=int(atom_ptr.shape[0]) - 1,
         x=x.data_ptr(), edge_attr=edge_attr.data_ptr(), src=src.data_ptr(), dst=dst.data_ptr(),
@@ -148,7 +148,8 @@ def _(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_
 @torch.library.custom_op("cgr_b200::gnn_backward", mutates_args=())
 def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor,
                  in_idx: Tensor, atom_ptr: Tensor, params: Sequence[Tensor], saved: Sequence[Tensor], depth: int,
-                 act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int) -> List[Tensor]:
+                 act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int, tc_weights: Tensor,
+                 x_hi: Tensor, x_lo: Tensor) -> List[Tensor]:
     """Explicit backward: gradients of every parameter, in parameter-list order."""
     _require_cuda(grad_out, x, *params)
     lib = _lib.load()
@@ -157,7 +158,9 @@ def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, ds
     grad_out = _f32c(grad_out)
     fa, fb = int(x.shape[1]), int(edge_attr.shape[1])
     ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
-    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr)
+    if tc_weights.numel() > 0:
+        ctx.params.tc_weights = tc_weights.data_ptr()
+    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, None, 0, None, x_hi, x_lo)
     h_all, m_all, z_all, s, hv, zv, pooled = saved
     need_z = act != 0
     sv = _lib.CgrSaved(h_all=h_all.data_ptr(), m_all=m_all.data_ptr(), z_all=z_all.data_ptr() if need_z else None,
@@ -182,7 +185,7 @@ def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, ds
 
 @gnn_backward.register_fake
 def _(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip, dropout_ps,
-      seed, engine):
+      seed, engine, tc_weights, x_hi, x_lo):
     return [torch.empty_like(p) for p in params]
 
 
@@ -191,7 +194,8 @@ def _setup_context(ctx, inputs, output):
      engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo, _tp) = inputs
     ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine)
     ctx.n_params = len(params)
-    ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:])
+    ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:], _tc_weights, _x_hi,
+                          _x_lo)
 
 
 def _backward(ctx, grads):
@@ -202,12 +206,13 @@ def _backward(ctx, grads):
     t = ctx.saved_tensors
     x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr = t[:7]
     params = list(t[7:7 + ctx.n_params])
-    saved = list(t[7 + ctx.n_params:])
+    saved = list(t[7 + ctx.n_params:-3])
+    tc_weights, x_hi, x_lo = t[-3:]
     g_out = grads[0]
     if g_out is None:
         g_out = torch.zeros(atom_ptr.shape[0] - 1, dtype=torch.float32, device=x.device)
     pg = gnn_backward(g_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip,
-                      dropout_ps, seed, 0)
+                      dropout_ps, seed, engine, tc_weights, x_hi, x_lo)
     return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None, None, None,
             None, None, None, None, None)
 

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 EA_TOL = 1e-4      # north_star: per-reaction Ea within 1e-4 relative (fp32 / split-precision mode)
 GRAD_TOL = 1e-4
 
-ENGINES = ["simt"]
+ENGINES = ["simt", "tc"]
 
 
 @pytest.fixture(scope="module", autouse=True)
