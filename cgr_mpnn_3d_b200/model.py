@@ -200,7 +200,13 @@ class GNN(nn.Module):
                 tc_status = plan.tc_status
             else:
                 tile_info, n_tiles, tc_status = plan.tile_info, plan.n_tiles, plan.tc_status
-            tc_w = self._tc_weights([p.detach() for p in params], int(x.shape[1]), int(edge_attr.shape[1]))
+            if train_flag:
+                # weights change every optimizer step: always re-prepare (3 small launches, CUDA-graph safe --
+                # a version-keyed cache hit at capture time would freeze stale weights into the graph)
+                tc_w = ops.prepare_tc_weights([p.detach() for p in params], self.depth, _act_id(self.activation_fn),
+                                              bool(self.use_learnable_skip), int(x.shape[1]), int(edge_attr.shape[1]))
+            else:
+                tc_w = self._tc_weights([p.detach() for p in params], int(x.shape[1]), int(edge_attr.shape[1]))
             x_hi, x_lo = split_features_for(data, plan)
         else:
             tile_info, n_tiles, tc_status = empty_i, 0, empty_i
