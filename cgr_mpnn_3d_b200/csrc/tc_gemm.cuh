@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(cons
       const int ebase = aux->info[0], ecount = aux->info[1];
       const int H = p.n_total;
       const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+      float vmax = 0.f;
       for (int j0 = warp * RU; j0 < ecount; j0 += NWARPS * RU) {
         uint2 nb[RU];
         int deg[RU], maxdeg = 0;
@@ -380,14 +381,21 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(cons
           float4 acc[RU];
 #pragma unroll
           for (int u = 0; u < RU; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int fast = maxdeg < NBR ? maxdeg : NBR;
-          for (int t = 0; t < fast; ++t) {                        // ascending bond id: the reference's order
+          // ascending bond id: the reference's order.  Slots 0-3 are unrolled with constant shifts (a CGR atom
+          // rarely has more than 4 bonds), slots 4-7 loop.
 #pragma unroll
-            for (int u = 0; u < RU; ++u) {
-              const uint32_t w = t < 4 ? nb[u].x : nb[u].y;
-              const int k = (int)((w >> (8 * (t & 3))) & 0xffu);
-              if (t < deg[u]) add4(acc[u], ld4(y_s + k * CHP + c));
+          for (int t = 0; t < 4; ++t) {
+            if (t < maxdeg) {
+#pragma unroll
+              for (int u = 0; u < RU; ++u)
+                if (t < deg[u]) add4(acc[u], ld4(y_s + (int)((nb[u].x >> (8 * t)) & 0xffu) * CHP + c));
             }
+          }
+          const int fast = maxdeg < NBR ? maxdeg : NBR;
+          for (int t = 4; t < fast; ++t) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+              if (t < deg[u]) add4(acc[u], ld4(y_s + (int)((nb[u].y >> (8 * (t - 4))) & 0xffu) * CHP + c));
           }
           if (maxdeg > NBR) {                                     // rare: atoms with more than NBR bonds
 #pragma unroll
@@ -412,10 +420,9 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(cons
               if (p.dropout_p > 0.f)
                 v = cgr_dropout_keep(p.seed, p.layer, (uint64_t)(ebase + j) * (uint64_t)H + (uint64_t)(n + i),
                                      p.dropout_p) ? v * keep_scale : 0.f;
-              if (n + i >= H) v = 0.f;                            // K padding of the next operand
-              z[i] = v;
+              z[i] = v;                                            // H % 4 == 0: the whole column group is real
             }
-            ovf |= fmaxf(fmaxf(fabsf(z[0]), fabsf(z[1])), fmaxf(fabsf(z[2]), fabsf(z[3]))) > 60000.f;
+            vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(z[0]), fabsf(z[1]))), fmaxf(fabsf(z[2]), fabsf(z[3])));
             // FP16 (hi, lo) split with packed conversions: hi = rn(v), lo = rn(v - hi)
             const __half2 hi01 = __floats2half2_rn(z[0], z[1]), hi23 = __floats2half2_rn(z[2], z[3]);
             const float2 f01 = __half22float2(hi01), f23 = __half22float2(hi23);
@@ -431,6 +438,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(cons
           }
         }
       }
+      ovf |= vmax > 60000.f;
     } else {
       // readout: hv[v] = act(Q[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
       const int acount = aux->info[3];
@@ -451,14 +459,19 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(cons
           float4 acc[RU];
 #pragma unroll
           for (int u = 0; u < RU; ++u) acc[u] = v0 + u < acount ? ld4(r_s + (v0 + u) * CH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const int fast = maxdeg < NBR ? maxdeg : NBR;
-          for (int k = 0; k < fast; ++k) {
 #pragma unroll
-            for (int u = 0; u < RU; ++u) {
-              const uint32_t w = k < 4 ? nb[u].x : nb[u].y;
-              const int row = (int)((w >> (8 * (k & 3))) & 0xffu);
-              if (k < deg[u]) add4(acc[u], ld4(y_s + row * CHP + c));
+          for (int k = 0; k < 4; ++k) {
+            if (k < maxdeg) {
+#pragma unroll
+              for (int u = 0; u < RU; ++u)
+                if (k < deg[u]) add4(acc[u], ld4(y_s + (int)((nb[u].x >> (8 * k)) & 0xffu) * CHP + c));
             }
+          }
+          const int fast = maxdeg < NBR ? maxdeg : NBR;
+          for (int k = 4; k < fast; ++k) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+              if (k < deg[u]) add4(acc[u], ld4(y_s + (int)((nb[u].y >> (8 * (k - 4))) & 0xffu) * CHP + c));
           }
           if (maxdeg > NBR) {
 #pragma unroll
