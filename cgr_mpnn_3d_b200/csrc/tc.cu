@@ -327,7 +327,7 @@ int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char
 }
 
 constexpr int BN_SMALL = 80, BN_LARGE = 208;
-constexpr int NT_SMALL = 256;     // narrow slices run two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
+constexpr int NT_SMALL = 384;     // narrow slices run two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
 
 // Slice width: wide slices (208) amortise the A-operand fetch of the SS-mode MMA and halve the A re-reads;
 // narrow slices (80) give small batches enough CTAs to occupy the 148 SMs.
@@ -522,6 +522,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     if ((rc = make_map(&prm.tmB_hi, w_hi(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     prm.num_k = (int)cgr_ceil_div(fa, BK);
+    prm.k_total = fa;
     prm.n_total = 2 * H;
     prm.m_rows = (int)N;
     prm.unscale = unscale + 0;
@@ -562,6 +563,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     if ((rc = make_map(&prm.tmB_hi, w_hi(1 + l), H, H, wl.ld[1 + l], bn_h))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(1 + l), H, H, wl.ld[1 + l], bn_h))) return rc;
     prm.num_k = (int)cgr_ceil_div(H, BK);
+    prm.k_total = H;
     prm.n_total = H;
     prm.unscale = unscale + 1 + l;
     prm.bias = p->b_conv[l];
@@ -589,6 +591,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     if ((rc = make_map(&prm.tmB_hi, w_hi(d + 1), H, H, wl.ld[d + 1], bn_h))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(d + 1), H, H, wl.ld[d + 1], bn_h))) return rc;
     prm.num_k = (int)cgr_ceil_div(H, BK);
+    prm.k_total = H;
     prm.n_total = H;
     prm.unscale = unscale + d + 1;
     prm.tile_info = g->tile_info;
@@ -647,6 +650,7 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   if ((rc = make_map(&prm.tmB_hi, b_hi, N, K, kp, bn))) return rc;
   if ((rc = make_map(&prm.tmB_lo, b_lo, N, K, kp, bn))) return rc;
   prm.num_k = (int)cgr_ceil_div(K, BK);
+  prm.k_total = (int)K;
   prm.n_total = (int)N;
   prm.m_rows = (int)M;
   prm.unscale = one;

@@ -28,7 +28,7 @@ template <int BN_, int EPI, int NT_>
 struct Cfg {
   static constexpr int NT = NT_;
   static constexpr int NWARPS = NT / 32;
-  static constexpr int CTAS_PER_SM = NT <= 256 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = NT <= 384 ? 2 : 1;
   static constexpr bool R_ALIAS = CTAS_PER_SM > 1;      // fp32 operand chunk 0 lives in the drained pipeline
   static constexpr int BN = BN_;                          // output columns per CTA (UMMA N), multiple of 16
   static constexpr int NCH = BN > 128 ? 2 : 1;            // epilogue column chunks
@@ -61,6 +61,7 @@ struct TcGemmParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   CUtensorMap tmR;              // fp32 [rows, cols] operand of the epilogue (BOND: h0, READOUT: Q), box = [128, CH]
   int num_k;                    // k-chunks of BK
+  int k_total;                  // real K: the last chunk only issues the k-steps that hold data
   int n_total;                  // real output columns
   int m_rows;                   // real rows (EPI_PLAIN)
   int r_col0;                   // column offset of the R operand inside its tensor (READOUT: H)
@@ -122,7 +123,7 @@ __device__ __forceinline__ float act_t(float z, int act) { return RELU ? fmaxf(z
 
 // RELU: compile-time fast path for the reference's default activation (branch-free epilogue)
 template <int BN_, int EPI, bool RELU, int NT_>
-__global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+__global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using C = Cfg<BN_, EPI, NT_>;
   constexpr int THREADS = C::NT, NWARPS = C::NWARPS;
   constexpr int BN = C::BN, CH = C::CH, CHP = C::CHP, VL = C::VL, NCH = C::NCH, STAGES = C::STAGES;
@@ -219,8 +220,11 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 256 ? 2 : 1)) tc_gemm_kernel(cons
         const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
         const uint64_t db_hi = umma::smem_desc_k_sw128(st + 2 * A_BYTES);
         const uint64_t db_lo = umma::smem_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+        const int k_left = p.k_total - kc * BK;                   // K tail: skip k-steps that are all zero padding
+        const int ksteps = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ++ks) {
+          if (ks >= ksteps) break;
           const uint64_t adv = (uint64_t)(ks * 32 >> 4);          // 16 fp16 = 32 bytes along K inside the swizzle row
           if (C::CAT) {
             // cols [0,BN) += A_hi B_hi^T, cols [BN,2BN) += A_hi B_lo^T (one instruction), then cols [0,BN) += A_lo B_hi^T
