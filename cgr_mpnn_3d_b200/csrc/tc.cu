@@ -327,7 +327,7 @@ int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char
 }
 
 constexpr int BN_SMALL = 80, BN_LARGE = 208;
-constexpr int NT_SMALL = 384;     // narrow slices run two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
+constexpr int NT_SMALL = 256;     // narrow slices run two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
 
 // Slice width: wide slices (208) amortise the A-operand fetch of the SS-mode MMA and halve the A re-reads;
 // narrow slices (80) give small batches enough CTAs to occupy the 148 SMs.
