@@ -386,11 +386,11 @@ def main():
             barrier()
             e2e_single_s = time.perf_counter() - t0
             # the pipelined public API for a stream of host batches (H2D of batch i+1 overlaps batch i's kernels)
-            list(model.predict_stream((pinned[i % n_pool] for i in range(6)), depth=3))
+            list(model.predict_stream((pinned[i % n_pool] for i in range(8)), depth=4))
             barrier()
             t0 = time.perf_counter()
             n_done = 0
-            for res in model.predict_stream((pinned[i % n_pool] for i in range(args.steps)), depth=3):
+            for res in model.predict_stream((pinned[i % n_pool] for i in range(args.steps)), depth=4):
                 n_done += 1
             barrier()
             e2e_s = time.perf_counter() - t0
@@ -488,7 +488,7 @@ def main():
                                           "(optimizer excluded), batch %d/GPU, whole step replayed as a CUDA graph" % args.batch}
         if e2e:
             line["e2e"] = {"value": total_rxn / e2e_s, "unit": "reactions/s",
-                           "api": "GNN.predict_stream(host batches, depth=3): H2D + index build + kernels + D2H per step",
+                           "api": "GNN.predict_stream(host batches, depth=4, workers=2): H2D + index build + kernels + D2H per step",
                            "single_call_value": total_rxn / e2e_single_s, "single_call_api": "GNN.forward(host batch)",
                            "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
                            "d2h_bytes_per_step": e2e["d2h_bytes_per_step"]}

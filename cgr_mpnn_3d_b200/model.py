@@ -317,54 +317,75 @@ class GNN(nn.Module):
         _lib.check(rc, "cgr_gnn_infer_host")
         return hout[:b].clone()
 
-    def predict_stream(self, batches, depth: int = 3):
+    def predict_stream(self, batches, depth: int = 4, workers: int = 2):
         """Pipelined inference over an iterable of HOST batches (the screening workload): yields one CPU
         tensor of energies per batch, in order.  Up to ``depth`` batches are in flight, each on its own
         stream with its own staging buffers, so the H2D copy of batch i+1 overlaps the kernels of batch i
-        (``cgr_gnn_infer_host_async``).  Batches that cannot use the tcgen05 engine go through ``forward``."""
+        (``cgr_gnn_infer_host_async``); ``workers`` host threads issue the calls (the C entry releases the
+        GIL).  Batches that cannot use the tcgen05 engine go through ``forward``."""
         import ctypes as C
         from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
         lib = _lib.load()
+        depth = max(1, depth)
         pending = deque()
+        pool = ThreadPoolExecutor(max_workers=max(1, workers))
+
+        def submit(slot_id, data):
+            f = self._host_fields(data)
+            if f is None:
+                return None
+            x, ei, ea, batch, ptr, n, e, b = f
+            ctx, dev = self._host_ctx(int(x.shape[1]), int(ea.shape[1]))
+            with torch.cuda.device(dev):
+                slot = self._host_slot(slot_id, ctx, dev, n, e, b)
+                dws, hws, hout, st = slot
+                ctx.params.tc_throughput = 1          # several batches in flight
+                rc = lib.cgr_gnn_infer_host_async(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
+                                                  _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(),
+                                                  dws.data_ptr(), dws.numel(), hws.data_ptr(), hws.numel(),
+                                                  st.cuda_stream)
+            if rc == -3:
+                return None
+            _lib.check(rc, "cgr_gnn_infer_host_async")
+            return slot, ctx, n, e, b, (x, ei, ea, batch, ptr)
 
         def finish():
-            slot, ctx, n, e, b, keep = pending.popleft()
+            fut, data = pending.popleft()
+            res = fut.result()
+            if res is None:                         # not tileable: generic path
+                return self.forward(data)
+            slot, ctx, n, e, b, _keep = res
             dws, hws, hout, st = slot
             st.synchronize()
             _lib.check(lib.cgr_infer_host_check(C.byref(ctx.params), n, e, b, hws.data_ptr()), "cgr_infer_host_check")
             return hout[:b].clone()
 
-        i = 0
-        with torch.no_grad():
-            for data in batches:
-                f = self._host_fields(data) if (self._host_supported() and data.x.device.type == "cpu") else None
-                if f is None:
+        try:
+            with torch.no_grad():
+                if self._host_supported():
+                    first = True
+                    i = 0
+                    for data in batches:
+                        if data.x.device.type != "cpu":
+                            while pending:
+                                yield finish()
+                            yield self.forward(data)
+                            continue
+                        if first:                    # build the cached parameter block outside the workers
+                            self._host_ctx(int(data.x.shape[1]), int(data.edge_attr.shape[1]))
+                            first = False
+                        if len(pending) >= depth:
+                            yield finish()
+                        pending.append((pool.submit(submit, 1 + i % depth, data), data))
+                        i += 1
                     while pending:
                         yield finish()
-                    yield self.forward(data)
-                    continue
-                x, ei, ea, batch, ptr, n, e, b = f
-                ctx, dev = self._host_ctx(int(x.shape[1]), int(ea.shape[1]))
-                if len(pending) >= depth:
-                    yield finish()
-                with torch.cuda.device(dev):
-                    slot = self._host_slot(1 + i % depth, ctx, dev, n, e, b)
-                    dws, hws, hout, st = slot
-                    ctx.params.tc_throughput = 1          # several batches in flight
-                    rc = lib.cgr_gnn_infer_host_async(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
-                                                      _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(),
-                                                      dws.data_ptr(), dws.numel(), hws.data_ptr(), hws.numel(),
-                                                      st.cuda_stream)
-                if rc == -3:
-                    while pending:
-                        yield finish()
-                    yield self.forward(data)
-                    continue
-                _lib.check(rc, "cgr_gnn_infer_host_async")
-                pending.append((slot, ctx, n, e, b, (x, ei, ea, batch, ptr)))
-                i += 1
-            while pending:
-                yield finish()
+                else:
+                    for data in batches:
+                        yield self.forward(data)
+        finally:
+            pool.shutdown(wait=True)
 
     def check_numerics(self) -> None:
         """Synchronising check of the last tcgen05 forward: raises if an activation left the fp16 range

@@ -426,6 +426,7 @@ def test_host_buffer_inference_entry(name):
     # pipelined API over several host batches: same numbers, in order
     many = [data, nb, data]
     outs = list(model.predict_stream(many, depth=2))
+    assert all(torch.equal(o, out) for o in model.predict_stream(many * 3, depth=4, workers=3))
     assert len(outs) == 3 and all(torch.equal(o, out) for o in outs)
     bad = Batch(data.x, data.edge_index.clone(), data.edge_attr, data.batch, data.ptr, None)
     bad.edge_index[:, [0, 2]] = bad.edge_index[:, [2, 0]]
