@@ -333,9 +333,16 @@ def main():
     prof_steps = min(args.steps, 40)
     stage_ms, stage_cnt = {}, {}
     with torch.no_grad():
+        prof_model = lat_model if n_streams == 1 else model
+        for i in range(3):
+            prof_model(pool[i % n_pool])
+        torch.cuda.synchronize()
         lib.cgr_profile_enable(1)
         for i in range(prof_steps):
-            model(pool[i % n_pool])
+            # keep the stream busy while the host enqueues the step, so the kernels (and the events between
+            # them) execute back to back: the event pairs then bracket kernel time, not host launch latency
+            torch.cuda._sleep(2_000_000)
+            prof_model(pool[i % n_pool])
         torch.cuda.synchronize()
         name = ctypes.create_string_buffer(64)
         ms = ctypes.c_float()
