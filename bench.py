@@ -373,6 +373,8 @@ def main():
             pass
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": per_launch,
+                    "note": "achieved/frac: one launch bracketed by CUDA events on its stream (kernel alone on the GPU, "
+                            "launch latency included); sustained_*: its share of the pipelined timed region",
                     "peak_kind": peak_kind,
                     "avg_launch_us": avg_ms * 1e3, "launches_per_step": stage_cnt[dominant] / prof_steps,
                     "stage_share": {k: round(v / sum(stage_ms.values()), 4) for k, v in sorted(stage_ms.items())}}
@@ -466,6 +468,11 @@ def main():
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     clocks.stop()
+    if roofline:
+        share = roofline["stage_share"].get(roofline["kernel"], 0.0)
+        sus_us = (ms_total / args.steps) * 1e3 * share / max(1e-9, roofline["launches_per_step"])
+        roofline["sustained_us_per_launch"] = sus_us
+        roofline["sustained_frac"] = roofline["algorithmic_bytes_per_launch"] / (sus_us * 1e-6) / 1e9 / hbm_peak
     if rank == 0:
         alg = algorithmic_bytes_fwd(n_atoms, n_bonds, args.batch)
         line = {
