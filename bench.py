@@ -292,6 +292,10 @@ def main():
                 ev.record(st)
                 main.wait_event(ev)
 
+        if graphs is not None:             # initialisation, like the capture itself: instantiate/upload every graph once
+            for gph in graphs:
+                gph.replay()
+            torch.cuda.synchronize()
         clocks = ClockSampler(local_rank).start()
         run_steps(max(3, args.warmup))
         barrier()
