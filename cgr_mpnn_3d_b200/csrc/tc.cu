@@ -48,9 +48,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   if (ovf) atomicOr(overflow, 1);
 }
 
-// h0 = act(P'[src e] + ea[e] . W_e^T) on tile-packed rows (P' already holds b_i); one warp per bond row,
-// lanes sweep float4 column groups; W_e^T [fb][H] is read coalesced.  Writes the fp32 copy (skip operand of
-// every layer) and the FP16 (hi, lo) operand of layer 0.
+// h0 = act(P'[src e] + ea[e] . W_e^T) on tile-packed rows (P' already holds b_i).  A block owns 32 bond rows of one
+// tile: W_e^T [fb][H] and the rows' bond features are staged in shared memory, each warp then produces 4 rows at a
+// time (4 independent gathers of P' in flight per lane).  Writes the fp32 copy (skip operand of every layer) and the
+// FP16 (hi, lo) operand of layer 0.
+constexpr int EI_ROWS = 32;
 __global__ void __launch_bounds__(256) tc_edge_init_kernel(const float* __restrict__ PQ, int64_t ldpq,
                                                            const float* __restrict__ ea, const int32_t* __restrict__ src,
                                                            const float* __restrict__ wet,
@@ -58,41 +60,66 @@ __global__ void __launch_bounds__(256) tc_edge_init_kernel(const float* __restri
                                                            float* __restrict__ h0, __half* __restrict__ o_hi,
                                                            __half* __restrict__ o_lo, int64_t ldo,
                                                            int* __restrict__ overflow) {
+  extern __shared__ __align__(16) float ei_smem[];
+  float* wet_s = ei_smem;                          // [fb][H]
+  float* ea_s = ei_smem + (size_t)fb * H;          // [EI_ROWS][fb]
   const int tile = blockIdx.y;
   const int ebase = __ldg(tile_info + tile * 8), ecount = __ldg(tile_info + tile * 8 + 1);
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * EI_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   umma::grid_dep_launch();
+  if (j0 >= ecount) return;
+  // weights and bond features do not depend on the previous kernel: stage them before the dependency wait
+  for (int i = threadIdx.x; i < fb * H / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(wet_s)[i] = __ldg(reinterpret_cast<const float4*>(wet) + i);
+  for (int i = threadIdx.x; i < EI_ROWS * fb; i += blockDim.x) {
+    const int j = j0 + i / fb;
+    ea_s[i] = j < ecount ? __ldg(ea + (int64_t)(ebase + j) * fb + (i % fb)) : 0.f;
+  }
   umma::grid_dep_wait();                          // PQ comes from the atom-projection kernel
-  if (j >= ecount) return;
-  const int64_t e = (int64_t)ebase + j, r = (int64_t)tile * TM + j;
-  const float* prow = PQ + (int64_t)__ldg(src + e) * ldpq;
-  const float ea_l = lane < fb ? __ldg(ea + e * fb + lane) : 0.f;      // fb <= 32 (checked by the caller)
-  bool ovf = false;
-  for (int nb = 0; nb < H; nb += 128) {            // warp-uniform trip count: every lane takes part in the shuffles
-    const int n = nb + 4 * lane;
-    const bool on = n < H;
-    float4 a = on ? __ldg(reinterpret_cast<const float4*>(prow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int jw = j0 + warp * 4;                    // this warp's 4 rows
+  if (jw >= ecount) return;
+  const float* prow[4];
+  int64_t r[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = jw + u < ecount ? jw + u : jw;
+    prow[u] = PQ + (int64_t)__ldg(src + ebase + j) * ldpq;
+    r[u] = (int64_t)tile * TM + j;
+  }
+  float vmax = 0.f;
+  for (int n = 4 * lane; n < H; n += 128) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __ldg(reinterpret_cast<const float4*>(prow[u] + n));
     for (int k = 0; k < fb; ++k) {
-      const float ek = __shfl_sync(0xffffffffu, ea_l, k);
-      if (on) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(wet + (int64_t)k * H + n));
-        a.x = fmaf(ek, w.x, a.x); a.y = fmaf(ek, w.y, a.y); a.z = fmaf(ek, w.z, a.z); a.w = fmaf(ek, w.w, a.w);
+      const float4 w = *reinterpret_cast<const float4*>(wet_s + (size_t)k * H + n);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float ek = ea_s[(warp * 4 + u) * fb + k];
+        a[u].x = fmaf(ek, w.x, a[u].x); a[u].y = fmaf(ek, w.y, a[u].y);
+        a[u].z = fmaf(ek, w.z, a[u].z); a[u].w = fmaf(ek, w.w, a[u].w);
       }
     }
-    if (!on) continue;
-    a.x = cgr_act(a.x, act); a.y = cgr_act(a.y, act); a.z = cgr_act(a.z, act); a.w = cgr_act(a.w, act);
-    ovf |= fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))) > 60000.f;
-    *reinterpret_cast<float4*>(h0 + r * H + n) = a;
-    const __half2 hi01 = __floats2half2_rn(a.x, a.y), hi23 = __floats2half2_rn(a.z, a.w);
-    const float2 f01 = __half22float2(hi01), f23 = __half22float2(hi23);
-    const __half2 lo01 = __floats2half2_rn(a.x - f01.x, a.y - f01.y), lo23 = __floats2half2_rn(a.z - f23.x, a.w - f23.y);
-    uint2 ph, pl;
-    ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
-    pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
-    *reinterpret_cast<uint2*>(o_hi + r * ldo + n) = ph;
-    *reinterpret_cast<uint2*>(o_lo + r * ldo + n) = pl;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (jw + u >= ecount) break;
+      float4 v = a[u];
+      v.x = cgr_act(v.x, act); v.y = cgr_act(v.y, act); v.z = cgr_act(v.z, act); v.w = cgr_act(v.w, act);
+      vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      *reinterpret_cast<float4*>(h0 + r[u] * H + n) = v;
+      const __half2 hi01 = __floats2half2_rn(v.x, v.y), hi23 = __floats2half2_rn(v.z, v.w);
+      const float2 f01 = __half22float2(hi01), f23 = __half22float2(hi23);
+      const __half2 lo01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), lo23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+      uint2 ph, pl;
+      ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
+      pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
+      *reinterpret_cast<uint2*>(o_hi + r[u] * ldo + n) = ph;
+      *reinterpret_cast<uint2*>(o_lo + r[u] * ldo + n) = pl;
+    }
   }
-  if (ovf) atomicOr(overflow, 1);
+  if (vmax > 60000.f) atomicOr(overflow, 1);
 }
 
 // W_e^T [fb][H] from edge_init.weight[:, fa:]  (coalesced reads in the edge-init kernel)
@@ -539,8 +566,14 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     cgr_note_launch("tc_edge_init", st, 1);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(TM / 8, (unsigned)T);
+    cfg.gridDim = dim3(TM / EI_ROWS, (unsigned)T);
     cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = (size_t)((fb > 0 ? fb : 1) * H + EI_ROWS * (fb > 0 ? fb : 1)) * sizeof(float);
+    static bool ei_attr = false;
+    if (!ei_attr) {
+      CGR_CUDA(cudaFuncSetAttribute(tc_edge_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      ei_attr = true;
+    }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
