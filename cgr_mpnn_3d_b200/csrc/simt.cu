@@ -181,12 +181,25 @@ __global__ void __launch_bounds__(256) gather_bonds_kernel(const float* __restri
   const int32_t v = __ldg(node + e);
   const int32_t beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
   const int64_t rev = e ^ 1;
+  // neighbour ids fetched once by the lanes and broadcast, instead of a dependent load chain per column group
+  const int deg = end - beg;
+  const int32_t my_nb = lane < deg ? (__ldg(in_idx + beg + lane) ^ flip) : 0;
+  int32_t nbr[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) nbr[p] = __shfl_sync(0xffffffffu, my_nb, p);   // every lane takes part, before any divergence
   if (VEC == 4) {
     const int H4 = H >> 2;
     for (int c = lane; c < H4; c += 32) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int32_t p = beg; p < end; ++p) {          // ascending bond id: CPU scatter_add_ order
-        const int64_t k = (int64_t)(__ldg(in_idx + p) ^ flip);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {                  // ascending bond id: CPU scatter_add_ order
+        if (p < deg) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(in + (int64_t)nbr[p] * H) + c);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+      }
+      for (int32_t p = 8; p < deg; ++p) {
+        const int64_t k = (int64_t)(__ldg(in_idx + beg + p) ^ flip);
         const float4 t = __ldg(reinterpret_cast<const float4*>(in + k * H) + c);
         a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       }
@@ -367,12 +380,23 @@ __global__ void __launch_bounds__(128) colsum_pass1_kernel(const float* __restri
   const float sc = acc ? (scale ? __ldg(scale) : 1.f) : 0.f;
   float cs = 0.f, dt = 0.f;
   if (n < N) {
-    for (int64_t r = r0; r < r1; ++r) {
-      const int64_t idx = r * N + n;
-      const float a = __ldg(A + idx);
-      cs += a;
-      if (Bm) dt = fmaf(a, __ldg(Bm + idx), dt);
-      if (acc) acc[idx] = first ? sc * a : fmaf(sc, a, acc[idx]);
+    // 8 independent rows in flight per thread; sums are added in ascending row order (fixed, deterministic)
+    for (int64_t r = r0; r < r1; r += 8) {
+      float a[8], b[8], o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool on = r + i < r1;
+        const int64_t idx = (r + i) * N + n;
+        a[i] = on ? __ldg(A + idx) : 0.f;
+        b[i] = (on && Bm) ? __ldg(Bm + idx) : 0.f;
+        o[i] = (on && acc && !first) ? acc[idx] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cs += a[i];
+        dt = fmaf(a[i], b[i], dt);
+        if (acc && r + i < r1) acc[(r + i) * N + n] = fmaf(sc, a[i], o[i]);
+      }
     }
     part_col[(int64_t)blockIdx.y * N + n] = cs;
   }
@@ -382,21 +406,26 @@ __global__ void __launch_bounds__(128) colsum_pass1_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(128) colsum_pass2_kernel(const float* __restrict__ part_col,
+// second pass: one warp per column sums the chunk partials (lanes stride over chunks, fixed shuffle tree)
+__global__ void __launch_bounds__(256) colsum_pass2_kernel(const float* __restrict__ part_col,
                                                            const float* __restrict__ part_dot, int64_t chunks,
                                                            int N, int64_t n_dot, float* __restrict__ colsum,
                                                            float* __restrict__ dot) {
-  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
   if (n < N && colsum) {
     float s = 0.f;
-    for (int64_t c = 0; c < chunks; ++c) s += part_col[c * N + n];
-    colsum[n] = s;
+    for (int64_t c = lane; c < chunks; c += 32) s += part_col[c * N + n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) colsum[n] = s;
   }
-  if (dot && blockIdx.x == 0) {
+  if (dot && blockIdx.x == 0 && warp == 0) {
     float s = 0.f;
-    for (int64_t i = threadIdx.x; i < n_dot; i += 128) s += part_dot[i];
-    const float tot = block_sum_128(s);
-    if (threadIdx.x == 0) dot[0] = tot;
+    for (int64_t i = lane; i < n_dot; i += 32) s += part_dot[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) dot[0] = s;
   }
 }
 
@@ -548,8 +577,8 @@ int simt_colsum(const float* A, int64_t M, int N, float* colsum, const float* Bm
   CgrRange prof("colsum", st);
   cgr_note_launch("colsum", st, 2);
   colsum_pass1_kernel<<<grid, 128, 0, st>>>(A, M, N, Bm, acc, scale, first ? 1 : 0, part_col, part_dot);
-  colsum_pass2_kernel<<<(unsigned)ncb, 128, 0, st>>>(part_col, part_dot, chunks, N, chunks * ncb, colsum,
-                                                     Bm ? dot : nullptr);
+  colsum_pass2_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(part_col, part_dot, chunks, N, chunks * ncb, colsum,
+                                                                    Bm ? dot : nullptr);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }

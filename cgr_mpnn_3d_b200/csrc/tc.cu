@@ -699,15 +699,33 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// max |v| of a [rows, cols] tensor: one warp per row, float4 loads when the row is 16-byte aligned
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
                                                    unsigned int* __restrict__ amax_bits) {
-  const int64_t total = rows * cols;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(__ldg(in + (i / cols) * ld + (i % cols))));
+  if (r < rows) {
+    const float* row = in + r * ld;
+    if ((ld & 3) == 0 && (cols & 3) == 0 && ((uintptr_t)in & 15) == 0) {
+      for (int c = lane; c < cols / 4; c += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + c);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(__ldg(row + c)));
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));
+  __shared__ float wm[8];
+  if (lane == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = wm[0];
+    for (int i = 1; i < 8; ++i) b = fmaxf(b, wm[i]);
+    atomicMax(amax_bits, __float_as_uint(b));       // max is order-independent: deterministic
+  }
 }
 
 // fp32 [rows, cols] -> FP16 (hi, lo) with the power-of-two scale that maps amax into (2^13, 2^14];
@@ -721,11 +739,28 @@ __global__ void __launch_bounds__(256) split_scaled_kernel(const float* __restri
   if (blockIdx.x == 0 && threadIdx.x == 0) *unscale_out = 1.f / sc;
   const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
-  for (int c = threadIdx.x & 31; c < cols; c += 32) {
-    __half h, l;
-    split_f16(__ldg(in + r * ld + c) * sc, h, l);
-    hi[r * ldo + c] = h;
-    lo[r * ldo + c] = l;
+  const int lane = threadIdx.x & 31;
+  const float* row = in + r * ld;
+  if ((ld & 3) == 0 && (cols & 3) == 0 && ((uintptr_t)in & 15) == 0) {
+    for (int c4 = lane; c4 < cols / 4; c4 += 32) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(row) + c4);
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+      uint2 ph, pl;
+      ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(hi + r * ldo + 4 * c4) = ph;
+      *reinterpret_cast<uint2*>(lo + r * ldo + 4 * c4) = pl;
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      __half h, l;
+      split_f16(__ldg(row + c) * sc, h, l);
+      hi[r * ldo + c] = h;
+      lo[r * ldo + c] = l;
+    }
   }
 }
 
@@ -764,9 +799,7 @@ int tc_split(const float* in, int64_t ld, int64_t rows, int cols, bool scaled, _
   if (scaled) {
     cgr_note_launch("tc_split", st, 2);
     CGR_CUDA(cudaMemsetAsync(amax_slot, 0, sizeof(unsigned int), st));
-    const int64_t total = rows * cols;
-    amax_kernel<<<(unsigned)(total > 65536 * 64 ? 256 : cgr_ceil_div(total, 16384) > 0 ? cgr_ceil_div(total, 16384) : 1), 256, 0,
-                  st>>>(in, ld, rows, cols, amax_slot);
+    amax_kernel<<<(unsigned)cgr_ceil_div(rows, 8), 256, 0, st>>>(in, ld, rows, cols, amax_slot);
     split_scaled_kernel<<<(unsigned)cgr_ceil_div(rows, 8), 256, 0, st>>>(in, ld, rows, cols, amax_slot, unscale_slot, hi, lo,
                                                                          ldo);
   } else {
