@@ -491,7 +491,7 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
   // ---- readout (GNN.py:105-110) ----
   rc = simt_ffn_grads(grad_out, saved->pooled, grads->w_ffn, grads->b_ffn, B, (int)H, st);
   if (rc) return rc;
-  rc = simt_readout_dz(grad_out, g->atom_ptr, p->w_ffn, saved->hv, saved->zv, p->act, dzv, B, (int)H, st);
+  rc = simt_readout_dz(grad_out, g->atom_ptr, p->w_ffn, saved->hv, saved->zv, p->act, dzv, B, N, (int)H, st);
   if (rc) return rc;
   rc = simt_colsum(dzv, N, (int)H, grads->b_e2n, nullptr, nullptr, nullptr, nullptr, true, csws, st);
   if (rc) return rc;

@@ -333,21 +333,24 @@ __global__ void __launch_bounds__(128) pool_ffn_kernel(const float* __restrict__
   if (threadIdx.x == 0) out[b] = tot + __ldg(b_ffn);
 }
 
-__global__ void __launch_bounds__(128) readout_dz_kernel(const float* __restrict__ g, const int32_t* __restrict__ atom_ptr,
+// dzv[v] = g[b(v)] * w_f (.) act'(zv | hv): one warp per atom, the reaction of the atom found by bisection in atom_ptr
+__global__ void __launch_bounds__(256) readout_dz_kernel(const float* __restrict__ g, const int32_t* __restrict__ atom_ptr,
                                                          const float* __restrict__ w_ffn,
                                                          const float* __restrict__ hv, const float* __restrict__ zv,
-                                                         int act, float* __restrict__ dzv, int H) {
-  const int64_t b = blockIdx.x;
-  const int32_t v0 = __ldg(atom_ptr + b), v1 = __ldg(atom_ptr + b + 1);
-  const float gb = __ldg(g + b);
-  for (int n = threadIdx.x; n < H; n += blockDim.x) {
-    const float gw = gb * __ldg(w_ffn + n);
-    for (int32_t v = v0; v < v1; ++v) {
-      const int64_t idx = (int64_t)v * H + n;
-      const float d = act == CGR_ACT_RELU ? (__ldg(hv + idx) > 0.f ? 1.f : 0.f)
-                                          : cgr_act_grad(__ldg(zv + idx), 0.f, act);
-      dzv[idx] = gw * d;
-    }
+                                                         int act, float* __restrict__ dzv, int64_t B, int64_t N, int H) {
+  const int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (v >= N) return;
+  const int lane = threadIdx.x & 31;
+  int64_t lo = 0, hi = B;                         // atom_ptr[lo] <= v < atom_ptr[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(atom_ptr + mid) <= v) lo = mid; else hi = mid;
+  }
+  const float gb = __ldg(g + lo);
+  for (int n = lane; n < H; n += 32) {
+    const int64_t idx = v * H + n;
+    const float d = act == CGR_ACT_RELU ? (__ldg(hv + idx) > 0.f ? 1.f : 0.f) : cgr_act_grad(__ldg(zv + idx), 0.f, act);
+    dzv[idx] = gb * __ldg(w_ffn + n) * d;
   }
 }
 
@@ -534,11 +537,11 @@ int simt_pool_ffn(const float* hv, const int32_t* atom_ptr, const float* w_ffn, 
 }
 
 int simt_readout_dz(const float* g, const int32_t* atom_ptr, const float* w_ffn, const float* hv, const float* zv,
-                    int act, float* dzv, int64_t B, int H, cudaStream_t st) {
-  if (B <= 0) return CGR_OK;
+                    int act, float* dzv, int64_t B, int64_t N, int H, cudaStream_t st) {
+  if (B <= 0 || N <= 0) return CGR_OK;
   CgrRange prof("readout_dz", st);
   cgr_note_launch("readout_dz", st, 1);
-  readout_dz_kernel<<<(unsigned)B, 128, 0, st>>>(g, atom_ptr, w_ffn, hv, zv, act, dzv, H);
+  readout_dz_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(g, atom_ptr, w_ffn, hv, zv, act, dzv, B, N, H);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }

@@ -51,7 +51,7 @@ int simt_pool_ffn(const float* hv, const int32_t* atom_ptr, const float* w_ffn, 
 
 // dzv[v] = g[b(v)] * w_f (.) act'(zv | hv)
 int simt_readout_dz(const float* g, const int32_t* atom_ptr, const float* w_ffn, const float* hv,
-                    const float* zv, int act, float* dzv, int64_t B, int H, cudaStream_t st);
+                    const float* zv, int act, float* dzv, int64_t B, int64_t N, int H, cudaStream_t st);
 // dw_f[n] = sum_b g[b] pooled[b,n];  db_f = sum_b g[b]
 int simt_ffn_grads(const float* g, const float* pooled, float* dw_ffn, float* db_ffn, int64_t B, int H,
                    cudaStream_t st);

@@ -193,24 +193,57 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm2_kernel(const __grid_const
     float b4[4] = {0.f, 0.f, 0.f, 0.f};
     if (!partial && p.bias)
       for (int i = 0; i < 4; ++i) b4[i] = n + i < p.N ? __ldg(p.bias + n + i) : 0.f;
-    for (int r = warp; r < TM; r += NWARPS) {
-      const int64_t m = m0 + r;
-      if (m >= p.M) break;
-      const float4 y4 = *reinterpret_cast<const float4*>(y_s + r * YP + c);
-      float y[4] = {y4.x, y4.y, y4.z, y4.w};
+    // rows are handled four at a time: the residual loads of all four are in flight before the first is used
+    const bool vec = (n + 3 < p.N) && ((ldc & 3) == 0) && (((uintptr_t)Cb & 15) == 0) &&
+                     (!p.res || ((p.ldr & 3) == 0 && ((uintptr_t)p.res & 15) == 0)) &&
+                     (!p.preact || ((uintptr_t)p.preact & 15) == 0);
+    for (int r0 = warp * 4; r0 < TM; r0 += NWARPS * 4) {
+      float res4[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (n + i >= p.N) break;
-        float v = y[i];
-        if (!partial) {
-          v += b4[i];
-          if (p.res) v = fmaf(rs, __ldg(p.res + m * p.ldr + n + i), v);
-          if (p.preact) p.preact[m * ldc + n + i] = v;
-          v = cgr_act(v, p.act);
-          if (p.dropout_p > 0.f)
-            v = cgr_dropout_keep(p.seed, p.layer, (uint64_t)(m * p.N + n + i), p.dropout_p) ? v * keep_scale : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t m = m0 + r0 + u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res4[u][i] = 0.f;
+        if (!partial && p.res && m < p.M) {
+          if (vec) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.res + m * p.ldr + n));
+            res4[u][0] = t.x; res4[u][1] = t.y; res4[u][2] = t.z; res4[u][3] = t.w;
+          } else {
+            for (int i = 0; i < 4; ++i) if (n + i < p.N) res4[u][i] = __ldg(p.res + m * p.ldr + n + i);
+          }
         }
-        Cb[m * ldc + n + i] = v;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u;
+        const int64_t m = m0 + r;
+        if (m >= p.M) break;
+        const float4 y4 = *reinterpret_cast<const float4*>(y_s + r * YP + c);
+        float y[4] = {y4.x, y4.y, y4.z, y4.w};
+        float zpre[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = y[i];
+          if (!partial) {
+            v += b4[i];
+            if (p.res) v = fmaf(rs, res4[u][i], v);
+            zpre[i] = v;
+            v = cgr_act(v, p.act);
+            if (p.dropout_p > 0.f)
+              v = cgr_dropout_keep(p.seed, p.layer, (uint64_t)(m * p.N + n + i), p.dropout_p) ? v * keep_scale : 0.f;
+          }
+          y[i] = v;
+        }
+        if (vec) {
+          if (!partial && p.preact) *reinterpret_cast<float4*>(p.preact + m * ldc + n) = make_float4(zpre[0], zpre[1], zpre[2], zpre[3]);
+          *reinterpret_cast<float4*>(Cb + m * ldc + n) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+          for (int i = 0; i < 4; ++i) {
+            if (n + i >= p.N) break;
+            if (!partial && p.preact) p.preact[m * ldc + n + i] = zpre[i];
+            Cb[m * ldc + n + i] = y[i];
+          }
+        }
       }
     }
   }
