@@ -219,6 +219,7 @@ int bond_update_impl(GemmCtx& c, const float* h_in, const float* h0, const int32
   GatherPost np;
   int rc = simt_gather_bonds(h_in, src, in_ptr, in_idx, 0, m_out, E, H, np, st);   // GNN.py:134-141
   if (rc) return rc;
+  c.last_a = nullptr;                                      // m_out may be a buffer re-used every layer: re-split it
   GemmEpilogue e;
   e.bias = b;
   e.res = h0; e.ldr = H; e.res_scale = skip;               // GNN.py:94-97
@@ -236,6 +237,7 @@ int readout_impl(GemmCtx& c, const float* h, const float* x, const int32_t* in_p
                  int fa, int H, int depth, cudaStream_t st) {
   int rc = simt_atom_sum(h, in_ptr, in_idx, 0, s_out, N, H, st);                  // GNN.py:105
   if (rc) return rc;
+  c.last_a = nullptr;
   // W_o [x || s] = x W_ox^T + s W_os^T  (GNN.py:106-107 without the concat)
   GemmEpilogue e1;
   e1.tag = "gemm_readout_x";
@@ -367,7 +369,9 @@ extern "C" int cgr_readout_fwd(const float* h, const float* x, const int32_t* in
 extern "C" size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t training,
                                         int32_t engine) {
   if (!p || !g) return 0;
-  if (engine == CGR_ENGINE_TC && !training) return tc_forward_workspace(p, g, training);
+  // tcgen05 engine: fused tile kernels when a tile plan exists and nothing has to be saved; otherwise the layer-wise
+  // path with tensor-core GEMMs (training, or graphs whose reactions exceed a 128-bond tile)
+  if (engine == CGR_ENGINE_TC && !training && g->tile_info && g->n_tiles > 0) return tc_forward_workspace(p, g, training);
   const size_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
   size_t b = fbytes(N * H);
   if (!training) b += 4 * fbytes(E * H) + 2 * fbytes(N * H) + fbytes(B * H);
@@ -389,7 +393,7 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
                 cgr_forward_workspace(p, g, training, engine));
   CGR_CHECK_ARG(engine == CGR_ENGINE_SIMT || engine == CGR_ENGINE_TC, "unknown engine %d", engine);
   // inference on the tcgen05 engine: fused tile kernels.  Training on it: layer-wise path with tensor-core GEMMs.
-  if (engine == CGR_ENGINE_TC && !saved)
+  if (engine == CGR_ENGINE_TC && !saved && g->tile_info && g->n_tiles > 0)
     return tc_gnn_forward(p, g, out, saved, training, seed, workspace, workspace_bytes, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;

@@ -127,17 +127,15 @@ class GNN(nn.Module):
         e = getattr(self, "engine", "auto")
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
-        if needs_saved:
-            can_tc = self.depth <= 13
-        else:
-            can_tc = (self.hidden_sizes[0] % 4 == 0 and self.depth <= 13 and self.num_edge_features <= 32
-                      and plan.ensure_tiles())
-        if e in ("tc", 1):
-            if not can_tc:
-                raise RuntimeError("engine='tc' inference needs a hidden size divisible by 4 and reactions of at most "
-                                   "128 directed bonds (depth <= 13)")
-            return _lib.ENGINE_TC
+        can_tc = self.depth <= 13
+        if e in ("tc", 1) and not can_tc:
+            raise RuntimeError("engine='tc' supports depth <= 13")
         return _lib.ENGINE_TC if can_tc else _lib.ENGINE_SIMT
+
+    def _fused_ok(self, plan) -> bool:
+        """The fused tile kernels need a hidden size divisible by 4, <= 32 bond features and reactions that fit a
+        128-bond tile; other graphs (drug-like stress shape) run layer-wise with tensor-core GEMMs."""
+        return (self.hidden_sizes[0] % 4 == 0 and self.num_edge_features <= 32 and plan.ensure_tiles())
 
     def _tc_weights(self, params, fa: int, fb: int) -> torch.Tensor:
         from . import ops
@@ -193,7 +191,7 @@ class GNN(nn.Module):
         engine = self._engine_id(plan, train_flag)
         empty_i = torch.empty(0, dtype=torch.int32, device=dev)
         if engine == _lib.ENGINE_TC:
-            if train_flag:           # layer-wise path with tensor-core GEMMs: no tile plan needed
+            if train_flag or not self._fused_ok(plan):   # layer-wise path with tensor-core GEMMs: no tile plan needed
                 tile_info, n_tiles = empty_i, 0
                 if plan.tc_status is None:
                     plan.tc_status = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -216,7 +214,7 @@ class GNN(nn.Module):
                               self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
                               train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo,
                               getattr(self, "tile_policy", "latency") == "throughput")
-        self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and not train_flag) else None
+        self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and n_tiles > 0) else None
         self.__dict__["_last_engine"] = engine
         out = res[0]
         if caller_device != dev:
