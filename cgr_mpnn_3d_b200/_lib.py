@@ -52,6 +52,13 @@ class CgrGraph(C.Structure):
     ]
 
 
+class CgrHostBatch(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("edge_attr", C.c_void_p), ("edge_index", C.c_void_p), ("ptr", C.c_void_p),
+        ("batch", C.c_void_p), ("n_atoms", C.c_int64), ("n_bonds", C.c_int64), ("n_rxn", C.c_int64),
+    ]
+
+
 class CgrSaved(C.Structure):
     _fields_ = [
         ("h_all", C.c_void_p), ("m_all", C.c_void_p), ("z_all", C.c_void_p), ("s", C.c_void_p),
@@ -75,6 +82,7 @@ PROTOTYPES = {
     "cgr_infer_host_workspace": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "cgr_gnn_infer_host": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_async": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
+    "cgr_gnn_infer_host_multi_async": (C.c_int, [C.POINTER(CgrParams), _V, C.c_int32, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_infer_host_check": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, _V]),
     "cgr_atom_ptr_from_batch": (C.c_int, [_V, _I64, _I64, _V, _V]),
     "cgr_edge_init_fwd": (C.c_int, [_V, _V, _V, _V, _V, _I64, _I64, _I32, _I32, _I32, _I32, _V, _V, _V, _SZ, _V]),

@@ -623,9 +623,9 @@ extern "C" int cgr_dropout_mask(uint64_t seed, uint32_t layer, float dropout_p, 
 // ------------------------------------------------------------------------------------------------
 // End-to-end inference on host buffers
 // ------------------------------------------------------------------------------------------------
-extern "C" int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
-                                         int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src, int32_t* dst,
-                                         int32_t* in_ptr, int32_t* in_idx, int32_t* status, void* stream);
+int csr_by_reaction_shifted(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
+                            const int32_t* rxn_shift, int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src,
+                            int32_t* dst, int32_t* in_ptr, int32_t* in_idx, int32_t* status, cudaStream_t st);
 namespace {
 struct HostInferLayout {
   int64_t t_max, kp_x;
@@ -637,7 +637,7 @@ HostInferLayout host_infer_layout(const cgr_params_t* p, int64_t N, int64_t E, i
   L.t_max = 2 * E / 128 + 1 < B ? 2 * E / 128 + 1 : B;       // greedy packing: two consecutive tiles hold > 128 bonds
   if (L.t_max < 1) L.t_max = 1;
   L.kp_x = ((int64_t)p->fa + 63) / 64 * 64;
-  L.meta_ints = (size_t)L.t_max * 8 + 2 * (size_t)(B + 1);
+  L.meta_ints = (size_t)L.t_max * 8 + 2 * (size_t)(B + 1) + (size_t)B;   // tiles, atom_ptr, edge_ptr, atom-id shift
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += cgr_align_up(bytes, 1024); return o; };
   L.o_x = take((size_t)N * p->fa * 4);
@@ -675,18 +675,25 @@ extern "C" int cgr_infer_host_workspace(const cgr_params_t* p, int64_t n_atoms, 
   return CGR_OK;
 }
 
-extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
-                                        const int64_t* host_edge_index, const int64_t* host_ptr,
-                                        const int64_t* host_batch, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
-                                        float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
-                                        size_t host_bytes, void* stream) {
+extern "C" int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_host_batch_t* batches, int32_t n_batches,
+                                              float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
+                                              size_t host_bytes, void* stream) {
   int rc = check_params(p);
   if (rc) return rc;
-  CGR_CHECK_ARG(host_x && host_edge_index && host_out && dev_ws && host_ws, "cgr_gnn_infer_host: null pointer");
-  CGR_CHECK_ARG(p->fb == 0 || host_edge_attr, "cgr_gnn_infer_host: edge_attr missing");
+  CGR_CHECK_ARG(batches && n_batches > 0 && host_out && dev_ws && host_ws, "cgr_gnn_infer_host: null pointer");
   CGR_CHECK_ARG(p->tc_weights, "cgr_gnn_infer_host: prepare the weights first (cgr_tc_prepare_weights)");
-  CGR_CHECK_ARG(n_atoms > 0 && n_bonds > 0 && n_rxn > 0 && (n_bonds & 1) == 0, "cgr_gnn_infer_host: bad sizes");
-  const int64_t N = n_atoms, E = n_bonds, B = n_rxn;
+  int64_t N = 0, E = 0, B = 0;
+  for (int j = 0; j < n_batches; ++j) {
+    const cgr_host_batch_t& hb = batches[j];
+    CGR_CHECK_ARG(hb.x && hb.edge_index, "cgr_gnn_infer_host: null pointer in batch %d", j);
+    CGR_CHECK_ARG(p->fb == 0 || hb.edge_attr, "cgr_gnn_infer_host: edge_attr missing");
+    CGR_CHECK_ARG(hb.n_atoms > 0 && hb.n_bonds > 0 && hb.n_rxn > 0 && (hb.n_bonds & 1) == 0,
+                  "cgr_gnn_infer_host: bad sizes");
+    CGR_CHECK_ARG(hb.ptr || hb.batch || hb.n_rxn == 1,
+                  "cgr_gnn_infer_host: neither ptr nor batch given for a multi-graph batch");
+    N += hb.n_atoms; E += hb.n_bonds; B += hb.n_rxn;
+  }
+  CGR_CHECK_ARG(N < (1ll << 31) && E < (1ll << 31), "cgr_gnn_infer_host: sizes exceed the int32 index range");
   const HostInferLayout L = host_infer_layout(p, N, E, B);
   CGR_CHECK_ARG(dev_bytes >= L.dev_total && host_bytes >= L.host_total, "cgr_gnn_infer_host: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -695,32 +702,41 @@ extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host
   int32_t* h_tiles = h_meta;
   int32_t* h_aptr = h_meta + (size_t)L.t_max * 8;
   int32_t* h_eptr = h_aptr + (B + 1);
+  int32_t* h_shift = h_eptr + (B + 1);
   int32_t* h_flags = (int32_t*)((char*)host_ws + cgr_align_up(L.meta_ints * 4, 256));
 
-  // ---- host side: per-reaction offsets and the greedy tile plan (same rule as cgr_tc_plan_build) ----
-  if (host_ptr) {
-    for (int64_t g = 0; g <= B; ++g) h_aptr[g] = (int32_t)host_ptr[g];
-  } else if (host_batch) {
-    int64_t v = 0;
-    for (int64_t g = 0; g < B; ++g) {
-      h_aptr[g] = (int32_t)v;
-      while (v < N && host_batch[v] <= g) ++v;
-    }
-    h_aptr[B] = (int32_t)N;
-  } else {
-    CGR_CHECK_ARG(B == 1, "cgr_gnn_infer_host: neither ptr nor batch given for a multi-graph batch");
-    h_aptr[0] = 0; h_aptr[1] = (int32_t)N;
-  }
+  // ---- host side: per-reaction offsets of the super-batch (host batches laid end to end) ----
   {
-    int64_t e = 0;
-    h_eptr[0] = 0;
-    for (int64_t g = 0; g < B; ++g) {          // bonds of a collated batch are grouped by reaction
-      const int64_t a1 = h_aptr[g + 1];
-      while (e < E && host_edge_index[e] < a1) ++e;
-      h_eptr[g + 1] = (int32_t)e;
+    int64_t a_off = 0, e_off = 0, r_off = 0;
+    for (int j = 0; j < n_batches; ++j) {
+      const cgr_host_batch_t& hb = batches[j];
+      int32_t* ap = h_aptr + r_off;
+      if (hb.ptr) {
+        for (int64_t g = 0; g < hb.n_rxn; ++g) ap[g] = (int32_t)(a_off + hb.ptr[g]);
+      } else if (hb.batch) {
+        int64_t v = 0;
+        for (int64_t g = 0; g < hb.n_rxn; ++g) {
+          ap[g] = (int32_t)(a_off + v);
+          while (v < hb.n_atoms && hb.batch[v] <= g) ++v;
+        }
+      } else {
+        ap[0] = (int32_t)a_off;
+      }
+      ap[hb.n_rxn] = (int32_t)(a_off + hb.n_atoms);
+      int64_t e = 0;
+      int32_t* ep = h_eptr + r_off;
+      ep[0] = (int32_t)e_off;
+      for (int64_t g = 0; g < hb.n_rxn; ++g) {          // bonds of a collated batch are grouped by reaction
+        const int64_t a1 = ap[g + 1] - a_off;
+        while (e < hb.n_bonds && hb.edge_index[e] < a1) ++e;
+        ep[g + 1] = (int32_t)(e_off + e);
+        h_shift[r_off + g] = (int32_t)a_off;
+      }
+      if (e != hb.n_bonds) { cgr_set_error("edge_index is not grouped by reaction"); return CGR_ERR_ARG; }
+      a_off += hb.n_atoms; e_off += hb.n_bonds; r_off += hb.n_rxn;
     }
-    if (e != E) { cgr_set_error("edge_index is not grouped by reaction"); return CGR_ERR_ARG; }
   }
+  // ---- greedy tile plan (same rule as cgr_tc_plan_build) ----
   int64_t T = -1;
   {
     int used_e = 129, used_a = 129;
@@ -752,9 +768,25 @@ extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host
   int32_t* d_status = (int32_t*)(dws + L.o_status);
   float* d_out = (float*)(dws + L.o_out);
   CGR_CUDA(cudaMemcpyAsync(d_meta, h_meta, L.meta_ints * 4, cudaMemcpyHostToDevice, st));
-  CGR_CUDA(cudaMemcpyAsync(d_ei, host_edge_index, (size_t)2 * E * 8, cudaMemcpyHostToDevice, st));
-  CGR_CUDA(cudaMemcpyAsync(d_x, host_x, (size_t)N * p->fa * 4, cudaMemcpyHostToDevice, st));
-  if (p->fb > 0) CGR_CUDA(cudaMemcpyAsync(d_ea, host_edge_attr, (size_t)E * p->fb * 4, cudaMemcpyHostToDevice, st));
+  {
+    int64_t a_off = 0, e_off = 0;
+    for (int j = 0; j < n_batches; ++j) {
+      const cgr_host_batch_t& hb = batches[j];
+      if (n_batches == 1) {
+        CGR_CUDA(cudaMemcpyAsync(d_ei, hb.edge_index, (size_t)2 * E * 8, cudaMemcpyHostToDevice, st));
+      } else {                                     // rows of [2, E_j] go to their slices of the [2, E] super-batch
+        CGR_CUDA(cudaMemcpyAsync(d_ei + e_off, hb.edge_index, (size_t)hb.n_bonds * 8, cudaMemcpyHostToDevice, st));
+        CGR_CUDA(cudaMemcpyAsync(d_ei + E + e_off, hb.edge_index + hb.n_bonds, (size_t)hb.n_bonds * 8,
+                                 cudaMemcpyHostToDevice, st));
+      }
+      CGR_CUDA(cudaMemcpyAsync(d_x + (size_t)a_off * p->fa, hb.x, (size_t)hb.n_atoms * p->fa * 4,
+                               cudaMemcpyHostToDevice, st));
+      if (p->fb > 0)
+        CGR_CUDA(cudaMemcpyAsync(d_ea + (size_t)e_off * p->fb, hb.edge_attr, (size_t)hb.n_bonds * p->fb * 4,
+                                 cudaMemcpyHostToDevice, st));
+      a_off += hb.n_atoms; e_off += hb.n_bonds;
+    }
+  }
   CGR_CUDA(cudaMemsetAsync(d_status, 0, (size_t)(2 + L.t_max) * 4, st));
   cgr_graph_t g;
   memset(&g, 0, sizeof(g));
@@ -766,8 +798,9 @@ extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host
   g.atom_ptr = d_meta + (size_t)L.t_max * 8;
   g.tc_status = d_status + 1;
   g.x_hi = dws + L.o_xhi; g.x_lo = dws + L.o_xlo;
-  rc = cgr_csr_build_by_reaction(d_ei, g.atom_ptr + (B + 1), g.atom_ptr, B, E, N, (int32_t*)g.src, (int32_t*)g.dst,
-                                 (int32_t*)g.in_ptr, (int32_t*)g.in_idx, d_status, stream);
+  rc = csr_by_reaction_shifted(d_ei, g.atom_ptr + (B + 1), g.atom_ptr, n_batches > 1 ? g.atom_ptr + 2 * (B + 1) : nullptr,
+                               B, E, N, (int32_t*)g.src, (int32_t*)g.dst, (int32_t*)g.in_ptr, (int32_t*)g.in_idx,
+                               d_status, st);
   if (rc) return rc;
   rc = tc_split_features(d_x, N, p->fa, (void*)g.x_hi, (void*)g.x_lo, g.tc_status, st);
   if (rc) return rc;
@@ -776,6 +809,17 @@ extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host
   CGR_CUDA(cudaMemcpyAsync(host_out, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   CGR_CUDA(cudaMemcpyAsync(h_flags, d_status, 2 * 4, cudaMemcpyDeviceToHost, st));
   return CGR_OK;
+}
+
+extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host_x, const float* host_edge_attr,
+                                        const int64_t* host_edge_index, const int64_t* host_ptr,
+                                        const int64_t* host_batch, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
+                                        float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
+                                        size_t host_bytes, void* stream) {
+  cgr_host_batch_t hb;
+  hb.x = host_x; hb.edge_attr = host_edge_attr; hb.edge_index = host_edge_index; hb.ptr = host_ptr; hb.batch = host_batch;
+  hb.n_atoms = n_atoms; hb.n_bonds = n_bonds; hb.n_rxn = n_rxn;
+  return cgr_gnn_infer_host_multi_async(p, &hb, 1, host_out, dev_ws, dev_bytes, host_ws, host_bytes, stream);
 }
 
 extern "C" int cgr_infer_host_check(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,

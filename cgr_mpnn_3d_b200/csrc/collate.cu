@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(128) csr_by_reaction_kernel(const int64_t* __r
                                                               const int32_t* __restrict__ atom_ptr, int64_t ne, int64_t na,
                                                               int64_t nb, int32_t* __restrict__ src, int32_t* __restrict__ dst,
                                                               int32_t* __restrict__ in_ptr, int32_t* __restrict__ in_idx,
-                                                              int32_t* __restrict__ status) {
+                                                              int32_t* __restrict__ status,
+                                                              const int32_t* __restrict__ rxn_shift) {
   __shared__ int deg[RX_MAX], off[RX_MAX + 1], cur[RX_MAX];
   __shared__ int32_t loc[RX_MAX];
   const int g = blockIdx.x;
@@ -208,11 +209,12 @@ __global__ void __launch_bounds__(128) csr_by_reaction_kernel(const int64_t* __r
   for (int v = threadIdx.x; v < n_a; v += blockDim.x) { deg[v] = 0; cur[v] = 0; }
   __syncthreads();
   int flag = 0;
+  const int64_t sh = rxn_shift ? rxn_shift[g] : 0;     // atom-id shift of the host batch this reaction came from
   for (int j = threadIdx.x; j < n_e; j += blockDim.x) {
-    const int64_t e = e0 + j, s = ei[e], d = ei[ne + e];
+    const int64_t e = e0 + j, s = ei[e] + sh, d = ei[ne + e] + sh;
     if (s < a0 || s >= a1 || d < a0 || d >= a1) flag |= 2;
     const int64_t r = e ^ 1;
-    if (r >= ne || ei[r] != d || ei[ne + r] != s) flag |= 1;
+    if (r >= ne || ei[r] + sh != d || ei[ne + r] + sh != s) flag |= 1;
     src[e] = (int32_t)s;
     dst[e] = (int32_t)d;
     if (!(flag & 2)) atomicAdd(&deg[d - a0], 1);
@@ -249,17 +251,23 @@ __global__ void __launch_bounds__(128) csr_by_reaction_kernel(const int64_t* __r
 
 }  // namespace
 
+int csr_by_reaction_shifted(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
+                            const int32_t* rxn_shift, int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src,
+                            int32_t* dst, int32_t* in_ptr, int32_t* in_idx, int32_t* status, cudaStream_t st) {
+  CGR_CHECK_ARG(edge_index && edge_ptr && atom_ptr && src && dst && in_ptr && in_idx && status && n_rxn > 0,
+                "cgr_csr_build_by_reaction: bad argument");
+  cgr_note_launch("csr_by_reaction", st, 1);
+  csr_by_reaction_kernel<<<(unsigned)n_rxn, 128, 0, st>>>(edge_index, edge_ptr, atom_ptr, n_bonds, n_atoms, n_rxn, src,
+                                                          dst, in_ptr, in_idx, status, rxn_shift);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
 extern "C" int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
                                          int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src, int32_t* dst,
                                          int32_t* in_ptr, int32_t* in_idx, int32_t* status, void* stream) {
-  CGR_CHECK_ARG(edge_index && edge_ptr && atom_ptr && src && dst && in_ptr && in_idx && status && n_rxn > 0,
-                "cgr_csr_build_by_reaction: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  cgr_note_launch("csr_by_reaction", st, 1);
-  csr_by_reaction_kernel<<<(unsigned)n_rxn, 128, 0, st>>>(edge_index, edge_ptr, atom_ptr, n_bonds, n_atoms, n_rxn, src,
-                                                          dst, in_ptr, in_idx, status);
-  CGR_LAUNCH_CHECK();
-  return CGR_OK;
+  return csr_by_reaction_shifted(edge_index, edge_ptr, atom_ptr, nullptr, n_rxn, n_bonds, n_atoms, src, dst, in_ptr,
+                                 in_idx, status, (cudaStream_t)stream);
 }
 
 extern "C" size_t cgr_collate_workspace(int64_t n_rxn) {

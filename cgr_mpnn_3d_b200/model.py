@@ -315,70 +315,96 @@ class GNN(nn.Module):
         _lib.check(rc, "cgr_gnn_infer_host")
         return hout[:b].clone()
 
-    def predict_stream(self, batches, depth: int = 4, workers: int = 2):
+    def predict_stream(self, batches, depth: int = 4, workers: int = 2, coalesce: int = 8,
+                       coalesce_reactions: int = 1024):
         """Pipelined inference over an iterable of HOST batches (the screening workload): yields one CPU
-        tensor of energies per batch, in order.  Up to ``depth`` batches are in flight, each on its own
-        stream with its own staging buffers, so the H2D copy of batch i+1 overlaps the kernels of batch i
-        (``cgr_gnn_infer_host_async``); ``workers`` host threads issue the calls (the C entry releases the
-        GIL).  Batches that cannot use the tcgen05 engine go through ``forward``."""
+        tensor of energies per batch, in order.  Up to ``coalesce`` consecutive batches (closed early once they
+        hold ``coalesce_reactions`` reactions, which bounds the workspace) travel in ONE submission (``cgr_gnn_infer_host_multi_async``: each is staged straight from its own host buffers
+        into a device-side super-batch, so copies and launches are amortised; per-reaction results equal
+        separate submissions up to fp32 rounding of the final column sum).  Up to ``depth`` submissions are in flight, each on its own
+        stream with its own staging buffers, so the H2D copies of one overlap the kernels of another;
+        ``workers`` host threads issue the calls (the C entry releases the GIL).  Batches that cannot use
+        the tcgen05 engine go through ``forward``."""
         import ctypes as C
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
         lib = _lib.load()
-        depth = max(1, depth)
+        depth, coalesce = max(1, depth), max(1, coalesce)
         pending = deque()
         pool = ThreadPoolExecutor(max_workers=max(1, workers))
 
-        def submit(slot_id, data):
-            f = self._host_fields(data)
-            if f is None:
+        def submit(slot_id, group):
+            fields = [self._host_fields(d) for d in group]
+            if any(f is None for f in fields):
                 return None
-            x, ei, ea, batch, ptr, n, e, b = f
-            ctx, dev = self._host_ctx(int(x.shape[1]), int(ea.shape[1]))
+            k = len(fields)
+            arr = (_lib.CgrHostBatch * k)()
+            n = e = b = 0
+            for hb, (x, ei, ea, batch, ptr, nj, ej, bj) in zip(arr, fields):
+                hb.x, hb.edge_attr, hb.edge_index = x.data_ptr(), ea.data_ptr(), ei.data_ptr()
+                hb.ptr, hb.batch = _lib.ptr(ptr), _lib.ptr(batch)
+                hb.n_atoms, hb.n_bonds, hb.n_rxn = nj, ej, bj
+                n += nj; e += ej; b += bj
+            x0, ea0 = fields[0][0], fields[0][2]
+            ctx, dev = self._host_ctx(int(x0.shape[1]), int(ea0.shape[1]))
             with torch.cuda.device(dev):
                 slot = self._host_slot(slot_id, ctx, dev, n, e, b)
                 dws, hws, hout, st = slot
-                ctx.params.tc_throughput = 1          # several batches in flight
-                rc = lib.cgr_gnn_infer_host_async(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
-                                                  _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(),
-                                                  dws.data_ptr(), dws.numel(), hws.data_ptr(), hws.numel(),
-                                                  st.cuda_stream)
+                ctx.params.tc_throughput = 1          # several submissions in flight
+                rc = lib.cgr_gnn_infer_host_multi_async(C.byref(ctx.params), arr, k, hout.data_ptr(), dws.data_ptr(),
+                                                        dws.numel(), hws.data_ptr(), hws.numel(), st.cuda_stream)
             if rc == -3:
                 return None
-            _lib.check(rc, "cgr_gnn_infer_host_async")
-            return slot, ctx, n, e, b, (x, ei, ea, batch, ptr)
+            _lib.check(rc, "cgr_gnn_infer_host_multi_async")
+            return slot, ctx, n, e, b, [f[7] for f in fields], (arr, fields)
 
         def finish():
-            fut, data = pending.popleft()
+            fut, group = pending.popleft()
             res = fut.result()
             if res is None:                         # not tileable: generic path
-                return self.forward(data)
-            slot, ctx, n, e, b, _keep = res
+                return [self.forward(d) for d in group]
+            slot, ctx, n, e, b, counts, _keep = res
             dws, hws, hout, st = slot
             st.synchronize()
             _lib.check(lib.cgr_infer_host_check(C.byref(ctx.params), n, e, b, hws.data_ptr()), "cgr_infer_host_check")
-            return hout[:b].clone()
+            return list(hout[:b].clone().split(counts))
 
         try:
             with torch.no_grad():
                 if self._host_supported():
                     first = True
                     i = 0
+                    group, group_rxn = [], 0
+
+                    def flush():
+                        nonlocal i, group, group_rxn
+                        if group:
+                            pending.append((pool.submit(submit, 1 + i % depth, group), group))
+                            i += 1
+                            group, group_rxn = [], 0
+
                     for data in batches:
-                        if data.x.device.type != "cpu":
+                        if data.x.device.type != "cpu" or data.edge_attr is None:
+                            flush()
                             while pending:
-                                yield finish()
+                                yield from finish()
                             yield self.forward(data)
                             continue
                         if first:                    # build the cached parameter block outside the workers
                             self._host_ctx(int(data.x.shape[1]), int(data.edge_attr.shape[1]))
                             first = False
-                        if len(pending) >= depth:
-                            yield finish()
-                        pending.append((pool.submit(submit, 1 + i % depth, data), data))
-                        i += 1
+                        group.append(data)
+                        ptr = getattr(data, "ptr", None)
+                        group_rxn += int(ptr.numel()) - 1 if ptr is not None else 64
+                        if len(group) >= coalesce or group_rxn >= coalesce_reactions:
+                            if len(pending) >= depth:
+                                yield from finish()
+                            flush()
+                    if len(pending) >= depth:
+                        yield from finish()
+                    flush()
                     while pending:
-                        yield finish()
+                        yield from finish()
                 else:
                     for data in batches:
                         yield self.forward(data)

@@ -249,6 +249,24 @@ int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host_x, const f
 int cgr_infer_host_check(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
                          const void* host_ws);
 
+/* Several collated host batches in ONE submission (dynamic batching of a screening stream, CLI :71-76 looped over
+ * a DataLoader): every batch is staged straight from its own host buffers into one device-side super-batch (atom
+ * ids shifted on the device), so launches and copies are amortised over all of them.  Energies land in `host_out`
+ * in batch order ([sum of n_rxn]); per-reaction results equal separate submissions up to fp32 rounding of the final
+ * column sum (its order follows the N-slice width chosen for the super-batch).  Workspaces are
+ * sized by cgr_infer_host_workspace on the TOTAL atom / bond / reaction counts, which cgr_infer_host_check takes too. */
+typedef struct {
+  const float* x;              /* [n_atoms, fa] */
+  const float* edge_attr;      /* [n_bonds, fb] */
+  const int64_t* edge_index;   /* [2, n_bonds] batch-local atom ids */
+  const int64_t* ptr;          /* [n_rxn + 1] or NULL */
+  const int64_t* batch;        /* [n_atoms] or NULL */
+  int64_t n_atoms, n_bonds, n_rxn;
+} cgr_host_batch_t;
+int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_host_batch_t* batches, int32_t n_batches,
+                                   float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
+                                   size_t host_bytes, void* stream);
+
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,
                         float* grad_pred, void* stream);

@@ -427,13 +427,51 @@ def test_host_buffer_inference_entry(name):
     assert torch.equal(out, out_nb)
     # pipelined API over several host batches: same numbers, in order
     many = [data, nb, data]
-    outs = list(model.predict_stream(many, depth=2))
-    assert all(torch.equal(o, out) for o in model.predict_stream(many * 3, depth=4, workers=3))
+    outs = list(model.predict_stream(many, depth=2, coalesce=1))
+    assert all(torch.equal(o, out) for o in model.predict_stream(many * 3, depth=4, workers=3, coalesce=1))
+    assert all(scale_normalised_error(o, out) < 1e-5 for o in model.predict_stream(many * 3, depth=2, coalesce=4))
     assert len(outs) == 3 and all(torch.equal(o, out) for o in outs)
     bad = Batch(data.x, data.edge_index.clone(), data.edge_attr, data.batch, data.ptr, None)
     bad.edge_index[:, [0, 2]] = bad.edge_index[:, [2, 0]]
     with torch.no_grad(), pytest.raises(RuntimeError, match="reverse pairs|atom range|grouped"):
         model(bad)
+
+
+def test_predict_stream_coalesces_batches():
+    """Consecutive host batches of different sizes travel as one device-side super-batch (atom ids shifted on the
+    device); every batch gets its own energies back, in order.  They equal a separate submission up to fp32 rounding
+    of the final column sum (its order follows the N-slice width chosen for the super-batch), bit for bit when the
+    submission is the same."""
+    meta = dict(fa=78, fb=14, depth=3, hidden=300, skip=True, wseed=5, act="relu")
+    model = build_model(meta, engine="auto").eval()
+    sizes = [64, 1, 17, 64, 5, 33, 64, 2, 9, 64, 40]
+    batches = [make_batch(b, seed=100 + i, kind="t1x", fa=78) for i, b in enumerate(sizes)]
+    batches[2] = Batch(batches[2].x, batches[2].edge_index, batches[2].edge_attr, batches[2].batch, None, None)  # no ptr
+    with torch.no_grad():
+        singles = [model(b) for b in batches]
+        oracle = build_oracle(meta).eval()
+        assert scale_normalised_error(singles[0], oracle(batches[0])) < EA_TOL
+    for coalesce, depth in ((1, 2), (3, 2), (8, 4), (64, 1)):
+        outs = list(model.predict_stream(iter(batches), depth=depth, coalesce=coalesce))
+        assert len(outs) == len(batches)
+        for o, ref, b in zip(outs, singles, sizes):
+            assert o.shape == (b,), (coalesce, b)
+            if coalesce == 1:
+                assert torch.equal(o, ref)
+            else:
+                assert scale_normalised_error(o, ref) < 1e-5, (coalesce, b)
+        again = list(model.predict_stream(iter(batches), depth=depth, coalesce=coalesce))
+        assert all(torch.equal(a, o) for a, o in zip(again, outs))           # deterministic
+    # a malformed batch inside a group is reported, not silently mixed into its neighbours
+    bad = Batch(batches[1].x, batches[1].edge_index.clone(), batches[1].edge_attr, batches[1].batch, batches[1].ptr, None)
+    bad.edge_index[:, [0, 2]] = bad.edge_index[:, [2, 0]]
+    with pytest.raises(RuntimeError, match="reverse pairs|atom range|grouped"):
+        list(model.predict_stream([batches[0], bad, batches[3]], coalesce=3))
+    # an untileable batch in a group sends that group down the generic path
+    drug = make_batch(2, seed=1, kind="drug", fa=78)
+    outs = list(model.predict_stream([batches[0], drug, batches[3]], coalesce=3))
+    assert scale_normalised_error(outs[0], singles[0]) < EA_TOL
+    assert outs[1].shape == (2,) and scale_normalised_error(outs[2], singles[3]) < EA_TOL
 
 
 # ---------------------------------------------------------------------------------------------
