@@ -476,6 +476,27 @@ def main():
         t1e.record()
         barrier()
         train = {"ms_total": t0e.elapsed_time(t1e), "steps": n_t}
+        # optimizer step, reported separately (SURVEY.md section 8 d-ii / f-1): one fused launch vs torch's foreach Adam
+        from cgr_mpnn_3d_b200.optim import FusedAdam
+        for p_ in tm.parameters():
+            if p_.grad is None:
+                p_.grad = torch.zeros_like(p_)
+
+        def time_opt(opt, n=200):
+            for _ in range(5):
+                opt.step()
+            torch.cuda.synchronize()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record()
+            for _ in range(n):
+                opt.step()
+            o1.record()
+            torch.cuda.synchronize()
+            return o0.elapsed_time(o1) / n
+        l_before = lib.cgr_launch_count()
+        train["adam_fused_ms"] = time_opt(FusedAdam(tm.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True))
+        train["adam_fused_launches"] = (lib.cgr_launch_count() - l_before) / 205
+        train["adam_torch_ms"] = time_opt(torch.optim.Adam(tm.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True))
 
     # ---- reduce over ranks (max time), assemble the line ----
     t = torch.tensor([ms_total, e2e["seconds"] if e2e else 0.0, train["ms_total"] if train else 0.0,
@@ -535,6 +556,11 @@ def main():
         if train:
             line["train_step"] = {"value": args.batch * train["steps"] * world / (train_ms * 1e-3), "unit": "reactions/s",
                                   "ms_per_step": train_ms / train["steps"], "steps": train["steps"],
+                                  "optimizer": {"fused_adam_ms": train["adam_fused_ms"],
+                                                "fused_adam_launches_per_step": train["adam_fused_launches"],
+                                                "torch_adam_ms": train["adam_torch_ms"],
+                                                "what": "Adam(weight_decay, amsgrad=True) step over all parameters, eager "
+                                                        "launches, timed apart from the step above (train.py:117-119)"},
                                   "what": "forward + MSE(sum) + explicit backward + flat gradient SUM all-reduce "
                                           "(optimizer excluded), batch %d/GPU, whole step replayed as a CUDA graph" % args.batch}
         if e2e:

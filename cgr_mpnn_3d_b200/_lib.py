@@ -59,6 +59,13 @@ class CgrHostBatch(C.Structure):
     ]
 
 
+class CgrAdamTensor(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("max_exp_avg_sq", C.c_void_p), ("numel", C.c_int64),
+    ]
+
+
 class CgrSaved(C.Structure):
     _fields_ = [
         ("h_all", C.c_void_p), ("m_all", C.c_void_p), ("z_all", C.c_void_p), ("s", C.c_void_p),
@@ -83,6 +90,8 @@ PROTOTYPES = {
     "cgr_gnn_infer_host": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_async": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_multi_async": (C.c_int, [C.POINTER(CgrParams), _V, C.c_int32, _V, _V, _SZ, _V, _SZ, _V]),
+    "cgr_adam_step": (C.c_int, [_V, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64,
+                                C.c_int32, C.c_float, _V]),
     "cgr_infer_host_check": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, _V]),
     "cgr_atom_ptr_from_batch": (C.c_int, [_V, _I64, _I64, _V, _V]),
     "cgr_edge_init_fwd": (C.c_int, [_V, _V, _V, _V, _V, _I64, _I64, _I32, _I32, _I32, _I32, _V, _V, _V, _SZ, _V]),

@@ -1,0 +1,140 @@
+// Fused optimizer step: Adam with L2-in-gradient weight decay and amsgrad, as the reference
+// configures it (train.py:117-121 -- torch.optim.Adam(lr, weight_decay, amsgrad=True)), over every parameter tensor
+// in ONE launch.  HBM-bound: per element it reads param, grad, m, v, vmax and writes param, m, v, vmax (36 bytes).
+#include <math.h>
+#include <string.h>
+
+#include "../../include/cgr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int ADAM_MAX_TENSORS = 48;
+constexpr int ADAM_CHUNK = 4096;          // elements per block
+constexpr int ADAM_THREADS = 256;
+
+struct AdamTable {
+  float* param[ADAM_MAX_TENSORS];
+  const float* grad[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  float* vmax[ADAM_MAX_TENSORS];
+  long long numel[ADAM_MAX_TENSORS];
+  int first_block[ADAM_MAX_TENSORS + 1];  // blocks [first_block[t], first_block[t+1]) work on tensor t
+  int n;
+};
+
+struct AdamScalars {
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, neg_step_size, bc2_sqrt, grad_scale;
+  int amsgrad;
+};
+
+// One element, the operation order of torch.optim.Adam's single-tensor path (torch/optim/adam.py, _single_tensor_adam):
+//   g += wd * p;  m.lerp_(g, 1-b1);  v = v*b2 + (1-b2)*g*g;  vmax = max(vmax, v);
+//   denom = sqrt(vmax) / sqrt(bias_correction2) + eps;  p += (-lr / bias_correction1) * (m / denom)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float& vm, const AdamScalars& s) {
+  g *= s.grad_scale;
+  if (s.weight_decay != 0.f) g = fmaf(s.weight_decay, p, g);
+  m = fmaf(s.one_minus_beta1, g - m, m);
+  v = fmaf(s.one_minus_beta2 * g, g, v * s.beta2);
+  float d;
+  if (s.amsgrad) {
+    vm = fmaxf(vm, v);
+    d = sqrtf(vm) / s.bc2_sqrt + s.eps;
+  } else {
+    d = sqrtf(v) / s.bc2_sqrt + s.eps;
+  }
+  p = fmaf(s.neg_step_size, m / d, p);
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constant__ AdamTable tab,
+                                                            const __grid_constant__ AdamScalars s) {
+  int lo = 0, hi = tab.n;                      // tensor of this block: last t with first_block[t] <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tab.first_block[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const int t = lo;
+  const long long base = (long long)((int)blockIdx.x - tab.first_block[t]) * ADAM_CHUNK;
+  const long long n = tab.numel[t];
+  float* __restrict__ P = tab.param[t];
+  const float* __restrict__ G = tab.grad[t];
+  float* __restrict__ M = tab.m[t];
+  float* __restrict__ V = tab.v[t];
+  float* __restrict__ VM = tab.vmax[t];
+  const bool vec = (((uintptr_t)P | (uintptr_t)G | (uintptr_t)M | (uintptr_t)V | (uintptr_t)(s.amsgrad ? VM : P)) & 15) == 0;
+  if (vec && base + ADAM_CHUNK <= n) {
+#pragma unroll
+    for (int it = 0; it < ADAM_CHUNK / (ADAM_THREADS * 4); ++it) {
+      const long long i = base + (long long)(it * ADAM_THREADS + threadIdx.x) * 4;
+      float4 p = *reinterpret_cast<float4*>(P + i);
+      const float4 g = *reinterpret_cast<const float4*>(G + i);
+      float4 m = *reinterpret_cast<float4*>(M + i);
+      float4 v = *reinterpret_cast<float4*>(V + i);
+      float4 vm = s.amsgrad ? *reinterpret_cast<float4*>(VM + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      adam_one(p.x, g.x, m.x, v.x, vm.x, s);
+      adam_one(p.y, g.y, m.y, v.y, vm.y, s);
+      adam_one(p.z, g.z, m.z, v.z, vm.z, s);
+      adam_one(p.w, g.w, m.w, v.w, vm.w, s);
+      *reinterpret_cast<float4*>(P + i) = p;
+      *reinterpret_cast<float4*>(M + i) = m;
+      *reinterpret_cast<float4*>(V + i) = v;
+      if (s.amsgrad) *reinterpret_cast<float4*>(VM + i) = vm;
+    }
+  } else {
+    const long long end = base + ADAM_CHUNK < n ? base + ADAM_CHUNK : n;
+    for (long long i = base + threadIdx.x; i < end; i += ADAM_THREADS) {
+      float p = P[i], m = M[i], v = V[i], vm = s.amsgrad ? VM[i] : 0.f;
+      adam_one(p, G[i], m, v, vm, s);
+      P[i] = p; M[i] = m; V[i] = v;
+      if (s.amsgrad) VM[i] = vm;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int cgr_adam_step(const cgr_adam_tensor_t* tensors, int32_t n_tensors, double lr, double beta1, double beta2,
+                             double eps, double weight_decay, int64_t step, int32_t amsgrad, float grad_scale,
+                             void* stream) {
+  CGR_CHECK_ARG(tensors && n_tensors > 0, "cgr_adam_step: no tensors");
+  CGR_CHECK_ARG(step >= 1, "cgr_adam_step: step counts from 1");
+  CGR_CHECK_ARG(lr >= 0 && eps >= 0 && beta1 >= 0 && beta1 < 1 && beta2 >= 0 && beta2 < 1 && weight_decay >= 0,
+                "cgr_adam_step: hyper-parameter out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  // bias corrections in double, as the Python reference computes them
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars s;
+  s.beta1 = (float)beta1; s.beta2 = (float)beta2;
+  s.one_minus_beta1 = (float)(1.0 - beta1); s.one_minus_beta2 = (float)(1.0 - beta2);
+  s.eps = (float)eps; s.weight_decay = (float)weight_decay;
+  s.neg_step_size = (float)(-(lr / bc1));
+  s.bc2_sqrt = (float)sqrt(bc2);
+  s.grad_scale = grad_scale;
+  s.amsgrad = amsgrad ? 1 : 0;
+  for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_TENSORS) {      // one launch per 48 tensors (the GNN has <= 32)
+    AdamTable tab;
+    memset(&tab, 0, sizeof(tab));
+    const int cnt = n_tensors - t0 < ADAM_MAX_TENSORS ? n_tensors - t0 : ADAM_MAX_TENSORS;
+    int blocks = 0, k = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const cgr_adam_tensor_t& a = tensors[t0 + j];
+      CGR_CHECK_ARG(a.numel >= 0, "cgr_adam_step: negative size");
+      if (a.numel == 0) continue;
+      CGR_CHECK_ARG(a.param && a.grad && a.exp_avg && a.exp_avg_sq && (!amsgrad || a.max_exp_avg_sq),
+                    "cgr_adam_step: null pointer in tensor %d", t0 + j);
+      tab.param[k] = a.param; tab.grad[k] = a.grad; tab.m[k] = a.exp_avg; tab.v[k] = a.exp_avg_sq;
+      tab.vmax[k] = a.max_exp_avg_sq; tab.numel[k] = a.numel;
+      tab.first_block[k] = blocks;
+      blocks += (int)cgr_ceil_div(a.numel, (int64_t)ADAM_CHUNK);
+      ++k;
+    }
+    if (k == 0) continue;
+    tab.first_block[k] = blocks;
+    tab.n = k;
+    cgr_note_launch("adam_step", st, 1);
+    adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(tab, s);
+    CGR_LAUNCH_CHECK();
+  }
+  return CGR_OK;
+}

@@ -271,6 +271,26 @@ int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_host_batch_t
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,
                         float* grad_pred, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused optimizer step: what `optimizer.step()` does at training/trainer.py:144 with the
+ * optimizer of train.py:117-119 -- torch.optim.Adam(lr, weight_decay (L2 added to the gradient), amsgrad=True) --
+ * for ALL parameter tensors in one launch.  `tensors` is a HOST array; every pointer in it is a device pointer to
+ * contiguous fp32.  `step` counts from 1 (bias corrections 1 - beta^step, computed in double like the reference).
+ * `grad_scale` multiplies every gradient first (1.0, or 1/world for a mean over replicas).
+ * max_exp_avg_sq may be NULL when amsgrad == 0.  The learning-rate schedule (ExponentialLR, train.py:121) stays
+ * with the caller: pass the current lr.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* max_exp_avg_sq;
+  int64_t numel;
+} cgr_adam_tensor_t;
+int cgr_adam_step(const cgr_adam_tensor_t* tensors, int32_t n_tensors, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, int64_t step, int32_t amsgrad, float grad_scale, void* stream);
+
 /* Measurement hooks used by bench.py: number of kernels this library has launched so far, and
  * optional CUDA-event timing of each named stage (events are recorded on the launching stream). */
 long long cgr_launch_count(void);

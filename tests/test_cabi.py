@@ -86,3 +86,25 @@ def test_no_cpu_fallback():
     m = GNN(78, 14, depth=2, hidden_sizes=[32] * 2)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         m(make_batch(2, seed=0, fa=78))
+
+
+def test_fused_adam_has_torch_adam_interface_and_no_cpu_path():
+    """FusedAdam mirrors torch.optim.Adam (train.py:117-119): same arguments, param_groups drive ExponentialLR
+    (train.py:121), argument errors match; stepping CPU parameters fails loudly instead of falling back."""
+    import pytest
+    import torch
+    from cgr_mpnn_3d_b200.optim import FusedAdam
+    w = torch.nn.Parameter(torch.ones(4))
+    opt = FusedAdam([w], lr=1e-2, weight_decay=1e-4, amsgrad=True)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.5)
+    assert set(opt.param_groups[0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad"}
+    opt.step()                      # no gradients yet: nothing to do, like torch
+    sched.step()
+    assert opt.param_groups[0]["lr"] == pytest.approx(5e-3)
+    w.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([w], lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([w], betas=(1.0, 0.999))
