@@ -448,7 +448,7 @@ def main():
         side_t = torch.cuda.Stream()
         side_t.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side_t):
-            for d in tb[:3]:
+            for d in tb:                      # every batch once: builds its index arrays / tile plan before capture
                 tm.zero_grad(set_to_none=True)
                 train_step(d)
         torch.cuda.current_stream().wait_stream(side_t)

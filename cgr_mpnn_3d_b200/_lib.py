@@ -69,7 +69,8 @@ class CgrAdamTensor(C.Structure):
 class CgrSaved(C.Structure):
     _fields_ = [
         ("h_all", C.c_void_p), ("m_all", C.c_void_p), ("z_all", C.c_void_p), ("s", C.c_void_p),
-        ("hv", C.c_void_p), ("zv", C.c_void_p), ("pooled", C.c_void_p),
+        ("hv", C.c_void_p), ("zv", C.c_void_p), ("pooled", C.c_void_p), ("tc_blob", C.c_void_p),
+        ("tc_blob_bytes", C.c_size_t),
     ]
 
 
@@ -90,6 +91,7 @@ PROTOTYPES = {
     "cgr_gnn_infer_host": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_async": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_multi_async": (C.c_int, [C.POINTER(CgrParams), _V, C.c_int32, _V, _V, _SZ, _V, _SZ, _V]),
+    "cgr_tc_saved_bytes": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph)]),
     "cgr_adam_step": (C.c_int, [_V, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64,
                                 C.c_int32, C.c_float, _V]),
     "cgr_infer_host_check": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, _V]),

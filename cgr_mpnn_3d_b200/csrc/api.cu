@@ -371,7 +371,14 @@ extern "C" size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t
   if (!p || !g) return 0;
   // tcgen05 engine: fused tile kernels when a tile plan exists and nothing has to be saved; otherwise the layer-wise
   // path with tensor-core GEMMs (training, or graphs whose reactions exceed a 128-bond tile)
-  if (engine == CGR_ENGINE_TC && !training && g->tile_info && g->n_tiles > 0) return tc_forward_workspace(p, g, training);
+  if (engine == CGR_ENGINE_TC && g->tile_info && g->n_tiles > 0 && (!training || tc_fused_training_ok(p, g))) {
+    // training callers may still choose the layer-wise path (no tc_blob): size for the larger of the two
+    const size_t f = tc_forward_workspace(p, g, training);
+    if (!training) return f;
+    const size_t H_ = p->hidden, N_ = g->n_atoms;
+    const size_t lw = fbytes(N_ * H_) + tc_train_ws(p, g).total + 256;
+    return f > lw ? f : lw;
+  }
   const size_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
   size_t b = fbytes(N * H);
   if (!training) b += 4 * fbytes(E * H) + 2 * fbytes(N * H) + fbytes(B * H);
@@ -393,7 +400,7 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
                 cgr_forward_workspace(p, g, training, engine));
   CGR_CHECK_ARG(engine == CGR_ENGINE_SIMT || engine == CGR_ENGINE_TC, "unknown engine %d", engine);
   // inference on the tcgen05 engine: fused tile kernels.  Training on it: layer-wise path with tensor-core GEMMs.
-  if (engine == CGR_ENGINE_TC && !saved && g->tile_info && g->n_tiles > 0)
+  if (engine == CGR_ENGINE_TC && (!saved || saved->tc_blob) && g->tile_info && g->n_tiles > 0)
     return tc_gnn_forward(p, g, out, saved, training, seed, workspace, workspace_bytes, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t H = p->hidden, E = g->n_bonds, N = g->n_atoms, B = g->n_rxn;
@@ -403,6 +410,7 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
   float* P = ws.floats(N * H);
   float *h0, *hbuf[2] = {nullptr, nullptr}, *mbuf = nullptr, *s, *hv, *pooled;
   if (saved) {
+    CGR_CHECK_ARG(!saved->tc_blob, "cgr_gnn_forward: tc_blob needs the tcgen05 engine and a tile plan");
     CGR_CHECK_ARG(saved->h_all && saved->m_all && saved->s && saved->hv && saved->pooled,
                   "cgr_gnn_forward: saved buffers missing");
     CGR_CHECK_ARG(p->act == CGR_ACT_RELU || (saved->z_all && saved->zv),
@@ -449,7 +457,16 @@ extern "C" size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_
   size_t b = 2 * fbytes(N * H) + 3 * fbytes(E * H) + fbytes(partial) +
              fbytes(simt_colsum_workspace(E > N ? E : N, (int)H)) + 256;
   if (engine == CGR_ENGINE_TC) b += tc_train_ws(p, g).total;
+  if (engine == CGR_ENGINE_TC) {                // the fused tile-local backward (saved->tc_blob) has its own layout
+    const size_t f = tc_backward_workspace(p, g);
+    if (f > b) b = f;
+  }
   return b;
+}
+
+extern "C" size_t cgr_tc_saved_bytes(const cgr_params_t* p, const cgr_graph_t* g) {
+  if (!p || !g) return 0;
+  return tc_saved_bytes(p, g);
 }
 
 extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved,
@@ -460,6 +477,12 @@ extern "C" int cgr_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, con
   rc = check_graph(g);
   if (rc) return rc;
   CGR_CHECK_ARG(saved && grad_out && grads, "cgr_gnn_backward: null pointer");
+  if (engine == CGR_ENGINE_TC && saved->tc_blob) {      // fused tile-local backward
+    CGR_CHECK_ARG(grads->w_init && grads->b_init && grads->w_conv && grads->b_conv && grads->w_e2n && grads->b_e2n &&
+                      grads->w_ffn && grads->b_ffn && (!p->use_skip || grads->skip), "cgr_gnn_backward: null grad");
+    CGR_CHECK_ARG(workspace_bytes >= tc_backward_workspace(p, g), "cgr_gnn_backward: workspace too small");
+    return tc_gnn_backward(p, g, saved, grad_out, grads, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
   CGR_CHECK_ARG(saved->h_all && saved->m_all && saved->s && saved->hv && saved->pooled,
                 "cgr_gnn_backward: saved buffers missing");
   CGR_CHECK_ARG(p->act == CGR_ACT_RELU || (saved->z_all && saved->zv), "cgr_gnn_backward: z_all/zv required");

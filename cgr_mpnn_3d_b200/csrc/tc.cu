@@ -145,6 +145,8 @@ struct PrepArgs {
   float* unscale;               // [n_mat]
   __half* hi[MAX_SEG];          // per matrix
   __half* lo[MAX_SEG];
+  __half* hiT[MAX_SEG];         // optional transposed copy (backward data-gradient GEMMs), same scale
+  __half* loT[MAX_SEG];
   int64_t ldo[MAX_SEG];
 };
 
@@ -178,6 +180,10 @@ __global__ void __launch_bounds__(256) prep_split_kernel(const PrepArgs a) {
     split_f16(__ldg(s.src + r * s.ld + c) * sc, h, l);
     hi[(s.row0 + r) * ldo + c] = h;
     lo[(s.row0 + r) * ldo + c] = l;
+    if (a.hiT[s.mat]) {
+      a.hiT[s.mat][c * ldo + s.row0 + r] = h;
+      a.loT[s.mat][c * ldo + s.row0 + r] = l;
+    }
   }
 }
 
@@ -300,7 +306,7 @@ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 struct WLayout {                 // prepared-weight buffer: [amax | unscale | bias_cat | matrices (hi, lo)...]
   int n_mat;
   int64_t kp_x, kp_h;
-  size_t off_amax, off_unscale, off_bias, off_wet, off_hi[MAX_SEG], off_lo[MAX_SEG], total;
+  size_t off_amax, off_unscale, off_bias, off_wet, off_hi[MAX_SEG], off_lo[MAX_SEG], off_hiT[MAX_SEG], off_loT[MAX_SEG], total;
   int64_t rows[MAX_SEG], ld[MAX_SEG];
 };
 
@@ -321,6 +327,11 @@ WLayout wlayout(const cgr_params_t* p) {
     const size_t bytes = cgr_align_up((size_t)w.rows[m] * w.ld[m] * sizeof(__half), 1024);
     w.off_hi[m] = off; off += bytes;
     w.off_lo[m] = off; off += bytes;
+    w.off_hiT[m] = w.off_loT[m] = 0;
+    if (m >= 1) {                 // square [H, H] matrices: transposed copies for dh = dy W
+      w.off_hiT[m] = off; off += bytes;
+      w.off_loT[m] = off; off += bytes;
+    }
   }
   w.total = off;
   return w;
@@ -413,6 +424,8 @@ int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cud
   for (int m = 0; m < w.n_mat; ++m) {
     a.hi[m] = (__half*)(b + w.off_hi[m]);
     a.lo[m] = (__half*)(b + w.off_lo[m]);
+    a.hiT[m] = m >= 1 ? (__half*)(b + w.off_hiT[m]) : nullptr;
+    a.loT[m] = m >= 1 ? (__half*)(b + w.off_loT[m]) : nullptr;
     a.ldo[m] = w.ld[m];
   }
   int ns = 0;
@@ -485,6 +498,42 @@ TcWs tc_ws(const cgr_params_t* p, const cgr_graph_t* g, bool need_w) {
 }
 }  // namespace
 
+namespace {
+// Activations the fused training forward keeps for the fused backward (the cgr_saved_t.tc_blob buffer):
+// every layer's output as tile-packed FP16 (hi, lo) rows -- the backward's GEMM operands and ReLU masks --
+// then h_0 in fp32 (skip-weight gradient) and hv in fp32 (mask of the readout backward).
+struct TcSavedLayout {
+  int64_t kp_h, rows_pad;
+  size_t off_hhi[MAX_SEG], off_hlo[MAX_SEG], hl_bytes, off_h0, off_hv, total;
+};
+TcSavedLayout tc_saved_layout(const cgr_params_t* p, const cgr_graph_t* g) {
+  TcSavedLayout L;
+  const int64_t H = p->hidden;
+  L.kp_h = round_up(H, BK);
+  L.rows_pad = g->n_tiles * TM;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += cgr_align_up(bytes, 1024); return o; };
+  for (int l = 0; l <= p->depth; ++l) {
+    L.off_hhi[l] = take((size_t)L.rows_pad * L.kp_h * sizeof(__half));
+    L.off_hlo[l] = take((size_t)L.rows_pad * L.kp_h * sizeof(__half));
+  }
+  L.hl_bytes = off;
+  L.off_h0 = take((size_t)L.rows_pad * H * sizeof(float));
+  L.off_hv = take((size_t)g->n_atoms * H * sizeof(float));
+  L.total = off + 1024;
+  return L;
+}
+}  // namespace
+
+bool tc_fused_training_ok(const cgr_params_t* p, const cgr_graph_t* g) {
+  return g->tile_info && g->n_tiles > 0 && p->act == CGR_ACT_RELU && p->hidden % 4 == 0 && p->hidden <= 1024 &&
+         p->fb <= 32 && p->depth + 4 <= MAX_SEG;
+}
+size_t tc_saved_bytes(const cgr_params_t* p, const cgr_graph_t* g) {
+  if (!tc_fused_training_ok(p, g)) return 0;
+  return tc_saved_layout(p, g).total;
+}
+
 size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int training) {
   (void)training;
   if (!g->tile_info || g->n_tiles <= 0) return 0;
@@ -493,8 +542,18 @@ size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int tra
 
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  CGR_CHECK_ARG(!saved, "tcgen05 engine: the training (activation-saving) forward is not available yet; use engine simt");
   CGR_CHECK_ARG(g->tile_info && g->n_tiles > 0, "tcgen05 engine needs a tile plan (reactions of <= 128 bonds)");
+  char* blob = nullptr;               // training: per-layer activations are kept in the caller's blob
+  TcSavedLayout SL;
+  memset(&SL, 0, sizeof(SL));
+  if (saved) {
+    CGR_CHECK_ARG(saved->tc_blob && tc_fused_training_ok(p, g), "tcgen05 fused training forward: unsupported configuration or missing tc_blob");
+    SL = tc_saved_layout(p, g);
+    CGR_CHECK_ARG(saved->tc_blob_bytes >= SL.total, "tcgen05 fused training forward: tc_blob too small");
+    blob = (char*)(((uintptr_t)saved->tc_blob + 1023) & ~(uintptr_t)1023);
+    // pad rows of the tile-packed operands are read by the weight-gradient GEMMs (K = rows): they must be zero
+    CGR_CUDA(cudaMemsetAsync(blob, 0, SL.hl_bytes, st));
+  }
   CGR_CHECK_ARG(p->hidden % 4 == 0, "tcgen05 engine needs a hidden size that is a multiple of 4");
   CGR_CHECK_ARG(p->depth + 3 <= MAX_SEG, "tcgen05 engine supports depth <= %d", MAX_SEG - 3);
   CGR_CHECK_ARG(p->fb <= 32, "tcgen05 engine supports at most 32 bond features");
@@ -522,9 +581,12 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   __half* x_hi = need_x ? (__half*)(ws + w.off_xhi) : (__half*)g->x_hi;
   __half* x_lo = need_x ? (__half*)(ws + w.off_xlo) : (__half*)g->x_lo;
   float* PQ = (float*)(ws + w.off_pq);
-  float* h0 = (float*)(ws + w.off_h0);
+  float* h0 = blob ? (float*)(blob + SL.off_h0) : (float*)(ws + w.off_h0);
   __half* h_hi[2] = {(__half*)(ws + w.off_hhi[0]), (__half*)(ws + w.off_hhi[1])};
   __half* h_lo[2] = {(__half*)(ws + w.off_hlo[0]), (__half*)(ws + w.off_hlo[1])};
+  // operand buffers of layer l's input / output: ping-pong for inference, one pair per layer when saving
+  auto hbuf_hi = [&](int l) { return blob ? (__half*)(blob + SL.off_hhi[l]) : h_hi[l & 1]; };
+  auto hbuf_lo = [&](int l) { return blob ? (__half*)(blob + SL.off_hlo[l]) : h_lo[l & 1]; };
   float* partial = (float*)(ws + w.off_partial);
   static const bool use_pdl = getenv("CGR_NO_PDL") == nullptr;   // programmatic dependent launch between the kernels
   // grids larger than the machine, or forwards pipelined over streams by the caller, run two CTAs per SM
@@ -581,8 +643,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
     CGR_CUDA(cudaLaunchKernelEx(&cfg, tc_edge_init_kernel, (const float*)PQ, (int64_t)(2 * H), g->edge_attr, g->src,
-                                (const float*)(wbuf + wl.off_wet), g->tile_info, fb, H, (int)p->act, h0, h_hi[0],
-                                h_lo[0], (int64_t)w.kp_h, flag));
+                                (const float*)(wbuf + wl.off_wet), g->tile_info, fb, H, (int)p->act, h0, hbuf_hi(0),
+                                hbuf_lo(0), (int64_t)w.kp_h, flag));
   }
   // 4. message passing layers: one fused kernel each
   const int bn_h = choose_bn(T, H);
@@ -590,9 +652,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   for (int l = 0; l < d; ++l) {
     TcGemmParams prm;
     memset(&prm, 0, sizeof(prm));
-    const int in = l & 1, ob = in ^ 1;
-    if ((rc = make_map(&prm.tmA_hi, h_hi[in], w.rows_pad, H, w.kp_h, TM))) return rc;
-    if ((rc = make_map(&prm.tmA_lo, h_lo[in], w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmA_hi, hbuf_hi(l), w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmA_lo, hbuf_lo(l), w.rows_pad, H, w.kp_h, TM))) return rc;
     if ((rc = make_map(&prm.tmB_hi, w_hi(1 + l), H, H, wl.ld[1 + l], bn_h))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(1 + l), H, H, wl.ld[1 + l], bn_h))) return rc;
     prm.num_k = (int)cgr_ceil_div(H, BK);
@@ -608,7 +669,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.act = p->act;
     prm.dropout_p = (training && p->host_dropout_p) ? p->host_dropout_p[l] : 0.f;
     prm.seed = seed; prm.layer = (uint32_t)l;
-    prm.o_hi = h_hi[ob]; prm.o_lo = h_lo[ob]; prm.ldo = w.kp_h;
+    prm.o_hi = hbuf_hi(l + 1); prm.o_lo = hbuf_lo(l + 1); prm.ldo = w.kp_h;
     prm.overflow = flag;
     prm.dbg = g_tc_dbg;
     rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
@@ -618,9 +679,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   {
     TcGemmParams prm;
     memset(&prm, 0, sizeof(prm));
-    const int in = d & 1;
-    if ((rc = make_map(&prm.tmA_hi, h_hi[in], w.rows_pad, H, w.kp_h, TM))) return rc;
-    if ((rc = make_map(&prm.tmA_lo, h_lo[in], w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmA_hi, hbuf_hi(d), w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmA_lo, hbuf_lo(d), w.rows_pad, H, w.kp_h, TM))) return rc;
     if ((rc = make_map(&prm.tmB_hi, w_hi(d + 1), H, H, wl.ld[d + 1], bn_h))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(d + 1), H, H, wl.ld[d + 1], bn_h))) return rc;
     prm.num_k = (int)cgr_ceil_div(H, BK);
@@ -639,8 +699,413 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.partial_out = partial;
     prm.n_rxn = B;
     prm.overflow = flag;
+    prm.hv_out = blob ? (float*)(blob + SL.off_hv) : nullptr;
     rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
+  }
+  return CGR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused tile-local backward (training on the tcgen05 engine, ReLU networks on tileable batches).
+//
+// With the GEMM-first formulation  y_l = h_{l-1} W_l^T,  z_l = G y_l + b_l + skip_l h_0,  h_l = drop(relu(z_l))
+// (G = directed-bond gather), the backward of a layer is  dz_l = dh_l . [h_l > 0] . keep_scale,
+// dy_l = G^T dz_l,  dW_l = dy_l^T h_{l-1},  dh_{l-1} = dy_l W_l:  the same shape as the forward -- one GEMM whose
+// epilogue masks, reduces and gathers inside the tile (EPI_BOND_BWD) -- so the only tensors saved are the layer
+// outputs the forward already writes as FP16 (hi, lo) operands.  Gradient operands carry a power-of-two scale taken
+// from the amax of the previous gradient tensor (max is order-independent: deterministic).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int BWD_THREADS = 256;
+
+// gamax[0] = max|dout| * max|w_f| (bound on |dq|), gamax[1..] = 0;  db_f = sum_b dout[b]
+__global__ void __launch_bounds__(BWD_THREADS) bwd_prep_kernel(const float* __restrict__ dout, int64_t B,
+                                                               const float* __restrict__ w_ffn, int H,
+                                                               unsigned int* __restrict__ gamax, int n_gamax,
+                                                               float* __restrict__ db_ffn) {
+  __shared__ float red[BWD_THREADS];
+  __shared__ float red2[BWD_THREADS];
+  float am = 0.f, sum = 0.f, wm = 0.f;
+  for (int64_t i = threadIdx.x; i < B; i += BWD_THREADS) {
+    const float v = __ldg(dout + i);
+    am = fmaxf(am, fabsf(v));
+    sum += v;
+  }
+  for (int i = threadIdx.x; i < H; i += BWD_THREADS) wm = fmaxf(wm, fabsf(__ldg(w_ffn + i)));
+  red[threadIdx.x] = sum;
+  red2[threadIdx.x] = am;
+  __syncthreads();
+  for (int o = BWD_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[threadIdx.x] += red[threadIdx.x + o];
+      red2[threadIdx.x] = fmaxf(red2[threadIdx.x], red2[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  const float amax_d = red2[0];
+  if (threadIdx.x == 0) *db_ffn = red[0];
+  __syncthreads();
+  red2[threadIdx.x] = wm;
+  __syncthreads();
+  for (int o = BWD_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red2[threadIdx.x] = fmaxf(red2[threadIdx.x], red2[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gamax[0] = __float_as_uint(amax_d * red2[0]);
+  for (int i = 1 + threadIdx.x; i < n_gamax; i += BWD_THREADS) gamax[i] = 0u;
+}
+
+// Readout backward, one block per tile:  dzv[v] = dout[rxn(v)] . w_f . [hv[v] > 0]  (atoms of the tile),
+// dq[k] = dzv[dst k] (bonds of the tile, tile-packed), both as scaled FP16 (hi, lo) operands; per-tile column sums
+// of dzv (db_o) and of dout . hv (dw_f).
+__global__ void __launch_bounds__(BWD_THREADS) readout_bwd_kernel(
+    const float* __restrict__ dout, const float* __restrict__ hv, const float* __restrict__ w_ffn,
+    const int32_t* __restrict__ tile_info, const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ dst, int H,
+    int64_t kp_h, __half* __restrict__ dzv_hi, __half* __restrict__ dzv_lo, __half* __restrict__ dq_hi,
+    __half* __restrict__ dq_lo, float* __restrict__ dbo_partial, float* __restrict__ dwf_partial,
+    unsigned int* __restrict__ gamax, float* __restrict__ gunscale) {
+  extern __shared__ __align__(16) float rb_smem[];          // [8][H] cross-warp reduction scratch
+  __shared__ float dpl[TM];
+  const int tile = blockIdx.x;
+  const int ebase = __ldg(tile_info + tile * 8), ecount = __ldg(tile_info + tile * 8 + 1);
+  const int abase = __ldg(tile_info + tile * 8 + 2), acount = __ldg(tile_info + tile * 8 + 3);
+  const int rx0 = __ldg(tile_info + tile * 8 + 4), rxcount = __ldg(tile_info + tile * 8 + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rx = threadIdx.x; rx < rxcount; rx += BWD_THREADS) {
+    const float d = __ldg(dout + rx0 + rx);
+    const int v0 = __ldg(atom_ptr + rx0 + rx) - abase, v1 = __ldg(atom_ptr + rx0 + rx + 1) - abase;
+    for (int v = v0; v < v1; ++v) dpl[v] = d;
+  }
+  const float S0 = tcg::grad_scale(gamax[0]);
+  if (tile == 0 && threadIdx.x == 0) gunscale[0] = 1.f / S0;
+  __syncthreads();
+  constexpr int NG = 8;                                      // column groups of 128: H <= 1024
+  float4 csum[NG], wsum[NG];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) csum[q] = wsum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = warp; v < acount; v += BWD_THREADS / 32) {
+    const float d = dpl[v];
+    const int64_t row = abase + v;
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      const int n = q * 128 + 4 * lane;
+      if (n < H) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(hv + row * H + n));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w_ffn + n));
+        float4 dz;
+        dz.x = h.x > 0.f ? d * w.x : 0.f; dz.y = h.y > 0.f ? d * w.y : 0.f;
+        dz.z = h.z > 0.f ? d * w.z : 0.f; dz.w = h.w > 0.f ? d * w.w : 0.f;
+        tcg::store_split4(dz, S0, dzv_hi + row * kp_h + n, dzv_lo + row * kp_h + n);
+        tcg::add4(csum[q], dz);
+        wsum[q].x = fmaf(d, h.x, wsum[q].x); wsum[q].y = fmaf(d, h.y, wsum[q].y);
+        wsum[q].z = fmaf(d, h.z, wsum[q].z); wsum[q].w = fmaf(d, h.w, wsum[q].w);
+      }
+    }
+  }
+  for (int pass = 0; pass < 2; ++pass) {                     // fixed warp order: deterministic
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      const int n = q * 128 + 4 * lane;
+      if (n < H) *reinterpret_cast<float4*>(rb_smem + warp * H + n) = pass == 0 ? csum[q] : wsum[q];
+    }
+    __syncthreads();
+    float* outp = pass == 0 ? dbo_partial : dwf_partial;
+    for (int n = threadIdx.x; n < H; n += BWD_THREADS) {
+      float t = 0.f;
+      for (int w = 0; w < BWD_THREADS / 32; ++w) t += rb_smem[w * H + n];
+      outp[(int64_t)tile * H + n] = t;
+    }
+    __syncthreads();
+  }
+  float vmax = 0.f;
+  for (int j = warp; j < ecount; j += BWD_THREADS / 32) {
+    const int v = __ldg(dst + ebase + j) - abase;
+    const float d = dpl[v];
+    const int64_t row = abase + v, orow = (int64_t)tile * TM + j;
+    for (int n = 4 * lane; n < H; n += 128) {
+      const float4 h = __ldg(reinterpret_cast<const float4*>(hv + row * H + n));
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w_ffn + n));
+      float4 dz;
+      dz.x = h.x > 0.f ? d * w.x : 0.f; dz.y = h.y > 0.f ? d * w.y : 0.f;
+      dz.z = h.z > 0.f ? d * w.z : 0.f; dz.w = h.w > 0.f ? d * w.w : 0.f;
+      vmax = fmaxf(vmax, tcg::amax4(dz));
+      tcg::store_split4(dz, S0, dq_hi + orow * kp_h + n, dq_lo + orow * kp_h + n);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if (lane == 0 && vmax > 0.f) atomicMax(gamax + 1, __float_as_uint(vmax));
+}
+
+// Sums the per-tile partials in tile order: bias gradients / dw_f  ([T][H] -> [H]) and skip-weight gradients.
+struct BwdFinalizeArgs {
+  const float* col_src[MAX_SEG + 2];
+  float* col_dst[MAX_SEG + 2];
+  int n_col;
+  const float* skip_src[MAX_SEG];
+  float* skip_dst[MAX_SEG];
+  int n_skip;
+  int skip_cnt;                 // values per skip partial array
+  int T, H;
+};
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+  if ((int)blockIdx.y < a.n_col) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= a.H) return;
+    const float* src = a.col_src[blockIdx.y];
+    float t = 0.f;
+    for (int i = 0; i < a.T; ++i) t += __ldg(src + (int64_t)i * a.H + n);
+    a.col_dst[blockIdx.y][n] = t;
+  } else if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const int k = blockIdx.y - a.n_col;
+    const float* src = a.skip_src[k];
+    float t = 0.f;
+    for (int i = threadIdx.x; i < a.skip_cnt; i += 32) t += __ldg(src + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) *a.skip_dst[k] = t;
+  }
+}
+
+struct TcBwdWs {
+  int64_t kp_h, kp_x, rows_pad;
+  int n_slices;
+  size_t off_ghi[MAX_SEG], off_glo[MAX_SEG], off_dzv_hi, off_dzv_lo, off_dp_hi, off_dp_lo, zero_bytes;
+  size_t off_dh0, off_dz0, off_col, off_dwf, off_skip, off_gamax, off_gunscale, off_partial, off_xhi, off_xlo, off_w, total;
+  size_t skip_cnt, partial_floats;
+};
+TcBwdWs tc_bwd_ws(const cgr_params_t* p, const cgr_graph_t* g) {
+  TcBwdWs w;
+  const int64_t H = p->hidden, N = g->n_atoms, E = g->n_bonds, T = g->n_tiles;
+  const int d = p->depth;
+  w.kp_h = round_up(H, BK);
+  w.kp_x = round_up(p->fa, BK);
+  w.rows_pad = T * TM;
+  w.n_slices = (int)cgr_ceil_div(H, BN_SMALL);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += cgr_align_up(bytes, 1024); return o; };
+  for (int i = 0; i <= d; ++i) {                       // G_0 = dq, G_i = dy_{d+1-i}
+    w.off_ghi[i] = take((size_t)w.rows_pad * w.kp_h * sizeof(__half));
+    w.off_glo[i] = take((size_t)w.rows_pad * w.kp_h * sizeof(__half));
+  }
+  w.zero_bytes = off;                                  // tile-packed operands: pad rows must be zero (K of the wgrads)
+  w.off_dzv_hi = take((size_t)N * w.kp_h * sizeof(__half));
+  w.off_dzv_lo = take((size_t)N * w.kp_h * sizeof(__half));
+  w.off_dp_hi = take((size_t)N * w.kp_h * sizeof(__half));
+  w.off_dp_lo = take((size_t)N * w.kp_h * sizeof(__half));
+  w.off_dh0 = take((size_t)w.rows_pad * H * sizeof(float));
+  w.off_dz0 = take((size_t)E * H * sizeof(float));
+  w.off_col = take((size_t)(d + 2) * T * H * sizeof(float));
+  w.off_dwf = take((size_t)T * H * sizeof(float));
+  w.skip_cnt = (size_t)T * w.n_slices * 2;
+  w.off_skip = take((size_t)d * w.skip_cnt * sizeof(float));
+  w.off_gamax = take(MAX_SEG * 2 * sizeof(unsigned int));
+  w.off_gunscale = take(MAX_SEG * 2 * sizeof(float));
+  size_t pf = 0;
+  auto upd = [&](int64_t M_, int64_t N_, int64_t K_) {
+    const int sk = tc_splitk_choose(M_, N_, K_);
+    if (sk > 1) { const size_t f = (size_t)sk * M_ * N_; if (f > pf) pf = f; }
+  };
+  upd(H, H, w.rows_pad);
+  upd(H, p->fa, N);
+  const int ssk = simt_splitk_choose(H, p->fb > 0 ? p->fb : 1, E);
+  if (ssk > 1 && (size_t)ssk * H * p->fb > pf) pf = (size_t)ssk * H * p->fb;
+  w.partial_floats = pf;
+  w.off_partial = take(pf * sizeof(float));
+  const bool need_x = !(g->x_hi && g->x_lo);
+  w.off_xhi = take(need_x ? (size_t)N * w.kp_x * sizeof(__half) : 0);
+  w.off_xlo = take(need_x ? (size_t)N * w.kp_x * sizeof(__half) : 0);
+  w.off_w = take(p->tc_weights ? 0 : tc_weights_bytes(p));
+  w.total = off + 1024;
+  return w;
+}
+
+}  // namespace
+
+size_t tc_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g) {
+  if (!tc_fused_training_ok(p, g)) return 0;
+  return tc_bwd_ws(p, g).total;
+}
+
+int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved, const float* dout,
+                    const cgr_grads_t* grads, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  CGR_CHECK_ARG(tc_fused_training_ok(p, g) && saved && saved->tc_blob, "tcgen05 fused backward: unsupported configuration");
+  const TcSavedLayout SL = tc_saved_layout(p, g);
+  const TcBwdWs w = tc_bwd_ws(p, g);
+  CGR_CHECK_ARG(saved->tc_blob_bytes >= SL.total, "tcgen05 fused backward: tc_blob too small");
+  CGR_CHECK_ARG(workspace && workspace_bytes >= w.total, "tcgen05 fused backward: workspace too small");
+  CGR_CHECK_ARG(g->tc_status && g->dst, "tcgen05 fused backward: tc_status / dst missing");
+  char* blob = (char*)(((uintptr_t)saved->tc_blob + 1023) & ~(uintptr_t)1023);
+  char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  const int H = p->hidden, fa = p->fa, fb = p->fb, d = p->depth;
+  const int64_t N = g->n_atoms, E = g->n_bonds, T = g->n_tiles, B = g->n_rxn;
+  int rc;
+  char* wbuf = (char*)p->tc_weights;
+  if (!wbuf) {
+    wbuf = ws + w.off_w;
+    if ((rc = tc_prepare_weights(p, wbuf, tc_weights_bytes(p), st))) return rc;
+  }
+  const WLayout wl = wlayout(p);
+  const float* unscale = (const float*)(wbuf + wl.off_unscale);
+  int* flag = g->tc_status;
+  const __half* x_hi = (const __half*)g->x_hi;
+  const __half* x_lo = (const __half*)g->x_lo;
+  if (!(x_hi && x_lo)) {
+    __half* xh = (__half*)(ws + w.off_xhi);
+    __half* xl = (__half*)(ws + w.off_xlo);
+    if ((rc = tc_split_features(g->x, N, fa, xh, xl, flag, st))) return rc;
+    x_hi = xh; x_lo = xl;
+  }
+  auto h_hi = [&](int l) { return (const __half*)(blob + SL.off_hhi[l]); };
+  auto h_lo = [&](int l) { return (const __half*)(blob + SL.off_hlo[l]); };
+  const float* h0 = (const float*)(blob + SL.off_h0);
+  const float* hv = (const float*)(blob + SL.off_hv);
+  auto g_hi = [&](int i) { return (__half*)(ws + w.off_ghi[i]); };
+  auto g_lo = [&](int i) { return (__half*)(ws + w.off_glo[i]); };
+  __half* dzv_hi = (__half*)(ws + w.off_dzv_hi);
+  __half* dzv_lo = (__half*)(ws + w.off_dzv_lo);
+  __half* dp_hi = (__half*)(ws + w.off_dp_hi);
+  __half* dp_lo = (__half*)(ws + w.off_dp_lo);
+  float* dh0 = (float*)(ws + w.off_dh0);
+  float* dz0 = (float*)(ws + w.off_dz0);
+  float* col = (float*)(ws + w.off_col);               // [d+2][T][H]: 0 = db_o, 1..d = db_conv[d-1..0] in launch order, d+1 = db_i
+  float* dwf = (float*)(ws + w.off_dwf);
+  float* skp = (float*)(ws + w.off_skip);
+  unsigned int* gamax = (unsigned int*)(ws + w.off_gamax);
+  float* gunscale = (float*)(ws + w.off_gunscale);
+  float* partial = (float*)(ws + w.off_partial);
+  static const bool use_pdl = getenv("CGR_NO_PDL") == nullptr;
+  auto two_per_sm = [&](int64_t ctas) { return p->tc_throughput != 0 || ctas > 148; };
+
+  CGR_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
+  {
+    CgrRange prof("bwd_readout", st);
+    cgr_note_launch("bwd_readout", st, 2);
+    bwd_prep_kernel<<<1, BWD_THREADS, 0, st>>>(dout, B, p->w_ffn, H, gamax, d + 4, grads->b_ffn);
+    static bool attr = false;
+    if (!attr) {
+      CGR_CUDA(cudaFuncSetAttribute(readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
+      attr = true;
+    }
+    readout_bwd_kernel<<<(unsigned)T, BWD_THREADS, (size_t)8 * H * sizeof(float), st>>>(
+        dout, hv, p->w_ffn, g->tile_info, g->atom_ptr, g->dst, H, w.kp_h, dzv_hi, dzv_lo, g_hi(0), g_lo(0), col, dwf,
+        gamax, gunscale);
+    CGR_LAUNCH_CHECK();
+  }
+  const int bn_h = choose_bn(T, H);
+  // bond layers, last to first: kernel i turns G_i (dq or dy_{l+1}) into dy_l = G_{i+1}, l = d - i
+  for (int i = 0; i < d; ++i) {
+    const int l = d - i;                                 // 1-based layer whose output gradient this GEMM produces
+    const int wm = i == 0 ? d + 1 : l + 1;               // W_os for the readout, else W_{l+1} (matrix index = 1-based layer)
+    TcGemmParams prm;
+    memset(&prm, 0, sizeof(prm));
+    if ((rc = make_map(&prm.tmA_hi, g_hi(i), w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmA_lo, g_lo(i), w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmB_hi, (const __half*)(wbuf + wl.off_hiT[wm]), H, H, wl.ld[wm], bn_h))) return rc;
+    if ((rc = make_map(&prm.tmB_lo, (const __half*)(wbuf + wl.off_loT[wm]), H, H, wl.ld[wm], bn_h))) return rc;
+    prm.num_k = (int)cgr_ceil_div(H, BK);
+    prm.k_total = H;
+    prm.n_total = H;
+    prm.unscale = unscale + wm;
+    prm.tile_info = g->tile_info;
+    prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
+    prm.skip = p->use_skip ? p->skip[l - 1] : nullptr;
+    if ((rc = make_map_f32(&prm.tmR, h0, w.rows_pad, H, H, chunk_cols(bn_h), TM))) return rc;
+    prm.act = p->act;
+    prm.mask_hi = h_hi(l); prm.ld_mask = w.kp_h;
+    const float pd = p->host_dropout_p ? p->host_dropout_p[l - 1] : 0.f;
+    prm.keep_scale = pd > 0.f ? 1.f / (1.f - pd) : 1.f;
+    prm.dh0_acc = dh0; prm.dh0_first = i == 0 ? 1 : 0;
+    prm.colsum_partial = col + (size_t)(1 + i) * T * H;
+    prm.dskip_partial = p->use_skip ? skp + (size_t)i * w.skip_cnt : nullptr;
+    prm.gamax_in = gamax + i; prm.gamax_out = gamax + i + 1; prm.gamax_track = gamax + i + 2;
+    prm.gunscale_out = gunscale + i + 1;
+    prm.o_hi = g_hi(i + 1); prm.o_lo = g_lo(i + 1); prm.ldo = w.kp_h;
+    prm.overflow = flag;
+    rc = launch_gemm<EPI_BOND_BWD>(prm, bn_h, (int)T, true, "bwd_bond_layer", use_pdl && i > 0,
+                                   two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
+    if (rc) return rc;
+  }
+  // edge initialisation: dh_0 = dy_1 W_1 + dh0_acc, dz_0 = dh_0 . [h_0 > 0], dP[v] = sum of dz_0 over bonds leaving v
+  {
+    TcGemmParams prm;
+    memset(&prm, 0, sizeof(prm));
+    if ((rc = make_map(&prm.tmA_hi, g_hi(d), w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmA_lo, g_lo(d), w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&prm.tmB_hi, (const __half*)(wbuf + wl.off_hiT[1]), H, H, wl.ld[1], bn_h))) return rc;
+    if ((rc = make_map(&prm.tmB_lo, (const __half*)(wbuf + wl.off_loT[1]), H, H, wl.ld[1], bn_h))) return rc;
+    prm.num_k = (int)cgr_ceil_div(H, BK);
+    prm.k_total = H;
+    prm.n_total = H;
+    prm.unscale = unscale + 1;
+    prm.tile_info = g->tile_info;
+    prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
+    if ((rc = make_map_f32(&prm.tmR, dh0, w.rows_pad, H, H, chunk_cols(bn_h), TM))) return rc;
+    prm.act = p->act;
+    prm.mask_hi = h_hi(0); prm.ld_mask = w.kp_h;
+    prm.keep_scale = 1.f;
+    prm.colsum_partial = col + (size_t)(d + 1) * T * H;
+    prm.gamax_in = gamax + d; prm.gamax_out = gamax + d + 1; prm.gamax_track = gamax + d + 2;
+    prm.gunscale_out = gunscale + d + 1;
+    prm.o_hi = dp_hi; prm.o_lo = dp_lo; prm.ldo = w.kp_h;
+    prm.dz0_out = dz0;
+    prm.overflow = flag;
+    rc = launch_gemm<EPI_INIT_BWD>(prm, bn_h, (int)T, true, "bwd_edge_init", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
+    if (rc) return rc;
+  }
+  // weight gradients: reductions over bonds / atoms (K = rows) on tensor cores, deterministic split-K
+  GemmEpilogue none;
+  auto wgrad = [&](const __half* ahi, const __half* alo, int64_t lda, const float* aus, const __half* bhi,
+                   const __half* blo, int64_t ldb, int64_t M_, int64_t N_, int64_t K_, float* C, int64_t ldc,
+                   const char* tag) {
+    TcOperand A{ahi, alo, lda, aus, true}, Bo{bhi, blo, ldb, nullptr, true};
+    GemmEpilogue e = none;
+    e.tag = tag;
+    return tc_train_gemm(A, Bo, M_, N_, K_, C, ldc, e, tc_splitk_choose(M_, N_, K_), partial, st);
+  };
+  // dW_os = dq^T h_d ;  dW_l = dy_l^T h_{l-1}
+  if ((rc = wgrad(g_hi(0), g_lo(0), w.kp_h, gunscale + 0, h_hi(d), h_lo(d), w.kp_h, H, H, w.rows_pad,
+                  grads->w_e2n + fa, fa + H, "wgrad_readout_s"))) return rc;
+  for (int l = 1; l <= d; ++l) {
+    const int i = d + 1 - l;
+    if ((rc = wgrad(g_hi(i), g_lo(i), w.kp_h, gunscale + i, h_hi(l - 1), h_lo(l - 1), w.kp_h, H, H, w.rows_pad,
+                    grads->w_conv[l - 1], H, "wgrad_bond"))) return rc;
+  }
+  // dW_ox = dzv^T x ;  dW_x = dP^T x
+  if ((rc = wgrad(dzv_hi, dzv_lo, w.kp_h, gunscale + 0, x_hi, x_lo, w.kp_x, H, fa, N, grads->w_e2n, fa + H,
+                  "wgrad_readout_x"))) return rc;
+  if ((rc = wgrad(dp_hi, dp_lo, w.kp_h, gunscale + d + 1, x_hi, x_lo, w.kp_x, H, fa, N, grads->w_init, fa + fb,
+                  "wgrad_init_x"))) return rc;
+  if (fb > 0) {        // [H x fb] with fb = 14: too narrow for a tensor-core tile, stays on the fp32 kernel
+    GemmEpilogue e;
+    e.tag = "wgrad_edge_attr";
+    rc = simt_gemm(dz0, H, false, g->edge_attr, fb, false, grads->w_init + fa, fa + fb, H, fb, E, e,
+                   simt_splitk_choose(H, fb, E), partial, st);
+    if (rc) return rc;
+  }
+  {
+    BwdFinalizeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = (int)T; a.H = H;
+    int nc = 0;
+    a.col_src[nc] = col; a.col_dst[nc++] = grads->b_e2n;
+    for (int i = 0; i < d; ++i) { a.col_src[nc] = col + (size_t)(1 + i) * T * H; a.col_dst[nc++] = grads->b_conv[d - 1 - i]; }
+    a.col_src[nc] = col + (size_t)(d + 1) * T * H; a.col_dst[nc++] = grads->b_init;
+    a.col_src[nc] = dwf; a.col_dst[nc++] = grads->w_ffn;
+    a.n_col = nc;
+    if (p->use_skip) {
+      for (int i = 0; i < d; ++i) { a.skip_src[i] = skp + (size_t)i * w.skip_cnt; a.skip_dst[i] = grads->skip[d - 1 - i]; }
+      a.n_skip = d;
+      // each launch wrote [T][n_slices(bn)][NCH(bn)] values at the front of its array
+      a.skip_cnt = (int)(T * cgr_ceil_div(H, bn_h) * (bn_h > 128 ? 2 : 1));
+    }
+    CgrRange prof("bwd_finalize", st);
+    cgr_note_launch("bwd_finalize", st, 1);
+    bwd_finalize_kernel<<<dim3((unsigned)cgr_ceil_div(H, 256), (unsigned)(a.n_col + a.n_skip)), 256, 0, st>>>(a);
+    CGR_LAUNCH_CHECK();
   }
   return CGR_OK;
 }

@@ -9,6 +9,13 @@ size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int tra
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// fused tile-local training path (ReLU, tileable batches): activations kept in cgr_saved_t.tc_blob
+bool tc_fused_training_ok(const cgr_params_t* p, const cgr_graph_t* g);
+size_t tc_saved_bytes(const cgr_params_t* p, const cgr_graph_t* g);
+size_t tc_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g);
+int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved, const float* dout,
+                    const cgr_grads_t* grads, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 size_t tc_weights_bytes(const cgr_params_t* p);
 int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cudaStream_t st);
 int tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, const int32_t* src, const int32_t* dst,

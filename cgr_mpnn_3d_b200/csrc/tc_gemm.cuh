@@ -19,7 +19,8 @@ constexpr int SMEM_LIMIT = 232448;      // 227 KB opt-in maximum per CTA
 constexpr int RU = 4;                   // rows processed together by a warp in the epilogue (ILP)
 constexpr int NBR = 8;                  // neighbour slots per row kept in the packed descriptor
 
-enum { EPI_PLAIN = 0, EPI_BOND = 1, EPI_READOUT = 2 };
+// EPI_BOND_BWD / EPI_INIT_BWD: the tile-local backward of a bond layer / of the edge initialisation (training)
+enum { EPI_PLAIN = 0, EPI_BOND = 1, EPI_READOUT = 2, EPI_BOND_BWD = 3, EPI_INIT_BWD = 4 };
 
 // NT = threads per CTA.  NT=512: one CTA per SM, deep pipeline, dedicated buffer for the prefetched fp32 operand.
 // NT=256: two CTAs per SM (<= 113 KB each): 2-stage pipeline, the fp32 operand is loaded into the drained pipeline
@@ -49,6 +50,9 @@ struct Cfg {
   static constexpr int ACC_COLS = CAT ? 2 * BN : BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + R_DEDICATED + AUX_BYTES + 1024;
+  // backward epilogues: per-warp column sums [NWARPS][CH] behind the staging buffers
+  static constexpr int RED_OFF = Y_BYTES + ((NCH > 1 || R_ALIAS) ? R_BYTES : 0);
+  static_assert(EPI < 3 || RED_OFF + NWARPS * CH * 4 <= STAGES * STAGE_BYTES, "reduction scratch must fit in the pipeline buffers");
   static_assert(BN % 16 == 0 && BN <= 256 && CH % 4 == 0 && VL <= 32, "bad slice width");
   static_assert(STAGES >= 2, "pipeline needs two stages");
   static_assert(Y_BYTES + ((NCH > 1 || R_ALIAS) ? R_BYTES : 0) <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
@@ -91,6 +95,20 @@ struct TcGemmParams {
   int* tile_counter;            // [T] arrival counters of the readout (self-resetting)
   int64_t n_rxn;
   int* overflow;                // sticky flag: an activation left the fp16 range
+  float* hv_out;                // READOUT, training: hv [N, H] fp32 (ReLU mask of the readout backward)
+  // ---- backward epilogues (EPI_BOND_BWD / EPI_INIT_BWD) ----
+  const __half* mask_hi;        // hi part of the layer's saved output (tile-packed): dz = dh * [h > 0] * keep_scale
+  int64_t ld_mask;
+  float keep_scale;             // 1 / (1 - dropout_p) of the layer
+  float* dh0_acc;               // BOND_BWD: [T*128, H] fp32, += skip * dz  (INIT_BWD reads it through tmR)
+  int dh0_first;                // first contribution: store instead of accumulate
+  float* colsum_partial;        // [T][H]   per-tile column sums of dz  (bias gradient)
+  float* dskip_partial;         // [T][n_slices * NCH]  per-CTA sum of dz . h0 (skip-weight gradient) or null
+  const unsigned int* gamax_in;   // amax (float bits) that fixes the power-of-two scale of the A operand
+  const unsigned int* gamax_out;  // amax that fixes the scale of the produced operand
+  unsigned int* gamax_track;      // true amax of the produced operand (fixes the next kernel's scale)
+  float* gunscale_out;            // 1 / scale of the produced operand, for the weight-gradient GEMMs
+  float* dz0_out;               // INIT_BWD: dz_0 [E, H] fp32 in bond order (bond-feature weight gradient)
   long long* dbg;               // optional [n_cta][8] clock64 stamps of the kernel phases (debug)
 };
 
@@ -109,6 +127,7 @@ struct Aux {                    // small per-CTA shared state, lives after the p
   uint2 nbr[TM];                // first NBR neighbour rows, one byte each
   uint16_t nbr_pb[TM];          // CSR offset of the row's neighbour list (for degrees > NBR)
   uint8_t nbr_deg[TM];          // its length
+  float red2[16];               // backward: per-warp partial of the skip-weight gradient
 };
 static_assert(sizeof(Aux) <= AUX_BYTES, "Aux too large");
 
@@ -120,6 +139,70 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 template <bool RELU>
 __device__ __forceinline__ float act_t(float z, int act) { return RELU ? fmaxf(z, 0.f) : cgr_act(z, act); }
+
+// Power-of-two scale that maps a gradient tensor of magnitude `amax` into [2^7, 2^8] before its FP16 (hi, lo) split:
+// far from the fp16 overflow (2^16) when the next tensor grows, and ~2^30 above the lo part's underflow.
+__device__ __forceinline__ float grad_scale(unsigned int amax_bits) {
+  const float a = __uint_as_float(amax_bits);
+  if (!(a > 0.f) || !isfinite(a)) return 1.f;
+  int e;
+  frexpf(a, &e);
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return ldexpf(1.f, 8 - e);
+}
+
+// sum of the staged rows named by the packed neighbour descriptors of RU consecutive epilogue rows
+template <int CHP>
+__device__ __forceinline__ void nbr_sum(const float* y_s, const Aux* aux, int r0, int nrows, int c, float4 (&acc)[RU]) {
+  uint2 nb[RU];
+  int deg[RU], maxdeg = 0;
+#pragma unroll
+  for (int u = 0; u < RU; ++u) {
+    const int r = r0 + u < nrows ? r0 + u : r0;
+    nb[u] = aux->nbr[r];
+    deg[u] = r0 + u < nrows ? (int)aux->nbr_deg[r] : 0;
+    maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
+    acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < maxdeg) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+        if (t < deg[u]) add4(acc[u], ld4(y_s + (int)((nb[u].x >> (8 * t)) & 0xffu) * CHP + c));
+    }
+  }
+  const int fast = maxdeg < NBR ? maxdeg : NBR;
+  for (int t = 4; t < fast; ++t) {
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+      if (t < deg[u]) add4(acc[u], ld4(y_s + (int)((nb[u].y >> (8 * (t - 4))) & 0xffu) * CHP + c));
+  }
+  if (maxdeg > NBR) {
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      if (r0 + u >= nrows) break;
+      const int pb = aux->nbr_pb[r0 + u];
+      for (int t = NBR; t < deg[u]; ++t) add4(acc[u], ld4(y_s + (int)aux->idx_l[pb + t] * CHP + c));
+    }
+  }
+}
+
+// scaled FP16 (hi, lo) split of one float4 column group, stored as two 8-byte words
+__device__ __forceinline__ void store_split4(const float4 v, float scale, __half* hi, __half* lo) {
+  const float z0 = v.x * scale, z1 = v.y * scale, z2 = v.z * scale, z3 = v.w * scale;
+  const __half2 hi01 = __floats2half2_rn(z0, z1), hi23 = __floats2half2_rn(z2, z3);
+  const float2 f01 = __half22float2(hi01), f23 = __half22float2(hi23);
+  const __half2 lo01 = __floats2half2_rn(z0 - f01.x, z1 - f01.y), lo23 = __floats2half2_rn(z2 - f23.x, z3 - f23.y);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
+  pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
+  *reinterpret_cast<uint2*>(hi) = ph;
+  *reinterpret_cast<uint2*>(lo) = pl;
+}
+__device__ __forceinline__ float amax4(const float4 v) {
+  return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
 
 // RELU: compile-time fast path for the reference's default activation (branch-free epilogue)
 template <int BN_, int EPI, bool RELU, int NT_>
@@ -172,7 +255,8 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem = aux->tmem_base;
-  const int r_row0 = EPI == EPI_BOND ? tile * TM : (EPI == EPI_READOUT ? aux->info[2] : 0);
+  constexpr bool BWD = EPI == EPI_BOND_BWD || EPI == EPI_INIT_BWD;
+  const int r_row0 = (EPI == EPI_BOND || BWD) ? tile * TM : (EPI == EPI_READOUT ? aux->info[2] : 0);
   TC_STAMP(1);
   // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, tile info) only touches
   // data that no earlier kernel of the forward writes; let the next kernel start its own prologue now
@@ -244,29 +328,33 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   } else if (EPI != EPI_PLAIN) {
     // the other warps stage the tile's index rows into shared memory while the GEMM runs
     const int ebase = aux->info[0], ecount = aux->info[1], abase = aux->info[2], acount = aux->info[3];
+    constexpr int X1 = BWD ? 1 : 0;        // backward gathers read the reverse bond of every neighbour
     for (int j = threadIdx.x - 64; j < ecount; j += THREADS - 64) {
       aux->src_l[j] = (uint8_t)(__ldg(p.src + ebase + j) - abase);
-      aux->idx_l[j] = (uint8_t)(__ldg(p.in_idx + ebase + j) - ebase);
+      aux->idx_l[j] = (uint8_t)((__ldg(p.in_idx + ebase + j) - ebase) ^ X1);
     }
     for (int v = threadIdx.x - 64; v <= acount; v += THREADS - 64)
       aux->ptr_l[v] = (uint16_t)(__ldg(p.in_ptr + abase + v) - ebase);
     // packed neighbour descriptor of every epilogue row, read straight from the CSR (L2 hits, hidden
     // behind the GEMM): one 8-byte word + degree instead of a chain of dependent shared-memory loads
-    const int nrows = EPI == EPI_BOND ? ecount : acount;
+    const int nrows = (EPI == EPI_BOND || EPI == EPI_BOND_BWD) ? ecount : acount;
     for (int r = threadIdx.x - 64; r < nrows; r += THREADS - 64) {
-      const int a = EPI == EPI_BOND ? __ldg(p.src + ebase + r) : abase + r;
+      // BOND: in-bonds of src(r).  BOND_BWD: in-bonds of dst(r) = src(r^1), each replaced by its reverse.
+      // READOUT / INIT_BWD: in-bonds of atom r (INIT_BWD: their reverses = the bonds leaving r).
+      const int a = EPI == EPI_BOND ? __ldg(p.src + ebase + r)
+                                    : (EPI == EPI_BOND_BWD ? __ldg(p.src + ebase + (r ^ 1)) : abase + r);
       const int pb = __ldg(p.in_ptr + a), pe = __ldg(p.in_ptr + a + 1);
       uint32_t w[2] = {0u, 0u};
       for (int t = 0; t < NBR && pb + t < pe; ++t)
-        w[t >> 2] |= (uint32_t)((__ldg(p.in_idx + pb + t) - ebase) & 0xff) << (8 * (t & 3));
+        w[t >> 2] |= (uint32_t)(((__ldg(p.in_idx + pb + t) - ebase) ^ X1) & 0xff) << (8 * (t & 3));
       aux->nbr[r] = make_uint2(w[0], w[1]);
       aux->nbr_pb[r] = (uint16_t)(pb - ebase);
       aux->nbr_deg[r] = (uint8_t)(pe - pb > 255 ? 255 : pe - pb);
     }
   }
 
-  const float us = __ldg(p.unscale);
-  const float skip = (EPI == EPI_BOND && p.skip) ? __ldg(p.skip) : 1.f;
+  const float us_w = __ldg(p.unscale);
+  const float skip = ((EPI == EPI_BOND || EPI == EPI_BOND_BWD) && p.skip) ? __ldg(p.skip) : 1.f;
   const int c = 4 * lane;                                         // this lane's float4 column group inside a chunk
   // per-lane bias / readout weights of every column chunk, fetched while the GEMM is still running
   float4 bias_r[NCH], wf_r[NCH];
@@ -294,6 +382,15 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   // ------------------------------------------------------------------ epilogue (all 8 warps)
   umma::mbar_wait(umma::smem_u32(&aux->tmem_full), 0);
   umma::tc_fence_after_sync();
+  // backward: the A operand carries the power-of-two scale fixed by the amax its producer saw; the previous kernel
+  // has completed (the MMAs consumed its output), so these scalars are final
+  float us = us_w;
+  float out_scale = 1.f;
+  if (BWD) {
+    us /= grad_scale(__ldcg(p.gamax_in));
+    out_scale = grad_scale(__ldcg(p.gamax_out));
+    if (p.gunscale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.gunscale_out = 1.f / out_scale;
+  }
   TC_STAMP(2);
   if (C::R_ALIAS && EPI != EPI_PLAIN && threadIdx.x == 0) {
     // every MMA has retired and every pipeline load has landed: the stage buffers are free for the fp32 operand
@@ -443,6 +540,95 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
         }
       }
       ovf |= vmax > 60000.f;
+    } else if (BWD) {
+      // y_s holds dh (BOND_BWD: dL/dh_l of this tile's bonds; INIT_BWD: the layer-1 part of dL/dh_0).
+      //   pass 1 (row-local): dz = (dh [+ dh0_acc]) * [h > 0] * keep_scale, written back to y_s; column sums of dz
+      //           (bias gradient), sum of dz . h0 (skip-weight gradient), dh0_acc += skip * dz.
+      //   pass 2 (tile-local gather): BOND_BWD  dy[k] = sum_{j in in(dst k)} dz[j^1] - dz[k^1]   (transpose of the
+      //           forward gather);  INIT_BWD  dP[v] = sum_{j in in(v)} dz[j^1]  (bonds leaving atom v).
+      const int ebase = aux->info[0], ecount = aux->info[1], abase = aux->info[2], acount = aux->info[3];
+      const int H = p.n_total;
+      float* red_s = reinterpret_cast<float*>(smem + C::RED_OFF);
+      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+      float dsk = 0.f;
+      if (lane_on) {
+        for (int j = warp; j < ecount; j += NWARPS) {
+          const int64_t r = (int64_t)tile * TM + j;
+          float4 dh = ld4(y_s + j * CHP + c);
+          if (EPI == EPI_INIT_BWD) add4(dh, ld4(r_s + j * CH + c));
+          const uint2 mh = __ldg(reinterpret_cast<const uint2*>(p.mask_hi + r * p.ld_mask + n));
+          const __half2 m01 = *reinterpret_cast<const __half2*>(&mh.x), m23 = *reinterpret_cast<const __half2*>(&mh.y);
+          const float2 f01 = __half22float2(m01), f23 = __half22float2(m23);
+          float4 dz;
+          dz.x = f01.x > 0.f ? dh.x * p.keep_scale : 0.f;
+          dz.y = f01.y > 0.f ? dh.y * p.keep_scale : 0.f;
+          dz.z = f23.x > 0.f ? dh.z * p.keep_scale : 0.f;
+          dz.w = f23.y > 0.f ? dh.w * p.keep_scale : 0.f;
+          *reinterpret_cast<float4*>(y_s + j * CHP + c) = dz;
+          add4(csum, dz);
+          if (EPI == EPI_BOND_BWD) {
+            if (p.dskip_partial) {
+              const float4 h0v = ld4(r_s + j * CH + c);
+              dsk = fmaf(dz.x, h0v.x, fmaf(dz.y, h0v.y, fmaf(dz.z, h0v.z, fmaf(dz.w, h0v.w, dsk))));
+            }
+            float4* acc0 = reinterpret_cast<float4*>(p.dh0_acc + r * H + n);
+            float4 a0 = p.dh0_first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(acc0);   // written by the previous kernel: bypass L1
+            a0.x = fmaf(skip, dz.x, a0.x); a0.y = fmaf(skip, dz.y, a0.y);
+            a0.z = fmaf(skip, dz.z, a0.z); a0.w = fmaf(skip, dz.w, a0.w);
+            *acc0 = a0;
+          } else {
+            *reinterpret_cast<float4*>(p.dz0_out + (int64_t)(ebase + j) * H + n) = dz;
+          }
+        }
+      }
+      if (lane < VL) *reinterpret_cast<float4*>(red_s + warp * CH + c) = csum;
+      if (EPI == EPI_BOND_BWD && p.dskip_partial) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsk += __shfl_xor_sync(0xffffffffu, dsk, o);
+        if (lane == 0) aux->red2[warp] = dsk;
+      }
+      __syncthreads();
+      if (threadIdx.x < CH) {                                      // fixed warp order: deterministic
+        const int col = n0 + ch * CH + threadIdx.x;
+        if (col < p.n_total) {
+          float sres = 0.f;
+          for (int w = 0; w < NWARPS; ++w) sres += red_s[w * CH + threadIdx.x];
+          p.colsum_partial[(int64_t)tile * H + col] = sres;
+        }
+      }
+      if (EPI == EPI_BOND_BWD && p.dskip_partial && threadIdx.x == 0) {
+        float sres = 0.f;
+        for (int w = 0; w < NWARPS; ++w) sres += aux->red2[w];
+        p.dskip_partial[((int64_t)tile * gridDim.x + slice) * NCH + ch] = sres;
+      }
+      float vmax = 0.f;
+      const int nrows = EPI == EPI_BOND_BWD ? ecount : acount;
+      for (int j0 = warp * RU; j0 < nrows; j0 += NWARPS * RU) {
+        float4 acc[RU];
+        if (lane_on) {
+          nbr_sum<CHP>(y_s, aux, j0, nrows, c, acc);
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            const int j = j0 + u;
+            if (j >= nrows) break;
+            float4 g = acc[u];
+            int64_t orow;
+            if (EPI == EPI_BOND_BWD) {
+              const float4 yr = ld4(y_s + (j ^ 1) * CHP + c);
+              g.x -= yr.x; g.y -= yr.y; g.z -= yr.z; g.w -= yr.w;
+              orow = (int64_t)tile * TM + j;
+            } else {
+              orow = abase + j;
+            }
+            vmax = fmaxf(vmax, amax4(g));
+            store_split4(g, out_scale, p.o_hi + orow * p.ldo + n, p.o_lo + orow * p.ldo + n);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (lane == 0 && vmax > 0.f) atomicMax(p.gamax_track, __float_as_uint(vmax));   // max is order-independent
+      ovf |= vmax * out_scale > 60000.f;
     } else {
       // readout: hv[v] = act(Q[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
       const int acount = aux->info[3];
@@ -487,10 +673,14 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
           }
 #pragma unroll
           for (int u = 0; u < RU; ++u) {
-            t[u] = act_t<RELU>(acc[u].x, p.act) * wf4.x;
-            t[u] = fmaf(act_t<RELU>(acc[u].y, p.act), wf4.y, t[u]);
-            t[u] = fmaf(act_t<RELU>(acc[u].z, p.act), wf4.z, t[u]);
-            t[u] = fmaf(act_t<RELU>(acc[u].w, p.act), wf4.w, t[u]);
+            const float4 hv = make_float4(act_t<RELU>(acc[u].x, p.act), act_t<RELU>(acc[u].y, p.act),
+                                          act_t<RELU>(acc[u].z, p.act), act_t<RELU>(acc[u].w, p.act));
+            t[u] = hv.x * wf4.x;
+            t[u] = fmaf(hv.y, wf4.y, t[u]);
+            t[u] = fmaf(hv.z, wf4.z, t[u]);
+            t[u] = fmaf(hv.w, wf4.w, t[u]);
+            if (p.hv_out && v0 + u < acount)
+              *reinterpret_cast<float4*>(p.hv_out + (int64_t)(aux->info[2] + v0 + u) * p.n_total + n) = hv;
           }
         }
 #pragma unroll
@@ -507,7 +697,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
     }
   }
 
-  if (EPI == EPI_BOND && ovf) atomicOr(p.overflow, 1);
+  if ((EPI == EPI_BOND || BWD) && ovf) atomicOr(p.overflow, 1);
   if (EPI == EPI_READOUT) {
     __syncthreads();
     const int abase = aux->info[2], rx0 = aux->info[4], rxcount = aux->info[5];

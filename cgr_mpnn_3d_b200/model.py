@@ -128,7 +128,7 @@ class GNN(nn.Module):
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
         can_tc = self.depth <= 13
-        if e in ("tc", 1) and not can_tc:
+        if e in ("tc", "tc_layerwise", 1) and not can_tc:
             raise RuntimeError("engine='tc' supports depth <= 13")
         return _lib.ENGINE_TC if can_tc else _lib.ENGINE_SIMT
 
@@ -190,8 +190,14 @@ class GNN(nn.Module):
         train_flag = needs_grad or any(p > 0 for p in dps)
         engine = self._engine_id(plan, train_flag)
         empty_i = torch.empty(0, dtype=torch.int32, device=dev)
+        fused_train = False
         if engine == _lib.ENGINE_TC:
-            if train_flag or not self._fused_ok(plan):   # layer-wise path with tensor-core GEMMs: no tile plan needed
+            # training with the tile-local fused kernels: ReLU networks on tileable batches
+            fused_train = bool(train_flag and getattr(self, "engine", "auto") != "tc_layerwise"
+                               and _act_id(self.activation_fn) == 0 and self.hidden_sizes[0] <= 1024
+                               and self.depth <= 12 and self._fused_ok(plan))
+            if (train_flag and not fused_train) or not self._fused_ok(plan):
+                # layer-wise path with tensor-core GEMMs: no tile plan needed
                 tile_info, n_tiles = empty_i, 0
                 if plan.tc_status is None:
                     plan.tc_status = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -213,9 +219,10 @@ class GNN(nn.Module):
         res = ops.gnn_forward(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr, params,
                               self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
                               train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo,
-                              getattr(self, "tile_policy", "latency") == "throughput")
+                              getattr(self, "tile_policy", "latency") == "throughput", fused_train)
         self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and n_tiles > 0) else None
         self.__dict__["_last_engine"] = engine
+        self.__dict__["_last_fused_train"] = fused_train
         out = res[0]
         if caller_device != dev:
             out = out.to(caller_device)
@@ -426,6 +433,7 @@ class GNN(nn.Module):
         state.pop("_host_slots", None)
         state.pop("_host_ctx_cache", None)
         state.pop("_last_plan", None)
+        state.pop("_last_fused_train", None)
         return state
 
 

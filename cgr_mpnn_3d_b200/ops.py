@@ -88,8 +88,10 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
                 atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
                 dropout_ps: Sequence[float], training: bool, seed: int, engine: int, tile_info: Tensor,
                 n_tiles: int, tc_status: Tensor, tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor,
-                tc_throughput: bool) -> List[Tensor]:
-    """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled]`` (saved tensors are empty in eval).
+                tc_throughput: bool, fused_train: bool) -> List[Tensor]:
+    """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled, tc_blob]`` (saved tensors are empty in eval).
+    ``fused_train``: training on the tcgen05 engine with the tile-local fused kernels -- everything the backward
+    needs lives in ``tc_blob`` and the layer-wise buffers stay empty.
 
     ``tile_info`` / ``n_tiles`` / ``tc_status`` / ``tc_weights`` feed the tcgen05 engine (empty tensors
     when unused)."""
@@ -107,7 +109,17 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
     n, e, b = g.n_atoms, g.n_bonds, g.n_rxn
     f32 = dict(dtype=torch.float32, device=x.device)
     out = torch.empty(b, **f32)
-    if training:
+    tc_blob = torch.empty(0, dtype=torch.uint8, device=x.device)
+    if training and fused_train:
+        with torch.cuda.device(x.device):
+            blob_bytes = int(lib.cgr_tc_saved_bytes(C.byref(ctx.params), C.byref(g)))
+        if blob_bytes <= 0:
+            raise RuntimeError("fused tcgen05 training is not available for this configuration")
+        tc_blob = torch.empty(blob_bytes, dtype=torch.uint8, device=x.device)
+        h_all, m_all, z_all, s, hv, zv, pooled = (torch.empty(0, **f32) for _ in range(7))
+        saved = _lib.CgrSaved(tc_blob=tc_blob.data_ptr(), tc_blob_bytes=blob_bytes)
+        saved_p = C.byref(saved)
+    elif training:
         h_all = torch.empty((depth + 1, e, H), **f32)
         m_all = torch.empty((depth, e, H), **f32)
         need_z = act != 0
@@ -129,27 +141,34 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
         _lib.check(lib.cgr_gnn_forward(C.byref(ctx.params), C.byref(g), out.data_ptr(), saved_p, int(training),
                                        seed & 0xFFFFFFFFFFFFFFFF, engine, ws.data_ptr(), ws_bytes, _stream()),
                    "cgr_gnn_forward")
-    return [out, h_all, m_all, z_all, s, hv, zv, pooled]
+    return [out, h_all, m_all, z_all, s, hv, zv, pooled, tc_blob]
 
 
 @gnn_forward.register_fake
 def _(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-      engine, tile_info, n_tiles, tc_status, tc_weights, x_hi, x_lo, tc_throughput):
+      engine, tile_info, n_tiles, tc_status, tc_weights, x_hi, x_lo, tc_throughput, fused_train):
     H = params[0].shape[0]
     n, e, b = x.shape[0], src.shape[0], atom_ptr.shape[0] - 1
     mk = lambda *s: x.new_empty(s, dtype=torch.float32)
+    blob = x.new_empty((0,), dtype=torch.uint8)
     if not training:
-        return [mk(b)] + [mk(0) for _ in range(7)]
+        return [mk(b)] + [mk(0) for _ in range(7)] + [blob]
+    if fused_train:
+        kp = (H + 63) // 64 * 64
+        rows = int(n_tiles) * 128
+        return [mk(b)] + [mk(0) for _ in range(7)] + [
+            x.new_empty((2 * (depth + 1) * rows * kp * 2 + rows * H * 4 + n * H * 4 + 4096 * (2 * depth + 6),),
+                        dtype=torch.uint8)]
     need_z = act != 0
     return [mk(b), mk(depth + 1, e, H), mk(depth, e, H), mk(depth + 1, e, H) if need_z else mk(0), mk(n, H),
-            mk(n, H), mk(n, H) if need_z else mk(0), mk(b, H)]
+            mk(n, H), mk(n, H) if need_z else mk(0), mk(b, H), blob]
 
 
 @torch.library.custom_op("cgr_b200::gnn_backward", mutates_args=())
 def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor,
                  in_idx: Tensor, atom_ptr: Tensor, params: Sequence[Tensor], saved: Sequence[Tensor], depth: int,
                  act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int, tc_weights: Tensor,
-                 x_hi: Tensor, x_lo: Tensor) -> List[Tensor]:
+                 x_hi: Tensor, x_lo: Tensor, tile_info: Tensor, n_tiles: int, tc_status: Tensor) -> List[Tensor]:
     """Explicit backward: gradients of every parameter, in parameter-list order."""
     _require_cuda(grad_out, x, *params)
     lib = _lib.load()
@@ -160,12 +179,16 @@ def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, ds
     ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
     if tc_weights.numel() > 0:
         ctx.params.tc_weights = tc_weights.data_ptr()
-    g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, None, 0, None, x_hi, x_lo)
-    h_all, m_all, z_all, s, hv, zv, pooled = saved
+    h_all, m_all, z_all, s, hv, zv, pooled, tc_blob = saved
     need_z = act != 0
-    sv = _lib.CgrSaved(h_all=h_all.data_ptr(), m_all=m_all.data_ptr(), z_all=z_all.data_ptr() if need_z else None,
-                       s=s.data_ptr(), hv=hv.data_ptr(), zv=zv.data_ptr() if need_z else None,
-                       pooled=pooled.data_ptr())
+    if tc_blob.numel() > 0:          # fused tile-local backward of the tcgen05 engine
+        g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info, n_tiles, tc_status, x_hi, x_lo)
+        sv = _lib.CgrSaved(tc_blob=tc_blob.data_ptr(), tc_blob_bytes=tc_blob.numel())
+    else:
+        g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, None, 0, None, x_hi, x_lo)
+        sv = _lib.CgrSaved(h_all=h_all.data_ptr(), m_all=m_all.data_ptr(),
+                           z_all=z_all.data_ptr() if need_z else None, s=s.data_ptr(), hv=hv.data_ptr(),
+                           zv=zv.data_ptr() if need_z else None, pooled=pooled.data_ptr())
     grads = [torch.empty_like(p) for p in params]
     gw_init, gb_init, gw_conv, gb_conv, gw_e2n, gb_e2n, gw_ffn, gb_ffn, gskip = _unpack(grads, depth, use_skip)
     wc, bc = _lib.ptr_array(gw_conv), _lib.ptr_array(gb_conv)
@@ -185,36 +208,36 @@ def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, ds
 
 @gnn_backward.register_fake
 def _(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip, dropout_ps,
-      seed, engine, tc_weights, x_hi, x_lo):
+      seed, engine, tc_weights, x_hi, x_lo, tile_info, n_tiles, tc_status):
     return [torch.empty_like(p) for p in params]
 
 
 def _setup_context(ctx, inputs, output):
     (x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps, training, seed,
-     engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo, _tp) = inputs
-    ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine)
+     engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo, _tp, _fused) = inputs
+    ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine, int(_n_tiles))
     ctx.n_params = len(params)
     ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:], _tc_weights, _x_hi,
-                          _x_lo)
+                          _x_lo, _tile_info, _tc_status)
 
 
 def _backward(ctx, grads):
-    depth, act, use_skip, dropout_ps, training, seed, engine = ctx.cfg
+    depth, act, use_skip, dropout_ps, training, seed, engine, n_tiles = ctx.cfg
     if not training:
         raise RuntimeError("cgr_b200::gnn_forward was run with training=False; no activations were saved "
                            "(call model.train() before a forward that needs gradients)")
     t = ctx.saved_tensors
     x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr = t[:7]
     params = list(t[7:7 + ctx.n_params])
-    saved = list(t[7 + ctx.n_params:-3])
-    tc_weights, x_hi, x_lo = t[-3:]
+    saved = list(t[7 + ctx.n_params:-5])
+    tc_weights, x_hi, x_lo, tile_info, tc_status = t[-5:]
     g_out = grads[0]
     if g_out is None:
         g_out = torch.zeros(atom_ptr.shape[0] - 1, dtype=torch.float32, device=x.device)
     pg = gnn_backward(g_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act, use_skip,
-                      dropout_ps, seed, engine, tc_weights, x_hi, x_lo)
+                      dropout_ps, seed, engine, tc_weights, x_hi, x_lo, tile_info, n_tiles, tc_status)
     return (None, None, None, None, None, None, None, pg, None, None, None, None, None, None, None, None, None,
-            None, None, None, None, None)
+            None, None, None, None, None, None)
 
 
 gnn_forward.register_autograd(_backward, setup_context=_setup_context)

@@ -105,6 +105,10 @@ typedef struct cgr_saved {
   float* hv;        /* [N, H]  atom hidden states (GNN.py:107)                             */
   float* zv;        /* [N, H]  their pre-activations, only for act != relu, else NULL      */
   float* pooled;    /* [B, H]  per-reaction sums (GNN.py:110)                              */
+  void* tc_blob;    /* tcgen05 fused training path: ONE buffer of cgr_tc_saved_bytes() bytes that replaces all of
+                       the above (they may be NULL): per-layer FP16 (hi, lo) operands, h_0 and hv.  NULL selects
+                       the layer-wise path. */
+  size_t tc_blob_bytes;
 } cgr_saved_t;
 
 /* ------------------------------------------------------------------------------------------
@@ -266,6 +270,11 @@ typedef struct {
 int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_host_batch_t* batches, int32_t n_batches,
                                    float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
                                    size_t host_bytes, void* stream);
+
+/* Bytes of cgr_saved_t.tc_blob for the fused tile-local training path of the tcgen05 engine, or 0 when the
+ * configuration cannot use it (needs ReLU, a tile plan in `g`, hidden % 4 == 0 and <= 1024): then leave tc_blob
+ * NULL and provide the layer-wise buffers. */
+size_t cgr_tc_saved_bytes(const cgr_params_t* p, const cgr_graph_t* g);
 
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 EA_TOL = 1e-4      # north_star: per-reaction Ea within 1e-4 relative (fp32 / split-precision mode)
 GRAD_TOL = 1e-4
 
-ENGINES = ["simt", "tc"]
+ENGINES = ["simt", "tc", "tc_layerwise"]     # tc trains with the fused tile-local kernels when it can
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -158,6 +158,8 @@ def test_golden_forward_backward(name, engine):
     model.validate_inputs = True
     out = model(data)
     assert out.shape == tuple(z["out"].shape) and out.dtype == torch.float32 and out.is_cuda
+    # engine tc trains ReLU networks with the fused tile-local kernels, everything else layer-wise
+    assert model.__dict__["_last_fused_train"] == (engine == "tc" and meta["act"] == "relu" and meta["hidden"] % 4 == 0)
     ref = torch.from_numpy(z["out"])
     assert scale_normalised_error(out, ref) < EA_TOL
     loss = mse_sum_loss(out, data.y)
@@ -176,6 +178,7 @@ def test_baseline_configs_forward_backward(name, engine):
     data_cpu = case_batch(z, meta)
     model = build_model(meta, engine=engine).train()
     out = model(data_cpu.to("cuda"))
+    assert model.__dict__["_last_fused_train"] == (engine == "tc")
     assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL
     mse_sum_loss(out, data_cpu.y.cuda()).backward()
     # Gradients are compared with an fp64 evaluation of the same graph.  ReLU makes the gradient
@@ -260,7 +263,7 @@ def test_dropout_replay_against_oracle():
                           torch.empty(0, dtype=torch.int32, device="cuda"),
                           torch.empty(0, dtype=torch.uint8, device="cuda"),
                           torch.empty(0, dtype=torch.float16, device="cuda"),
-                          torch.empty(0, dtype=torch.float16, device="cuda"), False)
+                          torch.empty(0, dtype=torch.float16, device="cuda"), False, False)
     out = res[0]
     masks = [stage_ops.dropout_mask(seed, l, p, d.num_edges, meta["hidden"], "cuda").cpu()
              for l in range(meta["depth"])]
