@@ -441,7 +441,7 @@ def main():
         n_t = min(args.steps, 100)
 
         def train_step(d):
-            loss = ((tm(d) - d.y) ** 2).sum()
+            loss = torch.nn.functional.mse_loss(tm(d), d.y, reduction="sum")      # train.py:120
             loss.backward()
 
         # whole-step CUDA graphs (one per resident batch): the step is launch-bound when issued eagerly

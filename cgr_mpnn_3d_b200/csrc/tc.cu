@@ -15,6 +15,7 @@
 #include "tc.cuh"
 
 #include <math.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -152,13 +153,20 @@ struct PrepArgs {
 
 __global__ void __launch_bounds__(256) prep_amax_kernel(const PrepArgs a) {
   const Seg s = a.seg[blockIdx.y];
-  const int64_t total = (int64_t)s.rows * s.cols;
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(__ldg(s.src + (i / s.cols) * s.ld + (i % s.cols))));
+  for (int r = blockIdx.x; r < s.rows; r += gridDim.x) {          // rows over blocks, columns over threads: coalesced
+    const float* row = s.src + (int64_t)r * s.ld;
+    for (int c = threadIdx.x; c < s.cols; c += 256) m = fmaxf(m, fabsf(__ldg(row + c)));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(a.amax_bits + s.mat, __float_as_uint(m));   // max is order-independent
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+    atomicMax(a.amax_bits + s.mat, __float_as_uint(m));            // max is order-independent
+  }
 }
 
 __device__ __forceinline__ float weight_scale(float amax) {
@@ -166,23 +174,44 @@ __device__ __forceinline__ float weight_scale(float amax) {
   return exp2f(13.f - ceilf(log2f(amax)));        // amax * scale in (2^12, 2^13]
 }
 
+// 32 x 32 element tiles: rows are read and written coalesced; the transposed copy goes through shared memory
 __global__ void __launch_bounds__(256) prep_split_kernel(const PrepArgs a) {
+  __shared__ __half th[32][34], tl[32][34];
   const Seg s = a.seg[blockIdx.y];
   const float sc = weight_scale(__uint_as_float(a.amax_bits[s.mat]));
   if (blockIdx.x == 0 && threadIdx.x == 0 && s.row0 == 0) a.unscale[s.mat] = 1.f / sc;
-  const int64_t total = (int64_t)s.rows * s.cols;
   __half* hi = a.hi[s.mat];
   __half* lo = a.lo[s.mat];
+  __half* hiT = a.hiT[s.mat];
+  __half* loT = a.loT[s.mat];
   const int64_t ldo = a.ldo[s.mat];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / s.cols, c = i % s.cols;
-    __half h, l;
-    split_f16(__ldg(s.src + r * s.ld + c) * sc, h, l);
-    hi[(s.row0 + r) * ldo + c] = h;
-    lo[(s.row0 + r) * ldo + c] = l;
-    if (a.hiT[s.mat]) {
-      a.hiT[s.mat][c * ldo + s.row0 + r] = h;
-      a.loT[s.mat][c * ldo + s.row0 + r] = l;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tiles_c = (s.cols + 31) / 32, tiles = ((s.rows + 31) / 32) * tiles_c;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      __half h = __float2half_rn(0.f), l = h;
+      if (r < s.rows && c < s.cols) {
+        split_f16(__ldg(s.src + (int64_t)r * s.ld + c) * sc, h, l);
+        hi[(s.row0 + r) * ldo + c] = h;
+        lo[(s.row0 + r) * ldo + c] = l;
+      }
+      th[ty + 8 * i][tx] = h;
+      tl[ty + 8 * i][tx] = l;
+    }
+    if (hiT) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;                // T[c][row0 + r] = M[r][c]
+        if (r < s.rows && c < s.cols) {
+          hiT[(int64_t)c * ldo + s.row0 + r] = th[tx][ty + 8 * i];
+          loT[(int64_t)c * ldo + s.row0 + r] = tl[tx][ty + 8 * i];
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -437,8 +466,8 @@ int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cud
   CgrRange prof("tc_prep_weights", st);
   cgr_note_launch("tc_prep_weights", st, 3);
   CGR_CUDA(cudaMemsetAsync(a.amax_bits, 0, MAX_SEG * sizeof(unsigned int), st));
-  prep_amax_kernel<<<dim3(64, (unsigned)ns), 256, 0, st>>>(a);
-  prep_split_kernel<<<dim3(64, (unsigned)ns), 256, 0, st>>>(a);
+  prep_amax_kernel<<<dim3(48, (unsigned)ns), 256, 0, st>>>(a);
+  prep_split_kernel<<<dim3(96, (unsigned)ns), 256, 0, st>>>(a);
   concat_bias_kernel<<<(unsigned)cgr_ceil_div(H, 256), 256, 0, st>>>(p->b_init, p->b_e2n, H, (float*)(b + w.off_bias));
   if (fb > 0)
     transpose_we_kernel<<<(unsigned)cgr_ceil_div((int64_t)fb * H, 256), 256, 0, st>>>(p->w_init, fa, fb, H,
@@ -720,6 +749,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
 namespace {
 
 constexpr int BWD_THREADS = 256;
+constexpr int RB_PARTS = 8;          // blocks per tile in the readout backward
 
 // gamax[0] = max|dout| * max|w_f| (bound on |dq|), gamax[1..] = 0;  db_f = sum_b dout[b]
 __global__ void __launch_bounds__(BWD_THREADS) bwd_prep_kernel(const float* __restrict__ dout, int64_t B,
@@ -758,7 +788,7 @@ __global__ void __launch_bounds__(BWD_THREADS) bwd_prep_kernel(const float* __re
   for (int i = 1 + threadIdx.x; i < n_gamax; i += BWD_THREADS) gamax[i] = 0u;
 }
 
-// Readout backward, one block per tile:  dzv[v] = dout[rxn(v)] . w_f . [hv[v] > 0]  (atoms of the tile),
+// Readout backward, RB_PARTS blocks per tile (rows interleaved over the blocks):  dzv[v] = dout[rxn(v)] . w_f . [hv[v] > 0]  (atoms of the tile),
 // dq[k] = dzv[dst k] (bonds of the tile, tile-packed), both as scaled FP16 (hi, lo) operands; per-tile column sums
 // of dzv (db_o) and of dout . hv (dw_f).
 __global__ void __launch_bounds__(BWD_THREADS) readout_bwd_kernel(
@@ -769,24 +799,26 @@ __global__ void __launch_bounds__(BWD_THREADS) readout_bwd_kernel(
     unsigned int* __restrict__ gamax, float* __restrict__ gunscale) {
   extern __shared__ __align__(16) float rb_smem[];          // [8][H] cross-warp reduction scratch
   __shared__ float dpl[TM];
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.y, part = blockIdx.x;
   const int ebase = __ldg(tile_info + tile * 8), ecount = __ldg(tile_info + tile * 8 + 1);
   const int abase = __ldg(tile_info + tile * 8 + 2), acount = __ldg(tile_info + tile * 8 + 3);
   const int rx0 = __ldg(tile_info + tile * 8 + 4), rxcount = __ldg(tile_info + tile * 8 + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ROW_STEP = RB_PARTS * (BWD_THREADS / 32);
+  const int row_first = part + RB_PARTS * warp;              // this warp's rows: row_first, + ROW_STEP, ...
   for (int rx = threadIdx.x; rx < rxcount; rx += BWD_THREADS) {
     const float d = __ldg(dout + rx0 + rx);
     const int v0 = __ldg(atom_ptr + rx0 + rx) - abase, v1 = __ldg(atom_ptr + rx0 + rx + 1) - abase;
     for (int v = v0; v < v1; ++v) dpl[v] = d;
   }
   const float S0 = tcg::grad_scale(gamax[0]);
-  if (tile == 0 && threadIdx.x == 0) gunscale[0] = 1.f / S0;
+  if (tile == 0 && part == 0 && threadIdx.x == 0) gunscale[0] = 1.f / S0;
   __syncthreads();
   constexpr int NG = 8;                                      // column groups of 128: H <= 1024
   float4 csum[NG], wsum[NG];
 #pragma unroll
   for (int q = 0; q < NG; ++q) csum[q] = wsum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int v = warp; v < acount; v += BWD_THREADS / 32) {
+  for (int v = row_first; v < acount; v += ROW_STEP) {
     const float d = dpl[v];
     const int64_t row = abase + v;
 #pragma unroll
@@ -816,12 +848,12 @@ __global__ void __launch_bounds__(BWD_THREADS) readout_bwd_kernel(
     for (int n = threadIdx.x; n < H; n += BWD_THREADS) {
       float t = 0.f;
       for (int w = 0; w < BWD_THREADS / 32; ++w) t += rb_smem[w * H + n];
-      outp[(int64_t)tile * H + n] = t;
+      outp[((int64_t)tile * RB_PARTS + part) * H + n] = t;
     }
     __syncthreads();
   }
   float vmax = 0.f;
-  for (int j = warp; j < ecount; j += BWD_THREADS / 32) {
+  for (int j = row_first; j < ecount; j += ROW_STEP) {
     const int v = __ldg(dst + ebase + j) - abase;
     const float d = dpl[v];
     const int64_t row = abase + v, orow = (int64_t)tile * TM + j;
@@ -844,6 +876,7 @@ __global__ void __launch_bounds__(BWD_THREADS) readout_bwd_kernel(
 struct BwdFinalizeArgs {
   const float* col_src[MAX_SEG + 2];
   float* col_dst[MAX_SEG + 2];
+  int col_rows[MAX_SEG + 2];
   int n_col;
   const float* skip_src[MAX_SEG];
   float* skip_dst[MAX_SEG];
@@ -853,12 +886,22 @@ struct BwdFinalizeArgs {
 };
 __global__ void __launch_bounds__(256) bwd_finalize_kernel(const BwdFinalizeArgs a) {
   if ((int)blockIdx.y < a.n_col) {
-    const int n = blockIdx.x * 256 + threadIdx.x;
-    if (n >= a.H) return;
+    // 32 columns per block; 8 row lanes stride over the partial rows, then a fixed-order combine: deterministic
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + cx;
     const float* src = a.col_src[blockIdx.y];
+    const int rows = a.col_rows[blockIdx.y];
     float t = 0.f;
-    for (int i = 0; i < a.T; ++i) t += __ldg(src + (int64_t)i * a.H + n);
-    a.col_dst[blockIdx.y][n] = t;
+    if (n < a.H)
+      for (int i = ry; i < rows; i += 8) t += __ldg(src + (int64_t)i * a.H + n);
+    red[ry][cx] = t;
+    __syncthreads();
+    if (ry == 0 && n < a.H) {
+      float sres = 0.f;
+      for (int w = 0; w < 8; ++w) sres += red[w][cx];
+      a.col_dst[blockIdx.y][n] = sres;
+    }
   } else if (blockIdx.x == 0 && threadIdx.x < 32) {
     const int k = blockIdx.y - a.n_col;
     const float* src = a.skip_src[k];
@@ -898,19 +941,19 @@ TcBwdWs tc_bwd_ws(const cgr_params_t* p, const cgr_graph_t* g) {
   w.off_dp_lo = take((size_t)N * w.kp_h * sizeof(__half));
   w.off_dh0 = take((size_t)w.rows_pad * H * sizeof(float));
   w.off_dz0 = take((size_t)E * H * sizeof(float));
-  w.off_col = take((size_t)(d + 2) * T * H * sizeof(float));
-  w.off_dwf = take((size_t)T * H * sizeof(float));
+  w.off_col = take((size_t)(d + 1 + RB_PARTS) * T * H * sizeof(float));   // db_o [T*RB_PARTS][H], then d+1 arrays [T][H]
+  w.off_dwf = take((size_t)T * RB_PARTS * H * sizeof(float));
   w.skip_cnt = (size_t)T * w.n_slices * 2;
   w.off_skip = take((size_t)d * w.skip_cnt * sizeof(float));
   w.off_gamax = take(MAX_SEG * 2 * sizeof(unsigned int));
   w.off_gunscale = take(MAX_SEG * 2 * sizeof(float));
   size_t pf = 0;
-  auto upd = [&](int64_t M_, int64_t N_, int64_t K_) {
-    const int sk = tc_splitk_choose(M_, N_, K_);
-    if (sk > 1) { const size_t f = (size_t)sk * M_ * N_; if (f > pf) pf = f; }
+  auto upd = [&](int n_, int64_t M_, int64_t N_, int64_t K_) {       // batched weight-gradient GEMMs
+    const size_t f = (size_t)n_ * tc_splitk_choose(M_, N_, K_) * M_ * N_;
+    if (f > pf) pf = f;
   };
-  upd(H, H, w.rows_pad);
-  upd(H, p->fa, N);
+  upd(d + 1, H, H, w.rows_pad);
+  upd(2, H, p->fa, N);
   const int ssk = simt_splitk_choose(H, p->fb > 0 ? p->fb : 1, E);
   if (ssk > 1 && (size_t)ssk * H * p->fb > pf) pf = (size_t)ssk * H * p->fb;
   w.partial_floats = pf;
@@ -990,7 +1033,7 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
       CGR_CUDA(cudaFuncSetAttribute(readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
       attr = true;
     }
-    readout_bwd_kernel<<<(unsigned)T, BWD_THREADS, (size_t)8 * H * sizeof(float), st>>>(
+    readout_bwd_kernel<<<dim3(RB_PARTS, (unsigned)T), BWD_THREADS, (size_t)8 * H * sizeof(float), st>>>(
         dout, hv, p->w_ffn, g->tile_info, g->atom_ptr, g->dst, H, w.kp_h, dzv_hi, dzv_lo, g_hi(0), g_lo(0), col, dwf,
         gamax, gunscale);
     CGR_LAUNCH_CHECK();
@@ -1019,7 +1062,7 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     const float pd = p->host_dropout_p ? p->host_dropout_p[l - 1] : 0.f;
     prm.keep_scale = pd > 0.f ? 1.f / (1.f - pd) : 1.f;
     prm.dh0_acc = dh0; prm.dh0_first = i == 0 ? 1 : 0;
-    prm.colsum_partial = col + (size_t)(1 + i) * T * H;
+    prm.colsum_partial = col + (size_t)(RB_PARTS + i) * T * H;
     prm.dskip_partial = p->use_skip ? skp + (size_t)i * w.skip_cnt : nullptr;
     prm.gamax_in = gamax + i; prm.gamax_out = gamax + i + 1; prm.gamax_track = gamax + i + 2;
     prm.gunscale_out = gunscale + i + 1;
@@ -1047,7 +1090,7 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     prm.act = p->act;
     prm.mask_hi = h_hi(0); prm.ld_mask = w.kp_h;
     prm.keep_scale = 1.f;
-    prm.colsum_partial = col + (size_t)(d + 1) * T * H;
+    prm.colsum_partial = col + (size_t)(RB_PARTS + d) * T * H;
     prm.gamax_in = gamax + d; prm.gamax_out = gamax + d + 1; prm.gamax_track = gamax + d + 2;
     prm.gunscale_out = gunscale + d + 1;
     prm.o_hi = dp_hi; prm.o_lo = dp_lo; prm.ldo = w.kp_h;
@@ -1056,29 +1099,40 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     rc = launch_gemm<EPI_INIT_BWD>(prm, bn_h, (int)T, true, "bwd_edge_init", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
   }
-  // weight gradients: reductions over bonds / atoms (K = rows) on tensor cores, deterministic split-K
-  GemmEpilogue none;
-  auto wgrad = [&](const __half* ahi, const __half* alo, int64_t lda, const float* aus, const __half* bhi,
-                   const __half* blo, int64_t ldb, int64_t M_, int64_t N_, int64_t K_, float* C, int64_t ldc,
-                   const char* tag) {
-    TcOperand A{ahi, alo, lda, aus, true}, Bo{bhi, blo, ldb, nullptr, true};
-    GemmEpilogue e = none;
-    e.tag = tag;
-    return tc_train_gemm(A, Bo, M_, N_, K_, C, ldc, e, tc_splitk_choose(M_, N_, K_), partial, st);
-  };
-  // dW_os = dq^T h_d ;  dW_l = dy_l^T h_{l-1}
-  if ((rc = wgrad(g_hi(0), g_lo(0), w.kp_h, gunscale + 0, h_hi(d), h_lo(d), w.kp_h, H, H, w.rows_pad,
-                  grads->w_e2n + fa, fa + H, "wgrad_readout_s"))) return rc;
-  for (int l = 1; l <= d; ++l) {
-    const int i = d + 1 - l;
-    if ((rc = wgrad(g_hi(i), g_lo(i), w.kp_h, gunscale + i, h_hi(l - 1), h_lo(l - 1), w.kp_h, H, H, w.rows_pad,
-                    grads->w_conv[l - 1], H, "wgrad_bond"))) return rc;
+  // weight gradients: reductions over bonds / atoms (K = rows) on tensor cores, deterministic split-K; all GEMMs of
+  // one shape share a launch
+  {
+    TcOperand A[tcg2::MAX_BATCH], Bo[tcg2::MAX_BATCH];
+    float* C[tcg2::MAX_BATCH];
+    int64_t ldc[tcg2::MAX_BATCH];
+    int n = 0;
+    auto flush = [&](int64_t M_, int64_t N_, int64_t K_, const char* tag) {
+      if (n == 0) return (int)CGR_OK;
+      const int r = tc_train_gemm_batched_mn(A, Bo, C, ldc, n, M_, N_, K_, tc_splitk_choose(M_, N_, K_), partial, tag, st);
+      n = 0;
+      return r;
+    };
+    // dW_os = dq^T h_d ;  dW_l = dy_l^T h_{l-1}
+    A[n] = TcOperand{g_hi(0), g_lo(0), w.kp_h, gunscale + 0, true};
+    Bo[n] = TcOperand{h_hi(d), h_lo(d), w.kp_h, nullptr, true};
+    C[n] = grads->w_e2n + fa; ldc[n] = fa + H; ++n;
+    for (int l = 1; l <= d; ++l) {
+      if (n == tcg2::MAX_BATCH && (rc = flush(H, H, w.rows_pad, "wgrad_bond"))) return rc;
+      const int i = d + 1 - l;
+      A[n] = TcOperand{g_hi(i), g_lo(i), w.kp_h, gunscale + i, true};
+      Bo[n] = TcOperand{h_hi(l - 1), h_lo(l - 1), w.kp_h, nullptr, true};
+      C[n] = grads->w_conv[l - 1]; ldc[n] = H; ++n;
+    }
+    if ((rc = flush(H, H, w.rows_pad, "wgrad_bond"))) return rc;
+    // dW_ox = dzv^T x ;  dW_x = dP^T x
+    A[n] = TcOperand{dzv_hi, dzv_lo, w.kp_h, gunscale + 0, true};
+    Bo[n] = TcOperand{x_hi, x_lo, w.kp_x, nullptr, true};
+    C[n] = grads->w_e2n; ldc[n] = fa + H; ++n;
+    A[n] = TcOperand{dp_hi, dp_lo, w.kp_h, gunscale + d + 1, true};
+    Bo[n] = TcOperand{x_hi, x_lo, w.kp_x, nullptr, true};
+    C[n] = grads->w_init; ldc[n] = fa + fb; ++n;
+    if ((rc = flush(H, fa, N, "wgrad_atoms"))) return rc;
   }
-  // dW_ox = dzv^T x ;  dW_x = dP^T x
-  if ((rc = wgrad(dzv_hi, dzv_lo, w.kp_h, gunscale + 0, x_hi, x_lo, w.kp_x, H, fa, N, grads->w_e2n, fa + H,
-                  "wgrad_readout_x"))) return rc;
-  if ((rc = wgrad(dp_hi, dp_lo, w.kp_h, gunscale + d + 1, x_hi, x_lo, w.kp_x, H, fa, N, grads->w_init, fa + fb,
-                  "wgrad_init_x"))) return rc;
   if (fb > 0) {        // [H x fb] with fb = 14: too narrow for a tensor-core tile, stays on the fp32 kernel
     GemmEpilogue e;
     e.tag = "wgrad_edge_attr";
@@ -1091,10 +1145,12 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     memset(&a, 0, sizeof(a));
     a.T = (int)T; a.H = H;
     int nc = 0;
-    a.col_src[nc] = col; a.col_dst[nc++] = grads->b_e2n;
-    for (int i = 0; i < d; ++i) { a.col_src[nc] = col + (size_t)(1 + i) * T * H; a.col_dst[nc++] = grads->b_conv[d - 1 - i]; }
-    a.col_src[nc] = col + (size_t)(d + 1) * T * H; a.col_dst[nc++] = grads->b_init;
-    a.col_src[nc] = dwf; a.col_dst[nc++] = grads->w_ffn;
+    a.col_src[nc] = col; a.col_rows[nc] = (int)T * RB_PARTS; a.col_dst[nc++] = grads->b_e2n;
+    for (int i = 0; i < d; ++i) {
+      a.col_src[nc] = col + (size_t)(RB_PARTS + i) * T * H; a.col_rows[nc] = (int)T; a.col_dst[nc++] = grads->b_conv[d - 1 - i];
+    }
+    a.col_src[nc] = col + (size_t)(RB_PARTS + d) * T * H; a.col_rows[nc] = (int)T; a.col_dst[nc++] = grads->b_init;
+    a.col_src[nc] = dwf; a.col_rows[nc] = (int)T * RB_PARTS; a.col_dst[nc++] = grads->w_ffn;
     a.n_col = nc;
     if (p->use_skip) {
       for (int i = 0; i < d; ++i) { a.skip_src[i] = skp + (size_t)i * w.skip_cnt; a.skip_dst[i] = grads->skip[d - 1 - i]; }
@@ -1104,7 +1160,7 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     }
     CgrRange prof("bwd_finalize", st);
     cgr_note_launch("bwd_finalize", st, 1);
-    bwd_finalize_kernel<<<dim3((unsigned)cgr_ceil_div(H, 256), (unsigned)(a.n_col + a.n_skip)), 256, 0, st>>>(a);
+    bwd_finalize_kernel<<<dim3((unsigned)cgr_ceil_div(H, 32), (unsigned)(a.n_col + a.n_skip)), 256, 0, st>>>(a);
     CGR_LAUNCH_CHECK();
   }
   return CGR_OK;
@@ -1238,6 +1294,20 @@ __global__ void splitk_reduce2_kernel(const float* __restrict__ partial, int spl
   C[(i / N) * ldc + (i % N)] = s;
 }
 
+struct ReduceBatchArgs {
+  const float* partial[tcg2::MAX_BATCH];
+  float* C[tcg2::MAX_BATCH];
+  int64_t ldc[tcg2::MAX_BATCH];
+};
+__global__ void splitk_reduce2_batched_kernel(const ReduceBatchArgs a, int splits, int64_t M, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const float* partial = a.partial[blockIdx.y];
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * M * N + i];   // fixed order
+  a.C[blockIdx.y][(i / N) * a.ldc[blockIdx.y] + (i % N)] = s;
+}
+
 int make_operand_maps(CUtensorMap* hi_map, CUtensorMap* lo_map, const TcOperand& op, int64_t mn, int64_t K) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
@@ -1324,6 +1394,53 @@ int tc_train_gemm(const TcOperand& A, const TcOperand& B, int64_t M, int64_t N, 
   else tcg2::tc_gemm2_kernel<true, false><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(prm);
   if (split_k > 1)
     splitk_reduce2_kernel<<<(unsigned)cgr_ceil_div(M * N, 256), 256, 0, st>>>(partial, split_k, M, N, C, ldc);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+// Up to 8 reductions C_i[M,N] = A_i^T B_i of ONE shape (both operands [K rows, MN cols]) in one GEMM launch plus one
+// split-K reduction launch.  `partial` holds n * split_k * M * N floats.
+int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* const* C, const int64_t* ldc, int n,
+                             int64_t M, int64_t N, int64_t K, int split_k, float* partial, const char* name,
+                             cudaStream_t st) {
+  CGR_CHECK_ARG(n >= 1 && n <= tcg2::MAX_BATCH && M > 0 && N > 0 && K > 0, "tc_train_gemm_batched_mn: bad argument");
+  static tcg2::BatchParams bp;       // large (several KB): built in place; launches copy it
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  memset(&bp, 0, sizeof(bp));
+  const int64_t kc = cgr_ceil_div(K, tcg2::BK);
+  if (split_k < 1) split_k = 1;
+  const int64_t per = cgr_ceil_div(kc, split_k);
+  split_k = (int)cgr_ceil_div(kc, per);
+  CGR_CHECK_ARG(partial, "tc_train_gemm_batched_mn: partial buffer missing");
+  ReduceBatchArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  int rc;
+  for (int i = 0; i < n; ++i) {
+    tcg2::Params& prm = bp.prob[i];
+    CGR_CHECK_ARG(A[i].mn_major && B[i].mn_major, "tc_train_gemm_batched_mn: operands must be [K, MN]");
+    if ((rc = make_operand_maps(&prm.tmA_hi, &prm.tmA_lo, A[i], M, K))) return rc;
+    if ((rc = make_operand_maps(&prm.tmB_hi, &prm.tmB_lo, B[i], N, K))) return rc;
+    prm.M = M; prm.N = N; prm.K = K;
+    prm.k_chunks_per_split = per;
+    prm.unscale_a = A[i].unscale; prm.unscale_b = B[i].unscale;
+    prm.split_k = split_k;                       // results always go through the partial buffer
+    prm.act = CGR_ACT_IDENTITY;
+    prm.C = partial + (size_t)i * split_k * M * N;
+    prm.ldc = N;
+    ra.partial[i] = prm.C; ra.C[i] = C[i]; ra.ldc[i] = ldc[i];
+  }
+  bp.n_prob = n;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CGR_CUDA(cudaFuncSetAttribute(tcg2::tc_gemm2_batched_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg2::SMEM_BYTES));
+    attr_done = true;
+  }
+  CgrRange prof(name, st);
+  cgr_note_launch(name, st, 2);
+  dim3 grid((unsigned)cgr_ceil_div(N, tcg2::TN), (unsigned)cgr_ceil_div(M, tcg2::TM), (unsigned)(split_k * n));
+  tcg2::tc_gemm2_batched_kernel<true, true><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(bp);
+  splitk_reduce2_batched_kernel<<<dim3((unsigned)cgr_ceil_div(M * N, 256), (unsigned)n), 256, 0, st>>>(ra, split_k, M, N);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }

@@ -41,6 +41,9 @@ int tc_split(const float* in, int64_t ld, int64_t rows, int cols, bool scaled, _
 int tc_splitk_choose(int64_t M, int64_t N, int64_t K);
 int tc_train_gemm(const TcOperand& A, const TcOperand& B, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
                   const GemmEpilogue& epi, int split_k, float* partial, cudaStream_t st);
+int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* const* C, const int64_t* ldc, int n,
+                             int64_t M, int64_t N, int64_t K, int split_k, float* partial, const char* name,
+                             cudaStream_t st);
 TcOperand tc_weight_operand(const cgr_params_t* p, const void* wbuf, int mat, int64_t row0, bool mn_major);
 size_t tc_gemm2_test_workspace(int64_t M, int64_t N, int64_t K);
 int tc_gemm2_test(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn, float* C,

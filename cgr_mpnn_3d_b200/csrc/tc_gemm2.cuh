@@ -65,8 +65,15 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, bool a_mn, bool b_mn)
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Several GEMMs of one shape in one launch (the weight gradients of all layers): blockIdx.z = problem * split_k + split
+constexpr int MAX_BATCH = 8;
+struct BatchParams {
+  Params prob[MAX_BATCH];
+  int n_prob;
+};
+
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm2_kernel(const __grid_constant__ Params p) {
+__device__ __forceinline__ void gemm2_body(const Params& p, const int zsplit) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = umma::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm2_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
   const int64_t kc_total = (p.K + BK - 1) / BK;
-  const int64_t kc_beg = (int64_t)blockIdx.z * p.k_chunks_per_split;
+  const int64_t kc_beg = (int64_t)zsplit * p.k_chunks_per_split;
   int64_t kc_end = kc_beg + p.k_chunks_per_split;
   if (kc_end > kc_total) kc_end = kc_total;
   const int num_k = (int)(kc_end - kc_beg);      // >= 1 by construction of the grid
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm2_kernel(const __grid_const
   const int64_t n = n0 + c;
   if (n < p.N) {
     const bool partial = p.split_k > 1;
-    float* Cb = partial ? p.C + (int64_t)blockIdx.z * p.M * p.N : p.C;
+    float* Cb = partial ? p.C + (int64_t)zsplit * p.M * p.N : p.C;
     const int64_t ldc = partial ? p.N : p.ldc;
     const float rs = (!partial && p.res) ? (p.res_scale ? __ldg(p.res_scale) : 1.f) : 0.f;
     const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
@@ -249,6 +256,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm2_kernel(const __grid_const
   }
   __syncthreads();
   if (warp == 1) umma::tmem_dealloc(tmem, 128);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm2_kernel(const __grid_constant__ Params p) {
+  gemm2_body<A_MN, B_MN>(p, (int)blockIdx.z);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm2_batched_kernel(const __grid_constant__ BatchParams bp) {
+  const int split_k = bp.prob[0].split_k;
+  gemm2_body<A_MN, B_MN>(bp.prob[blockIdx.z / split_k], (int)(blockIdx.z % split_k));
 }
 
 }  // namespace tcg2

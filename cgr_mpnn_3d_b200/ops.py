@@ -217,6 +217,7 @@ def _setup_context(ctx, inputs, output):
      engine, _tile_info, _n_tiles, _tc_status, _tc_weights, _x_hi, _x_lo, _tp, _fused) = inputs
     ctx.cfg = (depth, act, use_skip, list(dropout_ps), training, seed, engine, int(_n_tiles))
     ctx.n_params = len(params)
+    ctx.set_materialize_grads(False)      # no zero-filled gradients for the saved-activation outputs
     ctx.save_for_backward(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, *params, *output[1:], _tc_weights, _x_hi,
                           _x_lo, _tile_info, _tc_status)
 
