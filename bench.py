@@ -476,6 +476,20 @@ def main():
         t1e.record()
         barrier()
         train = {"ms_total": t0e.elapsed_time(t1e), "steps": n_t}
+        # the same step issued eagerly, as a plain training loop does (trainer.py:139-144 without the optimizer):
+        # host-bound, so wall clock between two synchronisations
+        for i in range(5):
+            tm.zero_grad(set_to_none=True)
+            train_step(tb[i % len(tb)])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_t):
+            tm.zero_grad(set_to_none=True)
+            train_step(tb[i % len(tb)])
+            if world > 1:
+                allreduce_gradients_(tm.parameters())
+        barrier()
+        train["eager_ms"] = (time.perf_counter() - t0) * 1e3 / n_t
         # optimizer step, reported separately (SURVEY.md section 8 d-ii / f-1): one fused launch vs torch's foreach Adam
         from cgr_mpnn_3d_b200.optim import FusedAdam
         for p_ in tm.parameters():
@@ -556,6 +570,7 @@ def main():
         if train:
             line["train_step"] = {"value": args.batch * train["steps"] * world / (train_ms * 1e-3), "unit": "reactions/s",
                                   "ms_per_step": train_ms / train["steps"], "steps": train["steps"],
+                                  "eager_ms_per_step": train["eager_ms"],
                                   "optimizer": {"fused_adam_ms": train["adam_fused_ms"],
                                                 "fused_adam_launches_per_step": train["adam_fused_launches"],
                                                 "torch_adam_ms": train["adam_torch_ms"],

@@ -533,7 +533,7 @@ namespace {
 // then h_0 in fp32 (skip-weight gradient) and hv in fp32 (mask of the readout backward).
 struct TcSavedLayout {
   int64_t kp_h, rows_pad;
-  size_t off_hhi[MAX_SEG], off_hlo[MAX_SEG], hl_bytes, off_h0, off_hv, total;
+  size_t off_hhi[MAX_SEG], off_hlo[MAX_SEG], hl_bytes, off_h0, off_hv, off_w, total;
 };
 TcSavedLayout tc_saved_layout(const cgr_params_t* p, const cgr_graph_t* g) {
   TcSavedLayout L;
@@ -549,6 +549,7 @@ TcSavedLayout tc_saved_layout(const cgr_params_t* p, const cgr_graph_t* g) {
   L.hl_bytes = off;
   L.off_h0 = take((size_t)L.rows_pad * H * sizeof(float));
   L.off_hv = take((size_t)g->n_atoms * H * sizeof(float));
+  L.off_w = take(tc_weights_bytes(p));              // prepared weights of this step (when the caller passed none)
   L.total = off + 1024;
   return L;
 }
@@ -595,7 +596,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   const int64_t N = g->n_atoms, T = g->n_tiles, B = g->n_rxn;
   int rc;
 
-  char* wbuf = need_w ? ws + w.off_w : (char*)p->tc_weights;
+  char* wbuf = need_w ? (blob ? blob + SL.off_w : ws + w.off_w) : (char*)p->tc_weights;
   if (need_w) {
     rc = tc_prepare_weights(p, wbuf, tc_weights_bytes(p), st);
     if (rc) return rc;
@@ -948,9 +949,12 @@ TcBwdWs tc_bwd_ws(const cgr_params_t* p, const cgr_graph_t* g) {
   w.off_gamax = take(MAX_SEG * 2 * sizeof(unsigned int));
   w.off_gunscale = take(MAX_SEG * 2 * sizeof(float));
   size_t pf = 0;
-  auto upd = [&](int n_, int64_t M_, int64_t N_, int64_t K_) {       // batched weight-gradient GEMMs
-    const size_t f = (size_t)n_ * tc_splitk_choose(M_, N_, K_) * M_ * N_;
-    if (f > pf) pf = f;
+  auto upd = [&](int n_max, int64_t M_, int64_t N_, int64_t K_) {    // batched weight-gradient GEMMs (any batch <= n_max)
+    for (int n_ = 1; n_ <= n_max && n_ <= tcg2::MAX_BATCH; ++n_) {
+      const int sk = tc_splitk_batched(n_, M_, N_, K_);
+      const size_t f = sk > 1 ? (size_t)n_ * sk * M_ * N_ : 0;
+      if (f > pf) pf = f;
+    }
   };
   upd(d + 1, H, H, w.rows_pad);
   upd(2, H, p->fa, N);
@@ -961,7 +965,7 @@ TcBwdWs tc_bwd_ws(const cgr_params_t* p, const cgr_graph_t* g) {
   const bool need_x = !(g->x_hi && g->x_lo);
   w.off_xhi = take(need_x ? (size_t)N * w.kp_x * sizeof(__half) : 0);
   w.off_xlo = take(need_x ? (size_t)N * w.kp_x * sizeof(__half) : 0);
-  w.off_w = take(p->tc_weights ? 0 : tc_weights_bytes(p));
+  w.off_w = 0;
   w.total = off + 1024;
   return w;
 }
@@ -986,11 +990,8 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
   const int H = p->hidden, fa = p->fa, fb = p->fb, d = p->depth;
   const int64_t N = g->n_atoms, E = g->n_bonds, T = g->n_tiles, B = g->n_rxn;
   int rc;
-  char* wbuf = (char*)p->tc_weights;
-  if (!wbuf) {
-    wbuf = ws + w.off_w;
-    if ((rc = tc_prepare_weights(p, wbuf, tc_weights_bytes(p), st))) return rc;
-  }
+  // weights: the caller's prepared buffer, else the copy the training forward left in the blob
+  char* wbuf = p->tc_weights ? (char*)p->tc_weights : blob + SL.off_w;
   const WLayout wl = wlayout(p);
   const float* unscale = (const float*)(wbuf + wl.off_unscale);
   int* flag = g->tc_status;
@@ -1108,7 +1109,7 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     int n = 0;
     auto flush = [&](int64_t M_, int64_t N_, int64_t K_, const char* tag) {
       if (n == 0) return (int)CGR_OK;
-      const int r = tc_train_gemm_batched_mn(A, Bo, C, ldc, n, M_, N_, K_, tc_splitk_choose(M_, N_, K_), partial, tag, st);
+      const int r = tc_train_gemm_batched_mn(A, Bo, C, ldc, n, M_, N_, K_, tc_splitk_batched(n, M_, N_, K_), partial, tag, st);
       n = 0;
       return r;
     };
@@ -1398,6 +1399,23 @@ int tc_train_gemm(const TcOperand& A, const TcOperand& B, int64_t M, int64_t N, 
   return CGR_OK;
 }
 
+// Split-K for a batch of n same-shape reductions: one wave of CTAs (148 SMs, one CTA each) when K is short -- every CTA
+// pays a fixed prologue + epilogue -- and up to four waves of >= 32-chunk CTAs when K is long.
+int tc_splitk_batched(int n, int64_t M, int64_t N, int64_t K) {
+  const int64_t base = (int64_t)n * cgr_ceil_div(M, tcg2::TM) * cgr_ceil_div(N, tcg2::TN);
+  const int64_t kc = cgr_ceil_div(K > 0 ? K : 1, tcg2::BK);
+  int64_t s = 148 / base;
+  if (s < 1) s = 1;
+  if (kc / s >= 64) {
+    int64_t s2 = 592 / base;
+    if (s2 > kc / 32) s2 = kc / 32;
+    if (s2 > s) s = s2;
+  }
+  if (s > kc) s = kc;
+  if (s > 64) s = 64;
+  return (int)(s < 1 ? 1 : s);
+}
+
 // Up to 8 reductions C_i[M,N] = A_i^T B_i of ONE shape (both operands [K rows, MN cols]) in one GEMM launch plus one
 // split-K reduction launch.  `partial` holds n * split_k * M * N floats.
 int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* const* C, const int64_t* ldc, int n,
@@ -1412,7 +1430,7 @@ int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* cons
   if (split_k < 1) split_k = 1;
   const int64_t per = cgr_ceil_div(kc, split_k);
   split_k = (int)cgr_ceil_div(kc, per);
-  CGR_CHECK_ARG(partial, "tc_train_gemm_batched_mn: partial buffer missing");
+  CGR_CHECK_ARG(split_k == 1 || partial, "tc_train_gemm_batched_mn: partial buffer missing");
   ReduceBatchArgs ra;
   memset(&ra, 0, sizeof(ra));
   int rc;
@@ -1424,10 +1442,15 @@ int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* cons
     prm.M = M; prm.N = N; prm.K = K;
     prm.k_chunks_per_split = per;
     prm.unscale_a = A[i].unscale; prm.unscale_b = B[i].unscale;
-    prm.split_k = split_k;                       // results always go through the partial buffer
+    prm.split_k = split_k;
     prm.act = CGR_ACT_IDENTITY;
-    prm.C = partial + (size_t)i * split_k * M * N;
-    prm.ldc = N;
+    if (split_k > 1) {
+      prm.C = partial + (size_t)i * split_k * M * N;
+      prm.ldc = N;
+    } else {                                     // no split: the GEMM writes the gradient directly
+      prm.C = C[i];
+      prm.ldc = ldc[i];
+    }
     ra.partial[i] = prm.C; ra.C[i] = C[i]; ra.ldc[i] = ldc[i];
   }
   bp.n_prob = n;
@@ -1437,10 +1460,11 @@ int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* cons
     attr_done = true;
   }
   CgrRange prof(name, st);
-  cgr_note_launch(name, st, 2);
+  cgr_note_launch(name, st, split_k > 1 ? 2 : 1);
   dim3 grid((unsigned)cgr_ceil_div(N, tcg2::TN), (unsigned)cgr_ceil_div(M, tcg2::TM), (unsigned)(split_k * n));
   tcg2::tc_gemm2_batched_kernel<true, true><<<grid, tcg2::THREADS, tcg2::SMEM_BYTES, st>>>(bp);
-  splitk_reduce2_batched_kernel<<<dim3((unsigned)cgr_ceil_div(M * N, 256), (unsigned)n), 256, 0, st>>>(ra, split_k, M, N);
+  if (split_k > 1)
+    splitk_reduce2_batched_kernel<<<dim3((unsigned)cgr_ceil_div(M * N, 256), (unsigned)n), 256, 0, st>>>(ra, split_k, M, N);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }

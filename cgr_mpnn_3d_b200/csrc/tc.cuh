@@ -41,6 +41,7 @@ int tc_split(const float* in, int64_t ld, int64_t rows, int cols, bool scaled, _
 int tc_splitk_choose(int64_t M, int64_t N, int64_t K);
 int tc_train_gemm(const TcOperand& A, const TcOperand& B, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
                   const GemmEpilogue& epi, int split_k, float* partial, cudaStream_t st);
+int tc_splitk_batched(int n, int64_t M, int64_t N, int64_t K);
 int tc_train_gemm_batched_mn(const TcOperand* A, const TcOperand* B, float* const* C, const int64_t* ldc, int n,
                              int64_t M, int64_t N, int64_t K, int split_k, float* partial, const char* name,
                              cudaStream_t st);

@@ -204,9 +204,11 @@ class GNN(nn.Module):
                 tc_status = plan.tc_status
             else:
                 tile_info, n_tiles, tc_status = plan.tile_info, plan.n_tiles, plan.tc_status
-            if train_flag:
-                # weights change every optimizer step: always re-prepare (3 small launches, CUDA-graph safe --
-                # a version-keyed cache hit at capture time would freeze stale weights into the graph)
+            if fused_train:
+                # weights change every optimizer step: the fused training forward prepares them itself, next to the
+                # saved activations, and the backward reads them from there (CUDA-graph safe: nothing cached here)
+                tc_w = torch.empty(0, dtype=torch.uint8, device=dev)
+            elif train_flag:
                 tc_w = ops.prepare_tc_weights([p.detach() for p in params], self.depth, _act_id(self.activation_fn),
                                               bool(self.use_learnable_skip), int(x.shape[1]), int(edge_attr.shape[1]))
             else:
@@ -216,14 +218,22 @@ class GNN(nn.Module):
             tile_info, n_tiles, tc_status = empty_i, 0, empty_i
             tc_w = torch.empty(0, dtype=torch.uint8, device=dev)
             x_hi = x_lo = torch.empty(0, dtype=torch.float16, device=dev)
-        res = ops.gnn_forward(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr, params,
-                              self.depth, _act_id(self.activation_fn), bool(self.use_learnable_skip), dps,
-                              train_flag, seed, engine, tile_info, n_tiles, tc_status, tc_w, x_hi, x_lo,
-                              getattr(self, "tile_policy", "latency") == "throughput", fused_train)
+        throughput = getattr(self, "tile_policy", "latency") == "throughput"
+        if needs_grad:
+            call = dict(src=plan.src, dst=plan.dst, in_ptr=plan.in_ptr, in_idx=plan.in_idx, atom_ptr=plan.atom_ptr,
+                        depth=self.depth, act=_act_id(self.activation_fn), use_skip=bool(self.use_learnable_skip),
+                        dropout_ps=dps, seed=seed, engine=engine, tile_info=tile_info, n_tiles=n_tiles,
+                        tc_status=tc_status, tc_weights=tc_w, x_hi=x_hi, x_lo=x_lo, tc_throughput=throughput,
+                        fused_train=fused_train)
+            out = ops.GnnFunction.apply(call, x, edge_attr, *params)
+        else:
+            out = ops.gnn_forward_impl(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr,
+                                       [p.detach() for p in params], self.depth, _act_id(self.activation_fn),
+                                       bool(self.use_learnable_skip), dps, train_flag, seed, engine, tile_info,
+                                       n_tiles, tc_status, tc_w, x_hi, x_lo, throughput, fused_train)[0]
         self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and n_tiles > 0) else None
         self.__dict__["_last_engine"] = engine
         self.__dict__["_last_fused_train"] = fused_train
-        out = res[0]
         if caller_device != dev:
             out = out.to(caller_device)
         return out

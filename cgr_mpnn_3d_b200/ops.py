@@ -57,6 +57,26 @@ class _Ctx:
         )
 
 
+_CTX_CACHE: dict = {}
+
+
+def _ctx_cached(role: str, params: Sequence[Tensor], depth: int, act: int, use_skip: bool, fa: int, fb: int,
+                dropout_ps: Sequence[float]) -> "_Ctx":
+    """ctypes parameter block keyed by the parameter storage (optimizers update in place, so the pointers of a
+    training run never change); one block per role because forward and backward may run on different threads."""
+    key = (role, depth, act, use_skip, fa, fb, tuple(float(p) for p in dropout_ps[:depth]),
+           tuple(p.data_ptr() for p in params), int(params[0].shape[0]))
+    ctx = _CTX_CACHE.get(key)
+    if ctx is None:
+        if len(_CTX_CACHE) >= 16:
+            _CTX_CACHE.clear()
+        ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
+        _CTX_CACHE[key] = ctx
+    ctx.params.tc_weights = None
+    ctx.params.tc_throughput = 0
+    return ctx
+
+
 def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info=None, n_tiles=0,
                   tc_status=None, x_hi=None, x_lo=None) -> _lib.CgrGraph:
     has_tiles = tile_info is not None and tile_info.numel() > 0 and n_tiles > 0
@@ -89,6 +109,17 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
                 dropout_ps: Sequence[float], training: bool, seed: int, engine: int, tile_info: Tensor,
                 n_tiles: int, tc_status: Tensor, tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor,
                 tc_throughput: bool, fused_train: bool) -> List[Tensor]:
+    """Dispatcher-registered form of :func:`gnn_forward_impl` (same arguments, same results)."""
+    return gnn_forward_impl(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, depth, act, use_skip, dropout_ps,
+                            training, seed, engine, tile_info, n_tiles, tc_status, tc_weights, x_hi, x_lo,
+                            tc_throughput, fused_train)
+
+
+def gnn_forward_impl(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor, in_idx: Tensor,
+                     atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
+                     dropout_ps: Sequence[float], training: bool, seed: int, engine: int, tile_info: Tensor,
+                     n_tiles: int, tc_status: Tensor, tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor,
+                     tc_throughput: bool, fused_train: bool) -> List[Tensor]:
     """Returns ``[out, h_all, m_all, z_all, s, hv, zv, pooled, tc_blob]`` (saved tensors are empty in eval).
     ``fused_train``: training on the tcgen05 engine with the tile-local fused kernels -- everything the backward
     needs lives in ``tc_blob`` and the layer-wise buffers stay empty.
@@ -100,7 +131,7 @@ def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: 
     x, edge_attr = _f32c(x), _f32c(edge_attr)
     params = [_f32c(p) for p in params]
     fa, fb = int(x.shape[1]), int(edge_attr.shape[1])
-    ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
+    ctx = _ctx_cached("fwd", params, depth, act, use_skip, fa, fb, dropout_ps)
     if tc_weights.numel() > 0:
         ctx.params.tc_weights = tc_weights.data_ptr()
     ctx.params.tc_throughput = int(tc_throughput)
@@ -169,6 +200,16 @@ def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, ds
                  in_idx: Tensor, atom_ptr: Tensor, params: Sequence[Tensor], saved: Sequence[Tensor], depth: int,
                  act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int, tc_weights: Tensor,
                  x_hi: Tensor, x_lo: Tensor, tile_info: Tensor, n_tiles: int, tc_status: Tensor) -> List[Tensor]:
+    """Dispatcher-registered form of :func:`gnn_backward_impl`."""
+    return gnn_backward_impl(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act,
+                             use_skip, dropout_ps, seed, engine, tc_weights, x_hi, x_lo, tile_info, n_tiles, tc_status)
+
+
+def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor,
+                      in_idx: Tensor, atom_ptr: Tensor, params: Sequence[Tensor], saved: Sequence[Tensor], depth: int,
+                      act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int,
+                      tc_weights: Tensor, x_hi: Tensor, x_lo: Tensor, tile_info: Tensor, n_tiles: int,
+                      tc_status: Tensor) -> List[Tensor]:
     """Explicit backward: gradients of every parameter, in parameter-list order."""
     _require_cuda(grad_out, x, *params)
     lib = _lib.load()
@@ -242,6 +283,40 @@ def _backward(ctx, grads):
 
 
 gnn_forward.register_autograd(_backward, setup_context=_setup_context)
+
+
+class GnnFunction(torch.autograd.Function):
+    """Lean autograd node around the same two C calls (what ``GNN.forward`` uses when gradients are needed): the
+    dispatcher-registered ops above cost several hundred microseconds of host time per call, which is more than
+    the whole training step takes on the GPU.  ``call`` carries every non-differentiable argument."""
+
+    @staticmethod
+    def forward(ctx, call, x, edge_attr, *params):
+        res = gnn_forward_impl(x, edge_attr, call["src"], call["dst"], call["in_ptr"], call["in_idx"], call["atom_ptr"],
+                               list(params), call["depth"], call["act"], call["use_skip"], call["dropout_ps"], True,
+                               call["seed"], call["engine"], call["tile_info"], call["n_tiles"], call["tc_status"],
+                               call["tc_weights"], call["x_hi"], call["x_lo"], call["tc_throughput"],
+                               call["fused_train"])
+        ctx.call = call
+        ctx.n_params = len(params)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x, edge_attr, *params, *res[1:])
+        return res[0]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        call = ctx.call
+        t = ctx.saved_tensors
+        x, edge_attr = t[0], t[1]
+        params = list(t[2:2 + ctx.n_params])
+        saved = list(t[2 + ctx.n_params:])
+        if g_out is None:
+            g_out = torch.zeros(call["atom_ptr"].shape[0] - 1, dtype=torch.float32, device=x.device)
+        pg = gnn_backward_impl(g_out, x, edge_attr, call["src"], call["dst"], call["in_ptr"], call["in_idx"],
+                               call["atom_ptr"], params, saved, call["depth"], call["act"], call["use_skip"],
+                               call["dropout_ps"], call["seed"], call["engine"], call["tc_weights"], call["x_hi"],
+                               call["x_lo"], call["tile_info"], call["n_tiles"], call["tc_status"])
+        return (None, None, None, *pg)
 
 
 def prepare_tc_weights(params: Sequence[Tensor], depth: int, act: int, use_skip: bool, fa: int, fb: int) -> Tensor:
