@@ -123,15 +123,6 @@ __global__ void __launch_bounds__(256) tc_edge_init_kernel(const float* __restri
   if (vmax > 60000.f) atomicOr(overflow, 1);
 }
 
-// W_e^T [fb][H] from edge_init.weight[:, fa:]  (coalesced reads in the edge-init kernel)
-__global__ void transpose_we_kernel(const float* __restrict__ w_init, int fa, int fb, int H, float* __restrict__ wet) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < fb * H) {
-    const int k = i / H, n = i % H;
-    wet[i] = __ldg(w_init + (int64_t)n * (fa + fb) + fa + k);
-  }
-}
-
 // ---- weight preparation: per-matrix power-of-two scale, (hi, lo) split ----
 constexpr int MAX_SEG = 16;
 struct Seg {
@@ -149,13 +140,37 @@ struct PrepArgs {
   __half* hiT[MAX_SEG];         // optional transposed copy (backward data-gradient GEMMs), same scale
   __half* loT[MAX_SEG];
   int64_t ldo[MAX_SEG];
+  // side tables built by the same launch
+  const float* b0;
+  const float* b1;
+  float* bias_cat;
+  const float* w_init;
+  float* wet;
+  int H, fa, fb;
 };
 
+// blockIdx.y < n_seg: amax of one weight segment.  The two extra y values build the small fp32 side tables that do
+// not depend on the scales: [b_i | b_o] and W_e^T (edge_init.weight[:, fa:] transposed).
 __global__ void __launch_bounds__(256) prep_amax_kernel(const PrepArgs a) {
+  if ((int)blockIdx.y == a.n_seg) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < a.H; i += gridDim.x * 256) {
+      a.bias_cat[i] = __ldg(a.b0 + i);
+      a.bias_cat[a.H + i] = __ldg(a.b1 + i);
+    }
+    return;
+  }
+  if ((int)blockIdx.y == a.n_seg + 1) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < a.fb * a.H; i += gridDim.x * 256) {
+      const int k = i / a.H, n = i % a.H;
+      a.wet[i] = __ldg(a.w_init + (int64_t)n * (a.fa + a.fb) + a.fa + k);
+    }
+    return;
+  }
   const Seg s = a.seg[blockIdx.y];
   float m = 0.f;
   for (int r = blockIdx.x; r < s.rows; r += gridDim.x) {          // rows over blocks, columns over threads: coalesced
     const float* row = s.src + (int64_t)r * s.ld;
+#pragma unroll 4
     for (int c = threadIdx.x; c < s.cols; c += 256) m = fmaxf(m, fabsf(__ldg(row + c)));
   }
 #pragma unroll
@@ -213,15 +228,6 @@ __global__ void __launch_bounds__(256) prep_split_kernel(const PrepArgs a) {
       }
       __syncthreads();
     }
-  }
-}
-
-__global__ void concat_bias_kernel(const float* __restrict__ b0, const float* __restrict__ b1, int H,
-                                   float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < H) {
-    out[i] = __ldg(b0 + i);
-    out[H + i] = __ldg(b1 + i);
   }
 }
 
@@ -464,14 +470,13 @@ int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cud
   a.seg[ns++] = Seg{p->w_e2n + fa, fa + H, H, H, p->depth + 1, 0};  // W_os  = edge_to_node.weight[:, Fa:]
   a.n_seg = ns;
   CgrRange prof("tc_prep_weights", st);
-  cgr_note_launch("tc_prep_weights", st, 3);
+  cgr_note_launch("tc_prep_weights", st, 2);
+  a.b0 = p->b_init; a.b1 = p->b_e2n; a.bias_cat = (float*)(b + w.off_bias);
+  a.w_init = p->w_init; a.wet = (float*)(b + w.off_wet);
+  a.H = H; a.fa = fa; a.fb = fb;
   CGR_CUDA(cudaMemsetAsync(a.amax_bits, 0, MAX_SEG * sizeof(unsigned int), st));
-  prep_amax_kernel<<<dim3(48, (unsigned)ns), 256, 0, st>>>(a);
-  prep_split_kernel<<<dim3(96, (unsigned)ns), 256, 0, st>>>(a);
-  concat_bias_kernel<<<(unsigned)cgr_ceil_div(H, 256), 256, 0, st>>>(p->b_init, p->b_e2n, H, (float*)(b + w.off_bias));
-  if (fb > 0)
-    transpose_we_kernel<<<(unsigned)cgr_ceil_div((int64_t)fb * H, 256), 256, 0, st>>>(p->w_init, fa, fb, H,
-                                                                                       (float*)(b + w.off_wet));
+  prep_amax_kernel<<<dim3(200, (unsigned)ns + 2), 256, 0, st>>>(a);
+  prep_split_kernel<<<dim3(256, (unsigned)ns), 256, 0, st>>>(a);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }
