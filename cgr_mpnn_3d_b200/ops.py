@@ -201,8 +201,9 @@ def gnn_backward(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, ds
                  act: int, use_skip: bool, dropout_ps: Sequence[float], seed: int, engine: int, tc_weights: Tensor,
                  x_hi: Tensor, x_lo: Tensor, tile_info: Tensor, n_tiles: int, tc_status: Tensor) -> List[Tensor]:
     """Dispatcher-registered form of :func:`gnn_backward_impl`."""
-    return gnn_backward_impl(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act,
-                             use_skip, dropout_ps, seed, engine, tc_weights, x_hi, x_lo, tile_info, n_tiles, tc_status)
+    pg = gnn_backward_impl(grad_out, x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, params, saved, depth, act,
+                           use_skip, dropout_ps, seed, engine, tc_weights, x_hi, x_lo, tile_info, n_tiles, tc_status)
+    return [g.clone() for g in pg]       # registered ops may not return views of one buffer
 
 
 def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor,
@@ -230,7 +231,14 @@ def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tenso
         sv = _lib.CgrSaved(h_all=h_all.data_ptr(), m_all=m_all.data_ptr(),
                            z_all=z_all.data_ptr() if need_z else None, s=s.data_ptr(), hv=hv.data_ptr(),
                            zv=zv.data_ptr() if need_z else None, pooled=pooled.data_ptr())
-    grads = [torch.empty_like(p) for p in params]
+    # all gradients are views of ONE flat fp32 buffer (16-byte aligned pieces, parameter order), so data-parallel
+    # training all-reduces them with a single collective and no packing copies (parallel.allreduce_gradients_)
+    sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
+    grads, off = [], 0
+    for p, n in zip(params, sizes):
+        grads.append(flat[off:off + p.numel()].view(p.shape))
+        off += n
     gw_init, gb_init, gw_conv, gb_conv, gw_e2n, gb_e2n, gw_ffn, gb_ffn, gskip = _unpack(grads, depth, use_skip)
     wc, bc = _lib.ptr_array(gw_conv), _lib.ptr_array(gb_conv)
     sk = _lib.ptr_array(gskip) if use_skip else None

@@ -51,9 +51,34 @@ def flat_gradients(params: Iterable[torch.nn.Parameter]) -> Tuple[torch.Tensor, 
     return flat, ps
 
 
+def _shared_flat_view(ps: List[torch.nn.Parameter]):
+    """The gradients of the CGR backward are views of one flat buffer (ops.gnn_backward_impl); when every ``.grad`` still
+    is (nothing accumulated or replaced them), return a 1-D view spanning all of them, else None."""
+    gs = [p.grad for p in ps]
+    if any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in gs):
+        return None
+    base = gs[0].untyped_storage().data_ptr()
+    end = gs[0].storage_offset()
+    for g in gs:
+        if g.untyped_storage().data_ptr() != base or g.storage_offset() < end or g.storage_offset() - end > 3:
+            return None
+        end = g.storage_offset() + g.numel()
+    first = gs[0]
+    if end > first.untyped_storage().nbytes() // 4:
+        return None
+    return first.as_strided((end - first.storage_offset(),), (1,), first.storage_offset())
+
+
 def allreduce_gradients_(params: Iterable[torch.nn.Parameter], group=None) -> torch.Tensor:
-    """In-place SUM all-reduce of all gradients through one flat buffer; returns the reduced buffer."""
-    flat, ps = flat_gradients(params)
+    """In-place SUM all-reduce of all gradients through one flat buffer; returns the reduced buffer.  Gradients that
+    already live in one flat buffer (the CGR backward's do) are reduced in place: one collective, no copies."""
+    ps = [p for p in params if p.requires_grad]
+    view = _shared_flat_view(ps) if ps else None
+    if view is not None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+        return view
+    flat, ps = flat_gradients(ps)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0

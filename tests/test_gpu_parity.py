@@ -168,6 +168,9 @@ def test_golden_forward_backward(name, engine):
     for k, p in model.named_parameters():
         assert p.grad is not None, k
         assert tensor_error(p.grad, torch.from_numpy(z["g/" + k])) < GRAD_TOL, k
+    # every gradient is a view of one flat buffer: data-parallel training reduces them with one collective, no packing
+    from cgr_mpnn_3d_b200.parallel import _shared_flat_view
+    assert _shared_flat_view(list(model.parameters())) is not None
 
 
 @pytest.mark.parametrize("engine", ENGINES)

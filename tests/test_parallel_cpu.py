@@ -77,3 +77,27 @@ def test_sum_allreduce_matches_single_process_on_concatenated_batch():
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-5
+
+
+def test_allreduce_uses_shared_flat_gradient_buffer_in_place():
+    """Gradients that are views of one flat buffer (what the CGR backward returns) are reduced in place."""
+    import torch
+    from cgr_mpnn_3d_b200.parallel import _shared_flat_view, allreduce_gradients_
+    shapes = [(5, 7), (5,), (1,), (3, 3), (1,)]
+    ps = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    sizes = [(p.numel() + 3) // 4 * 4 for p in ps]
+    flat = torch.arange(sum(sizes), dtype=torch.float32)
+    off = 0
+    for p, n in zip(ps, sizes):
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += n
+    view = _shared_flat_view(ps)
+    assert view is not None and view.data_ptr() == flat.data_ptr() and view.numel() == off - sizes[-1] + ps[-1].numel()
+    out = allreduce_gradients_(ps)               # no process group: nothing to reduce, same buffer returned
+    assert out.data_ptr() == flat.data_ptr()
+    # separately allocated gradients take the packing path
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    assert _shared_flat_view(ps) is None
+    out = allreduce_gradients_(ps)
+    assert out.numel() == sum(p.numel() for p in ps) and bool((out == 1).all())
