@@ -607,3 +607,45 @@ def test_training_loop_with_fused_adam_tracks_reference():
         assert float(diff.max()) <= 5 * 1e-3 * 1.01, k
         if diff.numel() >= 100:
             assert float(diff.quantile(0.99)) < 1e-4 * scale, k
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the tile-local kernels: atoms with more bonds than the 8 packed neighbour slots, a reaction that fills
+# a whole 128-bond tile, a single two-atom reaction
+def _custom_graph(rng, pairs, n, fa, fb):
+    from cgr_mpnn_3d_b200.data import Graph
+    ei = np.array([[a, b] for (a, b) in pairs for (a, b) in ((a, b), (b, a))], dtype=np.int64).T.copy()
+    ea_half = rng.standard_normal((len(pairs), fb)).astype(np.float32)
+    ea = np.repeat(ea_half, 2, axis=0)               # both directions of a bond carry the same features
+    return Graph(x=rng.standard_normal((n, fa)).astype(np.float32) * 0.5, edge_index=ei, edge_attr=ea,
+                 y=rng.standard_normal(1).astype(np.float32))
+
+
+@pytest.mark.parametrize("skip", [False, True])
+def test_high_degree_and_full_tile_reactions(skip):
+    from cgr_mpnn_3d_b200.data import collate_host
+    rng = np.random.default_rng(11)
+    fa, fb = 78, 14
+    star = _custom_graph(rng, [(0, k) for k in range(1, 14)], 14, fa, fb)                      # centre atom: 13 bonds
+    two_hubs = _custom_graph(rng, [(0, k) for k in range(2, 12)] + [(1, k) for k in range(2, 12)] + [(0, 1)], 12, fa, fb)
+    chain = _custom_graph(rng, [(k, k + 1) for k in range(63)] + [(0, 63)], 64, fa, fb)        # 128 directed bonds
+    dimer = _custom_graph(rng, [(0, 1)], 2, fa, fb)
+    data = collate_host([star, dimer, two_hubs, chain, star, dimer])
+    meta = dict(fa=fa, fb=fb, depth=3, hidden=96, skip=skip, wseed=4, act="relu")
+    oracle = build_oracle(meta).train()
+    ref = oracle(data)
+    mse_sum_loss(ref, data.y).backward()
+    og = dict(oracle.named_parameters())
+    for engine in ("tc", "simt"):
+        model = build_model(meta, engine=engine).train()
+        d = data.to("cuda")
+        out = model(d)
+        assert model.__dict__["_last_fused_train"] == (engine == "tc")
+        assert scale_normalised_error(out, ref.detach()) < EA_TOL, engine
+        mse_sum_loss(out, d.y).backward()
+        for k, q in model.named_parameters():
+            assert tensor_error(q.grad, og[k].grad) < GRAD_TOL, (engine, k)
+        model.eval()
+        with torch.no_grad():
+            assert scale_normalised_error(model(d), ref.detach()) < EA_TOL           # fused inference kernels
+            assert scale_normalised_error(model(data), ref.detach()) < EA_TOL        # host-buffer entry
