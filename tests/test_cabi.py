@@ -108,3 +108,36 @@ def test_fused_adam_has_torch_adam_interface_and_no_cpu_path():
         FusedAdam([w], lr=-1.0)
     with pytest.raises(ValueError):
         FusedAdam([w], betas=(1.0, 0.999))
+
+
+def test_reference_whole_module_checkpoint_loads_without_torch_geometric():
+    """a checkpoint written by the reference (torch.save(self.model), trainer.py:208) -- classes
+    named cgr_mpnn_3D.models.GNN.*, torch_geometric objects inside -- loads into the B200 module with no torch_geometric
+    installed.  Fixture: tests/golden/ref_module_small.pth, written by the unmodified reference (make_ref_pickle.py)."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from cgr_mpnn_3d_b200.checkpoint import load_reference_checkpoint
+    from cgr_mpnn_3d_b200.model import GNN
+    assert "torch_geometric" not in sys.modules or "_pyg_shim" in (getattr(sys.modules["torch_geometric"], "__file__", "") or "")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    model = load_reference_checkpoint(os.path.join(here, "ref_module_small.pth"), map_location="cpu")
+    z = np.load(os.path.join(here, "ref_module_small.npz"))
+    assert type(model) is GNN and type(model).__module__ == "cgr_mpnn_3D.models.GNN"
+    assert model.depth == 2 and list(model.hidden_sizes) == [32, 32] and list(model.dropout_ps) == [0.1, 0.2]
+    assert model.activation_fn is F.relu and model.use_learnable_skip is True
+    assert model.num_node_features == 78 and model.num_edge_features == 14
+    sd = model.state_dict()
+    keys = [k[2:] for k in z.files if k.startswith("p/")]
+    assert list(sd.keys()) == keys
+    for k in keys:
+        assert torch.equal(sd[k], torch.from_numpy(z["p/" + k])), k
+    # a bare state_dict file (model.state_dict() saved by a user) loads too; hyper-parameters come from the shapes
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "sd.pth")
+        torch.save(sd, path)
+        m2 = load_reference_checkpoint(path, dropout_ps=[0.1, 0.2])
+        assert m2.depth == 2 and m2.use_learnable_skip and all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), sd.values()))

@@ -649,3 +649,18 @@ def test_high_degree_and_full_tile_reactions(skip):
         with torch.no_grad():
             assert scale_normalised_error(model(d), ref.detach()) < EA_TOL           # fused inference kernels
             assert scale_normalised_error(model(data), ref.detach()) < EA_TOL        # host-buffer entry
+
+
+def test_reference_checkpoint_reproduces_reference_outputs():
+    """A whole-module pickle written by the unmodified reference (trainer.py:208) loads through
+    cgr_mpnn_3d_b200.checkpoint and predicts what the reference predicted when it was saved (test.py:93-113)."""
+    import os
+    from cgr_mpnn_3d_b200.checkpoint import load_reference_checkpoint
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, "ref_module_small.npz"))
+    data = make_batch(int(z["nb"]), seed=int(z["dseed"]), kind="t1x", fa=78)
+    for loc in ("cpu", "cuda"):
+        model = load_reference_checkpoint(os.path.join(here, "ref_module_small.pth"), map_location=loc).eval()
+        with torch.no_grad():
+            out = model(data if loc == "cpu" else data.to("cuda"))
+        assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL, loc
