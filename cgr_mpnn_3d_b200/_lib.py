@@ -92,6 +92,9 @@ PROTOTYPES = {
     "cgr_gnn_infer_host_async": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_multi_async": (C.c_int, [C.POINTER(CgrParams), _V, C.c_int32, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_tc_saved_bytes": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph)]),
+    "cgr_tc_plan_host": (C.c_int, [_V, _V, _I64, _V, C.POINTER(C.c_int64)]),
+    "cgr_store_gather": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _V, _V, _V, _I64, C.c_int32, C.c_int32, _I64, _V, _V,
+                                   _V, _V, _V, _V]),
     "cgr_adam_step": (C.c_int, [_V, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64,
                                 C.c_int32, C.c_float, _V]),
     "cgr_infer_host_check": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, _V]),

@@ -464,6 +464,11 @@ extern "C" size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_
   return b;
 }
 
+extern "C" int cgr_tc_plan_host(const int64_t* atom_ptr, const int64_t* edge_ptr, int64_t n_rxn, int32_t* tile_info,
+                                int64_t* n_tiles) {
+  return tc_plan_host(atom_ptr, edge_ptr, n_rxn, tile_info, n_tiles);
+}
+
 extern "C" size_t cgr_tc_saved_bytes(const cgr_params_t* p, const cgr_graph_t* g) {
   if (!p || !g) return 0;
   return tc_saved_bytes(p, g);

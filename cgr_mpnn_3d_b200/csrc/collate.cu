@@ -270,6 +270,72 @@ extern "C" int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_
                                  in_idx, status, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-resident reaction store: the whole featurised data set lives packed in HBM
+// (per-reaction rows are contiguous) and a batch is ASSEMBLED ON THE DEVICE from a list of reaction ids -- what
+// ChemDataset.__getitem__ (data/ChemDataset.py:69-94) + PyG collate (trainer.py:105-118) do per item on the host.
+// One block per selected reaction: block copies of its atom / bond rows, edge_index shifted to batch-global ids,
+// batch vector, label.  HBM-bound copy; outputs are bit-identical to collating the same reactions on the host.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) store_gather_kernel(
+    const float* __restrict__ x_all, const float* __restrict__ ea_all, const int32_t* __restrict__ ei_all,
+    const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr, const float* __restrict__ y_all,
+    int64_t e_all, const int64_t* __restrict__ sel, const int64_t* __restrict__ out_node_ptr,
+    const int64_t* __restrict__ out_edge_ptr, int fa, int fb, int64_t e_out, float* __restrict__ x,
+    float* __restrict__ ea, int64_t* __restrict__ ei, int64_t* __restrict__ batch, float* __restrict__ y) {
+  const int64_t b = blockIdx.x;
+  const int64_t r = sel[b];
+  const int64_t a_in = node_ptr[r], n = node_ptr[r + 1] - a_in, a_out = out_node_ptr[b];
+  const int64_t e_in = edge_ptr[r], e = edge_ptr[r + 1] - e_in, e_o = out_edge_ptr[b];
+  {   // atom rows: n * fa contiguous floats
+    const float* src = x_all + a_in * fa;
+    float* dst = x + a_out * fa;
+    const int64_t total = n * fa;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      const int64_t v = total >> 2;
+      for (int64_t i = threadIdx.x; i < v; i += blockDim.x)
+        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+      for (int64_t i = (v << 2) + threadIdx.x; i < total; i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+      for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+  }
+  {   // bond rows
+    const float* src = ea_all + e_in * fb;
+    float* dst = ea + e_o * fb;
+    const int64_t total = e * fb;
+    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  for (int64_t j = threadIdx.x; j < e; j += blockDim.x) {        // local atom ids -> batch-global ids (int64 like PyG)
+    ei[e_o + j] = (int64_t)__ldg(ei_all + e_in + j) + a_out;
+    ei[e_out + e_o + j] = (int64_t)__ldg(ei_all + e_all + e_in + j) + a_out;
+  }
+  for (int64_t v = threadIdx.x; v < n; v += blockDim.x) batch[a_out + v] = b;
+  if (threadIdx.x == 0) y[b] = __ldg(y_all + r);
+}
+}  // namespace
+
+extern "C" int cgr_store_gather(const float* x_all, const float* ea_all, const int32_t* ei_all, const int64_t* node_ptr,
+                                const int64_t* edge_ptr, const float* y_all, int64_t e_all, const int64_t* sel,
+                                const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t n_sel, int32_t fa,
+                                int32_t fb, int64_t e_out, float* x, float* edge_attr, int64_t* edge_index,
+                                int64_t* batch, float* y, void* stream) {
+  CGR_CHECK_ARG(x_all && ei_all && node_ptr && edge_ptr && y_all && sel && out_node_ptr && out_edge_ptr,
+                "cgr_store_gather: null input");
+  CGR_CHECK_ARG(fb == 0 || ea_all, "cgr_store_gather: edge_attr store missing");
+  CGR_CHECK_ARG(x && edge_index && batch && y && (fb == 0 || edge_attr), "cgr_store_gather: null output");
+  CGR_CHECK_ARG(n_sel >= 0 && fa > 0 && fb >= 0 && e_all >= 0 && e_out >= 0, "cgr_store_gather: bad size");
+  if (n_sel == 0) return CGR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cgr_note_launch("store_gather", st, 1);
+  store_gather_kernel<<<(unsigned)n_sel, 256, 0, st>>>(x_all, ea_all, ei_all, node_ptr, edge_ptr, y_all, e_all, sel,
+                                                       out_node_ptr, out_edge_ptr, fa, fb, e_out, x, edge_attr,
+                                                       edge_index, batch, y);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
 extern "C" size_t cgr_collate_workspace(int64_t n_rxn) {
   return (size_t)(cgr_ceil_div(n_rxn > 0 ? n_rxn : 1, SCAN_TILE) + 1) * sizeof(int64_t);
 }

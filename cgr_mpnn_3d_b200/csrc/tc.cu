@@ -405,6 +405,8 @@ constexpr int NT_SMALL = 256;     // narrow slices run two CTAs per SM: one CTA'
 // Slice width: wide slices (208) amortise the A-operand fetch of the SS-mode MMA and halve the A re-reads;
 // narrow slices (80) give small batches enough CTAs to occupy the 148 SMs.
 int choose_bn(int64_t m_tiles, int64_t n_total) {
+  static const int forced = getenv("CGR_BN") ? atoi(getenv("CGR_BN")) : 0;     // experiments: force a slice width
+  if (forced == BN_LARGE || forced == BN_SMALL) return forced;
   return m_tiles * cgr_ceil_div(n_total, BN_LARGE) >= 148 ? BN_LARGE : BN_SMALL;
 }
 int chunk_cols(int bn) { return bn > 128 ? bn / 2 : bn; }
@@ -488,6 +490,34 @@ int tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, const int32_t*
   cgr_note_launch("tc_plan", st, 1);
   tile_plan_kernel<<<1, 256, (2 * 2048 + 2) * sizeof(int32_t), st>>>(in_ptr, atom_ptr, n_rxn, tile_info, status);
   CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+// Host-side twin of tile_plan_kernel for callers that already know the per-reaction offsets (reaction store, host
+// entry): same greedy rule, no device work, no synchronisation.  tile_info is a HOST array of [n_rxn][8] ints.
+int tc_plan_host(const int64_t* atom_ptr, const int64_t* edge_ptr, int64_t n_rxn, int32_t* tile_info, int64_t* n_tiles) {
+  CGR_CHECK_ARG(atom_ptr && edge_ptr && tile_info && n_tiles && n_rxn > 0, "tc_plan_host: bad argument");
+  int64_t t = -1;
+  int used_e = TM + 1, used_a = TM + 1;
+  for (int64_t g = 0; g < n_rxn; ++g) {
+    const int64_t ne = edge_ptr[g + 1] - edge_ptr[g], na = atom_ptr[g + 1] - atom_ptr[g];
+    if (ne > TM || na > TM || ne <= 0 || na <= 0 || (ne & 1)) {
+      cgr_set_error("reaction %lld has %lld bonds / %lld atoms: not tileable for the tcgen05 engine", (long long)g,
+                    (long long)ne, (long long)na);
+      return CGR_ERR_UNSUPPORTED;
+    }
+    if (used_e + ne > TM || used_a + na > TM) {
+      ++t;
+      int32_t* ti = tile_info + t * 8;
+      ti[0] = (int32_t)edge_ptr[g]; ti[1] = 0; ti[2] = (int32_t)atom_ptr[g]; ti[3] = 0; ti[4] = (int32_t)g; ti[5] = 0;
+      ti[6] = 0; ti[7] = 0;
+      used_e = 0; used_a = 0;
+    }
+    used_e += (int)ne; used_a += (int)na;
+    int32_t* ti = tile_info + t * 8;
+    ti[1] = used_e; ti[3] = used_a; ti[5] += 1;
+  }
+  *n_tiles = t + 1;
   return CGR_OK;
 }
 

@@ -20,6 +20,7 @@ size_t tc_weights_bytes(const cgr_params_t* p);
 int tc_prepare_weights(const cgr_params_t* p, void* wbuf, size_t wbuf_bytes, cudaStream_t st);
 int tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, const int32_t* src, const int32_t* dst,
                   int64_t n_rxn, int32_t* tile_info, int32_t* status, cudaStream_t st);
+int tc_plan_host(const int64_t* atom_ptr, const int64_t* edge_ptr, int64_t n_rxn, int32_t* tile_info, int64_t* n_tiles);
 int tc_plan_check(const int32_t* tile_info, int64_t n_tiles, const int32_t* src, const int32_t* dst, int32_t* status,
                   cudaStream_t st);
 size_t tc_linear_workspace(int64_t M, int64_t N, int64_t K);

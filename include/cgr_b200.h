@@ -271,10 +271,32 @@ int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_host_batch_t
                                    float* host_out, void* dev_ws, size_t dev_bytes, void* host_ws,
                                    size_t host_bytes, void* stream);
 
+/* Host-side tile plan for callers that know the per-reaction offsets (HOST arrays atom_ptr / edge_ptr [n_rxn + 1]):
+ * the greedy packing of cgr_tc_plan_build without device work or a synchronisation.  tile_info: HOST [n_rxn][8] ints,
+ * to be uploaded as cgr_graph_t.tile_info.  Returns CGR_ERR_UNSUPPORTED (-3) when a reaction exceeds a 128-row tile. */
+int cgr_tc_plan_host(const int64_t* atom_ptr, const int64_t* edge_ptr, int64_t n_rxn, int32_t* tile_info,
+                     int64_t* n_tiles);
+
 /* Bytes of cgr_saved_t.tc_blob for the fused tile-local training path of the tcgen05 engine, or 0 when the
  * configuration cannot use it (needs ReLU, a tile plan in `g`, hidden % 4 == 0 and <= 1024): then leave tc_blob
  * NULL and provide the layer-wise buffers. */
 size_t cgr_tc_saved_bytes(const cgr_params_t* p, const cgr_graph_t* g);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident reaction store.  The featurised data set is kept packed in device memory
+ * -- x_all [N_all, fa], ea_all [E_all, fb], ei_all [2, E_all] reaction-LOCAL atom ids (int32), node_ptr / edge_ptr
+ * [R + 1] (int64), y_all [R] -- and one call assembles the batch of the reactions `sel` [n_sel] (any order, repeats
+ * allowed): x, edge_attr, edge_index [2, e_out] (int64, batch-global ids), batch [n_out], y [n_sel].  The caller
+ * supplies the output offsets out_node_ptr / out_edge_ptr [n_sel + 1] (exclusive scans of the selected sizes; they
+ * are the batch's `ptr` / `edge_ptr`), all device pointers.  Replaces ChemDataset.__getitem__ + molgraph2data
+ * (data/ChemDataset.py:69-94, float32 concatenation of CGR and MACE features) and PyG's collate
+ * (training/trainer.py:105-118) for a data set that fits in HBM; results are bit-identical to the host collate.
+ * ---------------------------------------------------------------------------------------- */
+int cgr_store_gather(const float* x_all, const float* ea_all, const int32_t* ei_all, const int64_t* node_ptr,
+                     const int64_t* edge_ptr, const float* y_all, int64_t e_all, const int64_t* sel,
+                     const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t n_sel, int32_t fa, int32_t fb,
+                     int64_t e_out, float* x, float* edge_attr, int64_t* edge_index, int64_t* batch, float* y,
+                     void* stream);
 
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,

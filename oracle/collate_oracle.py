@@ -106,3 +106,21 @@ def tile_plan(ptr: np.ndarray, edge_ptr: np.ndarray, tile_rows: int = 128) -> Di
     tile_first.append(b)
     return {"ok": np.array(1), "tile_of": tile_of, "row0": row0, "atom0": atom0,
             "tile_first": np.array(tile_first, dtype=np.int32)}
+
+
+def gather_batch(graphs, indices):
+    """What ``ReactionStore.batch(indices)`` must return: ChemDataset.__getitem__ (data/ChemDataset.py:69-94) for every
+    index followed by PyG collate (training/trainer.py:105-118) -- cat on dim 0, edge_index shifted by the cumulative
+    atom count, batch vector, ptr.  ``graphs`` carry ``x``, ``edge_index`` (local ids), ``edge_attr``, ``y``."""
+    sel = [graphs[int(i)] for i in indices]
+    n = np.array([g.x.shape[0] for g in sel], dtype=np.int64)
+    ptr = np.zeros(len(sel) + 1, dtype=np.int64)
+    np.cumsum(n, out=ptr[1:])
+    return {
+        "x": np.concatenate([np.asarray(g.x, dtype=np.float32) for g in sel], axis=0),
+        "edge_attr": np.concatenate([np.asarray(g.edge_attr, dtype=np.float32) for g in sel], axis=0),
+        "edge_index": np.concatenate([np.asarray(g.edge_index, dtype=np.int64) + ptr[i] for i, g in enumerate(sel)], axis=1),
+        "batch": np.repeat(np.arange(len(sel), dtype=np.int64), n),
+        "ptr": ptr,
+        "y": np.concatenate([np.asarray(g.y, dtype=np.float32).reshape(-1)[:1] for g in sel]),
+    }

@@ -141,3 +141,13 @@ def test_reference_whole_module_checkpoint_loads_without_torch_geometric():
         torch.save(sd, path)
         m2 = load_reference_checkpoint(path, dropout_ps=[0.1, 0.2])
         assert m2.depth == 2 and m2.use_learnable_skip and all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), sd.values()))
+
+
+def test_reaction_store_is_device_only():
+    """The packed reaction store lives in GPU memory; a CPU device is refused, not emulated."""
+    import numpy as np
+    import pytest
+    from cgr_mpnn_3d_b200.data import make_reactions
+    from cgr_mpnn_3d_b200.store import ReactionStore
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ReactionStore.from_graphs(make_reactions(3, seed=0, kind="t1x", fa=8), device="cpu")

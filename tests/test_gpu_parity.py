@@ -664,3 +664,52 @@ def test_reference_checkpoint_reproduces_reference_outputs():
         with torch.no_grad():
             out = model(data if loc == "cpu" else data.to("cuda"))
         assert scale_normalised_error(out, torch.from_numpy(z["out"])) < EA_TOL, loc
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident reaction store: batch assembly on the GPU, bit-exact against the host collate
+def test_reaction_store_batches_match_host_collate(tmp_path):
+    from cgr_mpnn_3d_b200.data import Graph, collate_host
+    from cgr_mpnn_3d_b200.store import ReactionStore
+    graphs2d = make_reactions(40, seed=3, kind="t1x", fa=78)
+    rng = np.random.default_rng(0)
+    f3d = 24
+    mace = [rng.standard_normal((g.num_nodes, f3d)).astype(np.float64 if i % 2 else np.float32) for i, g in enumerate(graphs2d)]
+    np.savez(tmp_path / "feat.npz", *mace)                               # arr_0, arr_1, ... (download_preprocess_datasets.py:142)
+    labels = rng.standard_normal(len(graphs2d)).astype(np.float32)
+    with open(tmp_path / "data.csv", "w") as f:
+        f.write("smiles,ea\n" + "".join(f"rxn{i},{float(v)!r}\n" for i, v in enumerate(labels)))
+    store = ReactionStore.from_reference_files(graphs2d, str(tmp_path / "data.csv"), str(tmp_path / "feat.npz"))
+    assert len(store) == 40 and store.fa == 78 + f3d and store.x_all.dtype == torch.float32
+    full = [Graph(x=np.concatenate([g.x, m.astype(np.float32)], axis=1), edge_index=g.edge_index, edge_attr=g.edge_attr,
+                  y=np.array([labels[i]], dtype=np.float32)) for i, (g, m) in enumerate(zip(graphs2d, mace))]
+    meta = dict(fa=78 + f3d, fb=14, depth=3, hidden=64, skip=True, wseed=6, act="relu")
+    model = build_model(meta, engine="auto").eval()
+    for idx in ([0], [5, 3, 3, 39, 0], list(range(40)), rng.permutation(40)[:17].tolist()):
+        ref = collate_oracle.gather_batch(full, idx)
+        b = store.batch(idx)
+        for k in ("x", "edge_attr", "edge_index", "batch", "ptr", "y"):
+            assert np.array_equal(getattr(b, k).cpu().numpy(), ref[k]), (k, idx)
+        plan = b._cgr_plan
+        csr = collate_oracle.csr_arrays(ref["edge_index"], ref["x"].shape[0])
+        for k, t in (("src", plan.src), ("dst", plan.dst), ("in_ptr", plan.in_ptr), ("in_idx", plan.in_idx)):
+            assert np.array_equal(t.cpu().numpy(), csr[k]), k
+        assert int(plan.status.item()) == 0
+        eptr = np.concatenate([[0], np.cumsum([full[i].num_edges for i in idx])]).astype(np.int64)
+        tf = collate_oracle.tile_plan(ref["ptr"], eptr)["tile_first"]
+        assert plan.tc_ok and plan.n_tiles == tf.size - 1
+        info = plan.tile_info.cpu().numpy()[: plan.n_tiles]
+        assert np.array_equal(info[:, 4], tf[:-1]) and np.array_equal(info[:, 5], np.diff(tf))
+        assert np.array_equal(info[:, 0], eptr[tf[:-1]]) and np.array_equal(info[:, 1], eptr[tf[1:]] - eptr[tf[:-1]])
+        assert np.array_equal(info[:, 2], ref["ptr"][tf[:-1]]) and np.array_equal(info[:, 3], ref["ptr"][tf[1:]] - ref["ptr"][tf[:-1]])
+        host = collate_host([full[i] for i in idx])
+        with torch.no_grad():
+            assert torch.equal(model(b), model(host.to("cuda")))         # same kernels, same inputs
+    seen = torch.cat([bt.y for bt in store.loader(16, shuffle=True, seed=1)]).cpu().numpy()
+    assert seen.shape[0] == 40 and np.array_equal(np.sort(seen), np.sort(labels))
+    assert sum(1 for _ in store.loader(16, drop_last=True)) == 2
+    # training straight from the store
+    model.train()
+    bt = store.batch(list(range(8)))
+    mse_sum_loss(model(bt), bt.y).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
