@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over")
     ap.add_argument("--coalesce", type=int, default=8,
                     help="host batches predict_stream submits together in the e2e leg (1 = one submission per batch)")
+    ap.add_argument("--store", action="store_true",
+                    help="also time inference over a device-resident reaction store (no per-step feature copies)")
     ap.add_argument("--train", action="store_true", help="also time the training step (fwd+loss+bwd[+allreduce])")
     return ap.parse_args()
 
@@ -432,6 +434,29 @@ def main():
         e2e = {"seconds": e2e_s, "single_call_seconds": e2e_single_s, "uncoalesced_seconds": e2e_uncoalesced_s,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.numel() * 4), "h2d_peak_gbs": h2d_peak_gbs}
 
+    # ---- optional leg: device-resident reaction store (features stay in HBM, batches assembled by a kernel) ----
+    store_leg = None
+    if args.store:
+        from cgr_mpnn_3d_b200.data import make_reactions
+        from cgr_mpnn_3d_b200.store import ReactionStore
+        n_store = max(4096, 4 * args.batch)
+        store = ReactionStore.from_graphs(make_reactions(n_store, seed=9000 + rank, kind="t1x", fa=FA), device=dev)
+        with torch.no_grad():
+            for bt in store.loader(args.batch, shuffle=True, seed=0):          # warm-up pass
+                model(bt)
+            barrier()
+            t0 = time.perf_counter()
+            n_rx, ep = 0, 0
+            while n_rx < args.batch * args.steps:
+                for bt in store.loader(args.batch, shuffle=True, seed=1 + ep):
+                    out_r = model(bt)
+                    n_rx += int(bt.y.numel())
+                ep += 1
+            barrier()
+            store_leg = {"seconds": time.perf_counter() - t0, "reactions": n_rx, "store_bytes": store.nbytes(),
+                        "store_reactions": len(store)}
+        del store
+
     # ---- optional leg 4: training step (forward + MSE(sum) + explicit backward + gradient SUM all-reduce) ----
     train = None
     if args.train:
@@ -578,6 +603,12 @@ def main():
                                                         "launches, timed apart from the step above (train.py:117-119)"},
                                   "what": "forward + MSE(sum) + explicit backward + flat gradient SUM all-reduce "
                                           "(optimizer excluded), batch %d/GPU, whole step replayed as a CUDA graph" % args.batch}
+        if store_leg:
+            line["resident_store"] = {"value": store_leg["reactions"] * world / store_leg["seconds"], "unit": "reactions/s",
+                                      "store_reactions": store_leg["store_reactions"], "store_bytes": store_leg["store_bytes"],
+                                      "what": "shuffled epochs over a ReactionStore held in HBM: per step one small index "
+                                              "upload, the gather kernel, one-launch CSR and the forward (eager launches); "
+                                              "no host-to-device copy of features"}
         if e2e:
             line["e2e"] = {"value": total_rxn / e2e_s, "unit": "reactions/s",
                            "api": "GNN.predict_stream(host batches of %d, depth=4, workers=2, coalesce=%d): every step's "
