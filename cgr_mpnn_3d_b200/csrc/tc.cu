@@ -16,6 +16,7 @@
 
 #include <math.h>
 #include <mutex>
+#include <unordered_map>
 #include <stdlib.h>
 #include <string.h>
 
@@ -304,36 +305,65 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (pointer, shape, stride, box, type, swizzle).  The allocator hands the same
+// buffers back step after step, so the encoded descriptors are cached per host thread (cuTensorMapEncodeTiled costs
+// about a microsecond and a forward needs ~30 of them).
+struct MapKey {
+  const void* p;
+  uint64_t d0, d1, stride;
+  uint32_t b0, b1;
+  int dtype, swizzle;
+  bool operator==(const MapKey& o) const {
+    return p == o.p && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1 && dtype == o.dtype &&
+           swizzle == o.swizzle;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.p * 0x9E3779B97F4A7C15ull;
+    h ^= (k.d0 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.d1 * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (k.stride + ((uint64_t)k.b0 << 32) + k.b1 + ((uint64_t)k.dtype << 20) + ((uint64_t)k.swizzle << 28) + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
+int encode_map_cached(CUtensorMap* tm, CUtensorMapDataType dtype, const void* basep, uint64_t d0, uint64_t d1,
+                      uint64_t stride_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle swz) {
+  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static const bool use_cache = getenv("CGR_NO_MAP_CACHE") == nullptr;
+  const MapKey key{basep, d0, d1, stride_bytes, b0, b1, (int)dtype, (int)swz};
+  if (use_cache) {
+    auto it = cache.find(key);
+    if (it != cache.end()) { memcpy(tm, &it->second, sizeof(CUtensorMap)); return CGR_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dtype, 2, (void*)basep, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cgr_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CGR_ERR_ARG; }
+  if (use_cache) {
+    if (cache.size() >= 1024) cache.clear();
+    cache.emplace(key, *tm);
+  }
+  return CGR_OK;
+}
+
 // fp16 matrix [rows, cols] with row stride `ld` elements; box = [box_rows, 64 cols]; 128-byte swizzle;
 // out-of-bounds elements (K tail, row tail) are zero-filled by the TMA unit.
 int make_map(CUtensorMap* tm, const __half* basep, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)basep, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { cgr_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CGR_ERR_ARG; }
-  return CGR_OK;
+  return encode_map_cached(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, basep, (uint64_t)cols, (uint64_t)rows,
+                           (uint64_t)ld * sizeof(__half), (uint32_t)BK, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // fp32 matrix [rows, cols], row stride `ld` elements, dense (unswizzled) box [box_rows, box_cols]
 int make_map_f32(CUtensorMap* tm, const float* basep, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                  int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)basep, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { cgr_set_error("cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r); return CGR_ERR_ARG; }
-  return CGR_OK;
+  return encode_map_cached(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, basep, (uint64_t)cols, (uint64_t)rows,
+                           (uint64_t)ld * sizeof(float), (uint32_t)box_cols, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
@@ -1345,18 +1375,13 @@ __global__ void splitk_reduce2_batched_kernel(const ReduceBatchArgs a, int split
 }
 
 int make_operand_maps(CUtensorMap* hi_map, CUtensorMap* lo_map, const TcOperand& op, int64_t mn, int64_t K) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { cgr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CGR_ERR_UNSUPPORTED; }
   // K-major: tensor [mn rows, K cols], box [128 rows, 64 cols];  MN-major: tensor [K rows, mn cols], box [64 rows, 64 cols]
-  cuuint64_t dims[2] = {(cuuint64_t)(op.mn_major ? mn : K), (cuuint64_t)(op.mn_major ? K : mn)};
-  cuuint64_t strides[1] = {(cuuint64_t)op.ld * sizeof(__half)};
-  cuuint32_t box[2] = {64u, op.mn_major ? 64u : 128u};
-  cuuint32_t estr[2] = {1, 1};
   for (int h = 0; h < 2; ++h) {
-    CUresult r = fn(h ? lo_map : hi_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)(h ? op.lo : op.hi), dims, strides, box,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { cgr_set_error("cuTensorMapEncodeTiled(gemm2) failed with CUresult %d", (int)r); return CGR_ERR_ARG; }
+    const int rc = encode_map_cached(h ? lo_map : hi_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h ? op.lo : op.hi,
+                                     (uint64_t)(op.mn_major ? mn : K), (uint64_t)(op.mn_major ? K : mn),
+                                     (uint64_t)op.ld * sizeof(__half), 64u, op.mn_major ? 64u : 128u,
+                                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
   }
   return CGR_OK;
 }

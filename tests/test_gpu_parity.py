@@ -428,6 +428,18 @@ def test_tc_engine_on_untileable_graphs():
             assert model.__dict__.get("_last_plan") is None                 # not the fused tile path
             assert scale_normalised_error(out, ref) < EA_TOL
         assert scale_normalised_error(build_model(meta, engine="auto").eval()(data), ref) < EA_TOL   # host tensors
+    # training on such graphs: layer-wise path with tensor-core GEMMs (the fused tile-local kernels do not apply)
+    oracle.train()
+    oref = oracle(data)
+    mse_sum_loss(oref, data.y).backward()
+    og = dict(oracle.named_parameters())
+    model = build_model(meta, engine="tc").train()
+    d = data.to("cuda")
+    out = model(d)
+    assert model.__dict__["_last_fused_train"] is False
+    mse_sum_loss(out, d.y).backward()
+    for k, q in model.named_parameters():
+        assert tensor_error(q.grad, og[k].grad) < GRAD_TOL, k
 
 
 # ---------------------------------------------------------------------------------------------
