@@ -659,6 +659,7 @@ struct HostInferLayout {
   int64_t t_max, kp_x;
   size_t o_x, o_ea, o_ei, o_meta, o_src, o_dst, o_inidx, o_inptr, o_status, o_xhi, o_xlo, o_out, o_fwd, dev_total;
   size_t meta_ints, fwd_bytes, host_total;
+  size_t stage_bytes;          // [edge_attr | edge_index | meta]: contiguous on the device, mirrored in pinned host memory
 };
 HostInferLayout host_infer_layout(const cgr_params_t* p, int64_t N, int64_t E, int64_t B) {
   HostInferLayout L;
@@ -689,7 +690,9 @@ HostInferLayout host_infer_layout(const cgr_params_t* p, int64_t N, int64_t E, i
   L.fwd_bytes = tc_forward_workspace(&pp, &g, 0);
   L.o_fwd = take(L.fwd_bytes);
   L.dev_total = off + 1024;
-  L.host_total = cgr_align_up(L.meta_ints * 4, 256) + 256;
+  // the small inputs travel as ONE copy: the host workspace mirrors the device span [o_ea, o_meta + meta)
+  L.stage_bytes = cgr_align_up(L.o_meta + L.meta_ints * 4 - L.o_ea, 256);
+  L.host_total = L.stage_bytes + 256;
   return L;
 }
 }  // namespace
@@ -726,12 +729,15 @@ extern "C" int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_h
   CGR_CHECK_ARG(dev_bytes >= L.dev_total && host_bytes >= L.host_total, "cgr_gnn_infer_host: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   char* dws = (char*)(((uintptr_t)dev_ws + 1023) & ~(uintptr_t)1023);
-  int32_t* h_meta = (int32_t*)host_ws;
+  char* h_stage = (char*)host_ws;                                   // mirrors the device span that starts at o_ea
+  float* h_ea = (float*)h_stage;
+  int64_t* h_ei = (int64_t*)(h_stage + (L.o_ei - L.o_ea));
+  int32_t* h_meta = (int32_t*)(h_stage + (L.o_meta - L.o_ea));
   int32_t* h_tiles = h_meta;
   int32_t* h_aptr = h_meta + (size_t)L.t_max * 8;
   int32_t* h_eptr = h_aptr + (B + 1);
   int32_t* h_shift = h_eptr + (B + 1);
-  int32_t* h_flags = (int32_t*)((char*)host_ws + cgr_align_up(L.meta_ints * 4, 256));
+  int32_t* h_flags = (int32_t*)(h_stage + L.stage_bytes);
 
   // ---- host side: per-reaction offsets of the super-batch (host batches laid end to end) ----
   {
@@ -795,25 +801,21 @@ extern "C" int cgr_gnn_infer_host_multi_async(const cgr_params_t* p, const cgr_h
   int32_t* d_meta = (int32_t*)(dws + L.o_meta);
   int32_t* d_status = (int32_t*)(dws + L.o_status);
   float* d_out = (float*)(dws + L.o_out);
-  CGR_CUDA(cudaMemcpyAsync(d_meta, h_meta, L.meta_ints * 4, cudaMemcpyHostToDevice, st));
+  // Atom features (the bulk) are copied straight from each batch's own buffer; bond features, edge_index and the
+  // offsets are gathered into the pinned staging area by this host thread and travel as ONE copy (small copies cost
+  // the link a few microseconds each, whatever their size).
   {
     int64_t a_off = 0, e_off = 0;
     for (int j = 0; j < n_batches; ++j) {
       const cgr_host_batch_t& hb = batches[j];
-      if (n_batches == 1) {
-        CGR_CUDA(cudaMemcpyAsync(d_ei, hb.edge_index, (size_t)2 * E * 8, cudaMemcpyHostToDevice, st));
-      } else {                                     // rows of [2, E_j] go to their slices of the [2, E] super-batch
-        CGR_CUDA(cudaMemcpyAsync(d_ei + e_off, hb.edge_index, (size_t)hb.n_bonds * 8, cudaMemcpyHostToDevice, st));
-        CGR_CUDA(cudaMemcpyAsync(d_ei + E + e_off, hb.edge_index + hb.n_bonds, (size_t)hb.n_bonds * 8,
-                                 cudaMemcpyHostToDevice, st));
-      }
       CGR_CUDA(cudaMemcpyAsync(d_x + (size_t)a_off * p->fa, hb.x, (size_t)hb.n_atoms * p->fa * 4,
                                cudaMemcpyHostToDevice, st));
-      if (p->fb > 0)
-        CGR_CUDA(cudaMemcpyAsync(d_ea + (size_t)e_off * p->fb, hb.edge_attr, (size_t)hb.n_bonds * p->fb * 4,
-                                 cudaMemcpyHostToDevice, st));
+      if (p->fb > 0) memcpy(h_ea + (size_t)e_off * p->fb, hb.edge_attr, (size_t)hb.n_bonds * p->fb * 4);
+      memcpy(h_ei + e_off, hb.edge_index, (size_t)hb.n_bonds * 8);                       // row 0 of [2, E_j]
+      memcpy(h_ei + E + e_off, hb.edge_index + hb.n_bonds, (size_t)hb.n_bonds * 8);      // row 1
       a_off += hb.n_atoms; e_off += hb.n_bonds;
     }
+    CGR_CUDA(cudaMemcpyAsync(dws + L.o_ea, h_stage, L.o_meta + L.meta_ints * 4 - L.o_ea, cudaMemcpyHostToDevice, st));
   }
   CGR_CUDA(cudaMemsetAsync(d_status, 0, (size_t)(2 + L.t_max) * 4, st));
   cgr_graph_t g;
@@ -854,7 +856,7 @@ extern "C" int cgr_infer_host_check(const cgr_params_t* p, int64_t n_atoms, int6
                                     const void* host_ws) {
   CGR_CHECK_ARG(p && host_ws, "cgr_infer_host_check: null pointer");
   const HostInferLayout L = host_infer_layout(p, n_atoms, n_bonds, n_rxn);
-  const int32_t* h_flags = (const int32_t*)((const char*)host_ws + cgr_align_up(L.meta_ints * 4, 256));
+  const int32_t* h_flags = (const int32_t*)((const char*)host_ws + L.stage_bytes);
   if (h_flags[0] & 1) { cgr_set_error("directed bonds are not adjacent (e, e^1) reverse pairs"); return CGR_ERR_ARG; }
   if (h_flags[0] & 2) { cgr_set_error("a bond leaves its reaction's atom range"); return CGR_ERR_ARG; }
   if (h_flags[0] & 4) { cgr_set_error("an atom has no incoming bond (reference GNN.py:106 raises on this input)"); return CGR_ERR_ARG; }
