@@ -59,6 +59,14 @@ class CgrHostBatch(C.Structure):
     ]
 
 
+class CgrStore(C.Structure):
+    _fields_ = [
+        ("x_all", C.c_void_p), ("ea_all", C.c_void_p), ("ei_all", C.c_void_p), ("node_ptr", C.c_void_p),
+        ("edge_ptr", C.c_void_p), ("node_ptr_host", C.c_void_p), ("edge_ptr_host", C.c_void_p),
+        ("n_rxn", C.c_int64), ("e_all", C.c_int64), ("fa", C.c_int32), ("fb", C.c_int32),
+    ]
+
+
 class CgrAdamTensor(C.Structure):
     _fields_ = [
         ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
@@ -93,6 +101,10 @@ PROTOTYPES = {
     "cgr_gnn_infer_host_multi_async": (C.c_int, [C.POINTER(CgrParams), _V, C.c_int32, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_tc_saved_bytes": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph)]),
     "cgr_tc_plan_host": (C.c_int, [_V, _V, _I64, _V, C.POINTER(C.c_int64)]),
+    "cgr_store_infer_workspace": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrStore), _V, _I64, _I64, C.POINTER(_SZ),
+                                            C.POINTER(_SZ)]),
+    "cgr_store_infer": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrStore), _V, _I64, _I64, _V, _V, _SZ, _V, _SZ,
+                                  C.c_int32, _V]),
     "cgr_store_gather": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _V, _V, _V, _I64, C.c_int32, C.c_int32, _I64, _V, _V,
                                    _V, _V, _V, _V]),
     "cgr_adam_step": (C.c_int, [_V, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64,

@@ -852,6 +852,172 @@ extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host
   return cgr_gnn_infer_host_multi_async(p, &hb, 1, host_out, dev_ws, dev_bytes, host_ws, host_bytes, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Inference over a device-resident reaction store: the per-batch loop in C, pipelined over
+// streams.  Per batch: offsets + tile plan on the host, one small upload, gather kernel, one-launch CSR, feature
+// split, the 7 forward kernels writing straight into the caller's result vector.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct StoreBatchSizes { int64_t n_max, e_max, b_max; };
+int store_batch_sizes(const cgr_store_t* s, const int64_t* order, int64_t n_total, int64_t bs, StoreBatchSizes* out) {
+  int64_t n_max = 0, e_max = 0;
+  for (int64_t lo = 0; lo < n_total; lo += bs) {
+    const int64_t hi = lo + bs < n_total ? lo + bs : n_total;
+    int64_t n = 0, e = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+      const int64_t r = order[i];
+      CGR_CHECK_ARG(r >= 0 && r < s->n_rxn, "cgr_store_infer: reaction id %lld out of range", (long long)r);
+      n += s->node_ptr_host[r + 1] - s->node_ptr_host[r];
+      e += s->edge_ptr_host[r + 1] - s->edge_ptr_host[r];
+    }
+    if (n > n_max) n_max = n;
+    if (e > e_max) e_max = e;
+  }
+  out->n_max = n_max; out->e_max = e_max; out->b_max = bs < n_total ? bs : n_total;
+  return CGR_OK;
+}
+// host staging of one slot: [sel | out_node_ptr | out_edge_ptr] (int64) then the int32 meta block of the host entry
+size_t store_sel_bytes(int64_t b_max) { return cgr_align_up((size_t)(3 * b_max + 2) * 8, 1024); }
+}  // namespace
+
+extern "C" int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order,
+                                         int64_t n_total, int64_t batch_size, size_t* dev_bytes_per_slot,
+                                         size_t* host_bytes_per_slot) {
+  CGR_CHECK_ARG(p && store && order && n_total > 0 && batch_size > 0 && dev_bytes_per_slot && host_bytes_per_slot,
+                "cgr_store_infer_workspace: bad argument");
+  StoreBatchSizes z;
+  int rc = store_batch_sizes(store, order, n_total, batch_size, &z);
+  if (rc) return rc;
+  const HostInferLayout L = host_infer_layout(p, z.n_max, z.e_max, z.b_max);
+  *dev_bytes_per_slot = cgr_align_up(L.dev_total + store_sel_bytes(z.b_max) + 1024, 1024);
+  *host_bytes_per_slot = cgr_align_up(store_sel_bytes(z.b_max) + L.meta_ints * 4 + 1024, 1024);
+  return CGR_OK;
+}
+
+extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order, int64_t n_total,
+                               int64_t batch_size, float* out, void* dev_ws, size_t dev_bytes_per_slot, void* host_ws,
+                               size_t host_bytes_per_slot, int32_t n_slots, void* const* streams) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  CGR_CHECK_ARG(store && order && out && dev_ws && host_ws && streams && n_slots > 0 && n_total > 0 && batch_size > 0,
+                "cgr_store_infer: bad argument");
+  CGR_CHECK_ARG(p->tc_weights, "cgr_store_infer: prepare the weights first (cgr_tc_prepare_weights)");
+  CGR_CHECK_ARG(store->fa == p->fa && store->fb == p->fb, "cgr_store_infer: feature widths of store and model differ");
+  StoreBatchSizes z;
+  if ((rc = store_batch_sizes(store, order, n_total, batch_size, &z))) return rc;
+  const HostInferLayout Lmax = host_infer_layout(p, z.n_max, z.e_max, z.b_max);
+  const size_t sel_bytes = store_sel_bytes(z.b_max);
+  CGR_CHECK_ARG(dev_bytes_per_slot >= Lmax.dev_total + sel_bytes + 1024 &&
+                    host_bytes_per_slot >= sel_bytes + Lmax.meta_ints * 4 + 1024, "cgr_store_infer: workspace too small");
+  std::vector<cudaEvent_t> ev((size_t)n_slots, nullptr);
+  std::vector<char> used((size_t)n_slots, 0);
+  auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); };
+  for (int s = 0; s < n_slots; ++s)
+    if (cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming) != cudaSuccess) { cleanup(); cgr_set_error("cudaEventCreate failed"); return CGR_ERR_ARG; }
+  cgr_params_t pp = *p;
+  pp.tc_throughput = 1;                      // several batches in flight
+  const HostInferLayout& L = Lmax;           // one layout for every batch: fixed offsets, sizes vary
+  // status words of a slot: [0] validity flags and [1] fp16-range flag are sticky (atomicOr), the readout counters behind
+  // them reset themselves -- cleared once, read back once
+  rc = CGR_OK;
+  for (int s = 0; s < n_slots && rc == CGR_OK; ++s) {
+    char* dbase = (char*)(((uintptr_t)dev_ws + (size_t)s * dev_bytes_per_slot + 1023) & ~(uintptr_t)1023);
+    const cudaError_t e = cudaMemsetAsync(dbase + sel_bytes + L.o_status, 0, (size_t)(2 + L.t_max) * 4, (cudaStream_t)streams[s]);
+    if (e != cudaSuccess) { cgr_set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); rc = (int)e; }
+  }
+  int64_t it = 0;
+  for (int64_t lo = 0; lo < n_total && rc == CGR_OK; lo += batch_size, ++it) {
+    const int slot = (int)(it % n_slots);
+    cudaStream_t st = (cudaStream_t)streams[slot];
+    const int64_t B = lo + batch_size < n_total ? batch_size : n_total - lo;
+    char* hws = (char*)host_ws + (size_t)slot * host_bytes_per_slot;
+    char* dbase = (char*)(((uintptr_t)dev_ws + (size_t)slot * dev_bytes_per_slot + 1023) & ~(uintptr_t)1023);
+    // the previous batch of this slot must have consumed the pinned staging area
+    if (used[slot] && cudaEventSynchronize(ev[slot]) != cudaSuccess) { rc = CGR_ERR_ARG; cgr_set_error("event sync failed"); break; }
+    int64_t* h_sel = (int64_t*)hws;
+    int64_t* h_optr = h_sel + B;
+    int64_t* h_oeptr = h_optr + (B + 1);
+    h_optr[0] = 0; h_oeptr[0] = 0;
+    for (int64_t i = 0; i < B; ++i) {
+      const int64_t r = order[lo + i];
+      h_sel[i] = r;
+      h_optr[i + 1] = h_optr[i] + (store->node_ptr_host[r + 1] - store->node_ptr_host[r]);
+      h_oeptr[i + 1] = h_oeptr[i] + (store->edge_ptr_host[r + 1] - store->edge_ptr_host[r]);
+    }
+    const int64_t N = h_optr[B], E = h_oeptr[B];
+    int32_t* h_meta = (int32_t*)(hws + sel_bytes);
+    int32_t* h_tiles = h_meta;
+    int32_t* h_aptr = h_meta + (size_t)L.t_max * 8;
+    int32_t* h_eptr = h_aptr + (B + 1);
+    for (int64_t i = 0; i <= B; ++i) { h_aptr[i] = (int32_t)h_optr[i]; h_eptr[i] = (int32_t)h_oeptr[i]; }
+    int64_t T = 0;
+    rc = tc_plan_host(h_optr, h_oeptr, B, h_tiles, &T);
+    if (rc) break;
+    if (T > L.t_max) { cgr_set_error("tile bound exceeded"); rc = CGR_ERR_WORKSPACE; break; }
+    // device slot: [sel block | host-entry layout]
+    int64_t* d_sel = (int64_t*)dbase;
+    char* dws = dbase + sel_bytes;
+    float* d_x = (float*)(dws + L.o_x);
+    float* d_ea = (float*)(dws + L.o_ea);
+    int64_t* d_ei = (int64_t*)(dws + L.o_ei);
+    int32_t* d_meta = (int32_t*)(dws + L.o_meta);
+    int32_t* d_status = (int32_t*)(dws + L.o_status);
+    auto CK = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess && rc == CGR_OK) { cgr_set_error("%s failed: %s", what, cudaGetErrorString(e)); rc = (int)e; }
+    };
+    CK(cudaMemcpyAsync(d_sel, h_sel, (size_t)(3 * B + 2) * 8, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(sel)");
+    CK(cudaMemcpyAsync(d_meta, h_meta, ((size_t)L.t_max * 8 + 2 * (size_t)(B + 1)) * 4, cudaMemcpyHostToDevice, st),
+       "cudaMemcpyAsync(meta)");
+    CK(cudaEventRecord(ev[slot], st), "cudaEventRecord");
+    used[slot] = 1;
+    if (rc) break;
+    rc = cgr_store_gather(store->x_all, store->ea_all, store->ei_all, store->node_ptr, store->edge_ptr, nullptr,
+                          store->e_all, d_sel, d_sel + B, d_sel + 2 * B + 1, B, p->fa, p->fb, E, d_x, d_ea, d_ei, nullptr,
+                          nullptr, st);
+    if (rc) break;
+    cgr_graph_t g;
+    memset(&g, 0, sizeof(g));
+    g.n_atoms = N; g.n_bonds = E; g.n_rxn = B;
+    g.x = d_x; g.edge_attr = d_ea;
+    g.src = (int32_t*)(dws + L.o_src); g.dst = (int32_t*)(dws + L.o_dst);
+    g.in_ptr = (int32_t*)(dws + L.o_inptr); g.in_idx = (int32_t*)(dws + L.o_inidx);
+    g.tile_info = d_meta; g.n_tiles = T;
+    g.atom_ptr = d_meta + (size_t)L.t_max * 8;
+    g.tc_status = d_status + 1;
+    g.x_hi = dws + L.o_xhi; g.x_lo = dws + L.o_xlo;
+    rc = csr_by_reaction_shifted(d_ei, g.atom_ptr + (B + 1), g.atom_ptr, nullptr, B, E, N, (int32_t*)g.src, (int32_t*)g.dst,
+                                 (int32_t*)g.in_ptr, (int32_t*)g.in_idx, d_status, st);
+    if (rc) break;
+    rc = tc_split_features(d_x, N, p->fa, (void*)g.x_hi, (void*)g.x_lo, g.tc_status, st);
+    if (rc) break;
+    rc = tc_gnn_forward(&pp, &g, out + lo, nullptr, 0, 0, dws + L.o_fwd, L.fwd_bytes, st);
+  }
+  // validity / range flags of every slot
+  for (int s = 0; s < n_slots && rc == CGR_OK; ++s) {
+    char* dbase = (char*)(((uintptr_t)dev_ws + (size_t)s * dev_bytes_per_slot + 1023) & ~(uintptr_t)1023);
+    int32_t* h_flags = (int32_t*)((char*)host_ws + (size_t)s * host_bytes_per_slot + host_bytes_per_slot - 256);
+    const cudaError_t e = cudaMemcpyAsync(h_flags, dbase + sel_bytes + L.o_status, 8, cudaMemcpyDeviceToHost, (cudaStream_t)streams[s]);
+    if (e != cudaSuccess) { cgr_set_error("cudaMemcpyAsync(flags) failed: %s", cudaGetErrorString(e)); rc = (int)e; }
+  }
+  for (int s = 0; s < n_slots; ++s) {
+    const cudaError_t e = cudaStreamSynchronize((cudaStream_t)streams[s]);
+    if (e != cudaSuccess && rc == CGR_OK) { cgr_set_error("stream sync failed: %s", cudaGetErrorString(e)); rc = (int)e; }
+  }
+  cleanup();
+  if (rc == CGR_OK) {
+    int f0 = 0, f1 = 0;
+    for (int s = 0; s < n_slots; ++s) {
+      const int32_t* h_flags = (const int32_t*)((const char*)host_ws + (size_t)s * host_bytes_per_slot + host_bytes_per_slot - 256);
+      f0 |= h_flags[0]; f1 |= h_flags[1];
+    }
+    if (f0 & 1) { cgr_set_error("directed bonds are not adjacent (e, e^1) reverse pairs"); return CGR_ERR_ARG; }
+    if (f0 & 2) { cgr_set_error("a bond leaves its reaction's atom range"); return CGR_ERR_ARG; }
+    if (f0 & 4) { cgr_set_error("an atom has no incoming bond (reference GNN.py:106 raises on this input)"); return CGR_ERR_ARG; }
+    if (f1) { cgr_set_error("an activation exceeded the fp16 range of the FP16x3 split"); return CGR_ERR_UNSUPPORTED; }
+  }
+  return rc;
+}
+
 extern "C" int cgr_infer_host_check(const cgr_params_t* p, int64_t n_atoms, int64_t n_bonds, int64_t n_rxn,
                                     const void* host_ws) {
   CGR_CHECK_ARG(p && host_ws, "cgr_infer_host_check: null pointer");

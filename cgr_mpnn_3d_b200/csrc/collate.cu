@@ -274,45 +274,60 @@ extern "C" int cgr_csr_build_by_reaction(const int64_t* edge_index, const int32_
 // Device-resident reaction store: the whole featurised data set lives packed in HBM
 // (per-reaction rows are contiguous) and a batch is ASSEMBLED ON THE DEVICE from a list of reaction ids -- what
 // ChemDataset.__getitem__ (data/ChemDataset.py:69-94) + PyG collate (trainer.py:105-118) do per item on the host.
-// One block per selected reaction: block copies of its atom / bond rows, edge_index shifted to batch-global ids,
+// SG_PARTS blocks per selected reaction: vector copies of its atom / bond rows, edge_index shifted to batch-global ids,
 // batch vector, label.  HBM-bound copy; outputs are bit-identical to collating the same reactions on the host.
 // ------------------------------------------------------------------------------------------------
 namespace {
+constexpr int SG_PARTS = 8;          // blocks per selected reaction (a T1x reaction moves ~60 kB)
+
+// contiguous copy of `total` floats by part `part` of `parts` blocks, widest vector both pointers allow
+__device__ __forceinline__ void block_copy(const float* __restrict__ src, float* __restrict__ dst, int64_t total, int part,
+                                           int parts) {
+  const uintptr_t mis = (uintptr_t)src | (uintptr_t)dst;
+  const int64_t tid = (int64_t)part * blockDim.x + threadIdx.x, nth = (int64_t)parts * blockDim.x;
+  if ((mis & 15) == 0) {
+    const int64_t v = total >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+    for (int64_t i = tid; i < v; i += nth) d4[i] = __ldg(s4 + i);
+    for (int64_t i = (v << 2) + tid; i < total; i += nth) dst[i] = __ldg(src + i);
+  } else if ((mis & 7) == 0) {
+    const int64_t v = total >> 1;
+    const float2* s2 = reinterpret_cast<const float2*>(src);
+    float2* d2 = reinterpret_cast<float2*>(dst);
+#pragma unroll 4
+    for (int64_t i = tid; i < v; i += nth) d2[i] = __ldg(s2 + i);
+    for (int64_t i = (v << 1) + tid; i < total; i += nth) dst[i] = __ldg(src + i);
+  } else {
+#pragma unroll 4
+    for (int64_t i = tid; i < total; i += nth) dst[i] = __ldg(src + i);
+  }
+}
+
 __global__ void __launch_bounds__(256) store_gather_kernel(
     const float* __restrict__ x_all, const float* __restrict__ ea_all, const int32_t* __restrict__ ei_all,
     const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr, const float* __restrict__ y_all,
     int64_t e_all, const int64_t* __restrict__ sel, const int64_t* __restrict__ out_node_ptr,
     const int64_t* __restrict__ out_edge_ptr, int fa, int fb, int64_t e_out, float* __restrict__ x,
     float* __restrict__ ea, int64_t* __restrict__ ei, int64_t* __restrict__ batch, float* __restrict__ y) {
-  const int64_t b = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int part = blockIdx.x;
   const int64_t r = sel[b];
   const int64_t a_in = node_ptr[r], n = node_ptr[r + 1] - a_in, a_out = out_node_ptr[b];
   const int64_t e_in = edge_ptr[r], e = edge_ptr[r + 1] - e_in, e_o = out_edge_ptr[b];
-  {   // atom rows: n * fa contiguous floats
-    const float* src = x_all + a_in * fa;
-    float* dst = x + a_out * fa;
-    const int64_t total = n * fa;
-    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
-      const int64_t v = total >> 2;
-      for (int64_t i = threadIdx.x; i < v; i += blockDim.x)
-        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-      for (int64_t i = (v << 2) + threadIdx.x; i < total; i += blockDim.x) dst[i] = __ldg(src + i);
-    } else {
-      for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = __ldg(src + i);
+  block_copy(x_all + a_in * fa, x + a_out * fa, n * fa, part, SG_PARTS);                    // atom rows
+  if (fb > 0) block_copy(ea_all + e_in * fb, ea + e_o * fb, e * fb, part, SG_PARTS);         // bond rows
+  if (part == 0) {
+    for (int64_t j = threadIdx.x; j < e; j += blockDim.x) {      // local atom ids -> batch-global ids (int64 like PyG)
+      ei[e_o + j] = (int64_t)__ldg(ei_all + e_in + j) + a_out;
+      ei[e_out + e_o + j] = (int64_t)__ldg(ei_all + e_all + e_in + j) + a_out;
     }
+  } else if (part == 1) {
+    if (batch)
+      for (int64_t v = threadIdx.x; v < n; v += blockDim.x) batch[a_out + v] = b;
+    if (y && threadIdx.x == 0) y[b] = __ldg(y_all + r);
   }
-  {   // bond rows
-    const float* src = ea_all + e_in * fb;
-    float* dst = ea + e_o * fb;
-    const int64_t total = e * fb;
-    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
-  for (int64_t j = threadIdx.x; j < e; j += blockDim.x) {        // local atom ids -> batch-global ids (int64 like PyG)
-    ei[e_o + j] = (int64_t)__ldg(ei_all + e_in + j) + a_out;
-    ei[e_out + e_o + j] = (int64_t)__ldg(ei_all + e_all + e_in + j) + a_out;
-  }
-  for (int64_t v = threadIdx.x; v < n; v += blockDim.x) batch[a_out + v] = b;
-  if (threadIdx.x == 0) y[b] = __ldg(y_all + r);
 }
 }  // namespace
 
@@ -321,15 +336,15 @@ extern "C" int cgr_store_gather(const float* x_all, const float* ea_all, const i
                                 const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t n_sel, int32_t fa,
                                 int32_t fb, int64_t e_out, float* x, float* edge_attr, int64_t* edge_index,
                                 int64_t* batch, float* y, void* stream) {
-  CGR_CHECK_ARG(x_all && ei_all && node_ptr && edge_ptr && y_all && sel && out_node_ptr && out_edge_ptr,
+  CGR_CHECK_ARG(x_all && ei_all && node_ptr && edge_ptr && sel && out_node_ptr && out_edge_ptr && (y_all || !y),
                 "cgr_store_gather: null input");
   CGR_CHECK_ARG(fb == 0 || ea_all, "cgr_store_gather: edge_attr store missing");
-  CGR_CHECK_ARG(x && edge_index && batch && y && (fb == 0 || edge_attr), "cgr_store_gather: null output");
+  CGR_CHECK_ARG(x && edge_index && (fb == 0 || edge_attr), "cgr_store_gather: null output");   // batch / y optional
   CGR_CHECK_ARG(n_sel >= 0 && fa > 0 && fb >= 0 && e_all >= 0 && e_out >= 0, "cgr_store_gather: bad size");
   if (n_sel == 0) return CGR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   cgr_note_launch("store_gather", st, 1);
-  store_gather_kernel<<<(unsigned)n_sel, 256, 0, st>>>(x_all, ea_all, ei_all, node_ptr, edge_ptr, y_all, e_all, sel,
+  store_gather_kernel<<<dim3(SG_PARTS, (unsigned)n_sel), 256, 0, st>>>(x_all, ea_all, ei_all, node_ptr, edge_ptr, y_all, e_all, sel,
                                                        out_node_ptr, out_edge_ptr, fa, fb, e_out, x, edge_attr,
                                                        edge_index, batch, y);
   CGR_LAUNCH_CHECK();

@@ -298,6 +298,30 @@ int cgr_store_gather(const float* x_all, const float* ea_all, const int32_t* ei_
                      int64_t e_out, float* x, float* edge_attr, int64_t* edge_index, int64_t* batch, float* y,
                      void* stream);
 
+/* Inference over a resident store in ONE call (the screening loop of test.py:103-113 / the CLI over a data set that
+ * lives in HBM): for every consecutive `batch_size` ids of `order` (HOST, [n_total]) it assembles the batch on the
+ * device, builds the index arrays and runs the tcgen05 forward, writing the energies to `out` (DEVICE, [n_total], in
+ * `order` order).  Batches are pipelined over `n_slots` streams (`streams`: HOST array of cudaStream_t), each with its
+ * own slice of `dev_ws` (n_slots * dev_bytes_per_slot) and of the pinned `host_ws` (n_slots * host_bytes_per_slot), both
+ * sized by cgr_store_infer_workspace for the largest batch.  Returns after every stream is idle; -3 when a reaction
+ * does not fit a 128-row tile.  p->tc_weights must be prepared. */
+typedef struct {
+  const float* x_all;            /* device */
+  const float* ea_all;
+  const int32_t* ei_all;
+  const int64_t* node_ptr;
+  const int64_t* edge_ptr;
+  const int64_t* node_ptr_host;  /* host copies of the two offset arrays */
+  const int64_t* edge_ptr_host;
+  int64_t n_rxn, e_all;
+  int32_t fa, fb;
+} cgr_store_t;
+int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order, int64_t n_total,
+                              int64_t batch_size, size_t* dev_bytes_per_slot, size_t* host_bytes_per_slot);
+int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order, int64_t n_total,
+                    int64_t batch_size, float* out, void* dev_ws, size_t dev_bytes_per_slot, void* host_ws,
+                    size_t host_bytes_per_slot, int32_t n_slots, void* const* streams);
+
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,
                         float* grad_pred, void* stream);

@@ -717,6 +717,14 @@ def test_reaction_store_batches_match_host_collate(tmp_path):
         host = collate_host([full[i] for i in idx])
         with torch.no_grad():
             assert torch.equal(model(b), model(host.to("cuda")))         # same kernels, same inputs
+    # the whole screening loop in one C call: energies of every reaction, any order, any batch size
+    with torch.no_grad():
+        ref_all = torch.cat([model(bt) for bt in store.loader(7)])
+    for bs, slots in ((7, 3), (64, 8), (1, 2), (16, 1)):
+        assert scale_normalised_error(store.predict(model, batch_size=bs, slots=slots), ref_all) < 1e-5, bs
+    perm = rng.permutation(40)
+    assert scale_normalised_error(store.predict(model, batch_size=9, order=perm), ref_all[torch.from_numpy(perm).cuda()]) < 1e-5
+    assert torch.equal(store.predict(model, batch_size=7, slots=3), store.predict(model, batch_size=7, slots=3))
     seen = torch.cat([bt.y for bt in store.loader(16, shuffle=True, seed=1)]).cpu().numpy()
     assert seen.shape[0] == 40 and np.array_equal(np.sort(seen), np.sort(labels))
     assert sum(1 for _ in store.loader(16, drop_last=True)) == 2
