@@ -209,7 +209,7 @@ def main():
             "e2e": {"value": leg["value"], "unit": "reactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     # ---------------------------------------------------------------- this framework ---------
@@ -638,11 +638,31 @@ def main():
                            "h2d_copy_peak_gbs": e2e["h2d_peak_gbs"],
                            "bound": "host link: h2d_gbs is the per-GPU input traffic the e2e rate implies, "
                                     "h2d_copy_peak_gbs plain pinned 64 MiB cudaMemcpyAsync copies on 4 streams of this box"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line: dict) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout (see _quiet_stdout)."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1 behind Python's back; the contract is ONE
+    JSON line on stdout, so everything else is routed to stderr at the descriptor level."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     sys.exit(main())
