@@ -552,32 +552,51 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
       float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
       float dsk = 0.f;
       if (lane_on) {
-        for (int j = warp; j < ecount; j += NWARPS) {
-          const int64_t r = (int64_t)tile * TM + j;
-          float4 dh = ld4(y_s + j * CHP + c);
-          if (EPI == EPI_INIT_BWD) add4(dh, ld4(r_s + j * CH + c));
-          const uint2 mh = __ldg(reinterpret_cast<const uint2*>(p.mask_hi + r * p.ld_mask + n));
-          const __half2 m01 = *reinterpret_cast<const __half2*>(&mh.x), m23 = *reinterpret_cast<const __half2*>(&mh.y);
-          const float2 f01 = __half22float2(m01), f23 = __half22float2(m23);
-          float4 dz;
-          dz.x = f01.x > 0.f ? dh.x * p.keep_scale : 0.f;
-          dz.y = f01.y > 0.f ? dh.y * p.keep_scale : 0.f;
-          dz.z = f23.x > 0.f ? dh.z * p.keep_scale : 0.f;
-          dz.w = f23.y > 0.f ? dh.w * p.keep_scale : 0.f;
-          *reinterpret_cast<float4*>(y_s + j * CHP + c) = dz;
-          add4(csum, dz);
-          if (EPI == EPI_BOND_BWD) {
-            if (p.dskip_partial) {
-              const float4 h0v = ld4(r_s + j * CH + c);
-              dsk = fmaf(dz.x, h0v.x, fmaf(dz.y, h0v.y, fmaf(dz.z, h0v.z, fmaf(dz.w, h0v.w, dsk))));
+        // PU rows per step: their global loads (mask, dh0_acc) are issued together, then consumed
+        constexpr int PU = 4;
+        for (int j0 = warp; j0 < ecount; j0 += NWARPS * PU) {
+          uint2 mh[PU];
+          float4 a0[PU];
+#pragma unroll
+          for (int u = 0; u < PU; ++u) {
+            const int j = j0 + u * NWARPS;
+            if (j < ecount) {
+              const int64_t r = (int64_t)tile * TM + j;
+              mh[u] = __ldg(reinterpret_cast<const uint2*>(p.mask_hi + r * p.ld_mask + n));
+              if (EPI == EPI_BOND_BWD && !p.dh0_first)
+                a0[u] = __ldcg(reinterpret_cast<const float4*>(p.dh0_acc + r * H + n));   // previous kernel's: bypass L1
+              else
+                a0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float4* acc0 = reinterpret_cast<float4*>(p.dh0_acc + r * H + n);
-            float4 a0 = p.dh0_first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(acc0);   // written by the previous kernel: bypass L1
-            a0.x = fmaf(skip, dz.x, a0.x); a0.y = fmaf(skip, dz.y, a0.y);
-            a0.z = fmaf(skip, dz.z, a0.z); a0.w = fmaf(skip, dz.w, a0.w);
-            *acc0 = a0;
-          } else {
-            *reinterpret_cast<float4*>(p.dz0_out + (int64_t)(ebase + j) * H + n) = dz;
+          }
+#pragma unroll
+          for (int u = 0; u < PU; ++u) {
+            const int j = j0 + u * NWARPS;
+            if (j >= ecount) break;
+            const int64_t r = (int64_t)tile * TM + j;
+            float4 dh = ld4(y_s + j * CHP + c);
+            if (EPI == EPI_INIT_BWD) add4(dh, ld4(r_s + j * CH + c));
+            const __half2 m01 = *reinterpret_cast<const __half2*>(&mh[u].x), m23 = *reinterpret_cast<const __half2*>(&mh[u].y);
+            const float2 f01 = __half22float2(m01), f23 = __half22float2(m23);
+            float4 dz;
+            dz.x = f01.x > 0.f ? dh.x * p.keep_scale : 0.f;
+            dz.y = f01.y > 0.f ? dh.y * p.keep_scale : 0.f;
+            dz.z = f23.x > 0.f ? dh.z * p.keep_scale : 0.f;
+            dz.w = f23.y > 0.f ? dh.w * p.keep_scale : 0.f;
+            *reinterpret_cast<float4*>(y_s + j * CHP + c) = dz;
+            add4(csum, dz);
+            if (EPI == EPI_BOND_BWD) {
+              if (p.dskip_partial) {
+                const float4 h0v = ld4(r_s + j * CH + c);
+                dsk = fmaf(dz.x, h0v.x, fmaf(dz.y, h0v.y, fmaf(dz.z, h0v.z, fmaf(dz.w, h0v.w, dsk))));
+              }
+              float4 acc = a0[u];
+              acc.x = fmaf(skip, dz.x, acc.x); acc.y = fmaf(skip, dz.y, acc.y);
+              acc.z = fmaf(skip, dz.z, acc.z); acc.w = fmaf(skip, dz.w, acc.w);
+              *reinterpret_cast<float4*>(p.dh0_acc + r * H + n) = acc;
+            } else {
+              *reinterpret_cast<float4*>(p.dz0_out + (int64_t)(ebase + j) * H + n) = dz;
+            }
           }
         }
       }
