@@ -48,9 +48,12 @@ def parse():
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over")
     ap.add_argument("--coalesce", type=int, default=8,
                     help="host batches predict_stream submits together in the e2e leg (1 = one submission per batch)")
-    ap.add_argument("--store", action="store_true",
-                    help="also time inference over a device-resident reaction store (no per-step feature copies)")
-    ap.add_argument("--train", action="store_true", help="also time the training step (fwd+loss+bwd[+allreduce])")
+    ap.add_argument("--store", action="store_true", default=True,
+                    help="also time inference over a device-resident reaction store (no per-step feature copies) [default]")
+    ap.add_argument("--no-store", dest="store", action="store_false")
+    ap.add_argument("--train", action="store_true", default=True,
+                    help="also time the training step (fwd+loss+bwd[+allreduce]) [default]")
+    ap.add_argument("--no-train", dest="train", action="store_false")
     return ap.parse_args()
 
 
