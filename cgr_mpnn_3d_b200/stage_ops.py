@@ -104,3 +104,22 @@ def mse_sum(pred, y):
     _lib.check(lib.cgr_mse_sum_fwd_bwd(pred.data_ptr(), y.data_ptr(), pred.numel(), loss.data_ptr(),
                                        grad.data_ptr(), _stream()), "cgr_mse_sum_fwd_bwd")
     return loss, grad
+
+
+class _MSESumLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, y):
+        loss, grad = mse_sum(pred.detach(), y.detach())
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def mse_sum_loss(pred, y):
+    """Drop-in for ``torch.nn.MSELoss(reduction="sum")(pred, y)`` (train.py:120, trainer.py:142) as ONE launch that
+    produces the loss and dL/dpred together (``cgr_mse_sum_fwd_bwd``); the target gets no gradient."""
+    return _MSESumLoss.apply(pred, y)

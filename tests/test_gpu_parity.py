@@ -818,3 +818,18 @@ def test_fused_backward_gradient_scaling_is_scale_invariant():
     model.zero_grad(set_to_none=True)
     model(data).backward(gradient=torch.zeros(24, device="cuda"))
     assert all(float(p.grad.abs().max()) == 0.0 for p in model.parameters())
+
+
+def test_fused_mse_sum_loss_matches_torch():
+    from cgr_mpnn_3d_b200.stage_ops import mse_sum_loss as fused_mse
+    torch.manual_seed(0)
+    pred = torch.randn(777, device="cuda", requires_grad=True)
+    y = torch.randn(777, device="cuda")
+    ref = torch.nn.MSELoss(reduction="sum")(pred, y)           # train.py:120
+    (3.0 * ref).backward()
+    g_ref = pred.grad.clone()
+    pred.grad = None
+    loss = fused_mse(pred, y)
+    (3.0 * loss).backward()
+    assert loss.shape == () and abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert tensor_error(pred.grad, g_ref) < 1e-6
