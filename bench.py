@@ -569,22 +569,26 @@ def main():
 
     clocks.stop()
     if roofline:
-        # The dominant kernel's average duration inside a timed, host-gap-free run = its CUDA-event share of the step x the
-        # step time of the single-stream graph replay (latency configuration).  The event-bracketed figure of one isolated
-        # launch (launch latency and event overhead included) and the share of the pipelined timed region are kept beside it.
+        # Average launch duration of the dominant kernel OVER THE TIMED REGION of `value` = its CUDA-event share of a step
+        # (recorded by the library on the launching stream, the stream kept busy so event pairs bracket kernel time) x the
+        # timed region's time per step / launches per step -- the machine time the pipelined region spends per launch.
+        # Beside it: the same share of the un-pipelined single-stream step (latency of one launch in a dependent chain) and
+        # one isolated launch between two events (launch latency and event overhead included).
         share = roofline["stage_share"].get(roofline["kernel"], 0.0)
         lps = max(1e-9, roofline["launches_per_step"])
-        dur_us = single_stream_ms * 1e3 * share / lps
+        per_launch = roofline["algorithmic_bytes_per_launch"]
         roofline["event_bracketed_us"] = roofline.pop("avg_launch_us")
+        dur_us = (ms_total / args.steps) * 1e3 * share / lps
         roofline["avg_launch_us"] = dur_us
-        roofline["achieved"] = roofline["algorithmic_bytes_per_launch"] / (dur_us * 1e-6) / 1e9
+        roofline["achieved"] = per_launch / (dur_us * 1e-6) / 1e9
         roofline["frac"] = roofline["achieved"] / hbm_peak
-        sus_us = (ms_total / args.steps) * 1e3 * share / lps
-        roofline["sustained_us_per_launch"] = sus_us
-        roofline["sustained_frac"] = roofline["algorithmic_bytes_per_launch"] / (sus_us * 1e-6) / 1e9 / hbm_peak
-        roofline["note"] = ("avg_launch_us = (single-stream CUDA-graph step time) x (kernel's CUDA-event share of a step) / "
-                            "launches per step; event_bracketed_us = one isolated launch between two events (launch "
-                            "latency included); sustained_* = same share of the pipelined timed region (value)")
+        lat_us = single_stream_ms * 1e3 * share / lps
+        roofline["single_stream_us_per_launch"] = lat_us
+        roofline["single_stream_frac"] = per_launch / (lat_us * 1e-6) / 1e9 / hbm_peak
+        roofline["note"] = ("avg_launch_us / achieved / frac: kernel's CUDA-event share of a step x time per step of the timed "
+                            "region (value: independent steps pipelined over streams) / launches per step; single_stream_*: "
+                            "same share of the un-pipelined CUDA-graph step (latency of a launch in a dependent chain); "
+                            "event_bracketed_us: one isolated launch between two events (launch latency included)")
     if rank == 0:
         alg = algorithmic_bytes_fwd(n_atoms, n_bonds, args.batch)
         line = {
