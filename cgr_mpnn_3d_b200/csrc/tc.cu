@@ -638,6 +638,8 @@ size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int tra
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CGR_CHECK_ARG(g->tile_info && g->n_tiles > 0, "tcgen05 engine needs a tile plan (reactions of <= 128 bonds)");
+  CGR_CHECK_ARG(g->n_tiles <= 65535, "tcgen05 engine: %lld row tiles exceed one launch (65535): split the batch "
+                "(about 200k T1x-sized reactions per call)", (long long)g->n_tiles);
   char* blob = nullptr;               // training: per-layer activations are kept in the caller's blob
   TcSavedLayout SL;
   memset(&SL, 0, sizeof(SL));
@@ -1045,6 +1047,7 @@ size_t tc_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g) {
 int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved, const float* dout,
                     const cgr_grads_t* grads, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CGR_CHECK_ARG(tc_fused_training_ok(p, g) && saved && saved->tc_blob, "tcgen05 fused backward: unsupported configuration");
+  CGR_CHECK_ARG(g->n_tiles <= 65535, "tcgen05 engine: too many row tiles for one launch: split the batch");
   const TcSavedLayout SL = tc_saved_layout(p, g);
   const TcBwdWs w = tc_bwd_ws(p, g);
   CGR_CHECK_ARG(saved->tc_blob_bytes >= SL.total, "tcgen05 fused backward: tc_blob too small");
