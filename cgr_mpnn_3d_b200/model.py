@@ -111,6 +111,18 @@ class GNN(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _param_list(self) -> List[torch.Tensor]:
+        # module attribute lookups cost ~1 us each: keep the list, re-derive it if a parameter object was replaced
+        cached = self.__dict__.get("_plist")
+        if cached is not None:
+            i_fb = 2 + 2 * self.depth + 3                              # ffn.bias
+            if cached[0] is self._modules["edge_init"]._parameters["weight"] and \
+                    cached[i_fb] is self._modules["ffn"]._parameters["bias"]:
+                return list(cached)
+        ps = self._param_list_uncached()
+        self.__dict__["_plist"] = tuple(ps)
+        return ps
+
+    def _param_list_uncached(self) -> List[torch.Tensor]:
         ps = [self.edge_init.weight, self.edge_init.bias]
         for c in self.convs:
             ps += [c.lin.weight, c.lin.bias]
@@ -443,6 +455,7 @@ class GNN(nn.Module):
         state.pop("_host_slots", None)
         state.pop("_host_ctx_cache", None)
         state.pop("_last_plan", None)
+        state.pop("_plist", None)
         state.pop("_last_fused_train", None)
         return state
 

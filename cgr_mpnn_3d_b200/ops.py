@@ -235,10 +235,7 @@ def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tenso
     # training all-reduces them with a single collective and no packing copies (parallel.allreduce_gradients_)
     sizes = [(p.numel() + 3) // 4 * 4 for p in params]
     flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
-    grads, off = [], 0
-    for p, n in zip(params, sizes):
-        grads.append(flat[off:off + p.numel()].view(p.shape))
-        off += n
+    grads = [(c if c.numel() == p.numel() else c[:p.numel()]).view(p.shape) for c, p in zip(flat.split(sizes), params)]
     gw_init, gb_init, gw_conv, gb_conv, gw_e2n, gb_e2n, gw_ffn, gb_ffn, gskip = _unpack(grads, depth, use_skip)
     wc, bc = _lib.ptr_array(gw_conv), _lib.ptr_array(gb_conv)
     sk = _lib.ptr_array(gskip) if use_skip else None
