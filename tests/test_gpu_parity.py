@@ -833,3 +833,23 @@ def test_fused_mse_sum_loss_matches_torch():
     (3.0 * loss).backward()
     assert loss.shape == () and abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
     assert tensor_error(pred.grad, g_ref) < 1e-6
+
+
+@pytest.mark.parametrize("depth,hidden", [(1, 64), (6, 100), (2, 1024)])
+def test_fused_training_depth_and_width_extremes(depth, hidden):
+    """One-layer, deep and wide networks through the fused tile-local training kernels."""
+    meta = dict(fa=78, fb=14, depth=depth, hidden=hidden, skip=True, wseed=9, act="relu")
+    data = make_batch(12, seed=33, kind="t1x", fa=78)
+    oracle = build_oracle(meta).train()
+    ref = oracle(data)
+    mse_sum_loss(ref, data.y).backward()
+    og = dict(oracle.named_parameters())
+    model = build_model(meta, engine="tc").train()
+    d = data.to("cuda")
+    out = model(d)
+    assert model.__dict__["_last_fused_train"]
+    assert scale_normalised_error(out, ref.detach()) < EA_TOL
+    mse_sum_loss(out, d.y).backward()
+    for k, q in model.named_parameters():
+        assert tensor_error(q.grad, og[k].grad) < (GRAD_TOL if hidden < 1024 else 3e-4), k
+    model.check_numerics()
