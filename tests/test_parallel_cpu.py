@@ -52,7 +52,25 @@ def _worker(rank, world, port, q):
     broadcast_parameters_(model.parameters(), src=0)
     mine = collate_host(shard_reactions(rx, rank, world))
     mse_sum_loss(model(mine), mine.y).backward()
+    local = [p.grad.clone() for p in model.parameters()]
     allreduce_gradients_(model.parameters())           # SUM, not mean: loss is MSE(reduction="sum")
+    # the same reduction when the gradients are views of ONE flat buffer (what the CGR backward returns): in place, one
+    # collective, and the same numbers
+    from cgr_mpnn_3d_b200.parallel import _shared_flat_view
+    packed = [p.grad.clone() for p in model.parameters()]
+    ps = list(model.parameters())
+    sizes = [(p.numel() + 3) // 4 * 4 for p in ps]
+    flat = torch.full((sum(sizes),), float("nan"))          # padding between pieces is never read back
+    flat.zero_()
+    off = 0
+    for p, g, n in zip(ps, local, sizes):
+        flat[off:off + p.numel()] = g.reshape(-1)
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += n
+    assert _shared_flat_view(ps) is not None
+    out = allreduce_gradients_(ps)
+    assert out.data_ptr() == flat.data_ptr()
+    assert all(torch.equal(p.grad, g) for p, g in zip(ps, packed))
     if rank == 0:
         ref = OracleGNN(78, 14, depth=2, hidden_sizes=[32] * 2, dropout_ps=[0.0] * 2, activation_fn=F.relu,
                         use_learnable_skip=True)
