@@ -60,13 +60,16 @@ class FusedAdam(torch.optim.Optimizer):
             st["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
-    def _launch(self, lib, group, arr, n, step, amsgrad, dev):
+    def _launch(self, lib, group, arr, n, step, amsgrad, dev, params):
         beta1, beta2 = group["betas"]
         with torch.cuda.device(dev):
             rc = lib.cgr_adam_step(arr, n, float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
                                    float(group["weight_decay"]), step, int(amsgrad), self.grad_scale,
                                    torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "cgr_adam_step")
+        # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on tensor versions,
+        # e.g. the prepared tcgen05 weights of GNN) that they changed
+        torch.autograd.graph.increment_version(params)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -86,7 +89,7 @@ class FusedAdam(torch.optim.Optimizer):
             fast = self._fast.get(gi)
             if fast is not None and fast[0] == sig:          # steady state: same tensors as the previous step
                 fast[3] += 1
-                self._launch(lib, group, fast[1], len(fast[2]), fast[3], amsgrad, fast[4])
+                self._launch(lib, group, fast[1], len(fast[2]), fast[3], amsgrad, fast[4], fast[5])
                 continue
             if fast is not None:
                 for _, st in fast[2]:
@@ -114,9 +117,9 @@ class FusedAdam(torch.optim.Optimizer):
                     a.max_exp_avg_sq = st["max_exp_avg_sq"].data_ptr() if amsgrad else None
                     a.numel = p.numel()
                 dev = items[0][0].device
-                self._launch(lib, group, arr, len(items), step, amsgrad, dev)
+                self._launch(lib, group, arr, len(items), step, amsgrad, dev, [p for p, _ in items])
                 for _, st in items:
                     st["step"] += 1
                 if len(by_step) == 1 and all(g is p.grad for (p, _), g in zip(items, grads)):
-                    self._fast[gi] = [sig, arr, items, step, dev]
+                    self._fast[gi] = [sig, arr, items, step, dev, [p for p, _ in items]]
         return loss

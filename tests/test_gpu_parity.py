@@ -853,3 +853,30 @@ def test_fused_training_depth_and_width_extremes(depth, hidden):
     for k, q in model.named_parameters():
         assert tensor_error(q.grad, og[k].grad) < (GRAD_TOL if hidden < 1024 else 3e-4), k
     model.check_numerics()
+
+
+def test_fused_adam_invalidates_cached_inference_weights():
+    """FusedAdam writes parameters through raw pointers; caches keyed on tensor versions (the prepared tcgen05 weights
+    used by inference) must notice: predictions after a step use the new weights."""
+    from cgr_mpnn_3d_b200.optim import FusedAdam
+    meta = dict(fa=78, fb=14, depth=2, hidden=64, skip=True, wseed=3, act="relu")
+    model = build_model(meta, engine="auto")
+    data = make_batch(8, seed=2, kind="t1x", fa=78)
+    d = data.to("cuda")
+    opt = FusedAdam(model.parameters(), lr=1e-2, amsgrad=True)
+    model.eval()
+    with torch.no_grad():
+        before_dev, before_host = model(d).clone(), model(data).clone()
+    v0 = [p._version for p in model.parameters()]
+    model.train()
+    mse_sum_loss(model(d), d.y).backward()
+    opt.step()
+    assert all(p._version > v for p, v in zip(model.parameters(), v0))
+    model.eval()
+    with torch.no_grad():
+        after_dev, after_host = model(d), model(data)
+        ref = build_oracle(meta).eval()
+        ref.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+        expect = ref(data)
+    assert not torch.allclose(after_dev, before_dev) and not torch.allclose(after_host, before_host)
+    assert scale_normalised_error(after_dev, expect) < EA_TOL and scale_normalised_error(after_host, expect) < EA_TOL
