@@ -1,6 +1,7 @@
 // Fused optimizer step: Adam with L2-in-gradient weight decay and amsgrad, as the reference
 // configures it (train.py:117-121 -- torch.optim.Adam(lr, weight_decay, amsgrad=True)), over every parameter tensor
 // in ONE launch.  HBM-bound: per element it reads param, grad, m, v, vmax and writes param, m, v, vmax (36 bytes).
+#include <cuda.h>
 #include <math.h>
 #include <string.h>
 
@@ -92,7 +93,196 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data-parallel step without NCCL: gradient SUM over the replicas and the Adam update in ONE kernel.  Every rank keeps its
+// flat gradient arena in memory its peers can map (CUDA IPC); the kernel announces "my gradients of step s are complete"
+// in every peer's flag pad, waits until all peers have announced the same, then reads each gradient element from all
+// arenas over NVLink (fixed rank order: every replica computes bit-identical sums and stays in lock-step) and applies
+// Adam to its own parameters.  Arenas alternate between two buffers, so a rank may start writing step s+1 while slower
+// peers still read step s.
+// ------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX = 16;
+struct PeerTable {
+  const float* arena[PEER_MAX];     // every rank's gradient arena of this step (own one included), rank order
+  int* flags[PEER_MAX];             // every rank's flag pad [PEER_MAX] (own one included)
+  int world, rank, step;
+};
+
+__device__ __forceinline__ float ld_peer(const float* p) {       // peer lines must not be served from a stale L1 line
+  float v;
+  asm volatile("ld.global.cv.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cv.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) peer_adam_kernel(const __grid_constant__ AdamTable tab,
+                                                                 const __grid_constant__ AdamScalars s,
+                                                                 const __grid_constant__ PeerTable pt) {
+  // 1. announce (the gradients were written by earlier kernels of this stream: complete and visible device-wide; the
+  //    system-scope fence orders them before the flag for the peers), 2. wait for every peer
+  if (blockIdx.x == 0 && threadIdx.x < pt.world) {
+    __threadfence_system();
+    volatile int* f = pt.flags[threadIdx.x] + pt.rank;
+    *f = pt.step;
+  }
+  if (threadIdx.x < pt.world) {
+    volatile int* mine = pt.flags[pt.rank] + threadIdx.x;
+    unsigned int spins = 0;
+    while (*mine < pt.step) {
+      if (++spins > (1u << 28)) __trap();            // a peer died: fail the launch instead of hanging the GPU
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+
+  int lo = 0, hi = tab.n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tab.first_block[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const int t = lo;
+  const long long base = (long long)((int)blockIdx.x - tab.first_block[t]) * ADAM_CHUNK;
+  const long long n = tab.numel[t];
+  float* __restrict__ P = tab.param[t];
+  const long long goff = (long long)(size_t)tab.grad[t];      // gradient position inside the arenas, in floats
+  float* __restrict__ M = tab.m[t];
+  float* __restrict__ V = tab.v[t];
+  float* __restrict__ VM = tab.vmax[t];
+  const bool vec = ((((uintptr_t)P | (uintptr_t)M | (uintptr_t)V | (uintptr_t)(s.amsgrad ? VM : P)) & 15) == 0) && (goff & 3) == 0;
+  if (vec && base + ADAM_CHUNK <= n) {
+#pragma unroll
+    for (int it = 0; it < ADAM_CHUNK / (ADAM_THREADS * 4); ++it) {
+      const long long i = base + (long long)(it * ADAM_THREADS + threadIdx.x) * 4;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < pt.world; ++r) {
+        const float4 x = ld_peer4(pt.arena[r] + goff + i);
+        g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+      }
+      float4 p = *reinterpret_cast<float4*>(P + i);
+      float4 m = *reinterpret_cast<float4*>(M + i);
+      float4 v = *reinterpret_cast<float4*>(V + i);
+      float4 vm = s.amsgrad ? *reinterpret_cast<float4*>(VM + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      adam_one(p.x, g.x, m.x, v.x, vm.x, s);
+      adam_one(p.y, g.y, m.y, v.y, vm.y, s);
+      adam_one(p.z, g.z, m.z, v.z, vm.z, s);
+      adam_one(p.w, g.w, m.w, v.w, vm.w, s);
+      *reinterpret_cast<float4*>(P + i) = p;
+      *reinterpret_cast<float4*>(M + i) = m;
+      *reinterpret_cast<float4*>(V + i) = v;
+      if (s.amsgrad) *reinterpret_cast<float4*>(VM + i) = vm;
+    }
+  } else {
+    const long long end = base + ADAM_CHUNK < n ? base + ADAM_CHUNK : n;
+    for (long long i = base + threadIdx.x; i < end; i += ADAM_THREADS) {
+      float g = 0.f;
+      for (int r = 0; r < pt.world; ++r) g += ld_peer(pt.arena[r] + goff + i);
+      float p = P[i], m = M[i], v = V[i], vm = s.amsgrad ? VM[i] : 0.f;
+      adam_one(p, g, m, v, vm, s);
+      P[i] = p; M[i] = m; V[i] = v;
+      if (s.amsgrad) VM[i] = vm;
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int cgr_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  CGR_CUDA(cudaGetDevice(&dev));
+  if (dev == peer_device) return CGR_OK;
+  int can = 0;
+  CGR_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  CGR_CHECK_ARG(can, "device %d cannot map the memory of device %d (no P2P path)", dev, peer_device);
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return CGR_OK; }
+  CGR_CUDA(e);
+  return CGR_OK;
+}
+
+// CUDA IPC for the gradient arenas.  Export: the handle of the allocation that contains `dev_ptr` plus the pointer's
+// offset inside it (torch tensors live inside larger cudaMalloc'ed segments).  Open: map a peer's allocation for the
+// CURRENT device (peer access is enabled lazily by the driver) and return the address of the same bytes.
+extern "C" int cgr_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out) {
+  CGR_CHECK_ARG(dev_ptr && handle_out && offset_out, "cgr_ipc_export: null pointer");
+  typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CGR_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q));
+  CGR_CHECK_ARG(f && q == cudaDriverEntryPointSuccess, "cuMemGetAddressRange is not available from the driver");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  const CUresult r = ((GetRangeFn)f)(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr);
+  CGR_CHECK_ARG(r == CUDA_SUCCESS, "cuMemGetAddressRange failed with CUresult %d", (int)r);
+  cudaIpcMemHandle_t h;
+  CGR_CUDA(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  *offset_out = (int64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+  return CGR_OK;
+}
+
+extern "C" int cgr_ipc_open(const void* handle, int64_t offset, void** ptr_out) {
+  CGR_CHECK_ARG(handle && ptr_out && offset >= 0, "cgr_ipc_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* base = nullptr;
+  CGR_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = (char*)base + offset;
+  return CGR_OK;
+}
+
+extern "C" int cgr_peer_allreduce_adam(const cgr_adam_tensor_t* tensors, int32_t n_tensors, const float* const* peer_arenas,
+                                       int* const* peer_flags, int32_t world, int32_t rank, int32_t sync_step, double lr,
+                                       double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                                       int32_t amsgrad, float grad_scale, void* stream) {
+  CGR_CHECK_ARG(tensors && n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS, "cgr_peer_allreduce_adam: 1..%d tensors", ADAM_MAX_TENSORS);
+  CGR_CHECK_ARG(peer_arenas && peer_flags && world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world,
+                "cgr_peer_allreduce_adam: bad peer table");
+  CGR_CHECK_ARG(step >= 1 && sync_step >= 1, "cgr_peer_allreduce_adam: steps count from 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars s;
+  s.beta1 = (float)beta1; s.beta2 = (float)beta2;
+  s.one_minus_beta1 = (float)(1.0 - beta1); s.one_minus_beta2 = (float)(1.0 - beta2);
+  s.eps = (float)eps; s.weight_decay = (float)weight_decay;
+  s.neg_step_size = (float)(-(lr / bc1));
+  s.bc2_sqrt = (float)sqrt(bc2);
+  s.grad_scale = grad_scale;
+  s.amsgrad = amsgrad ? 1 : 0;
+  AdamTable tab;
+  memset(&tab, 0, sizeof(tab));
+  int blocks = 0, k = 0;
+  for (int j = 0; j < n_tensors; ++j) {
+    const cgr_adam_tensor_t& a = tensors[j];
+    if (a.numel <= 0) continue;
+    CGR_CHECK_ARG(a.param && a.exp_avg && a.exp_avg_sq && (!amsgrad || a.max_exp_avg_sq),
+                  "cgr_peer_allreduce_adam: null pointer in tensor %d", j);
+    tab.param[k] = a.param; tab.grad[k] = a.grad;        // grad = offset (in floats) of this tensor inside the arenas
+    tab.m[k] = a.exp_avg; tab.v[k] = a.exp_avg_sq; tab.vmax[k] = a.max_exp_avg_sq; tab.numel[k] = a.numel;
+    tab.first_block[k] = blocks;
+    blocks += (int)cgr_ceil_div(a.numel, (int64_t)ADAM_CHUNK);
+    ++k;
+  }
+  CGR_CHECK_ARG(k > 0, "cgr_peer_allreduce_adam: nothing to update");
+  tab.first_block[k] = blocks;
+  tab.n = k;
+  PeerTable pt;
+  memset(&pt, 0, sizeof(pt));
+  for (int r = 0; r < world; ++r) {
+    CGR_CHECK_ARG(peer_arenas[r] && peer_flags[r], "cgr_peer_allreduce_adam: null peer pointer");
+    pt.arena[r] = peer_arenas[r]; pt.flags[r] = peer_flags[r];
+  }
+  pt.world = world; pt.rank = rank; pt.step = sync_step;
+  cgr_note_launch("peer_allreduce_adam", st, 1);
+  peer_adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(tab, s, pt);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
 
 extern "C" int cgr_adam_step(const cgr_adam_tensor_t* tensors, int32_t n_tensors, double lr, double beta1, double beta2,
                              double eps, double weight_decay, int64_t step, int32_t amsgrad, float grad_scale,

@@ -59,6 +59,15 @@ class _Ctx:
 
 _CTX_CACHE: dict = {}
 
+# Optional provider of the flat gradient buffer the backward writes into: callable (n_floats, device) -> 1-D fp32 tensor
+# or None (optim.PeerFusedAdam installs one that hands out its CUDA-IPC-shared arenas).
+_GRAD_ARENA = None
+
+
+def set_grad_arena(provider) -> None:
+    global _GRAD_ARENA
+    _GRAD_ARENA = provider
+
 
 def _ctx_cached(role: str, params: Sequence[Tensor], depth: int, act: int, use_skip: bool, fa: int, fb: int,
                 dropout_ps: Sequence[float]) -> "_Ctx":
@@ -234,7 +243,11 @@ def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tenso
     # all gradients are views of ONE flat fp32 buffer (16-byte aligned pieces, parameter order), so data-parallel
     # training all-reduces them with a single collective and no packing copies (parallel.allreduce_gradients_)
     sizes = [(p.numel() + 3) // 4 * 4 for p in params]
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
+    flat = None
+    if _GRAD_ARENA is not None:              # a data-parallel optimizer wants the gradients in memory its peers can map
+        flat = _GRAD_ARENA(sum(sizes), x.device)
+    if flat is None:
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
     grads = [(c if c.numel() == p.numel() else c[:p.numel()]).view(p.shape) for c, p in zip(flat.split(sizes), params)]
     gw_init, gb_init, gw_conv, gb_conv, gw_e2n, gb_e2n, gw_ffn, gb_ffn, gskip = _unpack(grads, depth, use_skip)
     wc, bc = _lib.ptr_array(gw_conv), _lib.ptr_array(gb_conv)

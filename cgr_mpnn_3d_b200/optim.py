@@ -123,3 +123,130 @@ class FusedAdam(torch.optim.Optimizer):
                 if len(by_step) == 1 and all(g is p.grad for (p, _), g in zip(items, grads)):
                     self._fast[gi] = [sig, arr, items, step, dev, [p for p, _ in items]]
         return loss
+
+
+class PeerFusedAdam(torch.optim.Optimizer):
+    """Data-parallel Adam without a collective library: ``step()`` is ONE kernel (``cgr_peer_allreduce_adam``) that waits
+    for all replicas, SUMS their gradients by reading every replica's gradient arena over NVLink (CUDA-IPC-mapped peer
+    memory, fixed rank order: replicas stay bit-identical) and applies the Adam / amsgrad update of train.py:117-119.
+
+    One process per GPU on one node (``torch.distributed`` initialised, any backend: it is only used once, to exchange the
+    IPC handles).  The CGR backward writes its flat gradient buffer straight into the arena (``ops.set_grad_arena``), so
+    there is no packing copy either.  Gradients are SUMMED over replicas (the reference's loss is
+    ``MSELoss(reduction="sum")``); pass ``grad_scale=1/world`` for a mean.  All parameters must get a gradient every step
+    (true for the CGR model); all replicas must call ``step()`` the same number of times.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, grad_scale=1.0,
+                 group=None):
+        import torch.distributed as dist
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("PeerFusedAdam supports one parameter group")
+        ps = self.param_groups[0]["params"]
+        if not ps or any((not p.is_cuda) or p.dtype != torch.float32 or not p.is_contiguous() for p in ps):
+            raise RuntimeError("PeerFusedAdam: contiguous fp32 CUDA parameters only (no CPU path)")
+        if len(ps) > 48:
+            raise ValueError("PeerFusedAdam supports at most 48 parameter tensors")
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerFusedAdam needs torch.distributed (one process per GPU of one node)")
+        self.grad_scale = float(grad_scale)
+        self._group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("PeerFusedAdam supports up to 16 replicas")
+        self.device = ps[0].device
+        self._sizes = [(p.numel() + 3) // 4 * 4 for p in ps]
+        self._total = sum(self._sizes)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            # [arena 0 | arena 1 | flag pad]: one allocation of its own (cudaMalloc'ed block, exportable through CUDA IPC)
+            self._shared = torch.zeros(2 * self._total + 64, dtype=torch.float32, device=self.device)
+            torch.cuda.synchronize(self.device)
+            handle = C.create_string_buffer(64)
+            offset = C.c_int64(0)
+            _lib.check(lib.cgr_ipc_export(self._shared.data_ptr(), handle, C.byref(offset)), "cgr_ipc_export")
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (self.device.index, handle.raw, int(offset.value)), group=group)
+            self._peer_ptrs = []                  # address of every rank's shared block as seen from this device
+            for r, (peer_dev, h, off) in enumerate(gathered):
+                if r == self.rank:
+                    self._peer_ptrs.append(self._shared.data_ptr())
+                else:
+                    _lib.check(lib.cgr_enable_peer_access(int(peer_dev)), "cgr_enable_peer_access")
+                    ptr = C.c_void_p()
+                    _lib.check(lib.cgr_ipc_open(C.create_string_buffer(h, 64), off, C.byref(ptr)), "cgr_ipc_open")
+                    self._peer_ptrs.append(int(ptr.value))
+            dist.barrier(group=group)
+        self._arena_ptrs = []
+        for buf in (0, 1):
+            arr = (C.c_void_p * self.world)(*[q + buf * self._total * 4 for q in self._peer_ptrs])
+            self._arena_ptrs.append(arr)
+        self._flag_ptrs = (C.c_void_p * self.world)(*[q + 2 * self._total * 4 for q in self._peer_ptrs])
+        self._cur = 0                             # arena the next backward writes into
+        self._sync_step = 0
+        self._adam_step = 0
+        for p in ps:
+            st = self.state[p]
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["exp_avg"] = torch.zeros_like(p)
+            st["exp_avg_sq"] = torch.zeros_like(p)
+            if amsgrad:
+                st["max_exp_avg_sq"] = torch.zeros_like(p)
+        self._table = None
+        from . import ops
+        ops.set_grad_arena(self._provide)
+
+    def _provide(self, n_floats, device):
+        if n_floats != self._total or device != self.device:
+            return None
+        return self._shared[self._cur * self._total:(self._cur + 1) * self._total]
+
+    def state_dict(self):
+        for p in self.param_groups[0]["params"]:
+            self.state[p]["step"].fill_(float(self._adam_step))
+        return super().state_dict()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        group = self.param_groups[0]
+        ps = group["params"]
+        amsgrad = bool(group["amsgrad"])
+        base = self._shared.data_ptr() + self._cur * self._total * 4
+        off = 0
+        for p, n in zip(ps, self._sizes):          # every gradient must sit at its slot of the current arena
+            g = p.grad
+            if g is None or g.data_ptr() != base + off * 4:
+                raise RuntimeError("PeerFusedAdam: a gradient is missing or was not written into the shared arena "
+                                   "(use zero_grad(set_to_none=True) and one backward per step)")
+            off += n
+        if self._table is None:
+            arr = (_lib.CgrAdamTensor * len(ps))()
+            off = 0
+            for a, p, n in zip(arr, ps, self._sizes):
+                st = self.state[p]
+                a.param, a.grad = p.data_ptr(), off                 # grad = offset inside the arenas, in floats
+                a.exp_avg, a.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                a.max_exp_avg_sq = st["max_exp_avg_sq"].data_ptr() if amsgrad else None
+                a.numel = p.numel()
+                off += n
+            self._table = arr
+        self._sync_step += 1
+        self._adam_step += 1
+        beta1, beta2 = group["betas"]
+        with torch.cuda.device(self.device):
+            rc = lib.cgr_peer_allreduce_adam(self._table, len(ps), self._arena_ptrs[self._cur], self._flag_ptrs, self.world,
+                                             self.rank, self._sync_step, float(group["lr"]), float(beta1), float(beta2),
+                                             float(group["eps"]), float(group["weight_decay"]), self._adam_step,
+                                             int(amsgrad), self.grad_scale,
+                                             torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "cgr_peer_allreduce_adam")
+        torch.autograd.graph.increment_version(ps)
+        self._cur ^= 1                               # the next backward writes the other arena
+        return loss
