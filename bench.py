@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--train", action="store_true", default=True,
                     help="also time the training step (fwd+loss+bwd[+allreduce]) [default]")
     ap.add_argument("--no-train", dest="train", action="store_false")
+    ap.add_argument("--peer-adam", action="store_true",
+                    help="N > 1: also time the complete data-parallel step with NCCL all-reduce + FusedAdam and with "
+                         "PeerFusedAdam (gradient sum over NVLink peer memory + Adam in one kernel)")
     return ap.parse_args()
 
 
@@ -552,6 +555,60 @@ def main():
         train["adam_fused_launches"] = (lib.cgr_launch_count() - l_before) / 205
         train["adam_torch_ms"] = time_opt(torch.optim.Adam(tm.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True))
 
+        # opt-in: the COMPLETE data-parallel step (forward + loss + backward + gradient SUM + Adam) two ways -- NCCL all-reduce
+        # then the one-launch Adam, vs PeerFusedAdam (sum over NVLink peer memory + Adam in one kernel, no NCCL)
+        if args.peer_adam and world > 1:
+            from cgr_mpnn_3d_b200 import ops as _ops
+            from cgr_mpnn_3d_b200.optim import PeerFusedAdam
+
+            def timed_steps(step_fn, n):
+                for i in range(6):
+                    step_fn(i)
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for i in range(n):
+                    step_fn(i)
+                a1.record()
+                barrier()
+                return a0.elapsed_time(a1) / n
+            fa_opt = FusedAdam(tm.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+
+            def nccl_step(i):
+                tgraphs[i % len(tb)].replay()
+                allreduce_gradients_(tm.parameters())
+                fa_opt.step()
+            train["dp_step_nccl_ms"] = timed_steps(nccl_step, n_t)
+            tm2 = build_model("auto", dev).train()
+            popt = PeerFusedAdam(tm2.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+
+            def train_step2(d):
+                torch.nn.functional.mse_loss(tm2(d), d.y, reduction="sum").backward()
+            with torch.cuda.stream(side_t):
+                for j, d in enumerate(tb[:2]):
+                    tm2.zero_grad(set_to_none=True)
+                    train_step2(d)
+            torch.cuda.current_stream().wait_stream(side_t)
+            torch.cuda.synchronize()
+            pgraphs = []
+            for j, d in enumerate(tb):           # graph j writes its gradients into arena j % 2: replayed in order
+                tm2.zero_grad(set_to_none=True)
+                popt._cur = j % 2
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side_t):
+                    train_step2(d)
+                pgraphs.append(gph)
+            popt._cur = 0
+            state = {"i": 0}
+
+            def peer_step(_):
+                j = state["i"] % len(tb)
+                pgraphs[j].replay()
+                popt.step(arena=j % 2)
+                state["i"] += 1
+            train["dp_step_peer_ms"] = timed_steps(peer_step, n_t)
+            _ops.set_grad_arena(None)
+
     # ---- reduce over ranks (max time), assemble the line ----
     t = torch.tensor([ms_total, e2e["seconds"] if e2e else 0.0, train["ms_total"] if train else 0.0,
                       e2e["single_call_seconds"] if e2e else 0.0, e2e["uncoalesced_seconds"] if e2e else 0.0],
@@ -615,6 +672,12 @@ def main():
             line["train_step"] = {"value": args.batch * train["steps"] * world / (train_ms * 1e-3), "unit": "reactions/s",
                                   "ms_per_step": train_ms / train["steps"], "steps": train["steps"],
                                   "eager_ms_per_step": train["eager_ms"],
+                                  "dp_step_with_optimizer": ({"nccl_allreduce_plus_fused_adam_ms": train["dp_step_nccl_ms"],
+                                                              "peer_fused_adam_ms": train["dp_step_peer_ms"],
+                                                              "what": "graph-replayed fwd+loss+bwd, then gradient SUM over "
+                                                                      "replicas and Adam(amsgrad): NCCL all-reduce + one-launch "
+                                                                      "Adam vs ONE kernel over NVLink peer memory (no NCCL)"}
+                                                             if "dp_step_peer_ms" in train else None),
                                   "optimizer": {"fused_adam_ms": train["adam_fused_ms"],
                                                 "fused_adam_launches_per_step": train["adam_fused_launches"],
                                                 "torch_adam_ms": train["adam_torch_ms"],

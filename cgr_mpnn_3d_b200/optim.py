@@ -209,7 +209,9 @@ class PeerFusedAdam(torch.optim.Optimizer):
         return super().state_dict()
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, arena=None):
+        """``arena`` (0 / 1): only for CUDA-graph replay, where ``p.grad`` objects are not refreshed -- names the arena the
+        replayed backward wrote (the one that was current when that graph was captured); must agree on all replicas."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -218,14 +220,17 @@ class PeerFusedAdam(torch.optim.Optimizer):
         group = self.param_groups[0]
         ps = group["params"]
         amsgrad = bool(group["amsgrad"])
-        base = self._shared.data_ptr() + self._cur * self._total * 4
-        off = 0
-        for p, n in zip(ps, self._sizes):          # every gradient must sit at its slot of the current arena
-            g = p.grad
-            if g is None or g.data_ptr() != base + off * 4:
-                raise RuntimeError("PeerFusedAdam: a gradient is missing or was not written into the shared arena "
-                                   "(use zero_grad(set_to_none=True) and one backward per step)")
-            off += n
+        if arena is not None:
+            self._cur = int(arena) & 1
+        else:
+            base = self._shared.data_ptr() + self._cur * self._total * 4
+            off = 0
+            for p, n in zip(ps, self._sizes):      # every gradient must sit at its slot of the current arena
+                g = p.grad
+                if g is None or g.data_ptr() != base + off * 4:
+                    raise RuntimeError("PeerFusedAdam: a gradient is missing or was not written into the shared arena "
+                                       "(use zero_grad(set_to_none=True) and one backward per step)")
+                off += n
         if self._table is None:
             arr = (_lib.CgrAdamTensor * len(ps))()
             off = 0
