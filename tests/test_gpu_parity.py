@@ -880,3 +880,43 @@ def test_fused_adam_invalidates_cached_inference_weights():
         expect = ref(data)
     assert not torch.allclose(after_dev, before_dev) and not torch.allclose(after_host, before_host)
     assert scale_normalised_error(after_dev, expect) < EA_TOL and scale_normalised_error(after_host, expect) < EA_TOL
+
+
+def test_peer_fused_adam_single_replica_equals_fused_adam(tmp_path):
+    """PeerFusedAdam with one replica (own arena only) must reproduce FusedAdam exactly: covers the arena hand-over from
+    the backward, the flag protocol, the arena alternation and the parameter update (2- and 4-GPU runs against NCCL:
+    tools/check_peer_adam.py)."""
+    import torch.distributed as dist
+    from cgr_mpnn_3d_b200 import ops
+    from cgr_mpnn_3d_b200.optim import FusedAdam, PeerFusedAdam
+    meta = dict(fa=78, fb=14, depth=3, hidden=128, skip=True, wseed=5, act="relu")
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+        created = True
+    try:
+        ma, mb = build_model(meta, engine="auto").train(), build_model(meta, engine="auto").train()
+        oa = PeerFusedAdam(ma.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True)
+        ob = FusedAdam(mb.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True)
+        for it in range(5):
+            d = make_batch(16, seed=70 + it, kind="t1x", fa=78).to("cuda")
+            oa.zero_grad()
+            mse_sum_loss(ma(d), d.y).backward()
+            assert ma.edge_init.weight.grad.data_ptr() == oa._shared.data_ptr() + oa._cur * oa._total * 4   # in the arena
+            oa.step()
+            ops.set_grad_arena(None)
+            ob.zero_grad()
+            mse_sum_loss(mb(d), d.y).backward()
+            ob.step()
+            ops.set_grad_arena(oa._provide)
+        for (k, a), b in zip(ma.named_parameters(), mb.parameters()):
+            assert torch.equal(a, b), k
+        # a second backward without set_to_none leaves the gradients in the wrong arena: reported, not silently used
+        d = make_batch(16, seed=99, kind="t1x", fa=78).to("cuda")
+        mse_sum_loss(ma(d), d.y).backward()
+        with pytest.raises(RuntimeError, match="shared arena"):
+            oa.step()
+    finally:
+        ops.set_grad_arena(None)
+        if created:
+            dist.destroy_process_group()
