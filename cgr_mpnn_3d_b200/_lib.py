@@ -110,8 +110,8 @@ PROTOTYPES = {
     "cgr_ipc_export": (C.c_int, [_V, _V, C.POINTER(C.c_int64)]),
     "cgr_ipc_open": (C.c_int, [_V, _I64, C.POINTER(C.c_void_p)]),
     "cgr_enable_peer_access": (C.c_int, [C.c_int32]),
-    "cgr_peer_allreduce_adam": (C.c_int, [_V, C.c_int32, _V, _V, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
-                                          C.c_double, C.c_double, C.c_double, _I64, C.c_int32, C.c_float, _V]),
+    "cgr_peer_allreduce_adam": (C.c_int, [_V, C.c_int32, _V, _V, _V, _I64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                          C.c_double, C.c_double, C.c_double, C.c_double, _I64, C.c_int32, C.c_float, _V]),
     "cgr_adam_step": (C.c_int, [_V, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64,
                                 C.c_int32, C.c_float, _V]),
     "cgr_infer_host_check": (C.c_int, [C.POINTER(CgrParams), _I64, _I64, _I64, _V]),

@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constan
 constexpr int PEER_MAX = 16;
 struct PeerTable {
   const float* arena[PEER_MAX];     // every rank's gradient arena of this step (own one included), rank order
-  int* flags[PEER_MAX];             // every rank's flag pad [PEER_MAX] (own one included)
+  int* flags[PEER_MAX];             // every rank's flag pad (own one included): [0,16) gradients ready, [16,32) slice
+                                    // reduced (two-shot), [32] block counter of the owner
+  float* reduced[PEER_MAX];         // two-shot: every rank's buffer holding ITS reduced slice (arena index space)
+  long long total, slice;           // two-shot: arena length and slice length per rank (floats, multiples of 4)
+  int total_blocks;                 // two-shot: virtual blocks of the update phase (the launch is persistent)
   int world, rank, step;
 };
 
@@ -189,6 +193,113 @@ __global__ void __launch_bounds__(ADAM_THREADS) peer_adam_kernel(const __grid_co
   }
 }
 
+
+__device__ __forceinline__ void peer_wait(volatile int* flags, int world, int step) {
+  if ((int)threadIdx.x < world) {
+    unsigned int spins = 0;
+    while (flags[threadIdx.x] < step) {
+      if (++spins > (1u << 28)) __trap();            // a peer died: fail the launch instead of hanging the GPU
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+// Two-shot variant for larger replica counts: rank r first reduces only ITS slice of the gradient (reads that slice
+// from all W arenas, rank order) into its `reduced` buffer, then every rank gathers the W reduced slices and updates its
+// parameters -- 2 (W-1)/W gradient sizes over NVLink per GPU instead of W-1.  Persistent launch (all blocks co-resident:
+// they wait for each other through the owner's block counter).
+__global__ void __launch_bounds__(ADAM_THREADS) peer_adam2_kernel(const __grid_constant__ AdamTable tab,
+                                                                  const __grid_constant__ AdamScalars s,
+                                                                  const __grid_constant__ PeerTable pt) {
+  int* myflags = pt.flags[pt.rank];
+  // phase 0: gradients ready everywhere
+  if (blockIdx.x == 0 && (int)threadIdx.x < pt.world) {
+    __threadfence_system();
+    volatile int* f = pt.flags[threadIdx.x] + pt.rank;
+    *f = pt.step;
+  }
+  peer_wait(myflags, pt.world, pt.step);
+  // phase 1: reduce my slice
+  {
+    const long long lo = (long long)pt.rank * pt.slice;
+    long long hi = lo + pt.slice;
+    if (hi > pt.total) hi = pt.total;
+    float* out = pt.reduced[pt.rank];
+    for (long long i = lo + ((long long)blockIdx.x * ADAM_THREADS + threadIdx.x) * 4; i < hi;
+         i += (long long)gridDim.x * ADAM_THREADS * 4) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < pt.world; ++r) {
+        const float4 x = ld_peer4(pt.arena[r] + i);
+        g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+      }
+      *reinterpret_cast<float4*>(out + i) = g;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(myflags + 32, 1);
+    if (done == (int)gridDim.x - 1) {                 // every block of this rank has written its part of the slice
+      myflags[32] = 0;
+      __threadfence_system();
+      for (int r = 0; r < pt.world; ++r) {
+        volatile int* f = pt.flags[r] + 16 + pt.rank;
+        *f = pt.step;
+      }
+    }
+  }
+  // phase 2: all slices reduced everywhere -> gather + Adam
+  peer_wait(myflags + 16, pt.world, pt.step);
+  for (int vb = blockIdx.x; vb < pt.total_blocks; vb += gridDim.x) {
+    int lo = 0, hi = tab.n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tab.first_block[mid] <= vb) lo = mid; else hi = mid;
+    }
+    const int t = lo;
+    const long long base = (long long)(vb - tab.first_block[t]) * ADAM_CHUNK;
+    const long long n = tab.numel[t];
+    float* __restrict__ P = tab.param[t];
+    const long long goff = (long long)(size_t)tab.grad[t];
+    float* __restrict__ M = tab.m[t];
+    float* __restrict__ V = tab.v[t];
+    float* __restrict__ VM = tab.vmax[t];
+    const bool vec = ((((uintptr_t)P | (uintptr_t)M | (uintptr_t)V | (uintptr_t)(s.amsgrad ? VM : P)) & 15) == 0) && (goff & 3) == 0;
+    if (vec && base + ADAM_CHUNK <= n) {
+#pragma unroll
+      for (int it = 0; it < ADAM_CHUNK / (ADAM_THREADS * 4); ++it) {
+        const long long i = base + (long long)(it * ADAM_THREADS + threadIdx.x) * 4;
+        const long long a = goff + i;                        // slices are multiples of 4: one owner per float4
+        const float4 g = ld_peer4(pt.reduced[(int)(a / pt.slice)] + a);
+        float4 p = *reinterpret_cast<float4*>(P + i);
+        float4 m = *reinterpret_cast<float4*>(M + i);
+        float4 v = *reinterpret_cast<float4*>(V + i);
+        float4 vm = s.amsgrad ? *reinterpret_cast<float4*>(VM + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        adam_one(p.x, g.x, m.x, v.x, vm.x, s);
+        adam_one(p.y, g.y, m.y, v.y, vm.y, s);
+        adam_one(p.z, g.z, m.z, v.z, vm.z, s);
+        adam_one(p.w, g.w, m.w, v.w, vm.w, s);
+        *reinterpret_cast<float4*>(P + i) = p;
+        *reinterpret_cast<float4*>(M + i) = m;
+        *reinterpret_cast<float4*>(V + i) = v;
+        if (s.amsgrad) *reinterpret_cast<float4*>(VM + i) = vm;
+      }
+    } else {
+      const long long end = base + ADAM_CHUNK < n ? base + ADAM_CHUNK : n;
+      for (long long i = base + threadIdx.x; i < end; i += ADAM_THREADS) {
+        const long long a = goff + i;
+        const float g = ld_peer(pt.reduced[(int)(a / pt.slice)] + a);
+        float p = P[i], m = M[i], v = V[i], vm = s.amsgrad ? VM[i] : 0.f;
+        adam_one(p, g, m, v, vm, s);
+        P[i] = p; M[i] = m; V[i] = v;
+        if (s.amsgrad) VM[i] = vm;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int cgr_enable_peer_access(int32_t peer_device) {
@@ -237,9 +348,10 @@ extern "C" int cgr_ipc_open(const void* handle, int64_t offset, void** ptr_out) 
 }
 
 extern "C" int cgr_peer_allreduce_adam(const cgr_adam_tensor_t* tensors, int32_t n_tensors, const float* const* peer_arenas,
-                                       int* const* peer_flags, int32_t world, int32_t rank, int32_t sync_step, double lr,
-                                       double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                                       int32_t amsgrad, float grad_scale, void* stream) {
+                                       int* const* peer_flags, float* const* peer_reduced, int64_t arena_floats,
+                                       int32_t world, int32_t rank, int32_t sync_step, double lr, double beta1,
+                                       double beta2, double eps, double weight_decay, int64_t step, int32_t amsgrad,
+                                       float grad_scale, void* stream) {
   CGR_CHECK_ARG(tensors && n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS, "cgr_peer_allreduce_adam: 1..%d tensors", ADAM_MAX_TENSORS);
   CGR_CHECK_ARG(peer_arenas && peer_flags && world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world,
                 "cgr_peer_allreduce_adam: bad peer table");
@@ -279,7 +391,23 @@ extern "C" int cgr_peer_allreduce_adam(const cgr_adam_tensor_t* tensors, int32_t
   }
   pt.world = world; pt.rank = rank; pt.step = sync_step;
   cgr_note_launch("peer_allreduce_adam", st, 1);
-  peer_adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(tab, s, pt);
+  if (peer_reduced) {                                  // two-shot
+    CGR_CHECK_ARG(arena_floats > 0 && (arena_floats & 3) == 0, "cgr_peer_allreduce_adam: arena length must be a multiple of 4");
+    for (int r = 0; r < world; ++r) {
+      CGR_CHECK_ARG(peer_reduced[r], "cgr_peer_allreduce_adam: null reduced-slice pointer");
+      pt.reduced[r] = peer_reduced[r];
+    }
+    pt.total = arena_floats;
+    pt.slice = (cgr_ceil_div(arena_floats, (int64_t)world) + 3) / 4 * 4;
+    pt.total_blocks = blocks;
+    int dev = 0, sms = 0;
+    CGR_CUDA(cudaGetDevice(&dev));
+    CGR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = blocks < 4 * sms ? blocks : 4 * sms;     // persistent: every block resident (they wait for each other)
+    peer_adam2_kernel<<<grid, ADAM_THREADS, 0, st>>>(tab, s, pt);
+  } else {
+    peer_adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(tab, s, pt);
+  }
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }

@@ -138,7 +138,7 @@ class PeerFusedAdam(torch.optim.Optimizer):
     """
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, grad_scale=1.0,
-                 group=None):
+                 group=None, two_shot=None):
         import torch.distributed as dist
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
         super().__init__(params, defaults)
@@ -161,8 +161,8 @@ class PeerFusedAdam(torch.optim.Optimizer):
         self._total = sum(self._sizes)
         lib = _lib.load()
         with torch.cuda.device(self.device):
-            # [arena 0 | arena 1 | flag pad]: one allocation of its own (cudaMalloc'ed block, exportable through CUDA IPC)
-            self._shared = torch.zeros(2 * self._total + 64, dtype=torch.float32, device=self.device)
+            # [arena 0 | arena 1 | reduced slices | flag pad]: one block, exported to the peers through CUDA IPC
+            self._shared = torch.zeros(3 * self._total + 64, dtype=torch.float32, device=self.device)
             torch.cuda.synchronize(self.device)
             handle = C.create_string_buffer(64)
             offset = C.c_int64(0)
@@ -183,7 +183,13 @@ class PeerFusedAdam(torch.optim.Optimizer):
         for buf in (0, 1):
             arr = (C.c_void_p * self.world)(*[q + buf * self._total * 4 for q in self._peer_ptrs])
             self._arena_ptrs.append(arr)
-        self._flag_ptrs = (C.c_void_p * self.world)(*[q + 2 * self._total * 4 for q in self._peer_ptrs])
+        self._reduced_ptrs = (C.c_void_p * self.world)(*[q + 2 * self._total * 4 for q in self._peer_ptrs])
+        self._flag_ptrs = (C.c_void_p * self.world)(*[q + 3 * self._total * 4 for q in self._peer_ptrs])
+        # one-shot: every rank reads all W arenas (W-1 gradient sizes per GPU); two-shot: reduce one slice each, then
+        # gather (2 (W-1)/W sizes) -- the better trade from about 4 replicas up
+        import os
+        env = os.environ.get("CGR_PEER_TWO_SHOT")
+        self.two_shot = bool(two_shot) if two_shot is not None else (env == "1" if env is not None else self.world > 4)
         self._cur = 0                             # arena the next backward writes into
         self._sync_step = 0
         self._adam_step = 0
@@ -246,7 +252,8 @@ class PeerFusedAdam(torch.optim.Optimizer):
         self._adam_step += 1
         beta1, beta2 = group["betas"]
         with torch.cuda.device(self.device):
-            rc = lib.cgr_peer_allreduce_adam(self._table, len(ps), self._arena_ptrs[self._cur], self._flag_ptrs, self.world,
+            rc = lib.cgr_peer_allreduce_adam(self._table, len(ps), self._arena_ptrs[self._cur], self._flag_ptrs,
+                                             self._reduced_ptrs if self.two_shot else None, self._total, self.world,
                                              self.rank, self._sync_step, float(group["lr"]), float(beta1), float(beta2),
                                              float(group["eps"]), float(group["weight_decay"]), self._adam_step,
                                              int(amsgrad), self.grad_scale,

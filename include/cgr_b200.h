@@ -349,12 +349,15 @@ int cgr_adam_step(const cgr_adam_tensor_t* tensors, int32_t n_tensors, double lr
 /* Data-parallel optimizer step WITHOUT a collective library: the SUM of the replicas' gradients (the loss is
  * MSELoss(reduction="sum"), train.py:120, so replicas sum) and the Adam update of train.py:117-119 in ONE kernel.
  * `peer_arenas` / `peer_flags`: HOST arrays [world] of DEVICE pointers -- every rank's flat fp32 gradient arena of this
- * step and flag pad (int[16], zero-initialised once), rank order, the caller's own included; the peers' ones are mapped
+ * step and flag pad (int[64], zero-initialised once), rank order, the caller's own included; the peers' ones are mapped
  * with CUDA IPC and reachable after cgr_enable_peer_access.  In `tensors`, `grad` holds the tensor's OFFSET inside the
  * arenas in floats (cast to a pointer), identical on every rank.  `sync_step` must grow by one per call on every rank
  * (1, 2, ...): the kernel announces it in all flag pads, waits for all peers, then reads each gradient element from all
  * arenas in rank order (bit-identical sums on every replica) and updates its own parameters.  Callers alternate two
- * arenas per rank so a fast rank never overwrites gradients a slow peer still reads. */
+ * arenas per rank so a fast rank never overwrites gradients a slow peer still reads.
+ * `peer_reduced` NULL: one-shot (every rank reads all W arenas).  Non-NULL (HOST array [world] of DEVICE pointers to
+ * every rank's `arena_floats`-long scratch buffer, mapped like the arenas): two-shot -- each rank reduces one slice, all
+ * ranks gather the slices: 2 (W-1)/W instead of W-1 gradient sizes over NVLink per GPU, for larger replica counts. */
 int cgr_enable_peer_access(int32_t peer_device);
 /* CUDA IPC helpers for the arenas: export = 64-byte handle of the allocation containing `dev_ptr` + the pointer's byte
  * offset inside it; open = map a peer's allocation for the calling thread's current device and return the address of the
@@ -362,9 +365,9 @@ int cgr_enable_peer_access(int32_t peer_device);
 int cgr_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
 int cgr_ipc_open(const void* handle, int64_t offset, void** ptr_out);
 int cgr_peer_allreduce_adam(const cgr_adam_tensor_t* tensors, int32_t n_tensors, const float* const* peer_arenas,
-                            int* const* peer_flags, int32_t world, int32_t rank, int32_t sync_step, double lr,
-                            double beta1, double beta2, double eps, double weight_decay, int64_t step, int32_t amsgrad,
-                            float grad_scale, void* stream);
+                            int* const* peer_flags, float* const* peer_reduced, int64_t arena_floats, int32_t world,
+                            int32_t rank, int32_t sync_step, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, int64_t step, int32_t amsgrad, float grad_scale, void* stream);
 
 /* Measurement hooks used by bench.py: number of kernels this library has launched so far, and
  * optional CUDA-event timing of each named stage (events are recorded on the launching stream). */
