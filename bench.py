@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--engine", default=os.environ.get("CGR_ENGINE", "auto"))
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--pool", type=int, default=48, help="distinct resident batches rotated through (> L2)")
+    ap.add_argument("--no-group", action="store_true",
+                    help="replay one single-batch graph per step instead of one graph per group of --streams batches")
     ap.add_argument("--no-graph", action="store_true", help="time eager custom-op calls instead of CUDA-graph replay")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -284,26 +286,56 @@ def main():
         streams = [torch.cuda.Stream() for _ in range(n_streams)]
         main = torch.cuda.current_stream()
 
+        # One graph per GROUP of n_streams consecutive batches, their forwards on parallel branches (fork / join inside
+        # the capture): the same launches as replaying n_streams single-batch graphs on n_streams streams, with one host
+        # call instead of n_streams -- with one process per GPU on a shared host the submitting threads are the first
+        # thing to saturate.  Consecutive groups alternate between two streams so they overlap at their boundaries.
+        group_graphs = []
+        if graphs is not None and n_streams > 1 and not args.no_group:
+            for g0 in range(0, n_pool, n_streams):
+                gg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gg, stream=side):
+                    fork_c = torch.cuda.Event()
+                    fork_c.record(side)
+                    for k in range(n_streams):
+                        st = streams[k]
+                        st.wait_event(fork_c)
+                        with torch.cuda.stream(st):
+                            outs[g0 + k] = model(pool[g0 + k])
+                        ev_c = torch.cuda.Event()
+                        ev_c.record(st)
+                        side.wait_event(ev_c)
+                group_graphs.append(gg)
+        gstreams = [torch.cuda.Stream(), torch.cuda.Stream()]
+
         def run_steps(count):
-            """`count` independent forward passes; step i replays graph i % n_pool on stream i % n_streams."""
+            """`count` independent forward passes: batch i % n_pool, n_streams of them in flight."""
             if graphs is None:
                 for i in range(count):
                     outs[i % n_pool] = model(pool[i % n_pool])
                 return
             fork = torch.cuda.Event()
             fork.record(main)
-            for st in streams:
+            used = streams + gstreams
+            for st in used:
                 st.wait_event(fork)
-            for i in range(count):
-                with torch.cuda.stream(streams[i % n_streams]):
-                    graphs[i % n_pool].replay()
-            for st in streams:
+            i = 0
+            if group_graphs:
+                n_groups = count // n_streams
+                for j in range(n_groups):
+                    with torch.cuda.stream(gstreams[j & 1]):
+                        group_graphs[j % len(group_graphs)].replay()
+                i = n_groups * n_streams
+            for k in range(i, count):                 # remainder: single-batch graphs on their own streams
+                with torch.cuda.stream(streams[k % n_streams]):
+                    graphs[k % n_pool].replay()
+            for st in used:
                 ev = torch.cuda.Event()
                 ev.record(st)
                 main.wait_event(ev)
 
         if graphs is not None:             # initialisation, like the capture itself: instantiate/upload every graph once
-            for gph in graphs:
+            for gph in graphs + group_graphs:
                 gph.replay()
             torch.cuda.synchronize()
         clocks = ClockSampler(local_rank).start()
@@ -657,6 +689,8 @@ def main():
                                    f"{args.batch}/GPU, Fa={FA} Fb={FB}, T1x-shaped synthetic reactions, random-init "
                                    f"weights in the reference .pth layout",
                        "engine": engine, "cuda_graph": not args.no_graph, "streams": n_streams,
+                       "graph_grouping": (f"one graph per {n_streams} batches on parallel branches, groups alternate over 2 streams"
+                                          if group_graphs else "one graph per batch"),
                        "single_stream_ms_per_step": single_stream_ms,
                        "parallelism": f"replicas x{world}, no collective",
                        "l2": f"inputs rotate over {n_pool} distinct resident batches ({resident / 1e6:.0f} MB > "
