@@ -185,7 +185,16 @@ int cgr_readout_fwd(const float* h, const float* x, const int32_t* in_ptr, const
  * ---------------------------------------------------------------------------------------- */
 size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t training,
                              int32_t engine);
-/* out [B].  `saved` must be non-NULL when training != 0 (activations for backward). */
+/* out [B].  `saved` must be non-NULL when training != 0 (activations for backward).
+ * Engine CGR_ENGINE_TC picks its path from the arguments:
+ *   - g->tile_info set, saved == NULL           : fused tile kernels (7 launches), inference;
+ *   - g->tile_info set, saved->tc_blob != NULL  : the same kernels keeping every layer's FP16 operands in tc_blob
+ *                                                 (ReLU networks; cgr_tc_saved_bytes > 0) -- cgr_gnn_backward with the
+ *                                                 same `saved` then runs the fused tile-local backward; when
+ *                                                 p->tc_weights is NULL the prepared weights are stored in tc_blob too
+ *                                                 and the backward reads them from there (pass the same p);
+ *   - otherwise                                 : layer-wise kernels with tensor-core GEMMs (any activation, any
+ *                                                 reaction size), activations in the fp32 buffers of `saved`. */
 int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved,
                     int32_t training, uint64_t seed, int32_t engine, void* workspace,
                     size_t workspace_bytes, void* stream);
