@@ -151,3 +151,48 @@ def test_reaction_store_is_device_only():
     from cgr_mpnn_3d_b200.store import ReactionStore
     with pytest.raises(RuntimeError, match="CUDA"):
         ReactionStore.from_graphs(make_reactions(3, seed=0, kind="t1x", fa=8), device="cpu")
+
+
+def test_host_tile_plan_matches_oracle():
+    """cgr_tc_plan_host is pure host code (no device work): the greedy packing of whole reactions into 128-row tiles
+    must equal the oracle's restatement, and untileable reactions are reported with -3."""
+    import ctypes as C
+    import numpy as np
+    from cgr_mpnn_3d_b200 import _lib
+    from oracle import collate_oracle
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        b = int(rng.integers(1, 200))
+        na = rng.integers(2, 40, size=b)
+        ne = 2 * rng.integers(1, 45, size=b)
+        ptr = np.concatenate([[0], np.cumsum(na)]).astype(np.int64)
+        eptr = np.concatenate([[0], np.cumsum(ne)]).astype(np.int64)
+        tiles = np.zeros((b, 8), dtype=np.int32)
+        n_tiles = C.c_int64(0)
+        rc = lib.cgr_tc_plan_host(ptr.ctypes.data, eptr.ctypes.data, b, tiles.ctypes.data, C.byref(n_tiles))
+        assert rc == 0
+        tf = collate_oracle.tile_plan(ptr, eptr)["tile_first"]
+        t = int(n_tiles.value)
+        assert t == tf.size - 1
+        assert np.array_equal(tiles[:t, 4], tf[:-1]) and np.array_equal(tiles[:t, 5], np.diff(tf))
+        assert np.array_equal(tiles[:t, 0], eptr[tf[:-1]]) and np.array_equal(tiles[:t, 1], eptr[tf[1:]] - eptr[tf[:-1]])
+        assert np.array_equal(tiles[:t, 2], ptr[tf[:-1]]) and np.array_equal(tiles[:t, 3], ptr[tf[1:]] - ptr[tf[:-1]])
+        assert tiles[:t, 1].max() <= 128 and tiles[:t, 3].max() <= 128
+    ptr = np.array([0, 10, 150], dtype=np.int64)          # second reaction: 140 atoms / 300 bonds
+    eptr = np.array([0, 20, 320], dtype=np.int64)
+    tiles = np.zeros((2, 8), dtype=np.int32)
+    assert lib.cgr_tc_plan_host(ptr.ctypes.data, eptr.ctypes.data, 2, tiles.ctypes.data, C.byref(n_tiles)) == -3
+    assert b"not tileable" in lib.cgr_last_error_string()
+
+
+def test_optimizer_entry_points_validate_arguments_without_a_gpu():
+    import ctypes as C
+    from cgr_mpnn_3d_b200 import _lib
+    lib = _lib.load()
+    arr = (_lib.CgrAdamTensor * 1)()
+    assert lib.cgr_adam_step(None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1, 1.0, None) < 0
+    assert lib.cgr_adam_step(arr, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1, 1.0, None) < 0          # steps count from 1
+    assert lib.cgr_adam_step(arr, 1, 1e-3, 1.5, 0.999, 1e-8, 0.0, 1, 1, 1.0, None) < 0          # beta1 out of range
+    assert b"range" in lib.cgr_last_error_string()
+    assert lib.cgr_peer_allreduce_adam(arr, 1, None, None, None, 0, 2, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1, 1.0, None) < 0
