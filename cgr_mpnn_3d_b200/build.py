@@ -48,17 +48,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if fh.read().strip() == digest:
                 return LIB
     nvcc = _nvcc()
-    objs = []
-    logs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    objs = []
+    logs = []
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:     # one nvcc per source file
+        for src, obj, r in pool.map(compile_one, SOURCES):
+            logs.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"nvcc failed on {src}")
+            objs.append(obj)
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -84,33 +84,37 @@ def build_plan(edge_index: torch.Tensor, num_nodes: int, batch: Optional[torch.T
     p = GraphPlan()
     p.n_atoms, p.n_bonds = n, e
     i32 = dict(dtype=torch.int32, device=dev)
-    p.src = torch.empty(e, **i32)
-    p.dst = torch.empty(e, **i32)
-    p.in_ptr = torch.empty(n + 1, **i32)
-    p.in_idx = torch.empty(e, **i32)
-    p.status = torch.empty(1, **i32)
-    ws_bytes = lib.cgr_csr_workspace(n, e)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.cgr_csr_build(ei.data_ptr(), e, n, p.src.data_ptr(), p.dst.data_ptr(), p.in_ptr.data_ptr(),
-                                 p.in_idx.data_ptr(), p.status.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
-               "cgr_csr_build")
-    if batch is None:
-        p.n_rxn = 1
-        p.atom_ptr = torch.tensor([0, n], **i32)
-    else:
-        if ptr is not None:
-            p.n_rxn = int(ptr.numel()) - 1
-            p.atom_ptr = ptr.to(device=dev, dtype=torch.int32)
+    # the kernels launch on `dev` whatever the caller's current device is (a model / batch on cuda:1 in a process whose
+    # current device is cuda:0)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        p.src = torch.empty(e, **i32)
+        p.dst = torch.empty(e, **i32)
+        p.in_ptr = torch.empty(n + 1, **i32)
+        p.in_idx = torch.empty(e, **i32)
+        p.status = torch.empty(1, **i32)
+        ws_bytes = lib.cgr_csr_workspace(n, e)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.cgr_csr_build(ei.data_ptr(), e, n, p.src.data_ptr(), p.dst.data_ptr(), p.in_ptr.data_ptr(),
+                                     p.in_idx.data_ptr(), p.status.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                   "cgr_csr_build")
+        if batch is None:
+            p.n_rxn = 1
+            p.atom_ptr = torch.tensor([0, n], **i32)
         else:
-            # reference semantics: global_add_pool sizes its output as batch.max()+1 (one host sync,
-            # like PyG's own); pass `ptr` or `num_graphs` to avoid it
-            p.n_rxn = int(num_graphs) if num_graphs is not None else int(batch.max()) + 1
-            b = batch.contiguous()
-            if b.dtype != torch.int64:
-                b = b.to(torch.int64)
-            p.atom_ptr = torch.empty(p.n_rxn + 1, **i32)
-            _lib.check(lib.cgr_atom_ptr_from_batch(b.data_ptr(), n, p.n_rxn, p.atom_ptr.data_ptr(), _stream()),
-                       "cgr_atom_ptr_from_batch")
+            if ptr is not None:
+                p.n_rxn = int(ptr.numel()) - 1
+                p.atom_ptr = ptr.to(device=dev, dtype=torch.int32)
+            else:
+                # reference semantics: global_add_pool sizes its output as batch.max()+1 (one host sync,
+                # like PyG's own); pass `ptr` or `num_graphs` to avoid it
+                p.n_rxn = int(num_graphs) if num_graphs is not None else int(batch.max()) + 1
+                b = batch.contiguous()
+                if b.dtype != torch.int64:
+                    b = b.to(torch.int64)
+                p.atom_ptr = torch.empty(p.n_rxn + 1, **i32)
+                _lib.check(lib.cgr_atom_ptr_from_batch(b.data_ptr(), n, p.n_rxn, p.atom_ptr.data_ptr(), st),
+                           "cgr_atom_ptr_from_batch")
     return p
 
 

@@ -277,7 +277,8 @@ int setup_tc_ctx(GemmCtx& c, const cgr_params_t* p, const cgr_graph_t* g, char* 
   c.b_lo = (__half*)ptr; ptr += w.slot_bytes;
   c.amax = (unsigned int*)ptr;
   c.unscale = (float*)(ptr + 64);
-  c.overflow = (int*)(ptr + 128);
+  // fp16-range flag of the operand splits: the caller's tc_status[0] when given (observable), else scratch
+  c.overflow = g->tc_status ? g->tc_status : (int*)(ptr + 128);
   ptr += 1024;
   int rc;
   if (p->tc_weights) {
@@ -424,6 +425,7 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
   GemmCtx c;
   if (engine == CGR_ENGINE_TC) {
     CGR_CHECK_ARG(tc_training_ok(p), "tcgen05 training path supports depth <= 13");
+    if ((rc = tc_flag_begin(g->tc_status, st))) return rc;
     rc = setup_tc_ctx(c, p, g, ws.base + ws.off, st);
     if (rc) return rc;
   }
@@ -444,8 +446,11 @@ extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, floa
     if (rc) return rc;
     h = h_out;
   }
-  return readout_impl(c, h, g->x, g->in_ptr, g->in_idx, g->atom_ptr, p->w_e2n, p->b_e2n, p->w_ffn, p->b_ffn, p->act, out,
-                      s, hv, saved ? saved->zv : nullptr, pooled, N, B, p->fa, p->hidden, d, st);
+  rc = readout_impl(c, h, g->x, g->in_ptr, g->in_idx, g->atom_ptr, p->w_e2n, p->b_e2n, p->w_ffn, p->b_ffn, p->act, out,
+                    s, hv, saved ? saved->zv : nullptr, pooled, N, B, p->fa, p->hidden, d, st);
+  if (rc) return rc;
+  if (engine == CGR_ENGINE_TC) return tc_poison_outputs(out, B, g->tc_status, st);
+  return CGR_OK;
 }
 
 extern "C" size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t engine) {

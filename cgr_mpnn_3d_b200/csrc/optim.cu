@@ -3,6 +3,7 @@
 // in ONE launch.  HBM-bound: per element it reads param, grad, m, v, vmax and writes param, m, v, vmax (36 bytes).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cgr_b200.h"
@@ -110,7 +111,14 @@ struct PeerTable {
   long long total, slice;           // two-shot: arena length and slice length per rank (floats, multiples of 4)
   int total_blocks;                 // two-shot: virtual blocks of the update phase (the launch is persistent)
   int world, rank, step;
+  unsigned long long timeout_ns;    // how long to wait for a peer before failing the launch (CGR_PEER_TIMEOUT_S, default 600 s)
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float ld_peer(const float* p) {       // peer lines must not be served from a stale L1 line
   float v;
@@ -135,9 +143,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) peer_adam_kernel(const __grid_co
   }
   if (threadIdx.x < pt.world) {
     volatile int* mine = pt.flags[pt.rank] + threadIdx.x;
+    const unsigned long long t0 = global_ns();
     unsigned int spins = 0;
     while (*mine < pt.step) {
-      if (++spins > (1u << 28)) __trap();            // a peer died: fail the launch instead of hanging the GPU
+      // a peer that stays away for the whole timeout (default 10 minutes: validation, checkpointing and stragglers are
+      // fine) is taken for dead: fail the launch instead of hanging the GPU
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > pt.timeout_ns) __trap();
       __nanosleep(64);
     }
     __threadfence_system();
@@ -194,11 +205,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) peer_adam_kernel(const __grid_co
 }
 
 
-__device__ __forceinline__ void peer_wait(volatile int* flags, int world, int step) {
+__device__ __forceinline__ void peer_wait(volatile int* flags, int world, int step, unsigned long long timeout_ns) {
   if ((int)threadIdx.x < world) {
+    const unsigned long long t0 = global_ns();
     unsigned int spins = 0;
     while (flags[threadIdx.x] < step) {
-      if (++spins > (1u << 28)) __trap();            // a peer died: fail the launch instead of hanging the GPU
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) __trap();   // a peer died: fail the launch
       __nanosleep(64);
     }
     __threadfence_system();
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) peer_adam2_kernel(const __grid_c
     volatile int* f = pt.flags[threadIdx.x] + pt.rank;
     *f = pt.step;
   }
-  peer_wait(myflags, pt.world, pt.step);
+  peer_wait(myflags, pt.world, pt.step, pt.timeout_ns);
   // phase 1: reduce my slice
   {
     const long long lo = (long long)pt.rank * pt.slice;
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) peer_adam2_kernel(const __grid_c
     }
   }
   // phase 2: all slices reduced everywhere -> gather + Adam
-  peer_wait(myflags + 16, pt.world, pt.step);
+  peer_wait(myflags + 16, pt.world, pt.step, pt.timeout_ns);
   for (int vb = blockIdx.x; vb < pt.total_blocks; vb += gridDim.x) {
     int lo = 0, hi = tab.n;
     while (hi - lo > 1) {
@@ -390,6 +402,8 @@ extern "C" int cgr_peer_allreduce_adam(const cgr_adam_tensor_t* tensors, int32_t
     pt.arena[r] = peer_arenas[r]; pt.flags[r] = peer_flags[r];
   }
   pt.world = world; pt.rank = rank; pt.step = sync_step;
+  static const double timeout_s = getenv("CGR_PEER_TIMEOUT_S") ? atof(getenv("CGR_PEER_TIMEOUT_S")) : 600.0;
+  pt.timeout_ns = (unsigned long long)((timeout_s > 0 ? timeout_s : 600.0) * 1e9);
   cgr_note_launch("peer_allreduce_adam", st, 1);
   if (peer_reduced) {                                  // two-shot
     CGR_CHECK_ARG(arena_floats > 0 && (arena_floats & 3) == 0, "cgr_peer_allreduce_adam: arena length must be a multiple of 4");
@@ -403,8 +417,25 @@ extern "C" int cgr_peer_allreduce_adam(const cgr_adam_tensor_t* tensors, int32_t
     int dev = 0, sms = 0;
     CGR_CUDA(cudaGetDevice(&dev));
     CGR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = blocks < 4 * sms ? blocks : 4 * sms;     // persistent: every block resident (they wait for each other)
-    peer_adam2_kernel<<<grid, ADAM_THREADS, 0, st>>>(tab, s, pt);
+    // persistent: the blocks wait for each other, so all of them must be co-resident -- the grid is sized from the
+    // occupancy query and launched cooperatively (the driver then schedules it only when the whole grid fits, also
+    // when another stream holds SMs)
+    int occ = 0;
+    CGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_adam2_kernel, ADAM_THREADS, 0));
+    CGR_CHECK_ARG(occ >= 1, "cgr_peer_allreduce_adam: the two-shot kernel does not fit an SM");
+    if (occ > 4) occ = 4;
+    const int grid = blocks < occ * sms ? blocks : occ * sms;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(ADAM_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CGR_CUDA(cudaLaunchKernelEx(&cfg, peer_adam2_kernel, tab, s, pt));
   } else {
     peer_adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(tab, s, pt);
   }

@@ -35,7 +35,7 @@ using namespace tcg;
 // fp32 rows -> (hi, lo) fp16 rows; one warp per row
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
                                                          __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldo,
-                                                         int* __restrict__ overflow) {
+                                                         int* __restrict__ overflow, int flag_bit) {
   const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   bool ovf = false;
@@ -47,7 +47,18 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
     hi[r * ldo + c] = h;
     lo[r * ldo + c] = l;
   }
-  if (ovf) atomicOr(overflow, 1);
+  if (ovf && overflow) atomicOr(overflow, flag_bit);
+}
+
+// tc_status[0] bits (cgr_b200.h): bit 0 = an activation of THIS forward left the fp16 range (cleared when a forward
+// starts), bit 1 = a feature of data.x did (set by the feature split at batch preparation, kept for the batch's life)
+constexpr int FLAG_ACT = 1, FLAG_X = 2;
+__global__ void flag_begin_kernel(int* flag) { atomicAnd(flag, ~FLAG_ACT); }
+// energies computed from clipped operands are wrong: make that impossible to miss (NaN), no host synchronisation needed
+__global__ void poison_kernel(float* out, int64_t n, const int* flag) {
+  if ((*flag & (FLAG_ACT | FLAG_X)) == 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __int_as_float(0x7fc00000);
 }
 
 // h0 = act(P'[src e] + ea[e] . W_e^T) on tile-packed rows (P' already holds b_i).  A block owns 32 bond rows of one
@@ -468,7 +479,22 @@ int tc_split_features(const float* x, int64_t n, int fa, void* x_hi, void* x_lo,
   CgrRange prof("tc_split_x", st);
   cgr_note_launch("tc_split_x", st, 1);
   split_rows_kernel<<<(unsigned)cgr_ceil_div(n, 8), 256, 0, st>>>(x, fa, n, fa, (__half*)x_hi, (__half*)x_lo,
-                                                                  round_up(fa, BK), status);
+                                                                  round_up(fa, BK), status, FLAG_X);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+
+int tc_flag_begin(int* flag, cudaStream_t st) {
+  if (!flag) return CGR_OK;
+  cgr_note_launch("tc_flag", st, 1);
+  flag_begin_kernel<<<1, 1, 0, st>>>(flag);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+int tc_poison_outputs(float* out, int64_t n, const int* flag, cudaStream_t st) {
+  if (!flag || n <= 0) return CGR_OK;
+  cgr_note_launch("tc_flag", st, 1);
+  poison_kernel<<<(unsigned)(n < 65536 ? cgr_ceil_div(n, 256) : 256), 256, 0, st>>>(out, n, flag);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }
@@ -695,7 +721,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   if (need_x) {
     CgrRange prof("tc_split_x", st);
     cgr_note_launch("tc_split_x", st, 1);
-    split_rows_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(g->x, fa, N, fa, x_hi, x_lo, w.kp_x, flag);
+    split_rows_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(g->x, fa, N, fa, x_hi, x_lo, w.kp_x, flag, FLAG_X);
     CGR_LAUNCH_CHECK();
   }
   // 2. per-atom projections [P' | Q'] = x [W_x ; W_ox]^T + [b_i | b_o]   (GNN.py:86 and :106-107, x part)
@@ -715,6 +741,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.bias = bias_cat;
     prm.out_f32 = PQ;
     prm.ldc = 2 * H;
+    prm.overflow = flag;             // first kernel of the forward: clears the per-forward overflow bit
     rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false,
                                 two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
     if (rc) return rc;
@@ -1261,8 +1288,8 @@ int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wg
   int* flag = (int*)(one + 16);
   CGR_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   set_one_kernel<<<1, 1, 0, st>>>(one);
-  split_rows_kernel<<<(unsigned)cgr_ceil_div(M, 8), 256, 0, st>>>(x, ldx, M, (int)K, a_hi, a_lo, kp, flag);
-  split_rows_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(wgt, ldw, N, (int)K, b_hi, b_lo, kp, flag);
+  split_rows_kernel<<<(unsigned)cgr_ceil_div(M, 8), 256, 0, st>>>(x, ldx, M, (int)K, a_hi, a_lo, kp, flag, FLAG_ACT);
+  split_rows_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(wgt, ldw, N, (int)K, b_hi, b_lo, kp, flag, FLAG_ACT);
   CGR_LAUNCH_CHECK();
   TcGemmParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -1403,7 +1430,7 @@ int tc_split(const float* in, int64_t ld, int64_t rows, int cols, bool scaled, _
                                                                          ldo);
   } else {
     cgr_note_launch("tc_split", st, 1);
-    split_rows_kernel<<<(unsigned)cgr_ceil_div(rows, 8), 256, 0, st>>>(in, ld, rows, cols, hi, lo, ldo, overflow);
+    split_rows_kernel<<<(unsigned)cgr_ceil_div(rows, 8), 256, 0, st>>>(in, ld, rows, cols, hi, lo, ldo, overflow, FLAG_ACT);
   }
   CGR_LAUNCH_CHECK();
   return CGR_OK;

@@ -27,6 +27,9 @@ size_t tc_linear_workspace(int64_t M, int64_t N, int64_t K);
 int tc_linear(const float* x, int64_t M, int64_t K, int64_t ldx, const float* wgt, int64_t N, int64_t ldw,
               const float* bias, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void tc_set_debug_buffer(long long* p);
+// tc_status[0] handling of the layer-wise path: clear the per-forward overflow bit / poison the energies with NaN when set
+int tc_flag_begin(int* flag, cudaStream_t st);
+int tc_poison_outputs(float* out, int64_t n, const int* flag, cudaStream_t st);
 int tc_split_features(const float* x, int64_t n, int fa, void* x_hi, void* x_lo, int* status, cudaStream_t st);
 
 // ---- training path: tensor-core GEMMs on FP16 (hi, lo) operands of either major ----

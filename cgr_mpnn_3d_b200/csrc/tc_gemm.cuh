@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   long long* dbg = p.dbg ? p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
 #define TC_STAMP(k) do { if (dbg && threadIdx.x == 64) dbg[k] = clock64(); } while (0)
   TC_STAMP(0);
+  // the atom projection opens a forward: clear the per-forward overflow bit (bit 1, feature overflow, belongs to the batch)
+  if (EPI == EPI_PLAIN && p.overflow && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAnd(p.overflow, ~1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -735,11 +737,14 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
     if (aux->info[7] == (int)gridDim.x - 1) {
       __threadfence();
       const float bf = __ldg(p.b_ffn);
+      // an operand left the fp16 range somewhere in this forward (the flag is final: every producer kernel has completed):
+      // the energies are poisoned with NaN so the condition cannot go unnoticed without a host synchronisation
+      const bool poisoned = p.overflow && (__ldcg(p.overflow) & 3) != 0;
       for (int rx = threadIdx.x; rx < rxcount; rx += THREADS) {
         const int b = rx0 + rx;
         float s = 0.f;
         for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(p.partial_out + (int64_t)i * p.n_rxn + b);
-        p.out[b] = s + bf;
+        p.out[b] = poisoned ? __int_as_float(0x7fc00000) : s + bf;
       }
       if (threadIdx.x == 0) p.tile_counter[tile] = 0;             // ready for the next forward
     }

@@ -135,14 +135,79 @@ class GNN(nn.Module):
         """simt = exact-fp32 layer-wise kernels.  tc = tcgen05 FP16x3 tensor-core kernels: fused tile kernels for
         an inference forward (needs a hidden size divisible by 4 and reactions of at most 128 directed bonds),
         layer-wise path with tensor-core GEMMs when activations must be saved for a backward.
-        auto picks tc whenever it applies."""
+        auto picks tc whenever it applies -- unless the current weights already drove an activation out of the fp16
+        range of the FP16x3 split (see _settle_overflow): then the exact-fp32 engine is used until the weights change."""
         e = getattr(self, "engine", "auto")
         if e in ("simt", 0):
             return _lib.ENGINE_SIMT
         can_tc = self.depth <= 13
         if e in ("tc", "tc_layerwise", 1) and not can_tc:
             raise RuntimeError("engine='tc' supports depth <= 13")
+        if can_tc and self._tc_demoted():
+            if e in ("tc", "tc_layerwise", 1):
+                raise RuntimeError("tcgen05 engine: an activation exceeded the fp16 range of the FP16x3 split with these "
+                                   "weights (the energies of that forward were NaN); use engine='auto' or 'simt'")
+            return _lib.ENGINE_SIMT
         return _lib.ENGINE_TC if can_tc else _lib.ENGINE_SIMT
+
+    # ------------------------------------------------------------------ fp16-range guard of the tcgen05 engine ----
+    # The FP16x3 operand split represents |v| < 65504.  The kernels flag anything larger in tc_status[0] and write NaN
+    # energies (nothing wrong can pass silently).  The host reads the flag back WITHOUT stalling the stream:
+    #   * CPU callers and eager training synchronise anyway (result copy / loss.item()), so the flag is read right
+    #     there and the step is re-run on the exact-fp32 engine: correct energies, loss and gradients;
+    #   * a device-tensor inference forward only queues a 4-byte copy; when a later call finds it set, this weight
+    #     version is demoted to the exact-fp32 engine (engine='auto') -- the flagged forward itself returned NaN;
+    #   * under CUDA-graph capture nothing can be read back: NaN poisoning is the signal.
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self._param_list())
+
+    def _tc_demoted(self) -> bool:
+        self._poll_overflow()
+        key = self.__dict__.get("_tc_demoted_key")
+        if key is None:
+            return False
+        if key != self._weights_key():
+            self.__dict__["_tc_demoted_key"] = None      # weights changed: give the tensor-core engine another go
+            return False
+        return True
+
+    def _queue_overflow_check(self, tc_status: torch.Tensor):
+        """Queue a 4-byte copy of the flag word into a pinned ring slot; returns (event, ring, slot)."""
+        ring = self.__dict__.get("_ovf_ring")
+        if ring is None:
+            ring = torch.zeros(64, dtype=torch.int32).pin_memory()
+            self.__dict__["_ovf_ring"] = ring
+            self.__dict__["_ovf_next"] = 0
+        pend = self.__dict__.setdefault("_ovf_pending", [])
+        if len(pend) >= 60:                      # never hand out a slot an unfinished copy still targets
+            self._poll_overflow(wait=True)
+        slot = self.__dict__["_ovf_next"]
+        self.__dict__["_ovf_next"] = (slot + 1) % 64
+        ring[slot:slot + 1].copy_(tc_status[:1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev, ring, slot
+
+    def _poll_overflow(self, wait: bool = False) -> None:
+        pend = self.__dict__.get("_ovf_pending")
+        if not pend:
+            return
+        keep = []
+        for ev, ring, slot in pend:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                keep.append((ev, ring, slot))
+            elif int(ring[slot]) & 3:
+                self._demote(self._weights_key(), int(ring[slot]))
+        self.__dict__["_ovf_pending"] = keep
+
+    def _demote(self, key, bits: int) -> None:
+        import warnings
+        self.__dict__["_tc_demoted_key"] = key
+        warnings.warn("cgr_mpnn_3d_b200: %s left the fp16 range of the tcgen05 FP16x3 split (|v| >= 65504); that forward "
+                      "returned NaN energies unless it was re-run, and this weight version now runs on the exact-fp32 "
+                      "engine" % ("an input feature" if bits & 2 else "an activation"), RuntimeWarning, stacklevel=3)
 
     def _fused_ok(self, plan) -> bool:
         """The fused tile kernels need a hidden size divisible by 4, <= 32 bond features and reactions that fit a
@@ -177,10 +242,15 @@ class GNN(nn.Module):
         caller_device = x.device
         if caller_device.type == "cpu" and not (torch.is_grad_enabled() and any(
                 p.requires_grad for p in self.parameters())) and not (self.training and any(
-                    float(p) > 0 for p in self.dropout_ps[: self.depth])) and getattr(self, "engine", "auto") != "simt":
+                    float(p) > 0 for p in self.dropout_ps[: self.depth])) and getattr(self, "engine", "auto") != "simt" \
+                and not self._tc_demoted():
             out = self._infer_host(data)            # one C call on the host buffers (end-to-end entry)
             if out is not None:
                 return out
+        return self._forward_device(data, caller_device)
+
+    def _forward_device(self, data, caller_device, force_simt: bool = False) -> torch.Tensor:
+        x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
         params = self._param_list()
         pdev = params[0].device
         dev = pdev if pdev.type == "cuda" else (caller_device if caller_device.type == "cuda"
@@ -200,7 +270,7 @@ class GNN(nn.Module):
         # dropout only in train mode (GNN.py:100-102); activations are saved whenever a backward may follow
         dps = [float(p) if self.training else 0.0 for p in self.dropout_ps[: self.depth]]
         train_flag = needs_grad or any(p > 0 for p in dps)
-        engine = self._engine_id(plan, train_flag)
+        engine = _lib.ENGINE_SIMT if force_simt else self._engine_id(plan, train_flag)
         empty_i = torch.empty(0, dtype=torch.int32, device=dev)
         fused_train = False
         if engine == _lib.ENGINE_TC:
@@ -246,6 +316,19 @@ class GNN(nn.Module):
         self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and n_tiles > 0) else None
         self.__dict__["_last_engine"] = engine
         self.__dict__["_last_fused_train"] = fused_train
+        if engine == _lib.ENGINE_TC and not torch.cuda.is_current_stream_capturing():
+            with torch.cuda.device(dev):
+                pending = self._queue_overflow_check(tc_status)
+            if needs_grad or caller_device != dev:
+                # a synchronisation follows anyway (loss.item() at trainer.py:145-147 / the copy to the caller's device):
+                # read the flag here and, if it is set, repeat this step on the exact-fp32 engine
+                pending[0].synchronize()
+                bits = int(pending[1][pending[2]])
+                if bits & 3:
+                    self._demote(self._weights_key(), bits)
+                    return self._forward_device(data, caller_device, force_simt=True)
+            else:
+                self.__dict__.setdefault("_ovf_pending", []).append(pending)
         if caller_device != dev:
             out = out.to(caller_device)
         return out
@@ -339,7 +422,10 @@ class GNN(nn.Module):
                                         _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(), dws.data_ptr(),
                                         dws.numel(), hws.data_ptr(), hws.numel(),
                                         torch.cuda.current_stream().cuda_stream)
-        if rc == -3:            # not tileable / fp16 range: generic path (layer-wise kernels)
+        if rc == -3:            # not tileable: generic path (layer-wise kernels); fp16 range: exact-fp32 engine
+            msg = lib.cgr_last_error_string() or b""
+            if b"fp16 range" in msg:
+                self._demote(self._weights_key(), 1)
             return None
         _lib.check(rc, "cgr_gnn_infer_host")
         return hout[:b].clone()
@@ -395,12 +481,16 @@ class GNN(nn.Module):
             slot, ctx, n, e, b, counts, _keep = res
             dws, hws, hout, st = slot
             st.synchronize()
-            _lib.check(lib.cgr_infer_host_check(C.byref(ctx.params), n, e, b, hws.data_ptr()), "cgr_infer_host_check")
+            rc = lib.cgr_infer_host_check(C.byref(ctx.params), n, e, b, hws.data_ptr())
+            if rc == -3:                            # an operand left the fp16 range: exact-fp32 engine for this group
+                self._demote(self._weights_key(), 1)
+                return [self.forward(d) for d in group]
+            _lib.check(rc, "cgr_infer_host_check")
             return list(hout[:b].clone().split(counts))
 
         try:
             with torch.no_grad():
-                if self._host_supported():
+                if self._host_supported() and not self._tc_demoted():
                     first = True
                     i = 0
                     group, group_rxn = [], 0
@@ -441,12 +531,15 @@ class GNN(nn.Module):
             pool.shutdown(wait=True)
 
     def check_numerics(self) -> None:
-        """Synchronising check of the last tcgen05 forward: raises if an activation left the fp16 range
-        of the FP16x3 split (then use ``engine='simt'``)."""
+        """Synchronising check of the tcgen05 forwards issued so far: raises if an operand left the fp16 range of the
+        FP16x3 split (those forwards returned NaN energies; ``engine='auto'`` then continues on the exact-fp32 engine).
+        The flag word is cleared by the next forward of the same batch."""
+        self._poll_overflow(wait=True)
         plan = self.__dict__.get("_last_plan")
-        if plan is not None and plan.tc_status is not None and int(plan.tc_status[0].item()) != 0:
+        bad = plan is not None and plan.tc_status is not None and (int(plan.tc_status[0].item()) & 3) != 0
+        if bad or self.__dict__.get("_tc_demoted_key") == self._weights_key():
             raise RuntimeError("tcgen05 engine: an activation exceeded the fp16 range of the FP16x3 split; "
-                               "set model.engine = 'simt'")
+                               "set model.engine = 'simt' (engine='auto' has switched already)")
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -457,6 +550,10 @@ class GNN(nn.Module):
         state.pop("_last_plan", None)
         state.pop("_plist", None)
         state.pop("_last_fused_train", None)
+        state.pop("_ovf_pending", None)
+        state.pop("_ovf_ring", None)
+        state.pop("_ovf_next", None)
+        state.pop("_tc_demoted_key", None)
         return state
 
 

@@ -59,8 +59,8 @@ class _Ctx:
 
 _CTX_CACHE: dict = {}
 
-# Optional provider of the flat gradient buffer the backward writes into: callable (n_floats, device) -> 1-D fp32 tensor
-# or None (optim.PeerFusedAdam installs one that hands out its CUDA-IPC-shared arenas).
+# Optional provider of the flat gradient buffer the backward writes into: callable (n_floats, device, params) -> 1-D fp32
+# tensor or None (optim.PeerFusedAdam installs one that hands out its CUDA-IPC-shared arenas to ITS parameters' backward).
 _GRAD_ARENA = None
 
 
@@ -95,7 +95,8 @@ def _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info=No
         x=x.data_ptr(), edge_attr=edge_attr.data_ptr(), src=src.data_ptr(), dst=dst.data_ptr(),
         in_ptr=in_ptr.data_ptr(), in_idx=in_idx.data_ptr(), atom_ptr=atom_ptr.data_ptr(),
         tile_info=tile_info.data_ptr() if has_tiles else None, n_tiles=int(n_tiles) if has_tiles else 0,
-        tc_status=tc_status.data_ptr() if (has_tiles and tc_status is not None and tc_status.numel() > 0) else None,
+        # the fp16-range flag word is observable on both tcgen05 paths (fused tile kernels and layer-wise GEMMs)
+        tc_status=tc_status.data_ptr() if (tc_status is not None and tc_status.numel() > 0) else None,
         x_hi=x_hi.data_ptr() if has_split else None, x_lo=x_lo.data_ptr() if has_split else None,
     )
 
@@ -245,7 +246,7 @@ def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tenso
     sizes = [(p.numel() + 3) // 4 * 4 for p in params]
     flat = None
     if _GRAD_ARENA is not None:              # a data-parallel optimizer wants the gradients in memory its peers can map
-        flat = _GRAD_ARENA(sum(sizes), x.device)
+        flat = _GRAD_ARENA(sum(sizes), x.device, params)
     if flat is None:
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
     grads = [(c if c.numel() == p.numel() else c[:p.numel()]).view(p.shape) for c, p in zip(flat.split(sizes), params)]

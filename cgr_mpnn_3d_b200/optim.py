@@ -193,6 +193,8 @@ class PeerFusedAdam(torch.optim.Optimizer):
         self._cur = 0                             # arena the next backward writes into
         self._sync_step = 0
         self._adam_step = 0
+        self._handed_out = 0                      # sync step whose arena a backward already received
+        self._param_ptrs = [p.data_ptr() for p in ps]
         for p in ps:
             st = self.state[p]
             st["step"] = torch.tensor(0.0, dtype=torch.float32)
@@ -204,15 +206,42 @@ class PeerFusedAdam(torch.optim.Optimizer):
         from . import ops
         ops.set_grad_arena(self._provide)
 
-    def _provide(self, n_floats, device):
-        if n_floats != self._total or device != self.device:
+    def _provide(self, n_floats, device, params=None):
+        """Arena of the current step for ONE backward: a second backward before ``step()`` (gradient accumulation, two
+        models of the same shape) gets a private buffer instead of overwriting the first one's gradients in place
+        (``step()`` then reports the misplaced gradient)."""
+        if n_floats != self._total or device != self.device or self._handed_out == self._sync_step + 1:
             return None
+        if params is not None and [q.data_ptr() for q in params] != self._param_ptrs:
+            return None                            # another model of the same shape: not this optimizer's gradients
+        if not torch.cuda.is_current_stream_capturing():
+            self._handed_out = self._sync_step + 1
         return self._shared[self._cur * self._total:(self._cur + 1) * self._total]
 
     def state_dict(self):
         for p in self.param_groups[0]["params"]:
             self.state[p]["step"].fill_(float(self._adam_step))
         return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Resume: torch installs NEW exp_avg / exp_avg_sq / max_exp_avg_sq tensors, so the cached pointer table is
+        rebuilt, and the bias-correction step continues from the saved ``step`` (identical on every replica: they
+        all load the same state).  The flag protocol's own counter keeps running -- it only has to agree between
+        replicas of this process group, which never stopped."""
+        super().load_state_dict(state_dict)
+        self._table = None
+        steps = {int(float(st["step"])) for st in self.state.values() if "step" in st}
+        if len(steps) > 1:
+            raise RuntimeError("PeerFusedAdam: parameters carry different step counts; one step per parameter set only")
+        self._adam_step = steps.pop() if steps else 0
+        for p in self.param_groups[0]["params"]:
+            st = self.state[p]
+            st["step"] = torch.tensor(float(self._adam_step), dtype=torch.float32)
+            for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                if k in st and (st[k].device != p.device or not st[k].is_contiguous() or st[k].dtype != torch.float32):
+                    st[k] = st[k].to(device=p.device, dtype=torch.float32).contiguous()
+            if self.param_groups[0]["amsgrad"] and "max_exp_avg_sq" not in st:
+                st["max_exp_avg_sq"] = torch.zeros_like(p)
 
     @torch.no_grad()
     def step(self, closure=None, arena=None):

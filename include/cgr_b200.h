@@ -91,7 +91,11 @@ typedef struct cgr_graph {
   const int32_t* tile_info;  /* [n_tiles, 8] tile plan of the tcgen05 engine (cgr_tc_plan_build) or NULL */
   int64_t n_tiles;
   int32_t* tc_status;        /* tcgen05 engine: [1 + n_tiles] ints, zero-initialised once by the caller:
-                                [0] sticky fp16-range overflow flag, [1..] self-resetting readout counters */
+                                [0] fp16-range flags of the FP16x3 split -- bit 0: an activation of the LAST forward
+                                left the range (cleared when a forward starts), bit 1: a feature of data.x did (set by
+                                cgr_tc_split_features, kept for the batch's life); whenever a bit is set the forward
+                                writes NaN energies; [1..] self-resetting readout counters.  The layer-wise path (no
+                                tile plan) only uses [0] and accepts a 1-int array. */
   const void* x_hi;          /* optional: data.x as FP16 (hi, lo) rows prepared by cgr_tc_split_features */
   const void* x_lo;          /*           (row stride cgr_tc_features_ld(fa) halfs); NULL: converted per call */
 } cgr_graph_t;

@@ -1,0 +1,63 @@
+"""Multi-GPU checks of the data-parallel training path, as tests (they skip on a one-GPU box).
+
+One process per GPU over NCCL / NVLink peer memory, launched with ``torch.distributed.run`` exactly like the bench:
+
+* ``tools/check_dp.py``: gradients SUM-reduced over replicas (64 reactions each) equal the gradients of ONE process on the
+  concatenated batch -- the reference's loss is ``MSELoss(reduction="sum")`` (train.py:120), so replicas sum, not average;
+* ``tools/check_peer_adam.py``: ``PeerFusedAdam`` (gradient sum over NVLink peer memory + Adam in one kernel) against NCCL
+  all-reduce + ``FusedAdam`` over 6 steps, replicas bit-identical to each other, and a state_dict resume.
+
+Their 2/4/8-GPU outputs of this round are kept under ``profiles/``.
+"""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(tool, world, tag):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", tool)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith(tag + " ")]
+    assert lines, r.stdout[-2000:]
+    return json.loads(lines[-1][len(tag) + 1:])
+
+
+def _worlds():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return [w for w in (2, 4, 8) if w <= n]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_dp_gradient_sum_matches_single_process(world):
+    if world not in _worlds():
+        pytest.skip(f"needs {world} GPUs")
+    res = _run("check_dp.py", world, "CHECK_DP")
+    assert res["fused_train"] and res["in_place_allreduce"]
+    assert res["worst_q995_grad_error"] < 1e-4, res
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_fused_adam_matches_nccl_allreduce_plus_adam(world):
+    if world not in _worlds():
+        pytest.skip(f"needs {world} GPUs")
+    res = _run("check_peer_adam.py", world, "CHECK_PEER_ADAM")
+    assert res["replicas_identical"] and res["resume_diff"] == 0.0, res
+    assert res["ok"], res

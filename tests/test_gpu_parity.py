@@ -920,3 +920,166 @@ def test_peer_fused_adam_single_replica_equals_fused_adam(tmp_path):
         ops.set_grad_arena(None)
         if created:
             dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# cfg-5 (BASELINE.json configs[4]): drug-like reactions (80-120 atoms, ~210 directed bonds -- more than a 128-bond tile),
+# depth 6, hidden 1024, Fa = 846: the layer-wise tcgen05 path (tensor-core GEMMs, SIMT gathers) and the exact engine
+@pytest.mark.parametrize("engine", ["tc", "auto", "simt"])
+def test_cfg5_drug_like_d6_h1024(engine):
+    meta = dict(fa=846, fb=14, depth=6, hidden=1024, skip=True, wseed=12, act="relu")
+    data = make_batch(16, seed=55, kind="drug", fa=846)
+    assert data.num_edges / 16 > 128                                     # no reaction fits a 128-bond tile
+    oracle = build_oracle(meta).train()
+    ref = oracle(data)
+    mse_sum_loss(ref, data.y).backward()
+    o64 = build_oracle(meta, dtype=torch.float64).train()
+    d64 = Batch(data.x.double(), data.edge_index, data.edge_attr.double(), data.batch, data.ptr, data.y.double())
+    mse_sum_loss(o64(d64), d64.y).backward()
+    og, og64 = dict(oracle.named_parameters()), dict(o64.named_parameters())
+    model = build_model(meta, engine=engine).train()
+    d = data.to("cuda")
+    out = model(d)
+    assert model.__dict__["_last_fused_train"] is False and model.__dict__.get("_last_plan") is None
+    assert model.__dict__["_last_engine"] == (0 if engine == "simt" else 1)
+    assert scale_normalised_error(out, ref.detach()) < EA_TOL
+    mse_sum_loss(out, d.y).backward()
+    for k, p in model.named_parameters():
+        # ReLU network: same bar as the other BASELINE-sized cases (a pre-activation within rounding of 0 may flip)
+        r64 = og64[k].grad
+        err = ((p.grad.detach().double().cpu() - r64).abs() / r64.abs().max().clamp_min(1e-30)).flatten()
+        if err.numel() >= 1000:
+            assert float(torch.quantile(err[: 2 ** 24], 0.995)) < GRAD_TOL, k
+        assert float(err.max()) < max(3e-3, 1.5 * tensor_error(og[k].grad, r64)), k
+    model.eval()
+    with torch.no_grad():
+        o1, o2 = model(d), model(d)
+        assert torch.equal(o1, o2) and scale_normalised_error(o1, ref.detach()) < EA_TOL
+        if engine != "simt":
+            assert scale_normalised_error(model(data), ref.detach()) < EA_TOL     # CPU batch in, same path underneath
+    model.check_numerics()
+
+
+# SiLU / GELU have continuous derivatives (no ReLU flips), so cfg-2-sized gradients are held to the strict 1e-4 bar
+# against fp64 through the layer-wise tensor-core path (engine tc / auto) and the exact engine
+@pytest.mark.parametrize("engine", ["tc", "auto", "simt"])
+@pytest.mark.parametrize("act", ["silu", "gelu"])
+def test_cfg2_sized_smooth_activation_strict_gradients(act, engine):
+    meta = dict(fa=846, fb=14, depth=4, hidden=400, skip=True, wseed=0, act=act)
+    data = make_batch(64, seed=3, kind="t1x", fa=846)
+    o64 = build_oracle(meta, dtype=torch.float64).train()
+    d64 = Batch(data.x.double(), data.edge_index, data.edge_attr.double(), data.batch, data.ptr, data.y.double())
+    ref = o64(d64)
+    mse_sum_loss(ref, d64.y).backward()
+    model = build_model(meta, engine=engine).train()
+    d = data.to("cuda")
+    out = model(d)
+    assert model.__dict__["_last_fused_train"] is False
+    assert scale_normalised_error(out, ref.detach()) < 2e-5
+    mse_sum_loss(out, d.y).backward()
+    for (k, p), q in zip(model.named_parameters(), o64.parameters()):
+        assert tensor_error(p.grad, q.grad) < GRAD_TOL, k
+    model.eval()
+    with torch.no_grad():
+        assert scale_normalised_error(model(d), ref.detach()) < 2e-5           # fused tile kernels with SiLU / GELU epilogues
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16 range of the FP16x3 split: activations beyond 65504 cannot pass silently on any path
+def _blown_up_model(engine):
+    meta = dict(fa=78, fb=14, depth=2, hidden=64, skip=True, wseed=3, act="relu")
+    model = build_model(meta, engine=engine)
+    oracle = build_oracle(meta)
+    with torch.no_grad():
+        model.edge_init.weight.mul_(1e5)                  # h_0 ~ 3e5: outside the fp16 range
+        model.ffn.weight.mul_(1e-6)
+        oracle.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    return meta, model, oracle
+
+
+def test_fp16_range_overflow_is_never_silent():
+    import warnings
+    data = make_batch(8, seed=4, kind="t1x", fa=78)
+    d = data.to("cuda")
+    meta, model, oracle = _blown_up_model("auto")
+    with torch.no_grad():
+        ref = oracle.eval()(data)
+        assert float(oracle.edge_init(torch.cat([data.x[data.edge_index[0]], data.edge_attr], 1)).abs().max()) > 7e4
+    model.eval()
+    with torch.no_grad(), warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        first = model(d)                                  # device tensors: no host sync, the energies are poisoned
+        torch.cuda.synchronize()
+        assert torch.isnan(first).all()
+        second = model(d)                                 # the flag was read back meanwhile: exact-fp32 engine from here on
+        assert model.__dict__["_last_engine"] == 0
+        assert scale_normalised_error(second, ref) < EA_TOL
+        assert any("fp16 range" in str(x.message) for x in w)
+        with pytest.raises(RuntimeError, match="fp16 range"):
+            model.check_numerics()
+        host = model(data)                                # CPU batch: result copy synchronises, never NaN
+        assert scale_normalised_error(host, ref) < EA_TOL
+    # a fresh model fed CPU tensors first: the host-buffer entry reports the overflow and the exact engine answers
+    meta, model, oracle = _blown_up_model("auto")
+    model.eval()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert scale_normalised_error(model(data), ref) < EA_TOL
+        outs = list(model.predict_stream([data, data], coalesce=2))
+        assert all(scale_normalised_error(o, ref) < EA_TOL for o in outs)
+    # training (eager): loss and gradients of the flagged step come from the exact engine
+    meta, model, oracle = _blown_up_model("auto")
+    model.train(); oracle.train()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = model(d)
+    assert model.__dict__["_last_engine"] == 0 and torch.isfinite(out).all()
+    lo = mse_sum_loss(oracle(data), data.y)
+    lo.backward()
+    lm = mse_sum_loss(out, d.y)
+    lm.backward()
+    assert abs(float(lm) - float(lo)) <= 1e-4 * abs(float(lo))
+    for (k, p), q in zip(model.named_parameters(), oracle.parameters()):
+        assert tensor_error(p.grad, q.grad) < GRAD_TOL, k
+    # weights back in range: the tensor-core engine is used again and the flag word was cleared by the new forward
+    with torch.no_grad():
+        model.edge_init.weight.mul_(1.0 / 1e5)
+    model.eval()
+    with torch.no_grad():
+        ok = model(d)
+    assert model.__dict__["_last_engine"] == 1 and torch.isfinite(ok).all()
+    model.check_numerics()
+    # layer-wise tensor-core path (untileable graphs) reports through the same flag word
+    meta, model, oracle = _blown_up_model("tc_layerwise")
+    drug = make_batch(2, seed=6, kind="drug", fa=78)
+    model.eval()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bad = model(drug.to("cuda"))
+        torch.cuda.synchronize()
+        assert torch.isnan(bad).all()
+        with pytest.raises(RuntimeError, match="fp16 range"):
+            model(drug.to("cuda"))                        # explicit tensor-core engine: refuses instead of switching
+    # features beyond the range are flagged at batch preparation (bit 1 of the flag word) with the same consequences
+    meta = dict(fa=78, fb=14, depth=2, hidden=64, skip=True, wseed=3, act="relu")
+    model = build_model(meta, engine="auto").eval()
+    big = make_batch(4, seed=8, kind="t1x", fa=78)
+    big.x[0, 0] = 1e5
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert scale_normalised_error(model(big), build_oracle(meta).eval()(big)) < EA_TOL
+
+
+def test_model_on_non_current_device_builds_its_plan_there():
+    """A batch on cuda:1 in a process whose current device is cuda:0 (collate.build_plan launches on the batch's device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    meta = dict(fa=78, fb=14, depth=2, hidden=64, skip=True, wseed=3, act="relu")
+    data = make_batch(6, seed=9, kind="t1x", fa=78)
+    ref = build_oracle(meta).eval()
+    assert torch.cuda.current_device() == 0
+    model = build_model(meta, device="cuda:1", engine="auto").eval()
+    with torch.no_grad():
+        out = model(data.to("cuda:1"))
+        assert out.device == torch.device("cuda:1")
+        assert scale_normalised_error(out, ref(data)) < EA_TOL

@@ -35,7 +35,11 @@ if rank == 0:
         err = ((a.grad.double() - b.grad.double()).abs() / b.grad.double().abs().max().clamp_min(1e-30)).flatten()
         q = float(torch.quantile(err[: 2 ** 24].float(), 0.995)) if err.numel() >= 1000 else float(err.max())
         worst = max(worst, q)
+    import json
+    ok = bool(fused and in_place and worst < 1e-4)
     print(f"world={world} fused_train={fused} in_place_allreduce={in_place} worst 99.5% grad error vs single process: {worst:.2e}",
           flush=True)
+    print("CHECK_DP " + json.dumps({"world": world, "fused_train": bool(fused), "in_place_allreduce": bool(in_place),
+                                    "worst_q995_grad_error": worst, "ok": ok}), flush=True)
 dist.barrier()
 dist.destroy_process_group()
