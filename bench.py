@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""Headline benchmark: reactions/s of the CGR-MPNN-3D d4 h400 forward (BASELINE.json configs[1]).
+"""Headline benchmark: reactions/s of the CGR-MPNN-3D forward (BASELINE.json configs) on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # this framework on N B200s
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W                     # cfg-2 (the headline): d4 h400 batch 64
+    python bench.py --config cfg4 ...                                  # 1 M reactions, batch 8192, sharded over the ranks
+    python bench.py --config cfg5 ...                                  # drug-like, d6 h1024, batch 1024
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference's CPU path (oracle port)
 
-A step is one forward pass of the hot path over one batch of 64 synthetic T1x-shaped reactions
-(Fa = 78 + 768 synthetic MACE columns, Fb = 14, depth 4, hidden 400, learnable skip, random-init
-weights in the reference .pth layout).  One JSON line is printed by rank 0.
+A step is one forward pass of the hot path over one batch of synthetic reactions (Fa = 78 + 768 synthetic MACE
+columns, Fb = 14, random-init weights in the reference .pth layout).  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -14,6 +15,7 @@ import argparse
 import ctypes
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -26,39 +28,56 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-from cgr_mpnn_3d_b200.data import Batch, make_batch  # noqa: E402
+from cgr_mpnn_3d_b200.data import Batch, make_batch, make_reactions  # noqa: E402
 
-FA, FB, DEPTH, HID, BATCH = 846, 14, 4, 400, 64
 L2_BYTES = 126e6
+
+# BASELINE.json configs: [1] cfg-2 (headline), [3] cfg-4, [4] cfg-5
+CONFIGS = {
+    "cfg2": dict(fa=846, fb=14, depth=4, hidden=400, batch=64, kind="t1x", n_params=1485205,
+                 name="cfg-2: CGR-MPNN-3D d4 h400 learnable-skip forward (inference), batch 64/GPU"),
+    "cfg4": dict(fa=846, fb=14, depth=4, hidden=400, batch=8192, kind="t1x", n_params=1485205,
+                 name="cfg-4: high-throughput screening, CGR-MPNN-3D d4 h400 learnable-skip forward, batch 8192, "
+                      "reactions sharded over the GPUs with no communication"),
+    "cfg5": dict(fa=846, fb=14, depth=6, hidden=1024, batch=1024, kind="drug", n_params=9096199,
+                 name="cfg-5: stress shape, drug-like reactions (80-120 atoms), d6 h1024 learnable-skip forward, "
+                      "batch 1024/GPU"),
+}
+
+
+def workload_string(cfg) -> str:
+    return (f"{cfg['name']}, Fa={cfg['fa']} Fb={cfg['fb']}, "
+            f"{'T1x-shaped' if cfg['kind'] == 't1x' else 'drug-like'} synthetic reactions, random-init weights in the "
+            f"reference .pth layout")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--engine", default=os.environ.get("CGR_ENGINE", "auto"))
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--pool", type=int, default=48, help="distinct resident batches rotated through (> L2)")
-    ap.add_argument("--no-group", action="store_true",
-                    help="replay one single-batch graph per step instead of one graph per group of --streams batches")
-    ap.add_argument("--no-graph", action="store_true", help="time eager custom-op calls instead of CUDA-graph replay")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fast"],
+                    help="fp32: FP16x3 split (1e-4 parity mode, the headline); fast: single-pass fp16 operands, "
+                         "reported with its measured error")
+    ap.add_argument("--batch", type=int, default=None, help="override the config's batch size")
+    ap.add_argument("--pool", type=int, default=None, help="distinct resident batches rotated through (> L2)")
+    ap.add_argument("--repeats", type=int, default=50, help="timed regions of --steps steps; the median is reported")
+    ap.add_argument("--no-graph", action="store_true", help="time eager calls instead of CUDA-graph replay")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--leg-seconds", type=float, default=0.6, help="work per e2e / store measurement")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over")
     ap.add_argument("--coalesce", type=int, default=8,
                     help="host batches predict_stream submits together in the e2e leg (1 = one submission per batch)")
-    ap.add_argument("--store", action="store_true", default=True,
-                    help="also time inference over a device-resident reaction store (no per-step feature copies) [default]")
-    ap.add_argument("--no-store", dest="store", action="store_false")
-    ap.add_argument("--train", action="store_true", default=True,
-                    help="also time the training step (fwd+loss+bwd[+allreduce]) [default]")
-    ap.add_argument("--no-train", dest="train", action="store_false")
-    ap.add_argument("--peer-adam", action="store_true",
-                    help="N > 1: also time the complete data-parallel step with NCCL all-reduce + FusedAdam and with "
-                         "PeerFusedAdam (gradient sum over NVLink peer memory + Adam in one kernel)")
+    ap.add_argument("--no-store", dest="store", action="store_false", default=True)
+    ap.add_argument("--no-train", dest="train", action="store_false", default=True)
+    ap.add_argument("--no-collate", dest="collate", action="store_false", default=True)
+    ap.add_argument("--job-reactions", type=int, default=1_000_000, help="cfg4: reactions of the sharded screening job")
+    ap.add_argument("--job-unique", type=int, default=65536, help="cfg4: distinct reactions held per GPU (drawn with repeats)")
     return ap.parse_args()
 
 
@@ -67,19 +86,36 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as fh:
             d = json.load(fh)
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
-    return 6650.0, 1590.0, "fallback"
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), float(d.get("bf16_tflops_sustained", 1400.0)),
+                "measured")
+    return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def algorithmic_bytes_fwd(n, e, b, fa=FA, fb=FB, h=HID, d=DEPTH, n_params=1485205, s=4):
+def algorithmic_bytes_fwd(n, e, b, cfg, s=4):
     """SURVEY.md §8(d) forward byte formula (layer-wise formulation, fp32, int64 indices)."""
+    fa, fb, h, d = cfg["fa"], cfg["fb"], cfg["hidden"], cfg["depth"]
     return (s * (n * fa + e * fb) + (16 * e + 8 * n) + s * e * h + d * s * (3 * e * h + 2 * n * h)
-            + s * (e * h + n * fa + 2 * b * h) + 4 * b + 4 * n_params)
+            + s * (e * h + n * fa + 2 * b * h) + 4 * b + 4 * cfg["n_params"])
 
 
-def bond_update_bytes(n, e, h=HID, s=4):
-    """per-depth term of the same formula: read h_l, read h0, write h_{l+1}, write+read atom sums."""
-    return s * (3 * e * h + 2 * n * h)
+def algorithmic_flops_fwd(n, e, b, cfg):
+    fa, fb, h, d = cfg["fa"], cfg["fb"], cfg["hidden"], cfg["depth"]
+    return 2 * e * (fa + fb) * h + d * 2 * e * h * h + 2 * n * (fa + h) * h + 2 * b * h
+
+
+def stage_bytes(stage, n, e, b, cfg, s=4):
+    """Algorithmic bytes ONE launch of a stage accounts for: the matching terms of the §8(d) formula."""
+    fa, fb, h, d = cfg["fa"], cfg["fb"], cfg["hidden"], cfg["depth"]
+    per_depth = s * (3 * e * h + 2 * n * h)              # read h_l, read h0, write h_{l+1}, write + read atom sums
+    readout = s * (e * h + 2 * b * h) + 4 * b             # read h_d, pooled write + read, energies
+    return {
+        "bond_layer": per_depth,
+        "tc_readout": readout,
+        "tc_fwd_fused": d * per_depth + readout,         # every bond layer + the readout in one launch
+        "tc_atom_proj": s * (2 * n * fa) + 4 * 2 * h * fa,   # x for the edge initialisation and for the readout, W_x / W_ox
+        "tc_edge_init": s * (e * fb + e * h) + 16 * e + 8 * n,   # bond features, indices, write h0
+        "gemm_bond_update": s * (3 * e * h) + 4 * h * h,
+    }.get(stage)
 
 
 class ClockSampler:
@@ -147,9 +183,9 @@ class ClockSampler:
                         reasons.add(name)
             return sm, mx, reasons
         timed = [x for x in self.rows if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30)]
-        window = "timed region"
-        if len(timed) < 3:      # timed region shorter than the sampler period: use every sample of the GPU-busy legs
-            timed, window = self.rows, "all GPU legs of this run (timed region shorter than the sampling period)"
+        window = "timed regions of `value`"
+        if len(timed) < 3:      # timed regions shorter than the sampler period: use every sample of the GPU-busy legs
+            timed, window = self.rows, "all GPU legs of this run (timed regions shorter than the sampling period)"
         sm, mx, reasons = parse(timed)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
@@ -158,45 +194,88 @@ class ClockSampler:
                 "window": window}
 
 
-def build_model(engine: str, device):
+def build_model(cfg, engine: str, device, precision: str = "fp32"):
     from cgr_mpnn_3D.models.GNN import GNN
     torch.manual_seed(0)
-    m = GNN(FA, FB, depth=DEPTH, hidden_sizes=[HID] * DEPTH, dropout_ps=[0.0] * DEPTH, activation_fn=F.relu,
-            use_learnable_skip=True)
+    d = cfg["depth"]
+    m = GNN(cfg["fa"], cfg["fb"], depth=d, hidden_sizes=[cfg["hidden"]] * d, dropout_ps=[0.0] * d,
+            activation_fn=F.relu, use_learnable_skip=True)
     m.engine = engine
+    m.precision = precision
     return m.to(device)
 
 
-def build_oracle():
+def build_oracle(cfg, dtype=torch.float32):
     from oracle.gnn_oracle import OracleGNN
     torch.manual_seed(0)
-    return OracleGNN(FA, FB, depth=DEPTH, hidden_sizes=[HID] * DEPTH, dropout_ps=[0.0] * DEPTH,
-                     activation_fn=F.relu, use_learnable_skip=True).eval()
+    d = cfg["depth"]
+    return OracleGNN(cfg["fa"], cfg["fb"], depth=d, hidden_sizes=[cfg["hidden"]] * d, dropout_ps=[0.0] * d,
+                     activation_fn=F.relu, use_learnable_skip=True).to(dtype).eval()
 
 
-def cpu_reference_leg(batch_size: int, steps: int, warmup: int, budget_s: float):
-    """The reference's CPU implementation of the path (oracle port of GNN.py) on the host cores."""
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    model = build_oracle()
-    batches = [make_batch(batch_size, seed=9000 + i, kind="t1x", fa=FA) for i in range(4)]
+def cpu_reference_leg(cfg, batch_size: int, steps: int, warmup: int, budget_s: float, threads: int):
+    """The reference's CPU implementation of the path (oracle port of GNN.py, bit-identical to the reference's fp32
+    output) on the host cores: `steps` forward passes, bounded by `budget_s` seconds.  cfg-5 steps are sampled at 32
+    reactions per pass (one full 1024-reaction pass is minutes of CPU time); throughput is per reaction either way."""
+    torch.set_num_threads(threads)
+    model = build_oracle(cfg)
+    sample_b = batch_size if cfg["kind"] == "t1x" else min(batch_size, 32)
+    n_b = 4 if sample_b <= 1024 else 1
+    batches = [make_batch(sample_b, seed=9000 + i, kind=cfg["kind"], fa=cfg["fa"]) for i in range(n_b)]
     with torch.no_grad():
-        for i in range(max(1, min(warmup, 3))):
-            model(batches[i % 4])
+        t0 = time.perf_counter()
+        for i in range(max(0, warmup)):
+            model(batches[i % n_b])
+            if time.perf_counter() - t0 > budget_s:           # a slow config: do not spend the whole budget warming up
+                break
         t0 = time.perf_counter()
         done = 0
-        while done < steps and (time.perf_counter() - t0) < budget_s:
-            model(batches[done % 4])
+        while done < steps and (done == 0 or (time.perf_counter() - t0) < budget_s):
+            model(batches[done % n_b])
             done += 1
         dt = time.perf_counter() - t0
-    return {"value": batch_size * done / dt, "unit": "reactions/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": f"{done} forward passes of one {batch_size}-reaction batch "
-                                      f"(oracle/gnn_oracle.py, fp32, {dt:.1f} s)", "ms_per_step": 1e3 * dt / done,
-            "steps_done": done}
+    return {"value": sample_b * done / dt, "unit": "reactions/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{done} forward passes of one {sample_b}-reaction batch "
+                                      f"(oracle/gnn_oracle.py, fp32, {torch.get_num_threads()} threads, {dt:.1f} s)",
+            "ms_per_step": 1e3 * dt / done * (batch_size / sample_b), "steps_done": done}
+
+
+def pin_rank_to_cores(local_rank: int, world: int) -> str:
+    """One process per GPU on a shared host: give every rank its own slice of the cores this process may use, so the
+    submitting threads of the ranks do not migrate over each other."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(cores) < 2 * world:
+            return "unpinned"
+        per = len(cores) // world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return f"cores {mine[0]}-{mine[-1]}"
+    except Exception:
+        return "unpinned"
+
+
+def timed_loop(seconds: float, fn):
+    """Call fn() until `seconds` of wall clock have passed (at least 3 calls); returns (calls, elapsed)."""
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or time.perf_counter() - t0 < seconds:
+        fn()
+        n += 1
+    torch.cuda.synchronize()
+    return n, time.perf_counter() - t0
 
 
 def main():
     args = parse()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["batch"] = args.batch
+        cfg["name"] = cfg["name"].replace("batch 64", f"batch {args.batch}").replace("batch 8192", f"batch {args.batch}") \
+            .replace("batch 1024", f"batch {args.batch}")
+    B = cfg["batch"]
+    workload = workload_string(cfg)
+    metric = "reactions/sec (CGR-MPNN-3D d%d h%d fwd)" % (cfg["depth"], cfg["hidden"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -205,14 +284,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        leg = cpu_reference_leg(args.batch, args.steps, args.warmup, budget_s=max(30.0, args.cpu_seconds * 10))
+        cores = os.cpu_count() or 1
+        leg = cpu_reference_leg(cfg, B, args.steps, args.warmup, budget_s=150.0, threads=cores)
         line = {
-            "impl": "reference", "metric": "reactions/sec (CGR-MPNN-3D d4 h400 fwd)", "value": leg["value"],
-            "unit": "reactions/s", "n_gpus": args.gpus, "steps": leg["steps_done"], "warmup": min(args.warmup, 3),
+            "impl": "reference", "metric": metric, "value": leg["value"],
+            "unit": "reactions/s", "n_gpus": args.gpus, "steps": leg["steps_done"], "warmup": args.warmup,
             "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg-2: CGR-MPNN-3D d{DEPTH} h{HID} learnable-skip forward, batch {args.batch}, "
-                                   f"Fa={FA} Fb={FB}, T1x-shaped synthetic reactions", "device": "host CPU"},
+            "config": {"workload": workload},
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": "reactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -224,25 +303,33 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the hot path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = pin_rank_to_cores(local_rank, world)
     if world > 1:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from cgr_mpnn_3d_b200 import _lib
-    from cgr_mpnn_3d_b200.collate import plan_for
+    from cgr_mpnn_3d_b200.collate import build_plan, plan_for, split_features_for
     lib = _lib.load()
-    hbm_peak, _, peak_kind = load_peaks()
+    hbm_peak, tc_peak, tc_sustained, peak_kind = load_peaks()
 
     engine = args.engine
-    model = build_model(engine, dev).eval()
-    model.tile_policy = "throughput" if (args.streams > 1 and not args.no_graph) else "latency"
-    lat_model = build_model(engine, dev).eval()      # latency configuration for the single-stream figure
-    n_pool = max(2, args.pool)
-    host = [make_batch(args.batch, seed=1000 + 997 * rank + i, kind="t1x", fa=FA) for i in range(n_pool)]
+    small = B <= 1024 and cfg["kind"] == "t1x"
+    model = build_model(cfg, engine, dev, args.precision).eval()
+    n_streams_req = max(1, args.streams) if (small and not args.no_graph) else 1
+    model.tile_policy = "throughput" if n_streams_req > 1 else "latency"
+    lat_model = build_model(cfg, engine, dev, args.precision).eval()      # latency configuration: a lone forward
+    if args.pool:
+        n_pool = max(2, args.pool)
+    else:
+        n_pool = 48 if small else (4 if cfg["kind"] == "t1x" else 3)
+    host = [make_batch(B, seed=1000 + 997 * rank + i, kind=cfg["kind"], fa=cfg["fa"]) for i in range(n_pool)]
     for hb in host:
         hb.y = None
     pool = [hb.to(dev) for hb in host]
+    if not small:
+        host = host[:1]                       # large batches: keep host memory bounded
     for b in pool:
         plan_for(b)
     torch.cuda.synchronize()
@@ -256,115 +343,80 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- leg 1: device-resident throughput (CUDA-graph replay of the forward, one graph per batch) ----
+    steps, repeats = max(1, args.steps), max(1, args.repeats)
+    # ---- leg 1: device-resident throughput.  ONE CUDA graph holds the whole timed region: `steps` forwards, batch
+    # i % n_pool, spread over n_streams parallel branches (a screening job is a stream of independent batches), so a
+    # rank's host issues one launch per region whatever the step count ----
     outs = [None] * n_pool
     with torch.no_grad():
         for i in range(n_pool):                   # eager pass: builds every plan (tile packing syncs once per batch)
             outs[i] = model(pool[i])
         model.check_numerics()
         torch.cuda.synchronize()
-        launches_per_step = 0
-        graphs = None
-        if not args.no_graph:
-            graphs = []
-            side = torch.cuda.Stream()
-            for i in range(n_pool):
-                g = torch.cuda.CUDAGraph()
-                c0 = lib.cgr_launch_count()
-                with torch.cuda.graph(g, stream=side):
-                    outs[i] = model(pool[i])
-                launches_per_step = lib.cgr_launch_count() - c0
-                graphs.append(g)
-        else:
-            c0 = lib.cgr_launch_count()
-            model(pool[0])
-            launches_per_step = lib.cgr_launch_count() - c0
-
-        n_streams = max(1, args.streams) if graphs is not None else 1
-        while n_pool % n_streams:          # a graph must always replay on the same stream
-            n_streams -= 1
+        c0 = lib.cgr_launch_count()
+        model(pool[0])
+        launches_per_step = lib.cgr_launch_count() - c0
+        n_streams = n_streams_req
         streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
+        region = None
+        if not args.no_graph:
+            region = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(region, stream=side):
+                fork_c = torch.cuda.Event()
+                fork_c.record(side)
+                for st in streams:
+                    st.wait_event(fork_c)
+                for i in range(steps):
+                    with torch.cuda.stream(streams[i % n_streams]):
+                        outs[i % n_pool] = model(pool[i % n_pool])
+                for st in streams:
+                    ev_c = torch.cuda.Event()
+                    ev_c.record(st)
+                    side.wait_event(ev_c)
 
-        # One graph per GROUP of n_streams consecutive batches, their forwards on parallel branches (fork / join inside
-        # the capture): the same launches as replaying n_streams single-batch graphs on n_streams streams, with one host
-        # call instead of n_streams -- with one process per GPU on a shared host the submitting threads are the first
-        # thing to saturate.  Consecutive groups alternate between two streams so they overlap at their boundaries.
-        group_graphs = []
-        if graphs is not None and n_streams > 1 and not args.no_group:
-            for g0 in range(0, n_pool, n_streams):
-                gg = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gg, stream=side):
-                    fork_c = torch.cuda.Event()
-                    fork_c.record(side)
-                    for k in range(n_streams):
-                        st = streams[k]
-                        st.wait_event(fork_c)
-                        with torch.cuda.stream(st):
-                            outs[g0 + k] = model(pool[g0 + k])
-                        ev_c = torch.cuda.Event()
-                        ev_c.record(st)
-                        side.wait_event(ev_c)
-                group_graphs.append(gg)
-        gstreams = [torch.cuda.Stream(), torch.cuda.Stream()]
-
-        def run_steps(count):
-            """`count` independent forward passes: batch i % n_pool, n_streams of them in flight."""
-            if graphs is None:
-                for i in range(count):
+        def run_region():
+            if region is not None:
+                region.replay()
+            else:
+                for i in range(steps):
                     outs[i % n_pool] = model(pool[i % n_pool])
-                return
-            fork = torch.cuda.Event()
-            fork.record(main)
-            used = streams + gstreams
-            for st in used:
-                st.wait_event(fork)
-            i = 0
-            if group_graphs:
-                n_groups = count // n_streams
-                for j in range(n_groups):
-                    with torch.cuda.stream(gstreams[j & 1]):
-                        group_graphs[j % len(group_graphs)].replay()
-                i = n_groups * n_streams
-            for k in range(i, count):                 # remainder: single-batch graphs on their own streams
-                with torch.cuda.stream(streams[k % n_streams]):
-                    graphs[k % n_pool].replay()
-            for st in used:
-                ev = torch.cuda.Event()
-                ev.record(st)
-                main.wait_event(ev)
 
-        if graphs is not None:             # initialisation, like the capture itself: instantiate/upload every graph once
-            for gph in graphs + group_graphs:
-                gph.replay()
-            torch.cuda.synchronize()
         clocks = ClockSampler(local_rank).start()
-        run_steps(max(3, args.warmup))
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(max(1, -(-max(3, args.warmup) // steps))):       # >= W untimed warm-up steps
+            run_region()
+        region_ms = []
         clocks.mark_begin()
-        ev0.record(main)
-        run_steps(args.steps)
-        ev1.record(main)
-        barrier()
+        for _ in range(repeats):
+            barrier()
+            # a short device-side sleep lets the host enqueue the region before the clock starts: the events then
+            # bracket device time, not the host's launch latency
+            torch.cuda._sleep(200_000)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(main)
+            run_region()
+            ev1.record(main)
+            barrier()
+            region_ms.append(ev0.elapsed_time(ev1))
         clocks.mark_end()
-        ms_total = ev0.elapsed_time(ev1)
-        # single-stream latency of one step with the latency kernel configuration (one CTA per SM), for reference
+
+        # single-stream latency of one step with the latency kernel configuration (one forward at a time)
         n_lg = min(8, n_pool)
-        lat_graphs = []
         for i in range(n_lg):
             lat_model(pool[i])
-        if graphs is not None:
+        lat_graphs = []
+        if not args.no_graph:
             for i in range(n_lg):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
                     lat_model(pool[i])
                 lat_graphs.append(g)
-        lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_lat = min(args.steps, 400)
+        n_lat = min(max(steps, 50), 400) if small else min(steps, 20)
         for i in range(n_lg):
             lat_graphs[i].replay() if lat_graphs else lat_model(pool[i])
         torch.cuda.synchronize()
+        lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lat0.record(main)
         for i in range(n_lat):
             if lat_graphs:
@@ -374,21 +426,22 @@ def main():
         lat1.record(main)
         torch.cuda.synchronize()
         single_stream_ms = lat0.elapsed_time(lat1) / n_lat
+        # eager public-API rate on device batches: model(batch) issued call by call (host-bound for small batches)
+        n_e, dt_e = timed_loop(min(args.leg_seconds, 0.5), lambda: lat_model(pool[0]))
+        eager_device_rate = B * n_e / dt_e
 
-    # ---- leg 2: per-stage CUDA-event timing of the same steps (eager, events on the launching stream) ----
-    prof_steps = min(args.steps, 40)
+    # ---- leg 2: per-stage CUDA-event timing (events recorded by the library around every launch of a stage, on the
+    # launching stream, the stream kept busy so that an event pair brackets kernel time, not host launch latency) ----
+    prof_steps = min(steps, 40) if small else min(steps, 6)
     stage_ms, stage_cnt = {}, {}
     with torch.no_grad():
-        prof_model = lat_model if n_streams == 1 else model
         for i in range(3):
-            prof_model(pool[i % n_pool])
+            lat_model(pool[i % n_pool])
         torch.cuda.synchronize()
         lib.cgr_profile_enable(1)
         for i in range(prof_steps):
-            # keep the stream busy while the host enqueues the step, so the kernels (and the events between
-            # them) execute back to back: the event pairs then bracket kernel time, not host launch latency
-            torch.cuda._sleep(2_000_000)
-            prof_model(pool[i % n_pool])
+            torch.cuda._sleep(2_000_000 if small else 200_000)
+            lat_model(pool[i % n_pool])
         torch.cuda.synchronize()
         name = ctypes.create_string_buffer(64)
         ms = ctypes.c_float()
@@ -399,60 +452,40 @@ def main():
                 stage_cnt[k] = stage_cnt.get(k, 0) + 1
         lib.cgr_profile_enable(0)
     dominant = max(stage_ms, key=stage_ms.get) if stage_ms else None
-    roofline = None
-    if dominant:
-        avg_ms = stage_ms[dominant] / stage_cnt[dominant]
-        per_launch = {
-            "gemm_bond_update": 4 * (3 * n_bonds * HID) + 4 * HID * HID,
-            "bond_layer": bond_update_bytes(n_atoms, n_bonds),
-            "gather_bonds": 4 * (2 * n_bonds * HID),
-            "gemm_atom_proj": 4 * (n_atoms * FA + n_atoms * HID + HID * FA),
-            "gemm_readout_x": 4 * (n_atoms * FA + n_atoms * HID + HID * FA),
-            "atom_proj": 4 * (n_atoms * FA + 2 * n_atoms * HID + 2 * HID * FA),
-        }.get(dominant, algorithmic_bytes_fwd(n_atoms, n_bonds, args.batch) / max(1, launches_per_step))
-        achieved = per_launch / (avg_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-                traffic = json.load(fh).get(dominant, {}).get(f"batch_{args.batch}")
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": per_launch,
 
-                    "peak_kind": peak_kind,
-                    "avg_launch_us": avg_ms * 1e3, "launches_per_step": stage_cnt[dominant] / prof_steps,
-                    "stage_share": {k: round(v / sum(stage_ms.values()), 4) for k, v in sorted(stage_ms.items())}}
-
-    # ---- leg 3: end to end through the public API with HOST buffers (H2D + forward + D2H per step) ----
+    # ---- leg 3: end to end through the public API with HOST buffers (H2D + index build + kernels + D2H per step) ----
     e2e = None
-    if not args.skip_e2e:
+    if not args.skip_e2e and small:
         pinned = [hb.pin_memory() for hb in host]
         h2d = sum(t.numel() * t.element_size() for t in (pinned[0].x, pinned[0].edge_attr, pinned[0].edge_index,
                                                          pinned[0].batch, pinned[0].ptr))
         with torch.no_grad():
             for i in range(3):
-                model(pinned[i % n_pool])
+                res = model(pinned[i % n_pool])
             barrier()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
-                res = model(pinned[i % n_pool])      # stages inputs, runs the kernels, copies Ea back to the host
-            barrier()
-            e2e_single_s = time.perf_counter() - t0
-            # the pipelined public API for a stream of host batches (H2D of batch i+1 overlaps batch i's kernels)
-            def stream_seconds(coalesce):
-                list(model.predict_stream((pinned[i % n_pool] for i in range(32)), depth=4, coalesce=coalesce))
+            n_s, dt_s = timed_loop(args.leg_seconds, lambda: model(pinned[0]))     # GNN.forward(host batch), call by call
+
+            def stream_rate(coalesce):
+                """GNN.predict_stream over pinned host batches for >= leg_seconds of work (pipeline fill / drain included)."""
+                list(model.predict_stream((pinned[i % n_pool] for i in range(64)), depth=4, coalesce=coalesce))
                 barrier()
                 t0 = time.perf_counter()
+
+                def feed():
+                    i = 0
+                    while i < 64 or time.perf_counter() - t0 < args.leg_seconds:
+                        yield pinned[i % n_pool]
+                        i += 1
                 n_done = 0
-                for res in model.predict_stream((pinned[i % n_pool] for i in range(args.steps)), depth=4,
-                                                coalesce=coalesce):
+                for r_ in model.predict_stream(feed(), depth=4, coalesce=coalesce):
                     n_done += 1
-                barrier()
-                assert n_done == args.steps and res.numel() == args.batch
-                return time.perf_counter() - t0
-            e2e_uncoalesced_s = stream_seconds(1)
-            e2e_s = stream_seconds(args.coalesce)
+                    last = r_
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                assert last.numel() == B
+                return n_done, dt
+            n_u, dt_u = stream_rate(1)
+            n_c, dt_c = stream_rate(args.coalesce)
             # what the host link can do at best: plain pinned H2D copies (4 x 64 MiB, 4 streams in flight)
             raw_h = [torch.empty(64 << 20, dtype=torch.uint8).pin_memory() for _ in range(4)]
             raw_d = [torch.empty_like(t, device=dev) for t in raw_h]
@@ -469,276 +502,238 @@ def main():
             torch.cuda.synchronize()
             h2d_peak_gbs = 8 * 4 * raw_h[0].numel() / (time.perf_counter() - t0) / 1e9
             del raw_h, raw_d
-        e2e = {"seconds": e2e_s, "single_call_seconds": e2e_single_s, "uncoalesced_seconds": e2e_uncoalesced_s,
+        e2e = {"rate": B * n_c / dt_c, "steps": n_c, "single_rate": B * n_s / dt_s, "uncoalesced_rate": B * n_u / dt_u,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.numel() * 4), "h2d_peak_gbs": h2d_peak_gbs}
-
-    # ---- optional leg: device-resident reaction store (features stay in HBM, batches assembled by a kernel) ----
-    store_leg = None
-    if args.store:
-        from cgr_mpnn_3d_b200.data import make_reactions
-        from cgr_mpnn_3d_b200.store import ReactionStore
-        n_store = max(4096, 4 * args.batch)
-        store = ReactionStore.from_graphs(make_reactions(n_store, seed=9000 + rank, kind="t1x", fa=FA), device=dev)
+    elif not args.skip_e2e:
+        # large batches: one host batch through GNN.forward (H2D of the whole batch, kernels, D2H), call by call
+        pinned = [host[0].pin_memory()]
+        h2d = sum(t.numel() * t.element_size() for t in (pinned[0].x, pinned[0].edge_attr, pinned[0].edge_index,
+                                                         pinned[0].batch, pinned[0].ptr))
         with torch.no_grad():
-            for bt in store.loader(args.batch, shuffle=True, seed=0):          # warm-up pass
+            res = model(pinned[0])
+            barrier()
+            n_s, dt_s = timed_loop(args.leg_seconds, lambda: model(pinned[0]))
+        e2e = {"rate": B * n_s / dt_s, "steps": n_s, "single_rate": B * n_s / dt_s, "uncoalesced_rate": None,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.numel() * 4), "h2d_peak_gbs": None}
+
+    # ---- leg: collation cost of a FRESH batch (north-star subsystem 1): CSR a2b / b2a arrays, tile plan, feature
+    # split -- everything `value` keeps cached on its resident batches ----
+    collate_leg = None
+    if args.collate and small:
+        fresh = [Batch(b.x, b.edge_index, b.edge_attr, b.batch, b.ptr, None) for b in pool[:16]]
+
+        def prep_once(k=[0]):
+            b = fresh[k[0] % len(fresh)]
+            k[0] += 1
+            plan = build_plan(b.edge_index, b.num_nodes, b.batch, b.ptr)
+            plan.ensure_tiles()                      # one host synchronisation (tile count)
+            b.__dict__.pop("_cgr_xsplit", None)
+            split_features_for(b, plan)
+        for _ in range(5):
+            prep_once()
+        n_p, dt_p = timed_loop(0.3, prep_once)
+        idx_bytes = 16 * n_bonds + 8 * n_atoms + 4 * (3 * n_bonds + n_atoms + 1)      # int64 edge_index + batch in, int32 CSR out
+        collate_leg = {"us_per_batch": 1e6 * dt_p / n_p, "batches_per_s": n_p / dt_p,
+                       "what": "fresh device batch -> cgr_csr_build (src, dst, in_ptr, in_idx, validity flags) + tile "
+                               "plan (cgr_tc_plan_build/check, one host sync) + cgr_tc_split_features (x -> fp16 hi/lo)",
+                       "index_bytes_per_batch": int(idx_bytes), "feature_bytes_per_batch": int(8 * n_atoms * cfg["fa"])}
+
+    # ---- leg: device-resident reaction store (features stay in HBM, batches assembled by a kernel) ----
+    store_leg = None
+    if args.store and small:
+        import numpy as np
+        from cgr_mpnn_3d_b200.store import ReactionStore
+        n_store = max(4096, 4 * B)
+        store = ReactionStore.from_graphs(make_reactions(n_store, seed=9000 + rank, kind="t1x", fa=cfg["fa"]), device=dev)
+        with torch.no_grad():
+            for bt in store.loader(B, shuffle=True, seed=0):          # warm-up pass
                 model(bt)
             barrier()
             t0 = time.perf_counter()
             n_rx, ep = 0, 0
-            while n_rx < args.batch * args.steps:
-                for bt in store.loader(args.batch, shuffle=True, seed=1 + ep):
-                    out_r = model(bt)
+            while time.perf_counter() - t0 < args.leg_seconds:
+                for bt in store.loader(B, shuffle=True, seed=1 + ep):
+                    model(bt)
                     n_rx += int(bt.y.numel())
                 ep += 1
-            barrier()
-            store_leg = {"seconds": time.perf_counter() - t0, "reactions": n_rx, "store_bytes": store.nbytes(),
-                         "store_reactions": len(store)}
-            # the same screening job through the one-call C loop (cgr_store_infer), shuffled order
-            import numpy as np
+            torch.cuda.synchronize()
+            dt_loader = time.perf_counter() - t0
             rng_o = np.random.default_rng(0)
-            n_pass = max(1, (args.batch * args.steps) // len(store))
-            store.predict(model, batch_size=args.batch, order=rng_o.permutation(len(store)))
+            for _ in range(2):
+                store.predict(model, batch_size=B, order=rng_o.permutation(len(store)))
             barrier()
-            t0 = time.perf_counter()
-            for _ in range(n_pass):
-                store.predict(model, batch_size=args.batch, order=rng_o.permutation(len(store)))
-            barrier()
-            store_leg["predict_seconds"] = time.perf_counter() - t0
-            store_leg["predict_reactions"] = n_pass * len(store)
+            n_pred, dt_pred = timed_loop(args.leg_seconds,
+                                         lambda: store.predict(model, batch_size=B, order=rng_o.permutation(len(store))))
+        store_leg = {"rate": n_rx / dt_loader, "predict_rate": n_pred * len(store) / dt_pred,
+                     "store_bytes": store.nbytes(), "store_reactions": len(store)}
         del store
 
-    # ---- optional leg 4: training step (forward + MSE(sum) + explicit backward + gradient SUM all-reduce) ----
+    # ---- cfg4: the sharded screening job itself: job_reactions reactions, batch 8192, ReactionStore.predict per rank ----
+    job = None
+    if args.config == "cfg4":
+        import numpy as np
+        from cgr_mpnn_3d_b200.parallel import shard_range
+        from cgr_mpnn_3d_b200.store import ReactionStore
+        lo, hi = shard_range(args.job_reactions, rank, world)
+        n_unique = min(args.job_unique, hi - lo)
+        store = ReactionStore.from_graphs(make_reactions(n_unique, seed=7000 + rank, kind="t1x", fa=cfg["fa"]), device=dev)
+        order = np.random.default_rng(rank).integers(0, n_unique, size=hi - lo)
+        with torch.no_grad():
+            store.predict(model, batch_size=B, order=order[: 4 * B])                      # warm-up (workspaces)
+            barrier()
+            j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            j0.record()
+            t0 = time.perf_counter()
+            out_job = store.predict(model, batch_size=B, order=order)
+            j1.record()
+            torch.cuda.synchronize()
+            dt_job = time.perf_counter() - t0
+            # spot check of a slice against the oracle (rank 0): the job's energies are the reference's
+            job_err = None
+            if rank == 0:
+                from cgr_mpnn_3d_b200.data import collate_host
+                from oracle.gnn_oracle import scale_normalised_error
+                gs = make_reactions(n_unique, seed=7000 + rank, kind="t1x", fa=cfg["fa"])
+                sl = [int(v) for v in order[:24]]
+                ref = build_oracle(cfg)(collate_host([gs[k] for k in sl]))
+                job_err = scale_normalised_error(out_job[:24].cpu(), ref)
+        job = {"seconds": dt_job, "reactions": int(hi - lo), "store_bytes": store.nbytes(), "unique": n_unique,
+               "oracle_slice_error": job_err}
+        del store
+
+    # ---- leg: training step (forward + MSE(sum) + explicit backward + gradient SUM over the replicas) ----
     train = None
-    if args.train:
-        from cgr_mpnn_3d_b200.parallel import allreduce_gradients_
-        tm = build_model("auto", dev).train()
-        tb = [make_batch(args.batch, seed=5000 + 997 * rank + i, kind="t1x", fa=FA).to(dev) for i in range(8)]
-        n_t = min(args.steps, 100)
-
-        def train_step(d):
-            loss = torch.nn.functional.mse_loss(tm(d), d.y, reduction="sum")      # train.py:120
-            loss.backward()
-
-        # whole-step CUDA graphs (one per resident batch): the step is launch-bound when issued eagerly
-        side_t = torch.cuda.Stream()
-        side_t.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side_t):
-            for d in tb:                      # every batch once: builds its index arrays / tile plan before capture
-                tm.zero_grad(set_to_none=True)
-                train_step(d)
-        torch.cuda.current_stream().wait_stream(side_t)
-        torch.cuda.synchronize()
-        tgraphs = []
-        tm.zero_grad(set_to_none=True)
-        for d in tb:
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph, stream=side_t):
-                train_step(d)
-            tgraphs.append(gph)
-
-        def run_train(i):
-            tgraphs[i % len(tb)].replay()
-            if world > 1:
-                allreduce_gradients_(tm.parameters())
-
-        for i in range(5):
-            run_train(i)
-        barrier()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record()
-        for i in range(n_t):
-            run_train(i)
-        t1e.record()
-        barrier()
-        train = {"ms_total": t0e.elapsed_time(t1e), "steps": n_t}
-        # the same step issued eagerly, as a plain training loop does (trainer.py:139-144 without the optimizer):
-        # host-bound, so wall clock between two synchronisations
-        for i in range(5):
-            tm.zero_grad(set_to_none=True)
-            train_step(tb[i % len(tb)])
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n_t):
-            tm.zero_grad(set_to_none=True)
-            train_step(tb[i % len(tb)])
-            if world > 1:
-                allreduce_gradients_(tm.parameters())
-        barrier()
-        train["eager_ms"] = (time.perf_counter() - t0) * 1e3 / n_t
-        # optimizer step, reported separately (SURVEY.md section 8 d-ii / f-1): one fused launch vs torch's foreach Adam
-        from cgr_mpnn_3d_b200.optim import FusedAdam
-        for p_ in tm.parameters():
-            if p_.grad is None:
-                p_.grad = torch.zeros_like(p_)
-
-        def time_opt(opt, n=200):
-            for _ in range(5):
-                opt.step()
-            torch.cuda.synchronize()
-            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            o0.record()
-            for _ in range(n):
-                opt.step()
-            o1.record()
-            torch.cuda.synchronize()
-            return o0.elapsed_time(o1) / n
-        l_before = lib.cgr_launch_count()
-        train["adam_fused_ms"] = time_opt(FusedAdam(tm.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True))
-        train["adam_fused_launches"] = (lib.cgr_launch_count() - l_before) / 205
-        train["adam_torch_ms"] = time_opt(torch.optim.Adam(tm.parameters(), lr=1e-3, weight_decay=1e-5, amsgrad=True))
-
-        # opt-in: the COMPLETE data-parallel step (forward + loss + backward + gradient SUM + Adam) two ways -- NCCL all-reduce
-        # then the one-launch Adam, vs PeerFusedAdam (sum over NVLink peer memory + Adam in one kernel, no NCCL)
-        if args.peer_adam and world > 1:
-            from cgr_mpnn_3d_b200 import ops as _ops
-            from cgr_mpnn_3d_b200.optim import PeerFusedAdam
-
-            def timed_steps(step_fn, n):
-                for i in range(6):
-                    step_fn(i)
-                barrier()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for i in range(n):
-                    step_fn(i)
-                a1.record()
-                barrier()
-                return a0.elapsed_time(a1) / n
-            fa_opt = FusedAdam(tm.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)
-
-            def nccl_step(i):
-                tgraphs[i % len(tb)].replay()
-                allreduce_gradients_(tm.parameters())
-                fa_opt.step()
-            train["dp_step_nccl_ms"] = timed_steps(nccl_step, n_t)
-            tm2 = build_model("auto", dev).train()
-            popt = PeerFusedAdam(tm2.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)
-
-            def train_step2(d):
-                torch.nn.functional.mse_loss(tm2(d), d.y, reduction="sum").backward()
-            with torch.cuda.stream(side_t):
-                for j, d in enumerate(tb[:2]):
-                    tm2.zero_grad(set_to_none=True)
-                    train_step2(d)
-            torch.cuda.current_stream().wait_stream(side_t)
-            torch.cuda.synchronize()
-            pgraphs = []
-            for j, d in enumerate(tb):           # graph j writes its gradients into arena j % 2: replayed in order
-                tm2.zero_grad(set_to_none=True)
-                popt._cur = j % 2
-                gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph, stream=side_t):
-                    train_step2(d)
-                pgraphs.append(gph)
-            popt._cur = 0
-            state = {"i": 0}
-
-            def peer_step(_):
-                j = state["i"] % len(tb)
-                pgraphs[j].replay()
-                popt.step(arena=j % 2)
-                state["i"] += 1
-            train["dp_step_peer_ms"] = timed_steps(peer_step, n_t)
-            _ops.set_grad_arena(None)
+    if args.train and args.config == "cfg2":
+        train = train_leg(args, cfg, dev, rank, world, barrier, lib)
 
     # ---- reduce over ranks (max time), assemble the line ----
-    t = torch.tensor([ms_total, e2e["seconds"] if e2e else 0.0, train["ms_total"] if train else 0.0,
-                      e2e["single_call_seconds"] if e2e else 0.0, e2e["uncoalesced_seconds"] if e2e else 0.0],
-                     dtype=torch.float64, device=dev)
+    med_ms = statistics.median(region_ms)
+    vals = [med_ms, min(region_ms), (1.0 / e2e["rate"]) if e2e else 0.0, train["ms_step"] if train else 0.0,
+            job["seconds"] if job else 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, train_ms, e2e_single_s, e2e_unco_s = (float(v) for v in t)
-    total_rxn = args.batch * args.steps * world
-    value = total_rxn / (ms_total * 1e-3)
+    med_ms, min_ms, e2e_inv, train_ms, job_s = (float(v) for v in t)
+    ms_per_step = med_ms / steps
+    value = B * world / (ms_per_step * 1e-3)
 
-    cpu = None
+    cpu = cpu1 = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_reference_leg(args.batch, 10 ** 9, 3, args.cpu_seconds)
+        cpu = cpu_reference_leg(cfg, B, 10 ** 9, 3, args.cpu_seconds, os.cpu_count() or 1)
+        cpu1 = cpu_reference_leg(cfg, B, 10 ** 9, 1, min(args.cpu_seconds, 6.0), 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["single_thread"] = {k: cpu1[k] for k in ("value", "unit", "cores", "sample")}
+
+    # fast mode: report the error it costs (scale-normalised, vs an fp64 evaluation of the same graphs)
+    precision_info = None
+    if rank == 0 and small:
+        with torch.no_grad():
+            hb = make_batch(B, seed=1000 + 997 * rank, kind=cfg["kind"], fa=cfg["fa"])
+            o64 = build_oracle(cfg, torch.float64)
+            ref = o64(Batch(hb.x.double(), hb.edge_index, hb.edge_attr.double(), hb.batch, hb.ptr, None))
+            from oracle.gnn_oracle import scale_normalised_error
+            precision_info = {"mode": args.precision,
+                              "ea_error_vs_fp64": scale_normalised_error(lat_model(hb.to(dev)).cpu(), ref)}
 
     clocks.stop()
-    if roofline:
-        # Average launch duration of the dominant kernel OVER THE TIMED REGION of `value` = its CUDA-event share of a step
-        # (recorded by the library on the launching stream, the stream kept busy so event pairs bracket kernel time) x the
-        # timed region's time per step / launches per step -- the machine time the pipelined region spends per launch.
-        # Beside it: the same share of the un-pipelined single-stream step (latency of one launch in a dependent chain) and
-        # one isolated launch between two events (launch latency and event overhead included).
-        share = roofline["stage_share"].get(roofline["kernel"], 0.0)
-        lps = max(1e-9, roofline["launches_per_step"])
-        per_launch = roofline["algorithmic_bytes_per_launch"]
-        roofline["event_bracketed_us"] = roofline.pop("avg_launch_us")
-        dur_us = (ms_total / args.steps) * 1e3 * share / lps
-        roofline["avg_launch_us"] = dur_us
-        roofline["achieved"] = per_launch / (dur_us * 1e-6) / 1e9
-        roofline["frac"] = roofline["achieved"] / hbm_peak
-        lat_us = single_stream_ms * 1e3 * share / lps
-        roofline["single_stream_us_per_launch"] = lat_us
-        roofline["single_stream_frac"] = per_launch / (lat_us * 1e-6) / 1e9 / hbm_peak
-        roofline["note"] = ("avg_launch_us / achieved / frac: kernel's CUDA-event share of a step x time per step of the timed "
-                            "region (value: independent steps pipelined over streams) / launches per step; single_stream_*: "
-                            "same share of the un-pipelined CUDA-graph step (latency of a launch in a dependent chain); "
-                            "event_bracketed_us: one isolated launch between two events (launch latency included)")
+    roofline = None
+    if dominant:
+        per_launch = stage_bytes(dominant, n_atoms, n_bonds, B, cfg)
+        if per_launch is None:
+            per_launch = algorithmic_bytes_fwd(n_atoms, n_bonds, B, cfg) / max(1, launches_per_step)
+        lps = stage_cnt[dominant] / prof_steps
+        dur_us = 1e3 * stage_ms[dominant] / stage_cnt[dominant]          # CUDA events around the launch, busy stream
+        share = stage_ms[dominant] / sum(stage_ms.values())
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+                traffic = json.load(fh).get(dominant, {}).get(f"batch_{B}")
+        except Exception:
+            pass
+        pipe_us = ms_per_step * 1e3 * share / lps                        # machine time the pipelined region spends per launch
+        roofline = {"bound": "hbm", "kernel": dominant, "achieved": per_launch / (dur_us * 1e-6) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": per_launch / (dur_us * 1e-6) / 1e9 / hbm_peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": per_launch, "peak_kind": peak_kind,
+                    "avg_launch_us": dur_us, "launches_per_step": lps,
+                    "pipelined_us_per_launch": pipe_us,
+                    "pipelined_frac": per_launch / (pipe_us * 1e-6) / 1e9 / hbm_peak,
+                    "stage_share": {k: round(v / sum(stage_ms.values()), 4) for k, v in sorted(stage_ms.items())},
+                    "note": "avg_launch_us / achieved / frac: the kernel's own duration (CUDA events around each launch on the "
+                            "launching stream, stream kept busy) against its algorithmic bytes; pipelined_*: the kernel's "
+                            "event share of a step x the timed region's time per step (independent forwards overlapped "
+                            "over streams) -- machine time per launch, not a launch duration"}
     if rank == 0:
-        alg = algorithmic_bytes_fwd(n_atoms, n_bonds, args.batch)
+        alg = algorithmic_bytes_fwd(n_atoms, n_bonds, B, cfg)
+        flops = algorithmic_flops_fwd(n_atoms, n_bonds, B, cfg)
+        step_s = ms_per_step * 1e-3
         line = {
-            "metric": "reactions/sec (CGR-MPNN-3D d4 h400 fwd)", "value": value, "unit": "reactions/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg-2: CGR-MPNN-3D d{DEPTH} h{HID} learnable-skip forward (inference), batch "
-                                   f"{args.batch}/GPU, Fa={FA} Fb={FB}, T1x-shaped synthetic reactions, random-init "
-                                   f"weights in the reference .pth layout",
-                       "engine": engine, "cuda_graph": not args.no_graph, "streams": n_streams,
-                       "graph_grouping": (f"one graph per {n_streams} batches on parallel branches, groups alternate over 2 streams"
-                                          if group_graphs else "one graph per batch"),
+            "metric": metric, "value": value, "unit": "reactions/s",
+            "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (FP16x3-split tcgen05 MMA, fp32 accumulate; 2e-6 of fp64)" if args.precision == "fp32"
+                     else "f16 single-pass tcgen05 MMA, fp32 accumulate (fast mode, error reported in `precision`)",
+            "data": "synthetic",
+            "config": {"workload": workload,
+                       "engine": engine, "precision": args.precision, "cuda_graph": not args.no_graph, "streams": n_streams,
+                       "timed_region": f"{steps} forwards captured as ONE CUDA graph over {n_streams} parallel branches; "
+                                       f"median of {repeats} regions (min {min_ms / steps * 1e3:.2f} us/step), each between "
+                                       f"barrier + synchronize, max over ranks",
                        "single_stream_ms_per_step": single_stream_ms,
-                       "parallelism": f"replicas x{world}, no collective",
+                       "eager_device_batch_rate": eager_device_rate,
+                       "parallelism": f"replicas x{world}, no collective", "cpu_affinity": affinity,
                        "l2": f"inputs rotate over {n_pool} distinct resident batches ({resident / 1e6:.0f} MB > "
-                             f"{L2_BYTES / 1e6:.0f} MB L2); weights (5.9 MB) stay resident",
+                             f"{L2_BYTES / 1e6:.0f} MB L2); weights ({4 * cfg['n_params'] / 1e6:.1f} MB) stay resident",
                        "atoms_per_batch": n_atoms, "bonds_per_batch": n_bonds},
-            "whole_forward": {"algorithmic_bytes": alg, "achieved_gbs": alg / (ms_total / args.steps * 1e-3) / 1e9,
-                              "hbm_frac": alg / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak,
+            "whole_forward": {"algorithmic_bytes": alg, "achieved_gbs": alg / step_s / 1e9,
+                              "hbm_frac": alg / step_s / 1e9 / hbm_peak,
+                              "algorithmic_flops": flops, "achieved_tflops": flops / step_s / 1e12,
+                              "tensor_frac_of_bf16_sustained": flops / step_s / 1e12 / tc_sustained,
+                              "executed_tensor_flops_factor": 3 if args.precision == "fp32" else 1,
                               "peak_kind": peak_kind},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
-            "gpu_launches": int(launches_per_step) * args.steps,
+            "gpu_launches": int(launches_per_step) * steps * repeats,
+            "launches_per_step": int(launches_per_step),
+            "precision": precision_info,
         }
         if train:
-            line["train_step"] = {"value": args.batch * train["steps"] * world / (train_ms * 1e-3), "unit": "reactions/s",
-                                  "ms_per_step": train_ms / train["steps"], "steps": train["steps"],
-                                  "eager_ms_per_step": train["eager_ms"],
-                                  "dp_step_with_optimizer": ({"nccl_allreduce_plus_fused_adam_ms": train["dp_step_nccl_ms"],
-                                                              "peer_fused_adam_ms": train["dp_step_peer_ms"],
-                                                              "what": "graph-replayed fwd+loss+bwd, then gradient SUM over "
-                                                                      "replicas and Adam(amsgrad): NCCL all-reduce + one-launch "
-                                                                      "Adam vs ONE kernel over NVLink peer memory (no NCCL)"}
-                                                             if "dp_step_peer_ms" in train else None),
-                                  "optimizer": {"fused_adam_ms": train["adam_fused_ms"],
-                                                "fused_adam_launches_per_step": train["adam_fused_launches"],
-                                                "torch_adam_ms": train["adam_torch_ms"],
-                                                "what": "Adam(weight_decay, amsgrad=True) step over all parameters, eager "
-                                                        "launches, timed apart from the step above (train.py:117-119)"},
-                                  "what": "forward + MSE(sum) + explicit backward + flat gradient SUM all-reduce "
-                                          "(optimizer excluded), batch %d/GPU, whole step replayed as a CUDA graph" % args.batch}
+            line["train_step"] = dict(train["line"], value=B * world / (train_ms * 1e-3), ms_per_step=train_ms)
+        if collate_leg:
+            line["collate"] = collate_leg
         if store_leg:
-            line["resident_store"] = {"value": store_leg["reactions"] * world / store_leg["seconds"], "unit": "reactions/s",
+            line["resident_store"] = {"value": store_leg["rate"] * world, "unit": "reactions/s",
                                       "store_reactions": store_leg["store_reactions"], "store_bytes": store_leg["store_bytes"],
-                                      "predict_value": store_leg["predict_reactions"] * world / store_leg["predict_seconds"],
+                                      "predict_value": store_leg["predict_rate"] * world,
                                       "predict_api": "ReactionStore.predict(model, batch_size): the per-batch loop in C "
                                                      "(cgr_store_infer), 8 streams, results stay on the device",
-                                      "what": "shuffled epochs over a ReactionStore held in HBM: per step one small index "
-                                              "upload, the gather kernel, one-launch CSR and the forward (eager launches); "
-                                              "no host-to-device copy of features"}
+                                      "what": "shuffled epochs over a ReactionStore held in HBM for >= %.1f s: per step one "
+                                              "small index upload, the gather kernel, one-launch CSR and the forward (eager "
+                                              "launches); no host-to-device copy of features" % args.leg_seconds}
+        if job:
+            line["screening_job"] = {"value": args.job_reactions / job_s, "unit": "reactions/s", "seconds": job_s,
+                                     "reactions": args.job_reactions, "reactions_per_gpu": job["reactions"],
+                                     "per_gpu_value": job["reactions"] / job_s, "batch": B,
+                                     "unique_reactions_per_gpu": job["unique"], "store_bytes_per_gpu": job["store_bytes"],
+                                     "hbm_frac_per_gpu": (alg / B) * job["reactions"] / job_s / 1e9 / hbm_peak,
+                                     "oracle_slice_error": job["oracle_slice_error"],
+                                     "what": "ReactionStore.predict over this rank's contiguous shard (parallel.shard_range) of "
+                                             "the job: ids drawn with repeats from a resident set (a 1 M-reaction set is "
+                                             "58 GB of HBM; host generation of it is the slow part), batches assembled on "
+                                             "the device, no collective, max over ranks"}
         if e2e:
-            line["e2e"] = {"value": total_rxn / e2e_s, "unit": "reactions/s",
-                           "api": "GNN.predict_stream(host batches of %d, depth=4, workers=2, coalesce=%d): every step's "
-                                  "H2D from its own pinned buffers + index build + kernels + D2H; up to %d consecutive "
-                                  "batches share one submission" % (args.batch, args.coalesce, args.coalesce),
-                           "uncoalesced_value": total_rxn / e2e_unco_s,
+            e2e_rate = (1.0 / e2e_inv) * world if e2e_inv > 0 else None
+            line["e2e"] = {"value": e2e_rate, "unit": "reactions/s",
+                           "api": ("GNN.predict_stream(host batches of %d, depth=4, workers=2, coalesce=%d) for >= %.1f s: "
+                                   "every step's H2D from its own pinned buffers + index build + kernels + D2H; up to %d "
+                                   "consecutive batches share one submission" % (B, args.coalesce, args.leg_seconds,
+                                                                                  args.coalesce)) if small
+                                  else "GNN.forward(host batch of %d): H2D of the whole batch + index build + kernels + D2H" % B,
+                           "steps": e2e["steps"],
+                           "uncoalesced_value": e2e["uncoalesced_rate"] * world if e2e["uncoalesced_rate"] else None,
                            "uncoalesced_api": "GNN.predict_stream(..., coalesce=1): one submission per batch",
-                           "single_call_value": total_rxn / e2e_single_s, "single_call_api": "GNN.forward(host batch)",
+                           "single_call_value": e2e["single_rate"] * world, "single_call_api": "GNN.forward(host batch)",
                            "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
                            "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
-                           "h2d_gbs": e2e["h2d_bytes_per_step"] * args.steps / e2e_s / 1e9,
+                           "h2d_gbs": (e2e["h2d_bytes_per_step"] / B) * (e2e_rate / world) / 1e9 if e2e_rate else None,
                            "h2d_copy_peak_gbs": e2e["h2d_peak_gbs"],
                            "bound": "host link: h2d_gbs is the per-GPU input traffic the e2e rate implies, "
                                     "h2d_copy_peak_gbs plain pinned 64 MiB cudaMemcpyAsync copies on 4 streams of this box"}
@@ -746,6 +741,141 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def train_leg(args, cfg, dev, rank, world, barrier, lib):
+    """cfg-3: the data-parallel training step at batch 64 per GPU.  The timed step is the COMPLETE step the reference's
+    trainer runs (trainer.py:139-144): forward, MSELoss(sum), explicit backward, gradient SUM over the replicas and the
+    Adam(amsgrad) update -- forward + loss + backward replayed as one CUDA graph, then the exchange + update."""
+    import torch.distributed as dist
+    from cgr_mpnn_3d_b200.optim import FusedAdam
+    from cgr_mpnn_3d_b200.parallel import allreduce_gradients_
+    B = cfg["batch"]
+    tm = build_model(cfg, "auto", dev).train()
+    tb = [make_batch(B, seed=5000 + 997 * rank + i, kind="t1x", fa=cfg["fa"]).to(dev) for i in range(8)]
+    n_t = min(max(args.steps, 20), 100)
+
+    def train_step(d):
+        loss = torch.nn.functional.mse_loss(tm(d), d.y, reduction="sum")      # train.py:120
+        loss.backward()
+
+    side_t = torch.cuda.Stream()
+    side_t.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side_t):
+        for d in tb:                      # every batch once: builds its index arrays / tile plan before capture
+            tm.zero_grad(set_to_none=True)
+            train_step(d)
+    torch.cuda.current_stream().wait_stream(side_t)
+    torch.cuda.synchronize()
+    tgraphs = []
+    tm.zero_grad(set_to_none=True)
+    for d in tb:
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph, stream=side_t):
+            train_step(d)
+        tgraphs.append(gph)
+    opt = FusedAdam(tm.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+
+    def timed(fn, n):
+        for i in range(5):
+            fn(i)
+        ms = []
+        for _ in range(5):
+            barrier()
+            torch.cuda._sleep(200_000)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(n):
+                fn(i)
+            a1.record()
+            barrier()
+            ms.append(a0.elapsed_time(a1) / n)
+        return statistics.median(ms)
+
+    def step_fb(i):                       # forward + loss + backward + gradient exchange (optimizer excluded)
+        tgraphs[i % len(tb)].replay()
+        if world > 1:
+            allreduce_gradients_(tm.parameters())
+
+    def step_full(i):                     # the complete step: + Adam
+        step_fb(i)
+        opt.step()
+    ms_fb = timed(step_fb, n_t)
+    ms_full = timed(step_full, n_t)
+    # the same step issued eagerly, as a plain training loop does: host-bound, wall clock between two synchronisations
+    for i in range(5):
+        tm.zero_grad(set_to_none=True)
+        train_step(tb[i % len(tb)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_t):
+        tm.zero_grad(set_to_none=True)
+        train_step(tb[i % len(tb)])
+        if world > 1:
+            allreduce_gradients_(tm.parameters())
+    barrier()
+    eager_ms = (time.perf_counter() - t0) * 1e3 / n_t
+
+    def time_opt(o, n=100):
+        for _ in range(5):
+            o.step()
+        torch.cuda.synchronize()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(n):
+            o.step()
+        o1.record()
+        torch.cuda.synchronize()
+        return o0.elapsed_time(o1) / n
+    adam_fused_ms = time_opt(opt)
+    adam_torch_ms = time_opt(torch.optim.Adam(tm.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True))
+    dp = None
+    if world > 1:
+        # the same complete step with the gradient exchange and the update as ONE kernel over NVLink peer memory
+        from cgr_mpnn_3d_b200 import ops as _ops
+        from cgr_mpnn_3d_b200.optim import PeerFusedAdam
+        tm2 = build_model(cfg, "auto", dev).train()
+        popt = PeerFusedAdam(tm2.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+
+        def train_step2(d):
+            torch.nn.functional.mse_loss(tm2(d), d.y, reduction="sum").backward()
+        with torch.cuda.stream(side_t):
+            for d in tb[:2]:
+                tm2.zero_grad(set_to_none=True)
+                train_step2(d)
+        torch.cuda.current_stream().wait_stream(side_t)
+        torch.cuda.synchronize()
+        pgraphs = []
+        for j, d in enumerate(tb):           # graph j writes its gradients into arena j % 2: replayed in order
+            tm2.zero_grad(set_to_none=True)
+            popt._cur = j % 2
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side_t):
+                train_step2(d)
+            pgraphs.append(gph)
+        popt._cur = 0
+        state = {"i": 0}
+
+        def peer_step(_):
+            j = state["i"] % len(tb)
+            pgraphs[j].replay()
+            popt.step(arena=j % 2)
+            state["i"] += 1
+        ms_peer = timed(peer_step, n_t)
+        _ops.set_grad_arena(None)
+        dp = {"nccl_allreduce_plus_fused_adam_ms": ms_full, "peer_fused_adam_ms": ms_peer,
+              "what": "graph-replayed fwd+loss+bwd, then gradient SUM over replicas and Adam(amsgrad): NCCL all-reduce + "
+                      "one-launch Adam vs ONE kernel over NVLink peer memory (no NCCL)"}
+    ms_step = ms_full if dp is None else min(ms_full, dp["peer_fused_adam_ms"])
+    line = {"unit": "reactions/s", "steps": n_t,
+            "fwd_loss_bwd_exchange_ms": ms_fb, "eager_ms_per_step": eager_ms,
+            "dp_step_with_optimizer": dp,
+            "optimizer": {"fused_adam_ms": adam_fused_ms, "torch_adam_ms": adam_torch_ms,
+                          "what": "Adam(weight_decay, amsgrad=True) over all parameters, timed apart (train.py:117-119)"},
+            "what": "COMPLETE data-parallel training step, batch %d/GPU: forward + MSE(sum) + explicit backward (one CUDA "
+                    "graph) + gradient SUM over the replicas + Adam(amsgrad) update; the faster of NCCL all-reduce + "
+                    "FusedAdam and PeerFusedAdam when N > 1; median of 5 regions, max over ranks" % B}
+    return {"ms_step": ms_step, "line": line}
 
 
 def _emit(line: dict) -> None:

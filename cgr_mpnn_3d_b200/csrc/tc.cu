@@ -22,6 +22,7 @@
 
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
+#include "tc_fwd.cuh"
 #include "umma.cuh"
 
 namespace {
@@ -469,6 +470,56 @@ int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const c
               : launch_gemm_t<BN_SMALL, EPI, false, NT_SMALL>(prm, m_tiles, n_slices, name, pdl, st);
 }
 
+// ---- fused forward: all bond layers + readout of a tile group in one cluster launch (tc_fwd.cuh) ----
+constexpr int FWD_BN_WIDE = 208, FWD_BN_NARROW = 80;
+
+template <int BN, bool RELU>
+int launch_fwd_t(const tcf::FwdParams& prm, int n_groups, int S, bool pdl, cudaStream_t st) {
+  using C = tcf::FCfg<BN>;
+  static bool attr_done = false;      // benign race: the attribute is idempotent
+  if (!attr_done) {
+    CGR_CUDA(cudaFuncSetAttribute(tcf::tc_fwd_kernel<BN, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  CgrRange prof("tc_fwd_fused", st);
+  cgr_note_launch("tc_fwd_fused", st, 1);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(n_groups * S));
+  cfg.blockDim = dim3(tcf::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  CGR_CUDA(cudaLaunchKernelEx(&cfg, tcf::tc_fwd_kernel<BN, RELU>, prm));
+  return CGR_OK;
+}
+
+struct FwdChoice { int bn, S, tpc; };
+// wide slices + two tiles per cluster (the epilogue of one tile hides behind the other's MMAs): throughput;
+// narrow slices + one tile per cluster (most CTAs per tile): latency of a lone small batch
+bool choose_fwd(int64_t T, int H, bool throughput, FwdChoice* c) {
+  const int s_wide = (int)cgr_ceil_div(H, FWD_BN_WIDE), s_narrow = (int)cgr_ceil_div(H, FWD_BN_NARROW);
+  static const char* forced = getenv("CGR_FWD_CFG");      // experiments: wide1 | wide2 | narrow1 | narrow2
+  if (forced) {
+    const bool wide = strncmp(forced, "wide", 4) == 0;
+    c->bn = wide ? FWD_BN_WIDE : FWD_BN_NARROW;
+    c->S = wide ? s_wide : s_narrow;
+    c->tpc = forced[strlen(forced) - 1] == '2' ? 2 : 1;
+    return c->S <= 8;
+  }
+  if (!throughput && s_narrow <= 8 && T * s_narrow <= 120) { *c = FwdChoice{FWD_BN_NARROW, s_narrow, 1}; return true; }
+  if (s_wide <= 8) { *c = FwdChoice{FWD_BN_WIDE, s_wide, T >= 2 ? 2 : 1}; return true; }
+  return false;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -770,9 +821,47 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
                                 (const float*)(wbuf + wl.off_wet), g->tile_info, fb, H, (int)p->act, h0, hbuf_hi(0),
                                 hbuf_lo(0), (int64_t)w.kp_h, flag));
   }
+  const bool relu = p->act == CGR_ACT_RELU;
+  // 4+5 fused: every bond layer and the readout of a tile group in ONE cluster launch (inference; the training forward
+  // keeps one operand pair per layer for the backward and stays on the per-layer kernels)
+  static const bool use_fused = getenv("CGR_NO_FUSED_FWD") == nullptr;
+  FwdChoice fc;
+  if (use_fused && !blob && !(training && p->host_dropout_p) && choose_fwd(T, H, p->tc_throughput != 0, &fc)) {
+    tcf::FwdParams prm;
+    memset(&prm, 0, sizeof(prm));
+    for (int b = 0; b < 2; ++b) {
+      if ((rc = make_map(&prm.tmA_hi[b], h_hi[b], w.rows_pad, H, w.kp_h, TM))) return rc;
+      if ((rc = make_map(&prm.tmA_lo[b], h_lo[b], w.rows_pad, H, w.kp_h, TM))) return rc;
+      prm.o_hi[b] = h_hi[b]; prm.o_lo[b] = h_lo[b];
+    }
+    for (int l = 0; l <= d; ++l) {
+      if ((rc = make_map(&prm.tmB_hi[l], w_hi(1 + l), H, H, wl.ld[1 + l], fc.bn))) return rc;
+      if ((rc = make_map(&prm.tmB_lo[l], w_lo(1 + l), H, H, wl.ld[1 + l], fc.bn))) return rc;
+      if (l < d) {
+        prm.bias[l] = p->b_conv[l];
+        prm.skip[l] = p->use_skip ? p->skip[l] : nullptr;
+      }
+    }
+    prm.ldo = w.kp_h;
+    prm.unscale = unscale;
+    prm.h0 = h0;
+    prm.PQ = PQ;
+    prm.w_ffn = p->w_ffn; prm.b_ffn = p->b_ffn;
+    prm.tile_info = g->tile_info;
+    prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
+    prm.partial_out = partial; prm.out = out; prm.tile_counter = tile_counter; prm.overflow = flag;
+    prm.n_rxn = B;
+    prm.depth = d; prm.H = H; prm.num_k = (int)cgr_ceil_div(H, BK); prm.act = p->act;
+    prm.n_tiles = (int)T; prm.tiles_per_cluster = fc.tpc;
+    const int n_groups = (int)cgr_ceil_div(T, fc.tpc);
+    if (fc.bn == FWD_BN_WIDE)
+      return relu ? launch_fwd_t<FWD_BN_WIDE, true>(prm, n_groups, fc.S, use_pdl, st)
+                  : launch_fwd_t<FWD_BN_WIDE, false>(prm, n_groups, fc.S, use_pdl, st);
+    return relu ? launch_fwd_t<FWD_BN_NARROW, true>(prm, n_groups, fc.S, use_pdl, st)
+                : launch_fwd_t<FWD_BN_NARROW, false>(prm, n_groups, fc.S, use_pdl, st);
+  }
   // 4. message passing layers: one fused kernel each
   const int bn_h = choose_bn(T, H);
-  const bool relu = p->act == CGR_ACT_RELU;
   for (int l = 0; l < d; ++l) {
     TcGemmParams prm;
     memset(&prm, 0, sizeof(prm));

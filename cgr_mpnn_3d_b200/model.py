@@ -190,7 +190,7 @@ class GNN(nn.Module):
 
     def _poll_overflow(self, wait: bool = False) -> None:
         pend = self.__dict__.get("_ovf_pending")
-        if not pend:
+        if not pend or torch.cuda.is_current_stream_capturing():      # event queries are illegal during graph capture
             return
         keep = []
         for ev, ring, slot in pend:

@@ -395,8 +395,9 @@ def test_tc_forward_golden(name):
     simt = build_model(meta, state, engine="simt").eval()
     with torch.no_grad():
         assert scale_normalised_error(out, simt(data)) < 2e-5
-        model.tile_policy = "throughput"               # two-CTAs-per-SM kernel configuration: same numbers
-        assert torch.equal(model(data), out)
+        model.tile_policy = "throughput"               # wide-slice / two-tiles-per-cluster configuration: same energies up to
+        o_t = model(data)                              # fp32 rounding of the final sum over column slices (2 instead of 5)
+        assert scale_normalised_error(o_t, out) < 1e-6 and torch.equal(model(data), o_t)
 
 
 def test_tc_forward_large_batch_against_fp64():
@@ -945,12 +946,17 @@ def test_cfg5_drug_like_d6_h1024(engine):
     assert scale_normalised_error(out, ref.detach()) < EA_TOL
     mse_sum_loss(out, d.y).backward()
     for k, p in model.named_parameters():
-        # ReLU network: same bar as the other BASELINE-sized cases (a pre-activation within rounding of 0 may flip)
+        # ReLU network: a pre-activation within rounding of 0 may flip in ANY fp32 evaluation, and depth 6 x 1024 units
+        # has many of them -- the bar is the 1e-4 of the other cases or, where the reference's own fp32 run is further
+        # from fp64 than that, "within 2x of the reference's own fp32 distance from fp64"
         r64 = og64[k].grad
-        err = ((p.grad.detach().double().cpu() - r64).abs() / r64.abs().max().clamp_min(1e-30)).flatten()
+        scale = r64.abs().max().clamp_min(1e-30)
+        err = ((p.grad.detach().double().cpu() - r64).abs() / scale).flatten()
+        err32 = ((og[k].grad.double() - r64).abs() / scale).flatten()
         if err.numel() >= 1000:
-            assert float(torch.quantile(err[: 2 ** 24], 0.995)) < GRAD_TOL, k
-        assert float(err.max()) < max(3e-3, 1.5 * tensor_error(og[k].grad, r64)), k
+            q, q32 = float(torch.quantile(err[: 2 ** 24], 0.995)), float(torch.quantile(err32[: 2 ** 24], 0.995))
+            assert q < max(GRAD_TOL, 2.0 * q32), (k, q, q32)
+        assert float(err.max()) < max(3e-3, 1.5 * float(err32.max())), k
     model.eval()
     with torch.no_grad():
         o1, o2 = model(d), model(d)
