@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libcgr_b200.so")
 
 ENGINE_SIMT = 0
 ENGINE_TC = 1
+ENGINE_TC_FAST = 2      # Python-level id: tcgen05 engine with cgr_params_t.tc_fast = 1 (single-pass fp16, inference only)
 ACT_IDS = {"relu": 0, "silu": 1, "gelu": 2}
 
 c_float_p = C.POINTER(C.c_float)
@@ -31,6 +32,7 @@ class CgrParams(C.Structure):
         ("host_dropout_p", c_float_p),
         ("tc_weights", C.c_void_p),
         ("tc_throughput", C.c_int32),
+        ("tc_fast", C.c_int32),
     ]
 
 

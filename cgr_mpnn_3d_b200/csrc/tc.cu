@@ -765,8 +765,9 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   static const bool use_pdl = getenv("CGR_NO_PDL") == nullptr;   // programmatic dependent launch between the kernels
   // grids larger than the machine, or forwards pipelined over streams by the caller, run two CTAs per SM
   auto two_per_sm = [&](int64_t ctas) { return p->tc_throughput != 0 || ctas > 148; };
-  int* flag = g->tc_status;              // [0] sticky fp16-range flag, [1..T] readout arrival counters
+  int* flag = g->tc_status;              // [0] fp16-range flag bits, [1..T] readout arrival counters
   int* tile_counter = g->tc_status + 1;
+  const int fast = (p->tc_fast && !blob) ? 1 : 0;      // single-pass fp16: inference only (training keeps the parity mode)
 
   // 1. x -> (hi, lo), unless the caller prepared it with cgr_tc_split_features (batch preparation)
   if (need_x) {
@@ -781,7 +782,9 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     memset(&prm, 0, sizeof(prm));
     if ((rc = make_map(&prm.tmA_hi, x_hi, N, fa, w.kp_x, TM))) return rc;
     if ((rc = make_map(&prm.tmA_lo, x_lo, N, fa, w.kp_x, TM))) return rc;
-    const int bn = choose_bn(cgr_ceil_div(N, TM), 2 * H);
+    // throughput mode: wide slices (operand bytes streamed per batch: 42 MB instead of 67 MB at cfg-2)
+    static const bool ap_wide = getenv("CGR_AP_NARROW") == nullptr;
+    const int bn = (p->tc_throughput != 0 && ap_wide) ? BN_LARGE : choose_bn(cgr_ceil_div(N, TM), 2 * H);
     if ((rc = make_map(&prm.tmB_hi, w_hi(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     prm.num_k = (int)cgr_ceil_div(fa, BK);
@@ -792,6 +795,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.bias = bias_cat;
     prm.out_f32 = PQ;
     prm.ldc = 2 * H;
+    prm.fast = fast;
     prm.overflow = flag;             // first kernel of the forward: clears the per-forward overflow bit
     rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false,
                                 two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
@@ -853,6 +857,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.n_rxn = B;
     prm.depth = d; prm.H = H; prm.num_k = (int)cgr_ceil_div(H, BK); prm.act = p->act;
     prm.n_tiles = (int)T; prm.tiles_per_cluster = fc.tpc;
+    prm.fast = fast;
+    prm.dbg = g_tc_dbg;
     const int n_groups = (int)cgr_ceil_div(T, fc.tpc);
     if (fc.bn == FWD_BN_WIDE)
       return relu ? launch_fwd_t<FWD_BN_WIDE, true>(prm, n_groups, fc.S, use_pdl, st)
@@ -884,6 +890,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.seed = seed; prm.layer = (uint32_t)l;
     prm.o_hi = hbuf_hi(l + 1); prm.o_lo = hbuf_lo(l + 1); prm.ldo = w.kp_h;
     prm.overflow = flag;
+    prm.fast = fast;
     prm.dbg = g_tc_dbg;
     rc = launch_gemm<EPI_BOND>(prm, bn_h, (int)T, relu, "bond_layer", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
@@ -912,6 +919,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.partial_out = partial;
     prm.n_rxn = B;
     prm.overflow = flag;
+    prm.fast = fast;
     prm.hv_out = blob ? (float*)(blob + SL.off_hv) : nullptr;
     rc = launch_gemm<EPI_READOUT>(prm, bn_h, (int)T, relu, "tc_readout", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;

@@ -29,9 +29,10 @@ using tcg::NBR;
 using tcg::TM;
 
 constexpr int MAX_LAYERS = 16;                 // bond layers + readout
-constexpr int EPI_WARPS = 12;
+constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = 128 + EPI_THREADS;     // 512
+constexpr int THREADS = 128 + EPI_THREADS;     // 640
+constexpr int ZROW = TM;                       // staging row that stays zero: target of unused neighbour slots
 constexpr int SLOT_COLS = 256;                 // TMEM columns per accumulator slot
 constexpr int MAX_TPC = 2;                     // tiles per cluster (ping-pong)
 constexpr int SMEM_LIMIT = 232448;
@@ -47,7 +48,7 @@ struct FCfg {
   static constexpr int UPR = CH / 4;                           // float4 units per row of a chunk
   static constexpr int CH8 = (CH + 7) / 8 * 8;
   static constexpr int CHP = ((CH8 / 4) % 2 == 1) ? CH8 : CH8 + 4;   // staging row pitch: odd multiple of 4 floats
-  static constexpr int Y_BYTES = (TM * CHP * 4 + 1023) / 1024 * 1024;
+  static constexpr int Y_BYTES = ((TM + 1) * CHP * 4 + 1023) / 1024 * 1024;     // + the zero row
   static constexpr int LPR = UPR <= 16 ? 16 : 32;              // lanes per row in the readout epilogue
   static constexpr int AUX_BYTES = 12288;
   static constexpr int FIT = (SMEM_LIMIT - 1024 - Y_BYTES - AUX_BYTES) / STAGE_BYTES;
@@ -82,16 +83,21 @@ struct FwdParams {
   int* overflow;                               // tc_status[0]
   int64_t n_rxn;
   int depth, H, num_k, act, n_tiles, tiles_per_cluster;
+  int fast;                                    // 1: single-pass fp16 (hi halves only), the "fast" precision mode
+  long long* dbg;                              // optional [n_cta][MAX_TPC * MAX_LAYERS][4] clock64 stamps (debug)
 };
 
 struct TileAux {                // per tile of the group: packed neighbour descriptors (built once, used by every layer)
   int32_t info[8];
-  uint2 nbr_b[TM];              // bond row j: first NBR in-bonds of src(j), one byte each (tile-local row ids)
-  uint2 nbr_a[TM];              // atom row v: first NBR in-bonds of v
-  uint16_t pb_b[TM];            // CSR offset of the row's full neighbour list (degrees > NBR)
+  // bond row j: the in-bonds of src(j) EXCEPT the reverse bond j^1 (GNN.py:141 adds it and subtracts it again), atom row
+  // v: the in-bonds of v -- tile-local row ids, one byte each, ascending bond id, unused slots = ZROW
+  uint2 nbr_b[TM];
+  uint2 nbr_a[TM];
+  uint16_t pb_b[TM];            // CSR offset of the row's full in-bond list (rows with more than NBR neighbours)
   uint16_t pb_a[TM];
-  uint8_t deg_b[TM];
-  uint8_t deg_a[TM];
+  uint8_t cnt_b[TM];            // neighbours of the row (bond rows: reverse excluded)
+  uint8_t cnt_a[TM];
+  uint8_t full_b[TM];           // length of the full CSR list behind pb_b
   uint8_t idx_l[TM];            // tile-local bond ids grouped by target atom
   float tat[TM];                // readout: per-atom dot with w_ffn
   int32_t ticket;
@@ -103,6 +109,7 @@ struct Aux {
   uint64_t tmem_empty[2];
   uint64_t ready[MAX_TPC];      // tile j's operand of the next layer is complete in every CTA of the cluster
   uint32_t tmem_base;
+  alignas(16) float bias_s[2][256];   // bias slice of the item being drained (double-buffered by accumulator slot)
   TileAux t[MAX_TPC];
 };
 static_assert(sizeof(Aux) <= 12288, "Aux too large");
@@ -122,17 +129,33 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
+// sum of the staged rows a packed descriptor names: slots 0..3 unconditionally (unused slots point at the zero row: no
+// branches, four independent loads), slots 4..7 only for rows with more than four neighbours
 template <int CHP>
-__device__ __forceinline__ void gather_rows(const float* y_s, const uint8_t* idx_l, uint2 nb, int deg, int pb, int c,
-                                            float4& acc) {
-#pragma unroll
-  for (int t = 0; t < 4; ++t)
-    if (t < deg) tcg::add4(acc, tcg::ld4(y_s + (int)((nb.x >> (8 * t)) & 0xffu) * CHP + c));
-  if (deg > 4) {
-    const int fast = deg < NBR ? deg : NBR;
-    for (int t = 4; t < fast; ++t) tcg::add4(acc, tcg::ld4(y_s + (int)((nb.y >> (8 * (t - 4))) & 0xffu) * CHP + c));
-    for (int t = NBR; t < deg; ++t) tcg::add4(acc, tcg::ld4(y_s + (int)idx_l[pb + t] * CHP + c));
+__device__ __forceinline__ float4 gather_packed(const float* y_c, uint2 nb, int cnt) {
+  float4 a = tcg::ld4(y_c + (int)(nb.x & 0xffu) * CHP);
+  const float4 v1 = tcg::ld4(y_c + (int)((nb.x >> 8) & 0xffu) * CHP);
+  const float4 v2 = tcg::ld4(y_c + (int)((nb.x >> 16) & 0xffu) * CHP);
+  const float4 v3 = tcg::ld4(y_c + (int)(nb.x >> 24) * CHP);
+  tcg::add4(a, v1); tcg::add4(a, v2); tcg::add4(a, v3);
+  if (cnt > 4) {
+    const float4 v4 = tcg::ld4(y_c + (int)(nb.y & 0xffu) * CHP);
+    const float4 v5 = tcg::ld4(y_c + (int)((nb.y >> 8) & 0xffu) * CHP);
+    const float4 v6 = tcg::ld4(y_c + (int)((nb.y >> 16) & 0xffu) * CHP);
+    const float4 v7 = tcg::ld4(y_c + (int)(nb.y >> 24) * CHP);
+    tcg::add4(a, v4); tcg::add4(a, v5); tcg::add4(a, v6); tcg::add4(a, v7);
   }
+  return a;
+}
+// rows with more than NBR neighbours (rare: an atom with ten or more bonds): walk the CSR list, skipping row `skip`
+template <int CHP>
+__device__ __forceinline__ float4 gather_list(const float* y_c, const uint8_t* idx_l, int pb, int n, int skip) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < n; ++t) {
+    const int k = idx_l[pb + t];
+    if (k != skip) tcg::add4(a, tcg::ld4(y_c + k * CHP));
+  }
+  return a;
 }
 
 template <int BN_, bool RELU>
@@ -200,20 +223,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     for (int r = threadIdx.x; r < ecount + acount; r += THREADS) {
       const bool bond = r < ecount;
       const int a = bond ? __ldg(p.src + ebase + r) : abase + (r - ecount);
+      const int skip = bond ? (r ^ 1) : -1;
       const int pb = __ldg(p.in_ptr + a), pe = __ldg(p.in_ptr + a + 1);
-      uint32_t w[2] = {0u, 0u};
-      for (int t = 0; t < NBR && pb + t < pe; ++t)
-        w[t >> 2] |= (uint32_t)((__ldg(p.in_idx + pb + t) - ebase) & 0xff) << (8 * (t & 3));
-      const int dg = pe - pb > 255 ? 255 : pe - pb;
+      uint32_t w[2] = {0x80808080u, 0x80808080u};             // ZROW in every slot
+      int cnt = 0;
+      for (int t = pb; t < pe; ++t) {
+        const int k = __ldg(p.in_idx + t) - ebase;
+        if (k == skip) continue;
+        if (cnt < NBR) w[cnt >> 2] = (w[cnt >> 2] & ~(0xffu << (8 * (cnt & 3)))) | ((uint32_t)(k & 0xff) << (8 * (cnt & 3)));
+        ++cnt;
+      }
       if (bond) {
-        ta.nbr_b[r] = make_uint2(w[0], w[1]); ta.pb_b[r] = (uint16_t)(pb - ebase); ta.deg_b[r] = (uint8_t)dg;
+        ta.nbr_b[r] = make_uint2(w[0], w[1]); ta.pb_b[r] = (uint16_t)(pb - ebase);
+        ta.cnt_b[r] = (uint8_t)(cnt > 255 ? 255 : cnt); ta.full_b[r] = (uint8_t)(pe - pb > 255 ? 255 : pe - pb);
       } else {
         const int v = r - ecount;
-        ta.nbr_a[v] = make_uint2(w[0], w[1]); ta.pb_a[v] = (uint16_t)(pb - ebase); ta.deg_a[v] = (uint8_t)dg;
+        ta.nbr_a[v] = make_uint2(w[0], w[1]); ta.pb_a[v] = (uint16_t)(pb - ebase); ta.cnt_a[v] = (uint8_t)(cnt > 255 ? 255 : cnt);
       }
     }
     for (int v = threadIdx.x; v < TM; v += THREADS) ta.tat[v] = 0.f;
   }
+  for (int k = threadIdx.x; k < CHP; k += THREADS) y_s[ZROW * CHP + k] = 0.f;
   __syncthreads();
 
   if (warp == 0) {
@@ -230,16 +260,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           umma::mbar_wait(umma::smem_u32(&aux->empty[s]), ph ^ 1u);
           const uint32_t full = umma::smem_u32(&aux->full[s]);
           const uint32_t st = base + s * STAGE_BYTES;
-          umma::mbar_arrive_expect_tx(full, STAGE_BYTES);
+          umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
           umma::tma_load_2d(&p.tmB_hi[l], full, st + 2 * A_BYTES, kc * BK, n0);
-          umma::tma_load_2d(&p.tmB_lo[l], full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+          if (!p.fast) umma::tma_load_2d(&p.tmB_lo[l], full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
           if (kc == 0 && l > 0) {
             // the S slices of this tile's previous layer have been stored (every CTA of the cluster arrived)
             umma::mbar_wait_cluster(umma::smem_u32(&aux->ready[j]), (uint32_t)(l - 1) & 1u);
             umma::fence_proxy_async();
+            if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) + i * 4 + 3] = clock64();
           }
           umma::tma_load_2d(&p.tmA_hi[buf], full, st, kc * BK, tile * TM);
-          umma::tma_load_2d(&p.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
+          if (!p.fast) umma::tma_load_2d(&p.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
         }
       }
     }
@@ -270,7 +301,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           for (int ks = 0; ks < BK / 16; ++ks) {
             if (ks >= ksteps) break;
             const uint64_t adv = (uint64_t)(ks * 32 >> 4);
-            if (C::CAT) {
+            if (p.fast) {
+              umma::mma_f16_ss(acc, da_hi + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+            } else if (C::CAT) {
               umma::mma_f16_ss(acc, da_hi + adv, db_hi + adv, idesc_cat, (kc | ks) ? 1u : 0u);
               umma::mma_f16_ss(acc, da_lo + adv, db_hi + adv, idesc, 1u);
             } else {
@@ -289,6 +322,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - 4, et = (int)threadIdx.x - 128;
     const int q = warp & 3, grp = ew >> 2;                          // TMEM lane quarter of this warp, column-group phase
+    // bond layers: flat unit mapping -- unit u = (row u / UPR, float4 column group u % UPR); thread et owns the units
+    // et, et + EPI_THREADS, ... of every chunk (SLOTS of them)
+    constexpr int SLOTS = (TM * UPR + EPI_THREADS - 1) / EPI_THREADS;
+    // readout: LPR lanes per atom row; the same lanes own atom v in every chunk
+    constexpr int LPR = C::LPR, RPW = 32 / LPR;
+    constexpr int RSLOTS = (TM + EPI_WARPS * RPW - 1) / (EPI_WARPS * RPW);
+    constexpr int RPF = RSLOTS < 6 ? RSLOTS : 6;                    // readout rows whose Q' operand is requested ahead
+    constexpr int NOP = SLOTS > RPF ? SLOTS : RPF;
+    const int sub = lane / LPR, hl = lane % LPR;
+    int rk[SLOTS], ck[SLOTS];                                       // this thread's units: the same in every chunk / item
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int u = et + k * EPI_THREADS;
+      rk[k] = u / UPR;
+      ck[k] = 4 * (u - rk[k] * UPR);
+    }
+    long long* dbg = p.dbg ? p.dbg + (int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) : nullptr;
+    // h_0 and Q' (outputs of the previous kernels of this forward) are requested by these threads directly, possibly
+    // before the producer's first load has landed: every epilogue thread orders itself behind the previous grids
+    umma::grid_dep_wait();
     for (int i = 0; i < n_items; ++i) {
       const int j = i % nt, l = i / nt;
       const uint32_t slot = (uint32_t)i & 1u;
@@ -298,11 +351,42 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const int ecount = ta.info[1], abase = ta.info[2], acount = ta.info[3];
       const float us = __ldg(p.unscale + 1 + l);
       const float skip = (!readout && p.skip[l]) ? __ldg(p.skip[l]) : 1.f;
-      const float* bias = readout ? nullptr : p.bias[l];
       __half* o_hi = p.o_hi[(l + 1) & 1];
       __half* o_lo = p.o_lo[(l + 1) & 1];
+      float* bias_s = aux->bias_s[slot];
+      if (!readout) {
+        for (int k = et; k < BN; k += EPI_THREADS) bias_s[k] = n0 + k < H ? __ldg(p.bias[l] + n0 + k) : 0.f;
+      } else {
+        for (int k = et; k < BN; k += EPI_THREADS) bias_s[k] = n0 + k < H ? __ldg(p.w_ffn + n0 + k) : 0.f;
+      }
+      // fp32 operand of the epilogue (h0 rows of a bond layer, Q' rows of the readout) for chunk 0: requested before the
+      // accumulator is ready, so its L2 latency hides behind the MMAs; later chunks are requested one chunk ahead
+      float4 opnd[NOP];
+      auto request = [&](int ch, float4 (&dst)[NOP]) {
+        const int ncol0 = n0 + ch * CH;
+        if (!readout) {
+#pragma unroll
+          for (int k = 0; k < SLOTS; ++k) {
+            const int n = ncol0 + ck[k];
+            dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rk[k] < ecount && n < H)
+              dst[k] = __ldcg(reinterpret_cast<const float4*>(p.h0 + ((int64_t)tile * TM + rk[k]) * H + n));
+          }
+        } else {
+          const int n = ncol0 + 4 * hl;
+#pragma unroll
+          for (int k = 0; k < RPF; ++k) {
+            const int v = ew * RPW + sub + k * EPI_WARPS * RPW;
+            dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < acount && hl < UPR && n < H)
+              dst[k] = __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
+          }
+        }
+      };
+      request(0, opnd);
       umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
       umma::tc_fence_after_sync();
+      if (dbg && et == 0) dbg[i * 4 + 0] = clock64();
       const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
       float vmax = 0.f;
 #pragma unroll 1
@@ -313,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           for (int cc = grp * 8; cc < CH; cc += 8 * (EPI_WARPS / 4)) {
             float v[8];
             umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v);
-            if (C::CAT) {
+            if (C::CAT && !p.fast) {
               float v2[8];
               umma::tmem_ld_x8(acc + (uint32_t)(BN + ch * CH + cc), v2);
               umma::tmem_ld_wait();
@@ -332,62 +416,58 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           __syncwarp();
           if (lane == 0) umma::mbar_arrive(umma::smem_u32(&aux->tmem_empty[slot]));
         }
+        float4 cur[NOP];
+#pragma unroll
+        for (int k = 0; k < NOP; ++k) cur[k] = opnd[k];
+        if (NCH > 1 && ch + 1 < NCH) request(ch + 1, opnd);        // next chunk's operand: in flight during this chunk's gather
         umma::named_bar_sync(2, EPI_THREADS);                      // staging rows complete
 
         const int ncol0 = n0 + ch * CH;                            // first global column of this chunk
         if (!readout) {
-          // bond layer: flat unit mapping (unit = one float4 column group of one bond row), two units in flight
-          const int units = ecount * UPR;
-#pragma unroll 1
-          for (int u0 = et; u0 < units; u0 += 2 * EPI_THREADS) {
-            int r[2], c[2], n[2];
-            bool on[2];
-            float4 h0v[2], b4[2], accv[2];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int u = u0 + k * EPI_THREADS;
-              r[k] = u / UPR;
-              c[k] = 4 * (u - r[k] * UPR);
-              n[k] = ncol0 + c[k];
-              on[k] = u < units && n[k] < H;
-              if (!on[k]) r[k] = 0;
-              h0v[k] = b4[k] = accv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (on[k]) {
-                h0v[k] = __ldcg(reinterpret_cast<const float4*>(p.h0 + ((int64_t)tile * TM + r[k]) * H + n[k]));
-                b4[k] = ldg4(bias + n[k]);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              if (on[k]) gather_rows<CHP>(y_s, ta.idx_l, ta.nbr_b[r[k]], (int)ta.deg_b[r[k]], (int)ta.pb_b[r[k]], c[k], accv[k]);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              if (!on[k]) continue;
-              const float4 yr = tcg::ld4(y_s + (r[k] ^ 1) * CHP + c[k]);
+          for (int k = 0; k < SLOTS; ++k) {
+            const int r = rk[k], c = ck[k], n = ncol0 + c;
+            if (r < ecount && n < H) {
+              const int cnt = ta.cnt_b[r];
+              const float4 a4 = cnt <= NBR ? gather_packed<CHP>(y_s + c, ta.nbr_b[r], cnt)
+                                           : gather_list<CHP>(y_s + c, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
+              const float4 b4 = tcg::ld4(bias_s + ch * CH + c);
               float4 z;
-              z.x = accv[k].x - yr.x + b4[k].x + skip * h0v[k].x;
-              z.y = accv[k].y - yr.y + b4[k].y + skip * h0v[k].y;
-              z.z = accv[k].z - yr.z + b4[k].z + skip * h0v[k].z;
-              z.w = accv[k].w - yr.w + b4[k].w + skip * h0v[k].w;
-              const int64_t orow = (int64_t)tile * TM + r[k];
-              vmax = fmaxf(vmax, act_split_store<RELU>(z, p.act, o_hi + orow * p.ldo + n[k], o_lo + orow * p.ldo + n[k]));
+              z.x = a4.x + b4.x + skip * cur[k].x;
+              z.y = a4.y + b4.y + skip * cur[k].y;
+              z.z = a4.z + b4.z + skip * cur[k].z;
+              z.w = a4.w + b4.w + skip * cur[k].w;
+              const int64_t orow = (int64_t)tile * TM + r;
+              z.x = tcg::act_t<RELU>(z.x, p.act); z.y = tcg::act_t<RELU>(z.y, p.act);
+              z.z = tcg::act_t<RELU>(z.z, p.act); z.w = tcg::act_t<RELU>(z.w, p.act);
+              vmax = fmaxf(vmax, tcg::amax4(z));
+              if (p.fast) {
+                const __half2 h01 = __floats2half2_rn(z.x, z.y), h23 = __floats2half2_rn(z.z, z.w);
+                uint2 ph;
+                ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(o_hi + orow * p.ldo + n) = ph;
+              } else {
+                tcg::store_split4(z, 1.f, o_hi + orow * p.ldo + n, o_lo + orow * p.ldo + n);
+              }
             }
           }
         } else {
-          // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns.
-          // LPR lanes per atom row (the same lanes own atom v in every chunk: the += below is race-free and ordered)
-          constexpr int LPR = C::LPR, RPW = 32 / LPR;
-          const int sub = lane / LPR, hl = lane % LPR;
+          // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
           const int c = 4 * hl, n = ncol0 + c;
           const bool lane_on = hl < UPR && n < H;
-          float4 wf4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (lane_on) wf4 = ldg4(p.w_ffn + n);
-          for (int v = ew * RPW + sub; v < ((acount + RPW - 1) / RPW) * RPW; v += EPI_WARPS * RPW) {
+          const float4 wf4 = lane_on ? tcg::ld4(bias_s + ch * CH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < RSLOTS; ++k) {
+            const int v = ew * RPW + sub + k * EPI_WARPS * RPW;
+            if (k * EPI_WARPS * RPW >= acount) break;              // warp-uniform: no row of this step exists
             const bool row_on = v < acount;
             float t = 0.f;
             if (lane_on && row_on) {
-              float4 a4 = __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
-              gather_rows<CHP>(y_s, ta.idx_l, ta.nbr_a[v], (int)ta.deg_a[v], (int)ta.pb_a[v], c, a4);
+              float4 a4 = k < RPF ? cur[k < RPF ? k : 0]
+                                  : __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
+              const int cnt = ta.cnt_a[v];
+              tcg::add4(a4, cnt <= NBR ? gather_packed<CHP>(y_s + c, ta.nbr_a[v], cnt)
+                                       : gather_list<CHP>(y_s + c, ta.idx_l, (int)ta.pb_a[v], cnt, -1));
               t = tcg::act_t<RELU>(a4.x, p.act) * wf4.x;
               t = fmaf(tcg::act_t<RELU>(a4.y, p.act), wf4.y, t);
               t = fmaf(tcg::act_t<RELU>(a4.z, p.act), wf4.z, t);
@@ -399,6 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           }
         }
       }
+      if (dbg && et == 0) dbg[i * 4 + 1] = clock64();
 
       if (!readout) {
         // this CTA's slice of h_{l+1} is stored: make it visible to the peers' TMA loads, then tell every CTA of the cluster
@@ -440,6 +521,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           if (et == 0) p.tile_counter[tile] = 0;                    // ready for the next forward
         }
       }
+      if (dbg && et == 0) dbg[i * 4 + 2] = clock64();
     }
   }
 

@@ -110,6 +110,7 @@ struct TcGemmParams {
   float* gunscale_out;            // 1 / scale of the produced operand, for the weight-gradient GEMMs
   float* dz0_out;               // INIT_BWD: dz_0 [E, H] fp32 in bond order (bond-feature weight gradient)
   long long* dbg;               // optional [n_cta][8] clock64 stamps of the kernel phases (debug)
+  int fast;                     // 1: single-pass fp16 (only the hi halves are loaded and multiplied): "fast" precision mode
 };
 
 struct Aux {                    // small per-CTA shared state, lives after the pipeline buffers
@@ -281,11 +282,13 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
         umma::mbar_wait(umma::smem_u32(&aux->empty[s]), ph ^ 1u);
         const uint32_t full = umma::smem_u32(&aux->full[s]);
         const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
-        umma::mbar_arrive_expect_tx(full, STAGE_BYTES);
+        umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
         umma::tma_load_2d(&p.tmA_hi, full, st, kc * BK, tile * TM);
-        umma::tma_load_2d(&p.tmA_lo, full, st + A_BYTES, kc * BK, tile * TM);
         umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
-        umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+        if (!p.fast) {
+          umma::tma_load_2d(&p.tmA_lo, full, st + A_BYTES, kc * BK, tile * TM);
+          umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+        }
       }
       __syncwarp();
     }
@@ -312,7 +315,9 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
         for (int ks = 0; ks < BK / 16; ++ks) {
           if (ks >= ksteps) break;
           const uint64_t adv = (uint64_t)(ks * 32 >> 4);          // 16 fp16 = 32 bytes along K inside the swizzle row
-          if (C::CAT) {
+          if (p.fast) {
+            umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+          } else if (C::CAT) {
             // cols [0,BN) += A_hi B_hi^T, cols [BN,2BN) += A_hi B_lo^T (one instruction), then cols [0,BN) += A_lo B_hi^T
             umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc_cat, (kc | ks) ? 1u : 0u);
             umma::mma_f16_ss(tmem, da_lo + adv, db_hi + adv, idesc, 1u);
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
       for (int cc = grp * 8; cc < CH; cc += 8 * (NWARPS / 4)) {
         float v[8];
         umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CH + cc), v);
-        if (C::CAT) {
+        if (C::CAT && !p.fast) {
           float v2[8];
           umma::tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + ch * CH + cc), v2);
           umma::tmem_ld_wait();

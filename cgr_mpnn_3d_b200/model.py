@@ -93,6 +93,9 @@ class GNN(nn.Module):
         self.pooling_fn = pooling_fn
         self.use_learnable_skip = use_learnable_skip
         self.engine = "auto"
+        #: "fp32": FP16x3-split tensor-core GEMMs, 1e-4 parity with the reference (2e-6 of fp64).  "fast": single-pass
+        #: fp16 operands in the inference kernels (one MMA per k-step instead of three), ~1e-3; training is unaffected.
+        self.precision = "fp32"
         #: "latency": a lone forward gets the one-CTA-per-SM kernels; "throughput": the caller pipelines several
         #: forwards over CUDA streams (bench, predict_stream) and wants the two-CTAs-per-SM configuration
         self.tile_policy = "latency"
@@ -209,6 +212,12 @@ class GNN(nn.Module):
                       "returned NaN energies unless it was re-run, and this weight version now runs on the exact-fp32 "
                       "engine" % ("an input feature" if bits & 2 else "an activation"), RuntimeWarning, stacklevel=3)
 
+    def _fast(self) -> bool:
+        prec = getattr(self, "precision", "fp32")
+        if prec not in ("fp32", "fast"):
+            raise ValueError("model.precision must be 'fp32' (parity mode) or 'fast' (single-pass fp16 inference)")
+        return prec == "fast"
+
     def _fused_ok(self, plan) -> bool:
         """The fused tile kernels need a hidden size divisible by 4, <= 32 bond features and reactions that fit a
         128-bond tile; other graphs (drug-like stress shape) run layer-wise with tensor-core GEMMs."""
@@ -271,6 +280,7 @@ class GNN(nn.Module):
         dps = [float(p) if self.training else 0.0 for p in self.dropout_ps[: self.depth]]
         train_flag = needs_grad or any(p > 0 for p in dps)
         engine = _lib.ENGINE_SIMT if force_simt else self._engine_id(plan, train_flag)
+        fast = self._fast() and engine == _lib.ENGINE_TC and not train_flag
         empty_i = torch.empty(0, dtype=torch.int32, device=dev)
         fused_train = False
         if engine == _lib.ENGINE_TC:
@@ -311,7 +321,8 @@ class GNN(nn.Module):
         else:
             out = ops.gnn_forward_impl(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr,
                                        [p.detach() for p in params], self.depth, _act_id(self.activation_fn),
-                                       bool(self.use_learnable_skip), dps, train_flag, seed, engine, tile_info,
+                                       bool(self.use_learnable_skip), dps, train_flag, seed,
+                                       _lib.ENGINE_TC_FAST if (fast and n_tiles > 0) else engine, tile_info,
                                        n_tiles, tc_status, tc_w, x_hi, x_lo, throughput, fused_train)[0]
         self.__dict__["_last_plan"] = plan if (engine == _lib.ENGINE_TC and n_tiles > 0) else None
         self.__dict__["_last_engine"] = engine
@@ -348,7 +359,7 @@ class GNN(nn.Module):
         """ctypes parameter block + prepared tcgen05 weights, cached per parameter version."""
         from . import ops
         params = self._param_list()
-        key = tuple((p.data_ptr(), p._version) for p in params) + (fa, fb)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (fa, fb, self._fast())
         cache = self.__dict__.get("_host_ctx_cache")
         if cache is not None and cache[0] == key:
             return cache[1], cache[2]
@@ -362,6 +373,7 @@ class GNN(nn.Module):
         ctx.params.tc_weights = tc_w.data_ptr()
         ctx._keep = (dparams, tc_w)
         ctx.params.tc_throughput = 0
+        ctx.params.tc_fast = int(self._fast())
         self.__dict__["_host_ctx_cache"] = (key, ctx, dev)
         return ctx, dev
 

@@ -83,6 +83,7 @@ def _ctx_cached(role: str, params: Sequence[Tensor], depth: int, act: int, use_s
         _CTX_CACHE[key] = ctx
     ctx.params.tc_weights = None
     ctx.params.tc_throughput = 0
+    ctx.params.tc_fast = 0
     return ctx
 
 
@@ -145,6 +146,11 @@ def gnn_forward_impl(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_
     if tc_weights.numel() > 0:
         ctx.params.tc_weights = tc_weights.data_ptr()
     ctx.params.tc_throughput = int(tc_throughput)
+    if engine == _lib.ENGINE_TC_FAST:        # "fast" precision mode of the tcgen05 engine: inference only
+        if training:
+            raise RuntimeError("precision='fast' is an inference mode; training runs in the fp32-parity mode")
+        ctx.params.tc_fast = 1
+        engine = _lib.ENGINE_TC
     H = ctx.hidden
     g = _graph_struct(x, edge_attr, src, dst, in_ptr, in_idx, atom_ptr, tile_info, n_tiles, tc_status, x_hi, x_lo)
     n, e, b = g.n_atoms, g.n_bonds, g.n_rxn

@@ -62,7 +62,10 @@ typedef struct cgr_params {
   const float* host_dropout_p;
   const void* tc_weights;    /* optional: buffer filled by cgr_tc_prepare_weights (NULL: prepared per call) */
   int32_t tc_throughput;     /* tcgen05 engine: 1 = the caller pipelines several forwards over streams, prefer the
-                                two-CTAs-per-SM kernel configuration; 0 = optimise the latency of a lone forward */
+                                wide-slice / two-tiles-per-cluster configuration; 0 = optimise the latency of a lone forward */
+  int32_t tc_fast;           /* tcgen05 engine, inference: 1 = "fast" precision mode -- single-pass fp16 operands (one MMA
+                                per k-step instead of the three of the FP16x3 split), ~1e-3 instead of 2e-6 of fp64; NOT
+                                the parity mode, reported separately.  0 = fp32-parity mode (default) */
 } cgr_params_t;
 
 /* gradient buffers, same shapes as cgr_params (written, not accumulated) */
