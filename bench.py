@@ -73,6 +73,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over")
     ap.add_argument("--coalesce", type=int, default=8,
                     help="host batches predict_stream submits together in the e2e leg (1 = one submission per batch)")
+    ap.add_argument("--policy", default="auto", choices=["auto", "latency", "throughput"],
+                    help="kernel configuration of the pipelined region (auto: throughput when several streams are used)")
     ap.add_argument("--no-store", dest="store", action="store_false", default=True)
     ap.add_argument("--no-train", dest="train", action="store_false", default=True)
     ap.add_argument("--no-collate", dest="collate", action="store_false", default=True)
@@ -318,7 +320,7 @@ def main():
     small = B <= 1024 and cfg["kind"] == "t1x"
     model = build_model(cfg, engine, dev, args.precision).eval()
     n_streams_req = max(1, args.streams) if (small and not args.no_graph) else 1
-    model.tile_policy = "throughput" if n_streams_req > 1 else "latency"
+    model.tile_policy = ("throughput" if n_streams_req > 1 else "latency") if args.policy == "auto" else args.policy
     lat_model = build_model(cfg, engine, dev, args.precision).eval()      # latency configuration: a lone forward
     if args.pool:
         n_pool = max(2, args.pool)

@@ -64,3 +64,47 @@ def build_model(meta, state=None, device="cuda", engine="simt", dropout_ps=None)
                 p.fill_(1.0 - 0.15 * l + 0.05 * (l % 2))
     m.engine = engine
     return m.to(device)
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's training loop, restated for the tests (test infrastructure, like the oracle): what
+# ``RxnGraphTrainer.train()`` does (reference training/trainer.py:185-217 with _train_epoch :124-155 and _val_epoch
+# :157-183), over the test-only ``torch_geometric.loader.DataLoader`` stand-in (tests/_pyg_shim).  Pinned against the
+# UNMODIFIED trainer by tests/golden/trainer_loop.npz (tests/golden/make_trainer_golden.py).
+def run_reference_training_loop(model, optimizer, loss_fn, lr_scheduler, train_data, val_data, device, num_epochs,
+                                batch_size, save_path, val_frequency=5):
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_pyg_shim")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    import torch_geometric as tg
+    train_loader = tg.loader.DataLoader(dataset=train_data, batch_size=batch_size, shuffle=True)     # trainer.py:105-111
+    val_loader = tg.loader.DataLoader(dataset=val_data, batch_size=batch_size, shuffle=False)        # trainer.py:112-118
+    hist = {"train_losses": [], "val_losses": []}
+    best = np.inf
+    for epoch in range(num_epochs):                                                                  # trainer.py:195
+        model.train()                                                                                # trainer.py:135
+        total = 0.0
+        for data in train_loader:                                                                    # trainer.py:138-147
+            data = data.to(device)
+            optimizer.zero_grad()
+            pred = model(data)
+            loss = loss_fn(pred, data.y)
+            loss.backward()
+            optimizer.step()
+            total += loss_fn(pred, data.y).item()
+        hist["train_losses"].append(float(np.sqrt(total / len(train_loader.dataset))))               # trainer.py:149
+        if epoch % val_frequency == 0 or epoch == num_epochs - 1:                                    # trainer.py:200
+            model.eval()                                                                             # trainer.py:167
+            total = 0.0
+            with torch.no_grad():
+                for data in val_loader:                                                              # trainer.py:170-175
+                    data = data.to(device)
+                    total += loss_fn(model(data), data.y).item()
+            val = float(np.sqrt(total / len(val_loader.dataset)))                                    # trainer.py:177
+            hist["val_losses"].append(val)
+            if val < best:                                                                           # trainer.py:205-208
+                best = val
+                torch.save(model, save_path)
+        lr_scheduler.step()                                                                          # trainer.py:212
+    return hist
