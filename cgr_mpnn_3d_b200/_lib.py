@@ -76,6 +76,11 @@ class CgrAdamTensor(C.Structure):
     ]
 
 
+class CgrFeatureTables(C.Structure):
+    _fields_ = [("symbol_z", C.c_int16 * 11), ("degrees", C.c_int16 * 6), ("charges", C.c_int16 * 5),
+                ("num_hs", C.c_int16 * 5), ("hybridizations", C.c_int16 * 5)]
+
+
 class CgrSaved(C.Structure):
     _fields_ = [
         ("h_all", C.c_void_p), ("m_all", C.c_void_p), ("z_all", C.c_void_p), ("s", C.c_void_p),
@@ -124,6 +129,12 @@ PROTOTYPES = {
     "cgr_conv_fwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I64, _I64, _I32, _V]),
     "cgr_readout_fwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I32, _V, _V, _V, _V, _V, _I64, _I64, _I64,
                                   _I32, _I32, _V]),
+    "cgr_stage_bwd_workspace": (_SZ, [_I64, _I64, _I32, _I32, _I32]),
+    "cgr_readout_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _I32, _V, _V, _V, _V, _V, _V, _V, _V, _V, _I64, _I64,
+                                  _I64, _I32, _I32, _V, _SZ, _V]),
+    "cgr_bond_update_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _I32, C.c_float, C.c_uint64, C.c_uint32,
+                                      _I32, _V, _V, _V, _V, _V, _I32, _I64, _I64, _I32, _V, _SZ, _V]),
+    "cgr_edge_init_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _I32, _V, _V, _I64, _I64, _I32, _I32, _I32, _V, _SZ, _V]),
     "cgr_forward_workspace": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph), _I32, _I32]),
     "cgr_gnn_forward": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrGraph), _V, C.POINTER(CgrSaved), _I32,
                                   C.c_uint64, _I32, _V, _SZ, _V]),
@@ -142,6 +153,7 @@ PROTOTYPES = {
     "cgr_tc_linear_workspace": (_SZ, [_I64, _I64, _I64]),
     "cgr_tc_linear": (C.c_int, [_V, _I64, _I64, _V, _I64, _V, _V, _V, _SZ, _V]),
     "cgr_mse_sum_fwd_bwd": (C.c_int, [_V, _V, _I64, _V, _V, _V]),
+    "cgr_featurize_cgr": (C.c_int, [C.POINTER(CgrFeatureTables), _V, _V, _V, _V, _I64, _V, _V, _I64, _V, _I64, _V, _V]),
     "cgr_launch_count": (C.c_longlong, []),
     "cgr_profile_enable": (C.c_int, [C.c_int]),
     "cgr_profile_count": (C.c_int, []),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcgr_b200.so")
 STAMP = os.path.join(HERE, ".libcgr_b200.stamp")
-SOURCES = ["api.cu", "collate.cu", "simt.cu", "tc.cu", "optim.cu"]
+SOURCES = ["api.cu", "collate.cu", "simt.cu", "tc.cu", "optim.cu", "featurize.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -364,6 +364,142 @@ extern "C" int cgr_readout_fwd(const float* h, const float* x, const int32_t* in
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage-level backward entry points (SIMT fp32 engine): the explicit mirror of autograd for each stage
+// ------------------------------------------------------------------------------------------------
+namespace {
+size_t stage_bwd_partial_floats(int64_t H, int64_t E, int64_t N, int64_t fa, int64_t fb) {
+  size_t m = 0;
+  auto upd = [&](int64_t M_, int64_t N_, int64_t K_) {
+    const int s = simt_splitk_choose(M_, N_, K_);
+    if (s > 1) { const size_t f = (size_t)s * M_ * N_; if (f > m) m = f; }
+  };
+  upd(H, H, E); upd(H, fa, N); upd(H, H, N); upd(H, fb > 0 ? fb : 1, E);
+  return m;
+}
+}  // namespace
+
+extern "C" size_t cgr_stage_bwd_workspace(int64_t n_atoms, int64_t n_bonds, int32_t fa, int32_t fb, int32_t hidden) {
+  const size_t H = hidden, E = n_bonds, N = n_atoms;
+  return 2 * fbytes(N * H) + 2 * fbytes(E * H) + fbytes(stage_bwd_partial_floats(H, E, N, fa, fb)) +
+         fbytes(simt_colsum_workspace(E > N ? E : N, (int)H)) + 256;
+}
+
+extern "C" int cgr_readout_bwd(const float* grad_out, const float* x, const int32_t* in_ptr, const int32_t* in_idx,
+                               const int32_t* atom_ptr, const int32_t* dst, const float* w_e2n, const float* w_ffn,
+                               int32_t act, const float* s, const float* hv, const float* zv, const float* pooled,
+                               float* gw_e2n, float* gb_e2n, float* gw_ffn, float* gb_ffn, float* dh, int64_t n_atoms,
+                               int64_t n_bonds, int64_t n_rxn, int32_t fa, int32_t hidden, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  CGR_CHECK_ARG(grad_out && x && in_ptr && in_idx && atom_ptr && dst && w_e2n && w_ffn && s && hv && pooled && gw_e2n &&
+                    gb_e2n && gw_ffn && gb_ffn && dh, "cgr_readout_bwd: null pointer");
+  CGR_CHECK_ARG(act == CGR_ACT_RELU || zv, "cgr_readout_bwd: zv (pre-activations) required for silu / gelu");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_stage_bwd_workspace(n_atoms, n_bonds, fa, 0, hidden), "cgr_readout_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t H = hidden, N = n_atoms, E = n_bonds, B = n_rxn;
+  (void)in_ptr; (void)in_idx;
+  Carver ws(workspace, workspace_bytes);
+  float* dzv = ws.floats(N * H);
+  float* ds = ws.floats(N * H);
+  float* partial = ws.floats(stage_bwd_partial_floats(H, E, N, fa, 0));
+  float* csws = ws.floats(simt_colsum_workspace(E > N ? E : N, (int)H));
+  if (!ws.ok) { cgr_set_error("cgr_readout_bwd: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  GemmCtx c;
+  c.partial = partial;
+  GemmEpilogue none;
+  int rc = simt_ffn_grads(grad_out, pooled, gw_ffn, gb_ffn, B, (int)H, st);                       // GNN.py:110
+  if (rc) return rc;
+  rc = simt_readout_dz(grad_out, atom_ptr, w_ffn, hv, zv, act, dzv, B, N, (int)H, st);            // GNN.py:107
+  if (rc) return rc;
+  rc = simt_colsum(dzv, N, (int)H, gb_e2n, nullptr, nullptr, nullptr, nullptr, true, csws, st);
+  if (rc) return rc;
+  rc = gemm(c, act_opnd(dzv, H, false), x_opnd(x, fa, false), gw_e2n, fa + H, H, fa, N, none, true, st);    // dW_o[:, :fa]
+  if (rc) return rc;
+  rc = gemm(c, act_opnd(dzv, H, false), act_opnd(s, H, false), gw_e2n + fa, fa + H, H, H, N, none, true, st);   // dW_o[:, fa:]
+  if (rc) return rc;
+  rc = gemm(c, act_opnd(dzv, H, true), act_opnd(w_e2n + fa, fa + H, false), ds, H, N, H, H, none, false, st);  // ds = dzv W_os
+  if (rc) return rc;
+  GatherPost np;
+  return simt_expand_dst(ds, dst, dh, E, (int)H, np, st);                                          // dh_d[e] = ds[dst e]
+}
+
+extern "C" int cgr_bond_update_bwd(const float* dh_out, const float* h_out, const float* z, const float* m,
+                                   const float* h0, const int32_t* in_ptr, const int32_t* in_idx, const int32_t* dst,
+                                   const float* w, const float* skip, int32_t act, float dropout_p, uint64_t seed,
+                                   uint32_t layer, int32_t training, float* gw, float* gb, float* gskip, float* dh_in,
+                                   float* dh0_acc, int32_t dh0_first, int64_t n_bonds, int64_t n_atoms, int32_t hidden,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  CGR_CHECK_ARG(dh_out && h_out && m && h0 && in_ptr && in_idx && dst && w && gw && gb && dh_in && dh0_acc,
+                "cgr_bond_update_bwd: null pointer");
+  CGR_CHECK_ARG(act == CGR_ACT_RELU || z, "cgr_bond_update_bwd: z (pre-activations) required for silu / gelu");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_stage_bwd_workspace(n_atoms, n_bonds, 1, 0, hidden), "cgr_bond_update_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t H = hidden, E = n_bonds, N = n_atoms;
+  Carver ws(workspace, workspace_bytes);
+  (void)ws.floats(N * H); (void)ws.floats(N * H);
+  float* dz = ws.floats(E * H);
+  float* dm = ws.floats(E * H);
+  float* partial = ws.floats(stage_bwd_partial_floats(H, E, N, 1, 0));
+  float* csws = ws.floats(simt_colsum_workspace(E > N ? E : N, (int)H));
+  if (!ws.ok) { cgr_set_error("cgr_bond_update_bwd: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  GemmCtx c;
+  c.partial = partial;
+  GemmEpilogue none;
+  // dz = dh_out (.) act'(z) (.) dropout                                                   (GNN.py:100-102)
+  GatherPost gp;
+  gp.mode = 1; gp.act = act; gp.h_next = h_out; gp.z = z;
+  gp.dropout_p = (training && dropout_p > 0.f) ? dropout_p : 0.f; gp.seed = seed; gp.layer = layer;
+  int rc = simt_expand_dst(dh_out, nullptr, dz, E, (int)H, gp, st);
+  if (rc) return rc;
+  // db = sum dz; dskip = sum dz . h0; dh0 (+)= skip * dz                                    (GNN.py:94-97)
+  rc = simt_colsum(dz, E, (int)H, gb, gskip ? h0 : nullptr, gskip, dh0_acc, skip, dh0_first != 0, csws, st);
+  if (rc) return rc;
+  rc = gemm(c, act_opnd(dz, H, false), act_opnd(m, H, false), gw, H, H, H, E, none, true, st);    // dW = dz^T m
+  if (rc) return rc;
+  rc = gemm(c, act_opnd(dz, H, true), act_opnd(w, H, false), dm, H, E, H, H, none, false, st);    // dm = dz W
+  if (rc) return rc;
+  GatherPost np;                                                                                  // GNN.py:134-141 transposed
+  return simt_gather_bonds(dm, dst, in_ptr, in_idx, 1, dh_in, E, (int)H, np, st);                  // dh[k] = sum dm[j^1] - dm[k^1]
+}
+
+extern "C" int cgr_edge_init_bwd(const float* dh0, const float* h0, const float* z0, const float* x,
+                                 const float* edge_attr, const int32_t* in_ptr, const int32_t* in_idx, int32_t act,
+                                 float* gw_init, float* gb_init, int64_t n_atoms, int64_t n_bonds, int32_t fa,
+                                 int32_t fb, int32_t hidden, void* workspace, size_t workspace_bytes, void* stream) {
+  CGR_CHECK_ARG(dh0 && h0 && x && in_ptr && in_idx && gw_init && gb_init, "cgr_edge_init_bwd: null pointer");
+  CGR_CHECK_ARG(fb == 0 || edge_attr, "cgr_edge_init_bwd: edge_attr is null but fb > 0");
+  CGR_CHECK_ARG(act == CGR_ACT_RELU || z0, "cgr_edge_init_bwd: z0 (pre-activations) required for silu / gelu");
+  CGR_CHECK_ARG(workspace_bytes >= cgr_stage_bwd_workspace(n_atoms, n_bonds, fa, fb, hidden), "cgr_edge_init_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t H = hidden, E = n_bonds, N = n_atoms;
+  Carver ws(workspace, workspace_bytes);
+  float* dP = ws.floats(N * H);
+  (void)ws.floats(N * H);
+  float* dz = ws.floats(E * H);
+  (void)ws.floats(E * H);
+  float* partial = ws.floats(stage_bwd_partial_floats(H, E, N, fa, fb));
+  float* csws = ws.floats(simt_colsum_workspace(E > N ? E : N, (int)H));
+  if (!ws.ok) { cgr_set_error("cgr_edge_init_bwd: workspace carve failed"); return CGR_ERR_WORKSPACE; }
+  GemmCtx c;
+  c.partial = partial;
+  GemmEpilogue none;
+  GatherPost gp;                                        // dz0 = dh0 (.) act'(z0)                 (GNN.py:86)
+  gp.mode = 1; gp.act = act; gp.h_next = h0; gp.z = z0;
+  int rc = simt_expand_dst(dh0, nullptr, dz, E, (int)H, gp, st);
+  if (rc) return rc;
+  rc = simt_colsum(dz, E, (int)H, gb_init, nullptr, nullptr, nullptr, nullptr, true, csws, st);
+  if (rc) return rc;
+  if (fb > 0) {                                         // dW_i[:, fa:] = dz0^T ea
+    rc = simt_gemm(dz, H, false, edge_attr, fb, false, gw_init + fa, fa + fb, H, fb, E, none,
+                   simt_splitk_choose(H, fb, E), partial, st);
+    if (rc) return rc;
+  }
+  // dW_i[:, :fa] = dP^T x with dP[v] = sum_{e: src e = v} dz0[e] = sum_{j in in(v)} dz0[j^1]
+  rc = simt_atom_sum(dz, in_ptr, in_idx, 1, dP, N, (int)H, st);
+  if (rc) return rc;
+  return gemm(c, act_opnd(dP, H, false), x_opnd(x, fa, false), gw_init, fa + fb, H, fa, N, none, true, st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // whole network
 // ------------------------------------------------------------------------------------------------
 

@@ -263,10 +263,10 @@ __global__ void __launch_bounds__(256) expand_dst_kernel(const float* __restrict
   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
-  const int64_t v = __ldg(dst + e);
+  const int64_t v = dst ? (int64_t)__ldg(dst + e) : e;       // dst == null: row-wise (dz = ds . fprime)
   for (int c = lane; c < H; c += 32) {
     const int64_t idx = e * H + c;
-    dz[idx] = __ldg(ds + v * H + c) * fprime_at(post, idx);
+    dz[idx] = __ldg(ds + v * H + c) * (post.mode ? fprime_at(post, idx) : 1.f);
   }
 }
 

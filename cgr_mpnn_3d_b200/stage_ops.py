@@ -1,7 +1,7 @@
 """Thin Python wrappers of the stage-level C entry points (one per north-star subsystem).
 
-Used by the parity tests to check each stage against the oracle in isolation, and by
-``DMPNNConv.forward`` when a conv layer is called on its own.  Inference-only (no autograd); the
+Used by the parity tests to check each stage (forward and backward) against the oracle in isolation, and by
+``DMPNNConv.forward`` when a conv layer is called on its own.  No autograd is attached here; the
 differentiable path is the fused ``cgr_b200::gnn_forward`` op.
 """
 from __future__ import annotations
@@ -52,8 +52,8 @@ def bond_update_fwd(h_in, h0, plan: GraphPlan, weight, bias, skip, act: int, dro
     return h_out, m, z
 
 
-def readout_fwd(h, x, plan: GraphPlan, w_e2n, b_e2n, w_ffn, b_ffn, act: int):
-    """reference GNN.py:105-110.  Returns (out, s, hv, pooled)."""
+def readout_fwd(h, x, plan: GraphPlan, w_e2n, b_e2n, w_ffn, b_ffn, act: int, want_z: bool = False):
+    """reference GNN.py:105-110.  Returns (out, s, hv, pooled[, zv])."""
     lib = _lib.load()
     h, x, w_e2n, b_e2n, w_ffn, b_ffn = (_f32(t) for t in (h, x, w_e2n, b_e2n, w_ffn, b_ffn))
     n, fa = x.shape
@@ -62,11 +62,12 @@ def readout_fwd(h, x, plan: GraphPlan, w_e2n, b_e2n, w_ffn, b_ffn, act: int):
     f32 = dict(dtype=torch.float32, device=x.device)
     out, s, hv, pooled = torch.empty(b, **f32), torch.empty((n, H), **f32), torch.empty((n, H), **f32), \
         torch.empty((b, H), **f32)
+    zv = torch.empty((n, H), **f32) if want_z else None
     _lib.check(lib.cgr_readout_fwd(h.data_ptr(), x.data_ptr(), plan.in_ptr.data_ptr(), plan.in_idx.data_ptr(),
                                    plan.atom_ptr.data_ptr(), w_e2n.data_ptr(), b_e2n.data_ptr(), w_ffn.data_ptr(),
-                                   b_ffn.data_ptr(), act, out.data_ptr(), s.data_ptr(), hv.data_ptr(), None,
+                                   b_ffn.data_ptr(), act, out.data_ptr(), s.data_ptr(), hv.data_ptr(), _lib.ptr(zv),
                                    pooled.data_ptr(), n, e, b, fa, H, _stream()), "cgr_readout_fwd")
-    return out, s, hv, pooled
+    return (out, s, hv, pooled, zv) if want_z else (out, s, hv, pooled)
 
 
 def conv_forward(conv, edge_index, edge_attr):
@@ -123,3 +124,74 @@ def mse_sum_loss(pred, y):
     """Drop-in for ``torch.nn.MSELoss(reduction="sum")(pred, y)`` (train.py:120, trainer.py:142) as ONE launch that
     produces the loss and dL/dpred together (``cgr_mse_sum_fwd_bwd``); the target gets no gradient."""
     return _MSESumLoss.apply(pred, y)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage-level backward (explicit mirror of autograd, one call per stage)
+def _bwd_ws(lib, n, e, fa, fb, H, device):
+    nbytes = int(lib.cgr_stage_bwd_workspace(n, e, fa, fb, H))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def readout_bwd(grad_out, x, plan: GraphPlan, w_e2n, w_ffn, act: int, s, hv, pooled, zv=None):
+    """Backward of :func:`readout_fwd`: returns (gw_e2n, gb_e2n, gw_ffn, gb_ffn, dh) with ``dh`` [E, H] the gradient
+    w.r.t. the bond states the readout consumed."""
+    lib = _lib.load()
+    grad_out, x, w_e2n, w_ffn, s, hv, pooled = (_f32(t) for t in (grad_out, x, w_e2n, w_ffn, s, hv, pooled))
+    zv = None if zv is None else _f32(zv)
+    n, fa = x.shape
+    H = hv.shape[1]
+    e, b = plan.n_bonds, plan.n_rxn
+    f32 = dict(dtype=torch.float32, device=x.device)
+    gw, gb, gwf, gbf = torch.empty((H, fa + H), **f32), torch.empty(H, **f32), torch.empty((1, H), **f32), torch.empty(1, **f32)
+    dh = torch.empty((e, H), **f32)
+    ws, nbytes = _bwd_ws(lib, n, e, fa, 0, H, x.device)
+    _lib.check(lib.cgr_readout_bwd(grad_out.data_ptr(), x.data_ptr(), plan.in_ptr.data_ptr(), plan.in_idx.data_ptr(),
+                                   plan.atom_ptr.data_ptr(), plan.dst.data_ptr(), w_e2n.data_ptr(), w_ffn.data_ptr(), act,
+                                   s.data_ptr(), hv.data_ptr(), _lib.ptr(zv), pooled.data_ptr(), gw.data_ptr(),
+                                   gb.data_ptr(), gwf.data_ptr(), gbf.data_ptr(), dh.data_ptr(), n, e, b, fa, H,
+                                   ws.data_ptr(), nbytes, _stream()), "cgr_readout_bwd")
+    return gw, gb, gwf, gbf, dh
+
+
+def bond_update_bwd(dh_out, h_out, m, h0, plan: GraphPlan, weight, skip, act: int, z=None, dropout_p: float = 0.0,
+                    seed: int = 0, layer: int = 0, training: bool = False, dh0_acc=None):
+    """Backward of :func:`bond_update_fwd`: returns (gw, gb, gskip, dh_in, dh0_acc); ``dh0_acc`` accumulates
+    ``skip * dz`` over the layers (pass the previous layer's result to add to it)."""
+    lib = _lib.load()
+    dh_out, h_out, m, h0, weight = (_f32(t) for t in (dh_out, h_out, m, h0, weight))
+    z = None if z is None else _f32(z)
+    skip = None if skip is None else _f32(skip)
+    e, H = dh_out.shape
+    f32 = dict(dtype=torch.float32, device=dh_out.device)
+    gw, gb = torch.empty((H, H), **f32), torch.empty(H, **f32)
+    gskip = torch.empty((), **f32) if skip is not None else None
+    dh_in = torch.empty((e, H), **f32)
+    first = dh0_acc is None
+    if first:
+        dh0_acc = torch.empty((e, H), **f32)
+    ws, nbytes = _bwd_ws(lib, plan.n_atoms, e, 1, 0, H, dh_out.device)
+    _lib.check(lib.cgr_bond_update_bwd(dh_out.data_ptr(), h_out.data_ptr(), _lib.ptr(z), m.data_ptr(), h0.data_ptr(),
+                                       plan.in_ptr.data_ptr(), plan.in_idx.data_ptr(), plan.dst.data_ptr(),
+                                       weight.data_ptr(), _lib.ptr(skip), act, float(dropout_p), seed, layer, int(training),
+                                       gw.data_ptr(), gb.data_ptr(), _lib.ptr(gskip), dh_in.data_ptr(), dh0_acc.data_ptr(),
+                                       int(first), e, plan.n_atoms, H, ws.data_ptr(), nbytes, _stream()),
+               "cgr_bond_update_bwd")
+    return gw, gb, gskip, dh_in, dh0_acc
+
+
+def edge_init_bwd(dh0, h0, x, edge_attr, plan: GraphPlan, act: int, z0=None):
+    """Backward of :func:`edge_init_fwd`: returns (gw_init [H, fa+fb], gb_init [H])."""
+    lib = _lib.load()
+    dh0, h0, x, edge_attr = (_f32(t) for t in (dh0, h0, x, edge_attr))
+    z0 = None if z0 is None else _f32(z0)
+    n, fa = x.shape
+    e, fb = edge_attr.shape
+    H = h0.shape[1]
+    f32 = dict(dtype=torch.float32, device=x.device)
+    gw, gb = torch.empty((H, fa + fb), **f32), torch.empty(H, **f32)
+    ws, nbytes = _bwd_ws(lib, n, e, fa, fb, H, x.device)
+    _lib.check(lib.cgr_edge_init_bwd(dh0.data_ptr(), h0.data_ptr(), _lib.ptr(z0), x.data_ptr(), edge_attr.data_ptr(),
+                                     plan.in_ptr.data_ptr(), plan.in_idx.data_ptr(), act, gw.data_ptr(), gb.data_ptr(), n,
+                                     e, fa, fb, H, ws.data_ptr(), nbytes, _stream()), "cgr_edge_init_bwd")
+    return gw, gb

@@ -152,7 +152,7 @@ int cgr_atom_ptr_from_batch(const int64_t* batch, int64_t n_atoms, int64_t n_rxn
                             int32_t* atom_ptr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * (2)-(4) Stage-level forward entry points (one per north-star subsystem).
+ * (2)-(4) Stage-level forward entry points (one per north-star subsystem; their backward: (5) below).
  * ---------------------------------------------------------------------------------------- */
 
 /* Edge initialisation, GNN.py:85-86: h0[e] = act(W_i [x[src e] || ea[e]] + b_i).
@@ -186,6 +186,40 @@ int cgr_readout_fwd(const float* h, const float* x, const int32_t* in_ptr, const
                     const float* w_ffn, const float* b_ffn, int32_t act, float* out, float* s_out,
                     float* hv_out, float* zv_out, float* pooled_out, int64_t n_atoms,
                     int64_t n_bonds, int64_t n_rxn, int32_t fa, int32_t hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) Stage-level backward entry points: the explicit mirror of autograd for each stage above (exact-fp32 kernels,
+ * fixed-order reductions: deterministic).  Every gradient buffer is written, not accumulated, except dh0_acc.
+ * workspace >= cgr_stage_bwd_workspace(N, E, fa, fb, H) bytes.
+ * ---------------------------------------------------------------------------------------- */
+size_t cgr_stage_bwd_workspace(int64_t n_atoms, int64_t n_bonds, int32_t fa, int32_t fb, int32_t hidden);
+
+/* Backward of cgr_readout_fwd (GNN.py:105-110): grad_out [B] and the saved s / hv / zv (NULL for relu) / pooled ->
+ * gw_e2n [H, fa+H], gb_e2n [H], gw_ffn [H], gb_ffn [1] and dh [E, H], the gradient w.r.t. the bond states the readout
+ * consumed (dh[e] = ds[dst e]). */
+int cgr_readout_bwd(const float* grad_out, const float* x, const int32_t* in_ptr, const int32_t* in_idx,
+                    const int32_t* atom_ptr, const int32_t* dst, const float* w_e2n, const float* w_ffn, int32_t act,
+                    const float* s, const float* hv, const float* zv, const float* pooled, float* gw_e2n,
+                    float* gb_e2n, float* gw_ffn, float* gb_ffn, float* dh, int64_t n_atoms, int64_t n_bonds,
+                    int64_t n_rxn, int32_t fa, int32_t hidden, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of cgr_bond_update_fwd (GNN.py:91-102, 131-141): dh_out [E, H] (gradient w.r.t. the layer's output) with the
+ * saved h_out, z (NULL for relu), m and h0 -> gw [H, H], gb [H], gskip (scalar, may be NULL), dh_in [E, H] (gradient
+ * w.r.t. the layer's input: dh[k] = sum_{j in in(dst k)} dm[j^1] - dm[k^1], dm = dz W) and dh0_acc [E, H] (+)= skip * dz
+ * (dh0_first != 0: stored instead of accumulated).  Dropout as in the forward (same seed / layer). */
+int cgr_bond_update_bwd(const float* dh_out, const float* h_out, const float* z, const float* m, const float* h0,
+                        const int32_t* in_ptr, const int32_t* in_idx, const int32_t* dst, const float* w,
+                        const float* skip, int32_t act, float dropout_p, uint64_t seed, uint32_t layer,
+                        int32_t training, float* gw, float* gb, float* gskip, float* dh_in, float* dh0_acc,
+                        int32_t dh0_first, int64_t n_bonds, int64_t n_atoms, int32_t hidden, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Backward of cgr_edge_init_fwd (GNN.py:85-86): dh0 [E, H] (total gradient w.r.t. h_0: layer 0's input gradient plus the
+ * accumulated skip contributions) with the saved h0 and z0 (NULL for relu) -> gw_init [H, fa+fb], gb_init [H]. */
+int cgr_edge_init_bwd(const float* dh0, const float* h0, const float* z0, const float* x, const float* edge_attr,
+                      const int32_t* in_ptr, const int32_t* in_idx, int32_t act, float* gw_init, float* gb_init,
+                      int64_t n_atoms, int64_t n_bonds, int32_t fa, int32_t fb, int32_t hidden, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-network entry points (what the torch custom ops call).
@@ -337,6 +371,30 @@ int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_t* store, c
 int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order, int64_t n_total,
                     int64_t batch_size, float* out, void* dev_ws, size_t dev_bytes_per_slot, void* host_ws,
                     size_t host_bytes_per_slot, int32_t n_slots, void* const* streams);
+
+/* ------------------------------------------------------------------------------------------
+ * CGR featurisation after the chemistry toolkit (reference utils/graph_features.py:4-63 atom /
+ * bond features, :177-195 reactant || (product - reactant) layout).  The caller parses SMILES (RDKit in the reference) and
+ * hands over compact attribute codes, product side aligned to the reactant atom order (graph_features.py:83-103):
+ *   atom_r / atom_p  [N, 6] int16: atomic number, total degree, formal charge, total #Hs, hybridisation code, aromatic;
+ *   mass_r / mass_p  [N] double (atom.GetMass(); the reference multiplies by 0.01 in Python floats);
+ *   bond_r / bond_p  [E, 3] int8 per DIRECTED bond of the reactant/product union, in the reference's edge order:
+ *                    type (-1 absent on this side, 0 single, 1 double, 2 triple, 3 aromatic, other = another type),
+ *                    conjugated, in ring.
+ * `host_tables` holds the one-hot choice lists (table-driven: the reference's lists are the defaults in
+ * cgr_mpnn_3d_b200/featurize.py; values not listed light the extra last slot, graph_features.py:66-80).
+ * Writes x[v, 0:78] (row stride ldx >= 78 floats, so a MACE block can follow in the same tensor) and edge_attr [E, 14].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int16_t symbol_z[11];        /* H C N O F Si P S Cl Br I as atomic numbers (graph_features.py:16-18) */
+  int16_t degrees[6];
+  int16_t charges[5];
+  int16_t num_hs[5];
+  int16_t hybridizations[5];   /* the parser's codes for SP, SP2, SP3, SP3D, SP3D2 */
+} cgr_feature_tables_t;
+int cgr_featurize_cgr(const cgr_feature_tables_t* host_tables, const int16_t* atom_r, const int16_t* atom_p,
+                      const double* mass_r, const double* mass_p, int64_t n_atoms, const int8_t* bond_r,
+                      const int8_t* bond_p, int64_t n_bonds, float* x, int64_t ldx, float* edge_attr, void* stream);
 
 /* Loss adjacent to the path (train.py:120, trainer.py:142): L = sum_b (pred-y)^2, and dL/dpred. */
 int cgr_mse_sum_fwd_bwd(const float* pred, const float* y, int64_t n_rxn, float* loss,

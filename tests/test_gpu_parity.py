@@ -1120,3 +1120,66 @@ def test_fast_precision_mode_is_separate_and_bounded():
     model.precision = "bf16"
     with pytest.raises(ValueError):
         model(d)
+
+
+# ---------------------------------------------------------------------------------------------
+# (5) stage-level backward through the C ABI (cgr_readout_bwd / cgr_bond_update_bwd / cgr_edge_init_bwd): each stage's
+# gradients against autograd on the oracle's stage, chained the way the whole backward chains them
+@pytest.mark.parametrize("name", ["small_skip", "small_gelu", "small_silu"])
+def test_stage_level_backward_parity(name):
+    from cgr_mpnn_3d_b200 import stage_ops
+    from cgr_mpnn_3d_b200.collate import build_plan
+    from oracle.gnn_oracle import global_add_pool, propagate_add
+    z, meta = load_case(name)
+    data = case_batch(z, meta)
+    oracle = build_oracle(meta, case_state_dict(z)).train()
+    act = ACTS[meta["act"]]
+    act_id = {"relu": 0, "silu": 1, "gelu": 2}[meta["act"]]
+    d = data.to("cuda")
+    plan = build_plan(d.edge_index, d.num_nodes, d.batch, d.ptr)
+    cu = lambda t: t.detach().cuda()
+    row = data.edge_index[0]
+    skip_p = oracle.skip_weights[0] if meta["skip"] else None
+    gen = torch.Generator().manual_seed(3)
+
+    # ---- forward of the three stages on the oracle, with autograd
+    h0_ref = act(oracle.edge_init(torch.cat([data.x[row], data.edge_attr], 1)))
+    h_in = h0_ref.detach().clone().requires_grad_(True)           # layer input and skip operand as separate leaves
+    h0_leaf = h0_ref.detach().clone().requires_grad_(True)
+    _, y = oracle.convs[0](data.edge_index, h_in)
+    h1_ref = act(y + (skip_p * h0_leaf if skip_p is not None else h0_leaf))
+    h_ro = h1_ref.detach().clone().requires_grad_(True)
+    s_ref = propagate_add(data.edge_index, h_ro)
+    hv_ref = act(oracle.edge_to_node(torch.cat([data.x, s_ref], 1)))
+    out_ref = oracle.ffn(global_add_pool(hv_ref, data.batch)).squeeze(-1)
+    g_out = torch.randn(out_ref.shape, generator=gen)
+
+    # ---- readout backward
+    out_ref.backward(g_out)
+    out, s, hv, pooled, zv = stage_ops.readout_fwd(cu(h1_ref), d.x, plan, cu(oracle.edge_to_node.weight),
+                                                   cu(oracle.edge_to_node.bias), cu(oracle.ffn.weight), cu(oracle.ffn.bias),
+                                                   act_id, want_z=True)
+    gw, gb, gwf, gbf, dh = stage_ops.readout_bwd(g_out.cuda(), d.x, plan, cu(oracle.edge_to_node.weight),
+                                                 cu(oracle.ffn.weight), act_id, s, hv, pooled, zv=None if act_id == 0 else zv)
+    assert tensor_error(gw, oracle.edge_to_node.weight.grad) < 1e-5 and tensor_error(gb, oracle.edge_to_node.bias.grad) < 1e-5
+    assert tensor_error(gwf, oracle.ffn.weight.grad) < 1e-5 and tensor_error(gbf, oracle.ffn.bias.grad) < 1e-5
+    assert tensor_error(dh, h_ro.grad) < 1e-5
+
+    # ---- bond update backward, fed with the readout's dh
+    h1_ref.backward(h_ro.grad)
+    h1, m, zz = stage_ops.bond_update_fwd(cu(h0_ref), cu(h0_ref), plan, cu(oracle.convs[0].lin.weight),
+                                          cu(oracle.convs[0].lin.bias), None if skip_p is None else cu(skip_p), act_id)
+    gw1, gb1, gsk, dh_in, dh0 = stage_ops.bond_update_bwd(dh, h1, m, cu(h0_ref), plan, cu(oracle.convs[0].lin.weight),
+                                                          None if skip_p is None else cu(skip_p), act_id,
+                                                          z=None if act_id == 0 else zz)
+    assert tensor_error(gw1, oracle.convs[0].lin.weight.grad) < 1e-5 and tensor_error(gb1, oracle.convs[0].lin.bias.grad) < 1e-5
+    if skip_p is not None:
+        assert tensor_error(gsk, skip_p.grad) < 1e-5
+    assert tensor_error(dh_in, h_in.grad) < 1e-5 and tensor_error(dh0, h0_leaf.grad) < 1e-5
+
+    # ---- edge initialisation backward: total gradient w.r.t. h_0 = layer-0 input gradient + skip contributions
+    h0_ref.backward(h_in.grad + h0_leaf.grad)
+    h0, z0 = stage_ops.edge_init_fwd(d.x, d.edge_attr, plan, cu(oracle.edge_init.weight), cu(oracle.edge_init.bias), act_id,
+                                     want_z=True)
+    gwi, gbi = stage_ops.edge_init_bwd(dh_in + dh0, h0, d.x, d.edge_attr, plan, act_id, z0=None if act_id == 0 else z0)
+    assert tensor_error(gwi, oracle.edge_init.weight.grad) < 1e-5 and tensor_error(gbi, oracle.edge_init.bias.grad) < 1e-5

@@ -71,7 +71,8 @@ def step_peer():
     oa.zero_grad(); F.mse_loss(ma(d0), d0.y, reduction="sum").backward(); oa.step()
 t_peer = timed(step_peer)
 # resume: state_dict -> a fresh PeerFusedAdam -> one more step must equal continuing the original optimizer
-sd = oa.state_dict()
+import copy
+sd = copy.deepcopy(oa.state_dict())          # a snapshot: state_dict() hands out the live state tensors
 snap = [p.detach().clone() for p in ma.parameters()]
 d1 = batches[1]
 oa.zero_grad(); F.mse_loss(ma(d1), d1.y, reduction="sum").backward(); oa.step()
