@@ -36,6 +36,7 @@ constexpr int ZROW = TM;                       // staging row that stays zero: t
 constexpr int SLOT_COLS = 256;                 // TMEM columns per accumulator slot
 constexpr int MAX_TPC = 2;                     // tiles per cluster (ping-pong)
 constexpr int SMEM_LIMIT = 232448;
+constexpr int FASTN = 4;                       // neighbours a packed descriptor holds (rows with more walk the CSR list)
 
 template <int BN_>
 struct FCfg {
@@ -43,20 +44,23 @@ struct FCfg {
   static constexpr bool CAT = 2 * BN <= 256;                   // A_hi x [B_hi ; B_lo] as one MMA of N = 2 BN
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int NCH = BN > 128 ? 4 : 1;                 // epilogue column chunks
-  static constexpr int CH = BN / NCH;                          // 52 (BN = 208), 80, 112
-  static constexpr int UPR = CH / 4;                           // float4 units per row of a chunk
-  static constexpr int CH8 = (CH + 7) / 8 * 8;
-  static constexpr int CHP = ((CH8 / 4) % 2 == 1) ? CH8 : CH8 + 4;   // staging row pitch: odd multiple of 4 floats
+  static constexpr int CH = BN > 128 ? 72 : BN;                // epilogue column chunk (208 = 72 + 72 + 64)
+  static constexpr int NCH = (BN + CH - 1) / CH;
+  static constexpr int UPR = CH / 4;                           // float4 column groups of a chunk
+  static constexpr int RPP = EPI_THREADS / UPR;                // bond rows the epilogue threads cover per pass
+  static constexpr int ACTIVE = RPP * UPR;                     // threads that own a (row, column group) unit
+  static constexpr int SLOTS = (TM + RPP - 1) / RPP;           // passes: units per thread and chunk
+  static constexpr int CHP = ((CH / 4) % 2 == 1) ? CH : CH + 4;     // staging row pitch: odd multiple of 4 floats
   static constexpr int Y_BYTES = ((TM + 1) * CHP * 4 + 1023) / 1024 * 1024;     // + the zero row
-  static constexpr int LPR = UPR <= 16 ? 16 : 32;              // lanes per row in the readout epilogue
-  static constexpr int AUX_BYTES = 12288;
+  static constexpr int NGW = (CH / 8 + 3) / 4;                 // 8-column TMEM groups per warp and chunk
+  static constexpr int AUX_BYTES = 8192;
   static constexpr int FIT = (SMEM_LIMIT - 1024 - Y_BYTES - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 4 ? 4 : FIT;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Y_BYTES + AUX_BYTES;
-  static_assert(BN % 16 == 0 && BN <= 256 && BN % NCH == 0 && CH % 4 == 0 && UPR <= 32, "bad slice width");
+  static_assert(BN % 16 == 0 && BN <= 256 && CH % 8 == 0 && UPR <= 32, "bad slice width");
   static_assert(STAGES >= 2, "pipeline needs two stages");
   static_assert((CAT ? 2 * BN : BN) <= SLOT_COLS, "accumulator exceeds its TMEM slot");
+  static_assert((TM + 1) * CHP < 65536, "staging offsets must fit 16 bits");
 };
 
 struct FwdParams {
@@ -89,11 +93,12 @@ struct FwdParams {
 
 struct TileAux {                // per tile of the group: packed neighbour descriptors (built once, used by every layer)
   int32_t info[8];
-  // bond row j: the in-bonds of src(j) EXCEPT the reverse bond j^1 (GNN.py:141 adds it and subtracts it again), atom row
-  // v: the in-bonds of v -- tile-local row ids, one byte each, ascending bond id, unused slots = ZROW
-  uint2 nbr_b[TM];
-  uint2 nbr_a[TM];
-  uint16_t pb_b[TM];            // CSR offset of the row's full in-bond list (rows with more than NBR neighbours)
+  // bond row j: the in-bonds of src(j) EXCEPT the reverse bond j^1 (GNN.py:141 adds it and subtracts it again); atom row
+  // v: the in-bonds of v.  Up to FASTN staging-row offsets (row * CHP floats, 16 bits each, ascending bond id); unused
+  // slots point at the zero row, so the gather is four unconditional loads
+  uint2 nbo_b[TM];
+  uint2 nbo_a[TM];
+  uint16_t pb_b[TM];            // CSR offset of the row's full in-bond list (rows with more than FASTN neighbours)
   uint16_t pb_a[TM];
   uint8_t cnt_b[TM];            // neighbours of the row (bond rows: reverse excluded)
   uint8_t cnt_a[TM];
@@ -109,19 +114,9 @@ struct Aux {
   uint64_t tmem_empty[2];
   uint64_t ready[MAX_TPC];      // tile j's operand of the next layer is complete in every CTA of the cluster
   uint32_t tmem_base;
-  alignas(16) float bias_s[2][256];   // bias slice of the item being drained (double-buffered by accumulator slot)
   TileAux t[MAX_TPC];
 };
-static_assert(sizeof(Aux) <= 12288, "Aux too large");
-
-// z -> activation -> FP16 (hi, lo) of one float4 unit, stored as two 8-byte words; returns max |h|
-template <bool RELU>
-__device__ __forceinline__ float act_split_store(float4 z, int act, __half* hi, __half* lo) {
-  z.x = tcg::act_t<RELU>(z.x, act); z.y = tcg::act_t<RELU>(z.y, act);
-  z.z = tcg::act_t<RELU>(z.z, act); z.w = tcg::act_t<RELU>(z.w, act);
-  tcg::store_split4(z, 1.f, hi, lo);
-  return tcg::amax4(z);
-}
+static_assert(sizeof(Aux) <= 8192, "Aux too large");
 
 // four consecutive floats of a parameter vector (16-byte aligned in practice; parameters may also be views)
 __device__ __forceinline__ float4 ldg4(const float* p) {
@@ -129,25 +124,16 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-// sum of the staged rows a packed descriptor names: slots 0..3 unconditionally (unused slots point at the zero row: no
-// branches, four independent loads), slots 4..7 only for rows with more than four neighbours
-template <int CHP>
-__device__ __forceinline__ float4 gather_packed(const float* y_c, uint2 nb, int cnt) {
-  float4 a = tcg::ld4(y_c + (int)(nb.x & 0xffu) * CHP);
-  const float4 v1 = tcg::ld4(y_c + (int)((nb.x >> 8) & 0xffu) * CHP);
-  const float4 v2 = tcg::ld4(y_c + (int)((nb.x >> 16) & 0xffu) * CHP);
-  const float4 v3 = tcg::ld4(y_c + (int)(nb.x >> 24) * CHP);
+// sum of the (up to four) staged rows a packed descriptor names: four independent loads, no branches
+__device__ __forceinline__ float4 gather4(const float* y_c, uint2 o) {
+  float4 a = tcg::ld4(y_c + (o.x & 0xffffu));
+  const float4 v1 = tcg::ld4(y_c + (o.x >> 16));
+  const float4 v2 = tcg::ld4(y_c + (o.y & 0xffffu));
+  const float4 v3 = tcg::ld4(y_c + (o.y >> 16));
   tcg::add4(a, v1); tcg::add4(a, v2); tcg::add4(a, v3);
-  if (cnt > 4) {
-    const float4 v4 = tcg::ld4(y_c + (int)(nb.y & 0xffu) * CHP);
-    const float4 v5 = tcg::ld4(y_c + (int)((nb.y >> 8) & 0xffu) * CHP);
-    const float4 v6 = tcg::ld4(y_c + (int)((nb.y >> 16) & 0xffu) * CHP);
-    const float4 v7 = tcg::ld4(y_c + (int)(nb.y >> 24) * CHP);
-    tcg::add4(a, v4); tcg::add4(a, v5); tcg::add4(a, v6); tcg::add4(a, v7);
-  }
   return a;
 }
-// rows with more than NBR neighbours (rare: an atom with ten or more bonds): walk the CSR list, skipping row `skip`
+// rows with more than FASTN neighbours (an atom with six or more bonds): walk the CSR list, skipping row `skip`
 template <int CHP>
 __device__ __forceinline__ float4 gather_list(const float* y_c, const uint8_t* idx_l, int pb, int n, int skip) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -225,20 +211,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const int a = bond ? __ldg(p.src + ebase + r) : abase + (r - ecount);
       const int skip = bond ? (r ^ 1) : -1;
       const int pb = __ldg(p.in_ptr + a), pe = __ldg(p.in_ptr + a + 1);
-      uint32_t w[2] = {0x80808080u, 0x80808080u};             // ZROW in every slot
+      uint32_t o[FASTN] = {ZROW * CHP, ZROW * CHP, ZROW * CHP, ZROW * CHP};
       int cnt = 0;
       for (int t = pb; t < pe; ++t) {
         const int k = __ldg(p.in_idx + t) - ebase;
         if (k == skip) continue;
-        if (cnt < NBR) w[cnt >> 2] = (w[cnt >> 2] & ~(0xffu << (8 * (cnt & 3)))) | ((uint32_t)(k & 0xff) << (8 * (cnt & 3)));
+        if (cnt < FASTN) o[cnt] = (uint32_t)(k * CHP);
         ++cnt;
       }
+      const uint2 packed = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
       if (bond) {
-        ta.nbr_b[r] = make_uint2(w[0], w[1]); ta.pb_b[r] = (uint16_t)(pb - ebase);
+        ta.nbo_b[r] = packed; ta.pb_b[r] = (uint16_t)(pb - ebase);
         ta.cnt_b[r] = (uint8_t)(cnt > 255 ? 255 : cnt); ta.full_b[r] = (uint8_t)(pe - pb > 255 ? 255 : pe - pb);
       } else {
         const int v = r - ecount;
-        ta.nbr_a[v] = make_uint2(w[0], w[1]); ta.pb_a[v] = (uint16_t)(pb - ebase); ta.cnt_a[v] = (uint8_t)(cnt > 255 ? 255 : cnt);
+        ta.nbo_a[v] = packed; ta.pb_a[v] = (uint16_t)(pb - ebase); ta.cnt_a[v] = (uint8_t)(cnt > 255 ? 255 : cnt);
       }
     }
     for (int v = threadIdx.x; v < TM; v += THREADS) ta.tat[v] = 0.f;
@@ -320,28 +307,49 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps
+    constexpr int RPP = C::RPP, SLOTS = C::SLOTS, NGW = C::NGW;
     const int ew = warp - 4, et = (int)threadIdx.x - 128;
     const int q = warp & 3, grp = ew >> 2;                          // TMEM lane quarter of this warp, column-group phase
-    // bond layers: flat unit mapping -- unit u = (row u / UPR, float4 column group u % UPR); thread et owns the units
-    // et, et + EPI_THREADS, ... of every chunk (SLOTS of them)
-    constexpr int SLOTS = (TM * UPR + EPI_THREADS - 1) / EPI_THREADS;
-    // readout: LPR lanes per atom row; the same lanes own atom v in every chunk
-    constexpr int LPR = C::LPR, RPW = 32 / LPR;
-    constexpr int RSLOTS = (TM + EPI_WARPS * RPW - 1) / (EPI_WARPS * RPW);
-    constexpr int RPF = RSLOTS < 6 ? RSLOTS : 6;                    // readout rows whose Q' operand is requested ahead
-    constexpr int NOP = SLOTS > RPF ? SLOTS : RPF;
-    const int sub = lane / LPR, hl = lane % LPR;
-    int rk[SLOTS], ck[SLOTS];                                       // this thread's units: the same in every chunk / item
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      const int u = et + k * EPI_THREADS;
-      rk[k] = u / UPR;
-      ck[k] = 4 * (u - rk[k] * UPR);
-    }
+    // bond layers: thread et owns column group cg of the rows r0, r0 + RPP, ... (SLOTS of them) in every chunk
+    const int cg = et % UPR, r0 = et / UPR;
+    const bool unit_thread = et < C::ACTIVE;
+    // readout: one warp per atom row, lanes = column groups (the same warp owns atom v in every chunk)
+    constexpr int RSLOTS = (TM + EPI_WARPS - 1) / EPI_WARPS;
+    constexpr int RPF = RSLOTS < SLOTS ? RSLOTS : SLOTS;            // readout rows whose Q' operand is requested ahead
     long long* dbg = p.dbg ? p.dbg + (int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) : nullptr;
     // h_0 and Q' (outputs of the previous kernels of this forward) are requested by these threads directly, possibly
     // before the producer's first load has landed: every epilogue thread orders itself behind the previous grids
     umma::grid_dep_wait();
+
+    // fp32 operand of the epilogue -- h0 rows of a bond layer, Q' rows of the readout -- for one chunk, requested well
+    // before its use (during the previous chunk's staging / the previous item's tail): its L2 latency never shows
+    float4 opnd[SLOTS];
+    auto request = [&](int i, int ch) {
+      const int j = i % nt, l = i / nt;
+      const TileAux& ta = aux->t[j];
+      const int n = n0 + ch * CH + 4 * (l == depth ? lane : cg);
+      const bool col_on = 4 * (l == depth ? lane : cg) < CH && n < n0 + BN && n < H;
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) opnd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!col_on) return;
+      if (l < depth) {
+        if (!unit_thread) return;
+        const int ecount = ta.info[1];
+        const float* hp = p.h0 + ((int64_t)(tile0 + j) * TM + r0) * H + n;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k)
+          if (r0 + k * RPP < ecount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(hp + (int64_t)k * RPP * H));
+      } else {
+        const int abase = ta.info[2], acount = ta.info[3];
+#pragma unroll
+        for (int k = 0; k < RPF; ++k) {
+          const int v = ew + k * EPI_WARPS;
+          if (v < acount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
+        }
+      }
+    };
+    if (n_items > 0) request(0, 0);
+
     for (int i = 0; i < n_items; ++i) {
       const int j = i % nt, l = i / nt;
       const uint32_t slot = (uint32_t)i & 1u;
@@ -351,39 +359,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const int ecount = ta.info[1], abase = ta.info[2], acount = ta.info[3];
       const float us = __ldg(p.unscale + 1 + l);
       const float skip = (!readout && p.skip[l]) ? __ldg(p.skip[l]) : 1.f;
+      const float* cvec = readout ? p.w_ffn : p.bias[l];           // per-column vector of the epilogue: bias / w_ffn
       __half* o_hi = p.o_hi[(l + 1) & 1];
       __half* o_lo = p.o_lo[(l + 1) & 1];
-      float* bias_s = aux->bias_s[slot];
-      if (!readout) {
-        for (int k = et; k < BN; k += EPI_THREADS) bias_s[k] = n0 + k < H ? __ldg(p.bias[l] + n0 + k) : 0.f;
-      } else {
-        for (int k = et; k < BN; k += EPI_THREADS) bias_s[k] = n0 + k < H ? __ldg(p.w_ffn + n0 + k) : 0.f;
-      }
-      // fp32 operand of the epilogue (h0 rows of a bond layer, Q' rows of the readout) for chunk 0: requested before the
-      // accumulator is ready, so its L2 latency hides behind the MMAs; later chunks are requested one chunk ahead
-      float4 opnd[NOP];
-      auto request = [&](int ch, float4 (&dst)[NOP]) {
-        const int ncol0 = n0 + ch * CH;
-        if (!readout) {
+      // this thread's rows of the tile: neighbour descriptors in registers for the whole item
+      uint2 nbo[SLOTS];
+      uint32_t valid = 0, slow = 0;
+      if (!readout && unit_thread) {
 #pragma unroll
-          for (int k = 0; k < SLOTS; ++k) {
-            const int n = ncol0 + ck[k];
-            dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rk[k] < ecount && n < H)
-              dst[k] = __ldcg(reinterpret_cast<const float4*>(p.h0 + ((int64_t)tile * TM + rk[k]) * H + n));
-          }
-        } else {
-          const int n = ncol0 + 4 * hl;
-#pragma unroll
-          for (int k = 0; k < RPF; ++k) {
-            const int v = ew * RPW + sub + k * EPI_WARPS * RPW;
-            dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (v < acount && hl < UPR && n < H)
-              dst[k] = __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
+        for (int k = 0; k < SLOTS; ++k) {
+          const int r = r0 + k * RPP;
+          nbo[k] = make_uint2((uint32_t)(ZROW * CHP) * 0x10001u, (uint32_t)(ZROW * CHP) * 0x10001u);
+          if (r < ecount) {
+            valid |= 1u << k;
+            nbo[k] = ta.nbo_b[r];
+            if (ta.cnt_b[r] > FASTN) slow |= 1u << k;
           }
         }
-      };
-      request(0, opnd);
+      }
       umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
       umma::tc_fence_after_sync();
       if (dbg && et == 0) dbg[i * 4 + 0] = clock64();
@@ -391,24 +384,42 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       float vmax = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
+        const int cw = (ch + 1) * CH <= BN ? CH : BN - ch * CH;    // columns of this chunk (the last one may be shorter)
+        const int ncol0 = n0 + ch * CH;                            // first global column of this chunk
+        const int n = ncol0 + 4 * (readout ? lane : cg);
+        const bool col_on = 4 * (readout ? lane : cg) < cw && n < H;
+        const float4 c4 = col_on ? ldg4(cvec + n) : make_float4(0.f, 0.f, 0.f, 0.f);   // in flight during the staging
         umma::named_bar_sync(1, EPI_THREADS);                      // the staging rows of the previous chunk are drained
         {
+          // TMEM -> registers -> staging rows (fp32, unscaled).  Warp: lane quarter q, every fourth 8-column group
           const int row = q * 32 + lane;
-          for (int cc = grp * 8; cc < CH; cc += 8 * (EPI_WARPS / 4)) {
-            float v[8];
-            umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v);
-            if (C::CAT && !p.fast) {
-              float v2[8];
+          if (C::CAT && !p.fast) {
+            for (int cc = grp * 8; cc < cw; cc += 32) {
+              float v[8], v2[8];
+              umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v);
               umma::tmem_ld_x8(acc + (uint32_t)(BN + ch * CH + cc), v2);
               umma::tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] += v2[k];
-            } else {
-              umma::tmem_ld_wait();
+              float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
+              dst[0] = make_float4((v[0] + v2[0]) * us, (v[1] + v2[1]) * us, (v[2] + v2[2]) * us, (v[3] + v2[3]) * us);
+              dst[1] = make_float4((v[4] + v2[4]) * us, (v[5] + v2[5]) * us, (v[6] + v2[6]) * us, (v[7] + v2[7]) * us);
             }
-            float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
-            dst[0] = make_float4(v[0] * us, v[1] * us, v[2] * us, v[3] * us);
-            dst[1] = make_float4(v[4] * us, v[5] * us, v[6] * us, v[7] * us);
+          } else {
+            float v[NGW][8];
+#pragma unroll
+            for (int gi = 0; gi < NGW; ++gi) {                     // all loads of the warp in flight, one wait
+              const int cc = (grp + 4 * gi) * 8;
+              if (cc < cw) umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v[gi]);
+            }
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int gi = 0; gi < NGW; ++gi) {
+              const int cc = (grp + 4 * gi) * 8;
+              if (cc < cw) {
+                float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
+                dst[0] = make_float4(v[gi][0] * us, v[gi][1] * us, v[gi][2] * us, v[gi][3] * us);
+                dst[1] = make_float4(v[gi][4] * us, v[gi][5] * us, v[gi][6] * us, v[gi][7] * us);
+              }
+            }
           }
         }
         if (ch == NCH - 1) {                                       // accumulator drained: the MMA warp may reuse the slot
@@ -416,68 +427,69 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           __syncwarp();
           if (lane == 0) umma::mbar_arrive(umma::smem_u32(&aux->tmem_empty[slot]));
         }
-        float4 cur[NOP];
-#pragma unroll
-        for (int k = 0; k < NOP; ++k) cur[k] = opnd[k];
-        if (NCH > 1 && ch + 1 < NCH) request(ch + 1, opnd);        // next chunk's operand: in flight during this chunk's gather
         umma::named_bar_sync(2, EPI_THREADS);                      // staging rows complete
 
-        const int ncol0 = n0 + ch * CH;                            // first global column of this chunk
         if (!readout) {
+          // z[e] = sum_{k in in(src e), k != e^1} y[k] + b + skip * h0[e];  h' = act(z) -> next operand (hi, lo)
+          if (col_on && unit_thread) {
+            const float* y_c = y_s + 4 * cg;
 #pragma unroll
-          for (int k = 0; k < SLOTS; ++k) {
-            const int r = rk[k], c = ck[k], n = ncol0 + c;
-            if (r < ecount && n < H) {
-              const int cnt = ta.cnt_b[r];
-              const float4 a4 = cnt <= NBR ? gather_packed<CHP>(y_s + c, ta.nbr_b[r], cnt)
-                                           : gather_list<CHP>(y_s + c, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
-              const float4 b4 = tcg::ld4(bias_s + ch * CH + c);
+            for (int k = 0; k < SLOTS; ++k) {
+              const float4 a4 = gather4(y_c, nbo[k]);              // rows beyond the tile read the zero row
               float4 z;
-              z.x = a4.x + b4.x + skip * cur[k].x;
-              z.y = a4.y + b4.y + skip * cur[k].y;
-              z.z = a4.z + b4.z + skip * cur[k].z;
-              z.w = a4.w + b4.w + skip * cur[k].w;
-              const int64_t orow = (int64_t)tile * TM + r;
+              z.x = a4.x + c4.x + skip * opnd[k].x;
+              z.y = a4.y + c4.y + skip * opnd[k].y;
+              z.z = a4.z + c4.z + skip * opnd[k].z;
+              z.w = a4.w + c4.w + skip * opnd[k].w;
+              if (slow & (1u << k)) {                              // more than FASTN neighbours: the full CSR list
+                const int r = r0 + k * RPP;
+                const float4 s4 = gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
+                z.x = s4.x + c4.x + skip * opnd[k].x; z.y = s4.y + c4.y + skip * opnd[k].y;
+                z.z = s4.z + c4.z + skip * opnd[k].z; z.w = s4.w + c4.w + skip * opnd[k].w;
+              }
               z.x = tcg::act_t<RELU>(z.x, p.act); z.y = tcg::act_t<RELU>(z.y, p.act);
               z.z = tcg::act_t<RELU>(z.z, p.act); z.w = tcg::act_t<RELU>(z.w, p.act);
-              vmax = fmaxf(vmax, tcg::amax4(z));
-              if (p.fast) {
-                const __half2 h01 = __floats2half2_rn(z.x, z.y), h23 = __floats2half2_rn(z.z, z.w);
-                uint2 ph;
-                ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-                *reinterpret_cast<uint2*>(o_hi + orow * p.ldo + n) = ph;
-              } else {
-                tcg::store_split4(z, 1.f, o_hi + orow * p.ldo + n, o_lo + orow * p.ldo + n);
+              if (valid & (1u << k)) {
+                vmax = fmaxf(vmax, tcg::amax4(z));
+                const int64_t o = ((int64_t)tile * TM + r0 + k * RPP) * p.ldo + n;
+                if (p.fast) {
+                  const __half2 h01 = __floats2half2_rn(z.x, z.y), h23 = __floats2half2_rn(z.z, z.w);
+                  uint2 ph;
+                  ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+                  *reinterpret_cast<uint2*>(o_hi + o) = ph;
+                } else {
+                  tcg::store_split4(z, 1.f, o_hi + o, o_lo + o);
+                }
               }
             }
           }
         } else {
           // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
-          const int c = 4 * hl, n = ncol0 + c;
-          const bool lane_on = hl < UPR && n < H;
-          const float4 wf4 = lane_on ? tcg::ld4(bias_s + ch * CH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* y_c = y_s + 4 * lane;
 #pragma unroll
           for (int k = 0; k < RSLOTS; ++k) {
-            const int v = ew * RPW + sub + k * EPI_WARPS * RPW;
-            if (k * EPI_WARPS * RPW >= acount) break;              // warp-uniform: no row of this step exists
-            const bool row_on = v < acount;
+            const int v = ew + k * EPI_WARPS;
+            if (k * EPI_WARPS >= acount) break;                    // warp-uniform: no row of this step exists
             float t = 0.f;
-            if (lane_on && row_on) {
-              float4 a4 = k < RPF ? cur[k < RPF ? k : 0]
+            if (col_on && v < acount) {
+              float4 a4 = k < RPF ? opnd[k < RPF ? k : 0]
                                   : __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
               const int cnt = ta.cnt_a[v];
-              tcg::add4(a4, cnt <= NBR ? gather_packed<CHP>(y_s + c, ta.nbr_a[v], cnt)
-                                       : gather_list<CHP>(y_s + c, ta.idx_l, (int)ta.pb_a[v], cnt, -1));
-              t = tcg::act_t<RELU>(a4.x, p.act) * wf4.x;
-              t = fmaf(tcg::act_t<RELU>(a4.y, p.act), wf4.y, t);
-              t = fmaf(tcg::act_t<RELU>(a4.z, p.act), wf4.z, t);
-              t = fmaf(tcg::act_t<RELU>(a4.w, p.act), wf4.w, t);
+              tcg::add4(a4, cnt <= FASTN ? gather4(y_c, ta.nbo_a[v])
+                                         : gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_a[v], cnt, -1));
+              t = tcg::act_t<RELU>(a4.x, p.act) * c4.x;
+              t = fmaf(tcg::act_t<RELU>(a4.y, p.act), c4.y, t);
+              t = fmaf(tcg::act_t<RELU>(a4.z, p.act), c4.z, t);
+              t = fmaf(tcg::act_t<RELU>(a4.w, p.act), c4.w, t);
             }
 #pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (hl == 0 && row_on) ta.tat[v] += t;
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0 && v < acount) ta.tat[v] += t;
           }
         }
+        // the operand of the next chunk (or of the next item's first chunk) goes in flight now
+        if (ch + 1 < NCH) request(i, ch + 1);
+        else if (i + 1 < n_items) request(i + 1, 0);
       }
       if (dbg && et == 0) dbg[i * 4 + 1] = clock64();
 
