@@ -135,7 +135,7 @@ __device__ __forceinline__ float4 gather4(const float* y_c, uint2 o) {
 }
 // rows with more than FASTN neighbours (an atom with six or more bonds): walk the CSR list, skipping row `skip`
 template <int CHP>
-__device__ __forceinline__ float4 gather_list(const float* y_c, const uint8_t* idx_l, int pb, int n, int skip) {
+__device__ __noinline__ float4 gather_list(const float* y_c, const uint8_t* idx_l, int pb, int n, int skip) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = 0; t < n; ++t) {
     const int k = idx_l[pb + t];
@@ -360,8 +360,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const float us = __ldg(p.unscale + 1 + l);
       const float skip = (!readout && p.skip[l]) ? __ldg(p.skip[l]) : 1.f;
       const float* cvec = readout ? p.w_ffn : p.bias[l];           // per-column vector of the epilogue: bias / w_ffn
-      __half* o_hi = p.o_hi[(l + 1) & 1];
-      __half* o_lo = p.o_lo[(l + 1) & 1];
+      // this thread's unit (row r0, column group cg) of the output operand; rows step by RPP, chunks by CH columns
+      const size_t o_item = ((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg;
+      __half* oh_item = p.o_hi[(l + 1) & 1] + o_item;
+      __half* ol_item = p.o_lo[(l + 1) & 1] + o_item;
+      const size_t row_step = (size_t)RPP * (size_t)p.ldo;
       // this thread's rows of the tile: neighbour descriptors in registers for the whole item
       uint2 nbo[SLOTS];
       uint32_t valid = 0, slow = 0;
@@ -433,33 +436,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           // z[e] = sum_{k in in(src e), k != e^1} y[k] + b + skip * h0[e];  h' = act(z) -> next operand (hi, lo)
           if (col_on && unit_thread) {
             const float* y_c = y_s + 4 * cg;
+            __half* oh = oh_item + ch * CH;                         // this thread's column group of row r0
+            __half* ol = ol_item + ch * CH;
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
-              const float4 a4 = gather4(y_c, nbo[k]);              // rows beyond the tile read the zero row
-              float4 z;
-              z.x = a4.x + c4.x + skip * opnd[k].x;
-              z.y = a4.y + c4.y + skip * opnd[k].y;
-              z.z = a4.z + c4.z + skip * opnd[k].z;
-              z.w = a4.w + c4.w + skip * opnd[k].w;
-              if (slow & (1u << k)) {                              // more than FASTN neighbours: the full CSR list
+              float4 a4 = gather4(y_c, nbo[k]);                     // rows beyond the tile read the zero row
+              if (slow & (1u << k)) {                               // more than FASTN neighbours: the full CSR list
                 const int r = r0 + k * RPP;
-                const float4 s4 = gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
-                z.x = s4.x + c4.x + skip * opnd[k].x; z.y = s4.y + c4.y + skip * opnd[k].y;
-                z.z = s4.z + c4.z + skip * opnd[k].z; z.w = s4.w + c4.w + skip * opnd[k].w;
+                a4 = gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
               }
-              z.x = tcg::act_t<RELU>(z.x, p.act); z.y = tcg::act_t<RELU>(z.y, p.act);
-              z.z = tcg::act_t<RELU>(z.z, p.act); z.w = tcg::act_t<RELU>(z.w, p.act);
+              float4 z;
+              z.x = tcg::act_t<RELU>(fmaf(skip, opnd[k].x, a4.x + c4.x), p.act);
+              z.y = tcg::act_t<RELU>(fmaf(skip, opnd[k].y, a4.y + c4.y), p.act);
+              z.z = tcg::act_t<RELU>(fmaf(skip, opnd[k].z, a4.z + c4.z), p.act);
+              z.w = tcg::act_t<RELU>(fmaf(skip, opnd[k].w, a4.w + c4.w), p.act);
               if (valid & (1u << k)) {
                 vmax = fmaxf(vmax, tcg::amax4(z));
-                const int64_t o = ((int64_t)tile * TM + r0 + k * RPP) * p.ldo + n;
-                if (p.fast) {
-                  const __half2 h01 = __floats2half2_rn(z.x, z.y), h23 = __floats2half2_rn(z.z, z.w);
-                  uint2 ph;
-                  ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-                  *reinterpret_cast<uint2*>(o_hi + o) = ph;
-                } else {
-                  tcg::store_split4(z, 1.f, o_hi + o, o_lo + o);
-                }
+                tcg::store_split4(z, 1.f, oh + (size_t)k * row_step, ol + (size_t)k * row_step);
               }
             }
           }

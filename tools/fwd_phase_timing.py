@@ -10,10 +10,11 @@ from cgr_mpnn_3D.models.GNN import GNN
 from cgr_mpnn_3d_b200 import _lib
 from cgr_mpnn_3d_b200.data import make_batch
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--policy", default="latency"); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--policy", default="latency"); ap.add_argument("--precision", default="fp32"); a = ap.parse_args()
 torch.manual_seed(0)
 m = GNN(846, 14, depth=4, hidden_sizes=[400] * 4, dropout_ps=[0.0] * 4, activation_fn=F.relu, use_learnable_skip=True).cuda().eval()
 m.tile_policy = a.policy
+m.precision = a.precision
 d = make_batch(a.batch, seed=0, fa=846).to("cuda")
 lib = _lib.load()
 PER = 2 * 16 * 4

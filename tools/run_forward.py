@@ -20,11 +20,15 @@ ap.add_argument("--engine", default="auto")
 ap.add_argument("--train", action="store_true")
 ap.add_argument("--hidden", type=int, default=400)
 ap.add_argument("--depth", type=int, default=4)
+ap.add_argument("--policy", default="latency")
+ap.add_argument("--precision", default="fp32")
 a = ap.parse_args()
 torch.manual_seed(0)
 m = GNN(846, 14, depth=a.depth, hidden_sizes=[a.hidden] * a.depth, dropout_ps=[0.0] * a.depth, activation_fn=F.relu,
         use_learnable_skip=True).cuda()
 m.engine = a.engine
+m.tile_policy = a.policy
+m.precision = a.precision
 d = make_batch(a.batch, seed=0, fa=846).to("cuda")
 if a.train:
     m.train()
