@@ -847,6 +847,8 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
       }
     }
     prm.ldo = w.kp_h;
+    prm.lo_delta = (int64_t)((char*)h_lo[0] - (char*)h_hi[0]);
+    CGR_CHECK_ARG((char*)h_lo[1] - (char*)h_hi[1] == prm.lo_delta, "tc forward: operand buffers are not laid out pairwise");
     prm.unscale = unscale;
     prm.h0 = h0;
     prm.PQ = PQ;

@@ -37,6 +37,10 @@ constexpr int SLOT_COLS = 256;                 // TMEM columns per accumulator s
 constexpr int MAX_TPC = 2;                     // tiles per cluster (ping-pong)
 constexpr int SMEM_LIMIT = 232448;
 constexpr int FASTN = 4;                       // neighbours a packed descriptor holds (rows with more walk the CSR list)
+#ifndef CGR_REG_LOW
+#define CGR_REG_LOW 32
+#define CGR_REG_HIGH 112
+#endif
 
 template <int BN_>
 struct FCfg {
@@ -53,14 +57,14 @@ struct FCfg {
   static constexpr int CHP = ((CH / 4) % 2 == 1) ? CH : CH + 4;     // staging row pitch: odd multiple of 4 floats
   static constexpr int Y_BYTES = ((TM + 1) * CHP * 4 + 1023) / 1024 * 1024;     // + the zero row
   static constexpr int NGW = (CH / 8 + 3) / 4;                 // 8-column TMEM groups per warp and chunk
-  static constexpr int AUX_BYTES = 8192;
+  static constexpr int AUX_BYTES = 16384;
   static constexpr int FIT = (SMEM_LIMIT - 1024 - Y_BYTES - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 4 ? 4 : FIT;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Y_BYTES + AUX_BYTES;
   static_assert(BN % 16 == 0 && BN <= 256 && CH % 8 == 0 && UPR <= 32, "bad slice width");
   static_assert(STAGES >= 2, "pipeline needs two stages");
   static_assert((CAT ? 2 * BN : BN) <= SLOT_COLS, "accumulator exceeds its TMEM slot");
-  static_assert((TM + 1) * CHP < 65536, "staging offsets must fit 16 bits");
+  static_assert((TM + 1) * CHP * 4 < 65536, "staging byte offsets must fit 16 bits");
 };
 
 struct FwdParams {
@@ -71,6 +75,7 @@ struct FwdParams {
   __half* o_hi[2];                             // layer l writes buffer (l + 1) & 1, rows tile * 128 + j
   __half* o_lo[2];
   int64_t ldo;
+  int64_t lo_delta;                            // byte distance from a hi buffer to its lo buffer (same for both pairs)
   const float* unscale;                        // [1 + l]: 1 / weight scale of layer l's matrix
   const float* h0;                             // [T * 128, H] fp32, tile-packed (skip operand)
   const float* PQ;                             // [N, 2H] fp32: Q' = PQ[:, H:] (readout operand)
@@ -91,14 +96,17 @@ struct FwdParams {
   long long* dbg;                              // optional [n_cta][MAX_TPC * MAX_LAYERS][4] clock64 stamps (debug)
 };
 
-struct TileAux {                // per tile of the group: packed neighbour descriptors (built once, used by every layer)
+struct TileAux {                // per tile of the group: neighbour descriptors (built once, used by every layer)
   int32_t info[8];
   // bond row j: the in-bonds of src(j) EXCEPT the reverse bond j^1 (GNN.py:141 adds it and subtracts it again); atom row
-  // v: the in-bonds of v.  Up to FASTN staging-row offsets (row * CHP floats, 16 bits each, ascending bond id); unused
-  // slots point at the zero row, so the gather is four unconditional loads
-  uint2 nbo_b[TM];
-  uint2 nbo_a[TM];
-  uint16_t pb_b[TM];            // CSR offset of the row's full in-bond list (rows with more than FASTN neighbours)
+  // v: the in-bonds of v.  nbd_*: staging-row BYTE offsets (row * CHP * 4) of neighbours 1..4, nb2_*: of neighbours
+  // 5..8 (16 bits each), ascending bond id; unused slots point at the zero row, so a gather is four unconditional
+  // loads.  Rows with more than 2 * FASTN neighbours walk their CSR list (idx_l).
+  uint4 nbd_b[TM];
+  uint4 nbd_a[TM];
+  uint2 nb2_b[TM];
+  uint2 nb2_a[TM];
+  uint16_t pb_b[TM];            // CSR offset of the row's full in-bond list
   uint16_t pb_a[TM];
   uint8_t cnt_b[TM];            // neighbours of the row (bond rows: reverse excluded)
   uint8_t cnt_a[TM];
@@ -114,9 +122,11 @@ struct Aux {
   uint64_t tmem_empty[2];
   uint64_t ready[MAX_TPC];      // tile j's operand of the next layer is complete in every CTA of the cluster
   uint32_t tmem_base;
+  float us[MAX_LAYERS + 1];     // 1 / weight scale of every layer's matrix (staged once: no global load per item)
+  float skipv[MAX_LAYERS];      // learnable skip scalars (1 where the layer has none)
   TileAux t[MAX_TPC];
 };
-static_assert(sizeof(Aux) <= 8192, "Aux too large");
+static_assert(sizeof(Aux) <= 16384, "Aux too large");
 
 // four consecutive floats of a parameter vector (16-byte aligned in practice; parameters may also be views)
 __device__ __forceinline__ float4 ldg4(const float* p) {
@@ -124,22 +134,26 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-// sum of the (up to four) staged rows a packed descriptor names: four independent loads, no branches
-__device__ __forceinline__ float4 gather4(const float* y_c, uint2 o) {
-  float4 a = tcg::ld4(y_c + (o.x & 0xffffu));
-  const float4 v1 = tcg::ld4(y_c + (o.x >> 16));
-  const float4 v2 = tcg::ld4(y_c + (o.y & 0xffffu));
-  const float4 v3 = tcg::ld4(y_c + (o.y >> 16));
-  tcg::add4(a, v1); tcg::add4(a, v2); tcg::add4(a, v3);
-  return a;
+// sum of the four staged rows a descriptor names (byte offsets from y_b): four independent loads, no branches, a
+// two-level add tree
+__device__ __forceinline__ float4 ldb4(const char* y_b, uint32_t off) { return *reinterpret_cast<const float4*>(y_b + off); }
+__device__ __forceinline__ float4 sum4(const float4 v0, const float4 v1, const float4 v2, const float4 v3) {
+  return make_float4((v0.x + v1.x) + (v2.x + v3.x), (v0.y + v1.y) + (v2.y + v3.y), (v0.z + v1.z) + (v2.z + v3.z),
+                     (v0.w + v1.w) + (v2.w + v3.w));
 }
-// rows with more than FASTN neighbours (an atom with six or more bonds): walk the CSR list, skipping row `skip`
+__device__ __forceinline__ float4 gather4(const char* y_b, uint4 o) {
+  return sum4(ldb4(y_b, o.x), ldb4(y_b, o.y), ldb4(y_b, o.z), ldb4(y_b, o.w));
+}
+__device__ __forceinline__ float4 gather4p(const char* y_b, uint2 o) {     // packed: 16 bits per offset
+  return sum4(ldb4(y_b, o.x & 0xffffu), ldb4(y_b, o.x >> 16), ldb4(y_b, o.y & 0xffffu), ldb4(y_b, o.y >> 16));
+}
+// rows with more than 2 * FASTN neighbours: walk the CSR list, skipping row `skip`
 template <int CHP>
-__device__ __noinline__ float4 gather_list(const float* y_c, const uint8_t* idx_l, int pb, int n, int skip) {
+__device__ __noinline__ float4 gather_list(const char* y_b, const uint8_t* idx_l, int pb, int n, int skip) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = 0; t < n; ++t) {
     const int k = idx_l[pb + t];
-    if (k != skip) tcg::add4(a, tcg::ld4(y_c + k * CHP));
+    if (k != skip) tcg::add4(a, ldb4(y_b, (uint32_t)(k * CHP * 4)));
   }
   return a;
 }
@@ -206,32 +220,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     TileAux& ta = aux->t[j];
     const int ebase = ta.info[0], ecount = ta.info[1], abase = ta.info[2], acount = ta.info[3];
     for (int i = threadIdx.x; i < ecount; i += THREADS) ta.idx_l[i] = (uint8_t)(__ldg(p.in_idx + ebase + i) - ebase);
-    for (int r = threadIdx.x; r < ecount + acount; r += THREADS) {
-      const bool bond = r < ecount;
-      const int a = bond ? __ldg(p.src + ebase + r) : abase + (r - ecount);
+    for (int rr = threadIdx.x; rr < 2 * TM; rr += THREADS) {       // every row gets a descriptor: dead rows read zeros
+      const bool bond = rr < TM;
+      const int r = bond ? rr : rr - TM;
+      const bool live = r < (bond ? ecount : acount);
+      const int a = !live ? 0 : (bond ? __ldg(p.src + ebase + r) : abase + r);
       const int skip = bond ? (r ^ 1) : -1;
-      const int pb = __ldg(p.in_ptr + a), pe = __ldg(p.in_ptr + a + 1);
-      uint32_t o[FASTN] = {ZROW * CHP, ZROW * CHP, ZROW * CHP, ZROW * CHP};
+      const int pb = live ? __ldg(p.in_ptr + a) : ebase, pe = live ? __ldg(p.in_ptr + a + 1) : ebase;
+      uint32_t o[2 * FASTN];
+#pragma unroll
+      for (int t = 0; t < 2 * FASTN; ++t) o[t] = ZROW * CHP * 4;
       int cnt = 0;
       for (int t = pb; t < pe; ++t) {
         const int k = __ldg(p.in_idx + t) - ebase;
         if (k == skip) continue;
-        if (cnt < FASTN) o[cnt] = (uint32_t)(k * CHP);
+#pragma unroll
+        for (int u = 0; u < 2 * FASTN; ++u)
+          if (cnt == u) o[u] = (uint32_t)(k * CHP * 4);
         ++cnt;
       }
-      const uint2 packed = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+      const uint4 d1 = make_uint4(o[0], o[1], o[2], o[3]);
+      const uint2 d2 = make_uint2(o[4] | (o[5] << 16), o[6] | (o[7] << 16));
       if (bond) {
-        ta.nbo_b[r] = packed; ta.pb_b[r] = (uint16_t)(pb - ebase);
+        ta.nbd_b[r] = d1; ta.nb2_b[r] = d2; ta.pb_b[r] = (uint16_t)(pb - ebase);
         ta.cnt_b[r] = (uint8_t)(cnt > 255 ? 255 : cnt); ta.full_b[r] = (uint8_t)(pe - pb > 255 ? 255 : pe - pb);
       } else {
-        const int v = r - ecount;
-        ta.nbo_a[v] = packed; ta.pb_a[v] = (uint16_t)(pb - ebase); ta.cnt_a[v] = (uint8_t)(cnt > 255 ? 255 : cnt);
+        ta.nbd_a[r] = d1; ta.nb2_a[r] = d2; ta.pb_a[r] = (uint16_t)(pb - ebase);
+        ta.cnt_a[r] = (uint8_t)(cnt > 255 ? 255 : cnt);
       }
     }
     for (int v = threadIdx.x; v < TM; v += THREADS) ta.tat[v] = 0.f;
   }
   for (int k = threadIdx.x; k < CHP; k += THREADS) y_s[ZROW * CHP + k] = 0.f;
   __syncthreads();
+
+  // 640 threads x 96 registers are allocated at launch: warps 0..3 keep 32, the 16 epilogue warps grow to 112
+#ifdef CGR_SETMAXNREG   // measured: ptxas spills ~1.3 KB per thread with the split budget; off
+  if (warp < 4) umma::reg_dec<CGR_REG_LOW>(); else umma::reg_inc<CGR_REG_HIGH>();
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -316,16 +342,30 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     // readout: one warp per atom row, lanes = column groups (the same warp owns atom v in every chunk)
     constexpr int RSLOTS = (TM + EPI_WARPS - 1) / EPI_WARPS;
     constexpr int RPF = RSLOTS < SLOTS ? RSLOTS : SLOTS;            // readout rows whose Q' operand is requested ahead
-    long long* dbg = p.dbg ? p.dbg + (int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) : nullptr;
+    auto stamp = [&](int i, int w) {                                // debug: clock64 phase stamps
+      if (p.dbg && et == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) + i * 4 + w] = clock64();
+    };
     // h_0 and Q' (outputs of the previous kernels of this forward) are requested by these threads directly, possibly
     // before the producer's first load has landed: every epilogue thread orders itself behind the previous grids
     umma::grid_dep_wait();
+
+    // per-layer scalars staged once (read by every item): 1 / weight scale, learnable skip
+    if (et <= depth) aux->us[et] = __ldg(p.unscale + 1 + et);
+    if (et < depth) aux->skipv[et] = p.skip[et] ? __ldg(p.skip[et]) : 1.f;
+    umma::named_bar_sync(3, EPI_THREADS);
+
+    // item i of this CTA = (tile j of the group, layer l); nt is 1 or 2
+    auto item_tile = [&](int i) { return nt == 2 ? (i & 1) : 0; };
+    auto item_layer = [&](int i) { return nt == 2 ? (i >> 1) : i; };
+    const uint32_t col_b = (uint32_t)(16 * cg);                    // this thread's column group, bytes into a staging row
+    const uint32_t h0_row_step = (uint32_t)(RPP * H) * 4u;         // bytes between two of this thread's h0 rows
+    const uint32_t o_row_step = (uint32_t)RPP * (uint32_t)p.ldo * 2u;   // same for the (hi, lo) output operands
 
     // fp32 operand of the epilogue -- h0 rows of a bond layer, Q' rows of the readout -- for one chunk, requested well
     // before its use (during the previous chunk's staging / the previous item's tail): its L2 latency never shows
     float4 opnd[SLOTS];
     auto request = [&](int i, int ch) {
-      const int j = i % nt, l = i / nt;
+      const int j = item_tile(i), l = item_layer(i);
       const TileAux& ta = aux->t[j];
       const int n = n0 + ch * CH + 4 * (l == depth ? lane : cg);
       const bool col_on = 4 * (l == depth ? lane : cg) < CH && n < n0 + BN && n < H;
@@ -335,10 +375,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       if (l < depth) {
         if (!unit_thread) return;
         const int ecount = ta.info[1];
-        const float* hp = p.h0 + ((int64_t)(tile0 + j) * TM + r0) * H + n;
+        const char* hp = reinterpret_cast<const char*>(p.h0 + ((int64_t)(tile0 + j) * TM + r0) * H + n);
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k)
-          if (r0 + k * RPP < ecount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(hp + (int64_t)k * RPP * H));
+          if (r0 + k * RPP < ecount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(hp + (uint32_t)k * h0_row_step));
       } else {
         const int abase = ta.info[2], acount = ta.info[3];
 #pragma unroll
@@ -351,38 +391,37 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     if (n_items > 0) request(0, 0);
 
     for (int i = 0; i < n_items; ++i) {
-      const int j = i % nt, l = i / nt;
+      const int j = item_tile(i), l = item_layer(i);
       const uint32_t slot = (uint32_t)i & 1u;
       const int tile = tile0 + j;
       const bool readout = l == depth;
       TileAux& ta = aux->t[j];
       const int ecount = ta.info[1], abase = ta.info[2], acount = ta.info[3];
-      const float us = __ldg(p.unscale + 1 + l);
-      const float skip = (!readout && p.skip[l]) ? __ldg(p.skip[l]) : 1.f;
+      const float us = aux->us[l];
+      const float skip = readout ? 1.f : aux->skipv[l];
       const float* cvec = readout ? p.w_ffn : p.bias[l];           // per-column vector of the epilogue: bias / w_ffn
-      // this thread's unit (row r0, column group cg) of the output operand; rows step by RPP, chunks by CH columns
-      const size_t o_item = ((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg;
-      __half* oh_item = p.o_hi[(l + 1) & 1] + o_item;
-      __half* ol_item = p.o_lo[(l + 1) & 1] + o_item;
-      const size_t row_step = (size_t)RPP * (size_t)p.ldo;
-      // this thread's rows of the tile: neighbour descriptors in registers for the whole item
-      uint2 nbo[SLOTS];
-      uint32_t valid = 0, slow = 0;
+      // this thread's unit (row r0, column group cg) of the output operand; rows step by o_row_step bytes, chunks by
+      // CH columns
+      const size_t o_item = (((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg) * 2;
+      char* oh_item = reinterpret_cast<char*>(p.o_hi[(l + 1) & 1]) + o_item;    // lo rows: + p.lo_delta
+      asm volatile("" : "+l"(oh_item));                            // opaque: kept in registers, not recomputed per unit
+      // this thread's rows of the tile: which exist, which have more than FASTN / 2 FASTN neighbours
+      uint32_t valid = 0, slow = 0, vslow = 0;
       if (!readout && unit_thread) {
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k) {
           const int r = r0 + k * RPP;
-          nbo[k] = make_uint2((uint32_t)(ZROW * CHP) * 0x10001u, (uint32_t)(ZROW * CHP) * 0x10001u);
           if (r < ecount) {
             valid |= 1u << k;
-            nbo[k] = ta.nbo_b[r];
-            if (ta.cnt_b[r] > FASTN) slow |= 1u << k;
+            const int c = ta.cnt_b[r];
+            if (c > FASTN) slow |= 1u << k;
+            if (c > 2 * FASTN) vslow |= 1u << k;
           }
         }
       }
       umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
       umma::tc_fence_after_sync();
-      if (dbg && et == 0) dbg[i * 4 + 0] = clock64();
+      stamp(i, 0);
       const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
       float vmax = 0.f;
 #pragma unroll 1
@@ -407,20 +446,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
               dst[1] = make_float4((v[4] + v2[4]) * us, (v[5] + v2[5]) * us, (v[6] + v2[6]) * us, (v[7] + v2[7]) * us);
             }
           } else {
-            float v[NGW][8];
-#pragma unroll
-            for (int gi = 0; gi < NGW; ++gi) {                     // all loads of the warp in flight, one wait
-              const int cc = (grp + 4 * gi) * 8;
-              if (cc < cw) umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v[gi]);
-            }
-            umma::tmem_ld_wait();
 #pragma unroll
             for (int gi = 0; gi < NGW; ++gi) {
               const int cc = (grp + 4 * gi) * 8;
               if (cc < cw) {
+                float v[8];
+                umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v);
+                umma::tmem_ld_wait();
                 float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
-                dst[0] = make_float4(v[gi][0] * us, v[gi][1] * us, v[gi][2] * us, v[gi][3] * us);
-                dst[1] = make_float4(v[gi][4] * us, v[gi][5] * us, v[gi][6] * us, v[gi][7] * us);
+                dst[0] = make_float4(v[0] * us, v[1] * us, v[2] * us, v[3] * us);
+                dst[1] = make_float4(v[4] * us, v[5] * us, v[6] * us, v[7] * us);
               }
             }
           }
@@ -435,30 +470,49 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         if (!readout) {
           // z[e] = sum_{k in in(src e), k != e^1} y[k] + b + skip * h0[e];  h' = act(z) -> next operand (hi, lo)
           if (col_on && unit_thread) {
-            const float* y_c = y_s + 4 * cg;
-            __half* oh = oh_item + ch * CH;                         // this thread's column group of row r0
-            __half* ol = ol_item + ch * CH;
+            const char* y_b = reinterpret_cast<const char*>(y_s);
+            char* oh = oh_item + ch * (CH * 2);                     // this thread's column group of row r0
+            const char* y_bc = y_b + col_b;                         // this thread's column group of staging row 0
+            const uint32_t fastm = valid & ~vslow;
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
-              float4 a4 = gather4(y_c, nbo[k]);                     // rows beyond the tile read the zero row
-              if (slow & (1u << k)) {                               // more than FASTN neighbours: the full CSR list
-                const int r = r0 + k * RPP;
-                a4 = gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
-              }
-              float4 z;
-              z.x = tcg::act_t<RELU>(fmaf(skip, opnd[k].x, a4.x + c4.x), p.act);
-              z.y = tcg::act_t<RELU>(fmaf(skip, opnd[k].y, a4.y + c4.y), p.act);
-              z.z = tcg::act_t<RELU>(fmaf(skip, opnd[k].z, a4.z + c4.z), p.act);
-              z.w = tcg::act_t<RELU>(fmaf(skip, opnd[k].w, a4.w + c4.w), p.act);
-              if (valid & (1u << k)) {
+              const int r = r0 + k * RPP < TM ? r0 + k * RPP : TM - 1;
+              float4 a4 = gather4(y_bc, ta.nbd_b[r]);               // dead rows read the zero row
+              if (slow & (1u << k)) tcg::add4(a4, gather4p(y_bc, ta.nb2_b[r]));   // neighbours 5..8 (one row in 25)
+              float4 z;                                             // b + skip * h0 is independent of the gather
+              z.x = tcg::act_t<RELU>(a4.x + fmaf(skip, opnd[k].x, c4.x), p.act);
+              z.y = tcg::act_t<RELU>(a4.y + fmaf(skip, opnd[k].y, c4.y), p.act);
+              z.z = tcg::act_t<RELU>(a4.z + fmaf(skip, opnd[k].z, c4.z), p.act);
+              z.w = tcg::act_t<RELU>(a4.w + fmaf(skip, opnd[k].w, c4.w), p.act);
+              if (fastm & (1u << k)) {
                 vmax = fmaxf(vmax, tcg::amax4(z));
-                tcg::store_split4(z, 1.f, oh + (size_t)k * row_step, ol + (size_t)k * row_step);
+                char* od = oh + (uint32_t)k * o_row_step;
+                tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
+              }
+            }
+            if (vslow) {
+              // cold path, kept out of the loop above: rows with more than 2 FASTN neighbours (an atom with ten or
+              // more bonds) walk their full CSR list
+#pragma unroll
+              for (int k = 0; k < SLOTS; ++k) {
+                if (vslow & (1u << k)) {
+                  const int r = r0 + k * RPP;
+                  const float4 a4 = gather_list<CHP>(y_bc, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
+                  float4 z;
+                  z.x = tcg::act_t<RELU>(a4.x + fmaf(skip, opnd[k].x, c4.x), p.act);
+                  z.y = tcg::act_t<RELU>(a4.y + fmaf(skip, opnd[k].y, c4.y), p.act);
+                  z.z = tcg::act_t<RELU>(a4.z + fmaf(skip, opnd[k].z, c4.z), p.act);
+                  z.w = tcg::act_t<RELU>(a4.w + fmaf(skip, opnd[k].w, c4.w), p.act);
+                  vmax = fmaxf(vmax, tcg::amax4(z));
+                  char* od = oh + (uint32_t)k * o_row_step;
+                  tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
+                }
               }
             }
           }
         } else {
           // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
-          const float* y_c = y_s + 4 * lane;
+          const char* y_c = reinterpret_cast<const char*>(y_s + 4 * lane);
 #pragma unroll
           for (int k = 0; k < RSLOTS; ++k) {
             const int v = ew + k * EPI_WARPS;
@@ -468,8 +522,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
               float4 a4 = k < RPF ? opnd[k < RPF ? k : 0]
                                   : __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
               const int cnt = ta.cnt_a[v];
-              tcg::add4(a4, cnt <= FASTN ? gather4(y_c, ta.nbo_a[v])
-                                         : gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_a[v], cnt, -1));
+              if (cnt <= 2 * FASTN) {
+                tcg::add4(a4, gather4(y_c, ta.nbd_a[v]));
+                if (cnt > FASTN) tcg::add4(a4, gather4p(y_c, ta.nb2_a[v]));
+              } else {
+                tcg::add4(a4, gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_a[v], cnt, -1));
+              }
               t = tcg::act_t<RELU>(a4.x, p.act) * c4.x;
               t = fmaf(tcg::act_t<RELU>(a4.y, p.act), c4.y, t);
               t = fmaf(tcg::act_t<RELU>(a4.z, p.act), c4.z, t);
@@ -484,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         if (ch + 1 < NCH) request(i, ch + 1);
         else if (i + 1 < n_items) request(i + 1, 0);
       }
-      if (dbg && et == 0) dbg[i * 4 + 1] = clock64();
+      stamp(i, 1);
 
       if (!readout) {
         // this CTA's slice of h_{l+1} is stored: make it visible to the peers' TMA loads, then tell every CTA of the cluster
@@ -492,10 +550,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           atomicOr(p.overflow, 1);
           atomicOr(p.tile_counter + tile, 0x10000);
         }
-        __threadfence();
+        // the writers order their stores against the peers' TMA reads (proxy fence) and meet at the barrier; the
+        // arriving threads then publish the whole slice: their fence + release is cumulative over everything the
+        // barrier ordered before it (the grid-sync pattern: bar.sync, then one thread fences and signals)
         umma::fence_proxy_async();
         umma::named_bar_sync(3, EPI_THREADS);
-        if (et < S) umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[j]), (uint32_t)et);
+        if (et < S) {
+          __threadfence();
+          umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[j]), (uint32_t)et);
+        }
       } else {
         umma::named_bar_sync(3, EPI_THREADS);                      // every atom's dot product is complete
         const int rx0 = ta.info[4], rxcount = ta.info[5];
@@ -526,7 +589,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           if (et == 0) p.tile_counter[tile] = 0;                    // ready for the next forward
         }
       }
-      if (dbg && et == 0) dbg[i * 4 + 2] = clock64();
+      stamp(i, 2);
     }
   }
 
