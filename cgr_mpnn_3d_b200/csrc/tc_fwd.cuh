@@ -11,13 +11,16 @@
 // wait can never deadlock, whatever else runs on the device.
 //
 // Warp roles (persistent over the items (tile, layer) of the group):
-//   warp 0       TMA producer: weight chunks are requested as soon as a stage is free (they never depend on a peer),
-//                the activation chunks once the tile's previous layer is complete cluster-wide
-//   warp 1       tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x 256 columns)
-//   warp 2       TMEM allocation
-//   warps 4..15  epilogue: TMEM -> fp32 staging rows -> gather / activation / split -> global
-// With two tiles per cluster the epilogue of tile X, layer l overlaps the MMAs of tile Y, layer l, and so on:
-// the dependency chain of one tile hides behind the other tile's work.
+//   warp 0        TMA producer: weight chunks are requested as soon as a stage is free (they never depend on a peer),
+//                 the activation chunks once the tile's previous layer is complete cluster-wide
+//   warp 1        tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 2        TMEM allocation
+//   warps 4..7    staging: TMEM -> fp32 rows of a two-buffer ring in shared memory, 32 columns per chunk
+//   warps 8..23   gather: staged rows -> gather / activation / split -> global; they never touch TMEM
+// The staging and gather warps meet through mbarriers only (full / empty per ring buffer): no CTA-wide barrier per
+// chunk, a slow gather warp is absorbed by the second buffer, and the accumulator is released as soon as its last
+// chunk is staged.  With two tiles per cluster the epilogue of tile X, layer l overlaps the MMAs of tile Y, layer l,
+// and so on: the dependency chain of one tile hides behind the other tile's work.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -29,9 +32,10 @@ using tcg::NBR;
 using tcg::TM;
 
 constexpr int MAX_LAYERS = 16;                 // bond layers + readout
-constexpr int EPI_WARPS = 16;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = 128 + EPI_THREADS;     // 640
+constexpr int STG_WARPS = 4;                   // one per TMEM lane quarter
+constexpr int GAT_WARPS = 16;
+constexpr int GAT_THREADS = GAT_WARPS * 32;
+constexpr int THREADS = 128 + STG_WARPS * 32 + GAT_THREADS;     // 768
 constexpr int ZROW = TM;                       // staging row that stays zero: target of unused neighbour slots
 constexpr int SLOT_COLS = 256;                 // TMEM columns per accumulator slot
 constexpr int MAX_TPC = 2;                     // tiles per cluster (ping-pong)
@@ -48,20 +52,19 @@ struct FCfg {
   static constexpr bool CAT = 2 * BN <= 256;                   // A_hi x [B_hi ; B_lo] as one MMA of N = 2 BN
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int CH = BN > 128 ? 72 : BN;                // epilogue column chunk (208 = 72 + 72 + 64)
+  static constexpr int CH = 32;                                 // columns per staged chunk
   static constexpr int NCH = (BN + CH - 1) / CH;
-  static constexpr int UPR = CH / 4;                           // float4 column groups of a chunk
-  static constexpr int RPP = EPI_THREADS / UPR;                // bond rows the epilogue threads cover per pass
-  static constexpr int ACTIVE = RPP * UPR;                     // threads that own a (row, column group) unit
-  static constexpr int SLOTS = (TM + RPP - 1) / RPP;           // passes: units per thread and chunk
-  static constexpr int CHP = ((CH / 4) % 2 == 1) ? CH : CH + 4;     // staging row pitch: odd multiple of 4 floats
-  static constexpr int Y_BYTES = ((TM + 1) * CHP * 4 + 1023) / 1024 * 1024;     // + the zero row
-  static constexpr int NGW = (CH / 8 + 3) / 4;                 // 8-column TMEM groups per warp and chunk
+  static constexpr int UPR = CH / 4;                           // float4 column groups of a chunk: 8 lanes per row
+  static constexpr int RPP = GAT_THREADS / UPR;                // rows the gather threads cover per pass: 64
+  static constexpr int SLOTS = TM / RPP;                       // passes: units per thread and chunk: 2
+  static constexpr int CHP = CH + 4;                           // staging row pitch: 36 floats (conflict-free rows)
+  static constexpr int YBUF_BYTES = ((TM + 1) * CHP * 4 + 127) / 128 * 128;     // one ring buffer, + the zero row
+  static constexpr int Y_BYTES = 2 * YBUF_BYTES;
   static constexpr int AUX_BYTES = 16384;
   static constexpr int FIT = (SMEM_LIMIT - 1024 - Y_BYTES - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 4 ? 4 : FIT;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Y_BYTES + AUX_BYTES;
-  static_assert(BN % 16 == 0 && BN <= 256 && CH % 8 == 0 && UPR <= 32, "bad slice width");
+  static_assert(BN % 16 == 0 && BN <= 256 && TM % RPP == 0 && 32 % UPR == 0, "bad slice width");
   static_assert(STAGES >= 2, "pipeline needs two stages");
   static_assert((CAT ? 2 * BN : BN) <= SLOT_COLS, "accumulator exceeds its TMEM slot");
   static_assert((TM + 1) * CHP * 4 < 65536, "staging byte offsets must fit 16 bits");
@@ -120,6 +123,8 @@ struct Aux {
   uint64_t empty[4];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t st_full[2];          // staging ring: buffer b holds a complete chunk (the STG_WARPS arrived)
+  uint64_t st_empty[2];         // every gather warp has consumed buffer b
   uint64_t ready[MAX_TPC];      // tile j's operand of the next layer is complete in every CTA of the cluster
   uint32_t tmem_base;
   float us[MAX_LAYERS + 1];     // 1 / weight scale of every layer's matrix (staged once: no global load per item)
@@ -189,7 +194,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       umma::mbar_init(umma::smem_u32(&aux->tmem_full[s]), 1);
-      umma::mbar_init(umma::smem_u32(&aux->tmem_empty[s]), EPI_WARPS);
+      umma::mbar_init(umma::smem_u32(&aux->tmem_empty[s]), STG_WARPS);
+      umma::mbar_init(umma::smem_u32(&aux->st_full[s]), STG_WARPS);
+      umma::mbar_init(umma::smem_u32(&aux->st_empty[s]), GAT_WARPS);
     }
     for (int j = 0; j < MAX_TPC; ++j) umma::mbar_init(umma::smem_u32(&aux->ready[j]), (uint32_t)S);
     umma::mbar_fence_init();
@@ -251,7 +258,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     }
     for (int v = threadIdx.x; v < TM; v += THREADS) ta.tat[v] = 0.f;
   }
-  for (int k = threadIdx.x; k < CHP; k += THREADS) y_s[ZROW * CHP + k] = 0.f;
+  for (int k = threadIdx.x; k < 2 * CHP; k += THREADS)              // the zero row of both ring buffers
+    y_s[(k / CHP) * (C::YBUF_BYTES / 4) + ZROW * CHP + (k % CHP)] = 0.f;
+  // per-layer scalars staged once: 1 / weight scale (written by the weight preparation, complete before the first
+  // kernel of this forward started), learnable skip
+  if ((int)threadIdx.x <= depth) aux->us[threadIdx.x] = __ldg(p.unscale + 1 + threadIdx.x);
+  if ((int)threadIdx.x < depth) aux->skipv[threadIdx.x] = p.skip[threadIdx.x] ? __ldg(p.skip[threadIdx.x]) : 1.f;
   __syncthreads();
 
   // 640 threads x 96 registers are allocated at launch: warps 0..3 keep 32, the 16 epilogue warps grow to 112
@@ -331,214 +343,195 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue warps
-    constexpr int RPP = C::RPP, SLOTS = C::SLOTS, NGW = C::NGW;
-    const int ew = warp - 4, et = (int)threadIdx.x - 128;
-    const int q = warp & 3, grp = ew >> 2;                          // TMEM lane quarter of this warp, column-group phase
-    // bond layers: thread et owns column group cg of the rows r0, r0 + RPP, ... (SLOTS of them) in every chunk
-    const int cg = et % UPR, r0 = et / UPR;
-    const bool unit_thread = et < C::ACTIVE;
-    // readout: one warp per atom row, lanes = column groups (the same warp owns atom v in every chunk)
-    constexpr int RSLOTS = (TM + EPI_WARPS - 1) / EPI_WARPS;
-    constexpr int RPF = RSLOTS < SLOTS ? RSLOTS : SLOTS;            // readout rows whose Q' operand is requested ahead
+  } else if (warp >= 4 && warp < 4 + STG_WARPS) {
+    // ------------------------------------------------------------------ staging warps: TMEM -> ring buffer
+    const int q = warp & 3;                                         // TMEM lane quarter of this warp
+    const int row = q * 32 + lane;
+    uint32_t c = 0;                                                 // chunks staged so far (ring position)
+    for (int i = 0; i < n_items; ++i) {
+      const uint32_t slot = (uint32_t)i & 1u;
+      const float us = aux->us[nt == 2 ? (i >> 1) : i];
+      umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
+      umma::tc_fence_after_sync();
+      const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch, ++c) {
+        const int cw = (ch + 1) * CH <= BN ? CH : BN - ch * CH;    // columns of this chunk (the last one may be shorter)
+        const uint32_t buf = c & 1u;
+        umma::mbar_wait(umma::smem_u32(&aux->st_empty[buf]), ((c >> 1) & 1u) ^ 1u);
+        float* dst_row = y_s + buf * (C::YBUF_BYTES / 4) + row * CHP;
+        if (C::CAT && !p.fast) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                             // two 8-column groups at a time: hi.hi + hi.lo parts
+            float v[2][8], v2[2][8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int cc = (2 * h + g) * 8;
+              if (cc < cw) {
+                umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v[g]);
+                umma::tmem_ld_x8(acc + (uint32_t)(BN + ch * CH + cc), v2[g]);
+              }
+            }
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int cc = (2 * h + g) * 8;
+              if (cc < cw) {
+                float4* dst = reinterpret_cast<float4*>(dst_row + cc);
+                dst[0] = make_float4((v[g][0] + v2[g][0]) * us, (v[g][1] + v2[g][1]) * us, (v[g][2] + v2[g][2]) * us,
+                                     (v[g][3] + v2[g][3]) * us);
+                dst[1] = make_float4((v[g][4] + v2[g][4]) * us, (v[g][5] + v2[g][5]) * us, (v[g][6] + v2[g][6]) * us,
+                                     (v[g][7] + v2[g][7]) * us);
+              }
+            }
+          }
+        } else {
+          float v[CH / 8][8];
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g)                           // all loads of the chunk in flight, one wait
+            if (g * 8 < cw) umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + g * 8), v[g]);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) {
+            if (g * 8 < cw) {
+              float4* dst = reinterpret_cast<float4*>(dst_row + g * 8);
+              dst[0] = make_float4(v[g][0] * us, v[g][1] * us, v[g][2] * us, v[g][3] * us);
+              dst[1] = make_float4(v[g][4] * us, v[g][5] * us, v[g][6] * us, v[g][7] * us);
+            }
+          }
+        }
+        if (ch == NCH - 1) umma::tc_fence_before_sync();            // accumulator drained: the MMA warp may reuse it
+        __syncwarp();
+        if (lane == 0) {
+          if (ch == NCH - 1) umma::mbar_arrive(umma::smem_u32(&aux->tmem_empty[slot]));
+          umma::mbar_arrive(umma::smem_u32(&aux->st_full[buf]));    // release: the warp's rows are in the buffer
+        }
+      }
+    }
+  } else if (warp >= 4 + STG_WARPS) {
+    // ------------------------------------------------------------------ gather warps
+    constexpr int RPP = C::RPP, SLOTS = C::SLOTS;
+    const int et = (int)threadIdx.x - (128 + STG_WARPS * 32);       // 0 .. GAT_THREADS - 1
+    // thread et owns column group cg (4 columns) of the rows r0, r0 + RPP in every chunk: 8 lanes per row, so a
+    // warp reads four 128-byte row segments per load (no bank conflicts) and writes 64-byte segments
+    const int cg = et & (UPR - 1), r0 = et / UPR;
+    const uint32_t col_b = (uint32_t)(16 * cg);                    // this thread's column group, bytes into a staging row
+    const uint32_t h0_row_step = (uint32_t)(RPP * H) * 4u;         // bytes between this thread's two h0 rows
+    const uint32_t pq_row_step = (uint32_t)(RPP * 2 * H) * 4u;     // ... its two Q' rows
+    const uint32_t o_row_step = (uint32_t)RPP * (uint32_t)p.ldo * 2u;   // ... its two (hi, lo) output rows
     auto stamp = [&](int i, int w) {                                // debug: clock64 phase stamps
       if (p.dbg && et == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) + i * 4 + w] = clock64();
     };
-    // h_0 and Q' (outputs of the previous kernels of this forward) are requested by these threads directly, possibly
-    // before the producer's first load has landed: every epilogue thread orders itself behind the previous grids
-    umma::grid_dep_wait();
-
-    // per-layer scalars staged once (read by every item): 1 / weight scale, learnable skip
-    if (et <= depth) aux->us[et] = __ldg(p.unscale + 1 + et);
-    if (et < depth) aux->skipv[et] = p.skip[et] ? __ldg(p.skip[et]) : 1.f;
-    umma::named_bar_sync(3, EPI_THREADS);
-
     // item i of this CTA = (tile j of the group, layer l); nt is 1 or 2
     auto item_tile = [&](int i) { return nt == 2 ? (i & 1) : 0; };
     auto item_layer = [&](int i) { return nt == 2 ? (i >> 1) : i; };
-    const uint32_t col_b = (uint32_t)(16 * cg);                    // this thread's column group, bytes into a staging row
-    const uint32_t h0_row_step = (uint32_t)(RPP * H) * 4u;         // bytes between two of this thread's h0 rows
-    const uint32_t o_row_step = (uint32_t)RPP * (uint32_t)p.ldo * 2u;   // same for the (hi, lo) output operands
+    // h_0 and Q' (outputs of the previous kernels of this forward) are read by these threads directly
+    umma::grid_dep_wait();
 
-    // fp32 operand of the epilogue -- h0 rows of a bond layer, Q' rows of the readout -- for one chunk, requested well
-    // before its use (during the previous chunk's staging / the previous item's tail): its L2 latency never shows
-    float4 opnd[SLOTS];
+    // operands of one chunk, requested one chunk ahead (their L2 latency never shows): the fp32 rows added after the
+    // gather (h0 of a bond layer, Q' of the readout) and the per-column vector (bias / w_ffn)
+    float4 opnd[SLOTS], c4;
     auto request = [&](int i, int ch) {
       const int j = item_tile(i), l = item_layer(i);
       const TileAux& ta = aux->t[j];
-      const int n = n0 + ch * CH + 4 * (l == depth ? lane : cg);
-      const bool col_on = 4 * (l == depth ? lane : cg) < CH && n < n0 + BN && n < H;
+      const int n = n0 + ch * CH + 4 * cg;
+      const bool col_on = ch * CH + 4 * cg < BN && n < H;
 #pragma unroll
       for (int k = 0; k < SLOTS; ++k) opnd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      c4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (!col_on) return;
       if (l < depth) {
-        if (!unit_thread) return;
+        c4 = ldg4(p.bias[l] + n);
         const int ecount = ta.info[1];
         const char* hp = reinterpret_cast<const char*>(p.h0 + ((int64_t)(tile0 + j) * TM + r0) * H + n);
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k)
           if (r0 + k * RPP < ecount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(hp + (uint32_t)k * h0_row_step));
       } else {
+        c4 = ldg4(p.w_ffn + n);
         const int abase = ta.info[2], acount = ta.info[3];
+        const char* qp = reinterpret_cast<const char*>(p.PQ + (int64_t)(abase + r0) * (2 * H) + H + n);
 #pragma unroll
-        for (int k = 0; k < RPF; ++k) {
-          const int v = ew + k * EPI_WARPS;
-          if (v < acount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
-        }
+        for (int k = 0; k < SLOTS; ++k)
+          if (r0 + k * RPP < acount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(qp + (uint32_t)k * pq_row_step));
       }
     };
-    if (n_items > 0) request(0, 0);
+    request(0, 0);
 
+    uint32_t c = 0;                                                 // chunks consumed so far (ring position)
     for (int i = 0; i < n_items; ++i) {
       const int j = item_tile(i), l = item_layer(i);
-      const uint32_t slot = (uint32_t)i & 1u;
       const int tile = tile0 + j;
       const bool readout = l == depth;
       TileAux& ta = aux->t[j];
-      const int ecount = ta.info[1], abase = ta.info[2], acount = ta.info[3];
-      const float us = aux->us[l];
+      const int abase = ta.info[2];
+      const int count = readout ? ta.info[3] : ta.info[1];          // live rows of this item: atoms / bonds
       const float skip = readout ? 1.f : aux->skipv[l];
-      const float* cvec = readout ? p.w_ffn : p.bias[l];           // per-column vector of the epilogue: bias / w_ffn
-      // this thread's unit (row r0, column group cg) of the output operand; rows step by o_row_step bytes, chunks by
-      // CH columns
-      const size_t o_item = (((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg) * 2;
-      char* oh_item = reinterpret_cast<char*>(p.o_hi[(l + 1) & 1]) + o_item;    // lo rows: + p.lo_delta
+      const uint4* nbd = readout ? ta.nbd_a : ta.nbd_b;
+      const uint2* nb2 = readout ? ta.nb2_a : ta.nb2_b;
+      // this thread's unit (row r0, column group cg) of the output operand; the lo rows sit p.lo_delta bytes further
+      char* oh_item = reinterpret_cast<char*>(p.o_hi[(l + 1) & 1]) +
+                      (((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg) * 2;
       asm volatile("" : "+l"(oh_item));                            // opaque: kept in registers, not recomputed per unit
-      // this thread's rows of the tile: which exist, which have more than FASTN / 2 FASTN neighbours
+      // this thread's rows: which exist, which have more than FASTN / 2 FASTN neighbours
       uint32_t valid = 0, slow = 0, vslow = 0;
-      if (!readout && unit_thread) {
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-          const int r = r0 + k * RPP;
-          if (r < ecount) {
-            valid |= 1u << k;
-            const int c = ta.cnt_b[r];
-            if (c > FASTN) slow |= 1u << k;
-            if (c > 2 * FASTN) vslow |= 1u << k;
-          }
+      for (int k = 0; k < SLOTS; ++k) {
+        const int r = r0 + k * RPP;
+        if (r < count) {
+          valid |= 1u << k;
+          const int cn = readout ? ta.cnt_a[r] : ta.cnt_b[r];
+          if (cn > FASTN) slow |= 1u << k;
+          if (cn > 2 * FASTN) vslow |= 1u << k;
         }
       }
-      umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
-      umma::tc_fence_after_sync();
-      stamp(i, 0);
-      const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
       float vmax = 0.f;
+      float tsum[SLOTS];                                            // readout: this thread's part of hv[v] . w_f
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) tsum[k] = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int cw = (ch + 1) * CH <= BN ? CH : BN - ch * CH;    // columns of this chunk (the last one may be shorter)
-        const int ncol0 = n0 + ch * CH;                            // first global column of this chunk
-        const int n = ncol0 + 4 * (readout ? lane : cg);
-        const bool col_on = 4 * (readout ? lane : cg) < cw && n < H;
-        const float4 c4 = col_on ? ldg4(cvec + n) : make_float4(0.f, 0.f, 0.f, 0.f);   // in flight during the staging
-        umma::named_bar_sync(1, EPI_THREADS);                      // the staging rows of the previous chunk are drained
-        {
-          // TMEM -> registers -> staging rows (fp32, unscaled).  Warp: lane quarter q, every fourth 8-column group
-          const int row = q * 32 + lane;
-          if (C::CAT && !p.fast) {
-            for (int cc = grp * 8; cc < cw; cc += 32) {
-              float v[8], v2[8];
-              umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v);
-              umma::tmem_ld_x8(acc + (uint32_t)(BN + ch * CH + cc), v2);
-              umma::tmem_ld_wait();
-              float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
-              dst[0] = make_float4((v[0] + v2[0]) * us, (v[1] + v2[1]) * us, (v[2] + v2[2]) * us, (v[3] + v2[3]) * us);
-              dst[1] = make_float4((v[4] + v2[4]) * us, (v[5] + v2[5]) * us, (v[6] + v2[6]) * us, (v[7] + v2[7]) * us);
-            }
-          } else {
+      for (int ch = 0; ch < NCH; ++ch, ++c) {
+        const int n = n0 + ch * CH + 4 * cg;
+        const bool col_on = ch * CH + 4 * cg < BN && n < H;
+        const uint32_t buf = c & 1u;
+        umma::mbar_wait(umma::smem_u32(&aux->st_full[buf]), (c >> 1) & 1u);
+        if (ch == 0) stamp(i, 0);
+        const char* y_bc = reinterpret_cast<const char*>(y_s) + buf * C::YBUF_BYTES + col_b;
+        if (col_on) {
+          char* oh = oh_item + ch * (CH * 2);
 #pragma unroll
-            for (int gi = 0; gi < NGW; ++gi) {
-              const int cc = (grp + 4 * gi) * 8;
-              if (cc < cw) {
-                float v[8];
-                umma::tmem_ld_x8(acc + (uint32_t)(ch * CH + cc), v);
-                umma::tmem_ld_wait();
-                float4* dst = reinterpret_cast<float4*>(y_s + row * CHP + cc);
-                dst[0] = make_float4(v[0] * us, v[1] * us, v[2] * us, v[3] * us);
-                dst[1] = make_float4(v[4] * us, v[5] * us, v[6] * us, v[7] * us);
-              }
-            }
-          }
-        }
-        if (ch == NCH - 1) {                                       // accumulator drained: the MMA warp may reuse the slot
-          umma::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) umma::mbar_arrive(umma::smem_u32(&aux->tmem_empty[slot]));
-        }
-        umma::named_bar_sync(2, EPI_THREADS);                      // staging rows complete
-
-        if (!readout) {
-          // z[e] = sum_{k in in(src e), k != e^1} y[k] + b + skip * h0[e];  h' = act(z) -> next operand (hi, lo)
-          if (col_on && unit_thread) {
-            const char* y_b = reinterpret_cast<const char*>(y_s);
-            char* oh = oh_item + ch * (CH * 2);                     // this thread's column group of row r0
-            const char* y_bc = y_b + col_b;                         // this thread's column group of staging row 0
-            const uint32_t fastm = valid & ~vslow;
-#pragma unroll
-            for (int k = 0; k < SLOTS; ++k) {
-              const int r = r0 + k * RPP < TM ? r0 + k * RPP : TM - 1;
-              float4 a4 = gather4(y_bc, ta.nbd_b[r]);               // dead rows read the zero row
-              if (slow & (1u << k)) tcg::add4(a4, gather4p(y_bc, ta.nb2_b[r]));   // neighbours 5..8 (one row in 25)
-              float4 z;                                             // b + skip * h0 is independent of the gather
+          for (int k = 0; k < SLOTS; ++k) {
+            const int r = r0 + k * RPP;
+            float4 a4 = gather4(y_bc, nbd[r]);                      // dead rows and unused slots read the zero row
+            if (slow & (1u << k)) tcg::add4(a4, gather4p(y_bc, nb2[r]));          // neighbours 5..8 (one row in 25)
+            if (vslow & (1u << k))                                  // an atom with ten or more bonds: walk the CSR list
+              a4 = readout ? gather_list<CHP>(y_bc, ta.idx_l, (int)ta.pb_a[r], (int)ta.cnt_a[r], -1)
+                           : gather_list<CHP>(y_bc, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
+            if (!readout) {
+              // z[e] = sum_{k in in(src e), k != e^1} y[k] + b + skip * h0[e];  h' = act(z) -> next operand (hi, lo)
+              float4 z;
               z.x = tcg::act_t<RELU>(a4.x + fmaf(skip, opnd[k].x, c4.x), p.act);
               z.y = tcg::act_t<RELU>(a4.y + fmaf(skip, opnd[k].y, c4.y), p.act);
               z.z = tcg::act_t<RELU>(a4.z + fmaf(skip, opnd[k].z, c4.z), p.act);
               z.w = tcg::act_t<RELU>(a4.w + fmaf(skip, opnd[k].w, c4.w), p.act);
-              if (fastm & (1u << k)) {
+              if (valid & (1u << k)) {
                 vmax = fmaxf(vmax, tcg::amax4(z));
                 char* od = oh + (uint32_t)k * o_row_step;
                 tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
               }
+            } else {
+              // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this thread's columns
+              float t = tcg::act_t<RELU>(a4.x + opnd[k].x, p.act) * c4.x;
+              t = fmaf(tcg::act_t<RELU>(a4.y + opnd[k].y, p.act), c4.y, t);
+              t = fmaf(tcg::act_t<RELU>(a4.z + opnd[k].z, p.act), c4.z, t);
+              t = fmaf(tcg::act_t<RELU>(a4.w + opnd[k].w, p.act), c4.w, t);
+              tsum[k] += t;
             }
-            if (vslow) {
-              // cold path, kept out of the loop above: rows with more than 2 FASTN neighbours (an atom with ten or
-              // more bonds) walk their full CSR list
-#pragma unroll
-              for (int k = 0; k < SLOTS; ++k) {
-                if (vslow & (1u << k)) {
-                  const int r = r0 + k * RPP;
-                  const float4 a4 = gather_list<CHP>(y_bc, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
-                  float4 z;
-                  z.x = tcg::act_t<RELU>(a4.x + fmaf(skip, opnd[k].x, c4.x), p.act);
-                  z.y = tcg::act_t<RELU>(a4.y + fmaf(skip, opnd[k].y, c4.y), p.act);
-                  z.z = tcg::act_t<RELU>(a4.z + fmaf(skip, opnd[k].z, c4.z), p.act);
-                  z.w = tcg::act_t<RELU>(a4.w + fmaf(skip, opnd[k].w, c4.w), p.act);
-                  vmax = fmaxf(vmax, tcg::amax4(z));
-                  char* od = oh + (uint32_t)k * o_row_step;
-                  tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
-                }
-              }
-            }
-          }
-        } else {
-          // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this chunk's columns
-          const char* y_c = reinterpret_cast<const char*>(y_s + 4 * lane);
-#pragma unroll
-          for (int k = 0; k < RSLOTS; ++k) {
-            const int v = ew + k * EPI_WARPS;
-            if (k * EPI_WARPS >= acount) break;                    // warp-uniform: no row of this step exists
-            float t = 0.f;
-            if (col_on && v < acount) {
-              float4 a4 = k < RPF ? opnd[k < RPF ? k : 0]
-                                  : __ldcg(reinterpret_cast<const float4*>(p.PQ + (int64_t)(abase + v) * (2 * H) + H + n));
-              const int cnt = ta.cnt_a[v];
-              if (cnt <= 2 * FASTN) {
-                tcg::add4(a4, gather4(y_c, ta.nbd_a[v]));
-                if (cnt > FASTN) tcg::add4(a4, gather4p(y_c, ta.nb2_a[v]));
-              } else {
-                tcg::add4(a4, gather_list<CHP>(y_c, ta.idx_l, (int)ta.pb_a[v], cnt, -1));
-              }
-              t = tcg::act_t<RELU>(a4.x, p.act) * c4.x;
-              t = fmaf(tcg::act_t<RELU>(a4.y, p.act), c4.y, t);
-              t = fmaf(tcg::act_t<RELU>(a4.z, p.act), c4.z, t);
-              t = fmaf(tcg::act_t<RELU>(a4.w, p.act), c4.w, t);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0 && v < acount) ta.tat[v] += t;
           }
         }
-        // the operand of the next chunk (or of the next item's first chunk) goes in flight now
+        __syncwarp();                                               // every lane's reads of the buffer are done
+        if (lane == 0) umma::mbar_arrive(umma::smem_u32(&aux->st_empty[buf]));
+        // the operands of the next chunk (or of the next item's first chunk) go in flight now
         if (ch + 1 < NCH) request(i, ch + 1);
         else if (i + 1 < n_items) request(i + 1, 0);
       }
@@ -554,15 +547,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         // arriving threads then publish the whole slice: their fence + release is cumulative over everything the
         // barrier ordered before it (the grid-sync pattern: bar.sync, then one thread fences and signals)
         umma::fence_proxy_async();
-        umma::named_bar_sync(3, EPI_THREADS);
+        umma::named_bar_sync(3, GAT_THREADS);
         if (et < S) {
           __threadfence();
           umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[j]), (uint32_t)et);
         }
       } else {
-        umma::named_bar_sync(3, EPI_THREADS);                      // every atom's dot product is complete
+        // the 8 lanes of a row add their parts in a fixed tree order: the atom's dot product with w_f
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+          float t = tsum[k];
+#pragma unroll
+          for (int o = UPR / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (cg == 0) ta.tat[r0 + k * RPP] = t;
+        }
+        umma::named_bar_sync(3, GAT_THREADS);                      // every atom's dot product is complete
         const int rx0 = ta.info[4], rxcount = ta.info[5];
-        for (int rx = et; rx < rxcount; rx += EPI_THREADS) {
+        for (int rx = et; rx < rxcount; rx += GAT_THREADS) {
           const int b = rx0 + rx;
           const int v0 = __ldg(p.atom_ptr + b) - abase, v1 = __ldg(p.atom_ptr + b + 1) - abase;
           float s = 0.f;
@@ -571,16 +572,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         }
         // the last slice CTA of this tile to arrive adds the slices in a fixed order: deterministic, no extra kernel
         __threadfence();
-        umma::named_bar_sync(3, EPI_THREADS);
+        umma::named_bar_sync(3, GAT_THREADS);
         if (et == 0) ta.ticket = atomicAdd(p.tile_counter + tile, 1);
-        umma::named_bar_sync(3, EPI_THREADS);
+        umma::named_bar_sync(3, GAT_THREADS);
         const int ticket = ta.ticket;
         if ((ticket & 0xffff) == S - 1) {
           __threadfence();
           const float bf = __ldg(p.b_ffn);
           // an operand of this tile (or a feature / h_0 of the batch) left the fp16 range: NaN energies, never silent
           const bool poisoned = (ticket & 0x10000) != 0 || (__ldcg(p.overflow) & 3) != 0;
-          for (int rx = et; rx < rxcount; rx += EPI_THREADS) {
+          for (int rx = et; rx < rxcount; rx += GAT_THREADS) {
             const int b = rx0 + rx;
             float s = 0.f;
             for (int k = 0; k < S; ++k) s += __ldcg(p.partial_out + (int64_t)k * p.n_rxn + b);
