@@ -776,8 +776,12 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     split_rows_kernel<<<(unsigned)cgr_ceil_div(N, 8), 256, 0, st>>>(g->x, fa, N, fa, x_hi, x_lo, w.kp_x, flag, FLAG_X);
     CGR_LAUNCH_CHECK();
   }
+  // experiments only (results are wrong): CGR_DEBUG_SKIP=atom|edge|both leaves stages out to time the rest
+  static const char* dbg_skip = getenv("CGR_DEBUG_SKIP");
+  const bool skip_atom = dbg_skip && (!strcmp(dbg_skip, "atom") || !strcmp(dbg_skip, "both"));
+  const bool skip_edge = dbg_skip && (!strcmp(dbg_skip, "edge") || !strcmp(dbg_skip, "both"));
   // 2. per-atom projections [P' | Q'] = x [W_x ; W_ox]^T + [b_i | b_o]   (GNN.py:86 and :106-107, x part)
-  {
+  if (!skip_atom) {
     TcGemmParams prm;
     memset(&prm, 0, sizeof(prm));
     if ((rc = make_map(&prm.tmA_hi, x_hi, N, fa, w.kp_x, TM))) return rc;
@@ -801,8 +805,19 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
                                 two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
     if (rc) return rc;
   }
+  const bool relu = p->act == CGR_ACT_RELU;
+  // 4+5 fused: every bond layer and the readout of a tile group in ONE cluster launch (inference; the training forward
+  // keeps one operand pair per layer for the backward and stays on the per-layer kernels)
+  static const bool use_fused = getenv("CGR_NO_FUSED_FWD") == nullptr;
+  static const bool use_fused_init = getenv("CGR_NO_FUSED_INIT") == nullptr;
+  FwdChoice fc;
+  const bool fused = use_fused && !blob && !(training && p->host_dropout_p) && choose_fwd(T, H, p->tc_throughput != 0, &fc);
+  // the fused kernel also computes h0 (edge initialisation) when W_e^T's slice and the tiles' bond features fit its
+  // staging ring
+  const bool fused_init = fused && use_fused_init && fb > 0 &&
+                          (size_t)fb * (fc.bn + fc.tpc * TM) * sizeof(float) <= (size_t)tcf::ring_bytes(fc.bn);
   // 3. edge initialisation on tile-packed rows
-  {
+  if (!skip_edge && !fused_init) {
     CgrRange prof("tc_edge_init", st);
     cgr_note_launch("tc_edge_init", st, 1);
     cudaLaunchConfig_t cfg;
@@ -825,12 +840,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
                                 (const float*)(wbuf + wl.off_wet), g->tile_info, fb, H, (int)p->act, h0, hbuf_hi(0),
                                 hbuf_lo(0), (int64_t)w.kp_h, flag));
   }
-  const bool relu = p->act == CGR_ACT_RELU;
-  // 4+5 fused: every bond layer and the readout of a tile group in ONE cluster launch (inference; the training forward
-  // keeps one operand pair per layer for the backward and stays on the per-layer kernels)
-  static const bool use_fused = getenv("CGR_NO_FUSED_FWD") == nullptr;
-  FwdChoice fc;
-  if (use_fused && !blob && !(training && p->host_dropout_p) && choose_fwd(T, H, p->tc_throughput != 0, &fc)) {
+  if (fused) {
     tcf::FwdParams prm;
     memset(&prm, 0, sizeof(prm));
     for (int b = 0; b < 2; ++b) {
@@ -851,6 +861,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     CGR_CHECK_ARG((char*)h_lo[1] - (char*)h_hi[1] == prm.lo_delta, "tc forward: operand buffers are not laid out pairwise");
     prm.unscale = unscale;
     prm.h0 = h0;
+    prm.ea = g->edge_attr; prm.wet = (const float*)(wbuf + wl.off_wet); prm.fb = fb; prm.fuse_init = fused_init ? 1 : 0;
     prm.PQ = PQ;
     prm.w_ffn = p->w_ffn; prm.b_ffn = p->b_ffn;
     prm.tile_info = g->tile_info;

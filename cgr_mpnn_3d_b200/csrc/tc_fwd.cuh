@@ -70,6 +70,9 @@ struct FCfg {
   static_assert((TM + 1) * CHP * 4 < 65536, "staging byte offsets must fit 16 bits");
 };
 
+// bytes of the staging ring of a slice width (the fused edge initialisation borrows it)
+constexpr int ring_bytes(int bn) { return bn > 128 ? FCfg<208>::Y_BYTES : FCfg<80>::Y_BYTES; }
+
 struct FwdParams {
   CUtensorMap tmA_hi[2], tmA_lo[2];            // activation operand, ping-pong: layer l reads buffer l & 1
   CUtensorMap tmB_hi[MAX_LAYERS], tmB_lo[MAX_LAYERS];   // prepared weights of bond layer l; [depth] = W_os (readout)
@@ -80,7 +83,10 @@ struct FwdParams {
   int64_t ldo;
   int64_t lo_delta;                            // byte distance from a hi buffer to its lo buffer (same for both pairs)
   const float* unscale;                        // [1 + l]: 1 / weight scale of layer l's matrix
-  const float* h0;                             // [T * 128, H] fp32, tile-packed (skip operand)
+  float* h0;                                   // [T * 128, H] fp32, tile-packed (skip operand)
+  const float* ea;                             // fuse_init: bond features [E, fb] (bond id order)
+  const float* wet;                            // fuse_init: W_e^T [fb, H] fp32 (edge_init.weight[:, Fa:]^T)
+  int fb, fuse_init;                           // fuse_init: h0 is computed by this kernel (GNN.py:86), not read
   const float* PQ;                             // [N, 2H] fp32: Q' = PQ[:, H:] (readout operand)
   const float* w_ffn;
   const float* b_ffn;
@@ -96,7 +102,7 @@ struct FwdParams {
   int64_t n_rxn;
   int depth, H, num_k, act, n_tiles, tiles_per_cluster;
   int fast;                                    // 1: single-pass fp16 (hi halves only), the "fast" precision mode
-  long long* dbg;                              // optional [n_cta][MAX_TPC * MAX_LAYERS][4] clock64 stamps (debug)
+  long long* dbg;                              // optional [n_cta][MAX_TPC * MAX_LAYERS][8] clock64 stamps (debug)
 };
 
 struct TileAux {                // per tile of the group: neighbour descriptors (built once, used by every layer)
@@ -126,6 +132,7 @@ struct Aux {
   uint64_t st_full[2];          // staging ring: buffer b holds a complete chunk (the STG_WARPS arrived)
   uint64_t st_empty[2];         // every gather warp has consumed buffer b
   uint64_t ready[MAX_TPC];      // tile j's operand of the next layer is complete in every CTA of the cluster
+                                // (one arrival per gather warp of every CTA)
   uint32_t tmem_base;
   float us[MAX_LAYERS + 1];     // 1 / weight scale of every layer's matrix (staged once: no global load per item)
   float skipv[MAX_LAYERS];      // learnable skip scalars (1 where the layer has none)
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       umma::mbar_init(umma::smem_u32(&aux->st_full[s]), STG_WARPS);
       umma::mbar_init(umma::smem_u32(&aux->st_empty[s]), GAT_WARPS);
     }
-    for (int j = 0; j < MAX_TPC; ++j) umma::mbar_init(umma::smem_u32(&aux->ready[j]), (uint32_t)S);
+    for (int j = 0; j < MAX_TPC; ++j) umma::mbar_init(umma::smem_u32(&aux->ready[j]), (uint32_t)(S * GAT_WARPS));
     umma::mbar_fence_init();
     umma::tma_prefetch_desc(&p.tmA_hi[0]);
     umma::tma_prefetch_desc(&p.tmA_lo[0]);
@@ -288,11 +295,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
           umma::tma_load_2d(&p.tmB_hi[l], full, st + 2 * A_BYTES, kc * BK, n0);
           if (!p.fast) umma::tma_load_2d(&p.tmB_lo[l], full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
-          if (kc == 0 && l > 0) {
+          if (kc == 0 && (l > 0 || p.fuse_init)) {
             // the S slices of this tile's previous layer have been stored (every CTA of the cluster arrived)
-            umma::mbar_wait_cluster(umma::smem_u32(&aux->ready[j]), (uint32_t)(l - 1) & 1u);
+            umma::mbar_wait_cluster(umma::smem_u32(&aux->ready[j]), (uint32_t)(l - 1 + p.fuse_init) & 1u);
             umma::fence_proxy_async();
-            if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) + i * 4 + 3] = clock64();
+            if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 3] = clock64();
           }
           umma::tma_load_2d(&p.tmA_hi[buf], full, st, kc * BK, tile * TM);
           if (!p.fast) umma::tma_load_2d(&p.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
@@ -310,11 +317,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         const uint32_t slot = (uint32_t)i & 1u;
         umma::mbar_wait(umma::smem_u32(&aux->tmem_empty[slot]), (((uint32_t)i >> 1) & 1u) ^ 1u);
         umma::tc_fence_after_sync();
+        if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 4] = clock64();
         const uint32_t acc = tmem + slot * SLOT_COLS;
         for (int kc = 0; kc < p.num_k; ++kc, ++g) {
           const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
           umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
           umma::tc_fence_after_sync();
+          if (p.dbg && kc == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 7] = clock64();
           const uint32_t st = base + s * STAGE_BYTES;
           const uint64_t da_hi = umma::smem_desc_k_sw128(st);
           const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
@@ -353,12 +362,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const float us = aux->us[nt == 2 ? (i >> 1) : i];
       umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
       umma::tc_fence_after_sync();
+      if (p.dbg && warp == 4 && lane == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 5] = clock64();
       const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch, ++c) {
         const int cw = (ch + 1) * CH <= BN ? CH : BN - ch * CH;    // columns of this chunk (the last one may be shorter)
         const uint32_t buf = c & 1u;
-        umma::mbar_wait(umma::smem_u32(&aux->st_empty[buf]), ((c >> 1) & 1u) ^ 1u);
+        // use u of a buffer waits for the gather warps' release of use u - 1; with the fused edge initialisation the
+        // ring's first release is the end of that phase (it borrows the ring), so the phases shift by one
+        umma::mbar_wait(umma::smem_u32(&aux->st_empty[buf]), ((c >> 1) & 1u) ^ 1u ^ (uint32_t)p.fuse_init);
         float* dst_row = y_s + buf * (C::YBUF_BYTES / 4) + row * CHP;
         if (C::CAT && !p.fast) {
 #pragma unroll
@@ -407,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           umma::mbar_arrive(umma::smem_u32(&aux->st_full[buf]));    // release: the warp's rows are in the buffer
         }
       }
+      if (p.dbg && warp == 4 && lane == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 6] = clock64();
     }
   } else if (warp >= 4 + STG_WARPS) {
     // ------------------------------------------------------------------ gather warps
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     const uint32_t pq_row_step = (uint32_t)(RPP * 2 * H) * 4u;     // ... its two Q' rows
     const uint32_t o_row_step = (uint32_t)RPP * (uint32_t)p.ldo * 2u;   // ... its two (hi, lo) output rows
     auto stamp = [&](int i, int w) {                                // debug: clock64 phase stamps
-      if (p.dbg && et == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 4) + i * 4 + w] = clock64();
+      if (p.dbg && et == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + w] = clock64();
     };
     // item i of this CTA = (tile j of the group, layer l); nt is 1 or 2
     auto item_tile = [&](int i) { return nt == 2 ? (i & 1) : 0; };
@@ -456,6 +469,115 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           if (r0 + k * RPP < acount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(qp + (uint32_t)k * pq_row_step));
       }
     };
+    stamp(MAX_TPC * MAX_LAYERS - 1, 0);
+    if (p.fuse_init) {
+      // ---- edge initialisation for this slice's columns of the group's tiles (GNN.py:86):
+      //      h0[e] = act(P'[src e] + ea[e] . W_e^T), written as the fp32 skip operand and the (hi, lo) operand of layer 0.
+      // The ring memory is free until the first accumulator is staged: it holds W_e^T's slice and the tiles' bond
+      // features meanwhile.  8 lanes per row; a lane requests all its column groups of the row before it computes.
+      const int fb = p.fb;
+      float* wet_s = y_s;                                           // [fb][BN]
+      float* ea_s = y_s + fb * BN;                                  // [nt * TM][fb]
+      for (int t = et; t < fb * (BN / 4); t += GAT_THREADS) {
+        const int k = t / (BN / 4), c = 4 * (t % (BN / 4));
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + c < H) w = ldg4(p.wet + (size_t)k * H + n0 + c);
+        *reinterpret_cast<float4*>(wet_s + k * BN + c) = w;
+      }
+      {
+        // 16 threads per bond row; every thread's loads are issued before its first store (memory-level parallelism)
+        constexpr int NP = (MAX_TPC * TM) / (GAT_THREADS / 16);      // 8 passes cover two tiles
+        float ev[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const int jr = (et >> 4) + q * (GAT_THREADS / 16), k = et & 15;
+          ev[q] = 0.f;
+          if (jr < nt * TM && k < fb) {
+            const TileAux& ta = aux->t[jr / TM];
+            const int r = jr % TM;
+            if (r < ta.info[1]) ev[q] = __ldg(p.ea + (size_t)(ta.info[0] + r) * fb + k);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const int jr = (et >> 4) + q * (GAT_THREADS / 16), k = et & 15;
+          if (jr < nt * TM && k < fb) ea_s[jr * fb + k] = ev[q];
+        }
+        for (int jr = et >> 4; fb > 16 && jr < nt * TM; jr += GAT_THREADS / 16) {      // wider bond features: the rest
+          const TileAux& ta = aux->t[jr / TM];
+          const int r = jr % TM;
+          for (int k = 16 + (et & 15); k < fb; k += 16)
+            ea_s[jr * fb + k] = r < ta.info[1] ? __ldg(p.ea + (size_t)(ta.info[0] + r) * fb + k) : 0.f;
+        }
+      }
+      umma::named_bar_sync(3, GAT_THREADS);
+      float imax = 0.f;
+      constexpr int NI = (BN / 4 + UPR - 1) / UPR;                  // column groups of the slice per lane
+      for (int jj = 0; jj < nt; ++jj) {
+        const TileAux& ta = aux->t[jj];
+        const int ebase = ta.info[0], ecount = ta.info[1];
+#pragma unroll 1
+        for (int u = 0; u < SLOTS; ++u) {
+          const int r = r0 + u * RPP;
+          if (r < ecount) {
+            // the row's P' slice: every column group requested up front, then W_e^T's rows stream from shared memory
+            const float* pr = p.PQ + (size_t)__ldg(p.src + ebase + r) * (2 * H) + n0;
+            float4 a[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const int c = 4 * (cg + UPR * i);
+              a[i] = (c < BN && n0 + c < H) ? __ldcg(reinterpret_cast<const float4*>(pr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float* e = ea_s + (jj * TM + r) * fb;
+            const float* wr = wet_s + 4 * cg;
+#pragma unroll 2
+            for (int k = 0; k < fb; ++k) {
+              const float x = e[k];
+#pragma unroll
+              for (int i = 0; i < NI; ++i) {                        // (column groups past the slice read ring memory: unused)
+                const float4 w = *reinterpret_cast<const float4*>(wr + k * BN + 4 * UPR * i);
+                a[i].x = fmaf(x, w.x, a[i].x); a[i].y = fmaf(x, w.y, a[i].y);
+                a[i].z = fmaf(x, w.z, a[i].z); a[i].w = fmaf(x, w.w, a[i].w);
+              }
+            }
+            const size_t row = (size_t)(tile0 + jj) * TM + r;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const int c = 4 * (cg + UPR * i);
+              if (c < BN && n0 + c < H) {
+                float4 v = a[i];
+                v.x = tcg::act_t<RELU>(v.x, p.act); v.y = tcg::act_t<RELU>(v.y, p.act);
+                v.z = tcg::act_t<RELU>(v.z, p.act); v.w = tcg::act_t<RELU>(v.w, p.act);
+                imax = fmaxf(imax, tcg::amax4(v));
+                *reinterpret_cast<float4*>(p.h0 + row * H + n0 + c) = v;
+                char* od = reinterpret_cast<char*>(p.o_hi[0]) + (row * (size_t)p.ldo + n0 + c) * 2;
+                tcg::store_split4(v, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
+              }
+            }
+          }
+        }
+        // publish this tile's slice of the layer-0 operand (same protocol as a layer's output, below)
+        umma::fence_proxy_async();
+        __syncwarp();
+        if (lane < S) {
+          __threadfence();
+          umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[jj]), (uint32_t)lane);
+        }
+      }
+      if (imax > 60000.f) atomicOr(p.overflow, 1);                  // fp16 range of the split (as edge_init flags it)
+      // the ring goes back to its own use: its zero rows again, and this CTA's h0 columns are visible to every
+      // gather thread (they are read back as the skip operand)
+      umma::named_bar_sync(3, GAT_THREADS);
+      for (int k = et; k < 2 * CHP; k += GAT_THREADS)
+        y_s[(k / CHP) * (C::YBUF_BYTES / 4) + ZROW * CHP + (k % CHP)] = 0.f;
+      __threadfence_block();
+      umma::named_bar_sync(3, GAT_THREADS);
+      if (lane == 0) {                                              // the staging warps may use the ring from here on
+        umma::mbar_arrive(umma::smem_u32(&aux->st_empty[0]));
+        umma::mbar_arrive(umma::smem_u32(&aux->st_empty[1]));
+      }
+    }
+    stamp(MAX_TPC * MAX_LAYERS - 1, 1);
     request(0, 0);
 
     uint32_t c = 0;                                                 // chunks consumed so far (ring position)
@@ -543,14 +665,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           atomicOr(p.overflow, 1);
           atomicOr(p.tile_counter + tile, 0x10000);
         }
-        // the writers order their stores against the peers' TMA reads (proxy fence) and meet at the barrier; the
-        // arriving threads then publish the whole slice: their fence + release is cumulative over everything the
-        // barrier ordered before it (the grid-sync pattern: bar.sync, then one thread fences and signals)
+        // every gather warp publishes its own rows: the lanes order their stores against the peers' TMA reads (proxy
+        // fence) and meet at the warp barrier, then one lane per peer CTA fences (cumulative over what the warp
+        // barrier ordered before it) and arrives on that CTA's barrier -- S * GAT_WARPS arrivals complete a layer.
+        // No CTA-wide barrier: a warp that is done moves on to the next item's chunks
         umma::fence_proxy_async();
-        umma::named_bar_sync(3, GAT_THREADS);
-        if (et < S) {
+        __syncwarp();
+        if (lane < S) {
           __threadfence();
-          umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[j]), (uint32_t)et);
+          umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[j]), (uint32_t)lane);
         }
       } else {
         // the 8 lanes of a row add their parts in a fixed tree order: the atom's dot product with w_f

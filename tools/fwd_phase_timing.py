@@ -1,7 +1,9 @@
 """Debug: clock64 stamps of the fused forward kernel (tc_fwd.cuh), per CTA and item (tile, layer).
 
-stamp 0: accumulator ready seen by the epilogue; 1: gather of the last chunk done; 2: item tail (fences, cluster arrive /
-readout reduction) done; 3: producer passed the dependency wait of this item (layers >= 1).
+stamp 0: gather warps see the item's first staged chunk; 1: gather of the last chunk done; 2: item tail (publish /
+readout reduction) done; 3: producer passed the dependency wait of this item (layers >= 1); 4: MMA warp owns the
+accumulator slot; 7: first operand stage of the item landed; 5: staging warps see the accumulator complete;
+6: last chunk staged (accumulator released).
 """
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,7 +19,7 @@ m.tile_policy = a.policy
 m.precision = a.precision
 d = make_batch(a.batch, seed=0, fa=846).to("cuda")
 lib = _lib.load()
-PER = 2 * 16 * 4
+PER = 2 * 16 * 8
 with torch.no_grad():
     m(d); m(d)
     torch.cuda.synchronize()
@@ -26,18 +28,21 @@ with torch.no_grad():
     m(d)
     torch.cuda.synchronize()
     lib.cgr_tc_debug_buffer(None)
-t = dbg.view(-1, 32, 4).cpu()
+t = dbg.view(-1, 32, 8).cpu()
 t = t[t[:, 0, 0] != 0]
-n_items = int((t[0, :, 0] != 0).sum())
+n_items = int((t[0, :31, 0] != 0).sum())
 print("ctas", t.shape[0], "items per cta", n_items)
 t = t[:, :n_items].double()
-start = t[:, 0, 0:1]
-print("item: acc_ready(rel. to item 0)  gather(1-0)  tail(2-1)  gap to next acc_ready  dep_wait_passed(3, rel)")
+start = t[:, 0:1, 0:1]
+r = t - start
+r[t == 0] = float("nan")
+def col(i, k):
+    return float(torch.nanmean(r[:, i, k]))
+print("item:  mma_slot(4)  stage0_landed(7)  acc_done(5)  staged(6) | gather_first(0)  gather_done(1)  tail_done(2) | dep_passed(3)")
 for i in range(n_items):
-    rel = (t[:, i, 0] - start[:, 0]).mean()
-    gather = (t[:, i, 1] - t[:, i, 0]).mean()
-    tail = (t[:, i, 2] - t[:, i, 1]).mean()
-    gap = (t[:, i + 1, 0] - t[:, i, 2]).mean() if i + 1 < n_items else float("nan")
-    dep = (t[:, i, 3] - start[:, 0]).mean() if i >= 1 and float(t[:, i, 3].min()) > 0 else float("nan")
-    print(f"{i:3d}  {rel:10.0f}  {gather:8.0f}  {tail:8.0f}  {gap:8.0f}  {dep:10.0f}")
-print("total (last tail - first acc_ready): mean %.0f cycles" % (t[:, n_items - 1, 2] - t[:, 0, 0]).mean())
+    print(f"{i:3d}  {col(i,4):10.0f} {col(i,7):10.0f} {col(i,5):10.0f} {col(i,6):10.0f} | {col(i,0):10.0f} {col(i,1):10.0f} {col(i,2):10.0f} | {col(i,3):10.0f}")
+print("edge-init phase (gather warps, before the first item): %.0f cycles; it ends %.0f cycles before item 0's first chunk" % (float((t[:, 31, 1] - t[:, 31, 0]).mean()) if False else float((dbg.view(-1, 32, 8).cpu()[:t.shape[0], 31, 1] - dbg.view(-1, 32, 8).cpu()[:t.shape[0], 31, 0]).double().mean()), float((t[:, 0, 0] - dbg.view(-1, 32, 8).cpu()[:t.shape[0], 31, 1].double()).mean())))
+print("per item means: mma (5-7) %.0f   fill wait (7-4) %.0f   gather (1-0) %.0f   tail (2-1) %.0f   period %.0f" % (
+    sum(col(i, 5) - col(i, 7) for i in range(n_items)) / n_items, sum(col(i, 7) - col(i, 4) for i in range(n_items)) / n_items,
+    sum(col(i, 1) - col(i, 0) for i in range(n_items)) / n_items, sum(col(i, 2) - col(i, 1) for i in range(n_items)) / n_items,
+    (col(n_items - 1, 2) - col(0, 0)) / max(n_items - 1, 1)))
