@@ -107,6 +107,8 @@ PROTOTYPES = {
     "cgr_gnn_infer_host_async": (C.c_int, [C.POINTER(CgrParams), _V, _V, _V, _V, _V, _I64, _I64, _I64, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_gnn_infer_host_multi_async": (C.c_int, [C.POINTER(CgrParams), _V, C.c_int32, _V, _V, _SZ, _V, _SZ, _V]),
     "cgr_tc_saved_bytes": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph)]),
+    "cgr_forward_group_workspace": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph), C.c_int32]),
+    "cgr_gnn_forward_group": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrGraph), C.c_int32, _V, _V, _SZ, _V]),
     "cgr_tc_plan_host": (C.c_int, [_V, _V, _I64, _V, C.POINTER(C.c_int64)]),
     "cgr_store_infer_workspace": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrStore), _V, _I64, _I64, C.POINTER(_SZ),
                                             C.POINTER(_SZ)]),

@@ -523,6 +523,21 @@ extern "C" size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t
   return b + 256;
 }
 
+extern "C" size_t cgr_forward_group_workspace(const cgr_params_t* p, const cgr_graph_t* graphs, int32_t n_graphs) {
+  if (!p || !graphs) return 0;
+  return tc_forward_group_workspace(p, graphs, n_graphs);
+}
+
+extern "C" int cgr_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* graphs, int32_t n_graphs,
+                                     float* const* outs, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  CGR_CHECK_ARG(graphs && outs && n_graphs >= 1, "cgr_gnn_forward_group: null argument");
+  for (int32_t i = 0; i < n_graphs; ++i)
+    if ((rc = check_graph(&graphs[i]))) return rc;
+  return tc_gnn_forward_group(p, graphs, n_graphs, outs, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved,
                                int32_t training, uint64_t seed, int32_t engine, void* workspace,
                                size_t workspace_bytes, void* stream) {

@@ -712,6 +712,68 @@ size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int tra
   return tc_ws(p, g, p->tc_weights == nullptr).total;
 }
 
+namespace {
+// fused forward kernel: what every batch of a launch shares (weights, biases, shapes)
+int fwd_fill_shared(tcf::FwdParams* prm, const cgr_params_t* p, const char* wbuf, const WLayout& wl, const FwdChoice& fc,
+                    int64_t kp_h, bool fused_init, int fast) {
+  const int H = p->hidden, d = p->depth;
+  int rc;
+  for (int l = 0; l <= d; ++l) {
+    if ((rc = make_map(&prm->tmB_hi[l], (const __half*)(wbuf + wl.off_hi[1 + l]), H, H, wl.ld[1 + l], fc.bn))) return rc;
+    if ((rc = make_map(&prm->tmB_lo[l], (const __half*)(wbuf + wl.off_lo[1 + l]), H, H, wl.ld[1 + l], fc.bn))) return rc;
+    if (l < d) {
+      prm->bias[l] = p->b_conv[l];
+      prm->skip[l] = p->use_skip ? p->skip[l] : nullptr;
+    }
+  }
+  prm->ldo = kp_h;
+  prm->unscale = (const float*)(wbuf + wl.off_unscale);
+  prm->wet = (const float*)(wbuf + wl.off_wet);
+  prm->fb = p->fb;
+  prm->fuse_init = fused_init ? 1 : 0;
+  prm->w_ffn = p->w_ffn; prm->b_ffn = p->b_ffn;
+  prm->depth = d; prm->H = H; prm->num_k = (int)cgr_ceil_div(H, BK); prm->act = p->act;
+  prm->tiles_per_cluster = fc.tpc;
+  prm->fast = fast;
+  prm->dbg = g_tc_dbg;
+  return CGR_OK;
+}
+// ... and one batch's part: operand buffers of its workspace, index arrays, outputs
+int fwd_fill_batch(tcf::FwdBatch* bt, const cgr_graph_t* g, char* ws, const TcWs& w, int H, float* out) {
+  int rc;
+  __half* h_hi[2] = {(__half*)(ws + w.off_hhi[0]), (__half*)(ws + w.off_hhi[1])};
+  __half* h_lo[2] = {(__half*)(ws + w.off_hlo[0]), (__half*)(ws + w.off_hlo[1])};
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = make_map(&bt->tmA_hi[b], h_hi[b], w.rows_pad, H, w.kp_h, TM))) return rc;
+    if ((rc = make_map(&bt->tmA_lo[b], h_lo[b], w.rows_pad, H, w.kp_h, TM))) return rc;
+    bt->o_hi[b] = h_hi[b];
+    CGR_CHECK_ARG((char*)h_lo[b] - (char*)h_hi[b] == (char*)h_lo[0] - (char*)h_hi[0],
+                  "tc forward: operand buffers are not laid out pairwise");
+  }
+  bt->lo_delta = (int64_t)((char*)h_lo[0] - (char*)h_hi[0]);
+  bt->h0 = (float*)(ws + w.off_h0);
+  bt->ea = g->edge_attr;
+  bt->PQ = (const float*)(ws + w.off_pq);
+  bt->tile_info = g->tile_info;
+  bt->in_ptr = g->in_ptr; bt->in_idx = g->in_idx; bt->src = g->src; bt->atom_ptr = g->atom_ptr;
+  bt->partial_out = (float*)(ws + w.off_partial);
+  bt->out = out;
+  bt->tile_counter = g->tc_status + 1;
+  bt->overflow = g->tc_status;
+  bt->n_rxn = g->n_rxn;
+  bt->n_tiles = (int)g->n_tiles;
+  bt->group0 = 0;
+  return CGR_OK;
+}
+int launch_fwd(const tcf::FwdParams& prm, const FwdChoice& fc, bool relu, int n_groups, bool pdl, cudaStream_t st) {
+  if (fc.bn == FWD_BN_WIDE)
+    return relu ? launch_fwd_t<FWD_BN_WIDE, true>(prm, n_groups, fc.S, pdl, st)
+                : launch_fwd_t<FWD_BN_WIDE, false>(prm, n_groups, fc.S, pdl, st);
+  return relu ? launch_fwd_t<FWD_BN_NARROW, true>(prm, n_groups, fc.S, pdl, st)
+              : launch_fwd_t<FWD_BN_NARROW, false>(prm, n_groups, fc.S, pdl, st);
+}
+}  // namespace
+
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CGR_CHECK_ARG(g->tile_info && g->n_tiles > 0, "tcgen05 engine needs a tile plan (reactions of <= 128 bonds)");
@@ -843,41 +905,11 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   if (fused) {
     tcf::FwdParams prm;
     memset(&prm, 0, sizeof(prm));
-    for (int b = 0; b < 2; ++b) {
-      if ((rc = make_map(&prm.tmA_hi[b], h_hi[b], w.rows_pad, H, w.kp_h, TM))) return rc;
-      if ((rc = make_map(&prm.tmA_lo[b], h_lo[b], w.rows_pad, H, w.kp_h, TM))) return rc;
-      prm.o_hi[b] = h_hi[b]; prm.o_lo[b] = h_lo[b];
-    }
-    for (int l = 0; l <= d; ++l) {
-      if ((rc = make_map(&prm.tmB_hi[l], w_hi(1 + l), H, H, wl.ld[1 + l], fc.bn))) return rc;
-      if ((rc = make_map(&prm.tmB_lo[l], w_lo(1 + l), H, H, wl.ld[1 + l], fc.bn))) return rc;
-      if (l < d) {
-        prm.bias[l] = p->b_conv[l];
-        prm.skip[l] = p->use_skip ? p->skip[l] : nullptr;
-      }
-    }
-    prm.ldo = w.kp_h;
-    prm.lo_delta = (int64_t)((char*)h_lo[0] - (char*)h_hi[0]);
-    CGR_CHECK_ARG((char*)h_lo[1] - (char*)h_hi[1] == prm.lo_delta, "tc forward: operand buffers are not laid out pairwise");
-    prm.unscale = unscale;
-    prm.h0 = h0;
-    prm.ea = g->edge_attr; prm.wet = (const float*)(wbuf + wl.off_wet); prm.fb = fb; prm.fuse_init = fused_init ? 1 : 0;
-    prm.PQ = PQ;
-    prm.w_ffn = p->w_ffn; prm.b_ffn = p->b_ffn;
-    prm.tile_info = g->tile_info;
-    prm.in_ptr = g->in_ptr; prm.in_idx = g->in_idx; prm.src = g->src; prm.atom_ptr = g->atom_ptr;
-    prm.partial_out = partial; prm.out = out; prm.tile_counter = tile_counter; prm.overflow = flag;
-    prm.n_rxn = B;
-    prm.depth = d; prm.H = H; prm.num_k = (int)cgr_ceil_div(H, BK); prm.act = p->act;
-    prm.n_tiles = (int)T; prm.tiles_per_cluster = fc.tpc;
-    prm.fast = fast;
-    prm.dbg = g_tc_dbg;
+    if ((rc = fwd_fill_shared(&prm, p, wbuf, wl, fc, w.kp_h, fused_init, fast))) return rc;
+    if ((rc = fwd_fill_batch(&prm.bt[0], g, ws, w, H, out))) return rc;
+    prm.n_batches = 1;
     const int n_groups = (int)cgr_ceil_div(T, fc.tpc);
-    if (fc.bn == FWD_BN_WIDE)
-      return relu ? launch_fwd_t<FWD_BN_WIDE, true>(prm, n_groups, fc.S, use_pdl, st)
-                  : launch_fwd_t<FWD_BN_WIDE, false>(prm, n_groups, fc.S, use_pdl, st);
-    return relu ? launch_fwd_t<FWD_BN_NARROW, true>(prm, n_groups, fc.S, use_pdl, st)
-                : launch_fwd_t<FWD_BN_NARROW, false>(prm, n_groups, fc.S, use_pdl, st);
+    return launch_fwd(prm, fc, relu, n_groups, use_pdl, st);
   }
   // 4. message passing layers: one fused kernel each
   const int bn_h = choose_bn(T, H);
@@ -938,6 +970,144 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     if (rc) return rc;
   }
   return CGR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Group forward: SEVERAL independent batches (a screening job is a stream of them) in TWO launches -- one atom
+// projection over every batch's atom tiles, one fused cluster kernel over every batch's tile groups -- instead of
+// two launches per batch pipelined over streams.  One grid packs the SMs wave after wave (a 64-reaction forward
+// alone occupies 22 of the 148); per-batch operands, index arrays and outputs travel as kernel parameters
+// (FwdBatch / GemmBatch tables in the constant bank), the weights are shared.  Same kernels, same arithmetic: the
+// energies are bit-identical to per-batch forwards in the throughput configuration.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct GroupWs { size_t off_w, off_g[tcf::MAX_GROUP], total; };
+GroupWs group_ws(const cgr_params_t* p, const cgr_graph_t* gs, int n) {
+  GroupWs G;
+  size_t off = 0;
+  G.off_w = off;
+  off += cgr_align_up(p->tc_weights ? 0 : tc_weights_bytes(p), 1024);
+  for (int i = 0; i < n; ++i) {
+    G.off_g[i] = off;
+    off += cgr_align_up(tc_ws(p, &gs[i], false).total, 1024);
+  }
+  G.total = off + 1024;
+  return G;
+}
+}  // namespace
+
+size_t tc_forward_group_workspace(const cgr_params_t* p, const cgr_graph_t* gs, int n) {
+  if (n <= 0 || n > tcf::MAX_GROUP) return 0;
+  for (int i = 0; i < n; ++i)
+    if (!gs[i].tile_info || gs[i].n_tiles <= 0) return 0;
+  return group_ws(p, gs, n).total;
+}
+
+int tc_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* gs, int n, float* const* outs, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
+  CGR_CHECK_ARG(n >= 1 && n <= tcf::MAX_GROUP, "group forward takes 1..%d batches per call", tcf::MAX_GROUP);
+  CGR_CHECK_ARG(p->hidden % 4 == 0, "tcgen05 engine needs a hidden size that is a multiple of 4");
+  CGR_CHECK_ARG(p->depth + 3 <= MAX_SEG, "tcgen05 engine supports depth <= %d", MAX_SEG - 3);
+  CGR_CHECK_ARG(p->fb <= 32, "tcgen05 engine supports at most 32 bond features");
+  const int H = p->hidden, fa = p->fa, fb = p->fb;
+  int64_t t_sum = 0, m_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    CGR_CHECK_ARG(gs[i].tile_info && gs[i].n_tiles > 0 && gs[i].tc_status && outs[i],
+                  "group forward: batch %d needs a tile plan, tc_status and an output", i);
+    t_sum += gs[i].n_tiles;
+    m_tiles += cgr_ceil_div(gs[i].n_atoms, TM);
+  }
+  CGR_CHECK_ARG(t_sum <= 60000 && m_tiles <= 60000, "group forward: too many row tiles for one launch");
+  const GroupWs G = group_ws(p, gs, n);
+  CGR_CHECK_ARG(workspace && workspace_bytes >= G.total, "tc_gnn_forward_group: workspace too small");
+  char* base = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  int rc;
+  char* wbuf = p->tc_weights ? (char*)p->tc_weights : base + G.off_w;
+  if (!p->tc_weights && (rc = tc_prepare_weights(p, wbuf, tc_weights_bytes(p), st))) return rc;
+  const WLayout wl = wlayout(p);
+  const int fast = p->tc_fast ? 1 : 0;
+  FwdChoice fc;
+  CGR_CHECK_ARG(choose_fwd(2, H, true, &fc), "group forward: hidden size %d needs more than 8 column slices", H);
+  const bool fused_init = fb > 0 && getenv("CGR_NO_FUSED_INIT") == nullptr &&
+                          (size_t)fb * (fc.bn + fc.tpc * TM) * sizeof(float) <= (size_t)tcf::ring_bytes(fc.bn);
+  static const bool use_pdl = getenv("CGR_NO_PDL") == nullptr;
+
+  // 1 + 2. x -> (hi, lo) where the caller did not prepare it; ONE atom-projection launch over every batch's tiles
+  TcGemmParams ap;
+  memset(&ap, 0, sizeof(ap));
+  tcf::FwdParams prm;
+  memset(&prm, 0, sizeof(prm));
+  TcWs wi[tcf::MAX_GROUP];
+  int tile0 = 0, group0 = 0;
+  for (int i = 0; i < n; ++i) {
+    const cgr_graph_t* g = &gs[i];
+    wi[i] = tc_ws(p, g, false);
+    const TcWs& w = wi[i];
+    char* ws = base + G.off_g[i];
+    const bool need_x = !(g->x_hi && g->x_lo);
+    __half* x_hi = need_x ? (__half*)(ws + w.off_xhi) : (__half*)g->x_hi;
+    __half* x_lo = need_x ? (__half*)(ws + w.off_xlo) : (__half*)g->x_lo;
+    if (need_x) {
+      CgrRange prof("tc_split_x", st);
+      cgr_note_launch("tc_split_x", st, 1);
+      split_rows_kernel<<<(unsigned)cgr_ceil_div(g->n_atoms, 8), 256, 0, st>>>(g->x, fa, g->n_atoms, fa, x_hi, x_lo, w.kp_x,
+                                                                              g->tc_status, FLAG_X);
+      CGR_LAUNCH_CHECK();
+    }
+    GemmBatch& gb = ap.gb[i];
+    if ((rc = make_map(&gb.tmA_hi, x_hi, g->n_atoms, fa, w.kp_x, TM))) return rc;
+    if ((rc = make_map(&gb.tmA_lo, x_lo, g->n_atoms, fa, w.kp_x, TM))) return rc;
+    gb.out_f32 = (float*)(ws + w.off_pq);
+    gb.overflow = g->tc_status;
+    gb.m_rows = (int)g->n_atoms;
+    gb.tile0 = tile0;
+    tile0 += (int)cgr_ceil_div(g->n_atoms, TM);
+    if ((rc = fwd_fill_batch(&prm.bt[i], g, ws, w, H, outs[i]))) return rc;
+    prm.bt[i].group0 = group0;
+    group0 += (int)cgr_ceil_div(g->n_tiles, fc.tpc);
+  }
+  {
+    const int bn = BN_LARGE;
+    if ((rc = make_map(&ap.tmB_hi, (const __half*)(wbuf + wl.off_hi[0]), 2 * H, fa, wl.ld[0], bn))) return rc;
+    if ((rc = make_map(&ap.tmB_lo, (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa, wl.ld[0], bn))) return rc;
+    ap.tmA_hi = ap.gb[0].tmA_hi; ap.tmA_lo = ap.gb[0].tmA_lo;
+    ap.num_k = (int)cgr_ceil_div(fa, BK);
+    ap.k_total = fa;
+    ap.n_total = 2 * H;
+    ap.unscale = (const float*)(wbuf + wl.off_unscale);
+    ap.bias = (const float*)(wbuf + wl.off_bias);
+    ap.ldc = 2 * H;
+    ap.fast = fast;
+    ap.n_batches = n;
+    rc = launch_gemm<EPI_PLAIN>(ap, bn, tile0, true, "tc_atom_proj", false, false, st);
+    if (rc) return rc;
+  }
+  // 3. edge initialisation: inside the fused kernel, or (bond features too wide for its staging ring) per batch
+  if (!fused_init) {
+    for (int i = 0; i < n; ++i) {
+      const cgr_graph_t* g = &gs[i];
+      const TcWs& w = wi[i];
+      char* ws = base + G.off_g[i];
+      CgrRange prof("tc_edge_init", st);
+      cgr_note_launch("tc_edge_init", st, 1);
+      static bool ei_attr = false;
+      if (!ei_attr) {
+        CGR_CUDA(cudaFuncSetAttribute(tc_edge_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ei_attr = true;
+      }
+      const size_t smem = (size_t)((fb > 0 ? fb : 1) * H + EI_ROWS * (fb > 0 ? fb : 1)) * sizeof(float);
+      tc_edge_init_kernel<<<dim3(TM / EI_ROWS, (unsigned)g->n_tiles), 256, smem, st>>>(
+          (const float*)(ws + w.off_pq), (int64_t)(2 * H), g->edge_attr, g->src, (const float*)(wbuf + wl.off_wet),
+          g->tile_info, fb, H, (int)p->act, (float*)(ws + w.off_h0), (__half*)(ws + w.off_hhi[0]),
+          (__half*)(ws + w.off_hlo[0]), (int64_t)w.kp_h, g->tc_status);
+      CGR_LAUNCH_CHECK();
+    }
+  }
+  // 4 + 5. every bond layer and the readout of every batch's tile groups in one cluster launch
+  if ((rc = fwd_fill_shared(&prm, p, wbuf, wl, fc, wi[0].kp_h, fused_init, fast))) return rc;
+  prm.n_batches = n;
+  return launch_fwd(prm, fc, p->act == CGR_ACT_RELU, group0, use_pdl && fused_init, st);
 }
 
 

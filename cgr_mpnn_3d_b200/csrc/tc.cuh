@@ -6,6 +6,9 @@
 #include "simt.cuh"
 
 size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int training);
+size_t tc_forward_group_workspace(const cgr_params_t* p, const cgr_graph_t* gs, int n);
+int tc_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* gs, int n, float* const* outs, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st);
 int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved, int training,
                    uint64_t seed, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

@@ -73,23 +73,16 @@ struct FCfg {
 // bytes of the staging ring of a slice width (the fused edge initialisation borrows it)
 constexpr int ring_bytes(int bn) { return bn > 128 ? FCfg<208>::Y_BYTES : FCfg<80>::Y_BYTES; }
 
-struct FwdParams {
+constexpr int MAX_GROUP = 24;                  // batches one launch can take (cgr_gnn_forward_group)
+
+// what differs between the batches of a group launch: operand buffers, index arrays, outputs
+struct FwdBatch {
   CUtensorMap tmA_hi[2], tmA_lo[2];            // activation operand, ping-pong: layer l reads buffer l & 1
-  CUtensorMap tmB_hi[MAX_LAYERS], tmB_lo[MAX_LAYERS];   // prepared weights of bond layer l; [depth] = W_os (readout)
-  const float* bias[MAX_LAYERS];               // bond-layer biases
-  const float* skip[MAX_LAYERS];               // learnable skip scalars (device) or null (= 1)
-  __half* o_hi[2];                             // layer l writes buffer (l + 1) & 1, rows tile * 128 + j
-  __half* o_lo[2];
-  int64_t ldo;
+  __half* o_hi[2];                             // layer l writes buffer (l + 1) & 1, rows tile * 128 + j (lo: + lo_delta)
   int64_t lo_delta;                            // byte distance from a hi buffer to its lo buffer (same for both pairs)
-  const float* unscale;                        // [1 + l]: 1 / weight scale of layer l's matrix
   float* h0;                                   // [T * 128, H] fp32, tile-packed (skip operand)
   const float* ea;                             // fuse_init: bond features [E, fb] (bond id order)
-  const float* wet;                            // fuse_init: W_e^T [fb, H] fp32 (edge_init.weight[:, Fa:]^T)
-  int fb, fuse_init;                           // fuse_init: h0 is computed by this kernel (GNN.py:86), not read
-  const float* PQ;                             // [N, 2H] fp32: Q' = PQ[:, H:] (readout operand)
-  const float* w_ffn;
-  const float* b_ffn;
+  const float* PQ;                             // [N, 2H] fp32: P' | Q' (edge-init / readout operands)
   const int32_t* tile_info;
   const int32_t* in_ptr;
   const int32_t* in_idx;
@@ -100,7 +93,23 @@ struct FwdParams {
   int* tile_counter;                           // [T]: low 16 bits arrival counter, bit 16 = the tile overflowed
   int* overflow;                               // tc_status[0]
   int64_t n_rxn;
-  int depth, H, num_k, act, n_tiles, tiles_per_cluster;
+  int n_tiles;
+  int group0;                                  // first tile group (cluster) of this batch in the launch
+};
+
+struct FwdParams {
+  FwdBatch bt[MAX_GROUP];                      // kernel parameters (constant bank): one entry for a plain forward
+  int n_batches;
+  CUtensorMap tmB_hi[MAX_LAYERS], tmB_lo[MAX_LAYERS];   // prepared weights of bond layer l; [depth] = W_os (readout)
+  const float* bias[MAX_LAYERS];               // bond-layer biases
+  const float* skip[MAX_LAYERS];               // learnable skip scalars (device) or null (= 1)
+  int64_t ldo;
+  const float* unscale;                        // [1 + l]: 1 / weight scale of layer l's matrix
+  const float* wet;                            // fuse_init: W_e^T [fb, H] fp32 (edge_init.weight[:, Fa:]^T)
+  int fb, fuse_init;                           // fuse_init: h0 is computed by this kernel (GNN.py:86), not read
+  const float* w_ffn;
+  const float* b_ffn;
+  int depth, H, num_k, act, tiles_per_cluster;
   int fast;                                    // 1: single-pass fp16 (hi halves only), the "fast" precision mode
   long long* dbg;                              // optional [n_cta][MAX_TPC * MAX_LAYERS][8] clock64 stamps (debug)
 };
@@ -184,13 +193,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = (int)umma::cluster_nctarank();
   const int slice = (int)umma::cluster_ctarank();
-  const int group = (int)blockIdx.x / S;
+  // the launch's clusters are the tile groups of its batches, batch after batch
+  int group = (int)blockIdx.x / S, bi = 0;
+  while (bi + 1 < p.n_batches && group >= p.bt[bi + 1].group0) ++bi;
+  const FwdBatch& B = p.bt[bi];
+  group -= B.group0;
   const int n0 = slice * BN;
   const int H = p.H, depth = p.depth;
   int n_eff = H - n0;                                              // columns this slice owns, rounded to the MMA granularity
   n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
   const int tile0 = group * p.tiles_per_cluster;
-  int nt = p.n_tiles - tile0;
+  int nt = B.n_tiles - tile0;
   nt = nt < p.tiles_per_cluster ? nt : p.tiles_per_cluster;
   const int n_items = nt * (depth + 1);
 
@@ -207,8 +220,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     }
     for (int j = 0; j < MAX_TPC; ++j) umma::mbar_init(umma::smem_u32(&aux->ready[j]), (uint32_t)(S * GAT_WARPS));
     umma::mbar_fence_init();
-    umma::tma_prefetch_desc(&p.tmA_hi[0]);
-    umma::tma_prefetch_desc(&p.tmA_lo[0]);
+    umma::tma_prefetch_desc(&B.tmA_hi[0]);
+    umma::tma_prefetch_desc(&B.tmA_lo[0]);
     umma::tma_prefetch_desc(&p.tmB_hi[0]);
     umma::tma_prefetch_desc(&p.tmB_lo[0]);
   }
@@ -218,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
   }
   if (threadIdx.x >= 96 && threadIdx.x < 96 + 8 * MAX_TPC) {
     const int j = (threadIdx.x - 96) >> 3, k = (threadIdx.x - 96) & 7;
-    aux->t[j].info[k] = j < nt ? __ldg(p.tile_info + (int64_t)(tile0 + j) * 8 + k) : 0;
+    aux->t[j].info[k] = j < nt ? __ldg(B.tile_info + (int64_t)(tile0 + j) * 8 + k) : 0;
   }
   umma::tc_fence_before_sync();
   __syncthreads();
@@ -233,20 +246,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
   for (int j = 0; j < nt; ++j) {
     TileAux& ta = aux->t[j];
     const int ebase = ta.info[0], ecount = ta.info[1], abase = ta.info[2], acount = ta.info[3];
-    for (int i = threadIdx.x; i < ecount; i += THREADS) ta.idx_l[i] = (uint8_t)(__ldg(p.in_idx + ebase + i) - ebase);
+    for (int i = threadIdx.x; i < ecount; i += THREADS) ta.idx_l[i] = (uint8_t)(__ldg(B.in_idx + ebase + i) - ebase);
     for (int rr = threadIdx.x; rr < 2 * TM; rr += THREADS) {       // every row gets a descriptor: dead rows read zeros
       const bool bond = rr < TM;
       const int r = bond ? rr : rr - TM;
       const bool live = r < (bond ? ecount : acount);
-      const int a = !live ? 0 : (bond ? __ldg(p.src + ebase + r) : abase + r);
+      const int a = !live ? 0 : (bond ? __ldg(B.src + ebase + r) : abase + r);
       const int skip = bond ? (r ^ 1) : -1;
-      const int pb = live ? __ldg(p.in_ptr + a) : ebase, pe = live ? __ldg(p.in_ptr + a + 1) : ebase;
+      const int pb = live ? __ldg(B.in_ptr + a) : ebase, pe = live ? __ldg(B.in_ptr + a + 1) : ebase;
       uint32_t o[2 * FASTN];
 #pragma unroll
       for (int t = 0; t < 2 * FASTN; ++t) o[t] = ZROW * CHP * 4;
       int cnt = 0;
       for (int t = pb; t < pe; ++t) {
-        const int k = __ldg(p.in_idx + t) - ebase;
+        const int k = __ldg(B.in_idx + t) - ebase;
         if (k == skip) continue;
 #pragma unroll
         for (int u = 0; u < 2 * FASTN; ++u)
@@ -301,8 +314,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
             umma::fence_proxy_async();
             if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 3] = clock64();
           }
-          umma::tma_load_2d(&p.tmA_hi[buf], full, st, kc * BK, tile * TM);
-          if (!p.fast) umma::tma_load_2d(&p.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
+          umma::tma_load_2d(&B.tmA_hi[buf], full, st, kc * BK, tile * TM);
+          if (!p.fast) umma::tma_load_2d(&B.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
         }
       }
     }
@@ -456,14 +469,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       if (l < depth) {
         c4 = ldg4(p.bias[l] + n);
         const int ecount = ta.info[1];
-        const char* hp = reinterpret_cast<const char*>(p.h0 + ((int64_t)(tile0 + j) * TM + r0) * H + n);
+        const char* hp = reinterpret_cast<const char*>(B.h0 + ((int64_t)(tile0 + j) * TM + r0) * H + n);
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k)
           if (r0 + k * RPP < ecount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(hp + (uint32_t)k * h0_row_step));
       } else {
         c4 = ldg4(p.w_ffn + n);
         const int abase = ta.info[2], acount = ta.info[3];
-        const char* qp = reinterpret_cast<const char*>(p.PQ + (int64_t)(abase + r0) * (2 * H) + H + n);
+        const char* qp = reinterpret_cast<const char*>(B.PQ + (int64_t)(abase + r0) * (2 * H) + H + n);
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k)
           if (r0 + k * RPP < acount) opnd[k] = __ldcg(reinterpret_cast<const float4*>(qp + (uint32_t)k * pq_row_step));
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           if (jr < nt * TM && k < fb) {
             const TileAux& ta = aux->t[jr / TM];
             const int r = jr % TM;
-            if (r < ta.info[1]) ev[q] = __ldg(p.ea + (size_t)(ta.info[0] + r) * fb + k);
+            if (r < ta.info[1]) ev[q] = __ldg(B.ea + (size_t)(ta.info[0] + r) * fb + k);
           }
         }
 #pragma unroll
@@ -507,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           const TileAux& ta = aux->t[jr / TM];
           const int r = jr % TM;
           for (int k = 16 + (et & 15); k < fb; k += 16)
-            ea_s[jr * fb + k] = r < ta.info[1] ? __ldg(p.ea + (size_t)(ta.info[0] + r) * fb + k) : 0.f;
+            ea_s[jr * fb + k] = r < ta.info[1] ? __ldg(B.ea + (size_t)(ta.info[0] + r) * fb + k) : 0.f;
         }
       }
       umma::named_bar_sync(3, GAT_THREADS);
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           const int r = r0 + u * RPP;
           if (r < ecount) {
             // the row's P' slice: every column group requested up front, then W_e^T's rows stream from shared memory
-            const float* pr = p.PQ + (size_t)__ldg(p.src + ebase + r) * (2 * H) + n0;
+            const float* pr = B.PQ + (size_t)__ldg(B.src + ebase + r) * (2 * H) + n0;
             float4 a[NI];
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
@@ -549,9 +562,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
                 v.x = tcg::act_t<RELU>(v.x, p.act); v.y = tcg::act_t<RELU>(v.y, p.act);
                 v.z = tcg::act_t<RELU>(v.z, p.act); v.w = tcg::act_t<RELU>(v.w, p.act);
                 imax = fmaxf(imax, tcg::amax4(v));
-                *reinterpret_cast<float4*>(p.h0 + row * H + n0 + c) = v;
-                char* od = reinterpret_cast<char*>(p.o_hi[0]) + (row * (size_t)p.ldo + n0 + c) * 2;
-                tcg::store_split4(v, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
+                *reinterpret_cast<float4*>(B.h0 + row * H + n0 + c) = v;
+                char* od = reinterpret_cast<char*>(B.o_hi[0]) + (row * (size_t)p.ldo + n0 + c) * 2;
+                tcg::store_split4(v, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + B.lo_delta));
               }
             }
           }
@@ -564,7 +577,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[jj]), (uint32_t)lane);
         }
       }
-      if (imax > 60000.f) atomicOr(p.overflow, 1);                  // fp16 range of the split (as edge_init flags it)
+      if (imax > 60000.f) atomicOr(B.overflow, 1);                  // fp16 range of the split (as edge_init flags it)
       // the ring goes back to its own use: its zero rows again, and this CTA's h0 columns are visible to every
       // gather thread (they are read back as the skip operand)
       umma::named_bar_sync(3, GAT_THREADS);
@@ -591,8 +604,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const float skip = readout ? 1.f : aux->skipv[l];
       const uint4* nbd = readout ? ta.nbd_a : ta.nbd_b;
       const uint2* nb2 = readout ? ta.nb2_a : ta.nb2_b;
-      // this thread's unit (row r0, column group cg) of the output operand; the lo rows sit p.lo_delta bytes further
-      char* oh_item = reinterpret_cast<char*>(p.o_hi[(l + 1) & 1]) +
+      // this thread's unit (row r0, column group cg) of the output operand; the lo rows sit B.lo_delta bytes further
+      char* oh_item = reinterpret_cast<char*>(B.o_hi[(l + 1) & 1]) +
                       (((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg) * 2;
       asm volatile("" : "+l"(oh_item));                            // opaque: kept in registers, not recomputed per unit
       // this thread's rows: which exist, which have more than FASTN / 2 FASTN neighbours
@@ -639,7 +652,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
               if (valid & (1u << k)) {
                 vmax = fmaxf(vmax, tcg::amax4(z));
                 char* od = oh + (uint32_t)k * o_row_step;
-                tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + p.lo_delta));
+                tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + B.lo_delta));
               }
             } else {
               // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this thread's columns
@@ -662,8 +675,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       if (!readout) {
         // this CTA's slice of h_{l+1} is stored: make it visible to the peers' TMA loads, then tell every CTA of the cluster
         if (vmax > 60000.f) {                                       // fp16 range of the split: flag the batch and this tile
-          atomicOr(p.overflow, 1);
-          atomicOr(p.tile_counter + tile, 0x10000);
+          atomicOr(B.overflow, 1);
+          atomicOr(B.tile_counter + tile, 0x10000);
         }
         // every gather warp publishes its own rows: the lanes order their stores against the peers' TMA reads (proxy
         // fence) and meet at the warp barrier, then one lane per peer CTA fences (cumulative over what the warp
@@ -688,29 +701,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         const int rx0 = ta.info[4], rxcount = ta.info[5];
         for (int rx = et; rx < rxcount; rx += GAT_THREADS) {
           const int b = rx0 + rx;
-          const int v0 = __ldg(p.atom_ptr + b) - abase, v1 = __ldg(p.atom_ptr + b + 1) - abase;
+          const int v0 = __ldg(B.atom_ptr + b) - abase, v1 = __ldg(B.atom_ptr + b + 1) - abase;
           float s = 0.f;
           for (int v = v0; v < v1; ++v) s += ta.tat[v];            // ascending atom id
-          p.partial_out[(int64_t)slice * p.n_rxn + b] = s;
+          B.partial_out[(int64_t)slice * B.n_rxn + b] = s;
         }
         // the last slice CTA of this tile to arrive adds the slices in a fixed order: deterministic, no extra kernel
         __threadfence();
         umma::named_bar_sync(3, GAT_THREADS);
-        if (et == 0) ta.ticket = atomicAdd(p.tile_counter + tile, 1);
+        if (et == 0) ta.ticket = atomicAdd(B.tile_counter + tile, 1);
         umma::named_bar_sync(3, GAT_THREADS);
         const int ticket = ta.ticket;
         if ((ticket & 0xffff) == S - 1) {
           __threadfence();
           const float bf = __ldg(p.b_ffn);
           // an operand of this tile (or a feature / h_0 of the batch) left the fp16 range: NaN energies, never silent
-          const bool poisoned = (ticket & 0x10000) != 0 || (__ldcg(p.overflow) & 3) != 0;
+          const bool poisoned = (ticket & 0x10000) != 0 || (__ldcg(B.overflow) & 3) != 0;
           for (int rx = et; rx < rxcount; rx += GAT_THREADS) {
             const int b = rx0 + rx;
             float s = 0.f;
-            for (int k = 0; k < S; ++k) s += __ldcg(p.partial_out + (int64_t)k * p.n_rxn + b);
-            p.out[b] = poisoned ? __int_as_float(0x7fc00000) : s + bf;
+            for (int k = 0; k < S; ++k) s += __ldcg(B.partial_out + (int64_t)k * B.n_rxn + b);
+            B.out[b] = poisoned ? __int_as_float(0x7fc00000) : s + bf;
           }
-          if (et == 0) p.tile_counter[tile] = 0;                    // ready for the next forward
+          if (et == 0) B.tile_counter[tile] = 0;                    // ready for the next forward
         }
       }
       stamp(i, 2);

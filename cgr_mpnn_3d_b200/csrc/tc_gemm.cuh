@@ -61,6 +61,16 @@ struct Cfg {
   static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "TMEM budget");
 };
 
+constexpr int MAX_GEMM_GROUP = 24;        // batches one EPI_PLAIN launch can take (atom projection of a group forward)
+// EPI_PLAIN over several batches in one launch: row tiles of batch i are blockIdx.y in [tile0, next tile0)
+struct GemmBatch {
+  CUtensorMap tmA_hi, tmA_lo;
+  float* out_f32;
+  int* overflow;
+  int m_rows;
+  int tile0;
+};
+
 struct TcGemmParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   CUtensorMap tmR;              // fp32 [rows, cols] operand of the epilogue (BOND: h0, READOUT: Q), box = [128, CH]
@@ -74,6 +84,8 @@ struct TcGemmParams {
   // EPI_PLAIN
   float* out_f32;
   int64_t ldc;
+  int n_batches;                // > 0: the A operand, rows and output of every batch come from gb[] (group launch)
+  GemmBatch gb[MAX_GEMM_GROUP];
   // tile-local epilogues
   const int32_t* tile_info;     // [T][8]: ebase, ecount, abase, acount, rx0, rxcount, 0, 0
   const int32_t* in_ptr;
@@ -222,7 +234,24 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   float* y_s = reinterpret_cast<float*>(smem);                                  // [TM][CHP], aliases the drained pipeline
   float* r1_s = reinterpret_cast<float*>(smem + C::Y_BYTES);                    // [TM][CH], chunk 1 (alias)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slice = blockIdx.x, tile = blockIdx.y;               // slices of one tile are neighbours: they share A in L2
+  const int slice = blockIdx.x;                                  // slices of one tile are neighbours: they share A in L2
+  int tile = blockIdx.y;
+  // operand / output of this CTA's rows: the launch's own, or (group launch of the atom projection) its batch's
+  const CUtensorMap* mapA_hi = &p.tmA_hi;
+  const CUtensorMap* mapA_lo = &p.tmA_lo;
+  float* out_f32 = p.out_f32;
+  int* overflow = p.overflow;
+  int m_rows = p.m_rows;
+  bool first_cta = blockIdx.x == 0 && blockIdx.y == 0;
+  if (EPI == EPI_PLAIN && p.n_batches > 0) {
+    int bi = 0;
+    while (bi + 1 < p.n_batches && tile >= p.gb[bi + 1].tile0) ++bi;
+    const GemmBatch& gbi = p.gb[bi];
+    first_cta = blockIdx.x == 0 && tile == gbi.tile0;
+    tile -= gbi.tile0;
+    mapA_hi = &gbi.tmA_hi; mapA_lo = &gbi.tmA_lo;
+    out_f32 = gbi.out_f32; overflow = gbi.overflow; m_rows = gbi.m_rows;
+  }
   const int n0 = slice * BN;
   // columns this slice really owns, rounded up to the MMA granularity (runtime N of the instruction)
   int n_eff = p.n_total - n0;
@@ -231,7 +260,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
 #define TC_STAMP(k) do { if (dbg && threadIdx.x == 64) dbg[k] = clock64(); } while (0)
   TC_STAMP(0);
   // the atom projection opens a forward: clear the per-forward overflow bit (bit 1, feature overflow, belongs to the batch)
-  if (EPI == EPI_PLAIN && p.overflow && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAnd(p.overflow, ~1);
+  if (EPI == EPI_PLAIN && overflow && first_cta && threadIdx.x == 0) atomicAnd(overflow, ~1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -242,8 +271,8 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
     umma::mbar_init(umma::smem_u32(&aux->r_full[0]), 1);
     umma::mbar_init(umma::smem_u32(&aux->r_full[1]), 1);
     umma::mbar_fence_init();
-    umma::tma_prefetch_desc(&p.tmA_hi);
-    umma::tma_prefetch_desc(&p.tmA_lo);
+    umma::tma_prefetch_desc(mapA_hi);
+    umma::tma_prefetch_desc(mapA_lo);
     umma::tma_prefetch_desc(&p.tmB_hi);
     umma::tma_prefetch_desc(&p.tmB_lo);
     if (EPI != EPI_PLAIN) umma::tma_prefetch_desc(&p.tmR);
@@ -283,10 +312,10 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
         const uint32_t full = umma::smem_u32(&aux->full[s]);
         const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
         umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
-        umma::tma_load_2d(&p.tmA_hi, full, st, kc * BK, tile * TM);
+        umma::tma_load_2d(mapA_hi, full, st, kc * BK, tile * TM);
         umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
         if (!p.fast) {
-          umma::tma_load_2d(&p.tmA_lo, full, st + A_BYTES, kc * BK, tile * TM);
+          umma::tma_load_2d(mapA_lo, full, st + A_BYTES, kc * BK, tile * TM);
           umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
         }
       }
@@ -456,9 +485,9 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
       if (lane_on) {
         for (int r = warp; r < TM; r += NWARPS) {
           const int64_t row = (int64_t)tile * TM + r;
-          if (row >= p.m_rows) break;
+          if (row >= m_rows) break;
           const float4 y = ld4(y_s + r * CHP + c);
-          float* o = p.out_f32 + row * p.ldc + n;
+          float* o = out_f32 + row * p.ldc + n;
           if (n + 3 < p.n_total && (p.ldc & 3) == 0) {
             *reinterpret_cast<float4*>(o) = make_float4(y.x + bias4.x, y.y + bias4.y, y.z + bias4.z, y.w + bias4.w);
           } else {

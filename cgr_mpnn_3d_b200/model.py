@@ -442,6 +442,55 @@ class GNN(nn.Module):
         _lib.check(rc, "cgr_gnn_infer_host")
         return hout[:b].clone()
 
+    def forward_group(self, batches) -> list:
+        """Energies of several independent device-resident batches (a screening job is a stream of them), inference
+        only: ``[self(b) for b in batches]`` in TWO launches per group of up to 24 batches instead of two per batch --
+        one atom projection over every batch's atom tiles, one fused cluster kernel over every batch's tile groups
+        (``cgr_gnn_forward_group``).  Same kernels and arithmetic as ``forward`` with ``tile_policy="throughput"``: the
+        energies are bit-identical to it.  Batches the tcgen05 fused kernels cannot take (reactions of more than 128
+        directed bonds, engine "simt", a weight version demoted by the fp16-range guard) fall back to per-batch
+        ``forward`` calls -- inside CUDA, never on the CPU."""
+        from . import ops
+        batches = list(batches)
+        if not batches:
+            return []
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("forward_group is an inference entry: call it under torch.no_grad()")
+        self._check_arch()
+        params = self._param_list()
+        dev = params[0].device
+        if dev.type != "cuda" or any(b.x.device != dev for b in batches):
+            raise RuntimeError("forward_group needs the module and every batch on the same CUDA device")
+        plans = [plan_for(b) for b in batches]
+        if self.validate_inputs:
+            for pl in plans:
+                pl.check()
+        if (getattr(self, "engine", "auto") in ("simt", 0, "tc_layerwise") or self._tc_demoted() or self.depth > 13
+                or not all(self._fused_ok(pl) for pl in plans)):
+            return [self._forward_device(b, dev) for b in batches]
+        fa, fb = int(batches[0].x.shape[1]), int(batches[0].edge_attr.shape[1])
+        tc_w = self._tc_weights([p.detach() for p in params], fa, fb)
+        outs = []
+        with torch.cuda.device(dev):
+            lo = 0
+            while lo < len(batches):
+                # a call takes up to GROUP_MAX batches; a batch that appears twice goes to the next call (its status
+                # words -- readout tickets, range flag -- belong to one forward at a time)
+                graphs, seen = [], set()
+                while lo < len(batches) and len(graphs) < ops.GROUP_MAX and id(plans[lo]) not in seen:
+                    b, pl = batches[lo], plans[lo]
+                    seen.add(id(pl))
+                    x_hi, x_lo = split_features_for(b, pl)
+                    graphs.append((b.x, b.edge_attr, pl, x_hi, x_lo))
+                    lo += 1
+                outs += ops.gnn_forward_group(graphs, [p.detach() for p in params], self.depth,
+                                              _act_id(self.activation_fn), bool(self.use_learnable_skip), tc_w,
+                                              fast=self._fast())
+            if not torch.cuda.is_current_stream_capturing():
+                for pl in plans:
+                    self.__dict__.setdefault("_ovf_pending", []).append(self._queue_overflow_check(pl.tc_status))
+        return outs
+
     def predict_stream(self, batches, depth: int = 4, workers: int = 2, coalesce: int = 8,
                        coalesce_reactions: int = 1024):
         """Pipelined inference over an iterable of HOST batches (the screening workload): yields one CPU

@@ -114,6 +114,53 @@ def _f32c(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
+GROUP_MAX = 24      # batches one cgr_gnn_forward_group call takes (tcf::MAX_GROUP)
+
+
+def gnn_forward_group(graphs: Sequence[tuple], params: Sequence[Tensor], depth: int, act: int, use_skip: bool,
+                      tc_weights: Tensor, fast: bool = False) -> List[Tensor]:
+    """Inference forward of several independent batches in TWO launches (``cgr_gnn_forward_group``): one atom
+    projection over every batch's atom tiles, one fused cluster kernel over every batch's tile groups.
+
+    ``graphs``: per batch ``(x, edge_attr, plan, x_hi, x_lo)`` with a tile plan (``plan.tile_info``); returns one
+    energy tensor per batch (views of one allocation).  tcgen05 engine only, no autograd."""
+    lib = _lib.load()
+    if not 1 <= len(graphs) <= GROUP_MAX:
+        raise ValueError(f"a group holds 1..{GROUP_MAX} batches")
+    x0 = graphs[0][0]
+    _require_cuda(x0, *params)
+    params = [_f32c(p) for p in params]
+    fa, fb = int(x0.shape[1]), int(graphs[0][1].shape[1])
+    ctx = _ctx_cached("fwd", params, depth, act, use_skip, fa, fb, [0.0] * depth)
+    if tc_weights.numel() > 0:
+        ctx.params.tc_weights = tc_weights.data_ptr()
+    ctx.params.tc_throughput = 1
+    ctx.params.tc_fast = 1 if fast else 0
+    n = len(graphs)
+    keep = []
+    garr = (_lib.CgrGraph * n)()
+    sizes = []
+    for i, (x, edge_attr, plan, x_hi, x_lo) in enumerate(graphs):
+        x, edge_attr = _f32c(x), _f32c(edge_attr)
+        keep.append((x, edge_attr))
+        if plan.tile_info is None or plan.n_tiles <= 0:
+            raise RuntimeError("group forward needs tileable batches (reactions of <= 128 bonds)")
+        garr[i] = _graph_struct(x, edge_attr, plan.src, plan.dst, plan.in_ptr, plan.in_idx, plan.atom_ptr,
+                                plan.tile_info, plan.n_tiles, plan.tc_status, x_hi, x_lo)
+        sizes.append(int(garr[i].n_rxn))
+    out_all = torch.empty(sum(sizes), dtype=torch.float32, device=x0.device)
+    outs = list(out_all.split(sizes))
+    optr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(x0.device):
+        ws_bytes = int(lib.cgr_forward_group_workspace(C.byref(ctx.params), garr, n))
+        if ws_bytes <= 0:
+            raise RuntimeError("cgr_forward_group_workspace: unsupported group")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
+        _lib.check(lib.cgr_gnn_forward_group(C.byref(ctx.params), garr, n, optr, ws.data_ptr(), ws_bytes, _stream()),
+                   "cgr_gnn_forward_group")
+    return outs
+
+
 @torch.library.custom_op("cgr_b200::gnn_forward", mutates_args=())
 def gnn_forward(x: Tensor, edge_attr: Tensor, src: Tensor, dst: Tensor, in_ptr: Tensor, in_idx: Tensor,
                 atom_ptr: Tensor, params: Sequence[Tensor], depth: int, act: int, use_skip: bool,

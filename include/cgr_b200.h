@@ -228,7 +228,8 @@ size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_
                              int32_t engine);
 /* out [B].  `saved` must be non-NULL when training != 0 (activations for backward).
  * Engine CGR_ENGINE_TC picks its path from the arguments:
- *   - g->tile_info set, saved == NULL           : fused tile kernels (7 launches), inference;
+ *   - g->tile_info set, saved == NULL           : fused tile kernels, inference: the atom projection, then ONE cluster
+ *                                                 kernel (edge initialisation, every bond layer, readout, pool, FFN);
  *   - g->tile_info set, saved->tc_blob != NULL  : the same kernels keeping every layer's FP16 operands in tc_blob
  *                                                 (ReLU networks; cgr_tc_saved_bytes > 0) -- cgr_gnn_backward with the
  *                                                 same `saved` then runs the fused tile-local backward; when
@@ -239,6 +240,18 @@ size_t cgr_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_
 int cgr_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_saved_t* saved,
                     int32_t training, uint64_t seed, int32_t engine, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* The same inference forward for SEVERAL independent batches in one call (a screening loop -- test.py:103-113, the
+ * CLI -- is a stream of them): `graphs[0..n_graphs)` (1..24 per call, every one with a tile plan, tc_status and,
+ * optionally, prepared x_hi / x_lo), energies of batch i to outs[i] [graphs[i].n_rxn].  TWO launches per call instead
+ * of two per batch: one atom projection over every batch's atom tiles and one fused cluster kernel over every batch's
+ * tile groups (per-batch operands and index arrays travel as kernel parameters; the weights are shared), so a group
+ * of 64-reaction batches fills the 148 SMs wave after wave.  Same kernels and arithmetic as cgr_gnn_forward with
+ * p->tc_throughput = 1: bit-identical energies.  tcgen05 engine, inference only; p->tc_weights may be NULL
+ * (prepared per call).  workspace >= cgr_forward_group_workspace() (0: a batch has no tile plan / n_graphs > 24). */
+size_t cgr_forward_group_workspace(const cgr_params_t* p, const cgr_graph_t* graphs, int32_t n_graphs);
+int cgr_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* graphs, int32_t n_graphs, float* const* outs,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 size_t cgr_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int32_t engine);
 /* (5) explicit backward of (2)-(4): grad_out [B] -> every parameter gradient. */

@@ -1183,3 +1183,38 @@ def test_stage_level_backward_parity(name):
                                      want_z=True)
     gwi, gbi = stage_ops.edge_init_bwd(dh_in + dh0, h0, d.x, d.edge_attr, plan, act_id, z0=None if act_id == 0 else z0)
     assert tensor_error(gwi, oracle.edge_init.weight.grad) < 1e-5 and tensor_error(gbi, oracle.edge_init.bias.grad) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", ["relu", "silu"])
+def test_forward_group_matches_per_batch_forward(act):
+    """cgr_gnn_forward_group: several independent batches in two launches == per-batch forwards, bit for bit
+    (same kernels, same reduction orders), for ragged group members: one reaction, one tile, many tiles."""
+    meta = dict(fa=78 + 64, fb=14, depth=3, hidden=400, skip=True, wseed=5, act=act)
+    model = build_model(meta, engine="tc").eval()
+    model.tile_policy = "throughput"
+    sizes = [64, 1, 7, 33, 64, 2, 128]
+    batches = [make_batch(b, seed=100 + i, kind="t1x", fa=meta["fa"]).to("cuda") for i, b in enumerate(sizes)]
+    with torch.no_grad():
+        ref = [model(b) for b in batches]
+        got = model.forward_group(batches)
+        got2 = model.forward_group(batches[::-1])[::-1]           # another packing of the same batches
+    model.check_numerics()
+    oracle = build_oracle(meta)
+    for b, r, g, g2 in zip(batches, ref, got, got2):
+        assert g.shape == r.shape
+        assert torch.equal(g, r) and torch.equal(g2, r)
+        assert scale_normalised_error(g.cpu(), oracle(b.to("cpu")).detach()) < EA_TOL
+    # more batches than one call takes, fast precision mode, and a drug-like member (falls back to per-batch calls)
+    many = [batches[i % len(batches)] for i in range(30)]
+    with torch.no_grad():
+        outs = model.forward_group(many)
+        assert all(torch.equal(o, ref[i % len(batches)]) for i, o in enumerate(outs))
+        model.precision = "fast"
+        f_ref = [model(b) for b in batches]
+        f_got = model.forward_group(batches)
+        assert all(torch.equal(a, b) for a, b in zip(f_ref, f_got))
+        model.precision = "fp32"
+        big = make_batch(2, seed=9, kind="drug", fa=meta["fa"]).to("cuda")
+        mixed = model.forward_group([batches[0], big])
+        assert torch.equal(mixed[0], ref[0]) and scale_normalised_error(mixed[1].cpu(), oracle(big.to("cpu")).detach()) < EA_TOL
