@@ -71,6 +71,9 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=16, help="CUDA streams the independent steps are pipelined over")
+    ap.add_argument("--group", type=int, default=20,
+                    help="steps issued per GNN.forward_group call (two launches for the whole group); 1 = one "
+                         "GNN.forward call per step, pipelined over --streams")
     ap.add_argument("--coalesce", type=int, default=8,
                     help="host batches predict_stream submits together in the e2e leg (1 = one submission per batch)")
     ap.add_argument("--policy", default="auto", choices=["auto", "latency", "throughput"],
@@ -113,7 +116,8 @@ def stage_bytes(stage, n, e, b, cfg, s=4):
     return {
         "bond_layer": per_depth,
         "tc_readout": readout,
-        "tc_fwd_fused": d * per_depth + readout,         # every bond layer + the readout in one launch
+        # edge initialisation (bond features, indices, write h0) + every bond layer + the readout in one launch
+        "tc_fwd_fused": s * (e * fb + e * h) + 16 * e + 8 * n + d * per_depth + readout,
         "tc_atom_proj": s * (2 * n * fa) + 4 * 2 * h * fa,   # x for the edge initialisation and for the readout, W_x / W_ox
         "tc_edge_init": s * (e * fb + e * h) + 16 * e + 8 * n,   # bond features, indices, write h0
         "gemm_bond_update": s * (3 * e * h) + 4 * h * h,
@@ -325,7 +329,7 @@ def main():
     if args.pool:
         n_pool = max(2, args.pool)
     else:
-        n_pool = 48 if small else (4 if cfg["kind"] == "t1x" else 3)
+        n_pool = 60 if small else (4 if cfg["kind"] == "t1x" else 3)
     host = [make_batch(B, seed=1000 + 997 * rank + i, kind=cfg["kind"], fa=cfg["fa"]) for i in range(n_pool)]
     for hb in host:
         hb.y = None
@@ -358,32 +362,62 @@ def main():
         c0 = lib.cgr_launch_count()
         model(pool[0])
         launches_per_step = lib.cgr_launch_count() - c0
-        n_streams = max(1, min(n_streams_req, steps))
+        group = max(1, min(args.group, 24, steps)) if (small and engine != "simt") else 1
+        n_chunks = -(-steps // group)
+        n_streams = max(1, min(n_streams_req, n_chunks if group > 1 else steps))
         streams = [torch.cuda.Stream() for _ in range(n_streams)]
         side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
-        region = None
-        if not args.no_graph:
-            region = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(region, stream=side):
-                fork_c = torch.cuda.Event()
-                fork_c.record(side)
-                for st in streams:
-                    st.wait_event(fork_c)
-                for i in range(steps):
+        # distinct timed regions rotate through the pool, so a batch comes back only after more than an L2 of other
+        # inputs went through (20 steps x 3.5 MB = 70 MB per region, 60 batches = 210 MB in all)
+        n_regions = max(1, min(4, n_pool // steps))
+
+        def issue_region(r):
+            """`steps` forwards of region r: batches (r * steps + i) % n_pool."""
+            ids = [(r * steps + i) % n_pool for i in range(steps)]
+            if group > 1:
+                for c in range(n_chunks):
+                    chunk = ids[c * group:(c + 1) * group]
+                    with torch.cuda.stream(streams[c % n_streams]):
+                        for k, o in zip(chunk, model.forward_group([pool[k] for k in chunk])):
+                            outs[k] = o
+            else:
+                for i, k in enumerate(ids):
                     with torch.cuda.stream(streams[i % n_streams]):
-                        outs[i % n_pool] = model(pool[i % n_pool])
-                for st in streams:
-                    ev_c = torch.cuda.Event()
-                    ev_c.record(st)
-                    side.wait_event(ev_c)
+                        outs[k] = model(pool[k])
+
+        if group > 1:
+            model.forward_group(pool[:group])           # warm: workspaces, tensor maps
+            torch.cuda.synchronize()
+            c0 = lib.cgr_launch_count()
+            model.forward_group(pool[:group])
+            launches_per_step = (lib.cgr_launch_count() - c0) / group
+        regions = []
+        if not args.no_graph:
+            for r in range(n_regions):
+                region = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(region, stream=side):
+                    fork_c = torch.cuda.Event()
+                    fork_c.record(side)
+                    for st in streams:
+                        st.wait_event(fork_c)
+                    issue_region(r)
+                    for st in streams:
+                        ev_c = torch.cuda.Event()
+                        ev_c.record(st)
+                        side.wait_event(ev_c)
+                regions.append(region)
+        region_no = [0]
 
         def run_region():
-            if region is not None:
-                region.replay()
+            r = region_no[0] % n_regions
+            region_no[0] += 1
+            if regions:
+                regions[r].replay()
             else:
-                for i in range(steps):
-                    outs[i % n_pool] = model(pool[i % n_pool])
+                issue_region(r)
+                for st in streams:
+                    main.wait_stream(st)
 
         clocks = ClockSampler(local_rank).start()
         for _ in range(max(1, -(-max(3, args.warmup) // steps))):       # >= W untimed warm-up steps
@@ -436,14 +470,26 @@ def main():
     # launching stream, the stream kept busy so that an event pair brackets kernel time, not host launch latency) ----
     prof_steps = min(steps, 40) if small else min(steps, 6)
     stage_ms, stage_cnt = {}, {}
+    prof_units = 0                          # steps the profiled launches processed (group mode: `group` per launch)
     with torch.no_grad():
+        def prof_call(i):
+            nonlocal prof_units
+            if group > 1:
+                ids = [(i * group + k) % n_pool for k in range(group)]
+                model.forward_group([pool[k] for k in ids])
+                prof_units += group
+            else:
+                lat_model(pool[i % n_pool])
+                prof_units += 1
         for i in range(3):
-            lat_model(pool[i % n_pool])
+            prof_call(i)
+        prof_units = 0
         torch.cuda.synchronize()
         lib.cgr_profile_enable(1)
-        for i in range(prof_steps):
+        n_prof = max(3, prof_steps // group) if group > 1 else prof_steps
+        for i in range(n_prof):
             torch.cuda._sleep(2_000_000 if small else 200_000)
-            lat_model(pool[i % n_pool])
+            prof_call(i)
         torch.cuda.synchronize()
         name = ctypes.create_string_buffer(64)
         ms = ctypes.c_float()
@@ -640,10 +686,12 @@ def main():
     clocks.stop()
     roofline = None
     if dominant:
-        per_launch = stage_bytes(dominant, n_atoms, n_bonds, B, cfg)
-        if per_launch is None:
-            per_launch = algorithmic_bytes_fwd(n_atoms, n_bonds, B, cfg) / max(1, launches_per_step)
-        lps = stage_cnt[dominant] / prof_steps
+        per_unit = stage_bytes(dominant, n_atoms, n_bonds, B, cfg)
+        if per_unit is None:
+            per_unit = algorithmic_bytes_fwd(n_atoms, n_bonds, B, cfg) / max(1, launches_per_step)
+        units_per_launch = prof_units / stage_cnt[dominant]              # group mode: `group` batches per launch
+        per_launch = per_unit * units_per_launch
+        lps = stage_cnt[dominant] / prof_units
         dur_us = 1e3 * stage_ms[dominant] / stage_cnt[dominant]          # CUDA events around the launch, busy stream
         share = stage_ms[dominant] / sum(stage_ms.values())
         traffic = None
@@ -655,7 +703,8 @@ def main():
         pipe_us = ms_per_step * 1e3 * share / lps                        # machine time the pipelined region spends per launch
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": per_launch / (dur_us * 1e-6) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": per_launch / (dur_us * 1e-6) / 1e9 / hbm_peak, "traffic": traffic,
-                    "algorithmic_bytes_per_launch": per_launch, "peak_kind": peak_kind,
+                    "algorithmic_bytes_per_launch": per_launch, "algorithmic_bytes_per_batch": per_unit,
+                    "batches_per_launch": units_per_launch, "peak_kind": peak_kind,
                     "avg_launch_us": dur_us, "launches_per_step": lps,
                     "pipelined_us_per_launch": pipe_us,
                     "pipelined_frac": per_launch / (pipe_us * 1e-6) / 1e9 / hbm_peak,
@@ -677,9 +726,13 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload,
                        "engine": engine, "precision": args.precision, "cuda_graph": not args.no_graph, "streams": n_streams,
-                       "timed_region": f"{steps} forwards captured as ONE CUDA graph over {n_streams} parallel branches; "
-                                       f"median of {repeats} regions (min {min_ms / steps * 1e3:.2f} us/step), each between "
-                                       f"barrier + synchronize, max over ranks",
+                       "group": group,
+                       "timed_region": (f"{steps} forwards issued as {n_chunks} GNN.forward_group call(s) of up to {group} "
+                                        f"batches (two launches per call: atom projection + fused cluster kernel)"
+                                        if group > 1 else f"{steps} GNN.forward calls") +
+                                       f", captured as ONE CUDA graph over {n_streams} parallel branch(es); {n_regions} "
+                                       f"such regions rotate through the batch pool; median of {repeats} regions (min "
+                                       f"{min_ms / steps * 1e3:.2f} us/step), each between barrier + synchronize, max over ranks",
                        "single_stream_ms_per_step": single_stream_ms,
                        "eager_device_batch_rate": eager_device_rate,
                        "parallelism": f"replicas x{world}, no collective", "cpu_affinity": affinity,
@@ -693,8 +746,8 @@ def main():
                               "executed_tensor_flops_factor": 3 if args.precision == "fp32" else 1,
                               "peak_kind": peak_kind},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
-            "gpu_launches": int(launches_per_step) * steps * repeats,
-            "launches_per_step": int(launches_per_step),
+            "gpu_launches": int(round(launches_per_step * steps)) * repeats,
+            "launches_per_step": launches_per_step,
             "precision": precision_info,
         }
         if train:
