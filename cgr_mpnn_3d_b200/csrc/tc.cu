@@ -428,15 +428,27 @@ int launch_gemm_t(const TcGemmParams& prm, int m_tiles, int n_slices, const char
   cgr_note_launch(name, st, 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)n_slices, (unsigned)m_tiles);
+  const int mc = (EPI == EPI_PLAIN && prm.mc > 1) ? prm.mc : 1;     // weight multicast: clusters of mc row tiles
+  cfg.gridDim = dim3((unsigned)n_slices, (unsigned)(cgr_ceil_div(m_tiles, mc) * mc));   // (tiles past the end store nothing)
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {                                     // pdl: this launch may overlap the tail of its predecessor
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (mc > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = (unsigned)mc;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;                    // pdl: this launch may overlap the tail of its predecessor
+  cfg.numAttrs = na;
   CGR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, EPI, RELU, NT>, prm));
   return CGR_OK;
 }
@@ -713,6 +725,21 @@ size_t tc_forward_workspace(const cgr_params_t* p, const cgr_graph_t* g, int tra
 }
 
 namespace {
+// atom projection with wide slices: clusters of `mc` row tiles share every weight chunk (each CTA loads 1/mc of its rows
+// and multicasts them) -- the kernel is operand-fill bound, the weights are 62 % of its fill
+int ap_multicast(TcGemmParams* ap, const __half* w_hi, const __half* w_lo, int64_t rows, int64_t cols, int64_t ld, int bn) {
+  static const int mc_env = getenv("CGR_AP_MC") ? atoi(getenv("CGR_AP_MC")) : 1;   // measured: no gain (share 0.22 vs 0.21), off
+  const int mc = (mc_env == 2 || mc_env == 4) ? mc_env : 1;
+  if (mc == 1 || bn % (8 * mc) != 0) return CGR_OK;          // shares of whole 8-row swizzle groups only
+  int rc;
+  if ((rc = make_map(&ap->tmB_hi_mc, w_hi, rows, cols, ld, bn / mc))) return rc;
+  if ((rc = make_map(&ap->tmB_lo_mc, w_lo, rows, cols, ld, bn / mc))) return rc;
+  ap->mc = mc;
+  return CGR_OK;
+}
+}  // namespace
+
+namespace {
 // fused forward kernel: what every batch of a launch shares (weights, biases, shapes)
 int fwd_fill_shared(tcf::FwdParams* prm, const cgr_params_t* p, const char* wbuf, const WLayout& wl, const FwdChoice& fc,
                     int64_t kp_h, bool fused_init, int fast) {
@@ -863,6 +890,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.ldc = 2 * H;
     prm.fast = fast;
     prm.overflow = flag;             // first kernel of the forward: clears the per-forward overflow bit
+    if (bn == BN_LARGE && (rc = ap_multicast(&prm, w_hi(0), w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false,
                                 two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
     if (rc) return rc;
@@ -1080,6 +1108,8 @@ int tc_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* gs, int n, fl
     ap.ldc = 2 * H;
     ap.fast = fast;
     ap.n_batches = n;
+    if ((rc = ap_multicast(&ap, (const __half*)(wbuf + wl.off_hi[0]), (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa,
+                           wl.ld[0], bn))) return rc;
     rc = launch_gemm<EPI_PLAIN>(ap, bn, tile0, true, "tc_atom_proj", false, false, st);
     if (rc) return rc;
   }

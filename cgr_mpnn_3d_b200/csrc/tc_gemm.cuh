@@ -85,6 +85,9 @@ struct TcGemmParams {
   float* out_f32;
   int64_t ldc;
   int n_batches;                // > 0: the A operand, rows and output of every batch come from gb[] (group launch)
+  int mc;                       // EPI_PLAIN: > 1 = clusters of mc row tiles (grid.y) share the weight chunks -- every CTA
+                                // loads 1/mc of the B rows and multicasts them (tmB_*_mc: box of BN / mc rows)
+  CUtensorMap tmB_hi_mc, tmB_lo_mc;
   GemmBatch gb[MAX_GEMM_GROUP];
   // tile-local epilogues
   const int32_t* tile_info;     // [T][8]: ebase, ecount, abase, acount, rx0, rxcount, 0, 0
@@ -252,6 +255,9 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
     mapA_hi = &gbi.tmA_hi; mapA_lo = &gbi.tmA_lo;
     out_f32 = gbi.out_f32; overflow = gbi.overflow; m_rows = gbi.m_rows;
   }
+  const uint32_t mc = (EPI == EPI_PLAIN && p.mc > 1) ? (uint32_t)p.mc : 1u;
+  const uint32_t mc_rank = mc > 1 ? umma::cluster_ctarank() : 0u;
+  const uint16_t mc_mask = (uint16_t)((1u << mc) - 1u);
   const int n0 = slice * BN;
   // columns this slice really owns, rounded up to the MMA granularity (runtime N of the instruction)
   int n_eff = p.n_total - n0;
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       umma::mbar_init(umma::smem_u32(&aux->full[s]), 1);
-      umma::mbar_init(umma::smem_u32(&aux->empty[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->empty[s]), mc);       // multicast: every CTA of the cluster releases the stage
     }
     umma::mbar_init(umma::smem_u32(&aux->tmem_full), 1);
     umma::mbar_init(umma::smem_u32(&aux->r_full[0]), 1);
@@ -286,6 +292,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
+  if (mc > 1) umma::cluster_sync_all();           // the peers' barriers exist before anything is multicast to them
   const uint32_t tmem = aux->tmem_base;
   constexpr bool BWD = EPI == EPI_BOND_BWD || EPI == EPI_INIT_BWD;
   const int r_row0 = (EPI == EPI_BOND || BWD) ? tile * TM : (EPI == EPI_READOUT ? aux->info[2] : 0);
@@ -313,10 +320,17 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
         const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
         umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
         umma::tma_load_2d(mapA_hi, full, st, kc * BK, tile * TM);
-        umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
-        if (!p.fast) {
-          umma::tma_load_2d(mapA_lo, full, st + A_BYTES, kc * BK, tile * TM);
-          umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+        if (!p.fast) umma::tma_load_2d(mapA_lo, full, st + A_BYTES, kc * BK, tile * TM);
+        if (mc > 1) {
+          // this CTA's share of the weight rows, delivered to every CTA of the cluster (same stage, same offset)
+          const uint32_t rows = (uint32_t)BN / mc, roff = mc_rank * rows;
+          umma::tma_load_2d_mc(&p.tmB_hi_mc, full, st + 2 * A_BYTES + roff * (BK * 2), kc * BK, n0 + (int)roff, mc_mask);
+          if (!p.fast)
+            umma::tma_load_2d_mc(&p.tmB_lo_mc, full, st + 2 * A_BYTES + B_BYTES + roff * (BK * 2), kc * BK, n0 + (int)roff,
+                                 mc_mask);
+        } else {
+          umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
+          if (!p.fast) umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
         }
       }
       __syncwarp();
@@ -356,7 +370,8 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
             umma::mma_f16_ss(tmem, da_hi + adv, db_hi + adv, idesc, 1u);
           }
         }
-        umma::mma_commit(umma::smem_u32(&aux->empty[s]));         // frees the stage when these MMAs retire
+        if (mc > 1) umma::mma_commit_mc(umma::smem_u32(&aux->empty[s]), mc_mask);
+        else umma::mma_commit(umma::smem_u32(&aux->empty[s]));   // frees the stage when these MMAs retire
         if (kc == p.num_k - 1) umma::mma_commit(umma::smem_u32(&aux->tmem_full));
       }
       __syncwarp();
@@ -785,6 +800,7 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   }
 
   __syncthreads();
+  if (mc > 1) umma::cluster_sync_all();           // no CTA leaves while a peer may still arrive on its barriers
   TC_STAMP(5);
   if (warp == 1) umma::tmem_dealloc(tmem, C::TMEM_COLS);
 #undef TC_STAMP
