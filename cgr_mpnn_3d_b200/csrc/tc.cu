@@ -23,6 +23,7 @@
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
 #include "tc_fwd.cuh"
+#include "tc_proj.cuh"
 #include "umma.cuh"
 
 namespace {
@@ -482,6 +483,43 @@ int launch_gemm(const TcGemmParams& prm, int bn, int m_tiles, bool relu, const c
               : launch_gemm_t<BN_SMALL, EPI, false, NT_SMALL>(prm, m_tiles, n_slices, name, pdl, st);
 }
 
+// ---- persistent atom projection (tc_proj.cuh): one CTA per SM walks the (row tile, column slice) units ----
+constexpr int PROJ_BN_3STAGE = 160, PROJ_BN_WIDE = 208;
+// slice width of the persistent kernel: 160 (three operand stages) unless 208 pads the output width less; 0 = use
+// the one-unit-per-CTA kernel
+int proj_bn(int bn_default, int n_total) {
+  static const bool off = getenv("CGR_AP_OLD") != nullptr;       // experiments: the one-unit-per-CTA kernel
+  static const int forced = getenv("CGR_AP_BN") ? atoi(getenv("CGR_AP_BN")) : 0;
+  if (off || bn_default != BN_LARGE || n_total % 8 != 0) return 0;
+  if (forced == PROJ_BN_3STAGE || forced == PROJ_BN_WIDE) return forced;
+  const int64_t pad160 = cgr_ceil_div(n_total, PROJ_BN_3STAGE) * PROJ_BN_3STAGE - n_total;
+  const int64_t pad208 = cgr_ceil_div(n_total, PROJ_BN_WIDE) * PROJ_BN_WIDE - n_total;
+  return pad160 <= pad208 ? PROJ_BN_3STAGE : PROJ_BN_WIDE;
+}
+template <int BN>
+int launch_proj_t(const TcGemmParams& prm, int m_tiles, cudaStream_t st) {
+  using C = tcp::PCfg<BN>;
+  static bool attr_done = false;      // benign race: the attribute is idempotent
+  static int n_sm = 0;
+  if (!attr_done) {
+    CGR_CUDA(cudaFuncSetAttribute(tcp::tc_proj_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    int dev = 0;
+    CGR_CUDA(cudaGetDevice(&dev));
+    CGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  const int n_slices = (int)cgr_ceil_div(prm.n_total, BN);
+  const int n_units = m_tiles * n_slices;
+  CgrRange prof("tc_atom_proj", st);
+  cgr_note_launch("tc_atom_proj", st, 1);
+  tcp::tc_proj_kernel<BN><<<(unsigned)(n_units < n_sm ? n_units : n_sm), tcp::THREADS, C::SMEM_BYTES, st>>>(prm, n_units, n_slices);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
+int launch_proj(const TcGemmParams& prm, int bn, int m_tiles, cudaStream_t st) {
+  return bn == PROJ_BN_3STAGE ? launch_proj_t<PROJ_BN_3STAGE>(prm, m_tiles, st) : launch_proj_t<PROJ_BN_WIDE>(prm, m_tiles, st);
+}
+
 // ---- fused forward: all bond layers + readout of a tile group in one cluster launch (tc_fwd.cuh) ----
 constexpr int FWD_BN_WIDE = 208, FWD_BN_NARROW = 80;
 
@@ -877,7 +915,9 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     if ((rc = make_map(&prm.tmA_lo, x_lo, N, fa, w.kp_x, TM))) return rc;
     // throughput mode: wide slices (operand bytes streamed per batch: 42 MB instead of 67 MB at cfg-2)
     static const bool ap_wide = getenv("CGR_AP_NARROW") == nullptr;
-    const int bn = (p->tc_throughput != 0 && ap_wide) ? BN_LARGE : choose_bn(cgr_ceil_div(N, TM), 2 * H);
+    int bn = (p->tc_throughput != 0 && ap_wide) ? BN_LARGE : choose_bn(cgr_ceil_div(N, TM), 2 * H);
+    const int pbn = proj_bn(bn, 2 * H);          // persistent kernel (wide-slice regime): its own slice width
+    if (pbn) bn = pbn;
     if ((rc = make_map(&prm.tmB_hi, w_hi(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     if ((rc = make_map(&prm.tmB_lo, w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
     prm.num_k = (int)cgr_ceil_div(fa, BK);
@@ -890,9 +930,13 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.ldc = 2 * H;
     prm.fast = fast;
     prm.overflow = flag;             // first kernel of the forward: clears the per-forward overflow bit
-    if (bn == BN_LARGE && (rc = ap_multicast(&prm, w_hi(0), w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
-    rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false,
-                                two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
+    if (pbn) {
+      rc = launch_proj(prm, pbn, (int)cgr_ceil_div(N, TM), st);
+    } else {
+      if (bn == BN_LARGE && (rc = ap_multicast(&prm, w_hi(0), w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
+      rc = launch_gemm<EPI_PLAIN>(prm, bn, (int)cgr_ceil_div(N, TM), true, "tc_atom_proj", false,
+                                  two_per_sm(cgr_ceil_div(N, TM) * cgr_ceil_div(2 * H, bn)), st);
+    }
     if (rc) return rc;
   }
   const bool relu = p->act == CGR_ACT_RELU;
@@ -1096,7 +1140,8 @@ int tc_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* gs, int n, fl
     group0 += (int)cgr_ceil_div(g->n_tiles, fc.tpc);
   }
   {
-    const int bn = BN_LARGE;
+    const int pbn = proj_bn(BN_LARGE, 2 * H);
+    const int bn = pbn ? pbn : BN_LARGE;
     if ((rc = make_map(&ap.tmB_hi, (const __half*)(wbuf + wl.off_hi[0]), 2 * H, fa, wl.ld[0], bn))) return rc;
     if ((rc = make_map(&ap.tmB_lo, (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa, wl.ld[0], bn))) return rc;
     ap.tmA_hi = ap.gb[0].tmA_hi; ap.tmA_lo = ap.gb[0].tmA_lo;
@@ -1108,9 +1153,13 @@ int tc_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* gs, int n, fl
     ap.ldc = 2 * H;
     ap.fast = fast;
     ap.n_batches = n;
-    if ((rc = ap_multicast(&ap, (const __half*)(wbuf + wl.off_hi[0]), (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa,
-                           wl.ld[0], bn))) return rc;
-    rc = launch_gemm<EPI_PLAIN>(ap, bn, tile0, true, "tc_atom_proj", false, false, st);
+    if (pbn) {
+      rc = launch_proj(ap, pbn, tile0, st);
+    } else {
+      if ((rc = ap_multicast(&ap, (const __half*)(wbuf + wl.off_hi[0]), (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa,
+                             wl.ld[0], bn))) return rc;
+      rc = launch_gemm<EPI_PLAIN>(ap, bn, tile0, true, "tc_atom_proj", false, false, st);
+    }
     if (rc) return rc;
   }
   // 3. edge initialisation: inside the fused kernel, or (bond features too wide for its staging ring) per batch

@@ -489,6 +489,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       // The ring memory is free until the first accumulator is staged: it holds W_e^T's slice and the tiles' bond
       // features meanwhile.  8 lanes per row; a lane requests all its column groups of the row before it computes.
       const int fb = p.fb;
+      // source atoms of this thread's rows (-1: dead row), requested first: the latency hides behind the staging below
+      int srow[MAX_TPC * SLOTS];
+#pragma unroll
+      for (int q = 0; q < MAX_TPC * SLOTS; ++q) {
+        const int jj = q / SLOTS, r = r0 + (q % SLOTS) * RPP;
+        srow[q] = (jj < nt && r < aux->t[jj].info[1]) ? __ldg(B.src + aux->t[jj].info[0] + r) : -1;
+      }
       float* wet_s = y_s;                                           // [fb][BN]
       float* ea_s = y_s + fb * BN;                                  // [nt * TM][fb]
       for (int t = et; t < fb * (BN / 4); t += GAT_THREADS) {
@@ -524,58 +531,71 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         }
       }
       umma::named_bar_sync(3, GAT_THREADS);
+      stamp(MAX_TPC * MAX_LAYERS - 1, 2);
       float imax = 0.f;
       constexpr int NI = (BN / 4 + UPR - 1) / UPR;                  // column groups of the slice per lane
-      for (int jj = 0; jj < nt; ++jj) {
-        const TileAux& ta = aux->t[jj];
-        const int ebase = ta.info[0], ecount = ta.info[1];
-#pragma unroll 1
+      // One step = (tile, column group i of this lane) for the thread's SLOTS rows.  The P' operands of step q + 1 are
+      // requested before step q is computed, so the L2 latency of the gathered rows never shows (it used to be paid
+      // once per row: 45 k cycles for two tiles).
+      auto fetch = [&](int q, float4 (&dst)[SLOTS]) {
+        const int jj = q / NI, i = q - jj * NI;
+        const int c = 4 * (cg + UPR * i);
+        const bool on = c < BN && n0 + c < H;
+#pragma unroll
         for (int u = 0; u < SLOTS; ++u) {
-          const int r = r0 + u * RPP;
-          if (r < ecount) {
-            // the row's P' slice: every column group requested up front, then W_e^T's rows stream from shared memory
-            const float* pr = B.PQ + (size_t)__ldg(B.src + ebase + r) * (2 * H) + n0;
-            float4 a[NI];
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-              const int c = 4 * (cg + UPR * i);
-              a[i] = (c < BN && n0 + c < H) ? __ldcg(reinterpret_cast<const float4*>(pr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const float* e = ea_s + (jj * TM + r) * fb;
-            const float* wr = wet_s + 4 * cg;
+          const int sa = jj ? srow[SLOTS + u] : srow[u];
+          dst[u] = (on && sa >= 0) ? __ldcg(reinterpret_cast<const float4*>(B.PQ + (size_t)sa * (2 * H) + n0 + c))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 cur[SLOTS], nxt[SLOTS];
+      const int nq = nt * NI;
+      fetch(0, cur);
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q) {
+        if (q + 1 < nq) fetch(q + 1, nxt);
+        const int jj = q / NI, i = q - jj * NI;
+        const int c = 4 * (cg + UPR * i);
+        if (c < BN && n0 + c < H) {
+          const float* wr = wet_s + c;
+          const float* e0 = ea_s + (jj * TM + r0) * fb;
 #pragma unroll 2
-            for (int k = 0; k < fb; ++k) {
-              const float x = e[k];
+          for (int k = 0; k < fb; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + k * BN);
 #pragma unroll
-              for (int i = 0; i < NI; ++i) {                        // (column groups past the slice read ring memory: unused)
-                const float4 w = *reinterpret_cast<const float4*>(wr + k * BN + 4 * UPR * i);
-                a[i].x = fmaf(x, w.x, a[i].x); a[i].y = fmaf(x, w.y, a[i].y);
-                a[i].z = fmaf(x, w.z, a[i].z); a[i].w = fmaf(x, w.w, a[i].w);
-              }
+            for (int u = 0; u < SLOTS; ++u) {
+              const float x = e0[u * RPP * fb + k];                  // dead rows hold zeros
+              cur[u].x = fmaf(x, w.x, cur[u].x); cur[u].y = fmaf(x, w.y, cur[u].y);
+              cur[u].z = fmaf(x, w.z, cur[u].z); cur[u].w = fmaf(x, w.w, cur[u].w);
             }
-            const size_t row = (size_t)(tile0 + jj) * TM + r;
+          }
 #pragma unroll
-            for (int i = 0; i < NI; ++i) {
-              const int c = 4 * (cg + UPR * i);
-              if (c < BN && n0 + c < H) {
-                float4 v = a[i];
-                v.x = tcg::act_t<RELU>(v.x, p.act); v.y = tcg::act_t<RELU>(v.y, p.act);
-                v.z = tcg::act_t<RELU>(v.z, p.act); v.w = tcg::act_t<RELU>(v.w, p.act);
-                imax = fmaxf(imax, tcg::amax4(v));
-                *reinterpret_cast<float4*>(B.h0 + row * H + n0 + c) = v;
-                char* od = reinterpret_cast<char*>(B.o_hi[0]) + (row * (size_t)p.ldo + n0 + c) * 2;
-                tcg::store_split4(v, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + B.lo_delta));
-              }
+          for (int u = 0; u < SLOTS; ++u) {
+            if ((jj ? srow[SLOTS + u] : srow[u]) >= 0) {
+              float4 v = cur[u];
+              v.x = tcg::act_t<RELU>(v.x, p.act); v.y = tcg::act_t<RELU>(v.y, p.act);
+              v.z = tcg::act_t<RELU>(v.z, p.act); v.w = tcg::act_t<RELU>(v.w, p.act);
+              imax = fmaxf(imax, tcg::amax4(v));
+              const size_t row = (size_t)(tile0 + jj) * TM + r0 + u * RPP;
+              *reinterpret_cast<float4*>(B.h0 + row * H + n0 + c) = v;
+              char* od = reinterpret_cast<char*>(B.o_hi[0]) + (row * (size_t)p.ldo + n0 + c) * 2;
+              tcg::store_split4(v, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + B.lo_delta));
             }
           }
         }
-        // publish this tile's slice of the layer-0 operand (same protocol as a layer's output, below)
-        umma::fence_proxy_async();
-        __syncwarp();
-        if (lane < S) {
-          __threadfence();
-          umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[jj]), (uint32_t)lane);
+        if (i == NI - 1) {
+          stamp(MAX_TPC * MAX_LAYERS - 1, 3 + 2 * jj);
+          // publish this tile's slice of the layer-0 operand (same protocol as a layer's output, below)
+          umma::fence_proxy_async();
+          __syncwarp();
+          if (lane < S) {
+            __threadfence();
+            umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[jj]), (uint32_t)lane);
+          }
+          stamp(MAX_TPC * MAX_LAYERS - 1, 4 + 2 * jj);
         }
+#pragma unroll
+        for (int u = 0; u < SLOTS; ++u) cur[u] = nxt[u];
       }
       if (imax > 60000.f) atomicOr(B.overflow, 1);                  // fp16 range of the split (as edge_init flags it)
       // the ring goes back to its own use: its zero rows again, and this CTA's h0 columns are visible to every

@@ -1,0 +1,231 @@
+// Persistent atom projection of the tcgen05 engine:  [P' | Q'] = x [W_x ; W_ox]^T + [b_i | b_o]
+// (reference cgr_mpnn_3D/models/GNN.py:86 and :106-107, the parts that multiply atom features).
+//
+// One CTA per SM walks the work units (row tile, BN-column slice) of the launch in a fixed round-robin order --
+// the slices of one row tile run at the same time on neighbouring CTAs, so the activation tile is fetched from HBM
+// once and shared in L2.  The accumulator is double-buffered in TMEM (2 x 256 columns): dedicated epilogue warps
+// drain unit i (TMEM -> registers -> one 128-byte output line per thread and 32-column chunk) while the MMA warp
+// is already in unit i + 1, and barrier set-up, TMEM allocation and descriptor prefetch are paid once per SM instead
+// of once per unit.  The one-unit-per-CTA kernel (tc_gemm_kernel<208, EPI_PLAIN>) spent about half of every CTA's
+// life outside its MMAs (ncu: tensor pipe 43 % active, 656 CTAs = 4.4 waves).
+//
+// Same arithmetic as tc_gemm_kernel (FP16x3: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi per 16-wide k-step, fp32 accumulation
+// in the same order), so the results are bit-identical to it.
+//
+// Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2 = TMEM allocation, 4..7 = epilogue (one per TMEM lane quarter).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace tcp {
+
+using tcg::A_BYTES;
+using tcg::BK;
+using tcg::TM;
+using tcg::TcGemmParams;
+using tcg::GemmBatch;
+
+constexpr int THREADS = 256;
+constexpr int SLOT_COLS = 256;                                  // TMEM columns per accumulator slot
+constexpr int CH = 32;                                          // columns the epilogue reads per tcgen05.wait::ld
+constexpr int AUX_BYTES = 256;
+constexpr int MAX_STAGES = 4;
+
+// The operand ring is what bounds this kernel: a k-chunk lands a TMA round trip (~1.5 k cycles) after its stage was
+// freed, so with two 85 KB stages (BN = 208) the MMAs of a chunk (1.5 k cycles) wait for the next one and the SM pulls
+// only ~44 B/clk.  BN = 160 makes a stage 72 KB: three fit, two are in flight while one is consumed.
+template <int BN_>
+struct PCfg {
+  static constexpr int BN = BN_;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // A (hi, lo) + B (hi, lo) of one 64-wide k-chunk
+  static constexpr int FIT = (232448 - 1024 - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > MAX_STAGES ? MAX_STAGES : FIT;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + AUX_BYTES;
+  static_assert(BN % 16 == 0 && BN <= SLOT_COLS && STAGES >= 2, "bad slice width");
+};
+
+struct Aux {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Aux) <= AUX_BYTES, "Aux too large");
+
+// which batch of a group launch a global row tile belongs to (p.n_batches == 0: the launch's own operand)
+struct UnitRef {
+  const CUtensorMap* mapA_hi;
+  const CUtensorMap* mapA_lo;
+  float* out;
+  int* overflow;
+  int m_rows;
+  int tile;        // row tile inside its batch
+  bool first;      // first row tile of the batch
+};
+__device__ __forceinline__ UnitRef unit_ref(const TcGemmParams& p, int tile_g) {
+  UnitRef u;
+  if (p.n_batches > 0) {
+    int bi = 0;
+    while (bi + 1 < p.n_batches && tile_g >= p.gb[bi + 1].tile0) ++bi;
+    const GemmBatch& g = p.gb[bi];
+    u.mapA_hi = &g.tmA_hi; u.mapA_lo = &g.tmA_lo; u.out = g.out_f32; u.overflow = g.overflow; u.m_rows = g.m_rows;
+    u.tile = tile_g - g.tile0; u.first = tile_g == g.tile0;
+  } else {
+    u.mapA_hi = &p.tmA_hi; u.mapA_lo = &p.tmA_lo; u.out = p.out_f32; u.overflow = p.overflow; u.m_rows = p.m_rows;
+    u.tile = tile_g; u.first = tile_g == 0;
+  }
+  return u;
+}
+
+template <int BN_>
+__global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_constant__ TcGemmParams p, int n_units,
+                                                             int n_slices) {
+  using C = PCfg<BN_>;
+  constexpr int BN = C::BN, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = umma::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      umma::mbar_init(umma::smem_u32(&aux->full[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(umma::smem_u32(&aux->tmem_full[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->tmem_empty[s]), 4);
+    }
+    umma::mbar_fence_init();
+    umma::tma_prefetch_desc(&p.tmB_hi);
+    umma::tma_prefetch_desc(&p.tmB_lo);
+  }
+  if (warp == 2) {
+    umma::tmem_alloc(umma::smem_u32(&aux->tmem_base), 512);
+    umma::tmem_relinquish();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = aux->tmem_base;
+  // programmatic dependent launch: the next kernel may start its own prologue as soon as SMs free up
+  if (threadIdx.x == 0) umma::grid_dep_launch();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      umma::grid_dep_wait();                     // x (hi, lo) may be the output of the previous kernel
+      uint32_t g = 0;                            // k-chunks issued so far (ring position)
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int tile_g = u / n_slices, n0 = (u - tile_g * n_slices) * BN;
+        const UnitRef r = unit_ref(p, tile_g);
+        for (int kc = 0; kc < p.num_k; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          umma::mbar_wait(umma::smem_u32(&aux->empty[s]), ph ^ 1u);
+          const uint32_t full = umma::smem_u32(&aux->full[s]);
+          const uint32_t st = base + s * STAGE_BYTES;
+          umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
+          umma::tma_load_2d(r.mapA_hi, full, st, kc * BK, r.tile * TM);
+          if (!p.fast) umma::tma_load_2d(r.mapA_lo, full, st + A_BYTES, kc * BK, r.tile * TM);
+          umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
+          if (!p.fast) umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        const int n0 = (u % n_slices) * BN;
+        int n_eff = p.n_total - n0;                                // columns this slice owns, rounded to the MMA granularity
+        n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
+        const uint32_t idesc = umma::idesc_f16_f32(TM, n_eff);
+        const uint32_t slot = it & 1u;
+        umma::mbar_wait(umma::smem_u32(&aux->tmem_empty[slot]), ((it >> 1) & 1u) ^ 1u);
+        umma::tc_fence_after_sync();
+        const uint32_t acc = tmem + slot * SLOT_COLS;
+        for (int kc = 0; kc < p.num_k; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
+          umma::tc_fence_after_sync();
+          const uint32_t st = base + s * STAGE_BYTES;
+          const uint64_t da_hi = umma::smem_desc_k_sw128(st);
+          const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
+          const uint64_t db_hi = umma::smem_desc_k_sw128(st + 2 * A_BYTES);
+          const uint64_t db_lo = umma::smem_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+          const int k_left = p.k_total - kc * BK;                  // K tail: skip k-steps that are all zero padding
+          const int ksteps = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            if (ks >= ksteps) break;
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);         // 16 fp16 = 32 bytes along K inside the swizzle row
+            if (p.fast) {
+              umma::mma_f16_ss(acc, da_hi + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+            } else {
+              umma::mma_f16_ss(acc, da_lo + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+              umma::mma_f16_ss(acc, da_hi + adv, db_lo + adv, idesc, 1u);
+              umma::mma_f16_ss(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+          }
+          umma::mma_commit(umma::smem_u32(&aux->empty[s]));        // frees the stage when these MMAs retire
+          if (kc == p.num_k - 1) umma::mma_commit(umma::smem_u32(&aux->tmem_full[slot]));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                                        // TMEM lane quarter = the 32 rows this warp owns
+    const float us = __ldg(p.unscale);
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      const int tile_g = u / n_slices, n0 = (u - tile_g * n_slices) * BN;
+      const UnitRef r = unit_ref(p, tile_g);
+      // the atom projection opens a forward: clear the per-forward overflow bit (bit 1, feature overflow, belongs to
+      // the batch and stays)
+      if (r.first && n0 == 0 && r.overflow && threadIdx.x == 128) atomicAnd(r.overflow, ~1);
+      const uint32_t slot = it & 1u;
+      umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), (it >> 1) & 1u);
+      umma::tc_fence_after_sync();
+      const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
+      const int row = r.tile * TM + q * 32 + lane;                 // this thread's row inside the batch
+      const int n_cols = p.n_total - n0 < BN ? p.n_total - n0 : BN;
+      float* orow = r.out + (int64_t)row * p.ldc + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_cols; c0 += CH) {
+        float v[CH / 8][8];
+#pragma unroll
+        for (int g = 0; g < CH / 8; ++g)                             // all loads of the chunk in flight, one wait
+          if (c0 + g * 8 < n_cols) umma::tmem_ld_x8(acc + (uint32_t)(c0 + g * 8), v[g]);
+        umma::tmem_ld_wait();
+        // a thread owns a row: 8 x 16 bytes = one full 128-byte line of the output per chunk
+        if (row < r.m_rows) {
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) {
+            if (c0 + g * 8 < n_cols) {
+              const int c = c0 + g * 8;
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (p.bias) { b0 = tcg::ld4(p.bias + n0 + c); b1 = tcg::ld4(p.bias + n0 + c + 4); }
+              float4* dst = reinterpret_cast<float4*>(orow + c);
+              dst[0] = make_float4(v[g][0] * us + b0.x, v[g][1] * us + b0.y, v[g][2] * us + b0.z, v[g][3] * us + b0.w);
+              dst[1] = make_float4(v[g][4] * us + b1.x, v[g][5] * us + b1.y, v[g][6] * us + b1.z, v[g][7] * us + b1.w);
+            }
+          }
+        }
+      }
+      umma::tc_fence_before_sync();                                // accumulator drained: the MMA warp may reuse it
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(umma::smem_u32(&aux->tmem_empty[slot]));
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tcp

@@ -46,3 +46,6 @@ print("per item means: mma (5-7) %.0f   fill wait (7-4) %.0f   gather (1-0) %.0f
     sum(col(i, 5) - col(i, 7) for i in range(n_items)) / n_items, sum(col(i, 7) - col(i, 4) for i in range(n_items)) / n_items,
     sum(col(i, 1) - col(i, 0) for i in range(n_items)) / n_items, sum(col(i, 2) - col(i, 1) for i in range(n_items)) / n_items,
     (col(n_items - 1, 2) - col(0, 0)) / max(n_items - 1, 1)))
+e = dbg.view(-1, 32, 8).cpu()[:t.shape[0], 31].double()
+print("edge-init detail (cycles after its start): staged %.0f | tile0 computed %.0f published %.0f | tile1 computed %.0f published %.0f | end %.0f" % tuple(
+    float((e[:, k] - e[:, 0]).mean()) for k in (2, 3, 4, 5, 6, 1)))
