@@ -828,6 +828,28 @@ int fwd_fill_batch(tcf::FwdBatch* bt, const cgr_graph_t* g, char* ws, const TcWs
   bt->n_rxn = g->n_rxn;
   bt->n_tiles = (int)g->n_tiles;
   bt->group0 = 0;
+  bt->train_rows = 0;
+  bt->hv_out = nullptr;
+  return CGR_OK;
+}
+// training forward: the layers' operand pairs live in the saved blob, back to back (TcSavedLayout), and stay there
+int fwd_fill_training(tcf::FwdBatch* bt, const cgr_params_t* p, char* blob, const TcSavedLayout& SL, int H) {
+  const int64_t lo_delta = (int64_t)(SL.off_hlo[0] - SL.off_hhi[0]);
+  for (int l = 0; l <= p->depth; ++l)
+    CGR_CHECK_ARG((int64_t)SL.off_hhi[l] == (int64_t)SL.off_hhi[0] + 2 * l * lo_delta &&
+                      (int64_t)SL.off_hlo[l] == (int64_t)SL.off_hhi[l] + lo_delta &&
+                      lo_delta == SL.rows_pad * SL.kp_h * (int64_t)sizeof(__half),
+                  "tc training forward: saved operand pairs are not contiguous");
+  int rc;
+  __half* base = (__half*)(blob + SL.off_hhi[0]);
+  const int64_t rows = 2 * (int64_t)(p->depth + 1) * SL.rows_pad;
+  CGR_CHECK_ARG(rows < (int64_t)1 << 31, "tc training forward: batch too large for one operand map");
+  if ((rc = make_map(&bt->tmA_hi[0], base, rows, H, SL.kp_h, TM))) return rc;
+  bt->o_hi[0] = base;
+  bt->lo_delta = lo_delta;
+  bt->h0 = (float*)(blob + SL.off_h0);
+  bt->hv_out = (float*)(blob + SL.off_hv);
+  bt->train_rows = SL.rows_pad;
   return CGR_OK;
 }
 int launch_fwd(const tcf::FwdParams& prm, const FwdChoice& fc, bool relu, int n_groups, bool pdl, cudaStream_t st) {
@@ -945,7 +967,10 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
   static const bool use_fused = getenv("CGR_NO_FUSED_FWD") == nullptr;
   static const bool use_fused_init = getenv("CGR_NO_FUSED_INIT") == nullptr;
   FwdChoice fc;
-  const bool fused = use_fused && !blob && !(training && p->host_dropout_p) && choose_fwd(T, H, p->tc_throughput != 0, &fc);
+  bool any_dropout = false;                // dropout masks stay with the per-layer kernels (Philox stream per layer)
+  for (int l = 0; training && p->host_dropout_p && l < d; ++l) any_dropout |= p->host_dropout_p[l] > 0.f;
+  static const bool fused_train = getenv("CGR_NO_FUSED_TRAIN_FWD") == nullptr;
+  const bool fused = use_fused && (!blob || fused_train) && !any_dropout && choose_fwd(T, H, p->tc_throughput != 0, &fc);
   // the fused kernel also computes h0 (edge initialisation) when W_e^T's slice and the tiles' bond features fit its
   // staging ring
   const bool fused_init = fused && use_fused_init && fb > 0 &&
@@ -979,6 +1004,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     memset(&prm, 0, sizeof(prm));
     if ((rc = fwd_fill_shared(&prm, p, wbuf, wl, fc, w.kp_h, fused_init, fast))) return rc;
     if ((rc = fwd_fill_batch(&prm.bt[0], g, ws, w, H, out))) return rc;
+    if (blob && (rc = fwd_fill_training(&prm.bt[0], p, blob, SL, H))) return rc;
     prm.n_batches = 1;
     const int n_groups = (int)cgr_ceil_div(T, fc.tpc);
     return launch_fwd(prm, fc, relu, n_groups, use_pdl, st);
@@ -1430,6 +1456,32 @@ size_t tc_backward_workspace(const cgr_params_t* p, const cgr_graph_t* g) {
   return tc_bwd_ws(p, g).total;
 }
 
+namespace {
+// The weight-gradient GEMMs only consume what the backward chain produces: they run on a side stream, each as soon
+// as its operand exists, next to the (latency-bound, ~100-CTA) chain kernels instead of after them.  Fork and join
+// are event dependencies, so a stream capture records them as parallel branches of the step's graph.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[MAX_SEG + 4] = {};
+};
+SideStream* bwd_side_stream() {
+  // measured (cfg-3, B = 64, one CUDA graph per step): 0.342 ms forked against 0.315-0.329 ms in line -- the step is a
+  // chain of latency-bound kernels, the GEMMs compete with it for SMs and add split-K reductions; off unless asked for
+  static const bool on = getenv("CGR_BWD_FORK") != nullptr;
+  if (!on) return nullptr;
+  thread_local SideStream per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& S = per_dev[dev];
+  if (!S.s) {
+    if (cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) != cudaSuccess) { S.s = nullptr; return nullptr; }
+    for (auto& e : S.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &S;
+}
+}  // namespace
+
 int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved_t* saved, const float* dout,
                     const cgr_grads_t* grads, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CGR_CHECK_ARG(tc_fused_training_ok(p, g) && saved && saved->tc_blob, "tcgen05 fused backward: unsupported configuration");
@@ -1493,6 +1545,39 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
         gamax, gunscale);
     CGR_LAUNCH_CHECK();
   }
+  // weight gradients: reductions over bonds / atoms (K = rows) on tensor cores, deterministic split-K.  With the side
+  // stream every GEMM is issued as soon as its gradient operand exists; without it they follow the chain on `st`.
+  SideStream* side = bwd_side_stream();
+  cudaStream_t ws_st = side ? side->s : st;
+  int n_ev = 0;
+  auto fork = [&]() -> int {                        // the side stream's next launches wait for everything issued on st so far
+    if (!side) return CGR_OK;
+    CGR_CUDA(cudaEventRecord(side->ev[n_ev], st));
+    CGR_CUDA(cudaStreamWaitEvent(side->s, side->ev[n_ev], 0));
+    ++n_ev;
+    return CGR_OK;
+  };
+  auto wgrad = [&](const TcOperand& A_, const TcOperand& B_, float* C_, int64_t ldc_, int64_t M_, int64_t N_, int64_t K_,
+                   const char* tag) {
+    // forked: few CTAs per GEMM (it shares the machine with the chain kernel that runs next to it and must not take
+    // the SMs that kernel needs); otherwise the machine-filling split
+    int sk = tc_splitk_batched(1, M_, N_, K_);
+    if (side) {
+      static const int fork_ctas = getenv("CGR_BWD_FORK_CTAS") ? atoi(getenv("CGR_BWD_FORK_CTAS")) : 48;
+      const int64_t base = cgr_ceil_div(M_, tcg2::TM) * cgr_ceil_div(N_, tcg2::TN);
+      const int cap = (int)(fork_ctas / base > 1 ? fork_ctas / base : 1);
+      if (sk > cap) sk = cap;
+    }
+    return tc_train_gemm_batched_mn(&A_, &B_, &C_, &ldc_, 1, M_, N_, K_, sk, partial, tag, ws_st);
+  };
+  if (side) {
+    // dq and dzv exist: dW_os = dq^T h_d, dW_ox = dzv^T x
+    if ((rc = fork())) return rc;
+    if ((rc = wgrad(TcOperand{g_hi(0), g_lo(0), w.kp_h, gunscale + 0, true}, TcOperand{h_hi(d), h_lo(d), w.kp_h, nullptr, true},
+                    grads->w_e2n + fa, fa + H, H, H, w.rows_pad, "wgrad_bond"))) return rc;
+    if ((rc = wgrad(TcOperand{dzv_hi, dzv_lo, w.kp_h, gunscale + 0, true}, TcOperand{x_hi, x_lo, w.kp_x, nullptr, true},
+                    grads->w_e2n, fa + H, H, fa, N, "wgrad_atoms"))) return rc;
+  }
   const int bn_h = choose_bn(T, H);
   // bond layers, last to first: kernel i turns G_i (dq or dy_{l+1}) into dy_l = G_{i+1}, l = d - i
   for (int i = 0; i < d; ++i) {
@@ -1526,6 +1611,13 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     rc = launch_gemm<EPI_BOND_BWD>(prm, bn_h, (int)T, true, "bwd_bond_layer", use_pdl && i > 0,
                                    two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
+    if (side) {
+      // dy_l exists: dW_l = dy_l^T h_{l-1}
+      if ((rc = fork())) return rc;
+      if ((rc = wgrad(TcOperand{g_hi(i + 1), g_lo(i + 1), w.kp_h, gunscale + i + 1, true},
+                      TcOperand{h_hi(l - 1), h_lo(l - 1), w.kp_h, nullptr, true}, grads->w_conv[l - 1], H, H, H, w.rows_pad,
+                      "wgrad_bond"))) return rc;
+    }
   }
   // edge initialisation: dh_0 = dy_1 W_1 + dh0_acc, dz_0 = dh_0 . [h_0 > 0], dP[v] = sum of dz_0 over bonds leaving v
   {
@@ -1554,9 +1646,13 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     rc = launch_gemm<EPI_INIT_BWD>(prm, bn_h, (int)T, true, "bwd_edge_init", use_pdl, two_per_sm(T * cgr_ceil_div(H, bn_h)), st);
     if (rc) return rc;
   }
-  // weight gradients: reductions over bonds / atoms (K = rows) on tensor cores, deterministic split-K; all GEMMs of
-  // one shape share a launch
-  {
+  if (side) {
+    // dP and dz_0 exist: dW_x = dP^T x here, dW_e below (ws_st)
+    if ((rc = fork())) return rc;
+    if ((rc = wgrad(TcOperand{dp_hi, dp_lo, w.kp_h, gunscale + d + 1, true}, TcOperand{x_hi, x_lo, w.kp_x, nullptr, true},
+                    grads->w_init, fa + fb, H, fa, N, "wgrad_atoms"))) return rc;
+  } else {
+    // without the side stream all GEMMs of one shape share a launch
     TcOperand A[tcg2::MAX_BATCH], Bo[tcg2::MAX_BATCH];
     float* C[tcg2::MAX_BATCH];
     int64_t ldc[tcg2::MAX_BATCH];
@@ -1592,7 +1688,7 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     GemmEpilogue e;
     e.tag = "wgrad_edge_attr";
     rc = simt_gemm(dz0, H, false, g->edge_attr, fb, false, grads->w_init + fa, fa + fb, H, fb, E, e,
-                   simt_splitk_choose(H, fb, E), partial, st);
+                   simt_splitk_choose(H, fb, E), partial, ws_st);
     if (rc) return rc;
   }
   {
@@ -1617,6 +1713,10 @@ int tc_gnn_backward(const cgr_params_t* p, const cgr_graph_t* g, const cgr_saved
     cgr_note_launch("bwd_finalize", st, 1);
     bwd_finalize_kernel<<<dim3((unsigned)cgr_ceil_div(H, 32), (unsigned)(a.n_col + a.n_skip)), 256, 0, st>>>(a);
     CGR_LAUNCH_CHECK();
+  }
+  if (side) {                                       // join: everything the side stream wrote is ordered before what follows on st
+    CGR_CUDA(cudaEventRecord(side->ev[n_ev], side->s));
+    CGR_CUDA(cudaStreamWaitEvent(st, side->ev[n_ev], 0));
   }
   return CGR_OK;
 }

@@ -95,6 +95,12 @@ struct FwdBatch {
   int64_t n_rxn;
   int n_tiles;
   int group0;                                  // first tile group (cluster) of this batch in the launch
+  // training forward (one operand pair per layer is kept for the backward): train_rows = T * 128 > 0; the pairs lie
+  // back to back (hi_0 | lo_0 | hi_1 | ...), tmA_hi[0] spans all of them -- layer l reads rows 2 l train_rows (hi)
+  // and (2 l + 1) train_rows (lo) of it and writes o_hi[0] + (l + 1) * 2 * lo_delta; hv_out [N, H] fp32 keeps the
+  // readout's activation (mask of its backward)
+  int64_t train_rows;
+  float* hv_out;
 };
 
 struct FwdParams {
@@ -314,8 +320,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
             umma::fence_proxy_async();
             if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 3] = clock64();
           }
-          umma::tma_load_2d(&B.tmA_hi[buf], full, st, kc * BK, tile * TM);
-          if (!p.fast) umma::tma_load_2d(&B.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
+          if (B.train_rows) {
+            const int row = tile * TM + (int)(2 * l * B.train_rows);
+            umma::tma_load_2d(&B.tmA_hi[0], full, st, kc * BK, row);
+            if (!p.fast) umma::tma_load_2d(&B.tmA_hi[0], full, st + A_BYTES, kc * BK, row + (int)B.train_rows);
+          } else {
+            umma::tma_load_2d(&B.tmA_hi[buf], full, st, kc * BK, tile * TM);
+            if (!p.fast) umma::tma_load_2d(&B.tmA_lo[buf], full, st + A_BYTES, kc * BK, tile * TM);
+          }
         }
       }
     }
@@ -625,7 +637,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const uint4* nbd = readout ? ta.nbd_a : ta.nbd_b;
       const uint2* nb2 = readout ? ta.nb2_a : ta.nb2_b;
       // this thread's unit (row r0, column group cg) of the output operand; the lo rows sit B.lo_delta bytes further
-      char* oh_item = reinterpret_cast<char*>(B.o_hi[(l + 1) & 1]) +
+      char* oh_item = (B.train_rows ? reinterpret_cast<char*>(B.o_hi[0]) + (int64_t)(l + 1) * 2 * B.lo_delta
+                                    : reinterpret_cast<char*>(B.o_hi[(l + 1) & 1])) +
                       (((size_t)tile * TM + r0) * (size_t)p.ldo + n0 + 4 * cg) * 2;
       asm volatile("" : "+l"(oh_item));                            // opaque: kept in registers, not recomputed per unit
       // this thread's rows: which exist, which have more than FASTN / 2 FASTN neighbours
@@ -676,11 +689,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
               }
             } else {
               // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this thread's columns
-              float t = tcg::act_t<RELU>(a4.x + opnd[k].x, p.act) * c4.x;
-              t = fmaf(tcg::act_t<RELU>(a4.y + opnd[k].y, p.act), c4.y, t);
-              t = fmaf(tcg::act_t<RELU>(a4.z + opnd[k].z, p.act), c4.z, t);
-              t = fmaf(tcg::act_t<RELU>(a4.w + opnd[k].w, p.act), c4.w, t);
+              float4 hv;
+              hv.x = tcg::act_t<RELU>(a4.x + opnd[k].x, p.act); hv.y = tcg::act_t<RELU>(a4.y + opnd[k].y, p.act);
+              hv.z = tcg::act_t<RELU>(a4.z + opnd[k].z, p.act); hv.w = tcg::act_t<RELU>(a4.w + opnd[k].w, p.act);
+              float t = hv.x * c4.x;
+              t = fmaf(hv.y, c4.y, t);
+              t = fmaf(hv.z, c4.z, t);
+              t = fmaf(hv.w, c4.w, t);
               tsum[k] += t;
+              if (B.hv_out && (valid & (1u << k)))                   // training: the readout backward's mask
+                *reinterpret_cast<float4*>(B.hv_out + (size_t)(abase + r) * H + n) = hv;
             }
           }
         }
