@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
+if os.environ.get("CGR_FWD_STAMPS"):      # debug build: clock64 phase stamps in the fused forward kernel (tools/fwd_phase_timing.py)
+    NVCC_FLAGS.append("-DCGR_FWD_STAMPS")
 
 
 def _nvcc() -> str:

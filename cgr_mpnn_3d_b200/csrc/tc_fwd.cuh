@@ -41,6 +41,14 @@ constexpr int SLOT_COLS = 256;                 // TMEM columns per accumulator s
 constexpr int MAX_TPC = 2;                     // tiles per cluster (ping-pong)
 constexpr int SMEM_LIMIT = 232448;
 constexpr int FASTN = 4;                       // neighbours a packed descriptor holds (rows with more walk the CSR list)
+// Debug clock64 stamps (tools/fwd_phase_timing.py) are compiled in only with -DCGR_FWD_STAMPS (CGR_FWD_STAMPS=1 at build
+// time): the shipped kernel carries no debug stores in its item loop.
+#ifdef CGR_FWD_STAMPS
+#define FWD_STAMP(cond, slot, w) \
+  do { if (p.dbg && (cond)) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + (slot) * 8 + (w)] = clock64(); } while (0)
+#else
+#define FWD_STAMP(cond, slot, w) do { } while (0)
+#endif
 #ifndef CGR_REG_LOW
 #define CGR_REG_LOW 32
 #define CGR_REG_HIGH 112
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
             // the S slices of this tile's previous layer have been stored (every CTA of the cluster arrived)
             umma::mbar_wait_cluster(umma::smem_u32(&aux->ready[j]), (uint32_t)(l - 1 + p.fuse_init) & 1u);
             umma::fence_proxy_async();
-            if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 3] = clock64();
+            FWD_STAMP(true, i, 3);
           }
           if (B.train_rows) {
             const int row = tile * TM + (int)(2 * l * B.train_rows);
@@ -342,13 +350,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         const uint32_t slot = (uint32_t)i & 1u;
         umma::mbar_wait(umma::smem_u32(&aux->tmem_empty[slot]), (((uint32_t)i >> 1) & 1u) ^ 1u);
         umma::tc_fence_after_sync();
-        if (p.dbg) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 4] = clock64();
+        FWD_STAMP(true, i, 4);
         const uint32_t acc = tmem + slot * SLOT_COLS;
         for (int kc = 0; kc < p.num_k; ++kc, ++g) {
           const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
           umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
           umma::tc_fence_after_sync();
-          if (p.dbg && kc == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 7] = clock64();
+          FWD_STAMP(kc == 0, i, 7);
           const uint32_t st = base + s * STAGE_BYTES;
           const uint64_t da_hi = umma::smem_desc_k_sw128(st);
           const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
       const float us = aux->us[nt == 2 ? (i >> 1) : i];
       umma::mbar_wait(umma::smem_u32(&aux->tmem_full[slot]), ((uint32_t)i >> 1) & 1u);
       umma::tc_fence_after_sync();
-      if (p.dbg && warp == 4 && lane == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 5] = clock64();
+      FWD_STAMP(warp == 4 && lane == 0, i, 5);
       const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch, ++c) {
@@ -444,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           umma::mbar_arrive(umma::smem_u32(&aux->st_full[buf]));    // release: the warp's rows are in the buffer
         }
       }
-      if (p.dbg && warp == 4 && lane == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + 6] = clock64();
+      FWD_STAMP(warp == 4 && lane == 0, i, 6);
     }
   } else if (warp >= 4 + STG_WARPS) {
     // ------------------------------------------------------------------ gather warps
@@ -457,9 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
     const uint32_t h0_row_step = (uint32_t)(RPP * H) * 4u;         // bytes between this thread's two h0 rows
     const uint32_t pq_row_step = (uint32_t)(RPP * 2 * H) * 4u;     // ... its two Q' rows
     const uint32_t o_row_step = (uint32_t)RPP * (uint32_t)p.ldo * 2u;   // ... its two (hi, lo) output rows
-    auto stamp = [&](int i, int w) {                                // debug: clock64 phase stamps
-      if (p.dbg && et == 0) p.dbg[(int64_t)blockIdx.x * (MAX_TPC * MAX_LAYERS * 8) + i * 8 + w] = clock64();
-    };
+    auto stamp = [&](int i, int w) { FWD_STAMP(et == 0, i, w); (void)i; (void)w; };   // debug: clock64 phase stamps
     // item i of this CTA = (tile j of the group, layer l); nt is 1 or 2
     auto item_tile = [&](int i) { return nt == 2 ? (i & 1) : 0; };
     auto item_layer = [&](int i) { return nt == 2 ? (i >> 1) : i; };

@@ -263,7 +263,11 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
   int n_eff = p.n_total - n0;
   n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
   long long* dbg = p.dbg ? p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+#ifdef CGR_FWD_STAMPS      // debug builds only: a predicated-off stamp still waits on the scoreboards it shares (see tc_fwd.cuh)
 #define TC_STAMP(k) do { if (dbg && threadIdx.x == 64) dbg[k] = clock64(); } while (0)
+#else
+#define TC_STAMP(k) do { (void)dbg; } while (0)
+#endif
   TC_STAMP(0);
   // the atom projection opens a forward: clear the per-forward overflow bit (bit 1, feature overflow, belongs to the batch)
   if (EPI == EPI_PLAIN && overflow && first_cta && threadIdx.x == 0) atomicAnd(overflow, ~1);
@@ -345,8 +349,10 @@ __global__ void __launch_bounds__(NT_, (NT_ <= 384 ? 2 : 1)) tc_gemm_kernel(cons
       if (lane == 0) {
         umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
         umma::tc_fence_after_sync();
+#ifdef CGR_FWD_STAMPS
         if (dbg && kc == 0) dbg[6] = clock64();
         if (dbg && kc == p.num_k - 1) dbg[7] = clock64();
+#endif
         const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
         const uint64_t da_hi = umma::smem_desc_k_sw128(st);
         const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);

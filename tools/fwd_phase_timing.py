@@ -4,6 +4,9 @@ stamp 0: gather warps see the item's first staged chunk; 1: gather of the last c
 readout reduction) done; 3: producer passed the dependency wait of this item (layers >= 1); 4: MMA warp owns the
 accumulator slot; 7: first operand stage of the item landed; 5: staging warps see the accumulator complete;
 6: last chunk staged (accumulator released).
+
+Needs a library built with the stamps compiled in:  CGR_FWD_STAMPS=1 python -m cgr_mpnn_3d_b200.build --force
+(the shipped kernel has none), and a plain rebuild afterwards.
 """
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
