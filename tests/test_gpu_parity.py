@@ -415,6 +415,28 @@ def test_tc_forward_large_batch_against_fp64():
     assert scale_normalised_error(out, ref) < 2e-5
 
 
+def test_persistent_projection_wide_slices_h300():
+    """hidden 300: the output width 2H = 600 pads less with 208-wide slices, so the persistent atom projection runs its
+    two-stage 208 configuration (h400 runs 160-wide slices with three stages); large batch against fp64, and the
+    training forward (fused cluster kernel keeping one operand pair per layer) must return the inference energies."""
+    meta = dict(fa=846, fb=14, depth=3, hidden=300, skip=True, wseed=3, act="relu")
+    data = make_batch(512, seed=23, kind="t1x", fa=846)
+    o64 = build_oracle(meta, dtype=torch.float64).eval()
+    d64 = Batch(data.x.double(), data.edge_index, data.edge_attr.double(), data.batch, data.ptr, data.y)
+    model = build_model(meta, engine="auto").eval()
+    dev = data.to("cuda")
+    with torch.no_grad():
+        ref = o64(d64)
+        out = model(dev)
+    model.check_numerics()
+    assert scale_normalised_error(out, ref) < 2e-5
+    model.train()                                       # dropout 0: same arithmetic, activations kept for the backward
+    out_t = model(dev)
+    assert scale_normalised_error(out_t.detach(), out) < 1e-5
+    out_t.sum().backward()
+    assert all(torch.isfinite(q.grad).all() for q in model.parameters())
+
+
 def test_tc_engine_on_untileable_graphs():
     """Drug-like reactions (~210 bonds) do not fit a 128-bond tile: the tcgen05 engine then runs layer-wise with
     tensor-core GEMMs (no fused epilogue), the CPU-tensor entry falls back to the same path."""
