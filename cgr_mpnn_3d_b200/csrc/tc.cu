@@ -496,11 +496,31 @@ int proj_bn(int bn_default, int n_total) {
   const int64_t pad208 = cgr_ceil_div(n_total, PROJ_BN_WIDE) * PROJ_BN_WIDE - n_total;
   return pad160 <= pad208 ? PROJ_BN_3STAGE : PROJ_BN_WIDE;
 }
+// weight multicast of the persistent projection: clusters of `mc` CTAs (consecutive row tiles, same slice) share every
+// weight chunk.  0 / 1 = off.
+int proj_mc(int bn) {
+  // measured (group of 20 cfg-2 batches): 104.3 us without, 104.7 us with clusters of 2, 116.6 us with clusters of 4 --
+  // L2 already merges the same line requested by a few SMs at about the same time, so multicast at this cluster size
+  // saves no L2 throughput (the kernel runs at ~75-80 % of the ~6.3 KB/clk the L2 delivers to the SMs); off
+  static const int mc_env = getenv("CGR_AP_MC") ? atoi(getenv("CGR_AP_MC")) : 1;
+  const int mc = (mc_env == 2 || mc_env == 4) ? mc_env : 1;
+  return (mc > 1 && bn % (8 * mc) == 0) ? mc : 1;            // shares of whole 8-row swizzle groups only
+}
+int proj_multicast(TcGemmParams* ap, const __half* w_hi, const __half* w_lo, int64_t rows, int64_t cols, int64_t ld, int bn) {
+  const int mc = proj_mc(bn);
+  if (mc == 1) return CGR_OK;
+  int rc;
+  if ((rc = make_map(&ap->tmB_hi_mc, w_hi, rows, cols, ld, bn / mc))) return rc;
+  if ((rc = make_map(&ap->tmB_lo_mc, w_lo, rows, cols, ld, bn / mc))) return rc;
+  ap->mc = mc;
+  return CGR_OK;
+}
 template <int BN>
 int launch_proj_t(const TcGemmParams& prm, int m_tiles, cudaStream_t st) {
   using C = tcp::PCfg<BN>;
+  const int mc = prm.mc > 1 ? prm.mc : 1;
   static bool attr_done = false;      // benign race: the attribute is idempotent
-  static int n_sm = 0;
+  static int n_sm = 0, max_clusters[5] = {0, 0, 0, 0, 0};
   if (!attr_done) {
     CGR_CUDA(cudaFuncSetAttribute(tcp::tc_proj_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     int dev = 0;
@@ -508,12 +528,33 @@ int launch_proj_t(const TcGemmParams& prm, int m_tiles, cudaStream_t st) {
     CGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     attr_done = true;
   }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(tcp::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)mc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mc > 1 ? 1 : 0;
+  if (mc > 1 && max_clusters[mc] == 0) {
+    // a persistent grid must be co-resident: clusters the device can hold at once (GPCs with an odd number of SMs
+    // leave one out)
+    cfg.gridDim = dim3((unsigned)(n_sm / mc * mc));
+    int n = 0;
+    CGR_CUDA(cudaOccupancyMaxActiveClusters(&n, tcp::tc_proj_kernel<BN>, &cfg));
+    max_clusters[mc] = n > 0 ? n : 1;
+  }
   const int n_slices = (int)cgr_ceil_div(prm.n_total, BN);
-  const int n_units = m_tiles * n_slices;
+  const int n_units = (int)cgr_ceil_div(m_tiles, mc) * n_slices;         // cluster units
+  const int slots = mc > 1 ? max_clusters[mc] : n_sm;
   CgrRange prof("tc_atom_proj", st);
   cgr_note_launch("tc_atom_proj", st, 1);
-  tcp::tc_proj_kernel<BN><<<(unsigned)(n_units < n_sm ? n_units : n_sm), tcp::THREADS, C::SMEM_BYTES, st>>>(prm, n_units, n_slices);
-  CGR_LAUNCH_CHECK();
+  cfg.gridDim = dim3((unsigned)((n_units < slots ? n_units : slots) * mc));
+  CGR_CUDA(cudaLaunchKernelEx(&cfg, tcp::tc_proj_kernel<BN>, prm, n_units, n_slices));
   return CGR_OK;
 }
 int launch_proj(const TcGemmParams& prm, int bn, int m_tiles, cudaStream_t st) {
@@ -953,6 +994,7 @@ int tc_gnn_forward(const cgr_params_t* p, const cgr_graph_t* g, float* out, cgr_
     prm.fast = fast;
     prm.overflow = flag;             // first kernel of the forward: clears the per-forward overflow bit
     if (pbn) {
+      if ((rc = proj_multicast(&prm, w_hi(0), w_lo(0), 2 * H, fa, wl.ld[0], pbn))) return rc;
       rc = launch_proj(prm, pbn, (int)cgr_ceil_div(N, TM), st);
     } else {
       if (bn == BN_LARGE && (rc = ap_multicast(&prm, w_hi(0), w_lo(0), 2 * H, fa, wl.ld[0], bn))) return rc;
@@ -1180,6 +1222,8 @@ int tc_gnn_forward_group(const cgr_params_t* p, const cgr_graph_t* gs, int n, fl
     ap.fast = fast;
     ap.n_batches = n;
     if (pbn) {
+      if ((rc = proj_multicast(&ap, (const __half*)(wbuf + wl.off_hi[0]), (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa,
+                               wl.ld[0], pbn))) return rc;
       rc = launch_proj(ap, pbn, tile0, st);
     } else {
       if ((rc = ap_multicast(&ap, (const __half*)(wbuf + wl.off_hi[0]), (const __half*)(wbuf + wl.off_lo[0]), 2 * H, fa,

@@ -30,9 +30,10 @@ constexpr int CH = 32;                                          // columns the e
 constexpr int AUX_BYTES = 256;
 constexpr int MAX_STAGES = 4;
 
-// The operand ring is what bounds this kernel: a k-chunk lands a TMA round trip (~1.5 k cycles) after its stage was
-// freed, so with two 85 KB stages (BN = 208) the MMAs of a chunk (1.5 k cycles) wait for the next one and the SM pulls
-// only ~44 B/clk.  BN = 160 makes a stage 72 KB: three fit, two are in flight while one is consumed.
+// What bounds this kernel is the rate at which L2 feeds the SMs (~6.3 KB/clk chip-wide = ~43 B/clk per SM with all 148
+// pulling): every unit streams 14 k-chunks of 72 KB (BN = 160, three stages) or 85 KB (BN = 208, two stages) for
+// ~1 k cycles of MMAs per chunk; both configurations measure the same (92 us per group of 20 cfg-2 batches, 826 MB
+// of operand traffic = 9 TB/s).  BN = 160 is preferred where it pads the output width less.
 template <int BN_>
 struct PCfg {
   static constexpr int BN = BN_;
@@ -78,6 +79,9 @@ __device__ __forceinline__ UnitRef unit_ref(const TcGemmParams& p, int tile_g) {
   return u;
 }
 
+// p.mc > 1 (optional, CGR_AP_MC; measured no gain, off): clusters of mc CTAs take mc consecutive row tiles through the
+// same column slice; every CTA loads 1 / mc of the weight chunk's rows and multicasts them to the whole cluster
+// (tmB_*_mc: box of BN / mc rows).  n_units then counts cluster units.
 template <int BN_>
 __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_constant__ TcGemmParams p, int n_units,
                                                              int n_slices) {
@@ -89,11 +93,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
   uint8_t* smem = smem_raw + (base - raw);
   Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t mc = p.mc > 1 ? (uint32_t)p.mc : 1u;
+  const uint32_t mc_rank = mc > 1 ? umma::cluster_ctarank() : 0u;
+  const uint16_t mc_mask = (uint16_t)((1u << mc) - 1u);
+  // unit u of this CTA's cluster -> (row tile of this CTA, column slice)
+  const int u0 = (int)(blockIdx.x / mc), u_step = (int)(gridDim.x / mc);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       umma::mbar_init(umma::smem_u32(&aux->full[s]), 1);
-      umma::mbar_init(umma::smem_u32(&aux->empty[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->empty[s]), mc);       // multicast: every CTA of the cluster releases the stage
     }
     for (int s = 0; s < 2; ++s) {
       umma::mbar_init(umma::smem_u32(&aux->tmem_full[s]), 1);
@@ -110,6 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
+  if (mc > 1) umma::cluster_sync_all();           // the peers' barriers exist before anything is multicast to them
   const uint32_t tmem = aux->tmem_base;
   // programmatic dependent launch: the next kernel may start its own prologue as soon as SMs free up
   if (threadIdx.x == 0) umma::grid_dep_launch();
@@ -119,9 +129,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
     if (lane == 0) {
       umma::grid_dep_wait();                     // x (hi, lo) may be the output of the previous kernel
       uint32_t g = 0;                            // k-chunks issued so far (ring position)
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int tile_g = u / n_slices, n0 = (u - tile_g * n_slices) * BN;
-        const UnitRef r = unit_ref(p, tile_g);
+      for (int u = u0; u < n_units; u += u_step) {
+        const int tg = u / n_slices, n0 = (u - tg * n_slices) * BN;
+        const UnitRef r = unit_ref(p, tg * (int)mc + (int)mc_rank);
         for (int kc = 0; kc < p.num_k; ++kc, ++g) {
           const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
           umma::mbar_wait(umma::smem_u32(&aux->empty[s]), ph ^ 1u);
@@ -130,8 +140,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
           umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
           umma::tma_load_2d(r.mapA_hi, full, st, kc * BK, r.tile * TM);
           if (!p.fast) umma::tma_load_2d(r.mapA_lo, full, st + A_BYTES, kc * BK, r.tile * TM);
-          umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
-          if (!p.fast) umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+          if (mc > 1) {
+            // this CTA's share of the weight rows, delivered to every CTA of the cluster (same stage, same offset)
+            const uint32_t rows = (uint32_t)BN / mc, roff = mc_rank * rows;
+            umma::tma_load_2d_mc(&p.tmB_hi_mc, full, st + 2 * A_BYTES + roff * (BK * 2), kc * BK, n0 + (int)roff, mc_mask);
+            if (!p.fast)
+              umma::tma_load_2d_mc(&p.tmB_lo_mc, full, st + 2 * A_BYTES + B_BYTES + roff * (BK * 2), kc * BK, n0 + (int)roff,
+                                   mc_mask);
+          } else {
+            umma::tma_load_2d(&p.tmB_hi, full, st + 2 * A_BYTES, kc * BK, n0);
+            if (!p.fast) umma::tma_load_2d(&p.tmB_lo, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0);
+          }
         }
       }
     }
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t g = 0, it = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      for (int u = u0; u < n_units; u += u_step, ++it) {
         const int n0 = (u % n_slices) * BN;
         int n_eff = p.n_total - n0;                                // columns this slice owns, rounded to the MMA granularity
         n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
@@ -172,7 +191,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
               umma::mma_f16_ss(acc, da_hi + adv, db_hi + adv, idesc, 1u);
             }
           }
-          umma::mma_commit(umma::smem_u32(&aux->empty[s]));        // frees the stage when these MMAs retire
+          if (mc > 1) umma::mma_commit_mc(umma::smem_u32(&aux->empty[s]), mc_mask);
+          else umma::mma_commit(umma::smem_u32(&aux->empty[s]));   // frees the stage when these MMAs retire
           if (kc == p.num_k - 1) umma::mma_commit(umma::smem_u32(&aux->tmem_full[slot]));
         }
       }
@@ -183,9 +203,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
     const int q = warp & 3;                                        // TMEM lane quarter = the 32 rows this warp owns
     const float us = __ldg(p.unscale);
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-      const int tile_g = u / n_slices, n0 = (u - tile_g * n_slices) * BN;
-      const UnitRef r = unit_ref(p, tile_g);
+    for (int u = u0; u < n_units; u += u_step, ++it) {
+      const int tg = u / n_slices, n0 = (u - tg * n_slices) * BN;
+      const UnitRef r = unit_ref(p, tg * (int)mc + (int)mc_rank);
       // the atom projection opens a forward: clear the per-forward overflow bit (bit 1, feature overflow, belongs to
       // the batch and stays)
       if (r.first && n0 == 0 && r.overflow && threadIdx.x == 128) atomicAnd(r.overflow, ~1);
@@ -225,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
   }
 
   __syncthreads();
+  if (mc > 1) umma::cluster_sync_all();           // no CTA leaves while a peer may still multicast to it or arrive on its barriers
   if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
