@@ -690,7 +690,8 @@ def main():
         if per_unit is None:
             per_unit = algorithmic_bytes_fwd(n_atoms, n_bonds, B, cfg) / max(1, launches_per_step)
         units_per_launch = prof_units / stage_cnt[dominant]              # group mode: `group` batches per launch
-        per_launch = per_unit * units_per_launch
+        # stage_bytes() is per launch for one batch: a stage launched once per layer (units_per_launch < 1) needs no scaling
+        per_launch = per_unit * max(1.0, units_per_launch)
         lps = stage_cnt[dominant] / prof_units
         dur_us = 1e3 * stage_ms[dominant] / stage_cnt[dominant]          # CUDA events around the launch, busy stream
         share = stage_ms[dominant] / sum(stage_ms.values())
@@ -700,6 +701,8 @@ def main():
                 traffic = json.load(fh).get(dominant, {}).get(f"batch_{B}")
         except Exception:
             pass
+        if traffic is not None and dominant == "tc_fwd_fused" and abs(units_per_launch - 20.0) > 1e-6 and B == 64:
+            traffic = None                                               # the capture is of a 20-batch group launch
         pipe_us = ms_per_step * 1e3 * share / lps                        # machine time the pipelined region spends per launch
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": per_launch / (dur_us * 1e-6) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": per_launch / (dur_us * 1e-6) / 1e9 / hbm_peak, "traffic": traffic,
@@ -713,6 +716,20 @@ def main():
                             "launching stream, stream kept busy) against its algorithmic bytes; pipelined_*: the kernel's "
                             "event share of a step x the timed region's time per step (independent forwards overlapped "
                             "over streams) -- machine time per launch, not a launch duration"}
+        if dominant == "gemm_bond_update":
+            # layer-wise path (graphs that do not tile, cfg-5): the dominant launch is a plain [E, H] x [H, H] GEMM whose
+            # arithmetic intensity (H / 6 flop per algorithmic byte, x3 executed by the FP16x3 split) is past the ridge
+            # of the machine at H = 1024: the tensor pipe bounds it, not HBM
+            fl = 2.0 * n_bonds * cfg["hidden"] * cfg["hidden"] * max(1.0, units_per_launch)
+            tensor_peak = tc_sustained                      # a kernel timed inside a long step: the sustained figure
+            ridge = tensor_peak * 1e12 / (hbm_peak * 1e9)
+            if 3.0 * fl / per_launch > ridge:
+                tf = fl / (dur_us * 1e-6) / 1e12
+                roofline.update({"bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s",
+                                 "frac": tf / tensor_peak, "algorithmic_flops_per_launch": fl,
+                                 "executed_tensor_flops_factor": 3, "executed_frac": 3.0 * tf / tensor_peak,
+                                 "hbm_frac": per_launch / (dur_us * 1e-6) / 1e9 / hbm_peak,
+                                 "peak_kind": peak_kind + " (dense bf16, sustained)"})
     if rank == 0:
         alg = algorithmic_bytes_fwd(n_atoms, n_bonds, B, cfg)
         flops = algorithmic_flops_fwd(n_atoms, n_bonds, B, cfg)
