@@ -30,10 +30,14 @@ constexpr int CH = 32;                                          // columns the e
 constexpr int AUX_BYTES = 256;
 constexpr int MAX_STAGES = 4;
 
-// What bounds this kernel is the rate at which L2 feeds the SMs (~6.3 KB/clk chip-wide = ~43 B/clk per SM with all 148
-// pulling): every unit streams 14 k-chunks of 72 KB (BN = 160, three stages) or 85 KB (BN = 208, two stages) for
-// ~1 k cycles of MMAs per chunk; both configurations measure the same (92 us per group of 20 cfg-2 batches, 826 MB
-// of operand traffic = 9 TB/s).  BN = 160 is preferred where it pads the output width less.
+// What bounds this kernel is the tensor pipe fed from shared memory: an SS-mode MMA re-reads both operands from shared
+// memory (9-10.5 KB per 128 x N x 16 MMA) and the FP16x3 split issues three per k-step, so a k-chunk of 12 MMAs takes
+// ~2 k cycles where the math alone needs ~1 k (ncu: tensor pipe 51 % active; 1.0 PFLOP/s executed against 1.4-1.66 for
+// cuBLAS bf16).  Measured equal or worse, i.e. NOT the bound: 160-wide slices with three 72 KB stages vs 208 with two
+// 85 KB stages (92 us per group of 20 cfg-2 batches either way), weight multicast over clusters of 2 / 4 CTAs (104.3 /
+// 104.7 / 116.6 us on a slower box), two row tiles per unit sharing every weight chunk (28 % fewer bytes from L2:
+// 124 vs 105 us -- the accumulators then take both TMEM slots and the 10 k-cycle drain is exposed).  BN = 160 is
+// preferred where it pads the output width less.  The lever left is cta_group::2 (each CTA reads half of B).
 template <int BN_>
 struct PCfg {
   static constexpr int BN = BN_;
