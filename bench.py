@@ -798,7 +798,8 @@ def main():
                                    "every step's H2D from its own pinned buffers + index build + kernels + D2H; up to %d "
                                    "consecutive batches share one submission" % (B, args.coalesce, args.leg_seconds,
                                                                                   args.coalesce)) if small
-                                  else "GNN.forward(host batch of %d): H2D of the whole batch + index build + kernels + D2H" % B,
+                                  else "GNN.forward(host batch of %d): slices of 1024 whole reactions pipelined over 4 streams (H2D of one slice "
+                                       "overlaps the kernels of another) + index build + kernels + D2H" % B,
                            "steps": e2e["steps"],
                            "uncoalesced_value": e2e["uncoalesced_rate"] * world if e2e["uncoalesced_rate"] else None,
                            "uncoalesced_api": "GNN.predict_stream(..., coalesce=1): one submission per batch",

@@ -233,6 +233,28 @@ def test_fp64_accuracy_yardstick(engine):
 # ---------------------------------------------------------------------------------------------
 # behaviours of the drop-in boundary
 # ---------------------------------------------------------------------------------------------
+def test_large_host_batch_is_pipelined_over_slices():
+    """A host batch of >= HOST_CHUNK_MIN reactions goes through predict_stream in slices of whole reactions: same
+    energies as the device path of the whole batch (up to the fp32 order of the final column sums), with ptr or with
+    batch only, and the un-tileable fallback of a slice still sees a multi-reaction batch."""
+    from cgr_mpnn_3D.models.GNN import GNN
+    meta = dict(fa=78, fb=14, depth=2, hidden=64, skip=True, wseed=4, act="relu")
+    data = make_batch(700, seed=41, kind="t1x", fa=78)
+    model = build_model(meta, engine="auto").eval()
+    old = GNN.HOST_CHUNK_MIN, GNN.HOST_CHUNK
+    try:
+        GNN.HOST_CHUNK_MIN, GNN.HOST_CHUNK = 512, 200             # 4 slices, the last one short
+        with torch.no_grad():
+            ref = model(data.to("cuda")).cpu()
+            out = model(data)
+            assert out.device.type == "cpu" and out.shape == ref.shape
+            assert scale_normalised_error(out, ref) < 1e-5
+            nop = Batch(data.x, data.edge_index, data.edge_attr, data.batch, None, data.y)   # no ptr: rebuilt from batch
+            assert torch.equal(model(nop), out)
+    finally:
+        GNN.HOST_CHUNK_MIN, GNN.HOST_CHUNK = old
+
+
 def test_host_inputs_are_staged():
     """CPU tensors in -> result on CPU (reference CLI feeds un-batched CPU Data, CLI :71-76)."""
     z, meta = load_case("single_nobatch")
