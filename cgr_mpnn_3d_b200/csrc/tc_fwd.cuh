@@ -169,12 +169,35 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
+// Packed fp32 arithmetic (FADD2 / FFMA2 of sm_100: two IEEE operations per instruction on an aligned register pair --
+// the halves of a float4 loaded with one 128-bit access are such pairs).  Results are bit-identical to the scalar
+// forms; the gather warps are issue-bound, so halving their adds is worth a fifth of their instructions.
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 sub2(const float2 a, const float2 b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t*>(&a)),
+      "l"(*reinterpret_cast<const uint64_t*>(&b)), "l"(*reinterpret_cast<const uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat4(const float2 a, const float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float4 add4v(const float4 a, const float4 b) { return cat4(add2(lo2(a), lo2(b)), add2(hi2(a), hi2(b))); }
+
 // sum of the four staged rows a descriptor names (byte offsets from y_b): four independent loads, no branches, a
 // two-level add tree
 __device__ __forceinline__ float4 ldb4(const char* y_b, uint32_t off) { return *reinterpret_cast<const float4*>(y_b + off); }
 __device__ __forceinline__ float4 sum4(const float4 v0, const float4 v1, const float4 v2, const float4 v3) {
-  return make_float4((v0.x + v1.x) + (v2.x + v3.x), (v0.y + v1.y) + (v2.y + v3.y), (v0.z + v1.z) + (v2.z + v3.z),
-                     (v0.w + v1.w) + (v2.w + v3.w));
+  return add4v(add4v(v0, v1), add4v(v2, v3));
 }
 __device__ __forceinline__ float4 gather4(const char* y_b, uint4 o) {
   return sum4(ldb4(y_b, o.x), ldb4(y_b, o.y), ldb4(y_b, o.z), ldb4(y_b, o.w));
@@ -182,13 +205,26 @@ __device__ __forceinline__ float4 gather4(const char* y_b, uint4 o) {
 __device__ __forceinline__ float4 gather4p(const char* y_b, uint2 o) {     // packed: 16 bits per offset
   return sum4(ldb4(y_b, o.x & 0xffffu), ldb4(y_b, o.x >> 16), ldb4(y_b, o.y & 0xffffu), ldb4(y_b, o.y >> 16));
 }
+// FP16 (hi, lo) split of one float4 column group, stored as two 8-byte words; vmax2 tracks max |hi| of everything this
+// thread stored (the fp16-range guard: a value past the range rounds to a hi of inf)
+__device__ __forceinline__ void store_split4_track(const float4 z, __half* hi, __half* lo, __half2& vmax2) {
+  const __half2 hi01 = __floats2half2_rn(z.x, z.y), hi23 = __floats2half2_rn(z.z, z.w);
+  const float2 r01 = sub2(lo2(z), __half22float2(hi01)), r23 = sub2(hi2(z), __half22float2(hi23));
+  const __half2 lo01 = __floats2half2_rn(r01.x, r01.y), lo23 = __floats2half2_rn(r23.x, r23.y);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
+  pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
+  *reinterpret_cast<uint2*>(hi) = ph;
+  *reinterpret_cast<uint2*>(lo) = pl;
+  vmax2 = __hmax2(vmax2, __hmax2(__habs2(hi01), __habs2(hi23)));
+}
 // rows with more than 2 * FASTN neighbours: walk the CSR list, skipping row `skip`
 template <int CHP>
 __device__ __noinline__ float4 gather_list(const char* y_b, const uint8_t* idx_l, int pb, int n, int skip) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = 0; t < n; ++t) {
     const int k = idx_l[pb + t];
-    if (k != skip) tcg::add4(a, ldb4(y_b, (uint32_t)(k * CHP * 4)));
+    if (k != skip) a = add4v(a, ldb4(y_b, (uint32_t)(k * CHP * 4)));
   }
   return a;
 }
@@ -659,7 +695,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           if (cn > 2 * FASTN) vslow |= 1u << k;
         }
       }
-      float vmax = 0.f;
+      __half2 vmax2 = __float2half2_rn(0.f);                        // max |hi| of what this thread stores (fp16-range guard)
       float tsum[SLOTS];                                            // readout: this thread's part of hv[v] . w_f
 #pragma unroll
       for (int k = 0; k < SLOTS; ++k) tsum[k] = 0.f;
@@ -677,27 +713,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           for (int k = 0; k < SLOTS; ++k) {
             const int r = r0 + k * RPP;
             float4 a4 = gather4(y_bc, nbd[r]);                      // dead rows and unused slots read the zero row
-            if (slow & (1u << k)) tcg::add4(a4, gather4p(y_bc, nb2[r]));          // neighbours 5..8 (one row in 25)
+            if (slow & (1u << k)) a4 = add4v(a4, gather4p(y_bc, nb2[r]));         // neighbours 5..8 (one row in 25)
             if (vslow & (1u << k))                                  // an atom with ten or more bonds: walk the CSR list
               a4 = readout ? gather_list<CHP>(y_bc, ta.idx_l, (int)ta.pb_a[r], (int)ta.cnt_a[r], -1)
                            : gather_list<CHP>(y_bc, ta.idx_l, (int)ta.pb_b[r], (int)ta.full_b[r], r ^ 1);
             if (!readout) {
               // z[e] = sum_{k in in(src e), k != e^1} y[k] + b + skip * h0[e];  h' = act(z) -> next operand (hi, lo)
+              const float2 sk2 = make_float2(skip, skip);
+              const float2 p01 = add2(lo2(a4), fma2(sk2, lo2(opnd[k]), lo2(c4)));
+              const float2 p23 = add2(hi2(a4), fma2(sk2, hi2(opnd[k]), hi2(c4)));
               float4 z;
-              z.x = tcg::act_t<RELU>(a4.x + fmaf(skip, opnd[k].x, c4.x), p.act);
-              z.y = tcg::act_t<RELU>(a4.y + fmaf(skip, opnd[k].y, c4.y), p.act);
-              z.z = tcg::act_t<RELU>(a4.z + fmaf(skip, opnd[k].z, c4.z), p.act);
-              z.w = tcg::act_t<RELU>(a4.w + fmaf(skip, opnd[k].w, c4.w), p.act);
+              z.x = tcg::act_t<RELU>(p01.x, p.act); z.y = tcg::act_t<RELU>(p01.y, p.act);
+              z.z = tcg::act_t<RELU>(p23.x, p.act); z.w = tcg::act_t<RELU>(p23.y, p.act);
               if (valid & (1u << k)) {
-                vmax = fmaxf(vmax, tcg::amax4(z));
                 char* od = oh + (uint32_t)k * o_row_step;
-                tcg::store_split4(z, 1.f, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + B.lo_delta));
+                store_split4_track(z, reinterpret_cast<__half*>(od), reinterpret_cast<__half*>(od + B.lo_delta), vmax2);
               }
             } else {
               // readout: hv[v] = act(Q'[v] + sum_{k in in(v)} y[k]);  t[v] += hv[v] . w_f over this thread's columns
+              const float4 q4 = add4v(a4, opnd[k]);
               float4 hv;
-              hv.x = tcg::act_t<RELU>(a4.x + opnd[k].x, p.act); hv.y = tcg::act_t<RELU>(a4.y + opnd[k].y, p.act);
-              hv.z = tcg::act_t<RELU>(a4.z + opnd[k].z, p.act); hv.w = tcg::act_t<RELU>(a4.w + opnd[k].w, p.act);
+              hv.x = tcg::act_t<RELU>(q4.x, p.act); hv.y = tcg::act_t<RELU>(q4.y, p.act);
+              hv.z = tcg::act_t<RELU>(q4.z, p.act); hv.w = tcg::act_t<RELU>(q4.w, p.act);
               float t = hv.x * c4.x;
               t = fmaf(hv.y, c4.y, t);
               t = fmaf(hv.z, c4.z, t);
@@ -718,6 +755,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
 
       if (!readout) {
         // this CTA's slice of h_{l+1} is stored: make it visible to the peers' TMA loads, then tell every CTA of the cluster
+        const float vmax = fmaxf(__low2float(vmax2), __high2float(vmax2));
         if (vmax > 60000.f) {                                       // fp16 range of the split: flag the batch and this tile
           atomicOr(B.overflow, 1);
           atomicOr(B.tile_counter + tile, 0x10000);
