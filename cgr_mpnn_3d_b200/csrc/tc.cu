@@ -842,6 +842,8 @@ int fwd_fill_shared(tcf::FwdParams* prm, const cgr_params_t* p, const char* wbuf
   prm->tiles_per_cluster = fc.tpc;
   prm->fast = fast;
   prm->dbg = g_tc_dbg;
+  static const int publish = getenv("CGR_PUBLISH") ? atoi(getenv("CGR_PUBLISH")) : 2;     // experiments: 0 .. 3
+  prm->publish_mode = publish;
   return CGR_OK;
 }
 // ... and one batch's part: operand buffers of its workspace, index arrays, outputs

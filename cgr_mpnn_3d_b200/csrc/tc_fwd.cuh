@@ -126,6 +126,9 @@ struct FwdParams {
   int depth, H, num_k, act, tiles_per_cluster;
   int fast;                                    // 1: single-pass fp16 (hi halves only), the "fast" precision mode
   long long* dbg;                              // optional [n_cta][MAX_TPC * MAX_LAYERS][8] clock64 stamps (debug)
+  int publish_mode;                            // 0: proxy fence + __threadfence + release arrive; 1: no __threadfence
+                                               // (the arrive releases at cluster scope); 2: 1 + proxy fence on .global only;
+                                               // 3: 2 + no second proxy fence on the reading side
 };
 
 struct TileAux {                // per tile of the group: neighbour descriptors (built once, used by every layer)
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           if (kc == 0 && (l > 0 || p.fuse_init)) {
             // the S slices of this tile's previous layer have been stored (every CTA of the cluster arrived)
             umma::mbar_wait_cluster(umma::smem_u32(&aux->ready[j]), (uint32_t)(l - 1 + p.fuse_init) & 1u);
-            umma::fence_proxy_async();
+            if (p.publish_mode < 3) umma::fence_proxy_async();
             FWD_STAMP(true, i, 3);
           }
           if (B.train_rows) {
@@ -640,10 +643,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
         if (i == NI - 1) {
           stamp(MAX_TPC * MAX_LAYERS - 1, 3 + 2 * jj);
           // publish this tile's slice of the layer-0 operand (same protocol as a layer's output, below)
-          umma::fence_proxy_async();
+          if (p.publish_mode < 2) umma::fence_proxy_async(); else umma::fence_proxy_async_global();
           __syncwarp();
           if (lane < S) {
-            __threadfence();
+            if (p.publish_mode == 0) __threadfence();
             umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[jj]), (uint32_t)lane);
           }
           stamp(MAX_TPC * MAX_LAYERS - 1, 4 + 2 * jj);
@@ -761,13 +764,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(const __grid_constan
           atomicOr(B.tile_counter + tile, 0x10000);
         }
         // every gather warp publishes its own rows: the lanes order their stores against the peers' TMA reads (proxy
-        // fence) and meet at the warp barrier, then one lane per peer CTA fences (cumulative over what the warp
-        // barrier ordered before it) and arrives on that CTA's barrier -- S * GAT_WARPS arrivals complete a layer.
+        // fence) and meet at the warp barrier, then one lane per peer CTA arrives on that CTA's barrier with release
+        // semantics at cluster scope (cumulative over what the warp barrier ordered before it; a separate
+        // __threadfence() there cost a sequentially consistent fence + an L1 invalidate per item for nothing:
+        // publish_mode 0) -- S * GAT_WARPS arrivals complete a layer.
         // No CTA-wide barrier: a warp that is done moves on to the next item's chunks
-        umma::fence_proxy_async();
+        if (p.publish_mode < 2) umma::fence_proxy_async(); else umma::fence_proxy_async_global();
         __syncwarp();
         if (lane < S) {
-          __threadfence();
+          if (p.publish_mode == 0) __threadfence();
           umma::mbar_arrive_remote(umma::smem_u32(&aux->ready[j]), (uint32_t)lane);
         }
       } else {
