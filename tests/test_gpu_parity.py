@@ -233,6 +233,25 @@ def test_fp64_accuracy_yardstick(engine):
 # ---------------------------------------------------------------------------------------------
 # behaviours of the drop-in boundary
 # ---------------------------------------------------------------------------------------------
+def test_layer_handover_is_stable_under_repetition():
+    """The fused kernel hands a layer's rows to the peer CTAs of its cluster through release / acquire at cluster scope
+    and proxy fences (no sequentially consistent fence): a stale read of a peer's slice would show as a run-to-run
+    difference.  100 group forwards and 10 large batches must be bit-identical (tools/stress_publish.py runs more)."""
+    meta = dict(fa=846, fb=14, depth=4, hidden=400, skip=True, wseed=0, act="relu")
+    model = build_model(meta, engine="auto").eval()
+    model.tile_policy = "throughput"
+    bs = [make_batch(64, seed=200 + i, kind="t1x", fa=846).to("cuda") for i in range(12)]
+    big = make_batch(2048, seed=299, kind="t1x", fa=846).to("cuda")
+    with torch.no_grad():
+        ref = [o.clone() for o in model.forward_group(bs)]
+        refb = model(big).clone()
+        for _ in range(100):
+            assert all(torch.equal(a, b) for a, b in zip(model.forward_group(bs), ref))
+        for _ in range(10):
+            assert torch.equal(model(big), refb)
+    model.check_numerics()
+
+
 def test_large_host_batch_is_pipelined_over_slices():
     """A host batch of >= HOST_CHUNK_MIN reactions goes through predict_stream in slices of whole reactions: same
     energies as the device path of the whole batch (up to the fp32 order of the final column sums), with ptr or with
