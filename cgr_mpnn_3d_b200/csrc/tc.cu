@@ -506,7 +506,15 @@ int proj_mc(int bn) {
   const int mc = (mc_env == 2 || mc_env == 4) ? mc_env : 1;
   return (mc > 1 && bn % (8 * mc) == 0) ? mc : 1;            // shares of whole 8-row swizzle groups only
 }
+bool proj_cg2_wanted(int bn, int n_total);
 int proj_multicast(TcGemmParams* ap, const __half* w_hi, const __half* w_lo, int64_t rows, int64_t cols, int64_t ld, int bn) {
+  if (proj_cg2_wanted(bn, (int)rows)) {          // CTA-pair kernel: each CTA stages half of the slice's weight rows
+    int rc;
+    if ((rc = make_map(&ap->tmB_hi_mc, w_hi, rows, cols, ld, bn / 2))) return rc;
+    if ((rc = make_map(&ap->tmB_lo_mc, w_lo, rows, cols, ld, bn / 2))) return rc;
+    ap->mc = -2;
+    return CGR_OK;
+  }
   const int mc = proj_mc(bn);
   if (mc == 1) return CGR_OK;
   int rc;
@@ -557,7 +565,53 @@ int launch_proj_t(const TcGemmParams& prm, int m_tiles, cudaStream_t st) {
   CGR_CUDA(cudaLaunchKernelEx(&cfg, tcp::tc_proj_kernel<BN>, prm, n_units, n_slices));
   return CGR_OK;
 }
+// CTA-pair variant (tcgen05 cta_group::2): 160-wide slices only; needs the half-height weight maps (tmB_*_mc, mc = 2).
+// Measured (group of 20 cfg-2 batches): 109.5 us against 100.4 us for the one-CTA kernel on the same box -- halving the
+// weight rows a CTA reads from shared memory per MMA does not speed the MMAs up, and the peer's "chunk landed" relay
+// lengthens every stage's round trip; optional (CGR_AP_CG2=1), parity-tested, off.  Slice widths measured under ncu
+// (cold, ~1 GHz): 128 / 160 / 208 / 256 columns = 235 / 192 / 178 / 203 k cycles for the same launch (256 pads 2H = 800
+// to 1024).
+bool proj_cg2_wanted(int bn, int n_total) {
+  static const bool on = getenv("CGR_AP_CG2") != nullptr;
+  return on && bn == PROJ_BN_3STAGE && n_total % PROJ_BN_3STAGE == 0;
+}
+int launch_proj_cg2(const TcGemmParams& prm, int m_tiles, cudaStream_t st) {
+  using C = tcp::P2Cfg<PROJ_BN_3STAGE>;
+  static bool attr_done = false;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(tcp::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!attr_done) {
+    CGR_CUDA(cudaFuncSetAttribute(tcp::tc_proj_cg2_kernel<PROJ_BN_3STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    int dev = 0, n_sm = 0;
+    CGR_CUDA(cudaGetDevice(&dev));
+    CGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    cfg.gridDim = dim3((unsigned)(n_sm / 2 * 2));
+    int n = 0;
+    CGR_CUDA(cudaOccupancyMaxActiveClusters(&n, tcp::tc_proj_cg2_kernel<PROJ_BN_3STAGE>, &cfg));
+    max_clusters = n > 0 ? n : 1;
+    attr_done = true;
+  }
+  const int n_slices = (int)cgr_ceil_div(prm.n_total, PROJ_BN_3STAGE);
+  const int n_units = (int)cgr_ceil_div(m_tiles, 2) * n_slices;
+  CgrRange prof("tc_atom_proj", st);
+  cgr_note_launch("tc_atom_proj", st, 1);
+  cfg.gridDim = dim3((unsigned)((n_units < max_clusters ? n_units : max_clusters) * 2));
+  CGR_CUDA(cudaLaunchKernelEx(&cfg, tcp::tc_proj_cg2_kernel<PROJ_BN_3STAGE>, prm, n_units, n_slices));
+  return CGR_OK;
+}
 int launch_proj(const TcGemmParams& prm, int bn, int m_tiles, cudaStream_t st) {
+  if (prm.mc == -2) return launch_proj_cg2(prm, m_tiles, st);
   return bn == PROJ_BN_3STAGE ? launch_proj_t<PROJ_BN_3STAGE>(prm, m_tiles, st) : launch_proj_t<PROJ_BN_WIDE>(prm, m_tiles, st);
 }
 

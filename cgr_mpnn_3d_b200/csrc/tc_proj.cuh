@@ -253,4 +253,197 @@ __global__ void __launch_bounds__(THREADS, 1) tc_proj_kernel(const __grid_consta
   if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs takes two consecutive row tiles through one column slice as
+// ONE M = 256 MMA per k-step.  Each CTA stages its own 128 rows of x and only HALF of the weight slice's rows; the
+// tensor cores of both SMs read the two halves, so a CTA's shared-memory operand traffic per MMA drops from
+// 128 + BN to 128 + BN / 2 rows -- the SS-mode MMAs of the one-CTA kernel run at about half the math rate on it --
+// and a stage shrinks to 52 KB (four fit).  The leader CTA issues the MMAs; the peer relays "my chunk has landed" to
+// the leader's barrier; tcgen05.commit multicasts stage-free / accumulator-ready to both CTAs; each CTA's epilogue
+// warps drain their own 128 rows and report to the leader.  Same arithmetic per output element: bit-identical.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN_>
+struct P2Cfg {
+  static constexpr int BN = BN_;
+  static constexpr int HB = BN / 2;                               // weight rows each CTA of the pair stages
+  static constexpr int B_BYTES = HB * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A (hi, lo) + half of B (hi, lo)
+  static constexpr int FIT = (232448 - 1024 - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > MAX_STAGES ? MAX_STAGES : FIT;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + AUX_BYTES;
+  static_assert(BN % 32 == 0 && BN <= SLOT_COLS && HB % 8 == 0 && STAGE_BYTES % 1024 == 0, "bad slice width");
+};
+struct Aux2 {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t peer_full[MAX_STAGES];   // leader: the peer's chunk has landed in the peer's shared memory
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];           // leader: 8 arrivals (the epilogue warps of both CTAs)
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Aux2) <= AUX_BYTES, "Aux2 too large");
+
+template <int BN_>
+__global__ void __launch_bounds__(THREADS, 1) tc_proj_cg2_kernel(const __grid_constant__ TcGemmParams p, int n_units,
+                                                                 int n_slices) {
+  using C = P2Cfg<BN_>;
+  constexpr int BN = C::BN, HB = C::HB, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = umma::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  Aux2* aux = reinterpret_cast<Aux2*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = umma::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int u0 = (int)(blockIdx.x >> 1), u_step = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      umma::mbar_init(umma::smem_u32(&aux->full[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->empty[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->peer_full[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(umma::smem_u32(&aux->tmem_full[s]), 1);
+      umma::mbar_init(umma::smem_u32(&aux->tmem_empty[s]), 8);
+    }
+    umma::mbar_fence_init();
+    umma::tma_prefetch_desc(&p.tmB_hi_mc);
+    umma::tma_prefetch_desc(&p.tmB_lo_mc);
+  }
+  if (warp == 2) {
+    umma::tmem_alloc_cg2(umma::smem_u32(&aux->tmem_base), 512);
+    umma::tmem_relinquish_cg2();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  umma::cluster_sync_all();                       // both CTAs' barriers and TMEM exist before either is used
+  const uint32_t tmem = aux->tmem_base;
+  if (threadIdx.x == 0) umma::grid_dep_launch();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      umma::grid_dep_wait();                     // x (hi, lo) may be the output of the previous kernel
+      uint32_t g = 0;
+      for (int u = u0; u < n_units; u += u_step) {
+        const int tg = u / n_slices, n0 = (u - tg * n_slices) * BN;
+        const UnitRef r = unit_ref(p, 2 * tg + (int)rank);
+        for (int kc = 0; kc < p.num_k; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          umma::mbar_wait_cluster(umma::smem_u32(&aux->empty[s]), ph ^ 1u);
+          const uint32_t full = umma::smem_u32(&aux->full[s]);
+          const uint32_t st = base + s * STAGE_BYTES;
+          umma::mbar_arrive_expect_tx(full, p.fast ? A_BYTES + B_BYTES : STAGE_BYTES);
+          umma::tma_load_2d(r.mapA_hi, full, st, kc * BK, r.tile * TM);
+          if (!p.fast) umma::tma_load_2d(r.mapA_lo, full, st + A_BYTES, kc * BK, r.tile * TM);
+          // this CTA's half of the weight slice's rows (tmB_*_mc: box of BN / 2 rows)
+          umma::tma_load_2d(&p.tmB_hi_mc, full, st + 2 * A_BYTES, kc * BK, n0 + (int)rank * HB);
+          if (!p.fast) umma::tma_load_2d(&p.tmB_lo_mc, full, st + 2 * A_BYTES + B_BYTES, kc * BK, n0 + (int)rank * HB);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && !leader) {
+      // ---------------------------------------------------------------- peer CTA: relay "chunk landed" to the leader
+      uint32_t g = 0;
+      for (int u = u0; u < n_units; u += u_step)
+        for (int kc = 0; kc < p.num_k; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
+          umma::mbar_arrive_remote(umma::smem_u32(&aux->peer_full[s]), 0u);
+        }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------------- leader CTA: MMA issuer of the pair
+      uint32_t g = 0, it = 0;
+      for (int u = u0; u < n_units; u += u_step, ++it) {
+        const int n0 = (u % n_slices) * BN;
+        int n_eff = p.n_total - n0;                                // columns this slice owns (multiple of 32: both halves of 16)
+        n_eff = n_eff >= BN ? BN : ((n_eff + 31) & ~31);
+        const uint32_t idesc = umma::idesc_f16_f32(2 * TM, n_eff);
+        const uint32_t slot = it & 1u;
+        umma::mbar_wait_cluster(umma::smem_u32(&aux->tmem_empty[slot]), ((it >> 1) & 1u) ^ 1u);
+        umma::tc_fence_after_sync();
+        const uint32_t acc = tmem + slot * SLOT_COLS;
+        for (int kc = 0; kc < p.num_k; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          umma::mbar_wait(umma::smem_u32(&aux->full[s]), ph);
+          umma::mbar_wait_cluster(umma::smem_u32(&aux->peer_full[s]), ph);
+          umma::tc_fence_after_sync();
+          const uint32_t st = base + s * STAGE_BYTES;
+          const uint64_t da_hi = umma::smem_desc_k_sw128(st);
+          const uint64_t da_lo = umma::smem_desc_k_sw128(st + A_BYTES);
+          const uint64_t db_hi = umma::smem_desc_k_sw128(st + 2 * A_BYTES);
+          const uint64_t db_lo = umma::smem_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+          const int k_left = p.k_total - kc * BK;                  // K tail: skip k-steps that are all zero padding
+          const int ksteps = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            if (ks >= ksteps) break;
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);         // 16 fp16 = 32 bytes along K inside the swizzle row
+            if (p.fast) {
+              umma::mma_f16_ss_cg2(acc, da_hi + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+            } else {
+              umma::mma_f16_ss_cg2(acc, da_lo + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+              umma::mma_f16_ss_cg2(acc, da_hi + adv, db_lo + adv, idesc, 1u);
+              umma::mma_f16_ss_cg2(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+          }
+          umma::mma_commit_cg2_mc(umma::smem_u32(&aux->empty[s]), (uint16_t)3);   // the stage is free in both CTAs
+          if (kc == p.num_k - 1) umma::mma_commit_cg2_mc(umma::smem_u32(&aux->tmem_full[slot]), (uint16_t)3);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const float us = __ldg(p.unscale);
+    uint32_t it = 0;
+    for (int u = u0; u < n_units; u += u_step, ++it) {
+      const int tg = u / n_slices, n0 = (u - tg * n_slices) * BN;
+      const UnitRef r = unit_ref(p, 2 * tg + (int)rank);
+      if (r.first && n0 == 0 && r.overflow && threadIdx.x == 128) atomicAnd(r.overflow, ~1);
+      const uint32_t slot = it & 1u;
+      umma::mbar_wait_cluster(umma::smem_u32(&aux->tmem_full[slot]), (it >> 1) & 1u);
+      umma::tc_fence_after_sync();
+      const uint32_t acc = tmem + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
+      const int row = r.tile * TM + q * 32 + lane;
+      const int n_cols = p.n_total - n0 < BN ? p.n_total - n0 : BN;
+      float* orow = r.out + (int64_t)row * p.ldc + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_cols; c0 += CH) {
+        float v[CH / 8][8];
+#pragma unroll
+        for (int g = 0; g < CH / 8; ++g)
+          if (c0 + g * 8 < n_cols) umma::tmem_ld_x8(acc + (uint32_t)(c0 + g * 8), v[g]);
+        umma::tmem_ld_wait();
+        if (row < r.m_rows) {
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) {
+            if (c0 + g * 8 < n_cols) {
+              const int c = c0 + g * 8;
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (p.bias) { b0 = tcg::ld4(p.bias + n0 + c); b1 = tcg::ld4(p.bias + n0 + c + 4); }
+              float4* dst = reinterpret_cast<float4*>(orow + c);
+              dst[0] = make_float4(v[g][0] * us + b0.x, v[g][1] * us + b0.y, v[g][2] * us + b0.z, v[g][3] * us + b0.w);
+              dst[1] = make_float4(v[g][4] * us + b1.x, v[g][5] * us + b1.y, v[g][6] * us + b1.z, v[g][7] * us + b1.w);
+            }
+          }
+        }
+      }
+      umma::tc_fence_before_sync();                                // accumulator drained: the leader may reuse the slot
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive_remote(umma::smem_u32(&aux->tmem_empty[slot]), 0u);
+    }
+  }
+
+  __syncthreads();
+  umma::cluster_sync_all();                       // no CTA leaves while the pair's MMAs / arrivals may still touch it
+  if (warp == 2) umma::tmem_dealloc_cg2(tmem, 512);
+}
+
 }  // namespace tcp

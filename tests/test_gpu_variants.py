@@ -16,6 +16,7 @@ VARIANTS = {
     "CGR_AP_BN=208": ("persistent atom projection with 208-wide slices / two operand stages", True),
     "CGR_AP_MC=2": ("persistent atom projection, weight chunks multicast over clusters of two CTAs", True),
     "CGR_AP_OLD=1": ("one-unit-per-CTA atom projection kernel", True),
+    "CGR_AP_CG2=1": ("persistent atom projection on CTA pairs (tcgen05 cta_group::2, M = 256)", True),
     "CGR_NO_FUSED_TRAIN_FWD=1": ("training forward through the per-layer kernels", False),
     "CGR_BWD_FORK=1": ("weight-gradient GEMMs on a side stream", False),
 }

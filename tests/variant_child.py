@@ -16,6 +16,7 @@ def run(path=None):
     meta = dict(fa=846, fb=14, depth=3, hidden=400, skip=True, wseed=5, act="relu")
     data = make_batch(256, seed=31, kind="t1x", fa=846).to("cuda")
     model = build_model(meta, engine="auto").eval()
+    model.tile_policy = "throughput"          # wide-slice regime: the persistent atom projection and the 2-tile clusters
     with torch.no_grad():
         out = model(data)
     model.train()
