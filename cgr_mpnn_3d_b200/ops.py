@@ -21,7 +21,14 @@ from . import _lib
 #    edge_to_node.bias, ffn.weight, ffn.bias, (skip_weights.0, ...)]
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    # the raw handle of the current device's current stream: torch.cuda.current_stream() builds a Stream object and
+    # resolves the device index through several Python layers (~20 us, three times per training step)
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -281,7 +288,7 @@ def gnn_backward_impl(grad_out: Tensor, x: Tensor, edge_attr: Tensor, src: Tenso
     params = [_f32c(p) for p in params]
     grad_out = _f32c(grad_out)
     fa, fb = int(x.shape[1]), int(edge_attr.shape[1])
-    ctx = _Ctx(params, depth, act, use_skip, fa, fb, dropout_ps)
+    ctx = _ctx_cached("bwd", params, depth, act, use_skip, fa, fb, dropout_ps)      # resets tc_weights / tc_throughput / tc_fast
     if tc_weights.numel() > 0:
         ctx.params.tc_weights = tc_weights.data_ptr()
     h_all, m_all, z_all, s, hv, zv, pooled, tc_blob = saved
