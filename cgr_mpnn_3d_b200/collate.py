@@ -22,7 +22,7 @@ from .data import Batch, Graph
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _lib.current_stream_handle()
 
 
 class GraphPlan:

@@ -144,7 +144,7 @@ def featurize_batch(reactions: Sequence[Tuple[ParsedMol, Optional[ParsedMol]]], 
         t = tables or default_tables()
         _lib.check(lib.cgr_featurize_cgr(C.byref(t), d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
                                          n_atoms, d[4].data_ptr(), d[5].data_ptr(), n_bonds, x.data_ptr(), x.stride(0),
-                                         ea.data_ptr(), torch.cuda.current_stream().cuda_stream), "cgr_featurize_cgr")
+                                         ea.data_ptr(), _lib.current_stream_handle()), "cgr_featurize_cgr")
         if f3d:
             m = np.concatenate([np.asarray(a, dtype=np.float32) for a in mace], axis=0)     # float64 would promote x
             if m.shape[0] != n_atoms:

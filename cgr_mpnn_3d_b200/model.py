@@ -435,7 +435,7 @@ class GNN(nn.Module):
             rc = lib.cgr_gnn_infer_host(C.byref(ctx.params), x.data_ptr(), ea.data_ptr(), ei.data_ptr(),
                                         _lib.ptr(ptr), _lib.ptr(batch), n, e, b, hout.data_ptr(), dws.data_ptr(),
                                         dws.numel(), hws.data_ptr(), hws.numel(),
-                                        torch.cuda.current_stream().cuda_stream)
+                                        _lib.current_stream_handle())
         if rc == -3:            # not tileable: generic path (layer-wise kernels); fp16 range: exact-fp32 engine
             msg = lib.cgr_last_error_string() or b""
             if b"fp16 range" in msg:

@@ -21,15 +21,8 @@ from . import _lib
 #    edge_to_node.bias, ffn.weight, ffn.bias, (skip_weights.0, ...)]
 
 
-_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
-
-
 def _stream() -> int:
-    # the raw handle of the current device's current stream: torch.cuda.current_stream() builds a Stream object and
-    # resolves the device index through several Python layers (~20 us, three times per training step)
-    if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
-    return torch.cuda.current_stream().cuda_stream
+    return _lib.current_stream_handle()
 
 
 def _unpack(params: Sequence[Tensor], depth: int, use_skip: bool):

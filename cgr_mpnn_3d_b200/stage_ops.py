@@ -13,7 +13,7 @@ from .collate import GraphPlan, build_plan
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _lib.current_stream_handle()
 
 
 def _f32(t):

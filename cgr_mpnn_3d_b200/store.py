@@ -24,7 +24,7 @@ from .data import Batch
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _lib.current_stream_handle()
 
 
 class ReactionStore:
