@@ -1011,7 +1011,7 @@ extern "C" int cgr_gnn_infer_host_async(const cgr_params_t* p, const float* host
 // ------------------------------------------------------------------------------------------------
 // Inference over a device-resident reaction store: the per-batch loop in C, pipelined over
 // streams.  Per batch: offsets + tile plan on the host, one small upload, gather kernel, one-launch CSR, feature
-// split, the 7 forward kernels writing straight into the caller's result vector.
+// split, the two forward launches writing straight into the caller's result vector.
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct StoreBatchSizes { int64_t n_max, e_max, b_max; };
@@ -1032,6 +1032,15 @@ int store_batch_sizes(const cgr_store_t* s, const int64_t* order, int64_t n_tota
   out->n_max = n_max; out->e_max = e_max; out->b_max = bs < n_total ? bs : n_total;
   return CGR_OK;
 }
+// Reactions are independent and a reaction's energy does not depend on which others share its batch (tiles hold whole
+// reactions, every reduction is per reaction), so the screening loop assembles SUPER-batches: consecutive batches of the
+// caller's size up to ~1024 reactions go through one gather / CSR / split / forward (fewer, larger launches:
+// batch 64 screens at the rate of batch 1024).  The result vector is the same, bit for bit.
+int64_t store_effective_batch(int64_t batch_size) {
+  static const bool off = getenv("CGR_STORE_NO_COALESCE") != nullptr;      // experiments
+  if (off || batch_size >= 1024) return batch_size;
+  return (1024 / batch_size) * batch_size;
+}
 // host staging of one slot: [sel | out_node_ptr | out_edge_ptr] (int64) then the int32 meta block of the host entry
 size_t store_sel_bytes(int64_t b_max) { return cgr_align_up((size_t)(3 * b_max + 2) * 8, 1024); }
 }  // namespace
@@ -1041,6 +1050,7 @@ extern "C" int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_
                                          size_t* host_bytes_per_slot) {
   CGR_CHECK_ARG(p && store && order && n_total > 0 && batch_size > 0 && dev_bytes_per_slot && host_bytes_per_slot,
                 "cgr_store_infer_workspace: bad argument");
+  batch_size = store_effective_batch(batch_size);
   StoreBatchSizes z;
   int rc = store_batch_sizes(store, order, n_total, batch_size, &z);
   if (rc) return rc;
@@ -1059,6 +1069,7 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
                 "cgr_store_infer: bad argument");
   CGR_CHECK_ARG(p->tc_weights, "cgr_store_infer: prepare the weights first (cgr_tc_prepare_weights)");
   CGR_CHECK_ARG(store->fa == p->fa && store->fb == p->fb, "cgr_store_infer: feature widths of store and model differ");
+  batch_size = store_effective_batch(batch_size);
   StoreBatchSizes z;
   if ((rc = store_batch_sizes(store, order, n_total, batch_size, &z))) return rc;
   const HostInferLayout Lmax = host_infer_layout(p, z.n_max, z.e_max, z.b_max);
