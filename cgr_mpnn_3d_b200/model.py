@@ -187,7 +187,11 @@ class GNN(nn.Module):
         slot = self.__dict__["_ovf_next"]
         self.__dict__["_ovf_next"] = (slot + 1) % 64
         ring[slot:slot + 1].copy_(tc_status[:1], non_blocking=True)
-        ev = torch.cuda.Event()
+        evs = self.__dict__.setdefault("_ovf_events", {})        # one reusable event per ring slot and device
+        key = (slot, tc_status.device.index)
+        ev = evs.get(key)
+        if ev is None:
+            ev = evs[key] = torch.cuda.Event()
         ev.record()
         return ev, ring, slot
 
@@ -649,6 +653,7 @@ class GNN(nn.Module):
         state.pop("_mirror_cache", None)     # torch.save(model) must not pickle device mirrors
         state.pop("_tc_cache", None)
         state.pop("_host_slots", None)
+        state.pop("_ovf_events", None)
         state.pop("_host_ctx_cache", None)
         state.pop("_last_plan", None)
         state.pop("_plist", None)
