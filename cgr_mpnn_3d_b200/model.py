@@ -472,13 +472,23 @@ class GNN(nn.Module):
         if ptr is None:
             ptr = torch.zeros(b + 1, dtype=torch.int64)
             ptr[1:] = torch.bincount(batch, minlength=b).cumsum(0)
-        src = ei[0]
+        src = ei[0].numpy()
         chunks, e0 = [], 0
         for b0 in range(0, b, self.HOST_CHUNK):
             b1 = min(b, b0 + self.HOST_CHUNK)
             a0, a1 = int(ptr[b0]), int(ptr[b1])
             # bonds of a collated batch are grouped by reaction: the slice ends at the first bond of a later reaction
-            e1 = e if b1 == b else int((src < a1).sum())
+            # (source atom >= a1) -- a bisection on that monotone predicate, 18 probes instead of a pass over every bond
+            e1 = e
+            if b1 < b:
+                lo_, hi_ = e0, e
+                while lo_ < hi_:
+                    mid = (lo_ + hi_) >> 1
+                    if src[mid] < a1:
+                        lo_ = mid + 1
+                    else:
+                        hi_ = mid
+                e1 = lo_
             if e1 <= e0 or a1 <= a0:
                 return None
             lp = ptr[b0:b1 + 1] - a0
