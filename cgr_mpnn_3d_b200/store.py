@@ -210,15 +210,21 @@ class ReactionStore:
         dev_b, host_b = C.c_size_t(), C.c_size_t()
         _lib.check(lib.cgr_store_infer_workspace(C.byref(ctx.params), C.byref(cs), order.ctypes.data, n_total, batch_size,
                                                  C.byref(dev_b), C.byref(host_b)), "cgr_store_infer_workspace")
-        key = (dev_b.value, host_b.value, slots)
+        # workspaces are kept across calls and only ever grow: a call that needs no more than an earlier one (fewer
+        # slots, smaller batches) allocates nothing -- cudaMalloc / pinning of a batch-8192 workspace costs tens of ms
+        need_d, need_h = dev_b.value * slots + 2048, host_b.value * slots
         cache = self.__dict__.get("_predict_ws")
-        if cache is None or cache[0] != key:
+        if cache is None or cache[0].numel() < need_d or cache[1].numel() < need_h or len(cache[2]) < slots:
+            old_streams = cache[2] if cache is not None else []
+            cache = None                                       # free the smaller workspace before taking the larger one
+            self.__dict__["_predict_ws"] = None
             with torch.cuda.device(dev):
-                cache = (key, torch.empty(dev_b.value * slots + 2048, dtype=torch.uint8, device=dev),
-                         torch.empty(host_b.value * slots, dtype=torch.uint8).pin_memory(),
-                         [torch.cuda.Stream(device=dev) for _ in range(slots)])
+                # 2 % headroom: the next shard's largest batch is rarely exactly this one's
+                cache = (torch.empty(need_d + need_d // 50, dtype=torch.uint8, device=dev),
+                         torch.empty(need_h + need_h // 50, dtype=torch.uint8).pin_memory(),
+                         old_streams + [torch.cuda.Stream(device=dev) for _ in range(slots - len(old_streams))])
             self.__dict__["_predict_ws"] = cache
-        _, dws, hws, streams = cache
+        dws, hws, streams = cache[0], cache[1], cache[2][:slots]
         out = torch.empty(n_total, dtype=torch.float32, device=dev)
         cur = torch.cuda.current_stream(dev)
         for st in streams:
