@@ -810,6 +810,11 @@ extern "C" int cgr_dropout_mask(uint64_t seed, uint32_t layer, float dropout_p, 
 int csr_by_reaction_shifted(const int64_t* edge_index, const int32_t* edge_ptr, const int32_t* atom_ptr,
                             const int32_t* rxn_shift, int64_t n_rxn, int64_t n_bonds, int64_t n_atoms, int32_t* src,
                             int32_t* dst, int32_t* in_ptr, int32_t* in_idx, int32_t* status, cudaStream_t st);
+int store_gather_split(const float* x_all, const float* ea_all, const int32_t* ei_all, const int64_t* node_ptr,
+                       const int64_t* edge_ptr, int64_t e_all, const int64_t* sel, const int64_t* out_node_ptr,
+                       const int64_t* out_edge_ptr, int64_t n_sel, int32_t fa, int32_t fb, int64_t e_out, void* x_hi,
+                       void* x_lo, int64_t ldo, float* edge_attr, int64_t* edge_index, int* range_flag, int flag_bit,
+                       cudaStream_t st);
 namespace {
 struct HostInferLayout {
   int64_t t_max, kp_x;
@@ -1138,9 +1143,11 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
     CK(cudaEventRecord(ev[slot], st), "cudaEventRecord");
     used[slot] = 1;
     if (rc) break;
-    rc = cgr_store_gather(store->x_all, store->ea_all, store->ei_all, store->node_ptr, store->edge_ptr, nullptr,
-                          store->e_all, d_sel, d_sel + B, d_sel + 2 * B + 1, B, p->fa, p->fb, E, d_x, d_ea, d_ei, nullptr,
-                          nullptr, st);
+    // gather + feature split in one pass: the atom features go straight from the store rows to the FP16 (hi, lo)
+    // operand pair of the atom projection (no fp32 copy of x in the slot); 2 = FLAG_X of tc_status[0] (tc.cu)
+    rc = store_gather_split(store->x_all, store->ea_all, store->ei_all, store->node_ptr, store->edge_ptr, store->e_all,
+                            d_sel, d_sel + B, d_sel + 2 * B + 1, B, p->fa, p->fb, E, dws + L.o_xhi, dws + L.o_xlo, L.kp_x,
+                            d_ea, d_ei, d_status + 1, 2, st);
     if (rc) break;
     cgr_graph_t g;
     memset(&g, 0, sizeof(g));
@@ -1154,8 +1161,6 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
     g.x_hi = dws + L.o_xhi; g.x_lo = dws + L.o_xlo;
     rc = csr_by_reaction_shifted(d_ei, g.atom_ptr + (B + 1), g.atom_ptr, nullptr, B, E, N, (int32_t*)g.src, (int32_t*)g.dst,
                                  (int32_t*)g.in_ptr, (int32_t*)g.in_idx, d_status, st);
-    if (rc) break;
-    rc = tc_split_features(d_x, N, p->fa, (void*)g.x_hi, (void*)g.x_lo, g.tc_status, st);
     if (rc) break;
     rc = tc_gnn_forward(&pp, &g, out + lo, nullptr, 0, 0, dws + L.o_fwd, L.fwd_bytes, st);
   }

@@ -5,6 +5,7 @@
 // message passing needs from the batched edge_index (cgr_mpnn_3D/models/GNN.py:85,132-138).
 #include "common.cuh"
 #include "../../include/cgr_b200.h"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -329,7 +330,94 @@ __global__ void __launch_bounds__(256) store_gather_kernel(
     if (y && threadIdx.x == 0) y[b] = __ldg(y_all + r);
   }
 }
+
+// The screening loop (cgr_store_infer) never needs the batch's fp32 atom features: the tcgen05 forward reads them as the
+// FP16 (hi, lo) operand pair of the atom projection.  This variant of the gather writes that pair straight from the
+// store rows -- the same arithmetic as split_rows_kernel (tc.cu), so the operands are bit-identical -- instead of an
+// fp32 copy that a second kernel would read back: 8 bytes per feature over HBM instead of 16.
+// Work of a reaction is flattened over its SG_PARTS blocks in pairs of columns (fa even) or single columns.
+template <bool PAIRS>
+__global__ void __launch_bounds__(256) store_gather_split_kernel(
+    const float* __restrict__ x_all, const float* __restrict__ ea_all, const int32_t* __restrict__ ei_all,
+    const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr, int64_t e_all,
+    const int64_t* __restrict__ sel, const int64_t* __restrict__ out_node_ptr, const int64_t* __restrict__ out_edge_ptr,
+    int fa, int fb, int64_t e_out, __half* __restrict__ x_hi, __half* __restrict__ x_lo, int64_t ldo,
+    float* __restrict__ ea, int64_t* __restrict__ ei, int* __restrict__ range_flag, int flag_bit) {
+  const int64_t b = blockIdx.y;
+  const int part = blockIdx.x;
+  const int64_t r = sel[b];
+  const int64_t a_in = node_ptr[r], n = node_ptr[r + 1] - a_in, a_out = out_node_ptr[b];
+  const int64_t e_in = edge_ptr[r], e = edge_ptr[r + 1] - e_in, e_o = out_edge_ptr[b];
+  const float* __restrict__ xs = x_all + a_in * fa;
+  __half* __restrict__ hi = x_hi + a_out * ldo;
+  __half* __restrict__ lo = x_lo + a_out * ldo;
+  const int tid = part * blockDim.x + threadIdx.x, nth = SG_PARTS * blockDim.x;
+  bool ovf = false;
+  if (PAIRS) {                                           // rows start 8-byte aligned (fa even), outputs 4-byte (ldo even)
+    const int w2 = fa >> 1, total = (int)n * w2;
+    const float2* __restrict__ s2 = reinterpret_cast<const float2*>(xs);
+    const int dq = nth / w2, dr = nth - dq * w2;         // (row, column pair) advance by nth without a division per item
+    int row = tid / w2, c2 = tid - row * w2;
+#pragma unroll 4
+    for (int i = tid; i < total; i += nth, row += dq, c2 += dr) {
+      if (c2 >= w2) { c2 -= w2; ++row; }
+      const float2 v = __ldg(s2 + i);
+      ovf |= fabsf(v.x) > 60000.f || fabsf(v.y) > 60000.f;
+      const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y);
+      const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+      const int64_t o = (int64_t)row * ldo + 2 * c2;
+      *reinterpret_cast<__half2*>(hi + o) = __halves2half2(h0, h1);
+      *reinterpret_cast<__half2*>(lo + o) = __halves2half2(l0, l1);
+    }
+  } else {
+    const int total = (int)n * fa;
+    const int dq = nth / fa, dr = nth - dq * fa;
+    int row = tid / fa, c = tid - row * fa;
+#pragma unroll 4
+    for (int i = tid; i < total; i += nth, row += dq, c += dr) {
+      if (c >= fa) { c -= fa; ++row; }
+      const float v = __ldg(xs + i);
+      ovf |= fabsf(v) > 60000.f;
+      const __half h = __float2half_rn(v);
+      hi[(int64_t)row * ldo + c] = h;
+      lo[(int64_t)row * ldo + c] = __float2half_rn(v - __half2float(h));
+    }
+  }
+  if (ovf) atomicOr(range_flag, flag_bit);
+  if (fb > 0) block_copy(ea_all + e_in * fb, ea + e_o * fb, e * fb, part, SG_PARTS);         // bond rows
+  if (part == 0) {
+    for (int64_t j = threadIdx.x; j < e; j += blockDim.x) {      // local atom ids -> batch-global ids (int64 like PyG)
+      ei[e_o + j] = (int64_t)__ldg(ei_all + e_in + j) + a_out;
+      ei[e_out + e_o + j] = (int64_t)__ldg(ei_all + e_all + e_in + j) + a_out;
+    }
+  }
+}
 }  // namespace
+
+// internal (api.cu: cgr_store_infer): assemble the batch `sel` with the atom features as the FP16 (hi, lo) operand pair
+int store_gather_split(const float* x_all, const float* ea_all, const int32_t* ei_all, const int64_t* node_ptr,
+                       const int64_t* edge_ptr, int64_t e_all, const int64_t* sel, const int64_t* out_node_ptr,
+                       const int64_t* out_edge_ptr, int64_t n_sel, int32_t fa, int32_t fb, int64_t e_out, void* x_hi,
+                       void* x_lo, int64_t ldo, float* edge_attr, int64_t* edge_index, int* range_flag, int flag_bit,
+                       cudaStream_t st) {
+  CGR_CHECK_ARG(x_all && ei_all && node_ptr && edge_ptr && sel && out_node_ptr && out_edge_ptr && x_hi && x_lo &&
+                    edge_index && range_flag && (fb == 0 || (ea_all && edge_attr)),
+                "store_gather_split: null pointer");
+  CGR_CHECK_ARG(n_sel >= 0 && fa > 0 && fb >= 0 && e_all >= 0 && e_out >= 0 && ldo >= fa, "store_gather_split: bad size");
+  if (n_sel == 0) return CGR_OK;
+  cgr_note_launch("store_gather_split", st, 1);
+  const dim3 grid(SG_PARTS, (unsigned)n_sel);
+  if ((fa & 1) == 0 && (ldo & 1) == 0 && ((uintptr_t)x_all & 7) == 0 && ((uintptr_t)x_hi & 3) == 0 && ((uintptr_t)x_lo & 3) == 0)
+    store_gather_split_kernel<true><<<grid, 256, 0, st>>>(x_all, ea_all, ei_all, node_ptr, edge_ptr, e_all, sel, out_node_ptr,
+                                                           out_edge_ptr, fa, fb, e_out, (__half*)x_hi, (__half*)x_lo, ldo,
+                                                           edge_attr, edge_index, range_flag, flag_bit);
+  else
+    store_gather_split_kernel<false><<<grid, 256, 0, st>>>(x_all, ea_all, ei_all, node_ptr, edge_ptr, e_all, sel, out_node_ptr,
+                                                            out_edge_ptr, fa, fb, e_out, (__half*)x_hi, (__half*)x_lo, ldo,
+                                                            edge_attr, edge_index, range_flag, flag_bit);
+  CGR_LAUNCH_CHECK();
+  return CGR_OK;
+}
 
 extern "C" int cgr_store_gather(const float* x_all, const float* ea_all, const int32_t* ei_all, const int64_t* node_ptr,
                                 const int64_t* edge_ptr, const float* y_all, int64_t e_all, const int64_t* sel,

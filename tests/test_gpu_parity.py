@@ -788,6 +788,21 @@ def test_reaction_store_batches_match_host_collate(tmp_path):
     perm = rng.permutation(40)
     assert scale_normalised_error(store.predict(model, batch_size=9, order=perm), ref_all[torch.from_numpy(perm).cuda()]) < 1e-5
     assert torch.equal(store.predict(model, batch_size=7, slots=3), store.predict(model, batch_size=7, slots=3))
+    # the screening loop's gather writes the FP16 (hi, lo) operands of the atom projection itself (store_gather_split):
+    # odd feature widths take its scalar branch, and a stored feature beyond the fp16 range is flagged there
+    odd = [Graph(x=g.x[:, :77].copy(), edge_index=g.edge_index, edge_attr=g.edge_attr, y=g.y) for g in full]
+    odd_store = ReactionStore.from_graphs(odd, device="cuda")
+    odd_model = build_model(dict(meta, fa=77), engine="auto").eval()
+    with torch.no_grad():
+        odd_ref = torch.cat([odd_model(bt) for bt in odd_store.loader(7)])
+        assert scale_normalised_error(odd_store.predict(odd_model, batch_size=16), odd_ref) < 1e-5
+    saved = float(store.x_all[3, 1])
+    store.x_all[3, 1] = 1e5
+    with pytest.raises(RuntimeError, match="fp16 range"):
+        store.predict(model, batch_size=8)
+    store.x_all[3, 1] = saved
+    with torch.no_grad():
+        assert scale_normalised_error(store.predict(model, batch_size=8), ref_all) < 1e-5
     seen = torch.cat([bt.y for bt in store.loader(16, shuffle=True, seed=1)]).cpu().numpy()
     assert seen.shape[0] == 40 and np.array_equal(np.sort(seen), np.sort(labels))
     assert sum(1 for _ in store.loader(16, drop_last=True)) == 2
