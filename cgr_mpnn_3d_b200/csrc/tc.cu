@@ -245,45 +245,67 @@ __global__ void __launch_bounds__(256) prep_split_kernel(const PrepArgs a) {
   }
 }
 
-// greedy packing of consecutive whole reactions into 128-row tiles (bonds and atoms both <= 128)
-__global__ void tile_plan_kernel(const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ atom_ptr, int64_t B,
-                                 int32_t* __restrict__ tile_info, int32_t* __restrict__ status) {
-  extern __shared__ int32_t sh[];                  // chunks of (atom offset, bond offset)
-  constexpr int CH = 2048;
-  int32_t* a_s = sh;
-  int32_t* e_s = sh + CH + 1;
-  int t = -1, used_e = TM + 1, used_a = TM + 1, ok = 1;
-  int cur[6] = {0, 0, 0, 0, 0, 0};
-  for (int64_t g0 = 0; g0 < B; g0 += CH) {
-    const int n = (int)((B - g0) < CH ? (B - g0) : CH);
-    __syncthreads();
-    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+// greedy packing of consecutive whole reactions into 128-row tiles (bonds and atoms both <= 128).
+// The greedy rule is a chain: the tile that starts at reaction s ends at next(s) = the largest j with
+// bonds(s..j) <= 128 and atoms(s..j) <= 128, and the next tile starts there.  next() of every reaction is independent
+// (a bisection over at most 64 followers: a reaction has >= 2 directed bonds), so one block computes it for a chunk of
+// reactions in parallel from the offsets staged in shared memory (with a 64-reaction halo), ONE thread only follows the
+// chain through shared memory (one dependent load per TILE instead of ~160 cycles per REACTION: 668 -> ~45 us at 8192
+// reactions) and all threads write the chunk's tile records.  Same records as the host twin below (tc_plan_host).
+constexpr int PLAN_CH = 2048, PLAN_HALO = TM / 2, PLAN_THREADS = 512;
+__global__ void __launch_bounds__(PLAN_THREADS) tile_plan_kernel(const int32_t* __restrict__ in_ptr,
+                                                                 const int32_t* __restrict__ atom_ptr, int64_t B,
+                                                                 int32_t* __restrict__ tile_info,
+                                                                 int32_t* __restrict__ status) {
+  __shared__ int32_t a_s[PLAN_CH + PLAN_HALO + 1], e_s[PLAN_CH + PLAN_HALO + 1];   // (atom, bond) offsets of the chunk
+  __shared__ uint16_t nxt_s[PLAN_CH];         // local index of the reaction behind the tile that starts here
+  __shared__ uint16_t start_s[PLAN_CH];       // tile starts of the chunk, in chain order
+  __shared__ int64_t s_carry;                 // global index of the next tile start
+  __shared__ int n_start, t_base, ok_s;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) { s_carry = 0; t_base = 0; ok_s = 1; n_start = 0; }
+  __syncthreads();
+  for (int64_t g0 = 0; g0 < B; g0 += PLAN_CH) {
+    const int n = (int)((B - g0) < PLAN_CH ? (B - g0) : PLAN_CH);
+    const int m = (int)((B - g0) < n + PLAN_HALO ? (B - g0) : n + PLAN_HALO);
+    for (int i = tid; i <= m; i += nt) {
       const int32_t a = __ldg(atom_ptr + g0 + i);
       a_s[i] = a;
       e_s[i] = __ldg(in_ptr + a);                  // bonds of a reaction are the in-bonds of its atoms
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < n; ++i) {
-        const int ne = e_s[i + 1] - e_s[i], na = a_s[i + 1] - a_s[i];
-        if (ne > TM || na > TM || ne <= 0 || na <= 0 || (ne & 1)) { ok = 0; continue; }
-        if (used_e + ne > TM || used_a + na > TM) {
-          if (t >= 0)
-            for (int k = 0; k < 6; ++k) tile_info[t * 8 + k] = cur[k];
-          ++t;
-          cur[0] = e_s[i]; cur[1] = 0; cur[2] = a_s[i]; cur[3] = 0; cur[4] = (int)(g0 + i); cur[5] = 0;
-          used_e = 0; used_a = 0;
-        }
-        used_e += ne; used_a += na;
-        cur[1] = used_e; cur[3] = used_a; cur[5] += 1;
+    for (int i = tid; i < n; i += nt) {
+      const int e0 = e_s[i], a0 = a_s[i];
+      const int ne = e_s[i + 1] - e0, na = a_s[i + 1] - a0;
+      if (ne > TM || na > TM || ne <= 0 || na <= 0 || (ne & 1)) ok_s = 0;      // not tileable: the plan is void
+      int lo = i + 1, hi = i + PLAN_HALO < m ? i + PLAN_HALO : m;
+      while (lo < hi) {                            // largest j in [i + 1, hi] whose span still fits a tile
+        const int mid = (lo + hi + 1) >> 1;
+        if (e_s[mid] - e0 <= TM && a_s[mid] - a0 <= TM) lo = mid; else hi = mid - 1;
       }
+      nxt_s[i] = (uint16_t)lo;
     }
+    __syncthreads();
+    if (tid == 0) {
+      int s = (int)(s_carry - g0), c = 0;
+      while (s < n) { start_s[c++] = (uint16_t)s; s = nxt_s[s]; }
+      n_start = c;
+      s_carry = g0 + s;
+    }
+    __syncthreads();
+    for (int c = tid; c < n_start; c += nt) {
+      const int s = start_s[c], j = nxt_s[s];
+      int32_t* ti = tile_info + (int64_t)(t_base + c) * 8;
+      ti[0] = e_s[s]; ti[1] = e_s[j] - e_s[s]; ti[2] = a_s[s]; ti[3] = a_s[j] - a_s[s];
+      ti[4] = (int32_t)(g0 + s); ti[5] = j - s;
+    }
+    __syncthreads();
+    if (tid == 0) t_base += n_start;
+    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    if (t >= 0)
-      for (int k = 0; k < 6; ++k) tile_info[t * 8 + k] = cur[k];
-    status[0] = t + 1;
-    status[1] = ok;
+  if (tid == 0) {
+    status[0] = t_base;
+    status[1] = ok_s;
   }
 }
 
@@ -740,7 +762,7 @@ int tc_plan_build(const int32_t* in_ptr, const int32_t* atom_ptr, const int32_t*
   CGR_CHECK_ARG(in_ptr && atom_ptr && tile_info && status && n_rxn > 0, "tc_plan_build: bad argument");
   (void)src; (void)dst;            // endpoints are validated by tc_plan_check once the tile count is known
   cgr_note_launch("tc_plan", st, 1);
-  tile_plan_kernel<<<1, 256, (2 * 2048 + 2) * sizeof(int32_t), st>>>(in_ptr, atom_ptr, n_rxn, tile_info, status);
+  tile_plan_kernel<<<1, PLAN_THREADS, 0, st>>>(in_ptr, atom_ptr, n_rxn, tile_info, status);
   CGR_LAUNCH_CHECK();
   return CGR_OK;
 }

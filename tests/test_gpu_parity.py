@@ -1153,6 +1153,35 @@ def test_fp16_range_overflow_is_never_silent():
         assert scale_normalised_error(model(big), build_oracle(meta).eval()(big)) < EA_TOL
 
 
+def test_device_tile_plan_equals_host_plan_across_chunks():
+    """``cgr_tc_plan_build`` (parallel next-tile bisection + chain walk, 2048-reaction chunks with a 64-reaction halo) writes
+    the records of the sequential greedy rule (``cgr_tc_plan_host``, itself checked against ``collate_oracle.tile_plan``)."""
+    import ctypes as C
+    from cgr_mpnn_3d_b200 import _lib
+    from cgr_mpnn_3d_b200.collate import plan_for
+    lib = _lib.load()
+    for nb, seed in ((1, 1), (70, 2), (2048, 3), (4500, 4)):
+        data = make_batch(nb, seed=seed, kind="t1x", fa=78)
+        ptr = data.ptr.numpy().astype(np.int64)
+        rxn_of_bond = np.searchsorted(ptr, data.edge_index[0].numpy(), side="right") - 1
+        eptr = np.concatenate([[0], np.cumsum(np.bincount(rxn_of_bond, minlength=nb))]).astype(np.int64)
+        tiles = np.zeros((nb, 8), dtype=np.int32)
+        n_tiles = C.c_int64(0)
+        _lib.check(lib.cgr_tc_plan_host(ptr.ctypes.data, eptr.ctypes.data, nb, tiles.ctypes.data, C.byref(n_tiles)), "plan_host")
+        ref = collate_oracle.tile_plan(ptr, eptr)["tile_first"]
+        assert n_tiles.value == ref.size - 1 and np.array_equal(tiles[: n_tiles.value, 4], ref[:-1])
+        plan = plan_for(data.to("cuda"))
+        assert plan.ensure_tiles() and plan.n_tiles == n_tiles.value, nb
+        assert np.array_equal(plan.tile_info.cpu().numpy()[: plan.n_tiles, :6], tiles[: plan.n_tiles, :6]), nb
+    # tiny reactions: 64 of them fill a tile (the halo's bound)
+    from cgr_mpnn_3d_b200.data import Graph, collate_host
+    g = Graph(x=np.zeros((2, 78), np.float32), edge_index=np.array([[0, 1], [1, 0]], np.int64),
+              edge_attr=np.zeros((2, 14), np.float32), y=np.zeros(1, np.float32))
+    plan = plan_for(collate_host([g] * 200).to("cuda"))
+    assert plan.ensure_tiles() and plan.n_tiles == 4
+    assert plan.tile_info.cpu().numpy()[:4, 5].tolist() == [64, 64, 64, 8]
+
+
 def test_model_on_non_current_device_builds_its_plan_there():
     """A batch on cuda:1 in a process whose current device is cuda:0 (collate.build_plan launches on the batch's device)."""
     if torch.cuda.device_count() < 2:
