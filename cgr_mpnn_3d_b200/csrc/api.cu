@@ -1046,8 +1046,57 @@ int64_t store_effective_batch(int64_t batch_size) {
   if (off || batch_size >= 1024) return batch_size;
   return (1024 / batch_size) * batch_size;
 }
-// host staging of one slot: [sel | out_node_ptr | out_edge_ptr] (int64) then the int32 meta block of the host entry
-size_t store_sel_bytes(int64_t b_max) { return cgr_align_up((size_t)(3 * b_max + 2) * 8, 1024); }
+// host staging of one slot: [sel | out_node_ptr | out_edge_ptr | perm] (int64) then the int32 meta block of the host entry
+size_t store_sel_bytes(int64_t b_max) { return cgr_align_up((size_t)(4 * b_max + 2) * 8, 1024); }
+
+// The screening loop OWNS the order of the reactions inside a batch (the caller only sees the result vector), and the
+// tile plan packs CONSECUTIVE whole reactions into 128-row tiles: in the caller's order a T1x-shaped batch fills its
+// tiles to ~83 % (half a reaction is lost per tile on average).  Best-fit decreasing on the directed-bond counts --
+// bucketed, the counts are even integers <= 128 -- under the second constraint (atoms <= 128) orders the batch so that
+// the greedy plan closes every tile nearly full (~96 %): ~13 % fewer tiles for every kernel of the forward.  A
+// reaction's energy does not depend on its position (tiles hold whole reactions, every reduction is per reaction), so
+// the result vector is the same bit for bit; the energies are scattered back to the caller's order by one small kernel.
+// perm[i] = position in the caller's batch of the reaction assembled at position i.  Returns false (identity order)
+// when a reaction is not tileable.
+bool store_pack_order(const cgr_store_t* s, const int64_t* ord, int64_t B, std::vector<int32_t>& perm,
+                      std::vector<int32_t>& nxt) {
+  constexpr int TMAX = 128, NB = TMAX / 2;
+  int32_t head[NB + 1];
+  for (int c = 0; c <= NB; ++c) head[c] = -1;
+  perm.resize((size_t)B);
+  nxt.resize((size_t)B);
+  for (int64_t i = B - 1; i >= 0; --i) {                 // lists end up in ascending batch position
+    const int64_t r = ord[i];
+    const int64_t ne = s->edge_ptr_host[r + 1] - s->edge_ptr_host[r], na = s->node_ptr_host[r + 1] - s->node_ptr_host[r];
+    if (ne <= 0 || ne > TMAX || (ne & 1) || na <= 0 || na > TMAX) return false;
+    nxt[(size_t)i] = head[ne >> 1];
+    head[ne >> 1] = (int32_t)i;
+  }
+  auto atoms = [&](int32_t i) { const int64_t r = ord[i]; return (int)(s->node_ptr_host[r + 1] - s->node_ptr_host[r]); };
+  int64_t placed = 0;
+  int top = NB;
+  while (placed < B) {
+    while (top > 0 && head[top] < 0) --top;              // largest reaction left opens the tile
+    int cap_e = TMAX, cap_a = TMAX;
+    int c = top;
+    while (c > 0) {
+      const int32_t i = head[c];
+      if (i < 0 || 2 * c > cap_e || atoms(i) > cap_a) { --c; continue; }
+      head[c] = nxt[(size_t)i];
+      perm[(size_t)placed++] = i;
+      cap_e -= 2 * c;
+      cap_a -= atoms(i);
+      if (c > cap_e / 2) c = cap_e / 2;
+    }
+  }
+  return true;
+}
+
+__global__ void store_scatter_out_kernel(const float* __restrict__ tmp, const int64_t* __restrict__ perm, float* __restrict__ out,
+                                         int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[perm[i]] = tmp[i];
+}
 }  // namespace
 
 extern "C" int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order,
@@ -1088,6 +1137,8 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
     if (cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming) != cudaSuccess) { cleanup(); cgr_set_error("cudaEventCreate failed"); return CGR_ERR_ARG; }
   cgr_params_t pp = *p;
   pp.tc_throughput = 1;                      // several batches in flight
+  static const bool pack = getenv("CGR_STORE_NO_PACK") == nullptr;      // experiments: keep the caller's order
+  std::vector<int32_t> perm, perm_next;
   const HostInferLayout& L = Lmax;           // one layout for every batch: fixed offsets, sizes vary
   // status words of a slot: [0] validity flags and [1] fp16-range flag are sticky (atomicOr), the readout counters behind
   // them reset themselves -- cleared once, read back once
@@ -1109,9 +1160,13 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
     int64_t* h_sel = (int64_t*)hws;
     int64_t* h_optr = h_sel + B;
     int64_t* h_oeptr = h_optr + (B + 1);
+    int64_t* h_perm = h_oeptr + (B + 1);
     h_optr[0] = 0; h_oeptr[0] = 0;
+    const bool packed = pack && store_pack_order(store, order + lo, B, perm, perm_next);
     for (int64_t i = 0; i < B; ++i) {
-      const int64_t r = order[lo + i];
+      const int64_t pi = packed ? perm[(size_t)i] : i;
+      const int64_t r = order[lo + pi];
+      h_perm[i] = pi;
       h_sel[i] = r;
       h_optr[i + 1] = h_optr[i] + (store->node_ptr_host[r + 1] - store->node_ptr_host[r]);
       h_oeptr[i + 1] = h_oeptr[i] + (store->edge_ptr_host[r + 1] - store->edge_ptr_host[r]);
@@ -1137,7 +1192,7 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
     auto CK = [&](cudaError_t e, const char* what) {
       if (e != cudaSuccess && rc == CGR_OK) { cgr_set_error("%s failed: %s", what, cudaGetErrorString(e)); rc = (int)e; }
     };
-    CK(cudaMemcpyAsync(d_sel, h_sel, (size_t)(3 * B + 2) * 8, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(sel)");
+    CK(cudaMemcpyAsync(d_sel, h_sel, (size_t)(4 * B + 2) * 8, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(sel)");
     CK(cudaMemcpyAsync(d_meta, h_meta, ((size_t)L.t_max * 8 + 2 * (size_t)(B + 1)) * 4, cudaMemcpyHostToDevice, st),
        "cudaMemcpyAsync(meta)");
     CK(cudaEventRecord(ev[slot], st), "cudaEventRecord");
@@ -1162,7 +1217,15 @@ extern "C" int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, 
     rc = csr_by_reaction_shifted(d_ei, g.atom_ptr + (B + 1), g.atom_ptr, nullptr, B, E, N, (int32_t*)g.src, (int32_t*)g.dst,
                                  (int32_t*)g.in_ptr, (int32_t*)g.in_idx, d_status, st);
     if (rc) break;
-    rc = tc_gnn_forward(&pp, &g, out + lo, nullptr, 0, 0, dws + L.o_fwd, L.fwd_bytes, st);
+    // packed order: energies land in the slot's own vector and are scattered to the caller's positions
+    float* d_tmp = (float*)(dws + L.o_out);
+    rc = tc_gnn_forward(&pp, &g, packed ? d_tmp : out + lo, nullptr, 0, 0, dws + L.o_fwd, L.fwd_bytes, st);
+    if (rc) break;
+    if (packed) {
+      cgr_note_launch("store_scatter_out", st, 1);
+      store_scatter_out_kernel<<<(unsigned)cgr_ceil_div(B, 256), 256, 0, st>>>(d_tmp, d_sel + 3 * B + 2, out + lo, B);
+      CK(cudaGetLastError(), "store_scatter_out_kernel");
+    }
   }
   // validity / range flags of every slot
   for (int s = 0; s < n_slots && rc == CGR_OK; ++s) {
