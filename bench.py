@@ -794,8 +794,9 @@ def main():
                                       "predict_value": store_leg["predict_rate"] * world,
                                       "predict_api": "ReactionStore.predict(model, batch_size): the per-batch loop in C "
                                                      "(cgr_store_infer), 8 streams, results stay on the device; consecutive "
-                                                     "batches are assembled as super-batches of <= 1024 reactions (a reaction's "
-                                                     "energy does not depend on its batch: same result vector)",
+                                                     "batches are assembled as super-batches of <= 1024 reactions, in best-fit order "
+                                                     "for the 128-row tiles (a reaction's energy does not depend on its batch "
+                                                     "or position: same result vector)",
                                       "what": "shuffled epochs over a ReactionStore held in HBM for >= %.1f s: per step one "
                                               "small index upload, the gather kernel, one-launch CSR and the forward (eager "
                                               "launches); no host-to-device copy of features" % args.leg_seconds}
