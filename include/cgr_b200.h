@@ -367,7 +367,12 @@ int cgr_store_gather(const float* x_all, const float* ea_all, const int32_t* ei_
  * `order` order).  Batches are pipelined over `n_slots` streams (`streams`: HOST array of cudaStream_t), each with its
  * own slice of `dev_ws` (n_slots * dev_bytes_per_slot) and of the pinned `host_ws` (n_slots * host_bytes_per_slot), both
  * sized by cgr_store_infer_workspace for the largest batch.  Returns after every stream is idle; -3 when a reaction
- * does not fit a 128-row tile.  p->tc_weights must be prepared. */
+ * does not fit a 128-row tile.  p->tc_weights must be prepared.
+ * Inside the call the loop is free in everything the caller cannot observe: consecutive small batches are assembled as
+ * super-batches of <= 1024 reactions, the reactions of a batch are assembled in best-fit order for the 128-row tiles
+ * (energies scattered back to `order` positions), and the atom features go from the store rows straight to the FP16
+ * (hi, lo) operands of the atom projection (no fp32 copy of x).  A reaction's energy depends on neither its batch nor its
+ * position, so `out` equals per-batch forwards of the caller-ordered batches bit for bit. */
 typedef struct {
   const float* x_all;            /* device */
   const float* ea_all;
