@@ -372,7 +372,8 @@ int cgr_store_gather(const float* x_all, const float* ea_all, const int32_t* ei_
  * super-batches of <= 1024 reactions, the reactions of a batch are assembled in best-fit order for the 128-row tiles
  * (energies scattered back to `order` positions), and the atom features go from the store rows straight to the FP16
  * (hi, lo) operands of the atom projection (no fp32 copy of x).  A reaction's energy depends on neither its batch nor its
- * position, so `out` equals per-batch forwards of the caller-ordered batches bit for bit. */
+ * position, so `out` equals the forward of the caller-ordered batches in the same kernel configuration bit for bit
+ * (and any other configuration within the parity tolerance). */
 typedef struct {
   const float* x_all;            /* device */
   const float* ea_all;
