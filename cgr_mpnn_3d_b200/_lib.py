@@ -110,6 +110,7 @@ PROTOTYPES = {
     "cgr_forward_group_workspace": (_SZ, [C.POINTER(CgrParams), C.POINTER(CgrGraph), C.c_int32]),
     "cgr_gnn_forward_group": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrGraph), C.c_int32, _V, _V, _SZ, _V]),
     "cgr_tc_plan_host": (C.c_int, [_V, _V, _I64, _V, C.POINTER(C.c_int64)]),
+    "cgr_store_pack_order": (C.c_int, [_V, _V, _I64, _V, _I64, _V]),
     "cgr_store_infer_workspace": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrStore), _V, _I64, _I64, C.POINTER(_SZ),
                                             C.POINTER(_SZ)]),
     "cgr_store_infer": (C.c_int, [C.POINTER(CgrParams), C.POINTER(CgrStore), _V, _I64, _I64, _V, _V, _SZ, _V, _SZ,

@@ -1099,6 +1099,27 @@ __global__ void store_scatter_out_kernel(const float* __restrict__ tmp, const in
 }
 }  // namespace
 
+// The batch order of the screening loop as a host function of its own (pure host code): the loop's packing is testable
+// without a device, and a caller that assembles batches itself (ReactionStore.batch) can ask for the same order.
+extern "C" int cgr_store_pack_order(const int64_t* node_ptr_host, const int64_t* edge_ptr_host, int64_t n_rxn_store,
+                                    const int64_t* ids, int64_t n, int32_t* perm) {
+  CGR_CHECK_ARG(node_ptr_host && edge_ptr_host && ids && perm && n > 0 && n_rxn_store > 0, "cgr_store_pack_order: bad argument");
+  for (int64_t i = 0; i < n; ++i) {
+    CGR_CHECK_ARG(ids[i] >= 0 && ids[i] < n_rxn_store, "cgr_store_pack_order: reaction id %lld out of range", (long long)ids[i]);
+    perm[i] = (int32_t)i;
+  }
+  cgr_store_t s;
+  memset(&s, 0, sizeof(s));
+  s.node_ptr_host = node_ptr_host; s.edge_ptr_host = edge_ptr_host; s.n_rxn = n_rxn_store;
+  std::vector<int32_t> p, nxt;
+  if (!store_pack_order(&s, ids, n, p, nxt)) {
+    cgr_set_error("cgr_store_pack_order: a reaction does not fit a 128-row tile (identity order returned)");
+    return CGR_ERR_UNSUPPORTED;
+  }
+  memcpy(perm, p.data(), (size_t)n * sizeof(int32_t));
+  return CGR_OK;
+}
+
 extern "C" int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order,
                                          int64_t n_total, int64_t batch_size, size_t* dev_bytes_per_slot,
                                          size_t* host_bytes_per_slot) {

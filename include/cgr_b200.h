@@ -385,6 +385,14 @@ typedef struct {
   int64_t n_rxn, e_all;
   int32_t fa, fb;
 } cgr_store_t;
+/* The order in which cgr_store_infer assembles the reactions `ids` [n] (HOST) of one batch: bucketed best-fit decreasing
+ * on the directed-bond counts under the atoms <= 128 constraint, so that the greedy tile plan over consecutive reactions
+ * (cgr_tc_plan_host) closes every 128-row tile nearly full (T1x-shaped batches: ~97 % instead of ~87 %).  perm [n]
+ * (HOST, out): perm[i] = position in `ids` of the reaction assembled at position i.  Pure host code.  Returns -3 (and the
+ * identity order) when a reaction does not fit a tile.  No reference counterpart: PyG collates in loader order
+ * (training/trainer.py:105-118), and the energies do not depend on it (GNN.py:110 pools per reaction). */
+int cgr_store_pack_order(const int64_t* node_ptr_host, const int64_t* edge_ptr_host, int64_t n_rxn_store,
+                         const int64_t* ids, int64_t n, int32_t* perm);
 int cgr_store_infer_workspace(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order, int64_t n_total,
                               int64_t batch_size, size_t* dev_bytes_per_slot, size_t* host_bytes_per_slot);
 int cgr_store_infer(const cgr_params_t* p, const cgr_store_t* store, const int64_t* order, int64_t n_total,

@@ -186,6 +186,57 @@ def test_host_tile_plan_matches_oracle():
     assert b"not tileable" in lib.cgr_last_error_string()
 
 
+def test_store_pack_order_fills_tiles():
+    """cgr_store_pack_order (pure host code): a permutation of the batch, under which the greedy plan needs fewer tiles
+    than in the caller's order and comes close to the lower bound; both constraints (bonds, atoms <= 128) respected."""
+    import ctypes as C
+    import numpy as np
+    from cgr_mpnn_3d_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+
+    def n_tiles_of(na, ne):
+        ptr = np.concatenate([[0], np.cumsum(na)]).astype(np.int64)
+        eptr = np.concatenate([[0], np.cumsum(ne)]).astype(np.int64)
+        tiles = np.zeros((na.size, 8), dtype=np.int32)
+        t = C.c_int64(0)
+        assert lib.cgr_tc_plan_host(ptr.ctypes.data, eptr.ctypes.data, na.size, tiles.ctypes.data, C.byref(t)) == 0
+        assert tiles[: t.value, 1].max() <= 128 and tiles[: t.value, 3].max() <= 128
+        return int(t.value)
+
+    for kind, n_store, n in (("t1x", 5000, 2048), ("t1x", 300, 64), ("mixed", 4000, 1000), ("atoms", 500, 400)):
+        if kind == "t1x":                                  # n ~ U{8..23} atoms, about n + 1 undirected bonds
+            na = rng.integers(8, 24, size=n_store)
+            ne = 2 * (na + rng.integers(0, 3, size=n_store))
+        elif kind == "mixed":
+            na = rng.integers(1, 60, size=n_store)
+            ne = 2 * rng.integers(1, 65, size=n_store)
+        else:                                              # the atom constraint binds: many atoms, few bonds
+            na = rng.integers(30, 129, size=n_store)
+            ne = 2 * rng.integers(1, 20, size=n_store)
+        nptr = np.concatenate([[0], np.cumsum(na)]).astype(np.int64)
+        eptr = np.concatenate([[0], np.cumsum(ne)]).astype(np.int64)
+        ids = rng.integers(0, n_store, size=n).astype(np.int64)      # repeats allowed
+        perm = np.full(n, -1, dtype=np.int32)
+        assert lib.cgr_store_pack_order(nptr.ctypes.data, eptr.ctypes.data, n_store, ids.ctypes.data, n, perm.ctypes.data) == 0
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        before = n_tiles_of(na[ids], ne[ids])
+        after = n_tiles_of(na[ids[perm]], ne[ids[perm]])
+        bound = max(int(np.ceil(ne[ids].sum() / 128)), int(np.ceil(na[ids].sum() / 128)))
+        assert bound <= after <= before, (kind, bound, after, before)
+        if kind == "t1x" and n >= 1024:
+            assert after <= 0.92 * before and after <= 1.05 * bound, (bound, after, before)
+    # a reaction beyond a tile: identity order and -3; ids out of range are refused
+    nptr = np.array([0, 10, 150], dtype=np.int64)
+    eptr = np.array([0, 20, 320], dtype=np.int64)
+    ids = np.array([1, 0], dtype=np.int64)
+    perm = np.zeros(2, dtype=np.int32)
+    assert lib.cgr_store_pack_order(nptr.ctypes.data, eptr.ctypes.data, 2, ids.ctypes.data, 2, perm.ctypes.data) == -3
+    assert perm.tolist() == [0, 1]
+    ids[0] = 5
+    assert lib.cgr_store_pack_order(nptr.ctypes.data, eptr.ctypes.data, 2, ids.ctypes.data, 2, perm.ctypes.data) < 0
+
+
 def test_optimizer_entry_points_validate_arguments_without_a_gpu():
     import ctypes as C
     from cgr_mpnn_3d_b200 import _lib
